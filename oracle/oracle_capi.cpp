@@ -1,0 +1,145 @@
+// oracle_capi.cpp -- C entry points of the CPU ORACLE (test infrastructure only; see dirac_oracle.hpp).
+// Loaded with ctypes by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+// The product library (grid_b200/libgridb200.so) never links or dlopens this file.
+#include "dirac_oracle.hpp"
+#include <chrono>
+#include <omp.h>
+
+using namespace oracle;
+
+namespace {
+struct OpBox {
+  int prec; // 0 = fp32, 1 = fp64
+  FermOp<float> f;
+  FermOp<double> d;
+};
+template <class T> FermOp<T> &get(OpBox *b);
+template <> FermOp<float> &get<float>(OpBox *b) { return b->f; }
+template <> FermOp<double> &get<double>(OpBox *b) { return b->d; }
+
+// op codes shared with include/gridb200.h (gb_opcode)
+enum {
+  OP_DHOP = 0, OP_DHOP_OE = 1, OP_DHOP_EO = 2, OP_M = 3, OP_MDAG = 4, OP_MEOOE = 5, OP_MEOOE_DAG = 6, OP_MOOEE = 7,
+  OP_MOOEE_DAG = 8, OP_MOOEE_INV = 9, OP_MOOEE_INV_DAG = 10, OP_MPC = 11, OP_MPC_DAG = 12, OP_HERMOP = 13, OP_DW = 14,
+  OP_MEOOE5D = 15, OP_MEOOEDAG5D = 16
+};
+
+template <class T> int applyT(OpBox *box, int which, const void *vin, void *vout, int dag, int cb_in, int half) {
+  FermOp<T> &op = get<T>(box);
+  const Spinor<T> *in = (const Spinor<T> *)vin;
+  Spinor<T> *out = (Spinor<T> *)vout;
+  const int64_t n4 = half ? op.g.V4cb() : op.g.V4();
+  switch (which) {
+  case OP_DHOP: op.DhopFull(in, out, dag); break;
+  case OP_DHOP_OE: op.DhopOE(in, out, dag); break;
+  case OP_DHOP_EO: op.DhopEO(in, out, dag); break;
+  case OP_M: op.M(in, out); break;
+  case OP_MDAG: op.Mdag(in, out); break;
+  case OP_MEOOE: op.Meooe(in, out, cb_in); break;
+  case OP_MEOOE_DAG: op.MeooeDag(in, out, cb_in); break;
+  case OP_MOOEE: op.Mooee(n4, in, out); break;
+  case OP_MOOEE_DAG: op.MooeeDag(n4, in, out); break;
+  case OP_MOOEE_INV: op.MooeeInv(n4, in, out); break;
+  case OP_MOOEE_INV_DAG: op.MooeeInvDag(n4, in, out); break;
+  case OP_MPC: op.Mpc(in, out, cb_in); break;
+  case OP_MPC_DAG: op.MpcDag(in, out, cb_in); break;
+  case OP_HERMOP: op.HermOp(in, out, cb_in); break;
+  case OP_DW: op.DW(in, out, dag); break;
+  case OP_MEOOE5D: op.Meooe5D(n4, in, out); break;
+  case OP_MEOOEDAG5D: op.MeooeDag5D(n4, in, out); break;
+  default: return -1;
+  }
+  return 0;
+}
+} // namespace
+
+extern "C" {
+
+int orc_num_threads() { return omp_get_max_threads(); }
+void orc_set_num_threads(int n) { omp_set_num_threads(n); }
+
+// kind: 0 = Wilson 4D (Ls must be 1), 1 = Cayley 5D (Shamir b=1,c=0 / Moebius). prec: 0 fp32, 1 fp64.
+void *orc_op_create(int kind, const int *L, int Ls, double mass, double M5, double b, double c, int prec) {
+  OpBox *box = new OpBox();
+  box->prec = prec;
+  Geometry g; for (int i = 0; i < 4; i++) g.L[i] = L[i]; g.Ls = Ls;
+  auto init = [&](auto &op) {
+    op.kind = kind == 0 ? OpKind::Wilson4D : OpKind::Cayley5D;
+    op.g = g; op.mass = mass;
+    if (kind == 1) op.k = cayleyCoeffs(Ls, mass, M5, b, c);
+  };
+  if (prec == 0) init(box->f); else init(box->d);
+  return box;
+}
+void orc_op_destroy(void *h) { delete (OpBox *)h; }
+
+// Umu: [V4][4][3][3] complex in the operator's precision; phases: 4 complex doubles (re,im) or NULL for periodic.
+void orc_op_import_gauge(void *h, const void *Umu, const double *phases) {
+  OpBox *box = (OpBox *)h;
+  cx<double> ph[4];
+  for (int i = 0; i < 4; i++) ph[i] = phases ? cx<double>(phases[2 * i], phases[2 * i + 1]) : cx<double>(1.0, 0.0);
+  if (box->prec == 0) box->f.importGauge((const ColourMatrix<float> *)Umu, ph);
+  else box->d.importGauge((const ColourMatrix<double> *)Umu, ph);
+}
+// copies out the doubled links [V4][8][3][3] (for direct tests of DoubleStore)
+void orc_op_export_doubled(void *h, void *out) {
+  OpBox *box = (OpBox *)h;
+  if (box->prec == 0) std::memcpy(out, box->f.Uds.data(), box->f.Uds.size() * sizeof(ColourMatrix<float>));
+  else std::memcpy(out, box->d.Uds.data(), box->d.Uds.size() * sizeof(ColourMatrix<double>));
+}
+// Cayley coefficient vectors, each of length Ls: order bs,cs,bee,cee,dee,lee,leem,uee,ueem
+void orc_op_coeffs(void *h, double *out) {
+  OpBox *box = (OpBox *)h;
+  const CayleyCoeffs &k = box->prec == 0 ? box->f.k : box->d.k;
+  const std::vector<double> *v[9] = {&k.bs, &k.cs, &k.bee, &k.cee, &k.dee, &k.lee, &k.leem, &k.uee, &k.ueem};
+  for (int i = 0; i < 9; i++) for (int s = 0; s < k.Ls; s++) out[i * k.Ls + s] = (*v[i])[s];
+}
+
+int orc_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half) {
+  OpBox *box = (OpBox *)h;
+  return box->prec == 0 ? applyT<float>(box, which, in, out, dag, cb_in, half) : applyT<double>(box, which, in, out, dag, cb_in, half);
+}
+// independent naive Cshift-style hopping term on the ORIGINAL links (periodic)
+void orc_dhop_naive(const int *L, int Ls, int prec, const void *Umu, const void *in, void *out, int dag) {
+  Geometry g; for (int i = 0; i < 4; i++) g.L[i] = L[i]; g.Ls = Ls;
+  if (prec == 0) DhopNaive(g, (const ColourMatrix<float> *)Umu, (const Spinor<float> *)in, (Spinor<float> *)out, dag);
+  else DhopNaive(g, (const ColourMatrix<double> *)Umu, (const Spinor<double> *)in, (Spinor<double> *)out, dag);
+}
+void orc_pick_checkerboard(const int *L, int Ls, int prec, int cb, void *half, const void *full) {
+  Geometry g; for (int i = 0; i < 4; i++) g.L[i] = L[i]; g.Ls = Ls;
+  if (prec == 0) pickCheckerboard(g, cb, (Spinor<float> *)half, (const Spinor<float> *)full);
+  else pickCheckerboard(g, cb, (Spinor<double> *)half, (const Spinor<double> *)full);
+}
+void orc_set_checkerboard(const int *L, int Ls, int prec, int cb, void *full, const void *half) {
+  Geometry g; for (int i = 0; i < 4; i++) g.L[i] = L[i]; g.Ls = Ls;
+  if (prec == 0) setCheckerboard(g, cb, (Spinor<float> *)full, (const Spinor<float> *)half);
+  else setCheckerboard(g, cb, (Spinor<double> *)full, (const Spinor<double> *)half);
+}
+void orc_inner_product(int64_t nsites, int prec, const void *l, const void *r, double *out2) {
+  cx<double> v = prec == 0 ? innerProduct(nsites, (const Spinor<float> *)l, (const Spinor<float> *)r)
+                           : innerProduct(nsites, (const Spinor<double> *)l, (const Spinor<double> *)r);
+  out2[0] = v.re; out2[1] = v.im;
+}
+// Schur-preconditioned CG on checkerboard cb. out: [iterations, converged], true_resid.
+void orc_cg(void *h, int cb, const void *src, void *sol, double tol, int maxit, int *out_iters, double *out_true_resid) {
+  OpBox *box = (OpBox *)h;
+  CGResult r = box->prec == 0 ? ConjugateGradient(box->f, cb, (const Spinor<float> *)src, (Spinor<float> *)sol, tol, maxit)
+                              : ConjugateGradient(box->d, cb, (const Spinor<double> *)src, (Spinor<double> *)sol, tol, maxit);
+  out_iters[0] = r.iterations; out_iters[1] = r.converged; *out_true_resid = r.true_residual;
+}
+// out_iters: [inner, outer, final, converged]
+void orc_mixed_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d, double tol, int maxinner, int maxouter,
+                  int *out_iters, double *out_true_resid) {
+  OpBox *bd = (OpBox *)h_d, *bf = (OpBox *)h_f;
+  MixedCGResult r = MixedPrecisionCG(bd->d, bf->f, cb, (const Spinor<double> *)src_d, (Spinor<double> *)sol_d, tol, maxinner, maxouter);
+  out_iters[0] = r.inner_iterations; out_iters[1] = r.outer_iterations; out_iters[2] = r.final_iterations; out_iters[3] = r.converged;
+  *out_true_resid = r.true_residual;
+}
+// Timed loop for the CPU baseline: applies `which` ncall times, returns seconds.
+double orc_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < ncall; i++) orc_apply(h, which, in, out, dag, cb_in, half);
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+}

@@ -1,0 +1,165 @@
+"""ctypes binding of the CPU ORACLE (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY.  Importers allowed: tests/, __graft_entry__.smoke(), bench.py's
+cpu_baseline / --impl reference legs.  The product package grid_b200 never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+# op codes, identical to gb_opcode in include/gridb200.h
+(OP_DHOP, OP_DHOP_OE, OP_DHOP_EO, OP_M, OP_MDAG, OP_MEOOE, OP_MEOOE_DAG, OP_MOOEE, OP_MOOEE_DAG, OP_MOOEE_INV,
+ OP_MOOEE_INV_DAG, OP_MPC, OP_MPC_DAG, OP_HERMOP, OP_DW, OP_MEOOE5D, OP_MEOOEDAG5D) = range(17)
+EVEN, ODD = 0, 1
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", _HERE])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_op_create.restype = C.c_void_p
+        L.orc_op_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.orc_op_destroy.argtypes = [C.c_void_p]
+        L.orc_op_import_gauge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_op_export_doubled.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_op_coeffs.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_apply.restype = C.c_int
+        L.orc_dhop_naive.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_pick_checkerboard.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_set_checkerboard.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_inner_product.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_time_apply.restype = C.c_double
+        L.orc_num_threads.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _cdtype(prec):
+    return np.complex64 if prec == 0 else np.complex128
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _L(dims):
+    return (C.c_int * 4)(*dims)
+
+
+class OracleOp:
+    """CPU restatement of WilsonFermion (kind=0) / DomainWallFermion / MobiusFermion (kind=1)."""
+
+    def __init__(self, kind, dims, Ls, mass, M5=1.8, b=1.0, c=0.0, prec=1):
+        self.kind, self.dims, self.Ls, self.prec = kind, tuple(dims), Ls, prec
+        self.V4 = int(np.prod(dims))
+        self.h = lib().orc_op_create(kind, _L(dims), Ls, mass, M5, b, c, prec)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_op_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def import_gauge(self, Umu, phases=None):
+        """Umu: complex array [V4,4,3,3] (lexicographic, x fastest)."""
+        U = np.ascontiguousarray(Umu, dtype=_cdtype(self.prec))
+        assert U.shape == (self.V4, 4, 3, 3)
+        ph = None
+        if phases is not None:
+            ph = np.ascontiguousarray(np.asarray(phases, dtype=np.complex128))
+        lib().orc_op_import_gauge(self.h, _ptr(U), _ptr(ph) if ph is not None else None)
+
+    def doubled(self):
+        out = np.empty((self.V4, 8, 3, 3), dtype=_cdtype(self.prec))
+        lib().orc_op_export_doubled(self.h, _ptr(out))
+        return out
+
+    def coeffs(self):
+        out = np.empty((9, self.Ls), dtype=np.float64)
+        lib().orc_op_coeffs(self.h, _ptr(out))
+        return dict(zip(["bs", "cs", "bee", "cee", "dee", "lee", "leem", "uee", "ueem"], out))
+
+    def apply(self, which, x, dag=0, cb_in=0):
+        """x: complex [nsite5,4,3]; full (V4*Ls sites) or half (V4/2*Ls sites) field."""
+        x = np.ascontiguousarray(x, dtype=_cdtype(self.prec))
+        n = x.shape[0]
+        half = 1 if n == self.V4 * self.Ls // 2 else 0
+        assert n in (self.V4 * self.Ls, self.V4 * self.Ls // 2)
+        out = np.empty_like(x)
+        rc = lib().orc_apply(self.h, which, _ptr(x), _ptr(out), dag, cb_in, half)
+        assert rc == 0
+        return out
+
+    def time_apply(self, which, x, ncall, dag=0, cb_in=0):
+        x = np.ascontiguousarray(x, dtype=_cdtype(self.prec))
+        half = 1 if x.shape[0] == self.V4 * self.Ls // 2 else 0
+        out = np.empty_like(x)
+        return lib().orc_time_apply(self.h, which, _ptr(x), _ptr(out), dag, cb_in, half, ncall)
+
+    def cg(self, cb, src, tol, maxit, guess=None):
+        src = np.ascontiguousarray(src, dtype=_cdtype(self.prec))
+        sol = np.zeros_like(src) if guess is None else np.ascontiguousarray(guess, dtype=_cdtype(self.prec)).copy()
+        it = np.zeros(2, dtype=np.int32)
+        tr = np.zeros(1, dtype=np.float64)
+        lib().orc_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
+        return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
+
+
+def mixed_cg(op_d, op_f, cb, src_d, tol, maxinner, maxouter):
+    src = np.ascontiguousarray(src_d, dtype=np.complex128)
+    sol = np.zeros_like(src)
+    it = np.zeros(4, dtype=np.int32)
+    tr = np.zeros(1, dtype=np.float64)
+    lib().orc_mixed_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxinner, maxouter, _ptr(it), _ptr(tr))
+    return sol, dict(inner=int(it[0]), outer=int(it[1]), final=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))
+
+
+def dhop_naive(dims, Ls, Umu, x, dag=0, prec=1):
+    U = np.ascontiguousarray(Umu, dtype=_cdtype(prec))
+    x = np.ascontiguousarray(x, dtype=_cdtype(prec))
+    out = np.empty_like(x)
+    lib().orc_dhop_naive(_L(dims), Ls, prec, _ptr(U), _ptr(x), _ptr(out), dag)
+    return out
+
+
+def pick_checkerboard(dims, Ls, cb, full):
+    prec = 0 if full.dtype == np.complex64 else 1
+    full = np.ascontiguousarray(full)
+    half = np.empty((full.shape[0] // 2,) + full.shape[1:], dtype=full.dtype)
+    lib().orc_pick_checkerboard(_L(dims), Ls, prec, cb, _ptr(half), _ptr(full))
+    return half
+
+
+def set_checkerboard(dims, Ls, cb, full, half):
+    prec = 0 if full.dtype == np.complex64 else 1
+    assert full.flags.c_contiguous and half.flags.c_contiguous and full.dtype == half.dtype
+    lib().orc_set_checkerboard(_L(dims), Ls, prec, cb, _ptr(full), _ptr(half))
+
+
+def inner_product(l, r):
+    prec = 0 if l.dtype == np.complex64 else 1
+    l = np.ascontiguousarray(l); r = np.ascontiguousarray(r, dtype=l.dtype)
+    out = np.zeros(2)
+    lib().orc_inner_product(l.shape[0], prec, _ptr(l), _ptr(r), _ptr(out))
+    return complex(out[0], out[1])
+
+
+def num_threads():
+    return lib().orc_num_threads()
