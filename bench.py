@@ -1,0 +1,313 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline benchmark (Benchmark_dwf_fp32 shape) on the B200-native path.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--op Dhop|DhopEO] [--local L L L L] [--Ls 16]
+
+A "step" is one full-lattice DomainWallFermionF::Dhop call (ref: benchmarks/Benchmark_dwf_fp32.cc:271-306):
+fp32, 32^4 x Ls=16 per GPU (BASELINE.json configs[1]); random SU(3) links, random unit-norm source, mass 0.1, M5 1.8.
+N > 1 (launched by torchrun, one rank per GPU) keeps the per-GPU volume fixed (weak scaling) and decomposes the
+global lattice over z,t like the reference's --mpi 1.1.2.4: N=2 -> 1.1.1.2, N=4 -> 1.1.2.2, N=8 -> 1.1.2.4.
+
+value      = whole-job GFlop/s (1320 flop per 5D site, ref Benchmark_dwf_fp32.cc:124), fields resident in HBM,
+             CUDA events on the library's compute stream, max over ranks.
+e2e        = same metric through the C ABI with HOST buffers: every step imports the source from pinned host
+             memory (gb_fermion_import), runs Dhop and exports the result (gb_fermion_export).
+roofline   = algorithmic bytes (228 B per 5D site fp32) / measured kernel time vs MEASURED_PEAKS.json.
+cpu_baseline = the CPU oracle (a port of the reference's generic kernel; the reference itself cannot be built in
+             this image) timed on the host cores on a bounded sample.
+--impl reference runs only that CPU leg (rank 0 only) and prints the same JSON line with "impl": "reference".
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_SITE = 1320.0           # ref: benchmarks/Benchmark_dwf_fp32.cc:124
+METRIC = "DWF Dhop fp32 GFlop/s (1320 flop/site), whole job"
+UNIT = "GFlop/s"
+MPI_FOR_N = {1: (1, 1, 1, 1), 2: (1, 1, 1, 2), 4: (1, 1, 2, 2), 8: (1, 1, 2, 4)}
+PUBLISHED_A100_GFLOPS_PER_GPU = 2417.0  # Booster 4-node log, other hardware -- context only
+
+
+def alg_bytes_per_site(Ls, w=4):
+    """one spinor read + one written + the 8 double-stored links amortised over Ls."""
+    return 2 * 24 * w + 8 * 18 * w / Ls
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(op):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "dhop_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(op)
+        except Exception:
+            pass
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the GPU is under load (recipe: B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,utilization.gpu,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smmax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                util = float(f[4])
+                if util < 50:   # keep samples taken under load
+                    continue
+                sm.append(float(f[1])); smmax.append(float(f[2])); power.append(float(f[3]))
+                for n, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except ValueError:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smmax) if smmax else None,
+                "power_w_max": max(power) if power else None, "samples_under_load": len(sm), "reasons": sorted(reasons)}
+
+
+_CPU_SETUP = {}
+
+
+def cpu_leg(Ls, sample_L=16, target_s=12.0, op="Dhop"):
+    """Times the CPU oracle's hopping term (fp32) on a bounded sample: same kernel and per-site work, smaller volume."""
+    import numpy as np
+    from grid_b200 import synthetic as syn
+    from oracle import pyoracle as po
+    key = (Ls, sample_L, op)
+    if key not in _CPU_SETUP:
+        dims = (sample_L,) * 4
+        U = syn.hot_gauge(dims, seed=1, dtype=np.complex64)
+        orc = po.OracleOp(1, dims, Ls, 0.1, 1.8, prec=0)
+        orc.import_gauge(U)
+        x = syn.random_fermion(dims, Ls, seed=2, dtype=np.complex64, normalise=True)
+        which, vol = po.OP_DHOP, sample_L ** 4 * Ls
+        if op == "DhopEO":
+            x, which, vol = po.pick_checkerboard(dims, Ls, 1, x), po.OP_DHOP_EO, vol // 2
+        _CPU_SETUP[key] = (orc, x, which, vol, orc.time_apply(which, x, 1))
+    orc, x, which, vol, t1 = _CPU_SETUP[key]
+    ncall = max(2, int(target_s / max(t1, 1e-3)))
+    t = orc.time_apply(which, x, ncall)
+    return {"value": FLOPS_PER_SITE * vol * ncall / t / 1e9, "unit": UNIT, "cores": po.num_threads(), "kind": "port",
+            "sample": f"{ncall} calls of the oracle {op} fp32 on a {sample_L}^4 x Ls{Ls} sub-volume (same per-site work as the 32^4 workload), {t:.1f} s",
+            "seconds": t, "calls": ncall, "ms_per_call": 1e3 * t / ncall}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps = max(1, args.steps)
+    per_step_target = min(20.0, 150.0 / (steps + args.warmup))
+    legs = [cpu_leg(args.Ls, target_s=per_step_target, op=args.op) for _ in range(args.warmup + steps)][args.warmup:]
+    value = statistics.mean(l["value"] for l in legs)
+    ms = statistics.mean(l["seconds"] for l in legs) * 1e3
+    cb = dict(legs[-1]); cb["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args), "cpu_baseline": cb,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU oracle (port of the reference's generic Dhop kernel, OpenMP) on the host cores; each step is a bounded sample"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    mpi = MPI_FOR_N[args.gpus]
+    g = [l * m for l, m in zip(args.local, mpi)]
+    return {"workload": f"DomainWallFermionF::{args.op} fp32, local {'x'.join(map(str, args.local))} x Ls{args.Ls} per GPU "
+                        f"(BASELINE configs[1] shape), global {'x'.join(map(str, g))}, mpi {'.'.join(map(str, mpi))}",
+            "op": args.op, "local_lattice": list(args.local), "global_lattice": g, "Ls": args.Ls, "mpi": list(mpi),
+            "mass": 0.1, "M5": 1.8, "l2": "inputs (1.6 GB/field) larger than the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)   # ref: ncall=300, Benchmark_dwf_fp32.cc:274
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--op", default="Dhop", choices=["Dhop", "DhopEO"])
+    ap.add_argument("--local", type=int, nargs=4, default=[32, 32, 32, 32])
+    ap.add_argument("--Ls", type=int, default=16)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert args.gpus in MPI_FOR_N, "--gpus must be 1, 2, 4 or 8"
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    assert world == args.gpus, f"WORLD_SIZE={world} but --gpus {args.gpus}: launch with torch.distributed.run"
+
+    import numpy as np
+    import torch
+    import grid_b200 as gb
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = gb.Context(local_rank)
+    if world > 1:
+        uid = [gb.Context.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    else:
+        ctx.comm_init(0, 1, None)
+
+    mpi = MPI_FOR_N[args.gpus]
+    gdims = [l * m for l, m in zip(args.local, mpi)]
+    grid = gb.GridCartesian(ctx, gdims, mpi)
+    Ls = args.Ls
+    U = gb.LatticeGaugeField(grid, gb.F32).random(1)
+    Dw = gb.DomainWallFermion(U, grid, Ls, 0.1, 1.8)
+    if args.no_overlap:
+        Dw.set_overlap(False)
+    src = gb.LatticeFermion(grid, Ls, gb.F32).random(2)
+    n2 = gb.norm2(src)
+    gb.scale(src, 1.0 / np.sqrt(n2), src)     # ref: Benchmark_dwf_fp32.cc:175-176
+    if args.op == "Dhop":
+        fin, fout = src, gb.LatticeFermion(grid, Ls, gb.F32)
+        step = lambda: Dw.Dhop(fin, fout, 0)
+        sites_local = grid.lsites * Ls
+    else:
+        fin, fout = gb.LatticeFermion(grid, Ls, gb.F32, gb.HALF), gb.LatticeFermion(grid, Ls, gb.F32, gb.HALF)
+        gb.pickCheckerboard(gb.Odd, fin, src)
+        step = lambda: Dw.DhopEO(fin, fout, 0)
+        sites_local = grid.lsites * Ls // 2
+    sites_total = sites_local * world
+
+    def barrier():
+        ctx.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ctx.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    l0 = ctx.launch_count()
+    ctx.timer_start()
+    for _ in range(args.steps):
+        step()
+    ms_total = ctx.timer_stop()
+    launches = ctx.launch_count() - l0
+    barrier()
+    ms_total = max_over_ranks(ms_total)
+    ms_step = ms_total / args.steps
+    value = FLOPS_PER_SITE * sites_total / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
+    host_in = torch.empty((fin.local_sites, 4, 3), dtype=torch.complex64).pin_memory().numpy()
+    host_out = torch.empty((fin.local_sites, 4, 3), dtype=torch.complex64).pin_memory().numpy()
+    host_in[...] = fin.export_lex()
+    e2e_in = fin.like()
+    def e2e_step():
+        e2e_in.import_lex(host_in)
+        if args.op == "DhopEO":
+            e2e_in.set_checkerboard(gb.Odd)
+            Dw.DhopEO(e2e_in, fout, 0)
+        else:
+            Dw.Dhop(e2e_in, fout, 0)
+        lib = gb.lib()
+        gb._chk(lib.gb_fermion_export(fout.h, host_out.ctypes.data, gb.F32))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    ctx.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+    barrier()
+    e2e_value = FLOPS_PER_SITE * sites_total / e2e_s / 1e9
+    # keep the device busy a little longer so the clock sampler sees the kernel under load
+    t_end = time.time() + 1.5
+    while time.time() < t_end:
+        for _ in range(50):
+            step()
+        ctx.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bps = alg_bytes_per_site(Ls)
+        achieved = bps * sites_local / (ms_step * 1e-3) / 1e9       # per GPU; one dhop_kernel launch per step
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": workload_config(args),
+                "per_gpu_gflops": value / world, "vs_published_a100_per_gpu": value / world / PUBLISHED_A100_GFLOPS_PER_GPU,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes) * world, "d2h_bytes_per_step": int(host_out.nbytes) * world,
+                        "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "kernel": "gb::dhop_kernel<float,0,*>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": ncu_traffic(args.op), "peak_source": peak_src,
+                             "algorithmic_bytes_per_site": bps, "sites_per_launch": sites_local},
+                "clocks": clocks}
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_leg(Ls, op=args.op)
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

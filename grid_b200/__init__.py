@@ -1,0 +1,468 @@
+"""grid_b200 -- Python host-side mirror of the reference's operator / solver interface over the C ABI.
+
+The product is grid_b200/libgridb200.so (hand-written sm_100a CUDA behind include/gridb200.h).  This module only
+binds it with ctypes and re-exposes the reference's class and method names so that tests and drivers read like
+the reference's own (ref: Grid/qcd/action/fermion/FermionOperator.h:40-192, Grid/algorithms/LinearOperator.h:286-349,
+Grid/algorithms/iterative/ConjugateGradient.h:42-258, ConjugateGradientMixedPrec.h:34-170).
+
+There is no CPU fallback: importing works anywhere (so the symbol table can be checked), but creating a Context
+without a CUDA device raises, and a missing libgridb200.so raises at import of the library handle.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgridb200.so")
+
+F32, F64 = 0, 1
+Even, Odd = 0, 1
+FULL, HALF = 0, 1
+DaggerNo, DaggerYes = 0, 1
+(OP_DHOP, OP_DHOP_OE, OP_DHOP_EO, OP_M, OP_MDAG, OP_MEOOE, OP_MEOOE_DAG, OP_MOOEE, OP_MOOEE_DAG, OP_MOOEE_INV,
+ OP_MOOEE_INV_DAG, OP_MPC, OP_MPC_DAG, OP_HERMOP, OP_DW, OP_MEOOE5D, OP_MEOOEDAG5D) = range(17)
+GB_OK, GB_ERR_INVALID, GB_ERR_CUDA, GB_ERR_NO_DEVICE, GB_ERR_NOT_CONVERGED, GB_ERR_COMM = 0, -1, -2, -3, -4, -5
+UNIQUE_ID_BYTES = 128
+
+# every symbol include/gridb200.h declares: (name, restype, argtypes)
+_vp, _i, _d, _i64, _u64 = C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_uint64
+_pi, _pd, _pvp = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_void_p)
+HERMOP_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p)
+SYMBOLS = [
+    ("gb_context_create", _i, [_i, _pvp]), ("gb_context_destroy", _i, [_vp]), ("gb_last_error", C.c_char_p, []),
+    ("gb_device_count", _i, []), ("gb_synchronize", _i, [_vp]), ("gb_timer_start", _i, [_vp]), ("gb_timer_stop", _i, [_vp, _pd]),
+    ("gb_launch_count", _i64, [_vp]), ("gb_flush_l2", _i, [_vp]),
+    ("gb_comm_unique_id", _i, [_vp]), ("gb_comm_init", _i, [_vp, _i, _i, _vp]), ("gb_comm_rank", _i, [_vp, _pi, _pi]),
+    ("gb_comm_global_sum", _i, [_vp, _pd, _i]), ("gb_comm_barrier", _i, [_vp]),
+    ("gb_grid_create", _i, [_vp, _pi, _pi, _pvp]), ("gb_grid_destroy", _i, [_vp]), ("gb_grid_local_dims", _i, [_vp, _pi]),
+    ("gb_grid_local_origin", _i, [_vp, _pi]),
+    ("gb_fermion_create", _i, [_vp, _i, _i, _i, _pvp]), ("gb_fermion_destroy", _i, [_vp]), ("gb_fermion_checkerboard", _i, [_vp]),
+    ("gb_fermion_set_checkerboard_tag", _i, [_vp, _i]), ("gb_fermion_local_sites", _i64, [_vp]),
+    ("gb_fermion_import", _i, [_vp, _vp, _i]), ("gb_fermion_export", _i, [_vp, _vp, _i]),
+    ("gb_pick_checkerboard", _i, [_i, _vp, _vp]), ("gb_set_checkerboard", _i, [_vp, _vp]), ("gb_precision_change", _i, [_vp, _vp]),
+    ("gb_fermion_random", _i, [_vp, _u64]),
+    ("gb_zero", _i, [_vp]), ("gb_copy", _i, [_vp, _vp]), ("gb_scale", _i, [_vp, _d, _vp]), ("gb_axpy", _i, [_vp, _d, _vp, _vp]),
+    ("gb_axpby", _i, [_vp, _d, _d, _vp, _vp]), ("gb_axpy_norm", _i, [_vp, _d, _vp, _vp, _pd]), ("gb_norm2", _i, [_vp, _pd]),
+    ("gb_inner_product", _i, [_vp, _vp, _pd]),
+    ("gb_gauge_create", _i, [_vp, _i, _pvp]), ("gb_gauge_destroy", _i, [_vp]), ("gb_gauge_import", _i, [_vp, _vp, _i]),
+    ("gb_gauge_export", _i, [_vp, _vp, _i]), ("gb_gauge_random", _i, [_vp, _u64]), ("gb_gauge_unit", _i, [_vp]),
+    ("gb_op_create_wilson", _i, [_vp, _vp, _d, _pd, _pvp]), ("gb_op_create_dwf", _i, [_vp, _vp, _i, _d, _d, _pd, _pvp]),
+    ("gb_op_create_mobius", _i, [_vp, _vp, _i, _d, _d, _d, _d, _pd, _pvp]), ("gb_op_import_gauge", _i, [_vp, _vp]),
+    ("gb_op_destroy", _i, [_vp]), ("gb_op_Ls", _i, [_vp]), ("gb_op_apply", _i, [_vp, _i, _vp, _vp, _i]),
+    ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]),
+    ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
+    ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
+]
+
+_LIB = None
+
+
+class GridB200Error(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libgridb200 error {code}: {msg}")
+        self.code = code
+
+
+def lib():
+    """Load libgridb200.so; fails loudly if the CUDA extension has not been built."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C grid_b200). grid_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        for name, res, args in SYMBOLS:
+            fn = getattr(L, name)  # AttributeError if the header and the library disagree
+            fn.restype, fn.argtypes = res, args
+        _LIB = L
+    return _LIB
+
+
+def _chk(rc):
+    if rc != GB_OK:
+        raise GridB200Error(rc, lib().gb_last_error().decode())
+
+
+def _cdtype(prec):
+    return np.complex64 if prec == F32 else np.complex128
+
+
+def _prec_of(a):
+    if a.dtype in (np.complex64, np.float32):
+        return F32
+    if a.dtype in (np.complex128, np.float64):
+        return F64
+    raise TypeError(f"unsupported dtype {a.dtype}")
+
+
+def _i4(v):
+    return (C.c_int * 4)(*[int(x) for x in v])
+
+
+class Context:
+    """Grid_init analogue: device, streams, communicator (ref: Grid/util/Init.cc:300-560)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _chk(lib().gb_context_create(device, C.byref(self.h)))
+        self.device = device
+
+    def synchronize(self):
+        _chk(lib().gb_synchronize(self.h))
+
+    def timer_start(self):
+        _chk(lib().gb_timer_start(self.h))
+
+    def timer_stop(self):
+        ms = C.c_double()
+        _chk(lib().gb_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return lib().gb_launch_count(self.h)
+
+    def flush_l2(self):
+        _chk(lib().gb_flush_l2(self.h))
+
+    # ---- communicator
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+        _chk(lib().gb_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, rank, nranks, uid):
+        buf = C.create_string_buffer(uid, UNIQUE_ID_BYTES) if uid is not None else None
+        _chk(lib().gb_comm_init(self.h, rank, nranks, buf))
+        self.rank, self.nranks = rank, nranks
+
+    def global_sum(self, vals):
+        arr = (C.c_double * len(vals))(*vals)
+        _chk(lib().gb_comm_global_sum(self.h, arr, len(vals)))
+        return list(arr)
+
+    def barrier(self):
+        _chk(lib().gb_comm_barrier(self.h))
+
+    def close(self):
+        if self.h:
+            lib().gb_context_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class GridCartesian:
+    """4D grid + its red-black and 5D companions (ref: SpaceTimeGrid::makeFourDimGrid etc.)."""
+
+    def __init__(self, ctx, gdims, mpi=(1, 1, 1, 1)):
+        self.ctx, self.gdims, self.mpi = ctx, tuple(gdims), tuple(mpi)
+        self.h = C.c_void_p()
+        _chk(lib().gb_grid_create(ctx.h, _i4(gdims), _i4(mpi), C.byref(self.h)))
+        l, o = _i4([0] * 4), _i4([0] * 4)
+        lib().gb_grid_local_dims(self.h, l)
+        lib().gb_grid_local_origin(self.h, o)
+        self.ldims, self.origin = tuple(l), tuple(o)
+        self.lsites = int(np.prod(self.ldims))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().gb_grid_destroy(self.h)
+        except Exception:
+            pass
+
+
+class LatticeFermion:
+    """LatticeFermion{F,D} on the full (kind=FULL) or red-black (kind=HALF) 4D/5D grid."""
+
+    def __init__(self, grid, Ls=1, prec=F32, kind=FULL):
+        self.grid, self.Ls, self.prec, self.kind = grid, Ls, prec, kind
+        self.h = C.c_void_p()
+        _chk(lib().gb_fermion_create(grid.h, Ls, prec, kind, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().gb_fermion_destroy(self.h)
+        except Exception:
+            pass
+
+    def like(self, kind=None, prec=None):
+        return LatticeFermion(self.grid, self.Ls, self.prec if prec is None else prec, self.kind if kind is None else kind)
+
+    @property
+    def local_sites(self):
+        return lib().gb_fermion_local_sites(self.h)
+
+    def Checkerboard(self):
+        return lib().gb_fermion_checkerboard(self.h)
+
+    def set_checkerboard(self, cb):
+        lib().gb_fermion_set_checkerboard_tag(self.h, cb)
+
+    def import_lex(self, host):
+        """host: complex [nsites,4,3] in local lexicographic (full) or checkerboard-lexicographic (half) order."""
+        host = np.ascontiguousarray(host)
+        assert host.shape == (self.local_sites, 4, 3), (host.shape, self.local_sites)
+        _chk(lib().gb_fermion_import(self.h, host.ctypes.data_as(C.c_void_p), _prec_of(host)))
+        return self
+
+    def export_lex(self, dtype=None):
+        dt = _cdtype(self.prec) if dtype is None else dtype
+        out = np.empty((self.local_sites, 4, 3), dtype=dt)
+        _chk(lib().gb_fermion_export(self.h, out.ctypes.data_as(C.c_void_p), _prec_of(out)))
+        return out
+
+    def random(self, seed):
+        _chk(lib().gb_fermion_random(self.h, seed))
+        return self
+
+    def zero(self):
+        _chk(lib().gb_zero(self.h))
+        return self
+
+
+def pickCheckerboard(cb, half, full):
+    _chk(lib().gb_pick_checkerboard(cb, half.h, full.h))
+
+
+def setCheckerboard(full, half):
+    _chk(lib().gb_set_checkerboard(full.h, half.h))
+
+
+def precisionChange(out, inp):
+    _chk(lib().gb_precision_change(out.h, inp.h))
+
+
+def norm2(x):
+    v = C.c_double()
+    _chk(lib().gb_norm2(x.h, C.byref(v)))
+    return v.value
+
+
+def innerProduct(l, r):
+    v = (C.c_double * 2)()
+    _chk(lib().gb_inner_product(l.h, r.h, v))
+    return complex(v[0], v[1])
+
+
+def axpy(z, a, x, y):
+    _chk(lib().gb_axpy(z.h, a, x.h, y.h))
+
+
+def axpby(z, a, b, x, y):
+    _chk(lib().gb_axpby(z.h, a, b, x.h, y.h))
+
+
+def axpy_norm(z, a, x, y):
+    v = C.c_double()
+    _chk(lib().gb_axpy_norm(z.h, a, x.h, y.h, C.byref(v)))
+    return v.value
+
+
+def scale(z, a, x):
+    _chk(lib().gb_scale(z.h, a, x.h))
+
+
+def copy(z, x):
+    _chk(lib().gb_copy(z.h, x.h))
+
+
+class LatticeGaugeField:
+    def __init__(self, grid, prec=F32):
+        self.grid, self.prec = grid, prec
+        self.h = C.c_void_p()
+        _chk(lib().gb_gauge_create(grid.h, prec, C.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().gb_gauge_destroy(self.h)
+        except Exception:
+            pass
+
+    def import_lex(self, host):
+        host = np.ascontiguousarray(host)
+        assert host.shape == (self.grid.lsites, 4, 3, 3), host.shape
+        _chk(lib().gb_gauge_import(self.h, host.ctypes.data_as(C.c_void_p), _prec_of(host)))
+        return self
+
+    def export_lex(self, dtype=np.complex128):
+        out = np.empty((self.grid.lsites, 4, 3, 3), dtype=dtype)
+        _chk(lib().gb_gauge_export(self.h, out.ctypes.data_as(C.c_void_p), _prec_of(out)))
+        return out
+
+    def random(self, seed):
+        """SU<Nc>::HotConfiguration analogue, generated on the device."""
+        _chk(lib().gb_gauge_random(self.h, seed))
+        return self
+
+    def unit(self):
+        _chk(lib().gb_gauge_unit(self.h))
+        return self
+
+
+class FermionOperator:
+    """Mirror of FermionOperator<Impl> (ref: FermionOperator.h:40-192): same method names, (in, out[, dag])."""
+
+    def __init__(self):
+        self.h = C.c_void_p()
+        self.grid = None
+        self.Ls = 1
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().gb_op_destroy(self.h)
+        except Exception:
+            pass
+
+    def _apply(self, which, i, o, dag=0):
+        _chk(lib().gb_op_apply(self.h, which, i.h, o.h, dag))
+
+    def ImportGauge(self, Umu):
+        _chk(lib().gb_op_import_gauge(self.h, Umu.h))
+
+    def M(self, i, o): self._apply(OP_M, i, o)
+    def Mdag(self, i, o): self._apply(OP_MDAG, i, o)
+    def Meooe(self, i, o): self._apply(OP_MEOOE, i, o)
+    def MeooeDag(self, i, o): self._apply(OP_MEOOE_DAG, i, o)
+    def Mooee(self, i, o): self._apply(OP_MOOEE, i, o)
+    def MooeeDag(self, i, o): self._apply(OP_MOOEE_DAG, i, o)
+    def MooeeInv(self, i, o): self._apply(OP_MOOEE_INV, i, o)
+    def MooeeInvDag(self, i, o): self._apply(OP_MOOEE_INV_DAG, i, o)
+    def Dhop(self, i, o, dag=0): self._apply(OP_DHOP, i, o, dag)
+    def DhopOE(self, i, o, dag=0): self._apply(OP_DHOP_OE, i, o, dag)
+    def DhopEO(self, i, o, dag=0): self._apply(OP_DHOP_EO, i, o, dag)
+    def DW(self, i, o, dag=0): self._apply(OP_DW, i, o, dag)
+    def Meooe5D(self, i, o): self._apply(OP_MEOOE5D, i, o)
+    def MeooeDag5D(self, i, o): self._apply(OP_MEOOEDAG5D, i, o)
+
+    def set_tiling(self, by=0, bz=0, bt=0):
+        lib().gb_op_set_tiling(self.h, by, bz, bt)
+
+    def set_overlap(self, on):
+        lib().gb_op_set_overlap(self.h, 1 if on else 0)
+
+
+def _phases(ph):
+    if ph is None:
+        return None
+    a = np.ascontiguousarray(np.asarray(ph, dtype=np.complex128)).view(np.float64)
+    return (C.c_double * 8)(*a)
+
+
+class WilsonFermion(FermionOperator):
+    """ref: WilsonFermion.h:139-142"""
+
+    def __init__(self, Umu, grid, mass, boundary_phases=None):
+        super().__init__()
+        self.grid = grid
+        _chk(lib().gb_op_create_wilson(grid.h, Umu.h, mass, _phases(boundary_phases), C.byref(self.h)))
+
+
+class DomainWallFermion(FermionOperator):
+    """ref: DomainWallFermion.h:108-134 (Shamir: b=1, c=0)"""
+
+    def __init__(self, Umu, grid, Ls, mass, M5, boundary_phases=None):
+        super().__init__()
+        self.grid, self.Ls = grid, Ls
+        _chk(lib().gb_op_create_dwf(grid.h, Umu.h, Ls, mass, M5, _phases(boundary_phases), C.byref(self.h)))
+
+
+class MobiusFermion(FermionOperator):
+    """ref: MobiusFermion.h:45-71"""
+
+    def __init__(self, Umu, grid, Ls, mass, M5, b, c, boundary_phases=None):
+        super().__init__()
+        self.grid, self.Ls = grid, Ls
+        _chk(lib().gb_op_create_mobius(grid.h, Umu.h, Ls, mass, M5, b, c, _phases(boundary_phases), C.byref(self.h)))
+
+
+class LinearOperatorBase:
+    """ref: Grid/algorithms/LinearOperator.h:44-56"""
+
+    def Op(self, i, o): raise NotImplementedError
+    def AdjOp(self, i, o): raise NotImplementedError
+    def HermOp(self, i, o): raise NotImplementedError
+
+    def HermOpAndNorm(self, i, o):
+        self.HermOp(i, o)
+        return innerProduct(i, o).real, norm2(o)
+
+
+class SchurDiagMooeeOperator(LinearOperatorBase):
+    """ref: LinearOperator.h:325-349.  Mpc = Mooee - Meooe MooeeInv Meooe ; HermOp = MpcDag Mpc."""
+
+    def __init__(self, Mat):
+        self._Mat = Mat
+
+    def Mpc(self, i, o): self._Mat._apply(OP_MPC, i, o)
+    def MpcDag(self, i, o): self._Mat._apply(OP_MPC_DAG, i, o)
+    def MpcDagMpc(self, i, o): self._Mat._apply(OP_HERMOP, i, o)
+    def Op(self, i, o): self.Mpc(i, o)
+    def AdjOp(self, i, o): self.MpcDag(i, o)
+    def HermOp(self, i, o): self.MpcDagMpc(i, o)
+
+
+class ConjugateGradient:
+    """ref: ConjugateGradient.h:42-258.  __call__(Linop, src, psi); psi is the initial guess on entry."""
+
+    def __init__(self, tol, maxit, err_on_no_conv=True):
+        self.Tolerance, self.MaxIterations, self.ErrorOnNoConverge = tol, maxit, err_on_no_conv
+        self.IterationsToComplete, self.TrueResidual = 0, 0.0
+
+    def __call__(self, Linop, src, psi):
+        it, tr = C.c_int(), C.c_double()
+        if isinstance(Linop, SchurDiagMooeeOperator):
+            rc = lib().gb_cg_schur(Linop._Mat.h, src.h, psi.h, self.Tolerance, self.MaxIterations, C.byref(it), C.byref(tr))
+        else:  # any user-written LinearOperatorBase: CG drives its HermOp through the callback path
+            by_handle = {}
+
+            def cb(_user, hin, hout):
+                try:
+                    fin, fout = _Borrowed(hin, src), _Borrowed(hout, src)
+                    Linop.HermOp(fin, fout)
+                    return GB_OK
+                except GridB200Error as e:
+                    return e.code
+
+            fn = HERMOP_FN(cb)
+            rc = lib().gb_cg(src.grid.ctx.h, fn, None, src.h, psi.h, self.Tolerance, self.MaxIterations, C.byref(it), C.byref(tr))
+            del by_handle
+        self.IterationsToComplete, self.TrueResidual = it.value, tr.value
+        if rc == GB_ERR_NOT_CONVERGED:
+            assert not self.ErrorOnNoConverge, "ConjugateGradient did NOT converge"  # ref: ConjugateGradient.h:254
+            return
+        _chk(rc)
+        if self.ErrorOnNoConverge:
+            assert self.TrueResidual / self.Tolerance < 10000.0  # ref: ConjugateGradient.h:225
+
+
+class _Borrowed(LatticeFermion):
+    """Non-owning view of a library-owned field handle (used inside the generic-CG callback)."""
+
+    def __init__(self, handle, like):
+        self.grid, self.Ls, self.prec, self.kind = like.grid, like.Ls, like.prec, like.kind
+        self.h = C.c_void_p(handle)
+
+    def __del__(self):
+        pass
+
+
+class MixedPrecisionConjugateGradient:
+    """ref: ConjugateGradientMixedPrec.h:34-170."""
+
+    def __init__(self, tol, maxinnerit, maxouterit, Linop_f, Linop_d):
+        self.Tolerance, self.MaxInnerIterations, self.MaxOuterIterations = tol, maxinnerit, maxouterit
+        self.Linop_f, self.Linop_d = Linop_f, Linop_d
+        self.TotalInnerIterations = self.TotalOuterIterations = self.TotalFinalStepIterations = 0
+        self.TrueResidual = 0.0
+
+    def __call__(self, src_d, sol_d):
+        it, tr = (C.c_int * 3)(), C.c_double()
+        rc = lib().gb_mixed_cg_schur(self.Linop_f._Mat.h, self.Linop_d._Mat.h, src_d.h, sol_d.h, self.Tolerance,
+                                     self.MaxInnerIterations, self.MaxOuterIterations, it, C.byref(tr))
+        self.TotalInnerIterations, self.TotalOuterIterations, self.TotalFinalStepIterations = it[0], it[1], it[2]
+        self.TrueResidual = tr.value
+        _chk(rc)

@@ -1,0 +1,23 @@
+// comm.hpp -- NCCL entry points resolved at run time (see context.cu)
+#pragma once
+#include <nccl.h>
+#include "internal.hpp"
+
+namespace gb {
+struct NcclApi {
+  bool ok = false;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+NcclApi &nccl();
+void nccl_check(int r, const char *what);
+inline ncclDataType_t NCCL_DOUBLE = ncclDouble;
+inline ncclRedOp_t NCCL_SUM = ncclSum;
+} // namespace gb

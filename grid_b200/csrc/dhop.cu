@@ -1,0 +1,475 @@
+// dhop.cu -- hopping-term kernels, gauge DoubleStore, halo pack/exchange and their host orchestration.
+//
+// Host orchestration replaces WilsonFermion5D::DhopInternal{Serial,Overlapped}Comms
+//   (ref: Grid/qcd/action/fermion/implementation/WilsonFermion5DImplementation.h:308-411) and
+//   WilsonFermion::DhopInternal* (ref: .../WilsonFermionImplementation.h:394-498);
+// the pack kernel replaces WilsonStencil::HaloGatherOpt + FaceGatherSimple::Gather_plane_simple with the
+//   projecting WilsonCompressor (ref: WilsonCompressor.h:244-356,461-511 ; Grid/stencil/SimpleCompressor.h:22-37);
+// the exchange replaces CartesianStencil::CommunicateBegin/Complete -> StencilSendToRecvFromBegin
+//   (ref: Grid/stencil/Stencil.h:367-430 ; Grid/communicator/Communicator_mpi3.cc:390-461) with grouped
+//   ncclSend/ncclRecv on a dedicated stream, overlapped with the interior kernel;
+// double_store_kernel replaces WilsonImpl::DoubleStore + the -0.5 prefactor of ImportGauge
+//   (ref: WilsonImpl.h:127-171 ; WilsonFermion5DImplementation.h:149-181).
+#include "dhop_kernel.cuh"
+#include "comm.hpp"
+#include "fermop.hpp"
+#include <algorithm>
+
+namespace gb {
+
+// =====================================================================================================
+// site kernel
+// =====================================================================================================
+template <class T> struct SiteCtx {
+  int xh, y, z, t, pb, s;
+  uint32_t site;
+};
+
+// face index of a site for a halo in dimension MU (cb index with dimension MU removed; for MU==0 the
+// parity constraint halves y).  Must match pack_face_kernel.
+template <int MU> __device__ __forceinline__ uint32_t face_index(const DhopArgs &a, int xh, int y, int z, int t) {
+  if (MU == 0) return (uint32_t)(y >> 1) + (uint32_t)(a.Ly >> 1) * (z + a.Lz * t);
+  if (MU == 1) return (uint32_t)xh + (uint32_t)a.Lxh * (z + a.Lz * t);
+  if (MU == 2) return (uint32_t)xh + (uint32_t)a.Lxh * (y + a.Ly * t);
+  return (uint32_t)xh + (uint32_t)a.Lxh * (y + a.Ly * z);
+}
+
+// MODE 0: every leg (halo legs read the receive buffers); 1: local legs only; 2: off-node legs only
+template <class T, int DAG, int MODE, int MU, int FWD>
+__device__ __forceinline__ void dhop_leg(const DhopArgs &a, const typename Prec<T>::vec *__restrict__ in,
+                                         const typename Prec<T>::vec *__restrict__ Usite, const SiteCtx<T> &c, int ip,
+                                         SpinorReg<T> &result, int &nleg) {
+  using P = Prec<T>;
+  // non-dag: forward legs (x+mu) carry (1-gamma), backward legs (1+gamma); dag swaps.
+  // ref: WilsonKernelsImplementation.h:127-134 (dag) vs :154-161
+  constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
+  const int Lmu = MU == 0 ? a.Lx : MU == 1 ? a.Ly : MU == 2 ? a.Lz : a.Lt;
+  int coord;   // local coordinate along MU of the output site
+  if (MU == 0) coord = 2 * c.xh + c.pb; else coord = MU == 1 ? c.y : MU == 2 ? c.z : c.t;
+  const bool at_edge = FWD ? (coord == Lmu - 1) : (coord == 0);
+  const bool offnode = at_edge && ((a.comm_dim_mask >> MU) & 1);
+  if (MODE == 1 && offnode) return;
+  if (MODE == 2 && !offnode) return;
+  HalfReg<T> chi, Uchi;
+  if (MODE != 1 && offnode) {
+    const uint32_t fi = face_index<MU>(a, c.xh, c.y, c.z, c.t);
+    const uint32_t i = fi * a.Ls + c.s;
+    const typename P::vec *hp = (const typename P::vec *)a.halo[FWD ? MU : MU + 4] + (size_t)ip * a.halo_parity_stride[MU] +
+                                ((size_t)(i >> LOGW) * (P::NV / 2) << LOGW) + (i & (W - 1));
+    load_half(chi, hp);
+  } else {
+    uint32_t nsite;
+    if (MU == 0) {
+      int nx;
+      if (FWD) nx = c.pb ? (c.xh + 1 == a.Lxh ? 0 : c.xh + 1) : c.xh;
+      else nx = c.pb ? c.xh : (c.xh == 0 ? a.Lxh - 1 : c.xh - 1);
+      nsite = c.site - c.xh + nx;
+    } else {
+      const uint32_t stride = MU == 1 ? a.Lxh : MU == 2 ? a.Lxh * a.Ly : a.Lxh * a.Ly * a.Lz;
+      if (FWD) nsite = at_edge ? c.site - (Lmu - 1) * stride : c.site + stride;
+      else nsite = at_edge ? c.site + (Lmu - 1) * stride : c.site - stride;
+    }
+    const uint32_t i = nsite * a.Ls + c.s;
+    SpinorReg<T> f;
+    load_spinor(f, in + ((size_t)(i >> LOGW) * P::NV << LOGW) + (i & (W - 1)));
+    sp_proj<MU, SIGN>(chi, f);
+  }
+  LinkReg<T> u;
+  load_link(u, Usite + (FWD ? MU : MU + 4) * P::LV);
+  mult_link(Uchi, u, chi);
+  accum_recon<MU, SIGN>(result, Uchi);
+  nleg++;
+}
+
+template <class T, int DAG, int MODE>
+__global__ void __launch_bounds__(256) dhop_kernel(const DhopArgs a) {
+  using P = Prec<T>;
+  using V = typename P::vec;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.n5cb) return;
+  const int p = a.first_parity ^ (int)blockIdx.y; // output parity
+  SiteCtx<T> c;
+  uint32_t r, yl, zl, tl, yh, zh, th, s, xh;
+  a.dLs.divmod(q, r, s);
+  a.dLxh.divmod(r, r, xh);
+  a.dBy.divmod(r, r, yl);
+  a.dBz.divmod(r, r, zl);
+  a.dBt.divmod(r, r, tl);
+  a.dNy.divmod(r, r, yh);
+  a.dNz.divmod(r, th, zh);
+  c.s = s; c.xh = xh;
+  c.y = yh * a.By + yl; c.z = zh * a.Bz + zl; c.t = th * a.Bt + tl;
+  c.site = c.xh + a.Lxh * (c.y + a.Ly * (c.z + a.Lz * c.t));
+  c.pb = (p + a.origin_parity + c.y + c.z + c.t) & 1;
+
+  const V *__restrict__ in = (const V *)a.in[1 - p];
+  const V *__restrict__ Usite = (const V *)a.U[p] + (size_t)c.site * 8 * P::LV;
+  const int ip = 1 - p;
+
+  SpinorReg<T> result;
+#pragma unroll
+  for (int k = 0; k < 12; k++) { result.re[k] = 0; result.im[k] = 0; }
+  int nleg = 0;
+  // same leg order as the reference site kernel: Xm,Ym,Zm,Tm then Xp,Yp,Zp,Tp
+  dhop_leg<T, DAG, MODE, 0, 0>(a, in, Usite, c, ip, result, nleg);
+  dhop_leg<T, DAG, MODE, 1, 0>(a, in, Usite, c, ip, result, nleg);
+  dhop_leg<T, DAG, MODE, 2, 0>(a, in, Usite, c, ip, result, nleg);
+  dhop_leg<T, DAG, MODE, 3, 0>(a, in, Usite, c, ip, result, nleg);
+  dhop_leg<T, DAG, MODE, 0, 1>(a, in, Usite, c, ip, result, nleg);
+  dhop_leg<T, DAG, MODE, 1, 1>(a, in, Usite, c, ip, result, nleg);
+  dhop_leg<T, DAG, MODE, 2, 1>(a, in, Usite, c, ip, result, nleg);
+  dhop_leg<T, DAG, MODE, 3, 1>(a, in, Usite, c, ip, result, nleg);
+
+  const uint32_t i = c.site * a.Ls + c.s;
+  const size_t off = ((size_t)(i >> LOGW) * P::NV << LOGW) + (i & (W - 1));
+  V *outp = (V *)a.out[p] + off;
+  if (MODE == 2) {
+    if (nleg == 0) return;
+    SpinorReg<T> prev;
+    load_spinor(prev, outp);
+    const T sa = a.axpy[p] ? (T)a.axpy_a : (T)1;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { result.re[k] = fma(sa, result.re[k], prev.re[k]); result.im[k] = fma(sa, result.im[k], prev.im[k]); }
+  } else if (a.axpy[p] != nullptr) {
+    SpinorReg<T> ax;
+    load_spinor(ax, (const V *)a.axpy[p] + off);
+    const T sa = (T)a.axpy_a, sb = (T)a.axpy_b;
+#pragma unroll
+    for (int k = 0; k < 12; k++) { result.re[k] = fma(sa, result.re[k], sb * ax.re[k]); result.im[k] = fma(sa, result.im[k], sb * ax.im[k]); }
+  }
+  store_spinor(result, outp);
+}
+
+// =====================================================================================================
+// halo pack: project the boundary slice with the receiving leg's projector and write it contiguously.
+// One thread per (face site, s).  point = the stencil point on the RECEIVER that will consume the data:
+//   point mu   (receiver's forward leg, x+mu)  <- sender's slice x_mu = 0,    projector of the forward leg
+//   point mu+4 (receiver's backward leg, x-mu) <- sender's slice x_mu = L-1,  projector of the backward leg
+// =====================================================================================================
+struct PackArgs {
+  const void *in;      // parity block being packed (the hop's input parity)
+  void *buf;           // send buffer for this (point, parity)
+  int Ls, Lx, Lxh, Ly, Lz, Lt;
+  int ip;              // parity of the packed field
+  int origin_parity;
+  uint32_t nface;      // face sites (cb) = V4cb / L_mu
+};
+template <class T, int DAG, int MU, int FWD>
+__global__ void pack_face_kernel(const PackArgs a) {
+  using P = Prec<T>;
+  using V = typename P::vec;
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= a.nface * a.Ls) return;
+  const uint32_t fi = q / a.Ls, s = q - fi * a.Ls;
+  int xh, y, z, t;
+  const int slice = FWD ? 0 : (MU == 0 ? a.Lx : MU == 1 ? a.Ly : MU == 2 ? a.Lz : a.Lt) - 1;
+  uint32_t r = fi;
+  if (MU == 0) {
+    int yhalf = r % (a.Ly >> 1); r /= (a.Ly >> 1); z = r % a.Lz; t = r / a.Lz;
+    // x = slice has parity (ip + origin + y + z + t)&1 == slice&1  => fixes y parity
+    int ypar = (slice + a.ip + a.origin_parity + z + t) & 1;
+    y = 2 * yhalf + ypar; xh = slice >> 1;
+  } else if (MU == 1) { xh = r % a.Lxh; r /= a.Lxh; z = r % a.Lz; t = r / a.Lz; y = slice; }
+  else if (MU == 2) { xh = r % a.Lxh; r /= a.Lxh; y = r % a.Ly; t = r / a.Ly; z = slice; }
+  else { xh = r % a.Lxh; r /= a.Lxh; y = r % a.Ly; z = r / a.Ly; t = slice; }
+  const uint32_t site = xh + a.Lxh * (y + a.Ly * (z + a.Lz * t));
+  const uint32_t i = site * a.Ls + s;
+  SpinorReg<T> f;
+  load_spinor(f, (const V *)a.in + ((size_t)(i >> LOGW) * P::NV << LOGW) + (i & (W - 1)));
+  constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
+  HalfReg<T> h;
+  sp_proj<MU, SIGN>(h, f);
+  store_half(h, (V *)a.buf + ((size_t)(q >> LOGW) * (P::NV / 2) << LOGW) + (q & (W - 1)));
+}
+
+// =====================================================================================================
+// DoubleStore
+// =====================================================================================================
+struct DoubleStoreArgs {
+  const void *Ulex;         // [V4][4][9] complex
+  const void *Uhalo[4];     // backward-neighbour faces of U_mu (x_mu = L-1 slice of the -mu rank), or nullptr
+  void *Uds[2];
+  int L[4], gL[4], origin[4];
+  int comm_dim_mask;
+  double ph_re[4], ph_im[4];
+  uint32_t V4cb;
+};
+template <class T> __global__ void double_store_kernel(const DoubleStoreArgs a) {
+  using P = Prec<T>;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; // (parity, site, dir)
+  if (e >= 2u * a.V4cb * 8) return;
+  const int dir = e & 7;
+  uint32_t r = e >> 3;
+  const int p = r / a.V4cb;
+  const uint32_t site = r - p * a.V4cb;
+  const int Lxh = a.L[0] / 2;
+  int x[4];
+  uint32_t q = site;
+  int xh = q % Lxh; q /= Lxh; x[1] = q % a.L[1]; q /= a.L[1]; x[2] = q % a.L[2]; x[3] = q / a.L[2];
+  const int op = (a.origin[0] + a.origin[1] + a.origin[2] + a.origin[3]) & 1;
+  x[0] = 2 * xh + ((p + op + x[1] + x[2] + x[3]) & 1);
+  const int mu = dir & 3;
+  const T *src;
+  T m[18];
+  const T pre = (T)-0.5;
+  const int gx = x[mu] + a.origin[mu];
+  if (dir < 4) {
+    const size_t lex = x[0] + (size_t)a.L[0] * (x[1] + (size_t)a.L[1] * (x[2] + (size_t)a.L[2] * x[3]));
+    src = (const T *)a.Ulex + (lex * 4 + mu) * 18;
+    T pr = 1, pi = 0;
+    if (gx == a.gL[mu] - 1) { pr = (T)a.ph_re[mu]; pi = (T)a.ph_im[mu]; }
+    for (int k = 0; k < 9; k++) {
+      T ur = src[2 * k], ui = src[2 * k + 1];
+      m[2 * k] = pre * (pr * ur - pi * ui);
+      m[2 * k + 1] = pre * (pr * ui + pi * ur);
+    }
+  } else {
+    int y[4] = {x[0], x[1], x[2], x[3]};
+    if (x[mu] == 0 && ((a.comm_dim_mask >> mu) & 1)) {
+      // face index of the lexicographic face with dimension mu removed
+      size_t fi = 0, st = 1;
+      for (int d = 0; d < 4; d++) if (d != mu) { fi += st * x[d]; st *= a.L[d]; }
+      src = (const T *)a.Uhalo[mu] + fi * 18;
+    } else {
+      y[mu] = (x[mu] + a.L[mu] - 1) % a.L[mu];
+      const size_t lex = y[0] + (size_t)a.L[0] * (y[1] + (size_t)a.L[1] * (y[2] + (size_t)a.L[2] * y[3]));
+      src = (const T *)a.Ulex + (lex * 4 + mu) * 18;
+    }
+    T pr = 1, pi = 0;
+    if (gx == 0) { pr = (T)a.ph_re[mu]; pi = -(T)a.ph_im[mu]; } // conj(phase)
+    for (int rr = 0; rr < 3; rr++) for (int cc = 0; cc < 3; cc++) {
+      T ur = src[2 * (cc * 3 + rr)], ui = -src[2 * (cc * 3 + rr) + 1]; // adjoint
+      m[2 * (rr * 3 + cc)] = pre * (pr * ur - pi * ui);
+      m[2 * (rr * 3 + cc) + 1] = pre * (pr * ui + pi * ur);
+    }
+  }
+  if constexpr (sizeof(T) == 4) {
+    float4 *o = (float4 *)a.Uds[p] + ((size_t)site * 8 + dir) * P::LV;
+    o[0] = make_float4(m[0], m[1], m[2], m[3]);
+    o[1] = make_float4(m[4], m[5], m[6], m[7]);
+    o[2] = make_float4(m[8], m[9], m[10], m[11]);
+    o[3] = make_float4(m[12], m[13], m[14], m[15]);
+    o[4] = make_float4(m[16], m[17], 0.f, 0.f);
+  } else {
+    double2 *o = (double2 *)a.Uds[p] + ((size_t)site * 8 + dir) * P::LV;
+    for (int k = 0; k < 9; k++) o[k] = make_double2(m[2 * k], m[2 * k + 1]);
+  }
+}
+// gather the x_mu = L-1 slice of U_mu (lexicographic face order) for the gauge halo
+template <class T> __global__ void gauge_face_kernel(const T *Ulex, T *face, int4 L, int mu, uint32_t nface) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nface * 18) return;
+  const uint32_t fi = e / 18, k = e - fi * 18;
+  int Ld[4] = {L.x, L.y, L.z, L.w}, x[4];
+  uint32_t r = fi;
+  for (int d = 0; d < 4; d++) if (d != mu) { x[d] = r % Ld[d]; r /= Ld[d]; }
+  x[mu] = Ld[mu] - 1;
+  const size_t lex = x[0] + (size_t)Ld[0] * (x[1] + (size_t)Ld[1] * (x[2] + (size_t)Ld[2] * x[3]));
+  face[e] = Ulex[(lex * 4 + mu) * 18 + k];
+}
+
+// =====================================================================================================
+// host side
+// =====================================================================================================
+static int pick_block(int L, int want) {
+  if (want <= 0 || want >= L) return L;
+  int b = want;
+  while (L % b) b--;
+  return b;
+}
+
+void op_import_gauge(gb_fermop *op, const gb_gauge *Umu) {
+  gb_context *ctx = op->ctx;
+  const gb_grid *g = op->grid;
+  GB_REQUIRE(Umu->grid == g, "gauge field lives on a different grid");
+  GB_REQUIRE(Umu->prec == op->prec, "gauge precision must match the operator precision (use gb_gauge_create + import at that precision)");
+  GB_CUDA(cudaSetDevice(ctx->device));
+  const size_t vb = 16;
+  const size_t per_parity = (size_t)g->V4cb * 8 * lv_of(op->prec) * vb;
+  if (!op->Uds) {
+    op->uds_bytes = 2 * per_parity;
+    GB_CUDA(cudaMalloc(&op->Uds, op->uds_bytes));
+  }
+  DoubleStoreArgs a;
+  a.Ulex = Umu->data;
+  a.comm_dim_mask = op->comm_dim_mask;
+  a.V4cb = (uint32_t)g->V4cb;
+  for (int d = 0; d < 4; d++) {
+    a.L[d] = g->ldims[d]; a.gL[d] = g->gdims[d]; a.origin[d] = g->origin[d];
+    a.ph_re[d] = op->phases[2 * d]; a.ph_im[d] = op->phases[2 * d + 1];
+    a.Uhalo[d] = nullptr;
+  }
+  a.Uds[0] = op->Uds; a.Uds[1] = (char *)op->Uds + per_parity;
+  // gauge halo: my x_mu = L-1 slice of U_mu goes to the forward neighbour; I receive the backward neighbour's
+  void *sendf[4] = {nullptr, nullptr, nullptr, nullptr}, *recvf[4] = {nullptr, nullptr, nullptr, nullptr};
+  const size_t esz = op->prec == GB_F32 ? 4 : 8;
+  if (op->comm_dim_mask) {
+    int4 L4 = make_int4(g->ldims[0], g->ldims[1], g->ldims[2], g->ldims[3]);
+    for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+      const uint32_t nface = (uint32_t)(g->V4 / g->ldims[mu]);
+      GB_CUDA(cudaMalloc(&sendf[mu], (size_t)nface * 18 * esz));
+      GB_CUDA(cudaMalloc(&recvf[mu], (size_t)nface * 18 * esz));
+      const unsigned blocks = (nface * 18 + 255) / 256;
+      if (op->prec == GB_F32) gauge_face_kernel<float><<<blocks, 256, 0, ctx->stream>>>((const float *)Umu->data, (float *)sendf[mu], L4, mu, nface);
+      else gauge_face_kernel<double><<<blocks, 256, 0, ctx->stream>>>((const double *)Umu->data, (double *)sendf[mu], L4, mu, nface);
+      count_launch(ctx);
+    }
+    NcclApi &N = nccl();
+    nccl_check(N.GroupStart(), "ncclGroupStart");
+    for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+      const size_t bytes = (size_t)(g->V4 / g->ldims[mu]) * 18 * esz;
+      nccl_check(N.Send(sendf[mu], bytes, ncclChar, g->nbr_rank[mu][0], ctx->nccl, ctx->stream), "ncclSend");
+      nccl_check(N.Recv(recvf[mu], bytes, ncclChar, g->nbr_rank[mu][1], ctx->nccl, ctx->stream), "ncclRecv");
+    }
+    nccl_check(N.GroupEnd(), "ncclGroupEnd");
+    for (int mu = 0; mu < 4; mu++) a.Uhalo[mu] = recvf[mu];
+  }
+  const uint32_t n = 2u * a.V4cb * 8;
+  if (op->prec == GB_F32) double_store_kernel<float><<<(n + 127) / 128, 128, 0, ctx->stream>>>(a);
+  else double_store_kernel<double><<<(n + 127) / 128, 128, 0, ctx->stream>>>(a);
+  count_launch(ctx);
+  check_launch(ctx, "double_store");
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int mu = 0; mu < 4; mu++) { if (sendf[mu]) cudaFree(sendf[mu]); if (recvf[mu]) cudaFree(recvf[mu]); }
+}
+
+// allocate halo send/recv buffers (both parities) on first use
+static void ensure_halo(gb_fermop *op) {
+  if (!op->comm_dim_mask || op->halo_ready) return;
+  const gb_grid *g = op->grid;
+  const int hv = nv_of(op->prec) / 2;
+  for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+    const size_t nface5 = (size_t)(g->V4cb / g->ldims[mu]) * op->Ls;
+    const size_t blocks = (nface5 + W - 1) / W;
+    op->halo_parity_stride[mu] = blocks * hv * W; // vecs per parity
+    const size_t bytes = 2 * op->halo_parity_stride[mu] * 16;
+    for (int dir = 0; dir < 2; dir++) {
+      GB_CUDA(cudaMalloc(&op->halo_send[mu + 4 * dir], bytes));
+      GB_CUDA(cudaMalloc(&op->halo_recv[mu + 4 * dir], bytes));
+    }
+  }
+  op->halo_ready = true;
+}
+
+template <class T, int DAG> static void launch_pack(gb_fermop *op, const void *in_block, int ip, int slot, cudaStream_t st) {
+  // slot: 0 for cb operations / parity 0 of a full hop, 1 for the second parity of a full hop
+  const gb_grid *g = op->grid;
+  gb_context *ctx = op->ctx;
+  PackArgs a;
+  a.in = in_block; a.Ls = op->Ls;
+  a.Lx = g->ldims[0]; a.Lxh = a.Lx / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
+  a.ip = ip;
+  a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
+  for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+    a.nface = (uint32_t)(g->V4cb / g->ldims[mu]);
+    const uint32_t n = a.nface * op->Ls;
+    const unsigned blocks = (n + 255) / 256;
+    for (int fwd = 0; fwd < 2; fwd++) {
+      const int point = fwd ? mu : mu + 4;
+      a.buf = (char *)op->halo_send[point] + (size_t)slot * op->halo_parity_stride[mu] * 16;
+#define PK(M, F) pack_face_kernel<T, DAG, M, F><<<blocks, 256, 0, st>>>(a)
+      if (mu == 0) { if (fwd) PK(0, 1); else PK(0, 0); }
+      else if (mu == 1) { if (fwd) PK(1, 1); else PK(1, 0); }
+      else if (mu == 2) { if (fwd) PK(2, 1); else PK(2, 0); }
+      else { if (fwd) PK(3, 1); else PK(3, 0); }
+#undef PK
+      count_launch(ctx);
+    }
+  }
+  check_launch(ctx, "pack_face");
+}
+
+static void exchange_halos(gb_fermop *op, int nslots, cudaStream_t st) {
+  const gb_grid *g = op->grid;
+  gb_context *ctx = op->ctx;
+  NcclApi &N = nccl();
+  nccl_check(N.GroupStart(), "ncclGroupStart");
+  for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+    const size_t bytes = (size_t)nslots * op->halo_parity_stride[mu] * 16;
+    // data for the receiver's forward leg (point mu) is my x=0 slice: it travels to my backward neighbour
+    nccl_check(N.Send(op->halo_send[mu], bytes, ncclChar, g->nbr_rank[mu][1], ctx->nccl, st), "ncclSend");
+    nccl_check(N.Recv(op->halo_recv[mu], bytes, ncclChar, g->nbr_rank[mu][0], ctx->nccl, st), "ncclRecv");
+    // data for the receiver's backward leg (point mu+4) is my x=L-1 slice: it travels forward
+    nccl_check(N.Send(op->halo_send[mu + 4], bytes, ncclChar, g->nbr_rank[mu][0], ctx->nccl, st), "ncclSend");
+    nccl_check(N.Recv(op->halo_recv[mu + 4], bytes, ncclChar, g->nbr_rank[mu][1], ctx->nccl, st), "ncclRecv");
+  }
+  nccl_check(N.GroupEnd(), "ncclGroupEnd");
+}
+
+template <class T> static void launch_dhop_T(gb_fermop *op, DhopArgs &a, int nparity, int dag, int mode, cudaStream_t st) {
+  dim3 grid((a.n5cb + 255) / 256, nparity);
+#define DK(D, M) dhop_kernel<T, D, M><<<grid, 256, 0, st>>>(a)
+  if (!dag) { if (mode == 0) DK(0, 0); else if (mode == 1) DK(0, 1); else DK(0, 2); }
+  else { if (mode == 0) DK(1, 0); else if (mode == 1) DK(1, 1); else DK(1, 2); }
+#undef DK
+  count_launch(op->ctx);
+  check_launch(op->ctx, "dhop");
+}
+
+// The one entry used by every operator: hop from the parity blocks in[] to out[].
+//   parity_out_first: output parity of the first (or only) parity; nparity 1 (DhopEO/OE) or 2 (full Dhop)
+//   axpy: optional out = a*hop + b*ax (ax blocks indexed by output parity)
+void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
+                 const void *const ax[2], double axa, double axb) {
+  gb_context *ctx = op->ctx;
+  const gb_grid *g = op->grid;
+  GB_CUDA(cudaSetDevice(ctx->device));
+  DhopArgs a;
+  const size_t per_parity = (size_t)g->V4cb * 8 * lv_of(op->prec) * 16;
+  for (int p = 0; p < 2; p++) {
+    a.in[p] = in[p]; a.out[p] = out[p];
+    a.U[p] = (char *)op->Uds + p * per_parity;
+    a.axpy[p] = ax ? ax[p] : nullptr;
+  }
+  a.axpy_a = axa; a.axpy_b = axb;
+  a.comm_dim_mask = op->comm_dim_mask;
+  a.Ls = op->Ls; a.Lx = g->ldims[0]; a.Lxh = a.Lx / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
+  a.By = pick_block(a.Ly, op->By); a.Bz = pick_block(a.Lz, op->Bz); a.Bt = pick_block(a.Lt, op->Bt);
+  a.dLs = FastDiv(a.Ls); a.dLxh = FastDiv(a.Lxh); a.dBy = FastDiv(a.By); a.dBz = FastDiv(a.Bz); a.dBt = FastDiv(a.Bt);
+  a.dNy = FastDiv(a.Ly / a.By); a.dNz = FastDiv(a.Lz / a.Bz);
+  a.n5cb = (uint32_t)(g->V4cb * op->Ls);
+  a.first_parity = parity_out_first;
+  a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
+  for (int i = 0; i < 8; i++) a.halo[i] = nullptr;
+  for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = 0;
+  a.mode = 0;
+
+  auto run = [&](int mode, cudaStream_t st) {
+    if (op->prec == GB_F32) launch_dhop_T<float>(op, a, nparity, dag, mode, st);
+    else launch_dhop_T<double>(op, a, nparity, dag, mode, st);
+  };
+  if (!op->comm_dim_mask) { run(0, ctx->stream); return; }
+
+  // ---- multi-GPU: pack -> exchange (comm stream) || interior (compute stream) -> exterior
+  ensure_halo(op);
+  for (int i = 0; i < 8; i++) a.halo[i] = op->halo_recv[i];
+  for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = op->halo_parity_stride[i];
+  // the halo "slot" of an input parity: cb ops use slot 0; the full hop stores input parity ip in slot ip
+  // (dhop_leg indexes with ip * stride, so for cb ops we bias the base pointer instead)
+  if (nparity == 1) {
+    const int ip = 1 - parity_out_first;
+    for (int i = 0; i < 8; i++) if (a.halo[i]) a.halo[i] = (const char *)a.halo[i] - (size_t)ip * op->halo_parity_stride[i & 3] * 16;
+  }
+  // make sure previous consumers of the send/recv buffers are done (StencilBarrier analogue):
+  // everything is stream ordered on ctx->stream, and the comm stream waits on the pack event.
+  for (int j = 0; j < nparity; j++) {
+    const int po = parity_out_first ^ j, ip = 1 - po;
+    const int slot = nparity == 1 ? 0 : ip;
+    if (op->prec == GB_F32) { if (dag) launch_pack<float, 1>(op, in[ip], ip, slot, ctx->stream); else launch_pack<float, 0>(op, in[ip], ip, slot, ctx->stream); }
+    else { if (dag) launch_pack<double, 1>(op, in[ip], ip, slot, ctx->stream); else launch_pack<double, 0>(op, in[ip], ip, slot, ctx->stream); }
+  }
+  GB_CUDA(cudaEventRecord(ctx->ev_comp, ctx->stream));
+  GB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comp, 0));
+  exchange_halos(op, nparity, ctx->comm_stream);
+  GB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+  if (op->overlap_comms) {
+    run(1, ctx->stream);                                   // interior legs while the faces travel
+    GB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+    run(2, ctx->stream);                                   // exterior legs
+  } else {
+    GB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+    run(0, ctx->stream);
+  }
+}
+
+} // namespace gb

@@ -1,0 +1,45 @@
+// fermop.hpp -- the FermionOperator object behind the C ABI and the internal kernel entry points.
+#pragma once
+#include "internal.hpp"
+
+enum gb_opkind { GB_KIND_WILSON = 0, GB_KIND_CAYLEY = 1 };
+
+struct gb_fermop {
+  gb_grid *grid = nullptr;
+  gb_context *ctx = nullptr;
+  int kind = 0, prec = 0, Ls = 1;
+  double mass = 0, M5 = 0;
+  double phases[8] = {1, 0, 1, 0, 1, 0, 1, 0};
+  gb::CayleyCoeffs k;
+  void *Uds = nullptr; // doubled links [2 parities][V4cb][8][LV] vecs, -1/2 and phases folded in
+  size_t uds_bytes = 0;
+  // rasterisation blocking of the hopping kernel (0 = whole extent)
+  int By = 0, Bz = 0, Bt = 0;
+  // multi-GPU halos (ref: CartesianStencil u_send_buf/u_recv_buf, Stencil.h:839-848)
+  int comm_dim_mask = 0;
+  bool overlap_comms = true;
+  bool halo_ready = false;
+  void *halo_send[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void *halo_recv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t halo_parity_stride[4] = {0, 0, 0, 0};
+  // temporaries (ref: FermionOperator::tmp(), and the stack Fields of SchurDiagMooeeOperator)
+  gb_fermion *tmp_h[4] = {nullptr, nullptr, nullptr, nullptr};
+  gb_fermion *tmp_f[2] = {nullptr, nullptr};
+};
+
+namespace gb {
+void op_import_gauge(gb_fermop *op, const gb_gauge *Umu);
+void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
+                 const void *const ax[2], double axa, double axb);
+
+// 5D s-direction kernels (cayley.cu).  All operate on `nparity` parity blocks of nblk blocks each.
+// chi = diag_s*phi_s + upper_s*P(-/+)psi_{s+1} + lower_s*P(+/-)psi_{s-1} [+ alpha*w]
+void m5d_apply(gb_fermop *op, const gb_fermion *psi, const gb_fermion *phi, gb_fermion *chi, const std::vector<double> &lower,
+               const std::vector<double> &diag, const std::vector<double> &upper, int dag, const gb_fermion *w, double alpha);
+void mooee_inv_apply(gb_fermop *op, const gb_fermion *psi, gb_fermion *chi, int dag);
+
+// composite operator pieces used by the solvers
+void op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
+gb_fermion *op_tmp_half(gb_fermop *op, int i);
+gb_fermion *op_tmp_full(gb_fermop *op, int i);
+} // namespace gb

@@ -1,0 +1,160 @@
+// solver.cu -- ConjugateGradient and MixedPrecisionConjugateGradient on the device.
+//   ref: Grid/algorithms/iterative/ConjugateGradient.h:68-257 (update order, stopping rule cp <= tol^2 |src|^2,
+//        true residual via an extra HermOp), ConjugateGradientMixedPrec.h:71-167 (defect-correction restarts).
+// The iteration is   d = <p, A p> ; a = c/d ; r -= a Ap ; cp = |r|^2 ; b = cp/c ; psi += a p ; p = b p + r
+// with the norm fused into the r-update (axpy_norm) and the two axpys fused into one pass (ConjugateGradient.h:176-183).
+#include "fermop.hpp"
+#include "kernels_common.cuh"
+#include <cmath>
+#include <functional>
+
+namespace gb {
+
+// psi += a p ; p = b p + r    (ref: ConjugateGradient.h:176-183)
+template <class V, class T> __global__ void cg_update_kernel(V *psi, V *p, const V *r, T a, T b, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const V pv = p[i];
+    psi[i] = vaxpy(a, pv, psi[i]);
+    p[i] = vaxpy(b, pv, r[i]);
+  }
+}
+static void cg_update(gb_context *ctx, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, double a, double b) {
+  const int64_t n = psi->nvec();
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  if (psi->prec == GB_F32) cg_update_kernel<float4, float><<<blocks, 256, 0, ctx->stream>>>((float4 *)psi->data, (float4 *)p->data, (const float4 *)r->data, (float)a, (float)b, n);
+  else cg_update_kernel<double2, double><<<blocks, 256, 0, ctx->stream>>>((double2 *)psi->data, (double2 *)p->data, (const double2 *)r->data, a, b, n);
+  count_launch(ctx);
+  check_launch(ctx, "cg_update");
+}
+
+static void chk(int rc) { if (rc != GB_OK) throw Error(rc, gb_last_error()); }
+
+struct CGOut { int iters = 0; double true_resid = 0; bool converged = false; };
+using HermOpFn = std::function<void(const gb_fermion *, gb_fermion *)>;
+
+static CGOut cg_core(gb_context *ctx, const HermOpFn &A, const gb_fermion *src, gb_fermion *psi, double tol, int maxit) {
+  fermion_check_same(src, psi);
+  gb_grid *g = src->grid;
+  gb_fermion *p = nullptr, *mmp = nullptr, *r = nullptr;
+  auto mk = [&](gb_fermion **f) { chk(gb_fermion_create(g, src->Ls, (gb_precision)src->prec, (gb_gridkind)src->kind, f)); (*f)->cb = src->cb; };
+  mk(&p); mk(&mmp); mk(&r);
+  struct Guard { gb_fermion *a, *b, *c; ~Guard() { gb_fermion_destroy(a); gb_fermion_destroy(b); gb_fermion_destroy(c); } } guard{p, mmp, r};
+  psi->cb = src->cb;
+  CGOut out;
+  double ssq, guess, a, cp, c, d, b, dd[2];
+  chk(gb_norm2(src, &ssq));
+  chk(gb_norm2(psi, &guess));
+  GB_REQUIRE(!std::isnan(guess), "initial guess contains NaN");
+  if (guess == 0.0) { chk(gb_copy(r, src)); chk(gb_copy(p, r)); a = ssq; }
+  else {
+    A(psi, mmp);
+    chk(gb_axpy(r, -1.0, mmp, src));
+    chk(gb_copy(p, r));
+    chk(gb_norm2(p, &a));
+  }
+  cp = a;
+  if (ssq == 0.0) { chk(gb_zero(psi)); out.iters = 1; out.true_resid = 0; out.converged = true; return out; }
+  const double rsq = tol * tol * ssq;
+  if (cp <= rsq) { out.true_resid = std::sqrt(a / ssq); out.iters = 0; out.converged = true; return out; }
+  int k;
+  for (k = 1; k <= maxit; k++) {
+    c = cp;
+    A(p, mmp);
+    chk(gb_inner_product(p, mmp, dd));
+    d = dd[0];
+    a = c / d;
+    chk(gb_axpy_norm(r, -a, mmp, r, &cp));
+    b = cp / c;
+    cg_update(ctx, psi, p, r, a, b);
+    if (cp <= rsq) {
+      A(psi, mmp);
+      chk(gb_axpy(p, -1.0, src, mmp)); // p = mmp - src
+      double rn;
+      chk(gb_norm2(p, &rn));
+      out.true_resid = std::sqrt(rn) / std::sqrt(ssq);
+      out.iters = k; out.converged = true;
+      return out;
+    }
+  }
+  out.iters = k; out.converged = false;
+  return out;
+}
+
+} // namespace gb
+
+using namespace gb;
+
+extern "C" {
+
+int gb_cg_schur(gb_fermop *op, const gb_fermion *src, gb_fermion *sol, double tol, int maxit, int *iters_out, double *true_resid_out) {
+  GB_API_BEGIN
+  GB_REQUIRE(op && src && sol, "null argument");
+  CGOut o = cg_core(op->ctx, [&](const gb_fermion *in, gb_fermion *out) { op_apply(op, GB_OP_HERMOP, in, out, 0); }, src, sol, tol, maxit);
+  if (iters_out) *iters_out = o.iters;
+  if (true_resid_out) *true_resid_out = o.true_resid;
+  if (!o.converged) throw Error(GB_ERR_NOT_CONVERGED, "ConjugateGradient did NOT converge");
+  GB_API_END
+}
+
+int gb_cg(gb_context *ctx, gb_hermop_fn hermop, void *user, const gb_fermion *src, gb_fermion *sol, double tol, int maxit,
+          int *iters_out, double *true_resid_out) {
+  GB_API_BEGIN
+  GB_REQUIRE(ctx && hermop && src && sol, "null argument");
+  CGOut o = cg_core(ctx, [&](const gb_fermion *in, gb_fermion *out) {
+    int rc = hermop(user, in, out);
+    if (rc != GB_OK) throw Error(rc, "user HermOp failed");
+  }, src, sol, tol, maxit);
+  if (iters_out) *iters_out = o.iters;
+  if (true_resid_out) *true_resid_out = o.true_resid;
+  if (!o.converged) throw Error(GB_ERR_NOT_CONVERGED, "ConjugateGradient did NOT converge");
+  GB_API_END
+}
+
+int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, int max_inner,
+                      int max_outer, int iters_out[3], double *true_resid_out) {
+  GB_API_BEGIN
+  GB_REQUIRE(op_f && op_d && src_d_in && sol_d, "null argument");
+  GB_REQUIRE(op_f->prec == GB_F32 && op_d->prec == GB_F64, "mixed CG needs an fp32 and an fp64 operator");
+  GB_REQUIRE(src_d_in->prec == GB_F64 && sol_d->prec == GB_F64, "mixed CG outer fields must be fp64");
+  gb_context *ctx = op_d->ctx;
+  gb_grid *g = src_d_in->grid;
+  const int cb = src_d_in->cb;
+  sol_d->cb = cb;
+  gb_fermion *tmp_d = nullptr, *src_d = nullptr, *src_f = nullptr, *sol_f = nullptr;
+  chk(gb_fermion_create(g, src_d_in->Ls, GB_F64, GB_HALF, &tmp_d));
+  chk(gb_fermion_create(g, src_d_in->Ls, GB_F64, GB_HALF, &src_d));
+  chk(gb_fermion_create(g, src_d_in->Ls, GB_F32, GB_HALF, &src_f));
+  chk(gb_fermion_create(g, src_d_in->Ls, GB_F32, GB_HALF, &sol_f));
+  struct Guard { gb_fermion *a, *b, *c, *d; ~Guard() { gb_fermion_destroy(a); gb_fermion_destroy(b); gb_fermion_destroy(c); gb_fermion_destroy(d); } } guard{tmp_d, src_d, src_f, sol_f};
+  tmp_d->cb = src_d->cb = src_f->cb = sol_f->cb = cb;
+  double src_norm;
+  chk(gb_norm2(src_d_in, &src_norm));
+  const double stop = src_norm * tol * tol;
+  const double OuterLoopNormMult = 100.0;
+  double inner_tol = tol;
+  int total_inner = 0, outer;
+  auto Ad = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_d, GB_OP_HERMOP, in, out, 0); };
+  auto Af = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_f, GB_OP_HERMOP, in, out, 0); };
+  chk(gb_copy(src_d, src_d_in));
+  for (outer = 0; outer < max_outer; outer++) {
+    Ad(sol_d, tmp_d);
+    double norm;
+    chk(gb_axpy_norm(src_d, -1.0, tmp_d, src_d_in, &norm));
+    if (norm < OuterLoopNormMult * stop) break;
+    while (norm * inner_tol * inner_tol < stop) inner_tol *= 2;
+    chk(gb_precision_change(src_f, src_d));
+    chk(gb_zero(sol_f));
+    CGOut in = cg_core(ctx, Af, src_f, sol_f, inner_tol, max_inner); // ErrorOnNoConverge = false
+    total_inner += in.iters;
+    chk(gb_precision_change(tmp_d, sol_f));
+    chk(gb_axpy(sol_d, 1.0, tmp_d, sol_d));
+  }
+  CGOut fin = cg_core(ctx, Ad, src_d_in, sol_d, tol, max_inner);
+  if (iters_out) { iters_out[0] = total_inner; iters_out[1] = outer; iters_out[2] = fin.iters; }
+  if (true_resid_out) *true_resid_out = fin.true_resid;
+  if (!fin.converged) throw Error(GB_ERR_NOT_CONVERGED, "MixedPrecisionConjugateGradient final solve did NOT converge");
+  GB_API_END
+}
+}

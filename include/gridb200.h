@@ -1,0 +1,191 @@
+/* =====================================================================================
+ * gridb200.h -- C ABI of the B200-native Dirac hopping term / Schur-CG library (libgridb200.so)
+ *
+ * This is the drop-in boundary for paboyle/Grid's data-parallel hot path.  Every entry point names
+ * the reference interface it replaces ("ref:" paths are relative to the reference tree).  Signatures
+ * carry only plain pointers, sizes and opaque handles: no C++ or torch types.
+ *
+ * Host-side data layouts at the boundary (identical to what Grid's unvectorizeToLexOrdArray /
+ * vectorizeFromLexOrdArray, ref: Grid/lattice/Lattice_transfer.h:1123,1218, or a peekLocalSite loop,
+ * ref: Grid/lattice/Lattice_peekpoke.h:159-226, produce on each rank for its LOCAL lattice):
+ *   4D local lexicographic site index   i4 = x + Lx*(y + Ly*(z + Lz*t))       ref: Grid/util/Lexicographic.h:18-27
+ *   5D                                  i5 = s + Ls*i4   (s fastest)          ref: Grid/qcd/utils/SpaceTimeGrid.cc:49-63
+ *   fermion site object   psi[spin 4][colour 3] {re,im}                       (SpinColourVector)
+ *   gauge site object     U[mu 4][row 3][col 3] {re,im}, (U chi)_row = sum_col U[row][col] chi_col
+ *                                                                             ref: Grid/qcd/QCD.h:106
+ *   half (red-black) fields: icb = s + Ls*((x>>1) + (Lx/2)*(y + Ly*(z + Lz*t))), parity (x+y+z+t)&1 of the
+ *   GLOBAL coordinate, Even=0 / Odd=1, s ignored                             ref: Grid/cartesian/Cartesian_red_black.h:68-76,271-286
+ * The device layout is private to the library.
+ *
+ * Error model: the reference only asserts/exits (ref: ConjugateGradient.h:97,225,254).  Here every call
+ * returns GB_OK (0) or a negative gb_status; gb_last_error() gives the message.  The C++ wrappers in
+ * gridb200.hpp assert on failure to mimic the reference.  There is NO CPU fallback: without a CUDA device
+ * gb_context_create fails with GB_ERR_NO_DEVICE and no compute entry point can be reached.
+ *
+ * Threading: like the reference (one global computeStream, mutable statics; ref: Grid/threads/Accelerator.h:109-110)
+ * a context must be driven by one host thread at a time.
+ * ===================================================================================== */
+#ifndef GRIDB200_H
+#define GRIDB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gb_context gb_context; /* device + streams + communicator   (ref: Grid_init / acceleratorInit, Grid/util/Init.cc:300-560) */
+typedef struct gb_grid gb_grid;       /* GridCartesian 4D + its red-black + 5D companions (ref: SpaceTimeGrid.cc:36-78) */
+typedef struct gb_fermion gb_fermion; /* LatticeFermion{F,D} on a full or red-black, 4D or 5D grid (ref: Grid/lattice/Lattice_base.h) */
+typedef struct gb_gauge gb_gauge;     /* LatticeGaugeField{F,D} (ref: Grid/qcd/QCD.h:106) */
+typedef struct gb_fermop gb_fermop;   /* FermionOperator<Impl> (ref: Grid/qcd/action/fermion/FermionOperator.h:40-192) */
+
+typedef enum { GB_OK = 0, GB_ERR_INVALID = -1, GB_ERR_CUDA = -2, GB_ERR_NO_DEVICE = -3, GB_ERR_NOT_CONVERGED = -4, GB_ERR_COMM = -5 } gb_status;
+typedef enum { GB_F32 = 0, GB_F64 = 1 } gb_precision;
+typedef enum { GB_EVEN = 0, GB_ODD = 1 } gb_parity;       /* ref: Cartesian_red_black.h:34-37 */
+typedef enum { GB_FULL = 0, GB_HALF = 1 } gb_gridkind;    /* GridCartesian vs GridRedBlackCartesian */
+
+/* Operator entry points of FermionOperator / SchurDiagMooeeOperator, selected by code so that one
+ * C symbol serves them all.  ref: FermionOperator.h:63-78 ; LinearOperator.h:286-349 */
+typedef enum {
+  GB_OP_DHOP = 0,          /* Dhop(in,out,dag)    full grid          ref: WilsonFermion5DImplementation.h:437-445 */
+  GB_OP_DHOP_OE = 1,       /* DhopOE(in,out,dag)  in Even -> out Odd ref: :415-424 */
+  GB_OP_DHOP_EO = 2,       /* DhopEO(in,out,dag)  in Odd -> out Even ref: :426-435 */
+  GB_OP_M = 3,             /* ref: CayleyFermion5DImplementation.h:274-286 ; WilsonFermionImplementation.h:114-119 */
+  GB_OP_MDAG = 4,          /* ref: :289-304 */
+  GB_OP_MEOOE = 5,         /* ref: :308-317 (dispatches on in.Checkerboard()) */
+  GB_OP_MEOOE_DAG = 6,     /* ref: :320-329 */
+  GB_OP_MOOEE = 7,         /* ref: :191-204 */
+  GB_OP_MOOEE_DAG = 8,     /* ref: :206-233 */
+  GB_OP_MOOEE_INV = 9,     /* ref: CayleyFermion5Dcache.h:117-172 */
+  GB_OP_MOOEE_INV_DAG = 10,/* ref: CayleyFermion5Dcache.h:174-230 */
+  GB_OP_MPC = 11,          /* SchurDiagMooeeOperator::Mpc      ref: LinearOperator.h:330-339 */
+  GB_OP_MPC_DAG = 12,      /* SchurDiagMooeeOperator::MpcDag   ref: :340-348 */
+  GB_OP_HERMOP = 13,       /* SchurOperatorBase::HermOp = MpcDagMpc  ref: :291-307 */
+  GB_OP_DW = 14,           /* WilsonFermion5D::DW = Dhop + (4-M5)    ref: WilsonFermion5DImplementation.h:447-452 */
+  GB_OP_MEOOE5D = 15,      /* ref: CayleyFermion5DImplementation.h:165-174 */
+  GB_OP_MEOOEDAG5D = 16    /* ref: :248-271 */
+} gb_opcode;
+
+/* ---------------------------------------------------------------- context / runtime
+ * replaces Grid_init -> acceleratorInit (device by local rank, compute+copy streams)
+ * ref: Grid/threads/Accelerator.cc:19-110 ; Grid/util/Init.cc:300-560 */
+int gb_context_create(int device, gb_context **out);
+int gb_context_destroy(gb_context *ctx);
+const char *gb_last_error(void);
+int gb_device_count(void);
+int gb_synchronize(gb_context *ctx);                       /* ref: accelerator_barrier, Accelerator.h:233-245 */
+/* CUDA-event stopwatch on the library's compute stream (GridStopWatch analogue, ref: Grid/perfmon/Timer.h:83) */
+int gb_timer_start(gb_context *ctx);
+int gb_timer_stop(gb_context *ctx, double *elapsed_ms);
+/* number of kernels this library has launched on ctx since creation (evidence for "gpu_launches") */
+int64_t gb_launch_count(gb_context *ctx);
+/* write > L2-capacity bytes so that the next timed call starts with a cold L2 */
+int gb_flush_l2(gb_context *ctx);
+
+/* Multi-GPU: one process per GPU.  Replaces CartesianCommunicator (MPI_Cart_create + cudaIpc peer buffers,
+ * ref: Grid/communicator/Communicator_mpi3.cc:226,390-461 ; SharedMemoryMPI.cc:598-680) with NCCL over NVLink.
+ * The caller bootstraps: rank 0 calls gb_comm_unique_id, broadcasts the 128 bytes (MPI_Bcast / torch.distributed),
+ * every rank calls gb_comm_init.  Rank -> processor coordinate is lexicographic with dimension 0 fastest
+ * (ref: Communicator_base.h ShiftedRanks / Lexicographic::CoorFromIndex). */
+#define GB_UNIQUE_ID_BYTES 128
+int gb_comm_unique_id(void *id_out);
+int gb_comm_init(gb_context *ctx, int rank, int nranks, const void *id);
+int gb_comm_rank(gb_context *ctx, int *rank, int *nranks);
+/* GlobalSum of host doubles, ref: Communicator_mpi3.cc:299-307 */
+int gb_comm_global_sum(gb_context *ctx, double *vals, int n);
+int gb_comm_barrier(gb_context *ctx);
+
+/* ---------------------------------------------------------------- grids
+ * gdims = global 4D lattice (--grid), mpi = processor grid (--mpi).  ref: SpaceTimeGrid::makeFourDimGrid,
+ * makeFiveDimGrid, make*RedBlackGrid (Grid/qcd/utils/SpaceTimeGrid.cc:36-78).  The fifth dimension is never
+ * decomposed (ref: WilsonFermion5DImplementation.h:80-88).  Local extents must be even. */
+int gb_grid_create(gb_context *ctx, const int gdims[4], const int mpi[4], gb_grid **out);
+int gb_grid_destroy(gb_grid *g);
+int gb_grid_local_dims(const gb_grid *g, int ldims[4]);
+int gb_grid_local_origin(const gb_grid *g, int origin[4]);   /* global coordinate of local site 0 */
+
+/* ---------------------------------------------------------------- fermion fields
+ * Ls = 1 for 4D fields.  kind GB_HALF = field on the red-black grid; its Checkerboard() is set by
+ * gb_fermion_set_checkerboard or by the operation that fills it (ref: Lattice_base.h Checkerboard()). */
+int gb_fermion_create(gb_grid *g, int Ls, gb_precision prec, gb_gridkind kind, gb_fermion **out);
+int gb_fermion_destroy(gb_fermion *f);
+int gb_fermion_checkerboard(const gb_fermion *f);
+int gb_fermion_set_checkerboard_tag(gb_fermion *f, int cb);
+int64_t gb_fermion_local_sites(const gb_fermion *f);          /* number of 5D sites held locally */
+/* host lexicographic array (layout at top of file) -> device; host_prec may differ from the field's.
+ * ref: vectorizeFromLexOrdArray, Lattice_transfer.h:1218-1260 */
+int gb_fermion_import(gb_fermion *f, const void *host, gb_precision host_prec);
+/* ref: unvectorizeToLexOrdArray, Lattice_transfer.h:1123-1166 */
+int gb_fermion_export(const gb_fermion *f, void *host, gb_precision host_prec);
+/* ref: pickCheckerboard / setCheckerboard, Lattice_transfer.h:50-86 */
+int gb_pick_checkerboard(int cb, gb_fermion *half, const gb_fermion *full);
+int gb_set_checkerboard(gb_fermion *full, const gb_fermion *half);
+/* ref: precisionChange, Lattice_transfer.h:1461-1492 */
+int gb_precision_change(gb_fermion *out, const gb_fermion *in);
+/* synthetic sources generated on the device, decomposition independent (keyed by global site):
+ * uniform [0,1) real & imaginary parts like Grid's random() (ref: Benchmark_dwf_fp32.cc:163) */
+int gb_fermion_random(gb_fermion *f, uint64_t seed);
+
+/* BLAS-1 / reductions.  ref: Grid/lattice/Lattice_arith.h:231-258 ; Lattice_reduction.h:256-372.
+ * Site products in working precision, lattice sums in double, fixed reduction order (bit-reproducible),
+ * then GlobalSum over ranks. */
+int gb_zero(gb_fermion *z);
+int gb_copy(gb_fermion *z, const gb_fermion *x);
+int gb_scale(gb_fermion *z, double a, const gb_fermion *x);
+int gb_axpy(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y);             /* z = a x + y */
+int gb_axpby(gb_fermion *z, double a, double b, const gb_fermion *x, const gb_fermion *y);  /* z = a x + b y */
+int gb_axpy_norm(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y, double *norm2_z);
+int gb_norm2(const gb_fermion *x, double *out);
+int gb_inner_product(const gb_fermion *l, const gb_fermion *r, double out_re_im[2]);         /* sum conj(l) r */
+
+/* ---------------------------------------------------------------- gauge fields */
+int gb_gauge_create(gb_grid *g, gb_precision prec, gb_gauge **out);
+int gb_gauge_destroy(gb_gauge *u);
+int gb_gauge_import(gb_gauge *u, const void *host, gb_precision host_prec);  /* [V4 local][4][3][3] complex */
+int gb_gauge_export(const gb_gauge *u, void *host, gb_precision host_prec);
+/* random SU(3) links on the device: exp(Ta(gaussian)) restating SU<Nc>::HotConfiguration
+ * (ref: Grid/qcd/utils/GaugeGroup.h:332-349); decomposition independent */
+int gb_gauge_random(gb_gauge *u, uint64_t seed);
+int gb_gauge_unit(gb_gauge *u);
+
+/* ---------------------------------------------------------------- fermion operators
+ * ctor analogues: WilsonFermion(Umu,Grid,RBGrid,mass) ref: WilsonFermion.h:139-142
+ *                 DomainWallFermion(Umu,FGrid,FrbGrid,UGrid,UrbGrid,mass,M5) ref: DomainWallFermion.h:108-134
+ *                 MobiusFermion(...,mass,M5,b,c) ref: MobiusFermion.h:45-71
+ * boundary_phases: 4 complex numbers {re,im} (ImplParams::boundary_phases, ref: WilsonImpl.h:143-170) or NULL = periodic.
+ * The operator owns its double-stored links (ref: WilsonFermion5D.h:188-207); ImportGauge copies. */
+int gb_op_create_wilson(gb_grid *g, const gb_gauge *Umu, double mass, const double *boundary_phases, gb_fermop **out);
+int gb_op_create_dwf(gb_grid *g, const gb_gauge *Umu, int Ls, double mass, double M5, const double *boundary_phases, gb_fermop **out);
+int gb_op_create_mobius(gb_grid *g, const gb_gauge *Umu, int Ls, double mass, double M5, double b, double c, const double *boundary_phases, gb_fermop **out);
+int gb_op_import_gauge(gb_fermop *op, const gb_gauge *Umu);    /* ref: WilsonFermion5DImplementation.h:149-181 */
+int gb_op_destroy(gb_fermop *op);
+int gb_op_Ls(const gb_fermop *op);
+/* which: gb_opcode.  dag only matters for GB_OP_DHOP*, GB_OP_DW.  Checkerboard asserts as in the reference
+ * (DhopOE needs in.cb==Even ...).  in and out must be distinct fields of the operator's precision. */
+int gb_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
+/* tuning knob of the hopping kernel's CTA rasterisation (z/t blocking for L2 reuse); 0 = default */
+int gb_op_set_tiling(gb_fermop *op, int block_y, int block_z, int block_t);
+/* 1 (default): interior kernel overlaps the face exchange (ref: --comms-overlap, WilsonFermion5DImplementation.h:320-384);
+ * 0: exchange then compute (ref: DhopInternalSerialComms, :388-411) */
+int gb_op_set_overlap(gb_fermop *op, int overlap);
+
+/* ---------------------------------------------------------------- solvers
+ * ConjugateGradient on SchurDiagMooeeOperator(op).HermOp, fused device path.
+ * ref: Grid/algorithms/iterative/ConjugateGradient.h:68-257.  sol is the initial guess on entry.
+ * iters_out = IterationsToComplete, true_resid_out = TrueResidual.  Returns GB_ERR_NOT_CONVERGED if
+ * MaxIterations is reached (the wrapper asserts when ErrorOnNoConverge). */
+int gb_cg_schur(gb_fermop *op, const gb_fermion *src, gb_fermion *sol, double tol, int maxit, int *iters_out, double *true_resid_out);
+/* Generic LinearOperatorBase path: HermOp supplied by the caller (any user-written Schur operator). */
+typedef int (*gb_hermop_fn)(void *user, const gb_fermion *in, gb_fermion *out);
+int gb_cg(gb_context *ctx, gb_hermop_fn hermop, void *user, const gb_fermion *src, gb_fermion *sol, double tol, int maxit,
+          int *iters_out, double *true_resid_out);
+/* MixedPrecisionConjugateGradient: ref: Grid/algorithms/iterative/ConjugateGradientMixedPrec.h:71-167
+ * iters_out[3] = {TotalInnerIterations, TotalOuterIterations, TotalFinalStepIterations} */
+int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d, gb_fermion *sol_d, double tol, int max_inner,
+                      int max_outer, int iters_out[3], double *true_resid_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GRIDB200_H */
