@@ -50,7 +50,7 @@ SYMBOLS = [
     ("gb_op_create_wilson", _i, [_vp, _vp, _d, _pd, _pvp]), ("gb_op_create_dwf", _i, [_vp, _vp, _i, _d, _d, _pd, _pvp]),
     ("gb_op_create_mobius", _i, [_vp, _vp, _i, _d, _d, _d, _d, _pd, _pvp]), ("gb_op_import_gauge", _i, [_vp, _vp]),
     ("gb_op_destroy", _i, [_vp]), ("gb_op_Ls", _i, [_vp]), ("gb_op_apply", _i, [_vp, _i, _vp, _vp, _i]),
-    ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]),
+    ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
 ]
@@ -340,6 +340,9 @@ class FermionOperator:
 
     def set_tiling(self, by=0, bz=0, bt=0):
         lib().gb_op_set_tiling(self.h, by, bz, bt)
+
+    def set_fast_kernel(self, on):
+        lib().gb_op_set_fast_kernel(self.h, 1 if on else 0)
 
     def set_overlap(self, on):
         lib().gb_op_set_overlap(self.h, 1 if on else 0)

@@ -438,7 +438,10 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
     if (op->prec == GB_F32) launch_dhop_T<float>(op, a, nparity, dag, mode, st);
     else launch_dhop_T<double>(op, a, nparity, dag, mode, st);
   };
-  if (!op->comm_dim_mask) { run(0, ctx->stream); return; }
+  if (!op->comm_dim_mask) {
+    if (!dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 0, ctx->stream)) run(0, ctx->stream);
+    return;
+  }
 
   // ---- multi-GPU: pack -> exchange (comm stream) || interior (compute stream) -> exterior
   ensure_halo(op);
@@ -463,7 +466,8 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   exchange_halos(op, nparity, ctx->comm_stream);
   GB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
   if (op->overlap_comms) {
-    run(1, ctx->stream);                                   // interior legs while the faces travel
+    if (!dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream))
+      run(1, ctx->stream);                                 // interior legs while the faces travel
     GB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
     run(2, ctx->stream);                                   // exterior legs
   } else {

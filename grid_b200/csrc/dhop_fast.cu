@@ -1,0 +1,56 @@
+// dhop_fast.cu -- instantiations + launcher of the tuned fp32 hopping kernel (see dhop_fast.cuh)
+#include "dhop_fast.cuh"
+#include "fermop.hpp"
+
+namespace gb {
+
+static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
+
+template <int LS> static void launch_ls(const FastArgs &a, int nparity, int dag, int interior, cudaStream_t st) {
+  dim3 grid((a.V4cb + FAST_NSITE - 1) / FAST_NSITE, nparity);
+  const int threads = FAST_NSITE * LS;
+  if (!dag) { if (interior) dhop_fast_kernel<LS, 0, 1><<<grid, threads, 0, st>>>(a); else dhop_fast_kernel<LS, 0, 0><<<grid, threads, 0, st>>>(a); }
+  else { if (interior) dhop_fast_kernel<LS, 1, 1><<<grid, threads, 0, st>>>(a); else dhop_fast_kernel<LS, 1, 0><<<grid, threads, 0, st>>>(a); }
+}
+
+// returns false when the configuration is not covered by the fast path (caller falls back to dhop_kernel)
+bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
+                      const void *const ax[2], double axa, double axb, int interior, cudaStream_t st) {
+  const gb_grid *g = op->grid;
+  if (op->prec != GB_F32 || op->disable_fast) return false;
+  const int Ls = op->Ls;
+  if (!(Ls == 8 || Ls == 12 || Ls == 16 || Ls == 24 || Ls == 32)) return false;
+  if (g->V4cb % FAST_NSITE) return false;
+  FastArgs a;
+  const size_t per_parity = (size_t)g->V4cb * 8 * 5;
+  for (int p = 0; p < 2; p++) {
+    a.in[p] = (const float4 *)in[p]; a.out[p] = (float4 *)out[p];
+    a.U[p] = (const float4 *)op->Uds + p * per_parity;
+    a.axpy[p] = ax ? (const float4 *)ax[p] : nullptr;
+  }
+  a.axpy_a = (float)axa; a.axpy_b = (float)axb;
+  a.comm_dim_mask = interior ? op->comm_dim_mask : 0;
+  a.Lxh = g->ldims[0] / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
+  a.ibx = gcd_int(a.Lxh, 4); a.iby = gcd_int(a.Ly, 4);
+  int bz = op->Bz <= 0 ? a.Lz : op->Bz;
+  if (bz > a.Lz) bz = a.Lz;
+  while (a.Lz % bz) bz--;
+  a.Bz = bz;
+  a.dibx = FastDiv(a.ibx); a.diby = FastDiv(a.iby); a.dNxo = FastDiv(a.Lxh / a.ibx); a.dNyo = FastDiv(a.Ly / a.iby);
+  a.dBz = FastDiv(a.Bz); a.dLt = FastDiv(a.Lt);
+  a.V4cb = (uint32_t)g->V4cb;
+  a.first_parity = parity_out_first;
+  a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
+  switch (Ls) {
+  case 8: launch_ls<8>(a, nparity, dag, interior, st); break;
+  case 12: launch_ls<12>(a, nparity, dag, interior, st); break;
+  case 16: launch_ls<16>(a, nparity, dag, interior, st); break;
+  case 24: launch_ls<24>(a, nparity, dag, interior, st); break;
+  default: launch_ls<32>(a, nparity, dag, interior, st); break;
+  }
+  count_launch(op->ctx);
+  check_launch(op->ctx, "dhop_fast");
+  return true;
+}
+
+} // namespace gb

@@ -273,6 +273,10 @@ int gb_op_set_tiling(gb_fermop *op, int by, int bz, int bt) {
   op->By = by; op->Bz = bz; op->Bt = bt;
   return GB_OK;
 }
+int gb_op_set_fast_kernel(gb_fermop *op, int enable) {
+  op->disable_fast = enable == 0;
+  return GB_OK;
+}
 int gb_op_set_overlap(gb_fermop *op, int overlap) {
   op->overlap_comms = overlap != 0;
   return GB_OK;

@@ -18,6 +18,7 @@ struct gb_fermop {
   // multi-GPU halos (ref: CartesianStencil u_send_buf/u_recv_buf, Stencil.h:839-848)
   int comm_dim_mask = 0;
   bool overlap_comms = true;
+  bool disable_fast = false;   // force the generic kernel (tests compare the two)
   bool halo_ready = false;
   void *halo_send[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *halo_recv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -31,6 +32,9 @@ namespace gb {
 void op_import_gauge(gb_fermop *op, const gb_gauge *Umu);
 void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                  const void *const ax[2], double axa, double axb);
+
+bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
+                      const void *const ax[2], double axa, double axb, int interior, cudaStream_t st);
 
 // 5D s-direction kernels (cayley.cu).  All operate on `nparity` parity blocks of nblk blocks each.
 // chi = diag_s*phi_s + upper_s*P(-/+)psi_{s+1} + lower_s*P(+/-)psi_{s-1} [+ alpha*w]

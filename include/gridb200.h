@@ -169,6 +169,8 @@ int gb_op_set_tiling(gb_fermop *op, int block_y, int block_z, int block_t);
 /* 1 (default): interior kernel overlaps the face exchange (ref: --comms-overlap, WilsonFermion5DImplementation.h:320-384);
  * 0: exchange then compute (ref: DhopInternalSerialComms, :388-411) */
 int gb_op_set_overlap(gb_fermop *op, int overlap);
+/* 1 (default): fp32 operators use the tuned FFMA2 + TMA kernel where it applies; 0: always the generic kernel */
+int gb_op_set_fast_kernel(gb_fermop *op, int enable);
 
 /* ---------------------------------------------------------------- solvers
  * ConjugateGradient on SchurDiagMooeeOperator(op).HermOp, fused device path.

@@ -182,6 +182,32 @@ def test_dhop_tiling_invariance(setup, tiling):
     assert np.array_equal(o1.export_lex(), o2.export_lex())
 
 
+@pytest.mark.parametrize("dag", [0, 1])
+def test_fast_and_generic_kernels_agree(setup, dag):
+    """fp32: the tuned FFMA2/TMA kernel (where it applies) and the generic kernel both match the oracle"""
+    prec = gb.F32
+    h = setup.host(14, prec)
+    fin, o_fast, o_gen = setup.field(prec).import_lex(h), setup.field(prec), setup.field(prec)
+    op = setup.dev[prec]
+    op.Dhop(fin, o_fast, dag)
+    op.set_fast_kernel(False)
+    op.Dhop(fin, o_gen, dag)
+    op.set_fast_kernel(True)
+    ref = setup.oracle[gb.F64].apply(po.OP_DHOP, h.astype(np.complex128), dag=dag)
+    assert site_rel_err(o_fast.export_lex(), ref) < TOL_HOP[prec]
+    assert site_rel_err(o_gen.export_lex(), ref) < TOL_HOP[prec]
+    assert site_rel_err(o_fast.export_lex(), o_gen.export_lex()) < 2 * TOL_HOP[prec]
+    # DW = Dhop + (4-M5): exercises the fused axpy epilogue of both kernels
+    if setup.kind != "wilson":
+        op.DW(fin, o_fast, dag)
+        op.set_fast_kernel(False)
+        op.DW(fin, o_gen, dag)
+        op.set_fast_kernel(True)
+        refdw = setup.oracle[gb.F64].apply(po.OP_DW, h.astype(np.complex128), dag=dag)
+        assert site_rel_err(o_fast.export_lex(), refdw) < TOL_HOP[prec]
+        assert site_rel_err(o_gen.export_lex(), refdw) < TOL_HOP[prec]
+
+
 # ------------------------------------------------------------------ operator entry points
 FULL_OPS = [("M", po.OP_M), ("Mdag", po.OP_MDAG)]
 HALF_OPS = [("Meooe", po.OP_MEOOE), ("MeooeDag", po.OP_MEOOE_DAG), ("Mooee", po.OP_MOOEE), ("MooeeDag", po.OP_MOOEE_DAG),
