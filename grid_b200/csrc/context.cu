@@ -92,7 +92,12 @@ int gb_context_create(int device, gb_context **out) {
   GB_CUDA(cudaGetDeviceProperties(&prop, device));
   c->sm_count = prop.multiProcessorCount;
   GB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  GB_CUDA(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+  {
+    // the halo stream outranks the compute stream so that exchange kernels are scheduled ahead of queued interior CTAs
+    int lo = 0, hi = 0;
+    GB_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GB_CUDA(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+  }
   GB_CUDA(cudaEventCreate(&c->ev_start));
   GB_CUDA(cudaEventCreate(&c->ev_stop));
   GB_CUDA(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));

@@ -91,14 +91,21 @@ __global__ void __launch_bounds__(256) dhop_kernel(const DhopArgs a) {
   SiteCtx<T> c;
   uint32_t r, yl, zl, tl, yh, zh, th, s, xh;
   a.dLs.divmod(q, r, s);
-  a.dLxh.divmod(r, r, xh);
-  a.dBy.divmod(r, r, yl);
-  a.dBz.divmod(r, r, zl);
-  a.dBt.divmod(r, r, tl);
-  a.dNy.divmod(r, r, yh);
-  a.dNz.divmod(r, th, zh);
-  c.s = s; c.xh = xh;
-  c.y = yh * a.By + yl; c.z = zh * a.Bz + zl; c.t = th * a.Bt + tl;
+  c.s = s;
+  if (a.box_on) {
+    uint32_t y, z, t;
+    a.dbe0.divmod(r, r, xh); a.dbe1.divmod(r, r, y); a.dbe2.divmod(r, t, z);
+    c.xh = a.bo[0] + xh; c.y = a.bo[1] + y; c.z = a.bo[2] + z; c.t = a.bo[3] + t;
+  } else {
+    a.dLxh.divmod(r, r, xh);
+    a.dBy.divmod(r, r, yl);
+    a.dBz.divmod(r, r, zl);
+    a.dBt.divmod(r, r, tl);
+    a.dNy.divmod(r, r, yh);
+    a.dNz.divmod(r, th, zh);
+    c.xh = xh;
+    c.y = yh * a.By + yl; c.z = zh * a.Bz + zl; c.t = th * a.Bt + tl;
+  }
   c.site = c.xh + a.Lxh * (c.y + a.Ly * (c.z + a.Lz * c.t));
   c.pb = (p + a.origin_parity + c.y + c.z + c.t) & 1;
 
@@ -433,10 +440,35 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   for (int i = 0; i < 8; i++) a.halo[i] = nullptr;
   for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = 0;
   a.mode = 0;
+  a.box_on = 0;
 
   auto run = [&](int mode, cudaStream_t st) {
     if (op->prec == GB_F32) launch_dhop_T<float>(op, a, nparity, dag, mode, st);
     else launch_dhop_T<double>(op, a, nparity, dag, mode, st);
+  };
+  // exterior pass: only the surface slabs, as disjoint boxes (ref: st.surface_list, Stencil.h:664-686)
+  auto run_exterior = [&](cudaStream_t st) {
+    int lo[4] = {0, 0, 0, 0}, hi[4] = {a.Lxh, a.Ly, a.Lz, a.Lt};
+    const uint32_t n5_full = a.n5cb;
+    for (int d = 3; d >= 0; d--) {
+      if (!((op->comm_dim_mask >> d) & 1)) continue;
+      for (int side = 0; side < 2; side++) {
+        int blo[4] = {lo[0], lo[1], lo[2], lo[3]}, bhi[4] = {hi[0], hi[1], hi[2], hi[3]};
+        if (side == 0) bhi[d] = lo[d] + 1; else blo[d] = hi[d] - 1;
+        if (bhi[d] - blo[d] <= 0 || (side == 1 && hi[d] - lo[d] == 1)) continue;
+        a.box_on = 1;
+        uint64_t vol = 1;
+        for (int k = 0; k < 4; k++) { a.bo[k] = blo[k]; a.be[k] = bhi[k] - blo[k]; vol *= a.be[k]; }
+        if (vol == 0) continue;
+        a.dbe0 = FastDiv(a.be[0]); a.dbe1 = FastDiv(a.be[1]); a.dbe2 = FastDiv(a.be[2]);
+        a.n5cb = (uint32_t)(vol * op->Ls);
+        run(2, st);
+      }
+      lo[d] += 1; hi[d] -= 1;
+      if (hi[d] <= lo[d]) break;
+    }
+    a.box_on = 0;
+    a.n5cb = n5_full;
   };
   if (!op->comm_dim_mask) {
     if (!dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 0, ctx->stream)) run(0, ctx->stream);
@@ -455,6 +487,12 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   }
   // make sure previous consumers of the send/recv buffers are done (StencilBarrier analogue):
   // everything is stream ordered on ctx->stream, and the comm stream waits on the pack event.
+  static const bool profile = getenv("GB_PROFILE") != nullptr;
+  static cudaEvent_t pe[6];
+  static double pacc[5];
+  static int pcount = 0;
+  if (profile && pcount == 0) for (auto &e : pe) GB_CUDA(cudaEventCreate(&e));
+  if (profile) GB_CUDA(cudaEventRecord(pe[0], ctx->stream));
   for (int j = 0; j < nparity; j++) {
     const int po = parity_out_first ^ j, ip = 1 - po;
     const int slot = nparity == 1 ? 0 : ip;
@@ -462,17 +500,36 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
     else { if (dag) launch_pack<double, 1>(op, in[ip], ip, slot, ctx->stream); else launch_pack<double, 0>(op, in[ip], ip, slot, ctx->stream); }
   }
   GB_CUDA(cudaEventRecord(ctx->ev_comp, ctx->stream));
+  if (profile) GB_CUDA(cudaEventRecord(pe[1], ctx->stream));
   GB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comp, 0));
+  if (profile) GB_CUDA(cudaEventRecord(pe[4], ctx->comm_stream));
   exchange_halos(op, nparity, ctx->comm_stream);
   GB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+  if (profile) GB_CUDA(cudaEventRecord(pe[5], ctx->comm_stream));
   if (op->overlap_comms) {
     if (!dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream))
       run(1, ctx->stream);                                 // interior legs while the faces travel
+    if (profile) GB_CUDA(cudaEventRecord(pe[2], ctx->stream));
     GB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
-    run(2, ctx->stream);                                   // exterior legs
+    run_exterior(ctx->stream);                             // exterior legs, surface slabs only
   } else {
+    if (profile) GB_CUDA(cudaEventRecord(pe[2], ctx->stream));
     GB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
     run(0, ctx->stream);
+  }
+  if (profile) {
+    GB_CUDA(cudaEventRecord(pe[3], ctx->stream));
+    GB_CUDA(cudaEventSynchronize(pe[3]));
+    GB_CUDA(cudaEventSynchronize(pe[5]));
+    float ms;
+    cudaEventElapsedTime(&ms, pe[0], pe[1]); pacc[0] += ms;
+    cudaEventElapsedTime(&ms, pe[1], pe[2]); pacc[1] += ms;
+    cudaEventElapsedTime(&ms, pe[2], pe[3]); pacc[2] += ms;
+    cudaEventElapsedTime(&ms, pe[4], pe[5]); pacc[3] += ms;
+    cudaEventElapsedTime(&ms, pe[0], pe[3]); pacc[4] += ms;
+    if (++pcount % 50 == 0 && ctx->rank == 0)
+      fprintf(stderr, "[gb profile] calls %d: pack %.4f interior %.4f wait+exterior %.4f | exchange(comm stream) %.4f | total %.4f ms\n", pcount,
+              pacc[0] / pcount, pacc[1] / pcount, pacc[2] / pcount, pacc[3] / pcount, pacc[4] / pcount);
   }
 }
 

@@ -31,6 +31,10 @@ struct DhopArgs {
   int By, Bz, Bt;      // rasterisation block extents (divide Ly, Lz, Lt)
   FastDiv dLs, dLxh, dBy, dBz, dBt, dNy, dNz;
   uint32_t n5cb;       // V4cb * Ls
+  // optional sub-box (exterior pass over one surface slab): cb coordinates (xh,y,z,t) in [bo, bo+be)
+  int box_on;
+  int bo[4], be[4];
+  FastDiv dbe0, dbe1, dbe2;
   int first_parity;    // output parity handled by blockIdx.y == 0
   int origin_parity;
 };

@@ -1,0 +1,105 @@
+"""Multi-GPU parity check, launched one rank per GPU:
+   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29533 scripts/mgpu_check.py
+Every rank builds the same global fields from fixed seeds, imports its local block, runs the decomposed operators
+(halo pack + NCCL exchange + interior/exterior kernels) and compares with the CPU oracle on the GLOBAL lattice."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import torch.distributed as dist
+import grid_b200 as gb
+from grid_b200 import synthetic as syn, decomp
+from oracle import pyoracle as po
+
+rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lrank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", lrank))
+ctx = gb.Context(lrank)
+uid = [gb.Context.unique_id() if rank == 0 else None]
+dist.broadcast_object_list(uid, src=0)
+ctx.comm_init(rank, world, uid[0])
+
+MPIS = {2: [(1, 1, 1, 2), (2, 1, 1, 1), (1, 2, 1, 1)], 4: [(1, 1, 2, 2), (2, 2, 1, 1)], 8: [(1, 1, 2, 4), (2, 2, 2, 1)]}[world]
+fails = []
+
+
+def site_err(a, b):
+    a = a.reshape(a.shape[0], -1).astype(np.complex128); b = b.reshape(b.shape[0], -1).astype(np.complex128)
+    return float(np.max(np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)))
+
+
+def check(name, err, tol):
+    t = torch.tensor([err], dtype=torch.float64, device=f"cuda:{lrank}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ok = t.item() < tol
+    if rank == 0:
+        print(f"{'ok  ' if ok else 'FAIL'} {name}: max site err {t.item():.3e} (tol {tol:.0e})", flush=True)
+    if not ok:
+        fails.append(name)
+
+
+for mpi in MPIS:
+    ld = (4, 4, 4, 4) if world < 8 else (4, 4, 4, 4)
+    gdims = tuple(l * m for l, m in zip(ld, mpi))
+    gdims = tuple(max(g, 8) if m > 1 else g for g, m in zip(gdims, mpi))
+    for Ls, kind in ((16, "dwf"), (6, "mobius"), (1, "wilson")):
+        U = syn.hot_gauge(gdims, seed=3)
+        src = syn.random_fermion(gdims, Ls, seed=4)
+        grid = gb.GridCartesian(ctx, gdims, mpi)
+        for prec, tol in ((gb.F32, 1e-6), (gb.F64, 1e-13)):
+            orc = po.OracleOp(0 if kind == "wilson" else 1, gdims, Ls, mass=0.1, M5=1.8, b=1.5 if kind == "mobius" else 1.0,
+                              c=0.5 if kind == "mobius" else 0.0, prec=1)
+            orc.import_gauge(U)
+            Umu = gb.LatticeGaugeField(grid, prec).import_lex(decomp.scatter(U, gdims, mpi, rank))
+            if kind == "wilson":
+                D = gb.WilsonFermion(Umu, grid, 0.1)
+            elif kind == "dwf":
+                D = gb.DomainWallFermion(Umu, grid, Ls, 0.1, 1.8)
+            else:
+                D = gb.MobiusFermion(Umu, grid, Ls, 0.1, 1.8, 1.5, 0.5)
+            fin = gb.LatticeFermion(grid, Ls, prec).import_lex(decomp.scatter(src, gdims, mpi, rank, inner=Ls).astype(gb._cdtype(prec)))
+            out = gb.LatticeFermion(grid, Ls, prec)
+            for overlap in (True, False):
+                D.set_overlap(overlap)
+                for dag in (0, 1):
+                    D.Dhop(fin, out, dag)
+                    ref = decomp.scatter(orc.apply(po.OP_DHOP, src, dag=dag), gdims, mpi, rank, inner=Ls)
+                    check(f"mpi {mpi} {kind} Ls{Ls} prec{prec} overlap{int(overlap)} Dhop dag{dag}", site_err(out.export_lex(), ref), tol)
+            D.set_overlap(True)
+            # checkerboard hop + full operator + Schur operator
+            he, ho = gb.LatticeFermion(grid, Ls, prec, gb.HALF), gb.LatticeFermion(grid, Ls, prec, gb.HALF)
+            gb.pickCheckerboard(gb.Odd, ho, fin)
+            D.DhopEO(ho, he, 0)
+            full = gb.LatticeFermion(grid, Ls, prec).zero()
+            gb.setCheckerboard(full, he)
+            ref_e = np.zeros_like(src)
+            po.set_checkerboard(gdims, Ls, 0, ref_e, orc.apply(po.OP_DHOP_EO, po.pick_checkerboard(gdims, Ls, 1, src)))
+            refl = decomp.scatter(ref_e, gdims, mpi, rank, inner=Ls)
+            got = full.export_lex()
+            mask = np.linalg.norm(refl.reshape(refl.shape[0], -1), axis=1) > 0
+            check(f"mpi {mpi} {kind} Ls{Ls} prec{prec} DhopEO", site_err(got[mask], refl[mask]), tol)
+            D.M(fin, out)
+            check(f"mpi {mpi} {kind} Ls{Ls} prec{prec} M", site_err(out.export_lex(), decomp.scatter(orc.apply(po.OP_M, src), gdims, mpi, rank, inner=Ls)), 4 * tol)
+            # reductions are global
+            n2 = gb.norm2(fin)
+            n2ref = np.vdot(src, src).real
+            check(f"mpi {mpi} {kind} Ls{Ls} prec{prec} norm2", abs(n2 - n2ref) / n2ref, 1e-6 if prec == gb.F32 else 1e-13)
+        # CG on the decomposed lattice vs the oracle on the global lattice (fp64)
+        if kind != "wilson" or True:
+            src_o = po.pick_checkerboard(gdims, Ls, 1, src)
+            x_ref, info = orc.cg(1, src_o, 1e-8, 5000)
+            so = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF)
+            gb.pickCheckerboard(gb.Odd, so, gb.LatticeFermion(grid, Ls, gb.F64).import_lex(decomp.scatter(src, gdims, mpi, rank, inner=Ls)))
+            sol = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()
+            cg = gb.ConjugateGradient(1e-8, 5000)
+            cg(gb.SchurDiagMooeeOperator(D), so, sol)
+            ok = abs(cg.IterationsToComplete - info["iterations"]) <= max(1, 0.02 * info["iterations"])
+            if rank == 0:
+                print(f"{'ok  ' if ok else 'FAIL'} mpi {mpi} {kind} Ls{Ls} CG iterations {cg.IterationsToComplete} vs oracle {info['iterations']}, true resid {cg.TrueResidual:.3e} vs {info['true_residual']:.3e}", flush=True)
+            if not ok:
+                fails.append("cg")
+dist.barrier()
+if rank == 0:
+    print("MGPU_CHECK " + ("PASS" if not fails else f"FAIL {fails}"), flush=True)
+dist.destroy_process_group()
+sys.exit(1 if fails else 0)
