@@ -1,0 +1,264 @@
+// gridb200.hpp -- header-only C++ mirror of the reference's operator / solver interface over the C ABI.
+//
+// Class and method names, argument order and error behaviour (assert) follow paboyle/Grid so that drivers shaped
+// like benchmarks/Benchmark_dwf_fp32.cc and tests/Test_dwf_mixedcg_prec.cc compile against this header with only
+// the include and the namespace changed.  Everything here is a thin veneer: all arithmetic happens in
+// libgridb200.so (hand-written sm_100a CUDA).  "ref:" paths are relative to the reference tree.
+#pragma once
+#include "gridb200.h"
+#include <cassert>
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <memory>
+#include <vector>
+
+namespace gridb200 {
+
+typedef double RealD;
+typedef std::complex<double> ComplexD;
+typedef int Integer;
+enum { Even = 0, Odd = 1 };
+enum { DaggerNo = 0, DaggerYes = 1 };
+typedef std::vector<int> Coordinate;
+
+#define GB_ASSERT_OK(expr)                                                              \
+  do {                                                                                  \
+    int _rc = (expr);                                                                   \
+    if (_rc != GB_OK) { std::fprintf(stderr, "gridb200: %s -> %s\n", #expr, gb_last_error()); assert(_rc == GB_OK); std::abort(); } \
+  } while (0)
+
+// ---- Grid_init analogue (ref: Grid/util/Init.cc:300-560): one context per process / GPU
+class Runtime {
+public:
+  static gb_context *&ctx() { static gb_context *c = nullptr; return c; }
+  static void init(int device = 0) { if (!ctx()) GB_ASSERT_OK(gb_context_create(device, &ctx())); }
+  static void finalize() { if (ctx()) { gb_context_destroy(ctx()); ctx() = nullptr; } }
+};
+inline void Grid_init(int * /*argc*/, char *** /*argv*/, int device = 0) { Runtime::init(device); }
+inline void Grid_finalize() { Runtime::finalize(); }
+
+// ---- grids (ref: Grid/cartesian/Cartesian_base.h, Cartesian_red_black.h, qcd/utils/SpaceTimeGrid.cc:36-78)
+class GridBase {
+public:
+  gb_grid *h = nullptr;
+  int Ls = 1;          // 1 for four-dimensional grids
+  bool redblack = false;
+  std::shared_ptr<gb_grid> owner;
+  Coordinate dims, mpi;
+  int64_t gSites() const { int64_t v = Ls; for (int d : dims) v *= d; return redblack ? v / 2 : v; }
+};
+typedef GridBase GridCartesian;
+typedef GridBase GridRedBlackCartesian;
+struct SpaceTimeGrid {
+  static GridCartesian *makeFourDimGrid(const Coordinate &latt, const Coordinate & /*simd*/, const Coordinate &mpi) {
+    Runtime::init();
+    GridBase *g = new GridBase();
+    gb_grid *raw = nullptr;
+    GB_ASSERT_OK(gb_grid_create(Runtime::ctx(), latt.data(), mpi.data(), &raw));
+    g->owner = std::shared_ptr<gb_grid>(raw, [](gb_grid *p) { gb_grid_destroy(p); });
+    g->h = raw; g->dims = latt; g->mpi = mpi;
+    return g;
+  }
+  static GridRedBlackCartesian *makeFourDimRedBlackGrid(const GridCartesian *g4) { GridBase *g = new GridBase(*g4); g->redblack = true; return g; }
+  static GridCartesian *makeFiveDimGrid(int Ls, const GridCartesian *g4) { GridBase *g = new GridBase(*g4); g->Ls = Ls; return g; }
+  static GridRedBlackCartesian *makeFiveDimRedBlackGrid(int Ls, const GridCartesian *g4) { GridBase *g = new GridBase(*g4); g->Ls = Ls; g->redblack = true; return g; }
+};
+
+// ---- lattice containers (ref: Grid/lattice/Lattice_base.h); Prec = GB_F32 / GB_F64
+template <gb_precision Prec> class LatticeFermionT {
+public:
+  gb_fermion *h = nullptr;
+  GridBase *_grid;
+  explicit LatticeFermionT(GridBase *g) : _grid(g) { GB_ASSERT_OK(gb_fermion_create(g->h, g->Ls, Prec, g->redblack ? GB_HALF : GB_FULL, &h)); }
+  LatticeFermionT(const LatticeFermionT &o) : _grid(o._grid) {
+    GB_ASSERT_OK(gb_fermion_create(_grid->h, _grid->Ls, Prec, _grid->redblack ? GB_HALF : GB_FULL, &h));
+    GB_ASSERT_OK(gb_copy(h, o.h));
+  }
+  LatticeFermionT &operator=(const LatticeFermionT &o) { GB_ASSERT_OK(gb_copy(h, o.h)); return *this; }
+  ~LatticeFermionT() { gb_fermion_destroy(h); }
+  GridBase *Grid() const { return _grid; }
+  int Checkerboard() const { return gb_fermion_checkerboard(h); }
+  void SetCheckerboard(int cb) { gb_fermion_set_checkerboard_tag(h, cb); } // Grid: f.Checkerboard() = cb
+  void Zero() { GB_ASSERT_OK(gb_zero(h)); }
+  // import/export of the local lattice in lexicographic order (ref: Lattice_transfer.h:1123,1218)
+  void ImportLex(const void *host, gb_precision hp) { GB_ASSERT_OK(gb_fermion_import(h, host, hp)); }
+  void ExportLex(void *host, gb_precision hp) const { GB_ASSERT_OK(gb_fermion_export(h, host, hp)); }
+};
+typedef LatticeFermionT<GB_F32> LatticeFermionF;
+typedef LatticeFermionT<GB_F64> LatticeFermionD;
+
+template <gb_precision Prec> class LatticeGaugeFieldT {
+public:
+  gb_gauge *h = nullptr;
+  GridBase *_grid;
+  explicit LatticeGaugeFieldT(GridBase *g) : _grid(g) { GB_ASSERT_OK(gb_gauge_create(g->h, Prec, &h)); }
+  ~LatticeGaugeFieldT() { gb_gauge_destroy(h); }
+  LatticeGaugeFieldT(const LatticeGaugeFieldT &) = delete;
+  void ImportLex(const void *host, gb_precision hp) { GB_ASSERT_OK(gb_gauge_import(h, host, hp)); }
+  void ExportLex(void *host, gb_precision hp) const { GB_ASSERT_OK(gb_gauge_export(h, host, hp)); }
+};
+typedef LatticeGaugeFieldT<GB_F32> LatticeGaugeFieldF;
+typedef LatticeGaugeFieldT<GB_F64> LatticeGaugeFieldD;
+
+// ---- RNG facade: synthetic fields are generated on the device, keyed by global site (decomposition independent)
+class GridParallelRNG {
+public:
+  uint64_t seed = 0;
+  explicit GridParallelRNG(GridBase *) {}
+  void SeedFixedIntegers(const std::vector<int> &s) { seed = 0; for (int v : s) seed = seed * 1000003ull + (uint64_t)v; }
+};
+template <gb_precision P> void random(GridParallelRNG &rng, LatticeFermionT<P> &f) { GB_ASSERT_OK(gb_fermion_random(f.h, rng.seed)); }
+template <int Nc> struct SU {
+  template <gb_precision P> static void HotConfiguration(GridParallelRNG &rng, LatticeGaugeFieldT<P> &U) { GB_ASSERT_OK(gb_gauge_random(U.h, rng.seed)); }
+  template <gb_precision P> static void ColdConfiguration(LatticeGaugeFieldT<P> &U) { GB_ASSERT_OK(gb_gauge_unit(U.h)); }
+};
+
+// ---- lattice algebra (ref: Lattice_arith.h:231-258, Lattice_reduction.h:256-372, Lattice_transfer.h:50-86,1461-1492)
+template <gb_precision P> RealD norm2(const LatticeFermionT<P> &x) { double v; GB_ASSERT_OK(gb_norm2(x.h, &v)); return v; }
+template <gb_precision P> ComplexD innerProduct(const LatticeFermionT<P> &l, const LatticeFermionT<P> &r) { double v[2]; GB_ASSERT_OK(gb_inner_product(l.h, r.h, v)); return ComplexD(v[0], v[1]); }
+template <gb_precision P> void axpy(LatticeFermionT<P> &z, RealD a, const LatticeFermionT<P> &x, const LatticeFermionT<P> &y) { GB_ASSERT_OK(gb_axpy(z.h, a, x.h, y.h)); }
+template <gb_precision P> void axpby(LatticeFermionT<P> &z, RealD a, RealD b, const LatticeFermionT<P> &x, const LatticeFermionT<P> &y) { GB_ASSERT_OK(gb_axpby(z.h, a, b, x.h, y.h)); }
+template <gb_precision P> RealD axpy_norm(LatticeFermionT<P> &z, RealD a, const LatticeFermionT<P> &x, const LatticeFermionT<P> &y) { double v; GB_ASSERT_OK(gb_axpy_norm(z.h, a, x.h, y.h, &v)); return v; }
+template <gb_precision P> void pickCheckerboard(int cb, LatticeFermionT<P> &half, const LatticeFermionT<P> &full) { GB_ASSERT_OK(gb_pick_checkerboard(cb, half.h, full.h)); }
+template <gb_precision P> void setCheckerboard(LatticeFermionT<P> &full, const LatticeFermionT<P> &half) { GB_ASSERT_OK(gb_set_checkerboard(full.h, half.h)); }
+template <gb_precision PO, gb_precision PI> void precisionChange(LatticeFermionT<PO> &out, const LatticeFermionT<PI> &in) { GB_ASSERT_OK(gb_precision_change(out.h, in.h)); }
+// gauge precision change goes through the host layout (setup only)
+inline void precisionChange(LatticeGaugeFieldF &out, const LatticeGaugeFieldD &in) {
+  std::vector<double> tmp((size_t)in._grid->gSites() / in._grid->Ls * 72);
+  in.ExportLex(tmp.data(), GB_F64);
+  out.ImportLex(tmp.data(), GB_F64);
+}
+
+// ---- FermionOperator (ref: Grid/qcd/action/fermion/FermionOperator.h:40-192)
+template <gb_precision Prec> class FermionOperator {
+public:
+  typedef LatticeFermionT<Prec> FermionField;
+  typedef LatticeGaugeFieldT<Prec> GaugeField;
+  gb_fermop *h = nullptr;
+  virtual ~FermionOperator() { gb_op_destroy(h); }
+  void apply(int which, const FermionField &in, FermionField &out, int dag = 0) { GB_ASSERT_OK(gb_op_apply(h, which, in.h, out.h, dag)); }
+  virtual void M(const FermionField &in, FermionField &out) { apply(GB_OP_M, in, out); }
+  virtual void Mdag(const FermionField &in, FermionField &out) { apply(GB_OP_MDAG, in, out); }
+  virtual void Meooe(const FermionField &in, FermionField &out) { apply(GB_OP_MEOOE, in, out); }
+  virtual void MeooeDag(const FermionField &in, FermionField &out) { apply(GB_OP_MEOOE_DAG, in, out); }
+  virtual void Mooee(const FermionField &in, FermionField &out) { apply(GB_OP_MOOEE, in, out); }
+  virtual void MooeeDag(const FermionField &in, FermionField &out) { apply(GB_OP_MOOEE_DAG, in, out); }
+  virtual void MooeeInv(const FermionField &in, FermionField &out) { apply(GB_OP_MOOEE_INV, in, out); }
+  virtual void MooeeInvDag(const FermionField &in, FermionField &out) { apply(GB_OP_MOOEE_INV_DAG, in, out); }
+  virtual void Dhop(const FermionField &in, FermionField &out, int dag) { apply(GB_OP_DHOP, in, out, dag); }
+  virtual void DhopOE(const FermionField &in, FermionField &out, int dag) { apply(GB_OP_DHOP_OE, in, out, dag); }
+  virtual void DhopEO(const FermionField &in, FermionField &out, int dag) { apply(GB_OP_DHOP_EO, in, out, dag); }
+  virtual void ImportGauge(const GaugeField &U) { GB_ASSERT_OK(gb_op_import_gauge(h, U.h)); }
+};
+template <gb_precision Prec> class WilsonFermionT : public FermionOperator<Prec> {
+public: // ref: WilsonFermion.h:139-142
+  WilsonFermionT(LatticeGaugeFieldT<Prec> &Umu, GridCartesian &Fgrid, GridRedBlackCartesian &, RealD mass) {
+    GB_ASSERT_OK(gb_op_create_wilson(Fgrid.h, Umu.h, mass, nullptr, &this->h));
+  }
+};
+template <gb_precision Prec> class DomainWallFermionT : public FermionOperator<Prec> {
+public: // ref: DomainWallFermion.h:108-134
+  DomainWallFermionT(LatticeGaugeFieldT<Prec> &Umu, GridCartesian &FGrid, GridRedBlackCartesian &, GridCartesian &UGrid, GridRedBlackCartesian &, RealD mass, RealD M5) {
+    GB_ASSERT_OK(gb_op_create_dwf(UGrid.h, Umu.h, FGrid.Ls, mass, M5, nullptr, &this->h));
+  }
+};
+template <gb_precision Prec> class MobiusFermionT : public FermionOperator<Prec> {
+public: // ref: MobiusFermion.h:45-71
+  MobiusFermionT(LatticeGaugeFieldT<Prec> &Umu, GridCartesian &FGrid, GridRedBlackCartesian &, GridCartesian &UGrid, GridRedBlackCartesian &, RealD mass, RealD M5, RealD b, RealD c) {
+    GB_ASSERT_OK(gb_op_create_mobius(UGrid.h, Umu.h, FGrid.Ls, mass, M5, b, c, nullptr, &this->h));
+  }
+};
+typedef WilsonFermionT<GB_F32> WilsonFermionF; typedef WilsonFermionT<GB_F64> WilsonFermionD;
+typedef DomainWallFermionT<GB_F32> DomainWallFermionF; typedef DomainWallFermionT<GB_F64> DomainWallFermionD;
+typedef MobiusFermionT<GB_F32> MobiusFermionF; typedef MobiusFermionT<GB_F64> MobiusFermionD;
+
+// ---- linear operators (ref: Grid/algorithms/LinearOperator.h:44-56,286-349)
+template <class Field> class LinearOperatorBase {
+public:
+  virtual ~LinearOperatorBase() {}
+  virtual void Op(const Field &in, Field &out) = 0;
+  virtual void AdjOp(const Field &in, Field &out) = 0;
+  virtual void HermOp(const Field &in, Field &out) = 0;
+  virtual void HermOpAndNorm(const Field &in, Field &out, RealD &n1, RealD &n2) {
+    HermOp(in, out);
+    n1 = innerProduct(in, out).real();
+    n2 = norm2(out);
+  }
+  virtual gb_fermop *FusedSchurMatrix() { return nullptr; } // non-null: CG may use the fused device path
+};
+template <class Matrix, class Field> class SchurDiagMooeeOperator : public LinearOperatorBase<Field> {
+public:
+  Matrix &_Mat;
+  explicit SchurDiagMooeeOperator(Matrix &Mat) : _Mat(Mat) {}
+  virtual void Mpc(const Field &in, Field &out) { _Mat.apply(GB_OP_MPC, in, out); }
+  virtual void MpcDag(const Field &in, Field &out) { _Mat.apply(GB_OP_MPC_DAG, in, out); }
+  virtual void MpcDagMpc(const Field &in, Field &out) { _Mat.apply(GB_OP_HERMOP, in, out); }
+  void Op(const Field &in, Field &out) override { Mpc(in, out); }
+  void AdjOp(const Field &in, Field &out) override { MpcDag(in, out); }
+  void HermOp(const Field &in, Field &out) override { MpcDagMpc(in, out); }
+  gb_fermop *FusedSchurMatrix() override { return _Mat.h; }
+};
+
+// ---- solvers (ref: Grid/algorithms/iterative/ConjugateGradient.h:42-258, ConjugateGradientMixedPrec.h:34-170)
+template <class Field> class ConjugateGradient {
+public:
+  bool ErrorOnNoConverge;
+  RealD Tolerance;
+  Integer MaxIterations;
+  Integer IterationsToComplete = 0;
+  RealD TrueResidual = 0;
+  ConjugateGradient(RealD tol, Integer maxit, bool err_on_no_conv = true) : ErrorOnNoConverge(err_on_no_conv), Tolerance(tol), MaxIterations(maxit) {}
+  void operator()(LinearOperatorBase<Field> &Linop, const Field &src, Field &psi) {
+    int rc;
+    if (gb_fermop *m = Linop.FusedSchurMatrix()) {
+      rc = gb_cg_schur(m, src.h, psi.h, Tolerance, MaxIterations, &IterationsToComplete, &TrueResidual);
+    } else { // user-written LinearOperatorBase: drive its virtual HermOp through the generic path
+      Thunk t{&Linop, &src};
+      rc = gb_cg(Runtime::ctx(), &Thunk::call, &t, src.h, psi.h, Tolerance, MaxIterations, &IterationsToComplete, &TrueResidual);
+    }
+    if (rc == GB_ERR_NOT_CONVERGED) { if (ErrorOnNoConverge) assert(0 && "ConjugateGradient did NOT converge"); return; }
+    GB_ASSERT_OK(rc);
+    if (ErrorOnNoConverge) assert(TrueResidual / Tolerance < 10000.0); // ref: ConjugateGradient.h:225
+  }
+private:
+  struct Thunk {
+    LinearOperatorBase<Field> *op; const Field *like;
+    static int call(void *user, const gb_fermion *in, gb_fermion *out) {
+      Thunk *t = (Thunk *)user;
+      Borrow bi(t->like->Grid(), const_cast<gb_fermion *>(in)), bo(t->like->Grid(), out);
+      t->op->HermOp(bi.f(), bo.f());
+      return GB_OK;
+    }
+  };
+  // wraps a library-owned handle in a Field without taking ownership
+  struct Borrow {
+    alignas(Field) unsigned char buf[sizeof(Field)];
+    Borrow(GridBase *g, gb_fermion *hh) { Field *p = reinterpret_cast<Field *>(buf); p->h = hh; p->_grid = g; }
+    Field &f() { return *reinterpret_cast<Field *>(buf); }
+  };
+};
+
+template <class FieldD, class FieldF> class MixedPrecisionConjugateGradient {
+public:
+  RealD Tolerance, InnerTolerance;
+  Integer MaxInnerIterations, MaxOuterIterations;
+  GridBase *SinglePrecGrid;
+  LinearOperatorBase<FieldF> &Linop_f;
+  LinearOperatorBase<FieldD> &Linop_d;
+  Integer TotalInnerIterations = 0, TotalOuterIterations = 0, TotalFinalStepIterations = 0;
+  RealD TrueResidual = 0;
+  MixedPrecisionConjugateGradient(RealD tol, Integer maxinnerit, Integer maxouterit, GridBase *sp_grid, LinearOperatorBase<FieldF> &lf, LinearOperatorBase<FieldD> &ld)
+      : Tolerance(tol), InnerTolerance(tol), MaxInnerIterations(maxinnerit), MaxOuterIterations(maxouterit), SinglePrecGrid(sp_grid), Linop_f(lf), Linop_d(ld) {}
+  void operator()(const FieldD &src, FieldD &sol) {
+    gb_fermop *mf = Linop_f.FusedSchurMatrix(), *md = Linop_d.FusedSchurMatrix();
+    assert(mf && md && "MixedPrecisionConjugateGradient needs SchurDiagMooeeOperator arguments");
+    int it[3];
+    int rc = gb_mixed_cg_schur(mf, md, src.h, sol.h, Tolerance, MaxInnerIterations, MaxOuterIterations, it, &TrueResidual);
+    TotalInnerIterations = it[0]; TotalOuterIterations = it[1]; TotalFinalStepIterations = it[2];
+    GB_ASSERT_OK(rc);
+  }
+};
+
+} // namespace gridb200

@@ -1,0 +1,28 @@
+"""The C++ drivers shaped like the reference's own programs run to completion (their asserts are the reference's)."""
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(name, *args):
+    exe = os.path.join(ROOT, "drivers", name)
+    assert os.path.exists(exe), f"{exe} missing: run make -C grid_b200"
+    p = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def test_benchmark_dwf_fp32_driver():
+    """ref: benchmarks/Benchmark_dwf_fp32.cc -- Deo + Doe == Dunprec (assert n2e < 1e-4, :438)"""
+    out = run("Benchmark_dwf_fp32", "--grid", "8.8.8.8", "--Ls", "8", "--ncall", "10")
+    assert "norm diff" in out and "done" in out
+
+
+def test_dwf_mixedcg_prec_driver():
+    """ref: tests/Test_dwf_mixedcg_prec.cc -- |x_mixed - x_double|^2 < 1e-4 (:212-215), Ls=12 as in the reference"""
+    out = run("Test_dwf_mixedcg_prec", "--grid", "8.8.8.8", "--Ls", "12")
+    assert "Diff between mixed and regular CG" in out and "done" in out
