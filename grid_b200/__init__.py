@@ -35,7 +35,7 @@ SYMBOLS = [
     ("gb_launch_count", _i64, [_vp]), ("gb_flush_l2", _i, [_vp]),
     ("gb_comm_unique_id", _i, [_vp]), ("gb_comm_init", _i, [_vp, _i, _i, _vp]), ("gb_comm_rank", _i, [_vp, _pi, _pi]),
     ("gb_comm_global_sum", _i, [_vp, _pd, _i]), ("gb_comm_barrier", _i, [_vp]),
-    ("gb_grid_create", _i, [_vp, _pi, _pi, _pvp]), ("gb_grid_destroy", _i, [_vp]), ("gb_grid_local_dims", _i, [_vp, _pi]),
+    ("gb_grid_create", _i, [_vp, _pi, _pi, _pvp]), ("gb_geometry_query", _i, [_pi, _pi, _i, _pi, _pi, _pi]), ("gb_grid_destroy", _i, [_vp]), ("gb_grid_local_dims", _i, [_vp, _pi]),
     ("gb_grid_local_origin", _i, [_vp, _pi]),
     ("gb_fermion_create", _i, [_vp, _i, _i, _i, _pvp]), ("gb_fermion_destroy", _i, [_vp]), ("gb_fermion_checkerboard", _i, [_vp]),
     ("gb_fermion_set_checkerboard_tag", _i, [_vp, _i]), ("gb_fermion_local_sites", _i64, [_vp]),
@@ -149,6 +149,13 @@ class Context:
         if self.h:
             lib().gb_context_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def geometry_query(gdims, mpi, rank):
+    """Host-only: (ldims, origin, [(fwd, bwd)] per dimension) of `rank` -- no device needed."""
+    l, o, n = _i4([0] * 4), _i4([0] * 4), (C.c_int * 8)()
+    _chk(lib().gb_geometry_query(_i4(gdims), _i4(mpi), rank, l, o, n))
+    return tuple(l), tuple(o), [(n[2 * d], n[2 * d + 1]) for d in range(4)]
 
 
 class GridCartesian:

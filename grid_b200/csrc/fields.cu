@@ -11,6 +11,27 @@ using namespace gb;
 // =====================================================================================================
 // grids
 // =====================================================================================================
+// pure host geometry (no device needed): local extents, origin and neighbour ranks of `rank` in the processor grid
+extern "C" int gb_geometry_query(const int gdims[4], const int mpi[4], int rank, int ldims[4], int origin[4], int nbr[8]) {
+  GB_API_BEGIN
+  GB_REQUIRE(gdims && mpi && ldims && origin && nbr, "null argument");
+  int np = 1, pc[4], r = rank;
+  for (int d = 0; d < 4; d++) {
+    GB_REQUIRE(mpi[d] >= 1 && gdims[d] % mpi[d] == 0, "processor grid must divide the lattice");
+    ldims[d] = gdims[d] / mpi[d];
+    np *= mpi[d];
+  }
+  GB_REQUIRE(rank >= 0 && rank < np, "rank outside the processor grid");
+  for (int d = 0; d < 4; d++) { pc[d] = r % mpi[d]; r /= mpi[d]; origin[d] = pc[d] * ldims[d]; }
+  for (int d = 0; d < 4; d++)
+    for (int dir = 0; dir < 2; dir++) {
+      int q[4] = {pc[0], pc[1], pc[2], pc[3]};
+      q[d] = (q[d] + (dir == 0 ? 1 : mpi[d] - 1)) % mpi[d];
+      nbr[2 * d + dir] = q[0] + mpi[0] * (q[1] + mpi[1] * (q[2] + mpi[2] * q[3]));
+    }
+  GB_API_END
+}
+
 extern "C" int gb_grid_create(gb_context *ctx, const int gdims[4], const int mpi[4], gb_grid **out) {
   GB_API_BEGIN
   GB_REQUIRE(ctx && gdims && out, "null argument");

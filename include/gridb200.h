@@ -101,6 +101,9 @@ int gb_comm_barrier(gb_context *ctx);
  * makeFiveDimGrid, make*RedBlackGrid (Grid/qcd/utils/SpaceTimeGrid.cc:36-78).  The fifth dimension is never
  * decomposed (ref: WilsonFermion5DImplementation.h:80-88).  Local extents must be even. */
 int gb_grid_create(gb_context *ctx, const int gdims[4], const int mpi[4], gb_grid **out);
+/* host-only geometry of one rank: local extents, global origin, neighbour ranks nbr[2*mu + {0:forward,1:backward}]
+ * (ref: CartesianCommunicator::ShiftedRanks, Communicator_base.h) -- needs no device */
+int gb_geometry_query(const int gdims[4], const int mpi[4], int rank, int ldims[4], int origin[4], int nbr[8]);
 int gb_grid_destroy(gb_grid *g);
 int gb_grid_local_dims(const gb_grid *g, int ldims[4]);
 int gb_grid_local_origin(const gb_grid *g, int origin[4]);   /* global coordinate of local site 0 */
