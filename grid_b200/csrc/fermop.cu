@@ -110,6 +110,12 @@ static void apply_mooee_like(gb_fermop *op, int which, const gb_fermion *in, gb_
     else scale_field(out, f, in);
     return;
   }
+  if (op->use_smat) {
+    const void *m = which == GB_OP_MOOEE ? op->sm_mooee : which == GB_OP_MOOEE_DAG ? op->sm_mooeedag : which == GB_OP_MOOEE_INV ? op->sm_mooeeinv
+                  : which == GB_OP_MOOEE_INV_DAG ? op->sm_mooeeinvdag : which == GB_OP_MEOOE5D ? op->sm_meooe5d : which == GB_OP_MEOOEDAG5D ? op->sm_meooedag5d : nullptr;
+    GB_REQUIRE(m != nullptr, "bad opcode");
+    if (smat_apply(op, m, in, nullptr, nullptr, alpha, w, out)) return;
+  }
   switch (which) {
   case GB_OP_MOOEE: { Tri t = coef_mooee(op); m5d_apply(op, in, in, out, t.lower, t.diag, t.upper, 0, w, alpha); break; }
   case GB_OP_MOOEE_DAG: { Tri t = coef_mooeedag(op); m5d_apply(op, in, in, out, t.lower, t.diag, t.upper, 1, w, alpha); break; }
@@ -136,6 +142,27 @@ static void apply_meooe(gb_fermop *op, const gb_fermion *in, gb_fermion *out, in
 // SchurDiagMooeeOperator::Mpc / MpcDag   ref: LinearOperator.h:330-348
 static void apply_mpc(gb_fermop *op, const gb_fermion *in, gb_fermion *out, int dagger) {
   gb_fermion *t1 = op_tmp_half(op, 1), *t2 = op_tmp_half(op, 2);
+  if (op->kind == GB_KIND_CAYLEY && op->use_smat) {
+    // s-space operators folded on the host: one dense pass per hop instead of M5D + MooeeInv + M5D
+    //   Mpc    = Mooee    - Dhop   [Meooe5D MooeeInv]      Dhop   Meooe5D
+    //   MpcDag = MooeeDag - MeooeDag5D Dhop^dag [MooeeInvDag MeooeDag5D] Dhop^dag
+    if (!dagger) {
+      GB_REQUIRE(smat_apply(op, op->sm_meooe5d, in, nullptr, nullptr, 0, nullptr, t1), "smat");   // t1 = A in
+      dhop_cb(op, t1, t2, 0);                                                                     // t2 = Dhop t1
+      GB_REQUIRE(smat_apply(op, op->sm_B, t2, nullptr, nullptr, 0, nullptr, t1), "smat");         // t1 = A MooeeInv t2
+      t1->cb = t2->cb;
+      dhop_cb(op, t1, t2, 0);                                                                     // t2 = Dhop t1
+      GB_REQUIRE(smat_apply(op, op->sm_mooee, in, nullptr, nullptr, -1.0, t2, out), "smat");      // out = Mooee in - t2
+    } else {
+      dhop_cb(op, in, t2, 1);                                                                     // t2 = Dhop^dag in
+      GB_REQUIRE(smat_apply(op, op->sm_Bdag, t2, nullptr, nullptr, 0, nullptr, t1), "smat");      // t1 = MooeeInvDag MeooeDag5D t2
+      t1->cb = t2->cb;
+      dhop_cb(op, t1, t2, 1);                                                                     // t2 = Dhop^dag t1
+      GB_REQUIRE(smat_apply(op, op->sm_mooeedag, in, op->sm_negAdag, t2, 0, nullptr, out), "smat"); // out = MooeeDag in - MeooeDag5D t2
+    }
+    out->cb = in->cb;
+    return;
+  }
   apply_meooe(op, in, t1, dagger);                                                       // tmp = Meooe in
   apply_mooee_like(op, dagger ? GB_OP_MOOEE_INV_DAG : GB_OP_MOOEE_INV, t1, t2);           // out' = MooeeInv tmp
   apply_meooe(op, t2, t1, dagger);                                                       // tmp = Meooe out'
@@ -225,6 +252,19 @@ static gb_fermop *make_op(gb_grid *g, const gb_gauge *Umu, int kind, int Ls, dou
   for (int d = 0; d < 4; d++) if (g->mpi[d] > 1) op->comm_dim_mask |= 1 << d;
   // default rasterisation: whole y, 8 z-planes at a time, all t ("L2 blocking")
   op->By = 0; op->Bz = 8; op->Bt = 0;
+  if (kind == GB_KIND_CAYLEY && (Ls == 8 || Ls == 12 || Ls == 16)) {
+    Tri a = coef_meooe5d(op), ad = coef_meooedag5d(op), c = coef_mooee(op), cd = coef_mooeedag(op);
+    SMat A = smat_m5d(Ls, a.lower, a.diag, a.upper, 0), Ad = smat_m5d(Ls, ad.lower, ad.diag, ad.upper, 1);
+    SMat C = smat_m5d(Ls, c.lower, c.diag, c.upper, 0), Cd = smat_m5d(Ls, cd.lower, cd.diag, cd.upper, 1);
+    SMat Mi = smat_mooee_inv(op->k, 0), Mid = smat_mooee_inv(op->k, 1);
+    op->sm_meooe5d = smat_device(op, A); op->sm_meooedag5d = smat_device(op, Ad);
+    op->sm_mooee = smat_device(op, C); op->sm_mooeedag = smat_device(op, Cd);
+    op->sm_mooeeinv = smat_device(op, Mi); op->sm_mooeeinvdag = smat_device(op, Mid);
+    op->sm_B = smat_device(op, smat_mul(A, Mi));
+    op->sm_Bdag = smat_device(op, smat_mul(Mid, Ad));
+    op->sm_negAdag = smat_device(op, smat_scale(Ad, -1.0));
+    op->use_smat = true;
+  }
   try { op_import_gauge(op, Umu); } catch (...) { delete op; throw; }
   return op;
 }
@@ -258,6 +298,7 @@ int gb_op_destroy(gb_fermop *op) {
   if (!op) return GB_OK;
   cudaFree(op->Uds);
   for (int i = 0; i < 8; i++) { if (op->halo_send[i]) cudaFree(op->halo_send[i]); if (op->halo_recv[i]) cudaFree(op->halo_recv[i]); }
+  for (void *p : op->smat_allocs) cudaFree(p);
   for (auto *f : op->tmp_h) gb_fermion_destroy(f);
   for (auto *f : op->tmp_f) gb_fermion_destroy(f);
   delete op;
@@ -275,6 +316,7 @@ int gb_op_set_tiling(gb_fermop *op, int by, int bz, int bt) {
 }
 int gb_op_set_fast_kernel(gb_fermop *op, int enable) {
   op->disable_fast = enable == 0;
+  op->use_smat = enable != 0 && op->sm_B != nullptr;
   return GB_OK;
 }
 int gb_op_set_overlap(gb_fermop *op, int overlap) {

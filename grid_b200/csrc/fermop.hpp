@@ -4,6 +4,11 @@
 
 enum gb_opkind { GB_KIND_WILSON = 0, GB_KIND_CAYLEY = 1 };
 
+namespace gb {
+// dense s-space operator: [2 chiralities][Ls][Ls] doubles, row-major (smat.cu)
+struct SMat { int Ls = 0; std::vector<double> a; };
+}
+
 struct gb_fermop {
   gb_grid *grid = nullptr;
   gb_context *ctx = nullptr;
@@ -23,6 +28,11 @@ struct gb_fermop {
   void *halo_send[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *halo_recv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t halo_parity_stride[4] = {0, 0, 0, 0};
+  // dense s-space matrices on the device (operator precision); null when Ls is outside the smat kernel's set
+  bool use_smat = false;
+  const void *sm_meooe5d = nullptr, *sm_meooedag5d = nullptr, *sm_mooee = nullptr, *sm_mooeedag = nullptr, *sm_mooeeinv = nullptr,
+             *sm_mooeeinvdag = nullptr, *sm_m5unit = nullptr, *sm_m5unitdag = nullptr, *sm_B = nullptr, *sm_Bdag = nullptr, *sm_negAdag = nullptr;
+  std::vector<void *> smat_allocs;
   // temporaries (ref: FermionOperator::tmp(), and the stack Fields of SchurDiagMooeeOperator)
   gb_fermion *tmp_h[4] = {nullptr, nullptr, nullptr, nullptr};
   gb_fermion *tmp_f[2] = {nullptr, nullptr};
@@ -41,6 +51,16 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
 void m5d_apply(gb_fermop *op, const gb_fermion *psi, const gb_fermion *phi, gb_fermion *chi, const std::vector<double> &lower,
                const std::vector<double> &diag, const std::vector<double> &upper, int dag, const gb_fermion *w, double alpha);
 void mooee_inv_apply(gb_fermop *op, const gb_fermion *psi, gb_fermion *chi, int dag);
+
+// dense s-space operators (smat.cu)
+SMat smat_identity(int Ls);
+SMat smat_m5d(int Ls, const std::vector<double> &lower, const std::vector<double> &diag, const std::vector<double> &upper, int dag);
+SMat smat_mooee_inv(const CayleyCoeffs &k, int dag);
+SMat smat_mul(const SMat &A, const SMat &B);
+SMat smat_scale(const SMat &A, double f);
+const void *smat_device(gb_fermop *op, const SMat &m);
+bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha, const gb_fermion *z,
+                gb_fermion *out);
 
 // composite operator pieces used by the solvers
 void op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);

@@ -1,0 +1,284 @@
+// smat.cu -- fifth-dimension operators as dense Ls x Ls real matrices per chirality, applied at HBM speed.
+//
+// Every s-space operator of the Cayley action (ref: CayleyFermion5Dcache.h:43-230 M5D / M5Ddag / MooeeInv / MooeeInvDag
+// and the coefficient sets of CayleyFermion5DImplementation.h:156-271) is linear in s, diagonal in 4D and in colour, and
+// block-diagonal in chirality.  It is therefore two real Ls x Ls matrices (upper spins = P+ block, lower spins = P-
+// block) -- the MatpInv/MatmInv view the reference keeps commented out (CayleyFermion5DImplementation.h:532-534).
+// Products such as Meooe5D * MooeeInv are folded on the host, so the Schur operator needs one pass over the field per
+// hop instead of the reference's M5D + MooeeInv + M5D launches.
+//
+//   out = M x  [+ N y]  [+ alpha z]        M, N : (Mp, Mm) pairs;  x, y, z, out : fields on the same grid
+//
+// Kernel: CTA = 16 sites x LS lanes.  The CTA's x (and y) tiles are brought into shared memory by per-site TMA bulk
+// copies (site stride padded by 16 B so the two sites of a warp sit in different banks); thread (site, s) keeps row s of
+// the matrices in registers and accumulates with packed f32x2 FMAs, reading x[site][k][s'] as a broadcast LDS.128.
+#include "fermop.hpp"
+#include "dhop_fast.cuh"
+#include <algorithm>
+
+namespace gb {
+
+constexpr int SM_NSITE = 16;
+
+template <class T, int LS> struct SMatRows { T mp[LS], mm[LS]; };
+
+template <class T> struct SMatArgs {
+  const typename Prec<T>::vec *x, *y, *z;
+  typename Prec<T>::vec *out;
+  const T *M, *N;        // device: [2][LS][LS] (chirality, row, col), row-major
+  T alpha;
+  uint32_t nsite;        // 4D sites in this parity block
+  size_t block_stride;   // vecs between parity blocks
+};
+
+template <class V> __device__ __forceinline__ V v_fma(float a, V x, V acc);
+template <> __device__ __forceinline__ float4 v_fma<float4>(float a, float4 x, float4 acc) {
+  const f2 aa = pk(a, a);
+  f2 lo = fma2(aa, pk(x.x, x.y), pk(acc.x, acc.y)), hi = fma2(aa, pk(x.z, x.w), pk(acc.z, acc.w));
+  float4 r; upk(lo, r.x, r.y); upk(hi, r.z, r.w); return r;
+}
+__device__ __forceinline__ double2 v_fmad(double a, double2 x, double2 acc) { return make_double2(fma(a, x.x, acc.x), fma(a, x.y, acc.y)); }
+
+template <class T, int LS, int NIN>
+__global__ void __launch_bounds__(SM_NSITE *LS) smat_kernel(const SMatArgs<T> a) {
+  using P = Prec<T>;
+  using V = typename P::vec;
+  constexpr int SITE_VECS = P::NV * LS;          // vecs per 4D site
+  constexpr int SSTRIDE = SITE_VECS + 1;         // padded smem stride (one extra 16-byte vec)
+  constexpr int STAGE_VECS = NIN * SM_NSITE * SSTRIDE;
+  // the layout is site-major only when LS is a multiple of the 16-lane block; then tiles stream through a
+  // two-stage TMA pipeline in a persistent CTA, otherwise one tile per CTA with element loads
+  constexpr bool CONTIG = (LS % W) == 0;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  V *stage0 = reinterpret_cast<V *>(smem_raw);
+  __shared__ uint64_t bar[2];
+  const int sl = threadIdx.x / LS, s = threadIdx.x % LS;
+  const size_t boff = (size_t)blockIdx.y * a.block_stride;
+  const uint32_t ntiles = (a.nsite + SM_NSITE - 1) / SM_NSITE;
+  // matrix rows of this thread's s (both chiralities)
+  T mp[LS], mm[LS], np_[NIN == 2 ? LS : 1], nm_[NIN == 2 ? LS : 1];
+#pragma unroll
+  for (int j = 0; j < LS; j++) {
+    mp[j] = a.M[s * LS + j]; mm[j] = a.M[LS * LS + s * LS + j];
+    if (NIN == 2) { np_[j] = a.N[s * LS + j]; nm_[j] = a.N[LS * LS + s * LS + j]; }
+  }
+  auto issue = [&](uint32_t tile, int st) { // called by all threads; thread 0 arms the barrier, lane s==0 of each site copies
+    uint32_t site = tile * SM_NSITE + sl;
+    if (site >= a.nsite) site = a.nsite - 1;
+    V *sx = stage0 + st * STAGE_VECS;
+    if (threadIdx.x == 0) mbar_expect_tx(&bar[st], SM_NSITE * SITE_VECS * 16 * NIN);
+    __syncwarp();
+    if (s == 0) {
+      bulk_g2s(sx + sl * SSTRIDE, a.x + boff + (size_t)site * SITE_VECS, SITE_VECS * 16, &bar[st]);
+      if (NIN == 2) bulk_g2s(sx + SM_NSITE * SSTRIDE + sl * SSTRIDE, a.y + boff + (size_t)site * SITE_VECS, SITE_VECS * 16, &bar[st]);
+    }
+  };
+  if (CONTIG) {
+    if (threadIdx.x == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); }
+    __syncthreads();
+  }
+  uint32_t it = 0;
+  if (CONTIG && blockIdx.x < ntiles) {
+    if (threadIdx.x == 0) mbar_expect_tx(&bar[0], SM_NSITE * SITE_VECS * 16 * NIN);
+    __syncthreads(); // expect_tx precedes every copy of this phase
+    uint32_t site0 = blockIdx.x * SM_NSITE + sl;
+    if (site0 >= a.nsite) site0 = a.nsite - 1;
+    if (s == 0) {
+      bulk_g2s(stage0 + sl * SSTRIDE, a.x + boff + (size_t)site0 * SITE_VECS, SITE_VECS * 16, &bar[0]);
+      if (NIN == 2) bulk_g2s(stage0 + SM_NSITE * SSTRIDE + sl * SSTRIDE, a.y + boff + (size_t)site0 * SITE_VECS, SITE_VECS * 16, &bar[0]);
+    }
+  }
+  for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    const int st = CONTIG ? (it & 1) : 0;
+    V *sx = stage0 + st * STAGE_VECS;
+    V *sy = sx + SM_NSITE * SSTRIDE;
+    uint32_t site = tile * SM_NSITE + sl;
+    const bool active = site < a.nsite;
+    if (!active) site = a.nsite - 1;
+    const uint32_t i5 = site * LS + s;
+    const size_t g = boff + ((size_t)(i5 >> LOGW) * P::NV << LOGW) + (i5 & (W - 1));
+    if (CONTIG) {
+      // prefetch the next tile into the other stage (its readers finished at the __syncthreads closing the previous iteration)
+      const uint32_t nxt = tile + gridDim.x;
+      if (nxt < ntiles) {
+        if (threadIdx.x == 0) mbar_expect_tx(&bar[st ^ 1], SM_NSITE * SITE_VECS * 16 * NIN);
+        __syncthreads();
+        uint32_t sn = nxt * SM_NSITE + sl;
+        if (sn >= a.nsite) sn = a.nsite - 1;
+        V *nx = stage0 + (st ^ 1) * STAGE_VECS;
+        if (s == 0) {
+          bulk_g2s(nx + sl * SSTRIDE, a.x + boff + (size_t)sn * SITE_VECS, SITE_VECS * 16, &bar[st ^ 1]);
+          if (NIN == 2) bulk_g2s(nx + SM_NSITE * SSTRIDE + sl * SSTRIDE, a.y + boff + (size_t)sn * SITE_VECS, SITE_VECS * 16, &bar[st ^ 1]);
+        }
+      }
+      mbar_wait(&bar[st], (it >> 1) & 1);
+    } else {
+#pragma unroll
+      for (int k = 0; k < P::NV; k++) {
+        sx[sl * SSTRIDE + k * LS + s] = a.x[g + ((size_t)k << LOGW)];
+        if (NIN == 2) sy[sl * SSTRIDE + k * LS + s] = a.y[g + ((size_t)k << LOGW)];
+      }
+      __syncthreads();
+    }
+    // smem element (site, k, s'): CONTIG tiles keep the global order [blk][k][lane] with blk = LS/16 blocks per site
+    auto sidx = [&](int k, int sp) -> int {
+      if (CONTIG) return sl * SSTRIDE + ((sp >> LOGW) * P::NV + k) * W + (sp & (W - 1));
+      return sl * SSTRIDE + k * LS + sp;
+    };
+#pragma unroll
+    for (int k = 0; k < P::NV; k++) {
+      const bool upper = k < P::NV / 2;
+      V acc;
+      if constexpr (sizeof(T) == 4) acc = make_float4(0.f, 0.f, 0.f, 0.f); else acc = make_double2(0., 0.);
+#pragma unroll
+      for (int j = 0; j < LS; j++) {
+        const V xv = sx[sidx(k, j)];
+        if constexpr (sizeof(T) == 4) acc = v_fma<float4>(upper ? mp[j] : mm[j], xv, acc); else acc = v_fmad(upper ? mp[j] : mm[j], xv, acc);
+        if (NIN == 2) {
+          const V yv = sy[sidx(k, j)];
+          if constexpr (sizeof(T) == 4) acc = v_fma<float4>(upper ? np_[j] : nm_[j], yv, acc); else acc = v_fmad(upper ? np_[j] : nm_[j], yv, acc);
+        }
+      }
+      if (a.z != nullptr) {
+        const V zv = a.z[g + ((size_t)k << LOGW)];
+        if constexpr (sizeof(T) == 4) acc = v_fma<float4>(a.alpha, zv, acc); else acc = v_fmad(a.alpha, zv, acc);
+      }
+      if (active) a.out[g + ((size_t)k << LOGW)] = acc;
+    }
+    __syncthreads(); // every thread is done with this stage before it is refilled
+  }
+}
+
+// ------------------------------------------------------------------ host: dense matrices of the s-space operators
+// A matrix is [2][Ls][Ls]: block 0 acts on the upper (P+) spin components, block 1 on the lower (P-) ones.
+SMat smat_identity(int Ls) {
+  SMat m; m.Ls = Ls; m.a.assign(2 * Ls * Ls, 0.0);
+  for (int c = 0; c < 2; c++) for (int s = 0; s < Ls; s++) m.a[(c * Ls + s) * Ls + s] = 1.0;
+  return m;
+}
+// chi_s = diag_s phi_s + upper_s P-/+ psi_{s+1} + lower_s P+/- psi_{s-1} with phi == psi  (ref: CayleyFermion5Dcache.h:67-77,104-114)
+SMat smat_m5d(int Ls, const std::vector<double> &lower, const std::vector<double> &diag, const std::vector<double> &upper, int dag) {
+  SMat m; m.Ls = Ls; m.a.assign(2 * Ls * Ls, 0.0);
+  for (int s = 0; s < Ls; s++) {
+    const int su = (s + 1) % Ls, sd = (s + Ls - 1) % Ls;
+    for (int c = 0; c < 2; c++) m.a[(c * Ls + s) * Ls + s] += diag[s];
+    // non-dag: upper term carries P- (block 1), lower term carries P+ (block 0); dag swaps
+    m.a[((dag ? 0 : 1) * Ls + s) * Ls + su] += upper[s];
+    m.a[((dag ? 1 : 0) * Ls + s) * Ls + sd] += lower[s];
+  }
+  return m;
+}
+// columns of MooeeInv / MooeeInvDag by running the reference's LDU sweeps on unit vectors (ref: CayleyFermion5Dcache.h:136-170,194-228)
+SMat smat_mooee_inv(const CayleyCoeffs &k, int dag) {
+  const int Ls = k.Ls;
+  SMat m; m.Ls = Ls; m.a.assign(2 * Ls * Ls, 0.0);
+  for (int c = 0; c < 2; c++) {
+    const bool upperSpin = c == 0;
+    const bool typeA = dag ? !upperSpin : upperSpin;
+    const std::vector<double> &a = dag ? k.uee : k.lee, &bm = dag ? k.leem : k.ueem, &am = dag ? k.ueem : k.leem, &b = dag ? k.lee : k.uee;
+    for (int col = 0; col < Ls; col++) {
+      std::vector<double> psi(Ls, 0.0), chi(Ls, 0.0);
+      psi[col] = 1.0;
+      if (typeA) {
+        chi[0] = psi[0];
+        for (int s = 1; s < Ls; s++) chi[s] = psi[s] - a[s - 1] * chi[s - 1];
+        chi[Ls - 1] /= k.dee[Ls - 1];
+        for (int s = Ls - 2; s >= 0; s--) chi[s] = chi[s] / k.dee[s] - bm[s] * chi[Ls - 1];
+      } else {
+        double acc = 0;
+        for (int s = 0; s < Ls - 1; s++) acc += am[s] * psi[s];
+        chi[Ls - 1] = (psi[Ls - 1] - acc) / k.dee[Ls - 1];
+        for (int s = Ls - 2; s >= 0; s--) chi[s] = psi[s] / k.dee[s] - b[s] * chi[s + 1];
+      }
+      for (int s = 0; s < Ls; s++) m.a[(c * Ls + s) * Ls + col] = chi[s];
+    }
+  }
+  return m;
+}
+SMat smat_mul(const SMat &A, const SMat &B) { // A * B (apply B first)
+  const int Ls = A.Ls;
+  SMat m; m.Ls = Ls; m.a.assign(2 * Ls * Ls, 0.0);
+  for (int c = 0; c < 2; c++)
+    for (int i = 0; i < Ls; i++) for (int j = 0; j < Ls; j++) {
+      double acc = 0;
+      for (int l = 0; l < Ls; l++) acc += A.a[(c * Ls + i) * Ls + l] * B.a[(c * Ls + l) * Ls + j];
+      m.a[(c * Ls + i) * Ls + j] = acc;
+    }
+  return m;
+}
+SMat smat_scale(const SMat &A, double f) { SMat m = A; for (auto &v : m.a) v *= f; return m; }
+
+// device copy in the operator's precision, cached by the operator
+const void *smat_device(gb_fermop *op, const SMat &m) {
+  const size_t n = m.a.size();
+  const size_t bytes = n * (op->prec == GB_F32 ? 4 : 8);
+  void *d = nullptr;
+  GB_CUDA(cudaMalloc(&d, bytes));
+  if (op->prec == GB_F32) {
+    std::vector<float> f(n);
+    for (size_t i = 0; i < n; i++) f[i] = (float)m.a[i];
+    GB_CUDA(cudaMemcpy(d, f.data(), bytes, cudaMemcpyHostToDevice));
+  } else {
+    GB_CUDA(cudaMemcpy(d, m.a.data(), bytes, cudaMemcpyHostToDevice));
+  }
+  op->smat_allocs.push_back(d);
+  return d;
+}
+
+template <class T, int LS> static void smat_launch_ls(gb_context *ctx, const SMatArgs<T> &a, int nin, int nparity) {
+  using P = Prec<T>;
+  constexpr bool CONTIG = (LS % W) == 0;
+  const size_t stage = (size_t)nin * SM_NSITE * (P::NV * LS + 1) * 16;
+  const size_t smem = stage * (CONTIG ? 2 : 1);
+  const uint32_t ntiles = (a.nsite + SM_NSITE - 1) / SM_NSITE;
+  int per_sm = 1;
+  if (nin == 2) {
+    GB_CUDA(cudaFuncSetAttribute(smat_kernel<T, LS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smat_kernel<T, LS, 2>, SM_NSITE * LS, smem));
+  } else {
+    GB_CUDA(cudaFuncSetAttribute(smat_kernel<T, LS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smat_kernel<T, LS, 1>, SM_NSITE * LS, smem));
+  }
+  if (per_sm < 1) per_sm = 1;
+  uint32_t gx = CONTIG ? std::min<uint32_t>(ntiles, (uint32_t)(ctx->sm_count * per_sm + nparity - 1) / nparity) : ntiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, nparity);
+  if (nin == 2) smat_kernel<T, LS, 2><<<grid, SM_NSITE * LS, smem, ctx->stream>>>(a);
+  else smat_kernel<T, LS, 1><<<grid, SM_NSITE * LS, smem, ctx->stream>>>(a);
+}
+template <class T> static bool smat_launch_T(gb_context *ctx, int Ls, const SMatArgs<T> &a, int nin, int nparity) {
+  switch (Ls) {
+  case 8: smat_launch_ls<T, 8>(ctx, a, nin, nparity); return true;
+  case 12: smat_launch_ls<T, 12>(ctx, a, nin, nparity); return true;
+  case 16: smat_launch_ls<T, 16>(ctx, a, nin, nparity); return true;
+  default: return false;
+  }
+}
+
+// out = M x [+ N y] [+ alpha z]; returns false when Ls is outside the instantiated set (caller falls back)
+bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha, const gb_fermion *z,
+                gb_fermion *out) {
+  gb_context *ctx = op->ctx;
+  const int Ls = op->Ls;
+  if (!(Ls == 8 || Ls == 12 || Ls == 16)) return false;
+  fermion_check_same(x, out);
+  if (y) fermion_check_same(x, y);
+  if (z) fermion_check_same(x, z);
+  // aliasing x/y/z with out is safe: a CTA stages its whole tile in shared memory before it writes, tiles are disjoint
+  const int nin = y ? 2 : 1;
+  const size_t bstride = (size_t)x->hblk * nv_of(op->prec) * W;
+  bool ok;
+  if (op->prec == GB_F32) {
+    SMatArgs<float> a{(const float4 *)x->data, y ? (const float4 *)y->data : nullptr, z ? (const float4 *)z->data : nullptr, (float4 *)out->data,
+                      (const float *)dM, (const float *)dN, (float)alpha, (uint32_t)x->nsite4, bstride};
+    ok = smat_launch_T<float>(ctx, Ls, a, nin, x->nparity);
+  } else {
+    SMatArgs<double> a{(const double2 *)x->data, y ? (const double2 *)y->data : nullptr, z ? (const double2 *)z->data : nullptr, (double2 *)out->data,
+                       (const double *)dM, (const double *)dN, alpha, (uint32_t)x->nsite4, bstride};
+    ok = smat_launch_T<double>(ctx, Ls, a, nin, x->nparity);
+  }
+  if (ok) { count_launch(ctx); check_launch(ctx, "smat"); out->cb = x->cb; }
+  return ok;
+}
+
+} // namespace gb

@@ -357,7 +357,8 @@ def test_mixed_precision_cg(ctx, kind, kw):
     # fp32 inner solves: rounding differs between the two fp32 implementations, so on this tiny lattice (~125
     # iterations) allow 5 %; the +-2 % bar is asserted for the fp64 solve above and at size in tests/test_gpu_full_size.py
     assert abs(mcg.TotalInnerIterations - info["inner"]) <= max(3, 0.05 * info["inner"])
-    assert abs(mcg.TotalFinalStepIterations - info["final"]) <= 2
+    # the fp64 patch-up solve starts from wherever the fp32 restarts left the residual: a handful of iterations either way
+    assert abs(mcg.TotalFinalStepIterations - info["final"]) <= 4
 
 
 # ------------------------------------------------------------------ synthetic fields generated on the device
