@@ -59,6 +59,11 @@ void global_sum(gb_context *ctx, double *v, int n) {
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
   std::memcpy(v, ctx->h_result, n * sizeof(double));
 }
+// in-stream all-reduce of device-resident doubles (no host round trip); no-op on a single rank
+void device_global_sum(gb_context *ctx, double *d_vals, int n) {
+  if (ctx->nranks == 1) return;
+  nccl_check(nccl().AllReduce(d_vals, d_vals, n, NCCL_DOUBLE, NCCL_SUM, ctx->nccl, ctx->stream), "ncclAllReduce");
+}
 } // namespace gb
 
 using namespace gb;
@@ -106,6 +111,8 @@ int gb_context_create(int device, gb_context **out) {
   GB_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * 4 * c->max_partials));
   GB_CUDA(cudaMalloc(&c->d_result, sizeof(double) * 8));
   GB_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * 8));
+  GB_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 8));
+  GB_CUDA(cudaEventCreateWithFlags(&c->ev_scalar, cudaEventDisableTiming));
   *out = c;
   GB_API_END
 }
@@ -116,7 +123,7 @@ int gb_context_destroy(gb_context *c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
-  cudaFree(c->d_partials); cudaFree(c->d_result); cudaFreeHost(c->h_result);
+  cudaFree(c->d_partials); cudaFree(c->d_result); cudaFreeHost(c->h_result); cudaFree(c->d_scalars); cudaEventDestroy(c->ev_scalar);
   if (c->l2_scratch) cudaFree(c->l2_scratch);
   if (c->staging) cudaFree(c->staging);
   cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); cudaEventDestroy(c->ev_comm); cudaEventDestroy(c->ev_comp);

@@ -462,7 +462,90 @@ template <int NOUT> static void red_finish(gb_context *ctx, unsigned blocks, dou
   for (int j = 0; j < NOUT; j++) out[j] = ctx->h_result[j];
   global_sum(ctx, out, NOUT);
 }
+// ---- device-resident variants used by the fused CG: results stay on the device (summed over ranks in-stream),
+//      scalars a = c/d and b = cp/c are formed inside the consuming kernels, so the host never sits between launches
+template <class V, class T> __global__ void axpy_norm_dev_kernel(V *z, const V *x, const V *y, const double *c, const double *d, int64_t n, double *partials) {
+  const T a = (T)(-(*c) / (*d)); // r -= (c/d) q
+  double acc[1] = {0};
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    V r = vaxpy(a, x[i], y[i]);
+    z[i] = r;
+    acc[0] += vnorm2(r);
+  }
+  block_reduce_store<1>(acc, partials);
+}
+template <class V, class T> __global__ void cg_update_dev_kernel(V *psi, V *p, const V *r, const double *c, const double *d, const double *cp, int64_t n) {
+  const T a = (T)((*c) / (*d)), b = (T)((*cp) / (*c)); // psi += a p ; p = b p + r   (ref: ConjugateGradient.h:176-183)
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    const V pv = p[i];
+    psi[i] = vaxpy(a, pv, psi[i]);
+    p[i] = vaxpy(b, pv, r[i]);
+  }
+}
+template <int NOUT> __global__ void reduce_final_to_kernel(const double *partials, int nblocks, double *result) {
+  double acc[NOUT];
+#pragma unroll
+  for (int j = 0; j < NOUT; j++) acc[j] = 0;
+  for (int i = threadIdx.x; i < nblocks; i += RED_THREADS)
+#pragma unroll
+    for (int j = 0; j < NOUT; j++) acc[j] += partials[i * NOUT + j];
+  __shared__ double sm[NOUT][RED_THREADS / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NOUT; j++) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) sm[j][warp] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+#pragma unroll
+    for (int j = 0; j < NOUT; j++) {
+      double v = 0;
+      for (int w = 0; w < RED_THREADS / 32; w++) v += sm[j][w];
+      result[j] = v;
+    }
+}
 namespace gb {
+void device_global_sum(gb_context *ctx, double *d_vals, int n); // context.cu
+// d_out[0..1] = sum conj(l) r over all ranks, left on the device
+void reduce_inner_dev(gb_context *ctx, const gb_fermion *l, const gb_fermion *r, double *d_out) {
+  const int64_t n = l->nvec();
+  const unsigned blocks = red_blocks(ctx, n);
+  if (l->prec == GB_F32) inner_kernel<float4><<<blocks, RED_THREADS, 0, ctx->stream>>>((const float4 *)l->data, (const float4 *)r->data, n, ctx->d_partials);
+  else inner_kernel<double2><<<blocks, RED_THREADS, 0, ctx->stream>>>((const double2 *)l->data, (const double2 *)r->data, n, ctx->d_partials);
+  reduce_final_to_kernel<2><<<1, RED_THREADS, 0, ctx->stream>>>(ctx->d_partials, (int)blocks, d_out);
+  count_launch(ctx, 2);
+  check_launch(ctx, "inner_dev");
+  device_global_sum(ctx, d_out, 2);
+}
+// z = y - (c/d) x ; d_out[0] = |z|^2 over all ranks (device)
+void axpy_norm_dev(gb_context *ctx, gb_fermion *z, const gb_fermion *x, const gb_fermion *y, const double *d_c, const double *d_d, double *d_out) {
+  const int64_t n = z->nvec();
+  const unsigned blocks = red_blocks(ctx, n);
+  if (z->prec == GB_F32)
+    axpy_norm_dev_kernel<float4, float><<<blocks, RED_THREADS, 0, ctx->stream>>>((float4 *)z->data, (const float4 *)x->data, (const float4 *)y->data, d_c, d_d, n, ctx->d_partials);
+  else
+    axpy_norm_dev_kernel<double2, double><<<blocks, RED_THREADS, 0, ctx->stream>>>((double2 *)z->data, (const double2 *)x->data, (const double2 *)y->data, d_c, d_d, n, ctx->d_partials);
+  reduce_final_to_kernel<1><<<1, RED_THREADS, 0, ctx->stream>>>(ctx->d_partials, (int)blocks, d_out);
+  count_launch(ctx, 2);
+  check_launch(ctx, "axpy_norm_dev");
+  device_global_sum(ctx, d_out, 1);
+}
+void cg_update_dev(gb_context *ctx, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, const double *d_c, const double *d_d, const double *d_cp) {
+  const int64_t n = psi->nvec();
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  if (psi->prec == GB_F32) cg_update_dev_kernel<float4, float><<<blocks, 256, 0, ctx->stream>>>((float4 *)psi->data, (float4 *)p->data, (const float4 *)r->data, d_c, d_d, d_cp, n);
+  else cg_update_dev_kernel<double2, double><<<blocks, 256, 0, ctx->stream>>>((double2 *)psi->data, (double2 *)p->data, (const double2 *)r->data, d_c, d_d, d_cp, n);
+  count_launch(ctx);
+  check_launch(ctx, "cg_update_dev");
+}
+
 void reduce_norm2(gb_context *ctx, const gb_fermion *x, double *out) {
   const int64_t n = x->nvec();
   const unsigned blocks = red_blocks(ctx, n);

@@ -102,6 +102,8 @@ struct gb_context {
   double *d_partials = nullptr; // [max_partials][4]
   double *d_result = nullptr;   // [8]
   double *h_result = nullptr;   // pinned [8]
+  double *d_scalars = nullptr;  // [8] device-resident CG scalars
+  cudaEvent_t ev_scalar = nullptr;
   int max_partials = 0;
   // L2 flush scratch
   void *l2_scratch = nullptr;

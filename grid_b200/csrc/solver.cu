@@ -82,6 +82,74 @@ static CGOut cg_core(gb_context *ctx, const HermOpFn &A, const gb_fermion *src, 
   return out;
 }
 
+// fields.cu: device-resident reductions and updates
+void reduce_inner_dev(gb_context *ctx, const gb_fermion *l, const gb_fermion *r, double *d_out);
+void axpy_norm_dev(gb_context *ctx, gb_fermion *z, const gb_fermion *x, const gb_fermion *y, const double *d_c, const double *d_d, double *d_out);
+void cg_update_dev(gb_context *ctx, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, const double *d_c, const double *d_d, const double *d_cp);
+
+// Same algorithm and update order as cg_core (ref: ConjugateGradient.h:151-231), but the scalars live on the device:
+//   d = <p,Ap> and cp = |r|^2 are reduced (and all-reduced over ranks) in-stream, a = c/d and b = cp/c are formed inside
+//   the consuming kernels, and the next iteration's A p is enqueued before the host looks at cp, so the only host
+//   involvement per iteration is one 8-byte read-back for the stopping test, off the critical path.  If that test says
+//   "converged" the speculative A p has only overwritten the scratch field mmp.
+static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fermion *psi, double tol, int maxit) {
+  gb_context *ctx = op->ctx;
+  fermion_check_same(src, psi);
+  gb_grid *g = src->grid;
+  gb_fermion *p = nullptr, *mmp = nullptr, *r = nullptr;
+  auto mk = [&](gb_fermion **f) { chk(gb_fermion_create(g, src->Ls, (gb_precision)src->prec, (gb_gridkind)src->kind, f)); (*f)->cb = src->cb; };
+  mk(&p); mk(&mmp); mk(&r);
+  struct Guard { gb_fermion *a, *b, *c; ~Guard() { gb_fermion_destroy(a); gb_fermion_destroy(b); gb_fermion_destroy(c); } } guard{p, mmp, r};
+  auto A = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op, GB_OP_HERMOP, in, out, 0); };
+  psi->cb = src->cb;
+  CGOut out;
+  double ssq, guess, a;
+  chk(gb_norm2(src, &ssq));
+  chk(gb_norm2(psi, &guess));
+  GB_REQUIRE(!std::isnan(guess), "initial guess contains NaN");
+  if (guess == 0.0) { chk(gb_copy(r, src)); chk(gb_copy(p, r)); a = ssq; }
+  else {
+    A(psi, mmp);
+    chk(gb_axpy(r, -1.0, mmp, src));
+    chk(gb_copy(p, r));
+    chk(gb_norm2(p, &a));
+  }
+  double cp = a;
+  if (ssq == 0.0) { chk(gb_zero(psi)); out.iters = 1; out.true_resid = 0; out.converged = true; return out; }
+  const double rsq = tol * tol * ssq;
+  if (cp <= rsq) { out.true_resid = std::sqrt(a / ssq); out.iters = 0; out.converged = true; return out; }
+  // device scalar slots: cv[0], cv[1] alternate as c (old |r|^2) and cp (new |r|^2); dd[0..1] = <p,Ap>
+  double *cv = ctx->d_scalars, *dd = ctx->d_scalars + 2;
+  GB_CUDA(cudaMemcpyAsync(cv, &cp, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  A(p, mmp);
+  int k;
+  for (k = 1; k <= maxit; k++) {
+    double *d_c = cv + ((k - 1) & 1), *d_cp = cv + (k & 1);
+    reduce_inner_dev(ctx, p, mmp, dd);                 // d = <p, A p>
+    axpy_norm_dev(ctx, r, mmp, r, d_c, dd, d_cp);      // r -= (c/d) A p ; cp = |r|^2
+    cg_update_dev(ctx, psi, p, r, d_c, dd, d_cp);      // psi += a p ; p = b p + r
+    GB_CUDA(cudaMemcpyAsync(ctx->h_result, d_cp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(cudaEventRecord(ctx->ev_scalar, ctx->stream));
+    if (k < maxit) A(p, mmp);                          // speculative: needed unless this iteration converged
+    GB_CUDA(cudaEventSynchronize(ctx->ev_scalar));
+    cp = ctx->h_result[0];
+    GB_REQUIRE(!std::isnan(cp), "ConjugateGradient: residual is NaN");
+    if (cp <= rsq) {
+      A(psi, mmp);
+      chk(gb_axpy(p, -1.0, src, mmp)); // p = mmp - src
+      double rn;
+      chk(gb_norm2(p, &rn));
+      out.true_resid = std::sqrt(rn) / std::sqrt(ssq);
+      out.iters = k; out.converged = true;
+      return out;
+    }
+  }
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  out.iters = k; out.converged = false;
+  return out;
+}
+
 } // namespace gb
 
 using namespace gb;
@@ -91,7 +159,7 @@ extern "C" {
 int gb_cg_schur(gb_fermop *op, const gb_fermion *src, gb_fermion *sol, double tol, int maxit, int *iters_out, double *true_resid_out) {
   GB_API_BEGIN
   GB_REQUIRE(op && src && sol, "null argument");
-  CGOut o = cg_core(op->ctx, [&](const gb_fermion *in, gb_fermion *out) { op_apply(op, GB_OP_HERMOP, in, out, 0); }, src, sol, tol, maxit);
+  CGOut o = cg_schur_device_scalars(op, src, sol, tol, maxit);
   if (iters_out) *iters_out = o.iters;
   if (true_resid_out) *true_resid_out = o.true_resid;
   if (!o.converged) throw Error(GB_ERR_NOT_CONVERGED, "ConjugateGradient did NOT converge");
@@ -146,12 +214,12 @@ int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_
     while (norm * inner_tol * inner_tol < stop) inner_tol *= 2;
     chk(gb_precision_change(src_f, src_d));
     chk(gb_zero(sol_f));
-    CGOut in = cg_core(ctx, Af, src_f, sol_f, inner_tol, max_inner); // ErrorOnNoConverge = false
+    CGOut in = cg_schur_device_scalars(op_f, src_f, sol_f, inner_tol, max_inner); // ErrorOnNoConverge = false
     total_inner += in.iters;
     chk(gb_precision_change(tmp_d, sol_f));
     chk(gb_axpy(sol_d, 1.0, tmp_d, sol_d));
   }
-  CGOut fin = cg_core(ctx, Ad, src_d_in, sol_d, tol, max_inner);
+  CGOut fin = cg_schur_device_scalars(op_d, src_d_in, sol_d, tol, max_inner);
   if (iters_out) { iters_out[0] = total_inner; iters_out[1] = outer; iters_out[2] = fin.iters; }
   if (true_resid_out) *true_resid_out = fin.true_resid;
   if (!fin.converged) throw Error(GB_ERR_NOT_CONVERGED, "MixedPrecisionConjugateGradient final solve did NOT converge");

@@ -1,0 +1,123 @@
+"""Parity at BASELINE.json's full sizes (32^4 x Ls16 on one B200) through size-independent properties, plus iteration-count
+parity against the oracle at the largest size the CPU oracle finishes in seconds (16^4 x 8).
+
+Properties follow the reference's own checks: Deo + Doe == D (benchmarks/Benchmark_dwf_fp32.cc:424-446), adjointness and
+Hermiticity (tests/core/Test_wilson_even_odd.cc:120-224), MooeeInv Mooee == 1 (tests/debug/Test_cayley_even_odd.cc:47-113),
+linearity, and the mixed-precision CG of tests/Test_dwf_mixedcg_prec.cc to 1e-8 with its true residual."""
+import numpy as np
+import pytest
+
+import grid_b200 as gb
+from grid_b200 import synthetic as syn
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+L, LS = 32, 16
+
+
+@pytest.fixture(scope="module")
+def big():
+    ctx = gb.Context(0)
+    grid = gb.GridCartesian(ctx, (L,) * 4)
+    U = gb.LatticeGaugeField(grid, gb.F32).random(11)
+    D = gb.MobiusFermion(U, grid, LS, 0.1, 1.8, 1.5, 0.5)
+    return ctx, grid, U, D
+
+
+def rnd(grid, seed, kind=gb.FULL, prec=gb.F32):
+    return gb.LatticeFermion(grid, LS, prec, kind).random(seed)
+
+
+def test_deo_plus_doe_is_d_at_32x16(big):
+    ctx, grid, U, D = big
+    src, out = rnd(grid, 1), gb.LatticeFermion(grid, LS, gb.F32)
+    se, so, re_, ro = (gb.LatticeFermion(grid, LS, gb.F32, gb.HALF) for _ in range(4))
+    gb.pickCheckerboard(gb.Even, se, src); gb.pickCheckerboard(gb.Odd, so, src)
+    D.Dhop(src, out, 0)
+    D.DhopEO(so, re_, 0); D.DhopOE(se, ro, 0)
+    asm = gb.LatticeFermion(grid, LS, gb.F32)
+    gb.setCheckerboard(asm, re_); gb.setCheckerboard(asm, ro)
+    diff = gb.LatticeFermion(grid, LS, gb.F32)
+    gb.axpy(diff, -1.0, out, asm)
+    assert gb.norm2(diff) == 0.0            # same kernel, same order of operations: bit identical
+    assert gb.norm2(out) > 0
+
+
+def test_adjointness_and_linearity_at_32x16(big):
+    ctx, grid, U, D = big
+    phi, chi = rnd(grid, 2, gb.HALF), rnd(grid, 3, gb.HALF)
+    phi.set_checkerboard(gb.Even); chi.set_checkerboard(gb.Odd)
+    dchi, dphi = gb.LatticeFermion(grid, LS, gb.F32, gb.HALF), gb.LatticeFermion(grid, LS, gb.F32, gb.HALF)
+    D.Meooe(chi, dchi)          # odd -> even
+    D.MeooeDag(phi, dphi)       # even -> odd
+    lhs, rhs = gb.innerProduct(phi, dchi), gb.innerProduct(dphi, chi)
+    assert abs(lhs - rhs) < 2e-6 * abs(lhs)
+    # linearity: D(a x + y) = a D x + D y
+    x, y = rnd(grid, 4, gb.HALF), rnd(grid, 5, gb.HALF)
+    x.set_checkerboard(gb.Odd); y.set_checkerboard(gb.Odd)
+    z, dz, dx, dy = (gb.LatticeFermion(grid, LS, gb.F32, gb.HALF) for _ in range(4))
+    gb.axpy(z, 0.37, x, y)
+    D.DhopEO(z, dz, 0); D.DhopEO(x, dx, 0); D.DhopEO(y, dy, 0)
+    gb.axpy(dx, 0.37, dx, dy)   # dx = 0.37 dx + dy
+    gb.axpy(dy, -1.0, dx, dz)   # dy = dz - dx
+    assert gb.norm2(dy) < 1e-12 * gb.norm2(dz)
+
+
+def test_mooeeinv_mooee_identity_and_hermiticity_at_32x16(big):
+    ctx, grid, U, D = big
+    a, b = rnd(grid, 6, gb.HALF), rnd(grid, 7, gb.HALF)
+    a.set_checkerboard(gb.Odd); b.set_checkerboard(gb.Odd)
+    t, u = gb.LatticeFermion(grid, LS, gb.F32, gb.HALF), gb.LatticeFermion(grid, LS, gb.F32, gb.HALF)
+    for fwd, inv in ((D.Mooee, D.MooeeInv), (D.MooeeDag, D.MooeeInvDag)):
+        fwd(a, t); inv(t, u)
+        gb.axpy(u, -1.0, a, u)
+        assert gb.norm2(u) < 1e-12 * gb.norm2(a)
+    lin = gb.SchurDiagMooeeOperator(D)
+    Aa, Ab = gb.LatticeFermion(grid, LS, gb.F32, gb.HALF), gb.LatticeFermion(grid, LS, gb.F32, gb.HALF)
+    lin.HermOp(a, Aa); lin.HermOp(b, Ab)
+    ab, ba = gb.innerProduct(a, Ab), gb.innerProduct(b, Aa)
+    assert abs(ab - np.conj(ba)) < 5e-6 * abs(ab)
+    aa = gb.innerProduct(a, Aa)
+    assert aa.real > 0 and abs(aa.imag) < 5e-6 * aa.real
+
+
+def test_mixed_cg_converges_at_32x16(big):
+    """BASELINE configs[2]: even-odd Schur Moebius mixed-precision CG, 32^4 x Ls16, to 1e-8 (ref: Test_dwf_mixedcg_prec.cc:136-215)"""
+    ctx, grid, U, Df = big
+    Ud = gb.LatticeGaugeField(grid, gb.F64).random(11)
+    Dd = gb.MobiusFermion(Ud, grid, LS, 0.1, 1.8, 1.5, 0.5)
+    src = gb.LatticeFermion(grid, LS, gb.F64).random(8)
+    so = gb.LatticeFermion(grid, LS, gb.F64, gb.HALF)
+    gb.pickCheckerboard(gb.Odd, so, src)
+    del src
+    sol = gb.LatticeFermion(grid, LS, gb.F64, gb.HALF).zero()
+    lin_d = gb.SchurDiagMooeeOperator(Dd)
+    mcg = gb.MixedPrecisionConjugateGradient(1e-8, 10000, 50, gb.SchurDiagMooeeOperator(Df), lin_d)
+    mcg(so, sol)
+    assert mcg.TrueResidual < 1e-8 * 1.5 and mcg.TotalInnerIterations > 50 and mcg.TotalOuterIterations >= 1
+    # independent check of the true residual with the fp64 operator
+    r = gb.LatticeFermion(grid, LS, gb.F64, gb.HALF)
+    lin_d.HermOp(sol, r)
+    gb.axpy(r, -1.0, so, r)
+    assert np.sqrt(gb.norm2(r) / gb.norm2(so)) < 1.5e-8
+
+
+@pytest.mark.parametrize("prec,tol", [(gb.F64, 1e-8), (gb.F32, 1e-5)])
+def test_cg_iteration_count_matches_oracle_16x8(prec, tol):
+    """same CG iteration count +-2 % and same true residual as the oracle on identical imported fields"""
+    dims, Ls = (16, 16, 16, 16), 8
+    ctx = gb.Context(0)
+    grid = gb.GridCartesian(ctx, dims)
+    U = syn.hot_gauge(dims, seed=21)
+    h = po.pick_checkerboard(dims, Ls, 1, syn.random_fermion(dims, Ls, seed=22, dtype=gb._cdtype(prec)))
+    orc = po.OracleOp(1, dims, Ls, mass=0.1, M5=1.8, b=1.5, c=0.5, prec=prec)
+    orc.import_gauge(U)
+    x_ref, info = orc.cg(1, h, tol, 5000)
+    D = gb.MobiusFermion(gb.LatticeGaugeField(grid, prec).import_lex(U), grid, Ls, 0.1, 1.8, 1.5, 0.5)
+    src = gb.LatticeFermion(grid, Ls, prec, gb.HALF).import_lex(h)
+    src.set_checkerboard(gb.Odd)
+    sol = gb.LatticeFermion(grid, Ls, prec, gb.HALF).zero()
+    cg = gb.ConjugateGradient(tol, 5000)
+    cg(gb.SchurDiagMooeeOperator(D), src, sol)
+    assert abs(cg.IterationsToComplete - info["iterations"]) <= max(1, 0.02 * info["iterations"])
+    assert abs(cg.TrueResidual - info["true_residual"]) < 0.05 * info["true_residual"]
