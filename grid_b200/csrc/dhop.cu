@@ -85,6 +85,14 @@ template <class T, int DAG, int MODE>
 __global__ void __launch_bounds__(256) dhop_kernel(const DhopArgs a) {
   using P = Prec<T>;
   using V = typename P::vec;
+  if (MODE != 1 && a.flags != nullptr) {
+    // acquire the neighbours' epoch flags (peer-written, system scope) before touching the receive buffers
+    if (threadIdx.x < 8 && ((a.comm_dim_mask >> (threadIdx.x & 3)) & 1)) {
+      unsigned long long v;
+      do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flags + threadIdx.x) : "memory"); } while (v < a.epoch);
+    }
+    __syncthreads();
+  }
   const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= a.n5cb) return;
   const int p = a.first_parity ^ (int)blockIdx.y; // output parity
@@ -342,7 +350,7 @@ void op_import_gauge(gb_fermop *op, const gb_gauge *Umu) {
 
 // allocate halo send/recv buffers (both parities) on first use
 static void ensure_halo(gb_fermop *op) {
-  if (!op->comm_dim_mask || op->halo_ready) return;
+  if (!op->comm_dim_mask || op->halo_send[0] || op->halo_send[1] || op->halo_send[2] || op->halo_send[3]) return;
   const gb_grid *g = op->grid;
   const int hv = nv_of(op->prec) / 2;
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
@@ -441,6 +449,7 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = 0;
   a.mode = 0;
   a.box_on = 0;
+  a.flags = nullptr; a.epoch = 0;
 
   auto run = [&](int mode, cudaStream_t st) {
     if (op->prec == GB_F32) launch_dhop_T<float>(op, a, nparity, dag, mode, st);
@@ -475,7 +484,26 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
     return;
   }
 
-  // ---- multi-GPU: pack -> exchange (comm stream) || interior (compute stream) -> exterior
+  // ---- multi-GPU, peer-to-peer path: one pack+send kernel (stores into the neighbours' buffers over NVLink),
+  //      interior kernel, exterior slabs that acquire the neighbours' epoch flags on the device
+  if (p2p_setup(op)) {
+    const unsigned long long epoch = p2p_pack_send(op, in, parity_out_first, nparity, dag, ctx->stream);
+    p2p_fill_halo(op, epoch, a.halo, &a.flags);
+    a.epoch = epoch;
+    for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = op->halo_parity_stride[i];
+    if (nparity == 1) {
+      const int ip = 1 - parity_out_first;
+      for (int i = 0; i < 8; i++) if (a.halo[i]) a.halo[i] = (const char *)a.halo[i] - (size_t)ip * op->halo_parity_stride[i & 3] * 16;
+    }
+    if (op->overlap_comms) {
+      if (!dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream)) run(1, ctx->stream);
+      run_exterior(ctx->stream);
+    } else {
+      run(0, ctx->stream);
+    }
+    return;
+  }
+  // ---- multi-GPU, NCCL path: pack -> exchange (comm stream) || interior (compute stream) -> exterior
   ensure_halo(op);
   for (int i = 0; i < 8; i++) a.halo[i] = op->halo_recv[i];
   for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = op->halo_parity_stride[i];

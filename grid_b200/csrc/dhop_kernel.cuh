@@ -25,6 +25,9 @@ struct DhopArgs {
   // halo buffers for legs that leave the local volume (multi-GPU): halo[point] holds projected half spinors
   const void *halo[8];
   size_t halo_parity_stride[4]; // vecs between the parity-0 and parity-1 faces of a halo buffer
+  // peer-to-peer halos: epoch flags written by the neighbours' pack kernels (nullptr: halos already complete)
+  const unsigned long long *flags;
+  unsigned long long epoch;
   int comm_dim_mask;   // bit mu set: dimension mu is decomposed over ranks
   int mode;            // 0 = all legs (single rank or serial comms), 1 = interior legs only, 2 = exterior legs only (accumulate)
   int Ls, Lx, Lxh, Ly, Lz, Lt;

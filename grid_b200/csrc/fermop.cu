@@ -298,6 +298,7 @@ int gb_op_destroy(gb_fermop *op) {
   if (!op) return GB_OK;
   cudaFree(op->Uds);
   for (int i = 0; i < 8; i++) { if (op->halo_send[i]) cudaFree(op->halo_send[i]); if (op->halo_recv[i]) cudaFree(op->halo_recv[i]); }
+  p2p_teardown(op);
   for (void *p : op->smat_allocs) cudaFree(p);
   for (auto *f : op->tmp_h) gb_fermion_destroy(f);
   for (auto *f : op->tmp_f) gb_fermion_destroy(f);

@@ -9,6 +9,19 @@ namespace gb {
 struct SMat { int Ls = 0; std::vector<double> a; };
 }
 
+namespace gb {
+// peer-to-peer halo state (halo_p2p.cu)
+struct P2PState {
+  bool tried = false, ok = false;
+  void *recv_base = nullptr;       // [2 epochs][regions per point] + flags [2][8]
+  size_t recv_bytes = 0, pt_off[8] = {0, 0, 0, 0, 0, 0, 0, 0}, epoch_stride = 0, flags_off = 0;
+  void *peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; // mapped base of the consumer of point p
+  std::vector<void *> opened;
+  unsigned long long epoch = 0;
+  unsigned int *d_counter = nullptr;
+};
+}
+
 struct gb_fermop {
   gb_grid *grid = nullptr;
   gb_context *ctx = nullptr;
@@ -28,6 +41,7 @@ struct gb_fermop {
   void *halo_send[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *halo_recv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   size_t halo_parity_stride[4] = {0, 0, 0, 0};
+  gb::P2PState p2p;
   // dense s-space matrices on the device (operator precision); null when Ls is outside the smat kernel's set
   bool use_smat = false;
   const void *sm_meooe5d = nullptr, *sm_meooedag5d = nullptr, *sm_mooee = nullptr, *sm_mooeedag = nullptr, *sm_mooeeinv = nullptr,
@@ -45,6 +59,11 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
 
 bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                       const void *const ax[2], double axa, double axb, int interior, cudaStream_t st);
+
+bool p2p_setup(gb_fermop *op);
+void p2p_teardown(gb_fermop *op);
+unsigned long long p2p_pack_send(gb_fermop *op, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st);
+void p2p_fill_halo(gb_fermop *op, unsigned long long epoch, const void *halo[8], const unsigned long long **flags);
 
 // 5D s-direction kernels (cayley.cu).  All operate on `nparity` parity blocks of nblk blocks each.
 // chi = diag_s*phi_s + upper_s*P(-/+)psi_{s+1} + lower_s*P(+/-)psi_{s-1} [+ alpha*w]
