@@ -487,7 +487,41 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   // ---- multi-GPU, peer-to-peer path: one pack+send kernel (stores into the neighbours' buffers over NVLink),
   //      interior kernel, exterior slabs that acquire the neighbours' epoch flags on the device
   if (p2p_setup(op)) {
-    const unsigned long long epoch = p2p_pack_send(op, in, parity_out_first, nparity, dag, ctx->stream);
+    static const bool prof = getenv("GB_PROFILE") != nullptr;
+    static cudaEvent_t qe[3];
+    static double qacc[2];
+    static int qn = 0;
+    if (prof && qn == 0) for (auto &e : qe) GB_CUDA(cudaEventCreate(&e));
+    if (prof) GB_CUDA(cudaEventRecord(qe[0], ctx->stream));
+    // fully fused path: ONE launch projects + sends the faces (pack CTAs interleaved at the head of the grid), does the
+    // local legs, and surface CTAs acquire the neighbours' flags and add the off-node legs
+    const bool try_fused = op->overlap_comms && !op->no_fused && op->prec == GB_F32 && !op->disable_fast;
+    unsigned long long epoch = 0;
+    if (try_fused) {
+      epoch = p2p_next_epoch(op);
+      p2p_fill_halo(op, epoch, a.halo, &a.flags);
+      for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = op->halo_parity_stride[i];
+      const void *hb[8];
+      for (int i = 0; i < 8; i++) hb[i] = a.halo[i];
+      if (nparity == 1) {
+        const int ip = 1 - parity_out_first;
+        for (int i = 0; i < 8; i++) if (hb[i]) hb[i] = (const char *)hb[i] - (size_t)ip * op->halo_parity_stride[i & 3] * 16;
+      }
+      if (dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 2, ctx->stream, hb, a.flags, epoch)) return;
+      p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, ctx->stream); // configuration not covered: separate pack kernel
+    } else {
+      epoch = p2p_pack_send(op, in, parity_out_first, nparity, dag, ctx->stream);
+    }
+    if (prof) GB_CUDA(cudaEventRecord(qe[1], ctx->stream));
+    struct ProfEnd {
+      gb_context *ctx; bool on; cudaEvent_t *qe; double *qacc; int *qn;
+      ~ProfEnd() {
+        if (!on) return;
+        cudaEventRecord(qe[2], ctx->stream); cudaEventSynchronize(qe[2]);
+        float ms; cudaEventElapsedTime(&ms, qe[0], qe[1]); qacc[0] += ms; cudaEventElapsedTime(&ms, qe[1], qe[2]); qacc[1] += ms;
+        if (++(*qn) % 50 == 0 && ctx->rank == 0) fprintf(stderr, "[gb profile p2p] calls %d: pack+send %.4f  hop kernels %.4f ms\n", *qn, qacc[0] / *qn, qacc[1] / *qn);
+      }
+    } prof_end{ctx, prof, qe, qacc, &qn};
     p2p_fill_halo(op, epoch, a.halo, &a.flags);
     a.epoch = epoch;
     for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = op->halo_parity_stride[i];

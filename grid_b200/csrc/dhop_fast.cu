@@ -1,6 +1,7 @@
 // dhop_fast.cu -- instantiations + launcher of the tuned fp32 hopping kernel (see dhop_fast.cuh)
 #include "dhop_fast.cuh"
 #include "fermop.hpp"
+#include <algorithm>
 
 namespace gb {
 
@@ -8,14 +9,23 @@ static int gcd_int(int a, int b) { while (b) { int t = a % b; a = b; b = t; } re
 
 template <int LS> static void launch_ls(const FastArgs &a, int nparity, int dag, int interior, cudaStream_t st) {
   dim3 grid((a.V4cb + FAST_NSITE - 1) / FAST_NSITE, nparity);
+  if (interior == 2) grid = dim3(a.nhop_ctas_per_parity * nparity + a.npack_ctas, 1);
   const int threads = FAST_NSITE * LS;
-  if (!dag) { if (interior) dhop_fast_kernel<LS, 0, 1><<<grid, threads, 0, st>>>(a); else dhop_fast_kernel<LS, 0, 0><<<grid, threads, 0, st>>>(a); }
-  else { if (interior) dhop_fast_kernel<LS, 1, 1><<<grid, threads, 0, st>>>(a); else dhop_fast_kernel<LS, 1, 0><<<grid, threads, 0, st>>>(a); }
+  if (!dag) {
+    if (interior == 2) dhop_fast_kernel<LS, 0, 2><<<grid, threads, 0, st>>>(a);
+    else if (interior) dhop_fast_kernel<LS, 0, 1><<<grid, threads, 0, st>>>(a);
+    else dhop_fast_kernel<LS, 0, 0><<<grid, threads, 0, st>>>(a);
+  } else {
+    if (interior == 2) dhop_fast_kernel<LS, 1, 2><<<grid, threads, 0, st>>>(a);
+    else if (interior) dhop_fast_kernel<LS, 1, 1><<<grid, threads, 0, st>>>(a);
+    else dhop_fast_kernel<LS, 1, 0><<<grid, threads, 0, st>>>(a);
+  }
 }
 
 // returns false when the configuration is not covered by the fast path (caller falls back to dhop_kernel)
 bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
-                      const void *const ax[2], double axa, double axb, int interior, cudaStream_t st) {
+                      const void *const ax[2], double axa, double axb, int interior, cudaStream_t st, const void *const halo[8],
+                      const unsigned long long *flags, unsigned long long epoch) {
   const gb_grid *g = op->grid;
   if (op->prec != GB_F32 || op->disable_fast) return false;
   const int Ls = op->Ls;
@@ -41,6 +51,41 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.V4cb = (uint32_t)g->V4cb;
   a.first_parity = parity_out_first;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
+  for (int i = 0; i < 8; i++) a.halo[i] = halo ? (const float4 *)halo[i] : nullptr;
+  for (int i = 0; i < 4; i++) a.hstride[i] = op->halo_parity_stride[i];
+  a.flags = flags; a.epoch = epoch;
+  a.rot_z = (op->comm_dim_mask >> 2) & 1; a.rot_t = (op->comm_dim_mask >> 3) & 1;
+  if (interior == 2 && (halo == nullptr || flags == nullptr)) return false;
+  a.npack_items = 0; a.npack_ctas = 0; a.pack_ratio = 4; a.pack_counter = nullptr;
+  a.nhop_ctas_per_parity = (a.V4cb + FAST_NSITE - 1) / FAST_NSITE;
+  for (int k = 0; k < 8; k++) a.peer_flag[k] = nullptr;
+  if (interior == 2) {
+    // pack items of this hop: for every decomposed dimension, both faces, every input parity
+    P2PState &S = op->p2p;
+    const size_t eoff = (size_t)(epoch & 1) * S.epoch_stride;
+    const uint32_t cta_threads = FAST_NSITE * Ls;
+    for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+      const uint32_t nface = (uint32_t)(g->V4cb / g->ldims[mu]);
+      for (int fwd = 0; fwd < 2; fwd++) {
+        const int point = fwd ? mu : mu + 4;
+        a.peer_flag[point] = (unsigned long long *)((char *)S.peer_base[point] + S.flags_off) + (epoch & 1) * 8 + point;
+        for (int j = 0; j < nparity; j++) {
+          const int po = parity_out_first ^ j, ip = 1 - po;
+          const int slot = nparity == 1 ? 0 : ip;
+          FastArgs::PackItemF &it = a.pack[a.npack_items++];
+          it.src = (const float4 *)in[ip];
+          it.dst = (float4 *)((char *)S.peer_base[point] + eoff + S.pt_off[point] + (size_t)slot * op->halo_parity_stride[mu] * 16);
+          it.nface = nface; it.mu = mu; it.fwd = fwd; it.ip = ip;
+          it.cta_start = a.npack_ctas;
+          a.npack_ctas += (nface * (uint32_t)Ls + cta_threads - 1) / cta_threads;
+        }
+      }
+    }
+    a.pack_counter = S.d_counter;
+    // pack CTAs sit at block indices 0, ratio, 2*ratio, ...: they must all exist inside the grid
+    const uint32_t nhop_total = a.nhop_ctas_per_parity * (uint32_t)nparity;
+    a.pack_ratio = std::max<uint32_t>(1u, std::min<uint32_t>(4u, 1u + nhop_total / std::max<uint32_t>(a.npack_ctas, 1u)));
+  }
   switch (Ls) {
   case 8: launch_ls<8>(a, nparity, dag, interior, st); break;
   case 12: launch_ls<12>(a, nparity, dag, interior, st); break;

@@ -32,6 +32,19 @@ struct FastArgs {
   FastDiv dibx, diby, dNxo, dNyo, dBz, dLt;
   uint32_t V4cb;
   int first_parity, origin_parity;
+  // fused multi-GPU mode: this rank's receive buffers (this epoch), epoch flags, rasterisation rotation
+  const float4 *halo[8];
+  size_t hstride[4];               // float4 between the parity-0 and parity-1 faces
+  const unsigned long long *flags;
+  unsigned long long epoch;
+  int rot_z, rot_t;                // 1: visit coordinate (i+1) mod L at step i, so the surface planes come last
+  // fused mode: the same launch also projects this rank's boundary slices and stores them into the neighbours'
+  // receive buffers (peer-mapped).  Pack CTAs are interleaved 1-in-pack_ratio with the hop CTAs at the start of the grid.
+  struct PackItemF { const float4 *src; float4 *dst; uint32_t nface; int mu, fwd, ip; uint32_t cta_start; } pack[16];
+  int npack_items;
+  uint32_t npack_ctas, pack_ratio, nhop_ctas_per_parity;
+  unsigned int *pack_counter;
+  unsigned long long *peer_flag[8];
 };
 
 // ------------------------------------------------------------------ packed f32x2 helpers
@@ -161,14 +174,107 @@ __device__ __forceinline__ void fast_leg(const float4 *__restrict__ in, uint32_t
   recon_p<MU, SIGN>(res, Uchi);
 }
 
-// INTERIOR = 0: all legs are local (single rank).  INTERIOR = 1: skip legs that leave the local volume.
+// off-node leg of the fused mode: the neighbour rank already projected the spinor; read the half spinor it stored
+// into this rank's receive buffer (face index = checkerboard index with dimension MU removed, as in pack_body)
+template <int LS, int DAG, int MU, int FWD>
+__device__ __forceinline__ void fast_halo_leg(const FastArgs &a, const FastSite &c, int s, int ip, const float4 *Usm, SpinorP &res) {
+  constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
+  uint32_t fi;
+  if (MU == 0) fi = (uint32_t)(c.y >> 1) + (uint32_t)(a.Ly >> 1) * (c.z + a.Lz * c.t);
+  else if (MU == 1) fi = (uint32_t)c.xh + (uint32_t)a.Lxh * (c.z + a.Lz * c.t);
+  else if (MU == 2) fi = (uint32_t)c.xh + (uint32_t)a.Lxh * (c.y + a.Ly * c.t);
+  else fi = (uint32_t)c.xh + (uint32_t)a.Lxh * (c.y + a.Ly * c.z);
+  const uint32_t i = fi * LS + s;
+  const float4 *hp = a.halo[FWD ? MU : MU + 4] + (size_t)ip * a.hstride[MU] + ((size_t)(i >> LOGW) * 3 << LOGW) + (i & (W - 1));
+  HalfP chi, Uchi; LinkS u;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const float4 v = hp[k << LOGW]; chi.c[2 * k] = pk(v.x, v.y); chi.c[2 * k + 1] = pk(v.z, v.w); }
+  lds_link(u, Usm + (FWD ? MU : MU + 4) * 5);
+  mult_p(Uchi, u, chi);
+  recon_p<MU, SIGN>(res, Uchi);
+}
+
+// INTERIOR = 0: all legs are local (single rank).  INTERIOR = 1: skip legs that leave the local volume (a separate
+// exterior pass adds them).  INTERIOR = 2: fused -- local legs first, then CTAs that own surface sites acquire the
+// neighbours' epoch flags (peer-written over NVLink by pack_send_kernel) and add the off-node legs from the receive
+// buffers: one kernel does the whole decomposed hop, and the surface CTAs are rasterised last.
+// pack CTA of the fused mode: project one chunk of a boundary slice with the receiving leg's projector and store the
+// half spinors into the neighbour's receive buffer over NVLink (same indexing as pack_body in halo_p2p.cu)
+template <int LS, int DAG, int MU, int FWD>
+__device__ __forceinline__ void fast_pack(const FastArgs &a, const FastArgs::PackItemF &it, uint32_t q) {
+  const uint32_t fi = q / LS, s = q - fi * LS;
+  int xh, y, z, t;
+  const int slice = FWD ? 0 : (MU == 0 ? 2 * a.Lxh : MU == 1 ? a.Ly : MU == 2 ? a.Lz : a.Lt) - 1;
+  uint32_t r = fi;
+  if (MU == 0) {
+    int yhalf = r % (a.Ly >> 1); r /= (a.Ly >> 1); z = r % a.Lz; t = r / a.Lz;
+    int ypar = (slice + it.ip + a.origin_parity + z + t) & 1;
+    y = 2 * yhalf + ypar; xh = slice >> 1;
+  } else if (MU == 1) { xh = r % a.Lxh; r /= a.Lxh; z = r % a.Lz; t = r / a.Lz; y = slice; }
+  else if (MU == 2) { xh = r % a.Lxh; r /= a.Lxh; y = r % a.Ly; t = r / a.Ly; z = slice; }
+  else { xh = r % a.Lxh; r /= a.Lxh; y = r % a.Ly; z = r / a.Ly; t = slice; }
+  const uint32_t site = xh + a.Lxh * (y + a.Ly * (z + a.Lz * t));
+  const uint32_t i = site * LS + s;
+  constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
+  SpinorP f; HalfP h;
+  load_spinor_p(f, it.src + ((size_t)(i >> LOGW) * 6 << LOGW) + (i & (W - 1)));
+  proj_p<MU, SIGN>(h, f);
+  float4 *d = it.dst + ((size_t)(q >> LOGW) * 3 << LOGW) + (q & (W - 1));
+#pragma unroll
+  for (int k = 0; k < 3; k++) { float4 v; upk(h.c[2 * k], v.x, v.y); upk(h.c[2 * k + 1], v.z, v.w); d[k << LOGW] = v; }
+}
+
 template <int LS, int DAG, int INTERIOR>
 __global__ void __launch_bounds__(FAST_NSITE *LS, (FAST_NSITE * LS <= 256) ? 3 : 1) dhop_fast_kernel(const FastArgs a) {
   __shared__ __align__(16) float4 Usm[FAST_NSITE * FAST_USTRIDE];
   __shared__ uint64_t bar;
   const int sl = threadIdx.x / LS, s = threadIdx.x % LS;
-  const int p = a.first_parity ^ (int)blockIdx.y;
-  uint32_t r = blockIdx.x * FAST_NSITE + sl;
+  int p = a.first_parity ^ (int)blockIdx.y;
+  uint32_t hop_cta = blockIdx.x;
+  if (INTERIOR == 2) {
+    // 1D grid: [pack CTAs interleaved 1-in-ratio] + [hop CTAs of parity slot 0] + [parity slot 1]
+    const uint32_t b = blockIdx.x;
+    if (b < a.npack_ctas * a.pack_ratio && b % a.pack_ratio == 0) {
+      const uint32_t pc = b / a.pack_ratio;
+      int it = 0;
+#pragma unroll 1
+      for (int j = 1; j < a.npack_items; j++) if (pc >= a.pack[j].cta_start) it = j;
+      const FastArgs::PackItemF &item = a.pack[it];
+      const uint32_t q = (pc - item.cta_start) * (FAST_NSITE * LS) + threadIdx.x;
+      if (q < item.nface * LS) {
+        switch (item.mu * 2 + item.fwd) {
+        case 0: fast_pack<LS, DAG, 0, 0>(a, item, q); break;
+        case 1: fast_pack<LS, DAG, 0, 1>(a, item, q); break;
+        case 2: fast_pack<LS, DAG, 1, 0>(a, item, q); break;
+        case 3: fast_pack<LS, DAG, 1, 1>(a, item, q); break;
+        case 4: fast_pack<LS, DAG, 2, 0>(a, item, q); break;
+        case 5: fast_pack<LS, DAG, 2, 1>(a, item, q); break;
+        case 6: fast_pack<LS, DAG, 3, 0>(a, item, q); break;
+        default: fast_pack<LS, DAG, 3, 1>(a, item, q); break;
+        }
+      }
+      // publish: fence the peer stores; the last pack CTA writes the epoch flags into the neighbours' memory
+      __threadfence_system();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(a.pack_counter, 1u);
+        if (prev == a.npack_ctas - 1) {
+          *a.pack_counter = 0;
+          __threadfence_system();
+#pragma unroll
+          for (int k = 0; k < 8; k++)
+            if (a.peer_flag[k]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.peer_flag[k]), "l"(a.epoch) : "memory");
+        }
+      }
+      return;
+    }
+    const uint32_t before = min(a.npack_ctas, (b + a.pack_ratio - 1) / a.pack_ratio);
+    uint32_t h = b - before;
+    const uint32_t slot = h / a.nhop_ctas_per_parity;
+    hop_cta = h - slot * a.nhop_ctas_per_parity;
+    p = a.first_parity ^ (int)slot;
+  }
+  uint32_t r = hop_cta * FAST_NSITE + sl;
   const bool active = r < a.V4cb;
   if (!active) r = a.V4cb - 1;
   FastSite c;
@@ -177,17 +283,25 @@ __global__ void __launch_bounds__(FAST_NSITE *LS, (FAST_NSITE * LS <= 256) ? 3 :
     a.dibx.divmod(r, r, xl); a.diby.divmod(r, r, yl); a.dNxo.divmod(r, r, xo); a.dNyo.divmod(r, r, yo);
     a.dBz.divmod(r, r, zl); a.dLt.divmod(r, zh, t);
     c.xh = xo * a.ibx + xl; c.y = yo * a.iby + yl; c.z = zh * a.Bz + zl; c.t = t;
+    if (INTERIOR == 2) {
+      if (a.rot_z) { c.z += 1; if (c.z == a.Lz) c.z = 0; }
+      if (a.rot_t) { c.t += 1; if (c.t == a.Lt) c.t = 0; }
+    }
     c.site = c.xh + a.Lxh * (c.y + a.Ly * (c.z + a.Lz * c.t));
     c.pb = (p + a.origin_parity + c.y + c.z + c.t) & 1;
   }
-  if (threadIdx.x == 0) mbar_init(&bar, 1);
-  __syncthreads();
-  if (threadIdx.x == 0) mbar_expect_tx(&bar, FAST_NSITE * 640);
-  if (s == 0) bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)c.site * 40, 640, &bar);
   uint32_t nb[8];
   bool off[8];
   off[0] = fast_nbr<0, 0>(a, c, nb[0]); off[1] = fast_nbr<0, 1>(a, c, nb[1]); off[2] = fast_nbr<1, 0>(a, c, nb[2]); off[3] = fast_nbr<1, 1>(a, c, nb[3]);
   off[4] = fast_nbr<2, 0>(a, c, nb[4]); off[5] = fast_nbr<2, 1>(a, c, nb[5]); off[6] = fast_nbr<3, 0>(a, c, nb[6]); off[7] = fast_nbr<3, 1>(a, c, nb[7]);
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  // the barrier that publishes the mbarrier also tells every thread whether this CTA owns surface sites (fused mode),
+  // so that interior CTAs never synchronise again
+  int cta_has_off = 0;
+  if (INTERIOR == 2) cta_has_off = __syncthreads_or(off[0] | off[1] | off[2] | off[3] | off[4] | off[5] | off[6] | off[7]);
+  else __syncthreads();
+  if (threadIdx.x == 0) mbar_expect_tx(&bar, FAST_NSITE * 640);
+  if (s == 0) bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)c.site * 40, 640, &bar);
   const float4 *__restrict__ in = a.in[1 - p];
   mbar_wait(&bar, 0);
   const float4 *Us = Usm + sl * FAST_USTRIDE;
@@ -198,6 +312,20 @@ __global__ void __launch_bounds__(FAST_NSITE *LS, (FAST_NSITE * LS <= 256) ? 3 :
   GB_LEG(0, 0, 0); GB_LEG(1, 0, 1); GB_LEG(2, 1, 0); GB_LEG(3, 1, 1);
   GB_LEG(4, 2, 0); GB_LEG(5, 2, 1); GB_LEG(6, 3, 0); GB_LEG(7, 3, 1);
 #undef GB_LEG
+  if (INTERIOR == 2) {
+    if (cta_has_off) {
+      if (threadIdx.x < 8 && ((a.comm_dim_mask >> (threadIdx.x & 3)) & 1)) {
+        unsigned long long v;
+        do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flags + threadIdx.x) : "memory"); } while (v < a.epoch);
+      }
+      __syncthreads();
+      const int ip = 1 - p;
+#define GB_HLEG(I, M, F) if (off[I]) fast_halo_leg<LS, DAG, M, F>(a, c, s, ip, Us, res)
+      GB_HLEG(0, 0, 0); GB_HLEG(1, 0, 1); GB_HLEG(2, 1, 0); GB_HLEG(3, 1, 1);
+      GB_HLEG(4, 2, 0); GB_HLEG(5, 2, 1); GB_HLEG(6, 3, 0); GB_HLEG(7, 3, 1);
+#undef GB_HLEG
+    }
+  }
   if (!active) return;
   const uint32_t i = c.site * LS + s;
   const size_t offs = ((size_t)(i >> LOGW) * 6 << LOGW) + (i & (W - 1));

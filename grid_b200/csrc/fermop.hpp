@@ -1,6 +1,7 @@
 // fermop.hpp -- the FermionOperator object behind the C ABI and the internal kernel entry points.
 #pragma once
 #include "internal.hpp"
+#include <cstdlib>
 
 enum gb_opkind { GB_KIND_WILSON = 0, GB_KIND_CAYLEY = 1 };
 
@@ -37,6 +38,10 @@ struct gb_fermop {
   int comm_dim_mask = 0;
   bool overlap_comms = true;
   bool disable_fast = false;   // force the generic kernel (tests compare the two)
+  // multi-GPU: the single-launch pack+hop+halo kernel is EXPERIMENTAL (opt-in with GB_FUSED=1).  It is parity-green on small
+  // lattices but can deadlock at 32^4 per GPU: surface CTAs spinning on the neighbours' flags can fill every resident slot
+  // before the last pack CTAs of the same launch are scheduled.  Default = pack+send kernel, interior pass, exterior slabs.
+  bool no_fused = getenv("GB_FUSED") == nullptr;
   bool halo_ready = false;
   void *halo_send[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   void *halo_recv[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -58,10 +63,13 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
                  const void *const ax[2], double axa, double axb);
 
 bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
-                      const void *const ax[2], double axa, double axb, int interior, cudaStream_t st);
+                      const void *const ax[2], double axa, double axb, int interior, cudaStream_t st, const void *const halo[8] = nullptr,
+                      const unsigned long long *flags = nullptr, unsigned long long epoch = 0);
 
 bool p2p_setup(gb_fermop *op);
 void p2p_teardown(gb_fermop *op);
+unsigned long long p2p_next_epoch(gb_fermop *op);
+void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st);
 unsigned long long p2p_pack_send(gb_fermop *op, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st);
 void p2p_fill_halo(gb_fermop *op, unsigned long long epoch, const void *halo[8], const unsigned long long **flags);
 

@@ -165,12 +165,18 @@ void p2p_teardown(gb_fermop *op) {
   S.recv_base = nullptr; S.d_counter = nullptr;
 }
 
+unsigned long long p2p_next_epoch(gb_fermop *op) { return ++op->p2p.epoch; }
+
 // pack + send every face of this hop in one launch; returns the epoch the consumer must wait for
 unsigned long long p2p_pack_send(gb_fermop *op, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st) {
+  const unsigned long long epoch = p2p_next_epoch(op);
+  p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, st);
+  return epoch;
+}
+void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st) {
   P2PState &S = op->p2p;
   gb_context *ctx = op->ctx;
   const gb_grid *g = op->grid;
-  const unsigned long long epoch = ++S.epoch;
   const size_t eoff = (size_t)(epoch & 1) * S.epoch_stride;
   PackSendArgs a;
   std::memset(&a, 0, sizeof(a));
@@ -200,7 +206,6 @@ unsigned long long p2p_pack_send(gb_fermop *op, const void *const in[2], int par
   else { if (dag) pack_send_kernel<double, 1><<<grid, 256, 0, st>>>(a); else pack_send_kernel<double, 0><<<grid, 256, 0, st>>>(a); }
   count_launch(ctx);
   check_launch(ctx, "pack_send");
-  return epoch;
 }
 
 // receive-side pointers of this epoch for the hop kernels

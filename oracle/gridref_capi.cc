@@ -1,0 +1,308 @@
+// gridref_capi.cc -- C entry points over the UNMODIFIED reference (paboyle/Grid) compiled from /root/reference.
+//
+// TEST INFRASTRUCTURE ONLY (same rule as the oracle): loaded with ctypes by tests/, by the fixture generator
+// (tests/golden/make_golden.py) and by bench.py's cpu_baseline / --impl reference legs.  The product library never
+// links or dlopens it.  This file contains no reference source: it only CALLS the reference's public classes
+//   WilsonFermion / DomainWallFermion / MobiusFermion / ImprovedStaggeredFermion  (Grid/qcd/action/fermion/*.h)
+//   SchurDiagMooeeOperator / SchurStaggeredOperator                                (Grid/algorithms/LinearOperator.h)
+//   ConjugateGradient / MixedPrecisionConjugateGradient                            (Grid/algorithms/iterative/*.h)
+//   vectorizeFromLexOrdArray / unvectorizeToLexOrdArray / pick/setCheckerboard     (Grid/lattice/Lattice_transfer.h)
+// through the same host layouts the C ABI of the product uses (include/gridb200.h), so a test can feed both the
+// same bytes.  Built by oracle/Makefile.ref into oracle/_ref/libgridref.so.
+#include <Grid/Grid.h>
+#include <chrono>
+#include <memory>
+
+using namespace Grid;
+
+namespace {
+
+enum {
+  OP_DHOP = 0, OP_DHOP_OE = 1, OP_DHOP_EO = 2, OP_M = 3, OP_MDAG = 4, OP_MEOOE = 5, OP_MEOOE_DAG = 6, OP_MOOEE = 7,
+  OP_MOOEE_DAG = 8, OP_MOOEE_INV = 9, OP_MOOEE_INV_DAG = 10, OP_MPC = 11, OP_MPC_DAG = 12, OP_HERMOP = 13, OP_DW = 14,
+  OP_MEOOE5D = 15, OP_MEOOEDAG5D = 16
+};
+enum { KIND_WILSON = 0, KIND_CAYLEY = 1, KIND_STAGGERED = 2 };
+
+bool g_inited = false;
+
+struct BoxBase {
+  int kind, prec, Ls;
+  virtual ~BoxBase() {}
+  virtual void import_gauge(const void *Umu, const double *phases) = 0;
+  virtual int apply(int which, const void *in, void *out, int dag, int cb_in, int half) = 0;
+  virtual void cg(int cb, const void *src, void *sol, double tol, int maxit, int *iters, double *tr) = 0;
+  virtual void pick(int cb, void *half, const void *full) = 0;
+  virtual void set(int cb, void *full, const void *half) = 0;
+};
+
+template <class Field> void import_lex(Field &f, const void *host) {
+  typedef typename Field::vector_object::scalar_object sobj;
+  const size_t n = f.Grid()->lSites();
+  std::vector<sobj> tmp(n);
+  std::memcpy((void *)tmp.data(), host, n * sizeof(sobj));
+  vectorizeFromLexOrdArray(tmp, f);
+}
+template <class Field> void export_lex(const Field &f, void *host) {
+  typedef typename Field::vector_object::scalar_object sobj;
+  std::vector<sobj> tmp;
+  unvectorizeToLexOrdArray(tmp, f);
+  std::memcpy(host, (const void *)tmp.data(), tmp.size() * sizeof(sobj));
+}
+
+// Simd tag -> grids
+template <class vComplexT> struct Grids {
+  GridCartesian *UGrid = nullptr, *FGrid = nullptr;
+  GridRedBlackCartesian *UrbGrid = nullptr, *FrbGrid = nullptr;
+  void make(const int *L, int Ls, bool fiveD) {
+    Coordinate latt({L[0], L[1], L[2], L[3]});
+    Coordinate mpi({1, 1, 1, 1});
+    UGrid = SpaceTimeGrid::makeFourDimGrid(latt, GridDefaultSimd(Nd, vComplexT::Nsimd()), mpi);
+    UrbGrid = SpaceTimeGrid::makeFourDimRedBlackGrid(UGrid);
+    if (fiveD) {
+      FGrid = SpaceTimeGrid::makeFiveDimGrid(Ls, UGrid);
+      FrbGrid = SpaceTimeGrid::makeFiveDimRedBlackGrid(Ls, UGrid);
+    }
+  }
+  ~Grids() { delete FrbGrid; delete FGrid; delete UrbGrid; delete UGrid; }
+};
+
+// ---- Wilson-type operators (WilsonFermion, DomainWallFermion, MobiusFermion)
+template <class Impl, class vComplexT> struct WilsonBox : BoxBase {
+  typedef typename Impl::FermionField FermionField;
+  typedef typename Impl::GaugeField GaugeField;
+  typedef FermionOperator<Impl> OpBase;
+  Grids<vComplexT> G;
+  double mass, M5, b, c;
+  std::unique_ptr<GaugeField> Umu;
+  std::unique_ptr<OpBase> op;
+  std::unique_ptr<WilsonFermion5D<Impl>> dummy;
+
+  GridBase *fgrid() { return kind == KIND_WILSON ? (GridBase *)G.UGrid : (GridBase *)G.FGrid; }
+  GridBase *frbgrid() { return kind == KIND_WILSON ? (GridBase *)G.UrbGrid : (GridBase *)G.FrbGrid; }
+
+  void import_gauge(const void *U, const double *phases) override {
+    Umu.reset(new GaugeField(G.UGrid));
+    import_lex(*Umu, U);
+    typename Impl::ImplParams p;
+    if (phases) for (int mu = 0; mu < Nd; mu++) p.boundary_phases[mu] = Complex(phases[2 * mu], phases[2 * mu + 1]);
+    if (kind == KIND_WILSON) op.reset(new WilsonFermion<Impl>(*Umu, *G.UGrid, *G.UrbGrid, mass, p));
+    else if (b == 1.0 && c == 0.0) op.reset(new DomainWallFermion<Impl>(*Umu, *G.FGrid, *G.FrbGrid, *G.UGrid, *G.UrbGrid, mass, M5, p));
+    else op.reset(new MobiusFermion<Impl>(*Umu, *G.FGrid, *G.FrbGrid, *G.UGrid, *G.UrbGrid, mass, M5, b, c, p));
+  }
+  int apply(int which, const void *in, void *out, int dag, int cb_in, int half) override {
+    GridBase *gi = half ? frbgrid() : fgrid();
+    FermionField x(gi), y(gi);
+    import_lex(x, in);
+    if (half) { x.Checkerboard() = cb_in; y.Checkerboard() = cb_in; }
+    SchurDiagMooeeOperator<OpBase, FermionField> S(*op);
+    CayleyFermion5D<Impl> *cay = dynamic_cast<CayleyFermion5D<Impl> *>(op.get());
+    WilsonFermion5D<Impl> *w5 = dynamic_cast<WilsonFermion5D<Impl> *>(op.get());
+    switch (which) {
+    case OP_DHOP: op->Dhop(x, y, dag); break;
+    case OP_DHOP_OE: x.Checkerboard() = Even; op->DhopOE(x, y, dag); break;
+    case OP_DHOP_EO: x.Checkerboard() = Odd; op->DhopEO(x, y, dag); break;
+    case OP_M: op->M(x, y); break;
+    case OP_MDAG: op->Mdag(x, y); break;
+    case OP_MEOOE: op->Meooe(x, y); break;
+    case OP_MEOOE_DAG: op->MeooeDag(x, y); break;
+    case OP_MOOEE: op->Mooee(x, y); break;
+    case OP_MOOEE_DAG: op->MooeeDag(x, y); break;
+    case OP_MOOEE_INV: op->MooeeInv(x, y); break;
+    case OP_MOOEE_INV_DAG: op->MooeeInvDag(x, y); break;
+    case OP_MPC: S.Mpc(x, y); break;
+    case OP_MPC_DAG: S.MpcDag(x, y); break;
+    case OP_HERMOP: S.HermOp(x, y); break;
+    case OP_DW: if (!w5) return -1; w5->DW(x, y, dag); break;
+    case OP_MEOOE5D: if (!cay) return -1; cay->Meooe5D(x, y); break;
+    case OP_MEOOEDAG5D: if (!cay) return -1; cay->MeooeDag5D(x, y); break;
+    default: return -1;
+    }
+    export_lex(y, out);
+    return 0;
+  }
+  void cg(int cb, const void *src, void *sol, double tol, int maxit, int *iters, double *tr) override {
+    FermionField s(frbgrid()), x(frbgrid());
+    import_lex(s, src); import_lex(x, sol);
+    s.Checkerboard() = cb; x.Checkerboard() = cb;
+    SchurDiagMooeeOperator<OpBase, FermionField> S(*op);
+    ConjugateGradient<FermionField> CG(tol, maxit, false);
+    CG(S, s, x);
+    iters[0] = CG.IterationsToComplete; iters[1] = CG.IterationsToComplete < maxit; *tr = CG.TrueResidual;
+    export_lex(x, sol);
+  }
+  void pick(int cb, void *half, const void *full) override {
+    FermionField f(fgrid()), h(frbgrid());
+    import_lex(f, full);
+    pickCheckerboard(cb, h, f);
+    export_lex(h, half);
+  }
+  void set(int cb, void *full, const void *half) override {
+    FermionField f(fgrid()), h(frbgrid());
+    import_lex(f, full); import_lex(h, half);
+    h.Checkerboard() = cb;
+    setCheckerboard(f, h);
+    export_lex(f, full);
+  }
+};
+
+// ---- improved staggered (fat = thin = the imported links, as Benchmark_staggered.cc:92-96 does)
+template <class Impl, class vComplexT> struct StagBox : BoxBase {
+  typedef typename Impl::FermionField FermionField;
+  typedef typename Impl::GaugeField GaugeField;
+  Grids<vComplexT> G;
+  double mass, c1, c2, u0;
+  std::unique_ptr<GaugeField> Umu;
+  std::unique_ptr<ImprovedStaggeredFermion<Impl>> op;
+  void import_gauge(const void *U, const double *phases) override {
+    Umu.reset(new GaugeField(G.UGrid));
+    import_lex(*Umu, U);
+    typename Impl::ImplParams p;
+    op.reset(new ImprovedStaggeredFermion<Impl>(*Umu, *Umu, *G.UGrid, *G.UrbGrid, mass, c1, c2, u0, p));
+  }
+  int apply(int which, const void *in, void *out, int dag, int cb_in, int half) override {
+    GridBase *gi = half ? (GridBase *)G.UrbGrid : (GridBase *)G.UGrid;
+    FermionField x(gi), y(gi);
+    import_lex(x, in);
+    if (half) { x.Checkerboard() = cb_in; y.Checkerboard() = cb_in; }
+    SchurStaggeredOperator<ImprovedStaggeredFermion<Impl>, FermionField> S(*op);
+    switch (which) {
+    case OP_DHOP: op->Dhop(x, y, dag); break;
+    case OP_DHOP_OE: x.Checkerboard() = Even; op->DhopOE(x, y, dag); break;
+    case OP_DHOP_EO: x.Checkerboard() = Odd; op->DhopEO(x, y, dag); break;
+    case OP_M: op->M(x, y); break;
+    case OP_MDAG: op->Mdag(x, y); break;
+    case OP_MEOOE: op->Meooe(x, y); break;
+    case OP_MEOOE_DAG: op->MeooeDag(x, y); break;
+    case OP_MOOEE: op->Mooee(x, y); break;
+    case OP_MOOEE_DAG: op->MooeeDag(x, y); break;
+    case OP_MOOEE_INV: op->MooeeInv(x, y); break;
+    case OP_MOOEE_INV_DAG: op->MooeeInvDag(x, y); break;
+    case OP_MPC: S.Mpc(x, y); break;
+    case OP_MPC_DAG: S.MpcDag(x, y); break;
+    case OP_HERMOP: S.HermOp(x, y); break;
+    default: return -1;
+    }
+    export_lex(y, out);
+    return 0;
+  }
+  void cg(int cb, const void *src, void *sol, double tol, int maxit, int *iters, double *tr) override {
+    FermionField s(G.UrbGrid), x(G.UrbGrid);
+    import_lex(s, src); import_lex(x, sol);
+    s.Checkerboard() = cb; x.Checkerboard() = cb;
+    SchurStaggeredOperator<ImprovedStaggeredFermion<Impl>, FermionField> S(*op);
+    ConjugateGradient<FermionField> CG(tol, maxit, false);
+    CG(S, s, x);
+    iters[0] = CG.IterationsToComplete; iters[1] = CG.IterationsToComplete < maxit; *tr = CG.TrueResidual;
+    export_lex(x, sol);
+  }
+  void pick(int cb, void *half, const void *full) override {
+    FermionField f(G.UGrid), h(G.UrbGrid);
+    import_lex(f, full); pickCheckerboard(cb, h, f); export_lex(h, half);
+  }
+  void set(int cb, void *full, const void *half) override {
+    FermionField f(G.UGrid), h(G.UrbGrid);
+    import_lex(f, full); import_lex(h, half); h.Checkerboard() = cb; setCheckerboard(f, h); export_lex(f, full);
+  }
+};
+
+} // namespace
+
+extern "C" {
+
+// Grid_init with a synthetic command line; threads <= 0 keeps the OpenMP default
+int gref_init(int threads) {
+  if (g_inited) return 0;
+  static std::string a0 = "gridref", a1 = "--threads", a2, a3 = "--grid", a4 = "8.8.8.8";
+  a2 = std::to_string(threads > 0 ? threads : omp_get_max_threads());
+  static char *args[] = {(char *)a0.c_str(), (char *)a1.c_str(), (char *)a2.c_str(), (char *)a3.c_str(), (char *)a4.c_str(), nullptr};
+  int argc = 5;
+  char **argv = args;
+  Grid_init(&argc, &argv);
+  g_inited = true;
+  return 0;
+}
+int gref_num_threads() { return GridThread::GetThreads(); }
+int gref_nsimd(int prec) { return prec == 0 ? vComplexF::Nsimd() : vComplexD::Nsimd(); }
+// 0 generic, 1 hand-unrolled (the reference's default on CPU), 2 asm
+void gref_set_kernel_opt(int opt) {
+  WilsonKernelsStatic::Opt = opt == 0 ? WilsonKernelsStatic::OptGeneric : opt == 1 ? WilsonKernelsStatic::OptHandUnroll : WilsonKernelsStatic::OptInlineAsm;
+  StaggeredKernelsStatic::Opt = opt == 0 ? StaggeredKernelsStatic::OptGeneric : StaggeredKernelsStatic::OptHandUnroll;
+}
+
+// kind 0: WilsonFermion (Ls = 1); 1: DomainWallFermion (b=1,c=0) or MobiusFermion; 2: ImprovedStaggeredFermion
+// (M5 = c1, b = c2, c = u0).  prec 0 = fp32 (…F types), 1 = fp64 (…D types).
+void *gref_op_create(int kind, const int *L, int Ls, double mass, double M5, double b, double c, int prec) {
+  gref_init(0);
+  BoxBase *r = nullptr;
+  if (kind == KIND_STAGGERED) {
+    if (prec == 0) { auto *x = new StagBox<StaggeredImplF, vComplexF>(); x->G.make(L, 1, false); x->mass = mass; x->c1 = M5; x->c2 = b; x->u0 = c; r = x; }
+    else { auto *x = new StagBox<StaggeredImplD, vComplexD>(); x->G.make(L, 1, false); x->mass = mass; x->c1 = M5; x->c2 = b; x->u0 = c; r = x; }
+  } else {
+    if (prec == 0) { auto *x = new WilsonBox<WilsonImplF, vComplexF>(); x->G.make(L, Ls, kind == KIND_CAYLEY); x->mass = mass; x->M5 = M5; x->b = b; x->c = c; r = x; }
+    else { auto *x = new WilsonBox<WilsonImplD, vComplexD>(); x->G.make(L, Ls, kind == KIND_CAYLEY); x->mass = mass; x->M5 = M5; x->b = b; x->c = c; r = x; }
+  }
+  r->kind = kind; r->prec = prec; r->Ls = Ls;
+  return r;
+}
+void gref_op_destroy(void *h) { delete (BoxBase *)h; }
+void gref_op_import_gauge(void *h, const void *Umu, const double *phases) { ((BoxBase *)h)->import_gauge(Umu, phases); }
+int gref_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half) {
+  return ((BoxBase *)h)->apply(which, in, out, dag, cb_in, half);
+}
+void gref_pick_checkerboard(void *h, int cb, void *half, const void *full) { ((BoxBase *)h)->pick(cb, half, full); }
+void gref_set_checkerboard(void *h, int cb, void *full, const void *half) { ((BoxBase *)h)->set(cb, full, half); }
+void gref_cg(void *h, int cb, const void *src, void *sol, double tol, int maxit, int *out_iters, double *out_true_resid) {
+  ((BoxBase *)h)->cg(cb, src, sol, tol, maxit, out_iters, out_true_resid);
+}
+
+// MixedPrecisionConjugateGradient exactly as tests/Test_dwf_mixedcg_prec.cc:113-196 sets it up.
+// out_iters: [inner, outer, final, converged]
+void gref_mixed_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d, double tol, int maxinner, int maxouter,
+                   int *out_iters, double *out_true_resid) {
+  auto *bd = dynamic_cast<WilsonBox<WilsonImplD, vComplexD> *>((BoxBase *)h_d);
+  auto *bf = dynamic_cast<WilsonBox<WilsonImplF, vComplexF> *>((BoxBase *)h_f);
+  assert(bd && bf);
+  typedef FermionOperator<WilsonImplD> OpD;
+  typedef FermionOperator<WilsonImplF> OpF;
+  SchurDiagMooeeOperator<OpD, LatticeFermionD> Sd(*bd->op);
+  SchurDiagMooeeOperator<OpF, LatticeFermionF> Sf(*bf->op);
+  LatticeFermionD s(bd->frbgrid()), x(bd->frbgrid());
+  import_lex(s, src_d); import_lex(x, sol_d);
+  s.Checkerboard() = cb; x.Checkerboard() = cb;
+  MixedPrecisionConjugateGradient<LatticeFermionD, LatticeFermionF> mCG(tol, maxinner, maxouter, bf->frbgrid(), Sf, Sd);
+  mCG(s, x);
+  out_iters[0] = mCG.TotalInnerIterations; out_iters[1] = mCG.TotalOuterIterations; out_iters[2] = mCG.TotalFinalStepIterations;
+  out_iters[3] = 1;
+  *out_true_resid = mCG.TrueResidual;
+  export_lex(x, sol_d);
+}
+
+// Timed loop for the CPU baseline: fields stay resident in Grid's own layout; returns seconds for ncall applications.
+double gref_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
+  BoxBase *b = (BoxBase *)h;
+  double secs = -1;
+  auto run = [&](auto *box) {
+    typedef typename std::remove_pointer<decltype(box)>::type Box;
+    typedef typename Box::FermionField FermionField;
+    GridBase *gi = half ? (GridBase *)box->frbgrid() : (GridBase *)box->fgrid();
+    FermionField x(gi), y(gi);
+    import_lex(x, in);
+    if (half) x.Checkerboard() = which == OP_DHOP_OE ? Even : Odd;
+    auto call = [&]() {
+      if (which == OP_DHOP) box->op->Dhop(x, y, dag);
+      else if (which == OP_DHOP_OE) box->op->DhopOE(x, y, dag);
+      else box->op->DhopEO(x, y, dag);
+    };
+    call(); // warm-up (stencil tables, first-touch)
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < ncall; i++) call();
+    auto t1 = std::chrono::steady_clock::now();
+    secs = std::chrono::duration<double>(t1 - t0).count();
+    export_lex(y, out);
+  };
+  if (auto *p = dynamic_cast<WilsonBox<WilsonImplF, vComplexF> *>(b)) run(p);
+  else if (auto *p = dynamic_cast<WilsonBox<WilsonImplD, vComplexD> *>(b)) run(p);
+  return secs;
+}
+}
