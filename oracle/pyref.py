@@ -1,0 +1,151 @@
+"""ctypes binding of the COMPILED REFERENCE (oracle/_ref/libgridref.so = unmodified paboyle/Grid CPU code + oracle/gridref_capi.cc).
+
+TEST INFRASTRUCTURE ONLY -- same rule as the oracle: only tests/, the fixture generator tests/golden/make_golden.py and
+bench.py's cpu_baseline / --impl reference legs import this.  The product package grid_b200 never does.
+
+The library is built by `make -C oracle -f Makefile.ref` in the container that has /root/reference (see the Makefile's header
+for what stands in for autotools' Config.h and the downloaded Eigen tree).  The built .so travels to the GPU box with the
+repository snapshot; nothing here reads /root/reference at run time.
+
+RefOp has the interface of pyoracle.OracleOp, so every check can be run against either.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libgridref.so")
+_LIB = None
+
+(OP_DHOP, OP_DHOP_OE, OP_DHOP_EO, OP_M, OP_MDAG, OP_MEOOE, OP_MEOOE_DAG, OP_MOOEE, OP_MOOEE_DAG, OP_MOOEE_INV,
+ OP_MOOEE_INV_DAG, OP_MPC, OP_MPC_DAG, OP_HERMOP, OP_DW, OP_MEOOE5D, OP_MEOOEDAG5D) = range(17)
+KIND_WILSON, KIND_CAYLEY, KIND_STAGGERED = 0, 1, 2
+OPT_GENERIC, OPT_HAND_UNROLL = 0, 1
+
+
+def available():
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not available():
+            raise RuntimeError(f"{_PATH} not built (make -C oracle -f Makefile.ref needs /root/reference)")
+        L = C.CDLL(_PATH)
+        L.gref_op_create.restype = C.c_void_p
+        L.gref_op_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.gref_op_destroy.argtypes = [C.c_void_p]
+        L.gref_op_import_gauge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gref_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.gref_apply.restype = C.c_int
+        L.gref_pick_checkerboard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_set_checkerboard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.gref_time_apply.restype = C.c_double
+        L.gref_init.argtypes = [C.c_int]
+        L.gref_set_kernel_opt.argtypes = [C.c_int]
+        # Grid_init prints its banner on stdout; keep the caller's stdout clean (bench.py prints ONE JSON line there)
+        import sys
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            L.gref_init(int(os.environ.get("GRIDREF_THREADS", "0")))
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
+        _LIB = L
+    return _LIB
+
+
+def _cdtype(prec):
+    return np.complex64 if prec == 0 else np.complex128
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads():
+    return lib().gref_num_threads()
+
+
+def nsimd(prec):
+    return lib().gref_nsimd(prec)
+
+
+def set_kernel_opt(opt):
+    """0 = WilsonKernelsStatic::OptGeneric (the reference's default), 1 = OptHandUnroll (--dslash-unroll)."""
+    lib().gref_set_kernel_opt(opt)
+
+
+class RefOp:
+    """The reference's own WilsonFermion (kind 0) / DomainWallFermion or MobiusFermion (kind 1) /
+    ImprovedStaggeredFermion (kind 2: M5,b,c carry c1,c2,u0), fp32 (prec 0) or fp64 (prec 1)."""
+
+    def __init__(self, kind, dims, Ls, mass, M5=1.8, b=1.0, c=0.0, prec=1):
+        self.kind, self.dims, self.Ls, self.prec = kind, tuple(dims), Ls, prec
+        self.V4 = int(np.prod(dims))
+        self.h = lib().gref_op_create(kind, (C.c_int * 4)(*dims), Ls, mass, M5, b, c, prec)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().gref_op_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def import_gauge(self, Umu, phases=None):
+        U = np.ascontiguousarray(Umu, dtype=_cdtype(self.prec))
+        assert U.shape == (self.V4, 4, 3, 3)
+        ph = None if phases is None else np.ascontiguousarray(np.asarray(phases, dtype=np.complex128))
+        lib().gref_op_import_gauge(self.h, _ptr(U), _ptr(ph) if ph is not None else None)
+
+    def _half(self, n):
+        assert n in (self.V4 * self.Ls, self.V4 * self.Ls // 2), n
+        return 1 if n == self.V4 * self.Ls // 2 else 0
+
+    def apply(self, which, x, dag=0, cb_in=0):
+        x = np.ascontiguousarray(x, dtype=_cdtype(self.prec))
+        out = np.empty_like(x)
+        rc = lib().gref_apply(self.h, which, _ptr(x), _ptr(out), dag, cb_in, self._half(x.shape[0]))
+        assert rc == 0, rc
+        return out
+
+    def time_apply(self, which, x, ncall, dag=0, cb_in=0):
+        x = np.ascontiguousarray(x, dtype=_cdtype(self.prec))
+        out = np.empty_like(x)
+        return lib().gref_time_apply(self.h, which, _ptr(x), _ptr(out), dag, cb_in, self._half(x.shape[0]), ncall)
+
+    def pick_checkerboard(self, cb, full):
+        full = np.ascontiguousarray(full, dtype=_cdtype(self.prec))
+        half = np.empty((full.shape[0] // 2,) + full.shape[1:], dtype=full.dtype)
+        lib().gref_pick_checkerboard(self.h, cb, _ptr(half), _ptr(full))
+        return half
+
+    def set_checkerboard(self, cb, full, half):
+        full = np.ascontiguousarray(full, dtype=_cdtype(self.prec)).copy()
+        half = np.ascontiguousarray(half, dtype=_cdtype(self.prec))
+        lib().gref_set_checkerboard(self.h, cb, _ptr(full), _ptr(half))
+        return full
+
+    def cg(self, cb, src, tol, maxit, guess=None):
+        src = np.ascontiguousarray(src, dtype=_cdtype(self.prec))
+        sol = np.zeros_like(src) if guess is None else np.ascontiguousarray(guess, dtype=_cdtype(self.prec)).copy()
+        it = np.zeros(2, dtype=np.int32)
+        tr = np.zeros(1, dtype=np.float64)
+        lib().gref_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
+        return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
+
+
+def mixed_cg(op_d, op_f, cb, src_d, tol, maxinner, maxouter):
+    src = np.ascontiguousarray(src_d, dtype=np.complex128)
+    sol = np.zeros_like(src)
+    it = np.zeros(4, dtype=np.int32)
+    tr = np.zeros(1, dtype=np.float64)
+    lib().gref_mixed_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxinner, maxouter, _ptr(it), _ptr(tr))
+    return sol, dict(inner=int(it[0]), outer=int(it[1]), final=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))

@@ -1,0 +1,118 @@
+"""Pins the CPU oracle against the REFERENCE ITSELF: oracle/_ref/libgridref.so is the unmodified paboyle/Grid CPU code
+compiled from /root/reference (oracle/Makefile.ref) and driven through its own public classes (oracle/gridref_capi.cc).
+
+Every operator entry of the path is compared oracle-vs-reference on identical random SU(3) links and fermion fields:
+fp64 agreement to rounding (<= 1e-13 per site, in practice a few ulp), fp32 to <= 1e-6, CG iteration counts equal.
+Skipped only where the compiled reference is absent (a checkout without /root/reference and without the built .so);
+the committed fixtures under tests/golden/ (made from the same library by tests/golden/make_golden.py) cover that case.
+"""
+import numpy as np
+import pytest
+
+from grid_b200 import synthetic as syn
+from oracle import pyoracle as po
+from oracle import pyref as pr
+
+pytestmark = pytest.mark.skipif(not pr.available(), reason="oracle/_ref/libgridref.so not built (needs /root/reference)")
+
+DIMS = (4, 6, 8, 4)   # unequal extents so index-order bugs show; z,t are multiples of 4 (the reference needs an even reduced extent under its SIMD layout)
+LS = 6
+CAYLEY_OPS_FULL = [po.OP_DHOP, po.OP_M, po.OP_MDAG, po.OP_DW]
+CAYLEY_OPS_HALF = [po.OP_DHOP_OE, po.OP_DHOP_EO, po.OP_MEOOE, po.OP_MEOOE_DAG, po.OP_MOOEE, po.OP_MOOEE_DAG, po.OP_MOOEE_INV,
+                   po.OP_MOOEE_INV_DAG, po.OP_MPC, po.OP_MPC_DAG, po.OP_HERMOP, po.OP_MEOOE5D, po.OP_MEOOEDAG5D]
+NAMES = {v: k for k, v in vars(po).items() if k.startswith("OP_")}
+
+
+def site_err(a, b):
+    a = a.reshape(a.shape[0], -1).astype(np.complex128); b = b.reshape(b.shape[0], -1).astype(np.complex128)
+    return float(np.max(np.linalg.norm(a - b, axis=1) / np.maximum(np.linalg.norm(b, axis=1), 1e-300)))
+
+
+@pytest.fixture(scope="module")
+def gauge():
+    return syn.hot_gauge(DIMS, seed=21)
+
+
+def pair(kind, gauge, Ls, prec, b=1.0, c=0.0, phases=None):
+    o = po.OracleOp(kind, DIMS, Ls, mass=0.1, M5=1.8, b=b, c=c, prec=prec)
+    r = pr.RefOp(kind, DIMS, Ls, mass=0.1, M5=1.8, b=b, c=c, prec=prec)
+    o.import_gauge(gauge, phases); r.import_gauge(gauge, phases)
+    return o, r
+
+
+TOL = {0: 1e-6, 1: 1e-13}
+ANTIPERIODIC_T = [1.0, 1.0, 1.0, -1.0]
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("phases", [None, ANTIPERIODIC_T])
+def test_wilson_all_entries(gauge, prec, phases):
+    o, r = pair(0, gauge, 1, prec, phases=phases)
+    src = syn.random_fermion(DIMS, 1, seed=5).astype(po._cdtype(prec))
+    for dag in (0, 1):
+        assert site_err(o.apply(po.OP_DHOP, src, dag=dag), r.apply(pr.OP_DHOP, src, dag=dag)) < TOL[prec]
+    for which in (po.OP_M, po.OP_MDAG):
+        assert site_err(o.apply(which, src), r.apply(which, src)) < TOL[prec], NAMES[which]
+    for cb in (0, 1):
+        h = po.pick_checkerboard(DIMS, 1, cb, src)
+        assert np.array_equal(h, r.pick_checkerboard(cb, src))          # red-black site order is the reference's
+        for which in (po.OP_MEOOE, po.OP_MEOOE_DAG, po.OP_MOOEE, po.OP_MOOEE_INV, po.OP_MPC, po.OP_MPC_DAG, po.OP_HERMOP):
+            assert site_err(o.apply(which, h, cb_in=cb), r.apply(which, h, cb_in=cb)) < 4 * TOL[prec], (NAMES[which], cb)
+    he, ho = po.pick_checkerboard(DIMS, 1, 0, src), po.pick_checkerboard(DIMS, 1, 1, src)
+    for dag in (0, 1):
+        assert site_err(o.apply(po.OP_DHOP_OE, he, dag=dag), r.apply(pr.OP_DHOP_OE, he, dag=dag)) < TOL[prec]
+        assert site_err(o.apply(po.OP_DHOP_EO, ho, dag=dag), r.apply(pr.OP_DHOP_EO, ho, dag=dag)) < TOL[prec]
+
+
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("bc", [(1.0, 0.0), (1.5, 0.5)], ids=["DomainWallFermion", "MobiusFermion"])
+def test_cayley_all_entries(gauge, prec, bc):
+    o, r = pair(1, gauge, LS, prec, b=bc[0], c=bc[1])
+    src = syn.random_fermion(DIMS, LS, seed=6).astype(po._cdtype(prec))
+    for which in CAYLEY_OPS_FULL:
+        for dag in ((0, 1) if which in (po.OP_DHOP, po.OP_DW) else (0,)):
+            assert site_err(o.apply(which, src, dag=dag), r.apply(which, src, dag=dag)) < 4 * TOL[prec], (NAMES[which], dag)
+    for cb in (0, 1):
+        h = po.pick_checkerboard(DIMS, LS, cb, src)
+        assert np.array_equal(h, r.pick_checkerboard(cb, src))
+        for which in CAYLEY_OPS_HALF:
+            if which == po.OP_DHOP_OE and cb != 0 or which == po.OP_DHOP_EO and cb != 1:
+                continue
+            for dag in ((0, 1) if which in (po.OP_DHOP_OE, po.OP_DHOP_EO) else (0,)):
+                e = site_err(o.apply(which, h, dag=dag, cb_in=cb), r.apply(which, h, dag=dag, cb_in=cb))
+                assert e < 8 * TOL[prec], (NAMES[which], cb, dag, e)
+
+
+def test_cayley_antiperiodic_and_set_checkerboard(gauge):
+    o, r = pair(1, gauge, LS, 1, b=1.5, c=0.5, phases=ANTIPERIODIC_T)
+    src = syn.random_fermion(DIMS, LS, seed=7)
+    assert site_err(o.apply(po.OP_M, src), r.apply(pr.OP_M, src)) < 1e-13
+    half = po.pick_checkerboard(DIMS, LS, 1, src)
+    full_o = np.zeros_like(src)
+    po.set_checkerboard(DIMS, LS, 1, full_o, half)
+    assert np.array_equal(full_o, r.set_checkerboard(1, np.zeros_like(src), half))
+
+
+@pytest.mark.parametrize("kind,Ls,bc", [(0, 1, (1.0, 0.0)), (1, LS, (1.0, 0.0)), (1, LS, (1.5, 0.5))], ids=["wilson", "dwf", "mobius"])
+def test_schur_cg_same_iterations_and_residual(gauge, kind, Ls, bc):
+    """ref: ConjugateGradient.h:68-258 on SchurDiagMooeeOperator -- same iteration count, same true residual, same solution."""
+    o, r = pair(kind, gauge, Ls, 1, b=bc[0], c=bc[1])
+    src = po.pick_checkerboard(DIMS, Ls, 1, syn.random_fermion(DIMS, Ls, seed=8))
+    xo, io = o.cg(1, src, 1e-8, 5000)
+    xr, ir = r.cg(1, src, 1e-8, 5000)
+    assert io["iterations"] == ir["iterations"], (io, ir)
+    assert abs(io["true_residual"] - ir["true_residual"]) < 1e-3 * ir["true_residual"] + 1e-14
+    assert site_err(xo, xr) < 1e-9
+
+
+def test_mixed_precision_cg(gauge):
+    """ref: tests/Test_dwf_mixedcg_prec.cc:113-196 (MixedPrecisionConjugateGradient, tol 1e-8)."""
+    od, rd = pair(1, gauge, LS, 1)
+    of, rf = pair(1, gauge, LS, 0)
+    src = po.pick_checkerboard(DIMS, LS, 1, syn.random_fermion(DIMS, LS, seed=9))
+    xo, io = po.mixed_cg(od, of, 1, src, 1e-8, 10000, 50)
+    xr, ir = pr.mixed_cg(rd, rf, 1, src, 1e-8, 10000, 50)
+    assert io["outer"] == ir["outer"], (io, ir)
+    assert abs(io["inner"] - ir["inner"]) <= max(1, 0.02 * ir["inner"]), (io, ir)   # fp32 inner solves: +-2 % (north_star)
+    assert ir["true_residual"] < 1e-8 and io["true_residual"] < 1e-8
+    assert site_err(xo, xr) < 1e-6
