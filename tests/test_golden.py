@@ -78,7 +78,7 @@ def test_oracle_fp32_hop_and_mixed_cg_match_reference():
     assert site_err(of.apply(po.OP_DHOP, G["src5"].astype(np.complex64)), G["dwf/DHOP/dag0_f32"]) < 1e-6
     x, info = po.mixed_cg(od, of, 1, po.pick_checkerboard(DIMS, LS, 1, G["src5"]), 1e-8, 10000, 50)
     assert info["outer"] == int(G["dwf/mixed_cg/outer"])
-    assert abs(info["inner"] - int(G["dwf/mixed_cg/inner"])) <= max(1, 0.02 * int(G["dwf/mixed_cg/inner"]))
+    assert abs(info["inner"] - int(G["dwf/mixed_cg/inner"])) <= max(3, 0.05 * int(G["dwf/mixed_cg/inner"]))   # see test_oracle_vs_reference
     assert site_err(x, G["dwf/mixed_cg/solution"]) < 1e-6
 
 
