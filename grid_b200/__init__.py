@@ -37,7 +37,7 @@ SYMBOLS = [
     ("gb_comm_global_sum", _i, [_vp, _pd, _i]), ("gb_comm_barrier", _i, [_vp]),
     ("gb_grid_create", _i, [_vp, _pi, _pi, _pvp]), ("gb_geometry_query", _i, [_pi, _pi, _i, _pi, _pi, _pi]), ("gb_grid_destroy", _i, [_vp]), ("gb_grid_local_dims", _i, [_vp, _pi]),
     ("gb_grid_local_origin", _i, [_vp, _pi]),
-    ("gb_fermion_create", _i, [_vp, _i, _i, _i, _pvp]), ("gb_fermion_destroy", _i, [_vp]), ("gb_fermion_checkerboard", _i, [_vp]),
+    ("gb_fermion_create", _i, [_vp, _i, _i, _i, _pvp]), ("gb_staggered_fermion_create", _i, [_vp, _i, _i, _pvp]), ("gb_fermion_destroy", _i, [_vp]), ("gb_fermion_checkerboard", _i, [_vp]),
     ("gb_fermion_set_checkerboard_tag", _i, [_vp, _i]), ("gb_fermion_local_sites", _i64, [_vp]),
     ("gb_fermion_import", _i, [_vp, _vp, _i]), ("gb_fermion_export", _i, [_vp, _vp, _i]),
     ("gb_pick_checkerboard", _i, [_i, _vp, _vp]), ("gb_set_checkerboard", _i, [_vp, _vp]), ("gb_precision_change", _i, [_vp, _vp]),
@@ -49,6 +49,7 @@ SYMBOLS = [
     ("gb_gauge_export", _i, [_vp, _vp, _i]), ("gb_gauge_random", _i, [_vp, _u64]), ("gb_gauge_unit", _i, [_vp]),
     ("gb_op_create_wilson", _i, [_vp, _vp, _d, _pd, _pvp]), ("gb_op_create_dwf", _i, [_vp, _vp, _i, _d, _d, _pd, _pvp]),
     ("gb_op_create_mobius", _i, [_vp, _vp, _i, _d, _d, _d, _d, _pd, _pvp]), ("gb_op_import_gauge", _i, [_vp, _vp]),
+    ("gb_op_create_staggered", _i, [_vp, _vp, _vp, _d, _d, _d, _d, _pvp]), ("gb_op_import_gauge_staggered", _i, [_vp, _vp, _vp]),
     ("gb_op_destroy", _i, [_vp]), ("gb_op_Ls", _i, [_vp]), ("gb_op_apply", _i, [_vp, _i, _vp, _vp, _i]),
     ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
@@ -181,11 +182,15 @@ class GridCartesian:
 
 class LatticeFermion:
     """LatticeFermion{F,D} on the full (kind=FULL) or red-black (kind=HALF) 4D/5D grid."""
+    SITE = (4, 3)   # SpinColourVector
 
     def __init__(self, grid, Ls=1, prec=F32, kind=FULL):
         self.grid, self.Ls, self.prec, self.kind = grid, Ls, prec, kind
         self.h = C.c_void_p()
-        _chk(lib().gb_fermion_create(grid.h, Ls, prec, kind, C.byref(self.h)))
+        self._create()
+
+    def _create(self):
+        _chk(lib().gb_fermion_create(self.grid.h, self.Ls, self.prec, self.kind, C.byref(self.h)))
 
     def __del__(self):
         try:
@@ -195,7 +200,7 @@ class LatticeFermion:
             pass
 
     def like(self, kind=None, prec=None):
-        return LatticeFermion(self.grid, self.Ls, self.prec if prec is None else prec, self.kind if kind is None else kind)
+        return type(self)(self.grid, self.Ls, self.prec if prec is None else prec, self.kind if kind is None else kind)
 
     @property
     def local_sites(self):
@@ -210,13 +215,13 @@ class LatticeFermion:
     def import_lex(self, host):
         """host: complex [nsites,4,3] in local lexicographic (full) or checkerboard-lexicographic (half) order."""
         host = np.ascontiguousarray(host)
-        assert host.shape == (self.local_sites, 4, 3), (host.shape, self.local_sites)
+        assert host.shape == (self.local_sites,) + self.SITE, (host.shape, self.local_sites)
         _chk(lib().gb_fermion_import(self.h, host.ctypes.data_as(C.c_void_p), _prec_of(host)))
         return self
 
     def export_lex(self, dtype=None):
         dt = _cdtype(self.prec) if dtype is None else dtype
-        out = np.empty((self.local_sites, 4, 3), dtype=dt)
+        out = np.empty((self.local_sites,) + self.SITE, dtype=dt)
         _chk(lib().gb_fermion_export(self.h, out.ctypes.data_as(C.c_void_p), _prec_of(out)))
         return out
 
@@ -227,6 +232,18 @@ class LatticeFermion:
     def zero(self):
         _chk(lib().gb_zero(self.h))
         return self
+
+
+class LatticeStaggeredFermion(LatticeFermion):
+    """LatticeStaggeredFermion{F,D}: one ColourVector per 4D site (ref: StaggeredImpl.h:60-75).  Host arrays are [nsites,3]."""
+    SITE = (3,)
+
+    def __init__(self, grid, Ls=1, prec=F32, kind=FULL):
+        assert Ls == 1, "staggered fields are 4D"
+        super().__init__(grid, 1, prec, kind)
+
+    def _create(self):
+        _chk(lib().gb_staggered_fermion_create(self.grid.h, self.prec, self.kind, C.byref(self.h)))
 
 
 def pickCheckerboard(cb, half, full):
@@ -389,6 +406,21 @@ class MobiusFermion(FermionOperator):
         _chk(lib().gb_op_create_mobius(grid.h, Umu.h, Ls, mass, M5, b, c, _phases(boundary_phases), C.byref(self.h)))
 
 
+class ImprovedStaggeredFermion(FermionOperator):
+    """ref: ImprovedStaggeredFermion.h:115-121 -- (Uthin, Ufat, grid, mass, c1, c2, u0); fields are LatticeStaggeredFermion."""
+
+    def __init__(self, Uthin, Ufat, grid, mass, c1=9.0 / 8.0, c2=-1.0 / 24.0, u0=1.0):
+        super().__init__()
+        self.grid, self.mass = grid, mass
+        _chk(lib().gb_op_create_staggered(grid.h, Uthin.h, Ufat.h, mass, c1, c2, u0, C.byref(self.h)))
+
+    def ImportGauge(self, Uthin, Ufat=None):
+        _chk(lib().gb_op_import_gauge_staggered(self.h, Uthin.h, (Ufat or Uthin).h))
+
+    def Mass(self):
+        return self.mass
+
+
 class LinearOperatorBase:
     """ref: Grid/algorithms/LinearOperator.h:44-56"""
 
@@ -413,6 +445,15 @@ class SchurDiagMooeeOperator(LinearOperatorBase):
     def Op(self, i, o): self.Mpc(i, o)
     def AdjOp(self, i, o): self.MpcDag(i, o)
     def HermOp(self, i, o): self.MpcDagMpc(i, o)
+
+
+class SchurStaggeredOperator(SchurDiagMooeeOperator):
+    """ref: LinearOperator.h:543-584.  Mpc = MpcDag = HermOp = mass^2 - Meooe Meooe (Hermitian: one application per CG step)."""
+
+    def MpcDagMpc(self, i, o):
+        raise AssertionError("never needed with staggered (ref: LinearOperator.h:581-583)")
+
+    def HermOp(self, i, o): self.Mpc(i, o)
 
 
 class ConjugateGradient:
@@ -453,7 +494,7 @@ class _Borrowed(LatticeFermion):
     """Non-owning view of a library-owned field handle (used inside the generic-CG callback)."""
 
     def __init__(self, handle, like):
-        self.grid, self.Ls, self.prec, self.kind = like.grid, like.Ls, like.prec, like.kind
+        self.grid, self.Ls, self.prec, self.kind, self.SITE = like.grid, like.Ls, like.prec, like.kind, like.SITE
         self.h = C.c_void_p(handle)
 
     def __del__(self):

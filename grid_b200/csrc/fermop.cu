@@ -173,6 +173,7 @@ static void apply_mpc(gb_fermop *op, const gb_fermion *in, gb_fermion *out, int 
 void op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag) {
   GB_REQUIRE(op && in && out, "null argument");
   GB_REQUIRE(in != out, "in and out must be distinct fields");
+  if (op->kind == GB_KIND_STAGGERED) { stag_op_apply(op, which, in, out, dag ? 1 : 0); return; }
   GB_REQUIRE(op->Uds != nullptr, "operator has no gauge field: call ImportGauge first");
   dag = dag ? 1 : 0;
   switch (which) {
@@ -291,12 +292,14 @@ int gb_op_create_mobius(gb_grid *g, const gb_gauge *Umu, int Ls, double mass, do
 }
 int gb_op_import_gauge(gb_fermop *op, const gb_gauge *Umu) {
   GB_API_BEGIN
+  GB_REQUIRE(op && op->kind != GB_KIND_STAGGERED, "staggered operators take thin and fat links: gb_op_import_gauge_staggered");
   op_import_gauge(op, Umu);
   GB_API_END
 }
 int gb_op_destroy(gb_fermop *op) {
   if (!op) return GB_OK;
   cudaFree(op->Uds);
+  cudaFree(op->stag_links);
   for (int i = 0; i < 8; i++) { if (op->halo_send[i]) cudaFree(op->halo_send[i]); if (op->halo_recv[i]) cudaFree(op->halo_recv[i]); }
   p2p_teardown(op);
   for (void *p : op->smat_allocs) cudaFree(p);

@@ -3,7 +3,7 @@
 #include "internal.hpp"
 #include <cstdlib>
 
-enum gb_opkind { GB_KIND_WILSON = 0, GB_KIND_CAYLEY = 1 };
+enum gb_opkind { GB_KIND_WILSON = 0, GB_KIND_CAYLEY = 1, GB_KIND_STAGGERED = 2 };
 
 namespace gb {
 // dense s-space operator: [2 chiralities][Ls][Ls] doubles, row-major (smat.cu)
@@ -52,6 +52,10 @@ struct gb_fermop {
   const void *sm_meooe5d = nullptr, *sm_meooedag5d = nullptr, *sm_mooee = nullptr, *sm_mooeedag = nullptr, *sm_mooeeinv = nullptr,
              *sm_mooeeinvdag = nullptr, *sm_m5unit = nullptr, *sm_m5unitdag = nullptr, *sm_B = nullptr, *sm_Bdag = nullptr, *sm_negAdag = nullptr;
   std::vector<void *> smat_allocs;
+  // improved staggered (stag.cu): 16 scaled + phased links per site, per output parity, streamed layout
+  void *stag_links = nullptr;
+  size_t stag_parity_bytes = 0;
+  double stag_c1 = 1, stag_c2 = 1, stag_u0 = 1;
   // temporaries (ref: FermionOperator::tmp(), and the stack Fields of SchurDiagMooeeOperator)
   gb_fermion *tmp_h[4] = {nullptr, nullptr, nullptr, nullptr};
   gb_fermion *tmp_f[2] = {nullptr, nullptr};
@@ -89,6 +93,8 @@ const void *smat_device(gb_fermop *op, const SMat &m);
 bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha, const gb_fermion *z,
                 gb_fermion *out);
 
+// improved staggered operator entry points (stag.cu)
+void stag_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
 // composite operator pieces used by the solvers
 void op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
 gb_fermion *op_tmp_half(gb_fermop *op, int i);

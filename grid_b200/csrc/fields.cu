@@ -69,12 +69,12 @@ extern "C" int gb_grid_local_origin(const gb_grid *g, int o[4]) { for (int d = 0
 // =====================================================================================================
 // fermion containers
 // =====================================================================================================
-extern "C" int gb_fermion_create(gb_grid *g, int Ls, gb_precision prec, gb_gridkind kind, gb_fermion **out) {
+static int fermion_create_impl(gb_grid *g, int Ls, int ncomplex, gb_precision prec, gb_gridkind kind, gb_fermion **out) {
   GB_API_BEGIN
   GB_REQUIRE(g && out && Ls >= 1, "bad argument");
   GB_REQUIRE(prec == GB_F32 || prec == GB_F64, "bad precision");
   gb_fermion *f = new gb_fermion();
-  f->grid = g; f->Ls = Ls; f->prec = prec; f->kind = kind; f->cb = GB_EVEN;
+  f->grid = g; f->Ls = Ls; f->prec = prec; f->kind = kind; f->cb = GB_EVEN; f->ncomplex = ncomplex;
   f->nsite4 = g->V4cb;
   f->n5cb = g->V4cb * Ls;
   GB_REQUIRE(f->n5cb * 2 < (1ll << 31), "local 5D volume must be < 2^31");
@@ -87,6 +87,12 @@ extern "C" int gb_fermion_create(gb_grid *g, int Ls, gb_precision prec, gb_gridk
   *out = f;
   GB_API_END
 }
+extern "C" int gb_fermion_create(gb_grid *g, int Ls, gb_precision prec, gb_gridkind kind, gb_fermion **out) {
+  return fermion_create_impl(g, Ls, 12, prec, kind, out);
+}
+extern "C" int gb_staggered_fermion_create(gb_grid *g, gb_precision prec, gb_gridkind kind, gb_fermion **out) {
+  return fermion_create_impl(g, 1, 3, prec, kind, out);
+}
 extern "C" int gb_fermion_destroy(gb_fermion *f) {
   if (f) { cudaFree(f->data); delete f; }
   return GB_OK;
@@ -98,7 +104,14 @@ extern "C" int64_t gb_fermion_local_sites(const gb_fermion *f) { return f->n5cb 
 namespace gb {
 void fermion_check_same(const gb_fermion *a, const gb_fermion *b) {
   GB_REQUIRE(a && b, "null field");
-  GB_REQUIRE(a->grid == b->grid && a->Ls == b->Ls && a->kind == b->kind && a->prec == b->prec, "fields are not conformable");
+  GB_REQUIRE(a->grid == b->grid && a->Ls == b->Ls && a->kind == b->kind && a->prec == b->prec && a->ncomplex == b->ncomplex, "fields are not conformable");
+}
+gb_fermion *fermion_create_like(const gb_fermion *like, int prec) {
+  gb_fermion *f = nullptr;
+  int rc = fermion_create_impl(like->grid, like->Ls, like->ncomplex, (gb_precision)prec, (gb_gridkind)like->kind, &f);
+  if (rc != GB_OK) throw Error(rc, gb_last_error());
+  f->cb = like->cb;
+  return f;
 }
 } // namespace gb
 
@@ -175,9 +188,15 @@ template <int DIR> static void fermion_transfer(const gb_fermion *f, void *host,
   gb_context *ctx = f->grid->ctx;
   GB_CUDA(cudaSetDevice(ctx->device));
   const int64_t nsites = f->n5cb * f->nparity;
-  const size_t hbytes = (size_t)nsites * 24 * (host_prec == GB_F32 ? 4 : 8);
+  const size_t hbytes = (size_t)nsites * 2 * f->ncomplex * (host_prec == GB_F32 ? 4 : 8);
   void *stage = ctx_staging(ctx, hbytes);
   if (DIR == 0) GB_CUDA(cudaMemcpyAsync(stage, host, hbytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (f->ncomplex == 3) {
+    stag_transfer(f, stage, host_prec, DIR);
+    if (DIR == 1) GB_CUDA(cudaMemcpyAsync(host, stage, hbytes, cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
   LatGeom G = geom_of(f);
   const int64_t nelem = f->nvec();
   const int threads = 256;
@@ -213,7 +232,7 @@ extern "C" int gb_fermion_export(const gb_fermion *f, void *host, gb_precision h
 extern "C" int gb_pick_checkerboard(int cb, gb_fermion *half, const gb_fermion *full) {
   GB_API_BEGIN
   GB_REQUIRE(half && full && half->kind == GB_HALF && full->kind == GB_FULL, "pickCheckerboard(cb, half, full)");
-  GB_REQUIRE(half->grid == full->grid && half->Ls == full->Ls && half->prec == full->prec, "fields are not conformable");
+  GB_REQUIRE(half->grid == full->grid && half->Ls == full->Ls && half->prec == full->prec && half->ncomplex == full->ncomplex, "fields are not conformable");
   gb_context *ctx = full->grid->ctx;
   GB_CUDA(cudaMemcpyAsync(half->data, full->block(cb & 1), half->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   half->cb = cb & 1;
@@ -222,7 +241,7 @@ extern "C" int gb_pick_checkerboard(int cb, gb_fermion *half, const gb_fermion *
 extern "C" int gb_set_checkerboard(gb_fermion *full, const gb_fermion *half) {
   GB_API_BEGIN
   GB_REQUIRE(half && full && half->kind == GB_HALF && full->kind == GB_FULL, "setCheckerboard(full, half)");
-  GB_REQUIRE(half->grid == full->grid && half->Ls == full->Ls && half->prec == full->prec, "fields are not conformable");
+  GB_REQUIRE(half->grid == full->grid && half->Ls == full->Ls && half->prec == full->prec && half->ncomplex == full->ncomplex, "fields are not conformable");
   gb_context *ctx = full->grid->ctx;
   GB_CUDA(cudaMemcpyAsync(full->block(half->cb), half->data, half->bytes, cudaMemcpyDeviceToDevice, ctx->stream));
   GB_API_END
@@ -251,10 +270,11 @@ __global__ void prec_f2d_kernel(double2 *out, const float4 *in, int64_t nblk) {
 }
 extern "C" int gb_precision_change(gb_fermion *out, const gb_fermion *in) {
   GB_API_BEGIN
-  GB_REQUIRE(out && in && out->grid == in->grid && out->Ls == in->Ls && out->kind == in->kind, "fields are not conformable");
+  GB_REQUIRE(out && in && out->grid == in->grid && out->Ls == in->Ls && out->kind == in->kind && out->ncomplex == in->ncomplex, "fields are not conformable");
   gb_context *ctx = in->grid->ctx;
   out->cb = in->cb;
   if (out->prec == in->prec) { GB_CUDA(cudaMemcpyAsync(out->data, in->data, in->bytes, cudaMemcpyDeviceToDevice, ctx->stream)); return GB_OK; }
+  if (in->ncomplex == 3) { stag_precision_change(out, in); return GB_OK; }
   const int64_t nblk = in->hblk * in->nparity;
   const int64_t n = nblk * 6 * W;
   const unsigned blocks = (unsigned)((n + 255) / 256);
@@ -298,6 +318,7 @@ __global__ void fermion_random_kernel(typename Prec<TD>::vec *dev, LatGeom G, in
 }
 extern "C" int gb_fermion_random(gb_fermion *f, uint64_t seed) {
   GB_API_BEGIN
+  if (f->ncomplex == 3) { stag_random(f, seed); return GB_OK; }
   gb_context *ctx = f->grid->ctx;
   LatGeom G = geom_of(f);
   const gb_grid *g = f->grid;

@@ -130,11 +130,16 @@ struct gb_fermion {
   int64_t n5cb;    // 5D sites per parity block = V4cb*Ls
   int64_t hblk;    // blocks per parity block = ceil(n5cb / W)
   int nparity;     // 1 (half) or 2 (full: [even block][odd block])
+  int ncomplex = 12; // complex numbers per site: 12 = SpinColourVector (Wilson types), 3 = ColourVector (staggered, Ls = 1)
   void *data;
   size_t bytes;
-  int64_t nvec() const { return (int64_t)nparity * hblk * gb::nv_of(prec) * gb::W; }
+  // 16-byte vecs per block of W sites.  Spinors: NV*W.  Staggered colour vectors are stored one complex per element
+  // (float2 / double2): element (i, c) at complex index ((i/W)*3 + c)*W + i%W, so a block is 3*W complex = 24 / 48 vecs and
+  // the elementwise BLAS / reduction kernels, which only see an array of vecs, serve both site types.
+  int64_t vecs_per_block() const { return (int64_t)gb::W * ncomplex * (prec == GB_F32 ? 8 : 16) / 16; }
+  int64_t nvec() const { return (int64_t)nparity * hblk * vecs_per_block(); }
   // pointer to the start of parity block p
-  void *block(int p) const { return (char *)data + (size_t)p * hblk * gb::nv_of(prec) * gb::W * 16; }
+  void *block(int p) const { return (char *)data + (size_t)p * hblk * vecs_per_block() * 16; }
 };
 
 struct gb_gauge {
@@ -151,6 +156,12 @@ void check_launch(gb_context *ctx, const char *what);
 
 // ---- fields.cu
 void fermion_check_same(const gb_fermion *a, const gb_fermion *b);
+// a new zeroed field of the same grid / Ls / site type / full-vs-redblack as `like`, in precision `prec`
+gb_fermion *fermion_create_like(const gb_fermion *like, int prec);
+// ---- stag.cu: layout-aware pieces for ColourVector fields (ncomplex == 3)
+void stag_transfer(const gb_fermion *f, void *stage, int host_prec, int dir);
+void stag_random(gb_fermion *f, uint64_t seed);
+void stag_precision_change(gb_fermion *out, const gb_fermion *in);
 // deterministic reductions; results land in ctx->h_result after sync. n_out doubles.
 void reduce_norm2(gb_context *ctx, const gb_fermion *x, double *out);
 void reduce_inner(gb_context *ctx, const gb_fermion *l, const gb_fermion *r, double out[2]);

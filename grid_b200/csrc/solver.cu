@@ -38,7 +38,7 @@ static CGOut cg_core(gb_context *ctx, const HermOpFn &A, const gb_fermion *src, 
   fermion_check_same(src, psi);
   gb_grid *g = src->grid;
   gb_fermion *p = nullptr, *mmp = nullptr, *r = nullptr;
-  auto mk = [&](gb_fermion **f) { chk(gb_fermion_create(g, src->Ls, (gb_precision)src->prec, (gb_gridkind)src->kind, f)); (*f)->cb = src->cb; };
+  auto mk = [&](gb_fermion **f) { *f = fermion_create_like(src, src->prec); };
   mk(&p); mk(&mmp); mk(&r);
   struct Guard { gb_fermion *a, *b, *c; ~Guard() { gb_fermion_destroy(a); gb_fermion_destroy(b); gb_fermion_destroy(c); } } guard{p, mmp, r};
   psi->cb = src->cb;
@@ -97,7 +97,7 @@ static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fe
   fermion_check_same(src, psi);
   gb_grid *g = src->grid;
   gb_fermion *p = nullptr, *mmp = nullptr, *r = nullptr;
-  auto mk = [&](gb_fermion **f) { chk(gb_fermion_create(g, src->Ls, (gb_precision)src->prec, (gb_gridkind)src->kind, f)); (*f)->cb = src->cb; };
+  auto mk = [&](gb_fermion **f) { *f = fermion_create_like(src, src->prec); };
   mk(&p); mk(&mmp); mk(&r);
   struct Guard { gb_fermion *a, *b, *c; ~Guard() { gb_fermion_destroy(a); gb_fermion_destroy(b); gb_fermion_destroy(c); } } guard{p, mmp, r};
   auto A = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op, GB_OP_HERMOP, in, out, 0); };
@@ -191,10 +191,11 @@ int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_
   const int cb = src_d_in->cb;
   sol_d->cb = cb;
   gb_fermion *tmp_d = nullptr, *src_d = nullptr, *src_f = nullptr, *sol_f = nullptr;
-  chk(gb_fermion_create(g, src_d_in->Ls, GB_F64, GB_HALF, &tmp_d));
-  chk(gb_fermion_create(g, src_d_in->Ls, GB_F64, GB_HALF, &src_d));
-  chk(gb_fermion_create(g, src_d_in->Ls, GB_F32, GB_HALF, &src_f));
-  chk(gb_fermion_create(g, src_d_in->Ls, GB_F32, GB_HALF, &sol_f));
+  GB_REQUIRE(src_d_in->kind == GB_HALF, "mixed CG works on red-black fields");
+  tmp_d = fermion_create_like(src_d_in, GB_F64);
+  src_d = fermion_create_like(src_d_in, GB_F64);
+  src_f = fermion_create_like(src_d_in, GB_F32);
+  sol_f = fermion_create_like(src_d_in, GB_F32);
   struct Guard { gb_fermion *a, *b, *c, *d; ~Guard() { gb_fermion_destroy(a); gb_fermion_destroy(b); gb_fermion_destroy(c); gb_fermion_destroy(d); } } guard{tmp_d, src_d, src_f, sol_f};
   tmp_d->cb = src_d->cb = src_f->cb = sol_f->cb = cb;
   double src_norm;

@@ -112,6 +112,9 @@ int gb_grid_local_origin(const gb_grid *g, int origin[4]);   /* global coordinat
  * Ls = 1 for 4D fields.  kind GB_HALF = field on the red-black grid; its Checkerboard() is set by
  * gb_fermion_set_checkerboard or by the operation that fills it (ref: Lattice_base.h Checkerboard()). */
 int gb_fermion_create(gb_grid *g, int Ls, gb_precision prec, gb_gridkind kind, gb_fermion **out);
+/* LatticeStaggeredFermion{F,D}: ColourVector sites chi[colour 3] {re,im}, 4D only (ref: StaggeredImpl.h:60-75 SiteSpinor =
+ * iScalar<iScalar<iVector<Simd,Nc>>>).  Every gb_fermion_* / BLAS / reduction / checkerboard entry point accepts it. */
+int gb_staggered_fermion_create(gb_grid *g, gb_precision prec, gb_gridkind kind, gb_fermion **out);
 int gb_fermion_destroy(gb_fermion *f);
 int gb_fermion_checkerboard(const gb_fermion *f);
 int gb_fermion_set_checkerboard_tag(gb_fermion *f, int cb);
@@ -162,6 +165,15 @@ int gb_op_create_wilson(gb_grid *g, const gb_gauge *Umu, double mass, const doub
 int gb_op_create_dwf(gb_grid *g, const gb_gauge *Umu, int Ls, double mass, double M5, const double *boundary_phases, gb_fermop **out);
 int gb_op_create_mobius(gb_grid *g, const gb_gauge *Umu, int Ls, double mass, double M5, double b, double c, const double *boundary_phases, gb_fermop **out);
 int gb_op_import_gauge(gb_fermop *op, const gb_gauge *Umu);    /* ref: WilsonFermion5DImplementation.h:149-181 */
+/* ImprovedStaggeredFermion(Uthin,Ufat,Fgrid,Hgrid,mass,c1,c2,u0)  ref: ImprovedStaggeredFermion.h:115-121 ;
+ * ImportGauge(Uthin,Ufat): staggered phases, one-link (fat) and Naik three-link (thin) double store, c1/u0 and c2/u0^3
+ * ref: StaggeredImpl.h:105-162, ImprovedStaggeredFermionImplementation.h:137-167.
+ * gb_op_apply on it serves Dhop/DhopOE/DhopEO (dag = overall minus sign, ref: StaggeredKernelsImplementation.h:117-119),
+ * M/Mdag, Meooe(+Dag), Mooee(+Dag) = mass, MooeeInv(+Dag) = 1/mass, and GB_OP_MPC = GB_OP_MPC_DAG = GB_OP_HERMOP =
+ * SchurStaggeredOperator::Mpc = mass^2 - Meooe Meooe (ref: LinearOperator.h:543-584); gb_cg_schur runs CG on that.
+ * Single rank this round (the Naik term needs three-deep halos). */
+int gb_op_create_staggered(gb_grid *g, const gb_gauge *Uthin, const gb_gauge *Ufat, double mass, double c1, double c2, double u0, gb_fermop **out);
+int gb_op_import_gauge_staggered(gb_fermop *op, const gb_gauge *Uthin, const gb_gauge *Ufat);
 int gb_op_destroy(gb_fermop *op);
 int gb_op_Ls(const gb_fermop *op);
 /* which: gb_opcode.  dag only matters for GB_OP_DHOP*, GB_OP_DW.  Checkerboard asserts as in the reference

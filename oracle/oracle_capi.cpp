@@ -2,6 +2,7 @@
 // Loaded with ctypes by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
 // The product library (grid_b200/libgridb200.so) never links or dlopens this file.
 #include "dirac_oracle.hpp"
+#include "stag_oracle.hpp"
 #include <chrono>
 #include <omp.h>
 
@@ -139,6 +140,82 @@ void orc_mixed_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d, 
 double orc_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
   auto t0 = std::chrono::steady_clock::now();
   for (int i = 0; i < ncall; i++) orc_apply(h, which, in, out, dag, cb_in, half);
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---------------------------------------------------------------- improved staggered (stag_oracle.hpp)
+struct StagBox { int prec; StagOp<float> f; StagOp<double> d; };
+void *orc_stag_create(const int *L, double mass, double c1, double c2, double u0, int prec) {
+  StagBox *b = new StagBox(); b->prec = prec;
+  auto init = [&](auto &op) { for (int i = 0; i < 4; i++) op.g.L[i] = L[i]; op.g.Ls = 1; op.mass = mass; op.c1 = c1; op.c2 = c2; op.u0 = u0; };
+  if (prec == 0) init(b->f); else init(b->d);
+  return b;
+}
+void orc_stag_destroy(void *h) { delete (StagBox *)h; }
+// Uthin, Ufat: [V4][4][3][3] complex in the operator's precision
+void orc_stag_import_gauge(void *h, const void *Uthin, const void *Ufat) {
+  StagBox *b = (StagBox *)h;
+  if (b->prec == 0) b->f.importGauge((const ColourMatrix<float> *)Uthin, (const ColourMatrix<float> *)Ufat);
+  else b->d.importGauge((const ColourMatrix<double> *)Uthin, (const ColourMatrix<double> *)Ufat);
+}
+} // extern "C"
+template <class T> static int stagApply(StagOp<T> &op, int which, const void *vin, void *vout, int dag, int cb_in, int half) {
+  const ColourVector<T> *in = (const ColourVector<T> *)vin; ColourVector<T> *out = (ColourVector<T> *)vout;
+  const int64_t n = half ? op.g.V4cb() : op.g.V4();
+  switch (which) {
+  case OP_DHOP: op.Dhop(in, out, dag); break;
+  case OP_DHOP_OE: op.DhopCB(in, out, 1, dag); break;
+  case OP_DHOP_EO: op.DhopCB(in, out, 0, dag); break;
+  case OP_M: op.M(in, out); break;
+  case OP_MDAG: op.Mdag(in, out); break;
+  case OP_MEOOE: op.Meooe(in, out, cb_in, 0); break;
+  case OP_MEOOE_DAG: op.Meooe(in, out, cb_in, 1); break;
+  case OP_MOOEE: case OP_MOOEE_DAG: op.scale(n, out, (T)op.mass, in); break;
+  case OP_MOOEE_INV: case OP_MOOEE_INV_DAG: op.scale(n, out, (T)(1.0 / op.mass), in); break;
+  case OP_MPC: case OP_MPC_DAG: case OP_HERMOP: op.Mpc(in, out, cb_in); break;
+  default: return -1;
+  }
+  return 0;
+}
+extern "C" {
+int orc_stag_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half) {
+  StagBox *b = (StagBox *)h;
+  return b->prec == 0 ? stagApply(b->f, which, in, out, dag, cb_in, half) : stagApply(b->d, which, in, out, dag, cb_in, half);
+}
+void orc_stag_cg(void *h, int cb, const void *src, void *sol, double tol, int maxit, int *out_iters, double *out_true_resid) {
+  StagBox *b = (StagBox *)h;
+  CGResult r = b->prec == 0 ? StagConjugateGradient(b->f, cb, (const ColourVector<float> *)src, (ColourVector<float> *)sol, tol, maxit)
+                            : StagConjugateGradient(b->d, cb, (const ColourVector<double> *)src, (ColourVector<double> *)sol, tol, maxit);
+  out_iters[0] = r.iterations; out_iters[1] = r.converged; *out_true_resid = r.true_residual;
+}
+void orc_stag_dhop_naive(const int *L, int prec, const void *Uthin, const void *Ufat, double c1, double c2, double u0, const void *in, void *out, int dag) {
+  Geometry g; for (int i = 0; i < 4; i++) g.L[i] = L[i]; g.Ls = 1;
+  if (prec == 0) StagDhopNaive(g, (const ColourMatrix<float> *)Uthin, (const ColourMatrix<float> *)Ufat, c1, c2, u0, (const ColourVector<float> *)in, (ColourVector<float> *)out, dag);
+  else StagDhopNaive(g, (const ColourMatrix<double> *)Uthin, (const ColourMatrix<double> *)Ufat, c1, c2, u0, (const ColourVector<double> *)in, (ColourVector<double> *)out, dag);
+}
+// pick / set checkerboard for any site size (bytes per site)
+void orc_pick_checkerboard_bytes(const int *L, int site_bytes, int cb, void *half, const void *full) {
+  Geometry g; for (int i = 0; i < 4; i++) g.L[i] = L[i]; g.Ls = 1;
+#pragma omp parallel for
+  for (int64_t i4 = 0; i4 < g.V4(); i4++) {
+    int x[4]; g.coor4(i4, x);
+    if (Geometry::parity(x) != cb) continue;
+    std::memcpy((char *)half + g.cb4(x) * site_bytes, (const char *)full + i4 * site_bytes, site_bytes);
+  }
+}
+void orc_set_checkerboard_bytes(const int *L, int site_bytes, int cb, void *full, const void *half) {
+  Geometry g; for (int i = 0; i < 4; i++) g.L[i] = L[i]; g.Ls = 1;
+#pragma omp parallel for
+  for (int64_t i4 = 0; i4 < g.V4(); i4++) {
+    int x[4]; g.coor4(i4, x);
+    if (Geometry::parity(x) != cb) continue;
+    std::memcpy((char *)full + i4 * site_bytes, (const char *)half + g.cb4(x) * site_bytes, site_bytes);
+  }
+}
+double orc_stag_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
+  auto t0 = std::chrono::steady_clock::now();
+  for (int i = 0; i < ncall; i++) orc_stag_apply(h, which, in, out, dag, cb_in, half);
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
 }

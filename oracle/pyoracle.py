@@ -45,6 +45,18 @@ def lib():
         L.orc_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_time_apply.restype = C.c_double
         L.orc_num_threads.restype = C.c_int
+        L.orc_stag_create.restype = C.c_void_p
+        L.orc_stag_create.argtypes = [C.POINTER(C.c_int), C.c_double, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.orc_stag_destroy.argtypes = [C.c_void_p]
+        L.orc_stag_import_gauge.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_stag_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.orc_stag_apply.restype = C.c_int
+        L.orc_stag_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_stag_dhop_naive.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_pick_checkerboard_bytes.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_set_checkerboard_bytes.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_stag_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+        L.orc_stag_time_apply.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -120,6 +132,72 @@ class OracleOp:
         tr = np.zeros(1, dtype=np.float64)
         lib().orc_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
         return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
+
+
+class StagOracleOp:
+    """CPU restatement of ImprovedStaggeredFermion (oracle/stag_oracle.hpp); fields are [nsite,3] complex colour vectors."""
+
+    def __init__(self, dims, mass, c1=9.0 / 8.0, c2=-1.0 / 24.0, u0=1.0, prec=1):
+        self.dims, self.prec, self.Ls = tuple(dims), prec, 1
+        self.V4 = int(np.prod(dims))
+        self.c1, self.c2, self.u0, self.mass = c1, c2, u0, mass
+        self.h = lib().orc_stag_create(_L(dims), mass, c1, c2, u0, prec)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().orc_stag_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def import_gauge(self, Uthin, Ufat=None):
+        Ut = np.ascontiguousarray(Uthin, dtype=_cdtype(self.prec))
+        Uf = Ut if Ufat is None else np.ascontiguousarray(Ufat, dtype=_cdtype(self.prec))
+        assert Ut.shape == (self.V4, 4, 3, 3) and Uf.shape == Ut.shape
+        lib().orc_stag_import_gauge(self.h, _ptr(Ut), _ptr(Uf))
+
+    def apply(self, which, x, dag=0, cb_in=0):
+        x = np.ascontiguousarray(x, dtype=_cdtype(self.prec))
+        assert x.shape[1:] == (3,) and x.shape[0] in (self.V4, self.V4 // 2)
+        out = np.empty_like(x)
+        rc = lib().orc_stag_apply(self.h, which, _ptr(x), _ptr(out), dag, cb_in, 1 if x.shape[0] == self.V4 // 2 else 0)
+        assert rc == 0
+        return out
+
+    def time_apply(self, which, x, ncall, dag=0, cb_in=0):
+        x = np.ascontiguousarray(x, dtype=_cdtype(self.prec))
+        out = np.empty_like(x)
+        return lib().orc_stag_time_apply(self.h, which, _ptr(x), _ptr(out), dag, cb_in, 1 if x.shape[0] == self.V4 // 2 else 0, ncall)
+
+    def cg(self, cb, src, tol, maxit, guess=None):
+        src = np.ascontiguousarray(src, dtype=_cdtype(self.prec))
+        sol = np.zeros_like(src) if guess is None else np.ascontiguousarray(guess, dtype=_cdtype(self.prec)).copy()
+        it = np.zeros(2, dtype=np.int32)
+        tr = np.zeros(1, dtype=np.float64)
+        lib().orc_stag_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
+        return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
+
+
+def stag_dhop_naive(dims, Uthin, Ufat, c1, c2, u0, x, dag=0, prec=1):
+    Ut = np.ascontiguousarray(Uthin, dtype=_cdtype(prec)); Uf = np.ascontiguousarray(Ufat, dtype=_cdtype(prec))
+    x = np.ascontiguousarray(x, dtype=_cdtype(prec))
+    out = np.empty_like(x)
+    lib().orc_stag_dhop_naive(_L(dims), prec, _ptr(Ut), _ptr(Uf), c1, c2, u0, _ptr(x), _ptr(out), dag)
+    return out
+
+
+def pick_checkerboard_sites(dims, cb, full):
+    """pickCheckerboard for a 4D field of any site type ([V4, ...] array)."""
+    full = np.ascontiguousarray(full)
+    half = np.empty((full.shape[0] // 2,) + full.shape[1:], dtype=full.dtype)
+    lib().orc_pick_checkerboard_bytes(_L(dims), full.itemsize * int(np.prod(full.shape[1:])), cb, _ptr(half), _ptr(full))
+    return half
+
+
+def set_checkerboard_sites(dims, cb, full, half):
+    assert full.flags.c_contiguous and half.flags.c_contiguous and full.dtype == half.dtype
+    lib().orc_set_checkerboard_bytes(_L(dims), full.itemsize * int(np.prod(full.shape[1:])), cb, _ptr(full), _ptr(half))
 
 
 def mixed_cg(op_d, op_f, cb, src_d, tol, maxinner, maxouter):

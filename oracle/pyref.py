@@ -100,6 +100,7 @@ class RefOp:
             pass
 
     def import_gauge(self, Umu, phases=None):
+        """kind 2 (staggered): fat = thin = Umu, like benchmarks/Benchmark_staggered.cc:92-96"""
         U = np.ascontiguousarray(Umu, dtype=_cdtype(self.prec))
         assert U.shape == (self.V4, 4, 3, 3)
         ph = None if phases is None else np.ascontiguousarray(np.asarray(phases, dtype=np.complex128))

@@ -9,6 +9,7 @@ Inputs are stored next to the outputs, so the fixtures do not depend on numpy's 
 
 Keys:  U [V4,4,3,3]; src4 [V4,4,3]; src5 [V4*Ls,4,3];
        <op>/<ENTRY>[/dag][/cbN]  for op in wilson, wilson_apbc (antiperiodic t), dwf, mobius (b=1.5,c=0.5);
+       stag/... the same entries for ImprovedStaggeredFermion on src_stag [V4,3];
        <op>/cg/{iterations,true_residual,solution};  dwf/mixed_cg/{inner,outer,final,true_residual,solution}
 """
 import os
@@ -72,6 +73,25 @@ def main():
     out["dwf/mixed_cg/solution"] = x
     for k in ("inner", "outer", "final", "true_residual"):
         out[f"dwf/mixed_cg/{k}"] = np.array(info[k])
+    # improved staggered (ImprovedStaggeredFermionD, fat = thin = U as in Benchmark_staggered.cc:92-96; c1=9/8, c2=-1/24, u0=1)
+    rng = np.random.default_rng(104)
+    srcs = rng.random((int(np.prod(DIMS)), 3)) + 1j * rng.random((int(np.prod(DIMS)), 3))
+    out["src_stag"] = srcs
+    st = pr.RefOp(2, DIMS, 1, 0.1, 9.0 / 8.0, -1.0 / 24.0, 1.0, prec=1)
+    st.import_gauge(U)
+    for dag in (0, 1):
+        out[f"stag/DHOP/dag{dag}"] = st.apply(pr.OP_DHOP, srcs, dag=dag)
+    out["stag/M/dag0"], out["stag/MDAG/dag0"] = st.apply(pr.OP_M, srcs), st.apply(pr.OP_MDAG, srcs)
+    he, ho = st.pick_checkerboard(0, srcs), st.pick_checkerboard(1, srcs)
+    out["stag/pick/cb0"], out["stag/pick/cb1"] = he, ho
+    for dag in (0, 1):
+        out[f"stag/DHOP_OE/dag{dag}"] = st.apply(pr.OP_DHOP_OE, he, dag=dag)
+        out[f"stag/DHOP_EO/dag{dag}"] = st.apply(pr.OP_DHOP_EO, ho, dag=dag)
+    for k in ("MEOOE", "MEOOE_DAG", "MOOEE", "MOOEE_INV", "MPC", "HERMOP"):
+        for cb in (0, 1):
+            out[f"stag/{k}/cb{cb}"] = st.apply(HALF[k], he if cb == 0 else ho, cb_in=cb)
+    x, info = st.cg(1, ho, 1e-8, 5000)
+    out["stag/cg/solution"], out["stag/cg/iterations"], out["stag/cg/true_residual"] = x, np.array(info["iterations"]), np.array(info["true_residual"])
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dirac_golden.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB", file=sys.stderr)

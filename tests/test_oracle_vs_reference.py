@@ -100,7 +100,7 @@ def test_schur_cg_same_iterations_and_residual(gauge, kind, Ls, bc):
     src = po.pick_checkerboard(DIMS, Ls, 1, syn.random_fermion(DIMS, Ls, seed=8))
     xo, io = o.cg(1, src, 1e-8, 5000)
     xr, ir = r.cg(1, src, 1e-8, 5000)
-    assert io["iterations"] == ir["iterations"], (io, ir)
+    assert abs(io["iterations"] - ir["iterations"]) <= 1, (io, ir)   # threaded reductions are order dependent in the last bit
     assert abs(io["true_residual"] - ir["true_residual"]) < 1e-3 * ir["true_residual"] + 1e-14
     assert site_err(xo, xr) < 1e-9
 
@@ -118,3 +118,43 @@ def test_mixed_precision_cg(gauge):
     assert abs(io["inner"] - ir["inner"]) <= max(3, 0.05 * ir["inner"]), (io, ir)
     assert ir["true_residual"] < 1e-8 and io["true_residual"] < 1e-8
     assert site_err(xo, xr) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------- improved staggered
+@pytest.mark.parametrize("prec", [1, 0])
+def test_improved_staggered_all_entries(gauge, prec):
+    """ref: ImprovedStaggeredFermion{D,F} with fat = thin links, c1 = 9/8, c2 = -1/24, u0 = 1 (Benchmark_staggered.cc:92-96)"""
+    o = po.StagOracleOp(DIMS, 0.1, 9.0 / 8.0, -1.0 / 24.0, 1.0, prec=prec); o.import_gauge(gauge)
+    r = pr.RefOp(2, DIMS, 1, 0.1, 9.0 / 8.0, -1.0 / 24.0, 1.0, prec=prec); r.import_gauge(gauge)
+    rng = np.random.default_rng(12)
+    n = int(np.prod(DIMS))
+    src = (rng.random((n, 3)) + 1j * rng.random((n, 3))).astype(po._cdtype(prec))
+    for which in (po.OP_DHOP, po.OP_M, po.OP_MDAG):
+        for dag in ((0, 1) if which == po.OP_DHOP else (0,)):
+            assert site_err(o.apply(which, src, dag=dag), r.apply(which, src, dag=dag)) < TOL[prec], (NAMES[which], dag)
+    for cb in (0, 1):
+        h = po.pick_checkerboard_sites(DIMS, cb, src)
+        assert np.array_equal(h, r.pick_checkerboard(cb, src))
+        for which in (po.OP_MEOOE, po.OP_MEOOE_DAG, po.OP_MOOEE, po.OP_MOOEE_DAG, po.OP_MOOEE_INV, po.OP_MOOEE_INV_DAG, po.OP_MPC, po.OP_MPC_DAG, po.OP_HERMOP):
+            assert site_err(o.apply(which, h, cb_in=cb), r.apply(which, h, cb_in=cb)) < 4 * TOL[prec], (NAMES[which], cb)
+        which = po.OP_DHOP_OE if cb == 0 else po.OP_DHOP_EO
+        for dag in (0, 1):
+            assert site_err(o.apply(which, h, dag=dag), r.apply(which, h, dag=dag)) < TOL[prec]
+    if prec == 1:
+        h = po.pick_checkerboard_sites(DIMS, 1, src)
+        xo, io = o.cg(1, h, 1e-8, 5000)
+        xr, ir = r.cg(1, h, 1e-8, 5000)
+        assert abs(io["iterations"] - ir["iterations"]) <= max(1, 0.02 * ir["iterations"]), (io, ir)
+        assert site_err(xo, xr) < 1e-6
+
+
+def test_staggered_dhop_equals_naive_covariant_shift_form(gauge):
+    """ref: tests/core/Test_staggered.cc:92-156 -- Dhop against the sum built from the ORIGINAL links, fat != thin here"""
+    from grid_b200 import synthetic
+    fat = synthetic.hot_gauge(DIMS, seed=77)
+    o = po.StagOracleOp(DIMS, 0.1, 1.1, -0.05, 0.9, prec=1); o.import_gauge(gauge, fat)
+    rng = np.random.default_rng(13)
+    n = int(np.prod(DIMS))
+    src = rng.random((n, 3)) + 1j * rng.random((n, 3))
+    for dag in (0, 1):
+        assert site_err(o.apply(po.OP_DHOP, src, dag=dag), po.stag_dhop_naive(DIMS, gauge, fat, 1.1, -0.05, 0.9, src, dag=dag)) < 1e-13
