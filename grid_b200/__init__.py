@@ -366,7 +366,8 @@ class FermionOperator:
         lib().gb_op_set_tiling(self.h, by, bz, bt)
 
     def set_fast_kernel(self, on):
-        lib().gb_op_set_fast_kernel(self.h, 1 if on else 0)
+        """True/1: default kernel selection; 2: micro-block kernel instead of the column-sweep kernel; False/0: generic kernel"""
+        lib().gb_op_set_fast_kernel(self.h, int(on))
 
     def set_overlap(self, on):
         lib().gb_op_set_overlap(self.h, 1 if on else 0)

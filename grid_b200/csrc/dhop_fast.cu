@@ -1,5 +1,7 @@
 // dhop_fast.cu -- instantiations + launcher of the tuned fp32 hopping kernel (see dhop_fast.cuh)
 #include "dhop_fast.cuh"
+#include "dhop_col.cuh"
+#include <cstdlib>
 #include "fermop.hpp"
 #include <algorithm>
 
@@ -22,12 +24,69 @@ template <int LS> static void launch_ls(const FastArgs &a, int nparity, int dag,
   }
 }
 
+// ---- column-sweep kernel (dhop_col.cuh): single-rank hops and the interior pass of z/t-decomposed lattices
+template <int LS> static void launch_col_ls(const ColArgs &a, dim3 grid, int dag, int interior, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = col_smem_bytes<LS>();
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(dhop_col_kernel<LS, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col_kernel<LS, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col_kernel<LS, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col_kernel<LS, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int threads = COL_NSITE * LS;
+  if (!dag) { if (interior) dhop_col_kernel<LS, 0, 1><<<grid, threads, smem, st>>>(a); else dhop_col_kernel<LS, 0, 0><<<grid, threads, smem, st>>>(a); }
+  else { if (interior) dhop_col_kernel<LS, 1, 1><<<grid, threads, smem, st>>>(a); else dhop_col_kernel<LS, 1, 0><<<grid, threads, smem, st>>>(a); }
+}
+static bool dhop_col_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
+                            const void *const ax[2], double axa, double axb, int interior, cudaStream_t st) {
+  static const bool disabled = getenv("GB_NO_COL") != nullptr;
+  static const int env_n = getenv("GB_COL_N") ? atoi(getenv("GB_COL_N")) : 0;
+  const gb_grid *g = op->grid;
+  const int Ls = op->Ls;
+  if (disabled || op->no_col || !(Ls == 8 || Ls == 12 || Ls == 16)) return false;
+  // decomposed lattices: the interior pass runs beside the pack / exterior / copy kernels of the halo exchange, and two
+  // column CTAs fill an SM's shared memory (207 KB) so those cannot co-reside: measured on 2 B200, t split, 32^4 x 16 per
+  // GPU: 1.248 ms with this kernel as interior pass vs 1.174 ms with the micro-block kernel.  GB_COL_INTERIOR=1 forces it.
+  static const bool col_interior = getenv("GB_COL_INTERIOR") != nullptr;
+  if (interior > 1 || (interior && (!col_interior || (op->comm_dim_mask & 3)))) return false;
+  const int Lxh = g->ldims[0] / 2, Ly = g->ldims[1], Lz = g->ldims[2], Lt = g->ldims[3];
+  if (Lxh % 4 || Ly % 4) return false;
+  int N = env_n > 0 ? env_n : (op->col_n > 0 ? op->col_n : 16);
+  if (N > Lz) N = Lz;
+  while (Lz % N) N--;
+  ColArgs a;
+  const size_t per_parity = (size_t)g->V4cb * 8 * 5;
+  for (int p = 0; p < 2; p++) {
+    a.in[p] = (const float4 *)in[p]; a.out[p] = (float4 *)out[p];
+    a.U[p] = (const float4 *)op->Uds + p * per_parity;
+    a.axpy[p] = ax ? (const float4 *)ax[p] : nullptr;
+  }
+  a.axpy_a = (float)axa; a.axpy_b = (float)axb;
+  a.comm_dim_mask = interior ? op->comm_dim_mask : 0;
+  a.Lxh = Lxh; a.Ly = Ly; a.Lz = Lz; a.Lt = Lt; a.N = N;
+  a.dLt = FastDiv(Lt); a.dNxo = FastDiv(Lxh / 4); a.dNyo = FastDiv(Ly / 4);
+  a.first_parity = parity_out_first;
+  a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
+  dim3 grid((unsigned)(Lt * (Lxh / 4) * (Ly / 4) * (Lz / N)), nparity);
+  switch (Ls) {
+  case 8: launch_col_ls<8>(a, grid, dag, interior, st); break;
+  case 12: launch_col_ls<12>(a, grid, dag, interior, st); break;
+  default: launch_col_ls<16>(a, grid, dag, interior, st); break;
+  }
+  count_launch(op->ctx);
+  check_launch(op->ctx, "dhop_col");
+  return true;
+}
+
 // returns false when the configuration is not covered by the fast path (caller falls back to dhop_kernel)
 bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                       const void *const ax[2], double axa, double axb, int interior, cudaStream_t st, const void *const halo[8],
                       const unsigned long long *flags, unsigned long long epoch) {
   const gb_grid *g = op->grid;
   if (op->prec != GB_F32 || op->disable_fast) return false;
+  if (dhop_col_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, interior, st)) return true;
   const int Ls = op->Ls;
   if (!(Ls == 8 || Ls == 12 || Ls == 16 || Ls == 24 || Ls == 32)) return false;
   if (g->V4cb % FAST_NSITE) return false;

@@ -316,10 +316,12 @@ int gb_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out,
 }
 int gb_op_set_tiling(gb_fermop *op, int by, int bz, int bt) {
   op->By = by; op->Bz = bz; op->Bt = bt;
+  op->col_n = bz;   // column-sweep kernel: z-planes per column
   return GB_OK;
 }
 int gb_op_set_fast_kernel(gb_fermop *op, int enable) {
   op->disable_fast = enable == 0;
+  op->no_col = enable == 2;
   op->use_smat = enable != 0 && op->sm_B != nullptr;
   return GB_OK;
 }

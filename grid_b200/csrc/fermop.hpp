@@ -38,6 +38,8 @@ struct gb_fermop {
   int comm_dim_mask = 0;
   bool overlap_comms = true;
   bool disable_fast = false;   // force the generic kernel (tests compare the two)
+  bool no_col = false;         // fp32: use the micro-block kernel instead of the column-sweep kernel (tests compare them)
+  int col_n = 0;               // z-planes per column of the column-sweep kernel (0 = default 16)
   // multi-GPU: the single-launch pack+hop+halo kernel is EXPERIMENTAL (opt-in with GB_FUSED=1).  It is parity-green on small
   // lattices but can deadlock at 32^4 per GPU: surface CTAs spinning on the neighbours' flags can fill every resident slot
   // before the last pack CTAs of the same launch are scheduled.  Default = pack+send kernel, interior pass, exterior slabs.

@@ -184,7 +184,8 @@ int gb_op_set_tiling(gb_fermop *op, int block_y, int block_z, int block_t);
 /* 1 (default): interior kernel overlaps the face exchange (ref: --comms-overlap, WilsonFermion5DImplementation.h:320-384);
  * 0: exchange then compute (ref: DhopInternalSerialComms, :388-411) */
 int gb_op_set_overlap(gb_fermop *op, int overlap);
-/* 1 (default): fp32 operators use the tuned FFMA2 + TMA kernel where it applies; 0: always the generic kernel */
+/* fp32 operators: 1 (default) = column-sweep kernel (shared-memory z-column reuse) where it applies, else the micro-block
+ * FFMA2 + TMA kernel, else the generic kernel; 2 = skip the column-sweep kernel; 0 = always the generic kernel */
 int gb_op_set_fast_kernel(gb_fermop *op, int enable);
 
 /* ---------------------------------------------------------------- solvers

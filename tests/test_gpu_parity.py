@@ -66,6 +66,8 @@ CONFIGS = {
     "dwf": dict(dims=(4, 4, 4, 6), Ls=16, kind="dwf"),
     "mobius_ls12": dict(dims=(8, 4, 6, 4), Ls=12, kind="mobius", b=1.5, c=0.5),  # Ls not a multiple of the 16-lane block
     "dwf_ls6": dict(dims=(4, 6, 4, 4), Ls=6, kind="dwf"),
+    "dwf_col": dict(dims=(16, 8, 8, 6), Ls=16, kind="dwf"),           # several 4x4 micro-blocks and z-columns: column-sweep kernel
+    "mobius_col_ls8": dict(dims=(8, 12, 4, 4), Ls=8, kind="mobius", b=1.5, c=0.5),
 }
 
 
@@ -192,10 +194,14 @@ def test_fast_and_generic_kernels_agree(setup, dag):
     op.Dhop(fin, o_fast, dag)
     op.set_fast_kernel(False)
     op.Dhop(fin, o_gen, dag)
+    o_mb = setup.field(prec)
+    op.set_fast_kernel(2)                     # micro-block kernel (what the column-sweep kernel falls back to)
+    op.Dhop(fin, o_mb, dag)
     op.set_fast_kernel(True)
     ref = setup.oracle[gb.F64].apply(po.OP_DHOP, h.astype(np.complex128), dag=dag)
     assert site_rel_err(o_fast.export_lex(), ref) < TOL_HOP[prec]
     assert site_rel_err(o_gen.export_lex(), ref) < TOL_HOP[prec]
+    assert site_rel_err(o_mb.export_lex(), ref) < TOL_HOP[prec]
     assert site_rel_err(o_fast.export_lex(), o_gen.export_lex()) < 2 * TOL_HOP[prec]
     # DW = Dhop + (4-M5): exercises the fused axpy epilogue of both kernels
     if setup.kind != "wilson":
