@@ -86,10 +86,10 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
                       const unsigned long long *flags, unsigned long long epoch) {
   const gb_grid *g = op->grid;
   if (op->prec != GB_F32 || op->disable_fast) return false;
-  if (dhop_col_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, interior, st)) return true;
+  if (interior != 3 && dhop_col_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, interior, st)) return true;
   const int Ls = op->Ls;
   if (!(Ls == 8 || Ls == 12 || Ls == 16 || Ls == 24 || Ls == 32)) return false;
-  if (g->V4cb % FAST_NSITE) return false;
+  if (g->V4cb % FAST_NSITE || ((size_t)(g->ldims[0] / 2) * g->ldims[1]) % FAST_NSITE) return false;
   FastArgs a;
   const size_t per_parity = (size_t)g->V4cb * 8 * 5;
   for (int p = 0; p < 2; p++) {
@@ -98,16 +98,30 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
     a.axpy[p] = ax ? (const float4 *)ax[p] : nullptr;
   }
   a.axpy_a = (float)axa; a.axpy_b = (float)axb;
+  // interior == 3: only the sites whose every leg is local (z, t in [1, L-1) of the decomposed dimensions), all 8 legs;
+  //                the surface sites are computed, also with all legs, by the caller's exterior pass -- no read-modify-write
+  const bool inner_box = interior == 3;
+  if (inner_box) {
+    if (op->comm_dim_mask & 3) return false;               // x / y decomposition: caller uses interior + accumulate passes
+    interior = 0;
+  }
   a.comm_dim_mask = interior ? op->comm_dim_mask : 0;
   a.Lxh = g->ldims[0] / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
   a.ibx = gcd_int(a.Lxh, 4); a.iby = gcd_int(a.Ly, 4);
-  int bz = op->Bz <= 0 ? a.Lz : op->Bz;
-  if (bz > a.Lz) bz = a.Lz;
-  while (a.Lz % bz) bz--;
+  a.zo = a.to = 0;
+  int nz = a.Lz, nt = a.Lt;
+  if (inner_box) {
+    if ((op->comm_dim_mask >> 2) & 1) { a.zo = 1; nz = a.Lz - 2; }
+    if ((op->comm_dim_mask >> 3) & 1) { a.to = 1; nt = a.Lt - 2; }
+    if (nz <= 0 || nt <= 0) return true;                   // no interior sites at all
+  }
+  int bz = op->Bz <= 0 ? nz : op->Bz;
+  if (bz > nz) bz = nz;
+  if (nz % bz) { int best = 1; for (int d = 2; d <= 12 && d <= nz; d++) if (nz % d == 0) best = d; bz = best == 1 ? nz : best; }
   a.Bz = bz;
   a.dibx = FastDiv(a.ibx); a.diby = FastDiv(a.iby); a.dNxo = FastDiv(a.Lxh / a.ibx); a.dNyo = FastDiv(a.Ly / a.iby);
-  a.dBz = FastDiv(a.Bz); a.dLt = FastDiv(a.Lt);
-  a.V4cb = (uint32_t)g->V4cb;
+  a.dBz = FastDiv(a.Bz); a.dLt = FastDiv(nt);
+  a.V4cb = (uint32_t)((size_t)a.Lxh * a.Ly * nz * nt);
   a.first_parity = parity_out_first;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
   for (int i = 0; i < 8; i++) a.halo[i] = halo ? (const float4 *)halo[i] : nullptr;

@@ -30,8 +30,9 @@ struct FastArgs {
   int Lxh, Ly, Lz, Lt;
   int ibx, iby, Bz;            // micro-block (ibx x iby) inside rows, z-chunk for the L2 sweep
   FastDiv dibx, diby, dNxo, dNyo, dBz, dLt;
-  uint32_t V4cb;
+  uint32_t V4cb;                // sites visited per parity (the box volume when a box is set)
   int first_parity, origin_parity;
+  int zo, to;                   // box origin in z and t: the kernel visits z in [zo, zo + nz), t in [to, to + nt) (dBz / dLt divide nz / nt)
   // fused multi-GPU mode: this rank's receive buffers (this epoch), epoch flags, rasterisation rotation
   const float4 *halo[8];
   size_t hstride[4];               // float4 between the parity-0 and parity-1 faces
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(FAST_NSITE *LS, (FAST_NSITE * LS <= 256) ? 3 :
     uint32_t xl, yl, xo, yo, zl, t, zh;
     a.dibx.divmod(r, r, xl); a.diby.divmod(r, r, yl); a.dNxo.divmod(r, r, xo); a.dNyo.divmod(r, r, yo);
     a.dBz.divmod(r, r, zl); a.dLt.divmod(r, zh, t);
-    c.xh = xo * a.ibx + xl; c.y = yo * a.iby + yl; c.z = zh * a.Bz + zl; c.t = t;
+    c.xh = xo * a.ibx + xl; c.y = yo * a.iby + yl; c.z = a.zo + zh * a.Bz + zl; c.t = a.to + t;
     if (INTERIOR == 2) {
       if (a.rot_z) { c.z += 1; if (c.z == a.Lz) c.z = 0; }
       if (a.rot_t) { c.t += 1; if (c.t == a.Lt) c.t = 0; }

@@ -38,11 +38,15 @@ def check(name, err, tol):
         fails.append(name)
 
 
+CASES = []
 for mpi in MPIS:
-    ld = (4, 4, 4, 4) if world < 8 else (4, 4, 4, 4)
-    gdims = tuple(l * m for l, m in zip(ld, mpi))
-    gdims = tuple(max(g, 8) if m > 1 else g for g, m in zip(gdims, mpi))
-    for Ls, kind in ((16, "dwf"), (6, "mobius"), (1, "wilson")):
+    gd = tuple(max(4 * m, 8) if m > 1 else 4 for m in mpi)
+    CASES.append((mpi, gd, ((16, "dwf"), (6, "mobius"), (1, "wilson"))))
+    # local x,y = 8: the tuned kernels apply, so a z/t decomposition takes the split-volume path (interior box + surface slabs)
+    gd2 = tuple((8 if d < 2 else 4) * m if m == 1 else max((8 if d < 2 else 4) * m, 8) for d, m in enumerate(mpi))
+    CASES.append((mpi, gd2, ((16, "dwf"), (8, "mobius"))))
+for mpi, gdims, kinds in CASES:
+    for Ls, kind in kinds:
         U = syn.hot_gauge(gdims, seed=3)
         src = syn.random_fermion(gdims, Ls, seed=4)
         grid = gb.GridCartesian(ctx, gdims, mpi)
