@@ -51,7 +51,7 @@ SYMBOLS = [
     ("gb_op_create_mobius", _i, [_vp, _vp, _i, _d, _d, _d, _d, _pd, _pvp]), ("gb_op_import_gauge", _i, [_vp, _vp]),
     ("gb_op_create_staggered", _i, [_vp, _vp, _vp, _d, _d, _d, _d, _pvp]), ("gb_op_import_gauge_staggered", _i, [_vp, _vp, _vp]),
     ("gb_op_destroy", _i, [_vp]), ("gb_op_Ls", _i, [_vp]), ("gb_op_apply", _i, [_vp, _i, _vp, _vp, _i]),
-    ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
+    ("gb_op_dhop_host", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
 ]
@@ -361,6 +361,12 @@ class FermionOperator:
     def DW(self, i, o, dag=0): self._apply(OP_DW, i, o, dag)
     def Meooe5D(self, i, o): self._apply(OP_MEOOE5D, i, o)
     def MeooeDag5D(self, i, o): self._apply(OP_MEOOEDAG5D, i, o)
+
+    def Dhop_host(self, host_in, host_out, dag=0):
+        """Dhop on host-resident full-lattice arrays [V4*Ls,4,3] (lexicographic); pipelined H2D / hop / D2H on one rank."""
+        assert host_in.flags.c_contiguous and host_out.flags.c_contiguous and host_in.dtype == host_out.dtype and host_in.shape == host_out.shape
+        _chk(lib().gb_op_dhop_host(self.h, host_in.ctypes.data_as(C.c_void_p), host_out.ctypes.data_as(C.c_void_p), _prec_of(host_in), dag))
+        return host_out
 
     def set_tiling(self, by=0, bz=0, bt=0):
         lib().gb_op_set_tiling(self.h, by, bz, bt)

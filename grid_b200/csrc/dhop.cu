@@ -608,4 +608,31 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   }
 }
 
+// Hop restricted to the t-slices [t0, t0 + nt) of both output parities, all 8 legs, single rank (periodic wrap inside the
+// local volume).  Used by the host-pipelined Dhop (fields.cu), where slices are computed as their neighbours arrive over PCIe.
+void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st) {
+  const gb_grid *g = op->grid;
+  DhopArgs a;
+  const size_t per_parity = (size_t)g->V4cb * 8 * lv_of(op->prec) * 16;
+  for (int p = 0; p < 2; p++) { a.in[p] = in[p]; a.out[p] = out[p]; a.U[p] = (char *)op->Uds + p * per_parity; a.axpy[p] = nullptr; }
+  a.axpy_a = 1; a.axpy_b = 0;
+  a.comm_dim_mask = 0;
+  a.Ls = op->Ls; a.Lx = g->ldims[0]; a.Lxh = a.Lx / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
+  a.By = a.Ly; a.Bz = a.Lz; a.Bt = a.Lt;
+  a.dLs = FastDiv(a.Ls); a.dLxh = FastDiv(a.Lxh); a.dBy = FastDiv(a.By); a.dBz = FastDiv(a.Bz); a.dBt = FastDiv(a.Bt);
+  a.dNy = FastDiv(1); a.dNz = FastDiv(1);
+  a.first_parity = 0;
+  a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
+  for (int i = 0; i < 8; i++) a.halo[i] = nullptr;
+  for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = 0;
+  a.mode = 0; a.flags = nullptr; a.epoch = 0;
+  a.box_on = 1;
+  a.bo[0] = 0; a.bo[1] = 0; a.bo[2] = 0; a.bo[3] = t0;
+  a.be[0] = a.Lxh; a.be[1] = a.Ly; a.be[2] = a.Lz; a.be[3] = nt;
+  a.dbe0 = FastDiv(a.be[0]); a.dbe1 = FastDiv(a.be[1]); a.dbe2 = FastDiv(a.be[2]);
+  a.n5cb = (uint32_t)((size_t)a.Lxh * a.Ly * a.Lz * nt * op->Ls);
+  if (op->prec == GB_F32) launch_dhop_T<float>(op, a, 2, dag, 0, st);
+  else launch_dhop_T<double>(op, a, 2, dag, 0, st);
+}
+
 } // namespace gb

@@ -179,6 +179,11 @@ int gb_op_Ls(const gb_fermop *op);
 /* which: gb_opcode.  dag only matters for GB_OP_DHOP*, GB_OP_DW.  Checkerboard asserts as in the reference
  * (DhopOE needs in.cb==Even ...).  in and out must be distinct fields of the operator's precision. */
 int gb_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
+/* Dhop(in,out,dag) on HOST-resident full-lattice fields (layout at top of file), for callers whose Lattice objects live in
+ * host memory (the reference's CPU build; ref: FermionOperator.h:72 Dhop + Lattice_transfer.h:1123,1218 for the layout).
+ * Single rank: pipelined over t-slices -- H2D of slice t+1, the hop of slice t and D2H of slice t-1 overlap on three streams,
+ * so the call costs one direction of PCIe traffic.  Decomposed lattices: import, hop, export.  Pinned host memory recommended. */
+int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_out, gb_precision host_prec, int dag);
 /* tuning knob of the hopping kernel's CTA rasterisation (z/t blocking for L2 reuse); 0 = default */
 int gb_op_set_tiling(gb_fermop *op, int block_y, int block_z, int block_t);
 /* 1 (default): interior kernel overlaps the face exchange (ref: --comms-overlap, WilsonFermion5DImplementation.h:320-384);

@@ -387,3 +387,21 @@ def test_device_random_fermion_distribution(ctx):
     assert 0.0 <= v.min() and v.max() < 1.0 and abs(v.mean() - 0.5) < 0.01
     g = gb.LatticeFermion(grid, 4, gb.F32).random(5).export_lex()
     assert np.allclose(g, f.astype(np.complex64))
+
+
+# ------------------------------------------------------------------ host-resident fields through the pipelined entry point
+@pytest.mark.parametrize("prec", [gb.F32, gb.F64])
+@pytest.mark.parametrize("dag", [0, 1])
+def test_dhop_host_pipelined_matches_device_path(setup, prec, dag):
+    """gb_op_dhop_host (H2D / hop / D2H pipelined over t-slices) == import + Dhop + export, and == the oracle"""
+    h = setup.host(61, prec)
+    out_dev = setup.field(prec)
+    setup.dev[prec].Dhop(setup.field(prec).import_lex(h), out_dev, dag)
+    got = setup.dev[prec].Dhop_host(h, np.empty_like(h), dag)
+    ref = setup.oracle[gb.F64].apply(po.OP_DHOP, h.astype(np.complex128), dag=dag)
+    assert site_rel_err(got, ref) < TOL_HOP[prec]
+    assert site_rel_err(got, out_dev.export_lex()) < 2 * TOL_HOP[prec]
+    # host precision may differ from the operator's
+    if prec == gb.F32:
+        got64 = setup.dev[prec].Dhop_host(h.astype(np.complex128), np.empty(h.shape, np.complex128), dag)
+        assert site_rel_err(got64, ref) < TOL_HOP[prec]
