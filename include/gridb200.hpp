@@ -71,11 +71,9 @@ template <gb_precision Prec> class LatticeFermionT {
 public:
   gb_fermion *h = nullptr;
   GridBase *_grid;
-  explicit LatticeFermionT(GridBase *g) : _grid(g) { GB_ASSERT_OK(gb_fermion_create(g->h, g->Ls, Prec, g->redblack ? GB_HALF : GB_FULL, &h)); }
-  LatticeFermionT(const LatticeFermionT &o) : _grid(o._grid) {
-    GB_ASSERT_OK(gb_fermion_create(_grid->h, _grid->Ls, Prec, _grid->redblack ? GB_HALF : GB_FULL, &h));
-    GB_ASSERT_OK(gb_copy(h, o.h));
-  }
+  bool _staggered = false;   // true: one ColourVector per site (LatticeStaggeredFermion), false: SpinColourVector
+  explicit LatticeFermionT(GridBase *g) : _grid(g) { create(); }
+  LatticeFermionT(const LatticeFermionT &o) : _grid(o._grid), _staggered(o._staggered) { create(); GB_ASSERT_OK(gb_copy(h, o.h)); }
   LatticeFermionT &operator=(const LatticeFermionT &o) { GB_ASSERT_OK(gb_copy(h, o.h)); return *this; }
   ~LatticeFermionT() { gb_fermion_destroy(h); }
   GridBase *Grid() const { return _grid; }
@@ -85,9 +83,24 @@ public:
   // import/export of the local lattice in lexicographic order (ref: Lattice_transfer.h:1123,1218)
   void ImportLex(const void *host, gb_precision hp) { GB_ASSERT_OK(gb_fermion_import(h, host, hp)); }
   void ExportLex(void *host, gb_precision hp) const { GB_ASSERT_OK(gb_fermion_export(h, host, hp)); }
+protected:
+  LatticeFermionT(GridBase *g, bool staggered) : _grid(g), _staggered(staggered) { create(); }
+  void create() {
+    const gb_gridkind kind = _grid->redblack ? GB_HALF : GB_FULL;
+    if (_staggered) GB_ASSERT_OK(gb_staggered_fermion_create(_grid->h, Prec, kind, &h));
+    else GB_ASSERT_OK(gb_fermion_create(_grid->h, _grid->Ls, Prec, kind, &h));
+  }
 };
 typedef LatticeFermionT<GB_F32> LatticeFermionF;
 typedef LatticeFermionT<GB_F64> LatticeFermionD;
+// LatticeStaggeredFermion{F,D} (ref: StaggeredImpl.h:60-75): every algebra / checkerboard / solver entry point above and
+// below takes it through its base class
+template <gb_precision Prec> class LatticeStaggeredFermionT : public LatticeFermionT<Prec> {
+public:
+  explicit LatticeStaggeredFermionT(GridBase *g) : LatticeFermionT<Prec>(g, true) {}
+};
+typedef LatticeStaggeredFermionT<GB_F32> LatticeStaggeredFermionF;
+typedef LatticeStaggeredFermionT<GB_F64> LatticeStaggeredFermionD;
 
 template <gb_precision Prec> class LatticeGaugeFieldT {
 public:
@@ -151,6 +164,8 @@ public:
   virtual void DhopOE(const FermionField &in, FermionField &out, int dag) { apply(GB_OP_DHOP_OE, in, out, dag); }
   virtual void DhopEO(const FermionField &in, FermionField &out, int dag) { apply(GB_OP_DHOP_EO, in, out, dag); }
   virtual void ImportGauge(const GaugeField &U) { GB_ASSERT_OK(gb_op_import_gauge(h, U.h)); }
+  // Dhop on host-resident full-lattice arrays in the reference's unvectorised layout (pipelined H2D / hop / D2H on one rank)
+  void DhopHost(const void *host_in, void *host_out, gb_precision host_prec, int dag) { GB_ASSERT_OK(gb_op_dhop_host(h, host_in, host_out, host_prec, dag)); }
 };
 template <gb_precision Prec> class WilsonFermionT : public FermionOperator<Prec> {
 public: // ref: WilsonFermion.h:139-142
@@ -170,6 +185,18 @@ public: // ref: MobiusFermion.h:45-71
     GB_ASSERT_OK(gb_op_create_mobius(UGrid.h, Umu.h, FGrid.Ls, mass, M5, b, c, nullptr, &this->h));
   }
 };
+template <gb_precision Prec> class ImprovedStaggeredFermionT : public FermionOperator<Prec> {
+public: // ref: ImprovedStaggeredFermion.h:115-121
+  RealD mass;
+  ImprovedStaggeredFermionT(LatticeGaugeFieldT<Prec> &Uthin, LatticeGaugeFieldT<Prec> &Ufat, GridCartesian &Fgrid, GridRedBlackCartesian &, RealD _mass,
+                            RealD c1 = 9.0 / 8.0, RealD c2 = -1.0 / 24.0, RealD u0 = 1.0) : mass(_mass) {
+    GB_ASSERT_OK(gb_op_create_staggered(Fgrid.h, Uthin.h, Ufat.h, _mass, c1, c2, u0, &this->h));
+  }
+  void ImportGauge(const LatticeGaugeFieldT<Prec> &Uthin, const LatticeGaugeFieldT<Prec> &Ufat) { GB_ASSERT_OK(gb_op_import_gauge_staggered(this->h, Uthin.h, Ufat.h)); }
+  RealD Mass() const { return mass; }
+  bool isTrivialEE() const { return true; }
+};
+typedef ImprovedStaggeredFermionT<GB_F32> ImprovedStaggeredFermionF; typedef ImprovedStaggeredFermionT<GB_F64> ImprovedStaggeredFermionD;
 typedef WilsonFermionT<GB_F32> WilsonFermionF; typedef WilsonFermionT<GB_F64> WilsonFermionD;
 typedef DomainWallFermionT<GB_F32> DomainWallFermionF; typedef DomainWallFermionT<GB_F64> DomainWallFermionD;
 typedef MobiusFermionT<GB_F32> MobiusFermionF; typedef MobiusFermionT<GB_F64> MobiusFermionD;
@@ -199,6 +226,14 @@ public:
   void AdjOp(const Field &in, Field &out) override { MpcDag(in, out); }
   void HermOp(const Field &in, Field &out) override { MpcDagMpc(in, out); }
   gb_fermop *FusedSchurMatrix() override { return _Mat.h; }
+};
+
+// SchurStaggeredOperator (ref: LinearOperator.h:543-584): Mpc = mass^2 - Meooe Meooe is Hermitian, HermOp = Mpc
+template <class Matrix, class Field> class SchurStaggeredOperator : public SchurDiagMooeeOperator<Matrix, Field> {
+public:
+  explicit SchurStaggeredOperator(Matrix &Mat) : SchurDiagMooeeOperator<Matrix, Field>(Mat) { assert(Mat.isTrivialEE()); }
+  void MpcDagMpc(const Field &, Field &) override { assert(0); } // never needed with staggered
+  void HermOp(const Field &in, Field &out) override { this->Mpc(in, out); }
 };
 
 // ---- solvers (ref: Grid/algorithms/iterative/ConjugateGradient.h:42-258, ConjugateGradientMixedPrec.h:34-170)

@@ -6,13 +6,13 @@
 // and bench.py's cpu_baseline / --impl reference legs can check and time the CUDA path against
 // an independent CPU implementation.  Nothing under grid_b200/ may include, link or call it.
 //
-// PARITY STATUS: "parity unpinned" in the strict sense -- the reference ships no stored golden
-// vectors for this path and its build (autotools + downloaded Eigen +
-// GMP/MPFR/FFTW) cannot be run in this image, so no reference outputs could be generated here.
-// What pins this oracle instead are the reference's own executable identities, restated in
-// tests/test_oracle_identities.py: Dhop == naive Cshift form (Benchmark_dwf_fp32.cc:214-245),
-// Deo+Doe == D (:424-446), adjointness / MooeeInv*Mooee==1 / Hermiticity
-// (tests/core/Test_wilson_even_odd.cc:120-224), free-field plane waves (tests/core/Test_fft.cc).
+// PARITY STATUS: PINNED against the reference itself.  oracle/Makefile.ref compiles the unmodified reference (CPU, AVX2,
+// OpenMP, comms none) from /root/reference into oracle/_ref/libgridref.so; tests/test_oracle_vs_reference.py compares every
+// entry point of this file with the reference's own WilsonFermion / DomainWallFermion / MobiusFermion (fp64 agreement to
+// rounding, same CG and mixed-CG iteration counts), and tests/golden/dirac_golden.npz stores reference outputs generated
+// from that library (tests/golden/make_golden.py) for machines without it.  The reference's executable identities
+// (Dhop == naive Cshift form, Deo+Doe == D, adjointness, MooeeInv*Mooee == 1, Hermiticity, free-field plane waves) are
+// kept as a second, independent pin in tests/test_oracle_identities.py.
 //
 // All "ref:" citations are paths relative to the reference tree.
 //

@@ -26,3 +26,9 @@ def test_dwf_mixedcg_prec_driver():
     """ref: tests/Test_dwf_mixedcg_prec.cc -- |x_mixed - x_double|^2 < 1e-4 (:212-215), Ls=12 as in the reference"""
     out = run("Test_dwf_mixedcg_prec", "--grid", "8.8.8.8", "--Ls", "12")
     assert "Diff between mixed and regular CG" in out and "done" in out
+
+
+def test_benchmark_staggered_driver():
+    """ref: benchmarks/Benchmark_staggered.cc (+ the even-odd / anti-Hermiticity checks of tests/core/Test_staggered.cc)"""
+    out = run("Benchmark_staggered", "--grid", "8.8.8.8", "--ncall", "10")
+    assert "norm diff" in out and "CG iterations" in out and "done" in out
