@@ -38,6 +38,8 @@ def check(name, err, tol):
         fails.append(name)
 
 
+if os.environ.get("MGPU_MPI_INDEX"):          # restrict to one processor grid (saves GPU time on 8-GPU boxes)
+    MPIS = [MPIS[int(os.environ["MGPU_MPI_INDEX"])]]
 CASES = []
 for mpi in MPIS:
     gd = tuple(max(4 * m, 8) if m > 1 else 4 for m in mpi)
