@@ -9,7 +9,10 @@
 #include <cstring>
 #include <mutex>
 
+#include <set>
 namespace gb {
+std::set<const gb_context *> &live_contexts() { static std::set<const gb_context *> s; return s; }
+bool context_alive(const gb_context *ctx) { return ctx && live_contexts().count(ctx) != 0; }
 static thread_local std::string g_last_error;
 void set_last_error(const std::string &m) { g_last_error = m; }
 
@@ -114,6 +117,7 @@ int gb_context_create(int device, gb_context **out) {
   GB_CUDA(cudaMallocHost(&c->h_result, sizeof(double) * 8));
   GB_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 8));
   GB_CUDA(cudaEventCreateWithFlags(&c->ev_scalar, cudaEventDisableTiming));
+  gb::live_contexts().insert(c);
   *out = c;
   GB_API_END
 }
@@ -121,12 +125,14 @@ int gb_context_create(int device, gb_context **out) {
 int gb_context_destroy(gb_context *c) {
   GB_API_BEGIN
   if (!c) return GB_OK;
+  gb::live_contexts().erase(c);
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
   cudaFree(c->d_partials); cudaFree(c->d_result); cudaFreeHost(c->h_result); cudaFree(c->d_scalars); cudaEventDestroy(c->ev_scalar);
   if (c->l2_scratch) cudaFree(c->l2_scratch);
   if (c->staging) cudaFree(c->staging);
+  for (auto &b : c->field_pool) cudaFree(b.second);
   cudaEventDestroy(c->ev_start); cudaEventDestroy(c->ev_stop); cudaEventDestroy(c->ev_comm); cudaEventDestroy(c->ev_comp);
   cudaStreamDestroy(c->stream); cudaStreamDestroy(c->comm_stream);
   delete c;

@@ -64,7 +64,7 @@ __device__ __forceinline__ void cp_async_arrive(uint64_t *bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
 
-template <int LS> constexpr size_t col_smem_bytes() { return (size_t)(3 * COL_NSITE * 6 * LS + 3 * COL_NSITE * FAST_USTRIDE) * 16 + 64; }
+template <int LS, int NT = 1> constexpr size_t col_smem_bytes() { return (size_t)NT * (3 * COL_NSITE * 6 * LS + 3 * COL_NSITE * FAST_USTRIDE) * 16 + 64; }
 
 // Synchronisation without a CTA-wide barrier per step:
 //  * plane z+1 of the ring is filled by cp.async issued at the TOP of step k; each thread's arrival on the plane mbarrier
@@ -72,25 +72,31 @@ template <int LS> constexpr size_t col_smem_bytes() { return (size_t)(3 * COL_NS
 //    Nobody waits for another thread's arithmetic, only for copies issued a whole step earlier.
 //  * passing that wait proves every thread has begun step k, i.e. finished step k-1: the ring slot overwritten next
 //    (plane z-1, read by other threads during step k-1) and the link buffer of step k-1 (3 buffers) are free.
-template <int LS, int DAG, int INTERIOR>
-__global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col_kernel(const ColArgs a) {
+// NT = 2: the CTA (512 threads at Ls = 16, one per SM) owns the same micro-block on TWO adjacent t-slices; the t leg between
+// them reads the partner slice's ring slot, so only one t leg per site is a global load (2.75 L2 fetches per site).
+template <int LS, int DAG, int INTERIOR, int NT = 1>
+__global__ void __launch_bounds__(NT *COL_NSITE *LS, NT == 1 ? 2 : 1) dhop_col_kernel(const ColArgs a) {
   extern __shared__ __align__(16) unsigned char col_smem[];
-  constexpr int PLANE = COL_NSITE * 6 * LS;                 // float4 per plane of the ring: [slot][vec k][s]
-  constexpr int UBUF = COL_NSITE * FAST_USTRIDE;
+  constexpr int TSLOT = COL_NSITE * 6 * LS;                 // float4 per t-slice of a ring plane
+  constexpr int PLANE = NT * TSLOT;                         // float4 per plane of the ring: [t-slice][slot][vec k][s]
+  constexpr int UBUF = NT * COL_NSITE * FAST_USTRIDE;
   float4 *ring = reinterpret_cast<float4 *>(col_smem);
   float4 *Usm = ring + 3 * PLANE;                            // 3 x [16 sites][41]
   uint64_t *bars = reinterpret_cast<uint64_t *>(Usm + 3 * UBUF);   // [0..2] links, [3] ring plane
-  const int sl = threadIdx.x / LS, s = threadIdx.x % LS;
+  const int tt = NT == 1 ? 0 : threadIdx.x / (COL_NSITE * LS);
+  const int tid1 = NT == 1 ? threadIdx.x : threadIdx.x % (COL_NSITE * LS);
+  const int sl = tid1 / LS, s = tid1 % LS;
   const int xl = sl & 3, yl = sl >> 2;
   const int p = a.first_parity ^ (int)blockIdx.y;
   uint32_t b = blockIdx.x, t, xo, yo, zc;
-  a.dLt.divmod(b, b, t); a.dNxo.divmod(b, b, xo); a.dNyo.divmod(b, zc, yo);
+  a.dLt.divmod(b, b, t); a.dNxo.divmod(b, b, xo); a.dNyo.divmod(b, zc, yo);   // dLt divides by Lt / NT
+  t = t * NT + tt;
   const int xh = xo * 4 + xl, y = yo * 4 + yl, z0 = zc * a.N;
   const float4 *__restrict__ in = a.in[1 - p];
   const uint32_t zstride = (uint32_t)a.Lxh * a.Ly, tstride = zstride * a.Lz;
   const uint32_t site_xyt = xh + a.Lxh * y + tstride * t;
   auto gptr = [&](uint32_t site) { const uint32_t i = site * LS + s; return in + ((size_t)(i >> LOGW) * 6 << LOGW) + (i & (W - 1)); };
-  float4 *const mine = ring + sl * 6 * LS + s;               // this thread's slot in plane buffer 0
+  float4 *const mine = ring + (tt * COL_NSITE + sl) * 6 * LS + s;   // this thread's slot in plane buffer 0
 
   // ---- prologue: planes z0-1 and z0 of the central column, links of step 0
   {
@@ -99,10 +105,11 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col_kernel(const ColArg
 #pragma unroll
     for (int k = 0; k < 6; k++) { mine[k * LS] = __ldg(g0 + (k << LOGW)); mine[PLANE + k * LS] = __ldg(g1 + (k << LOGW)); }
   }
-  if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], COL_NSITE * LS); }
+  if (threadIdx.x == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], NT * COL_NSITE * LS); }
   __syncthreads();
-  if (threadIdx.x == 0) mbar_expect_tx(&bars[0], COL_NSITE * 640);
-  if (s == 0) bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * z0) * 40, 640, &bars[0]);
+  const int usl = tt * COL_NSITE + sl;                        // this site's slot in a link buffer
+  if (threadIdx.x == 0) mbar_expect_tx(&bars[0], NT * COL_NSITE * 640);
+  if (s == 0) bulk_g2s(Usm + usl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * z0) * 40, 640, &bars[0]);
 
   const bool skip_tm = INTERIOR && ((a.comm_dim_mask >> 3) & 1) && t == 0;
   const bool skip_tp = INTERIOR && ((a.comm_dim_mask >> 3) & 1) && (int)t == a.Lt - 1;
@@ -129,19 +136,24 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col_kernel(const ColArg
       cp_async_arrive(&bars[3]);
     }
     if (k + 1 < a.N) {
-      if (threadIdx.x == 0) mbar_expect_tx(&bars[un], COL_NSITE * 640);
-      if (s == 0) bulk_g2s(Usm + un * UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * (z + 1)) * 40, 640, &bars[un]);
+      if (threadIdx.x == 0) mbar_expect_tx(&bars[un], NT * COL_NSITE * 640);
+      if (s == 0) bulk_g2s(Usm + un * UBUF + usl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * (z + 1)) * 40, 640, &bars[un]);
     }
     // ---- t neighbours into registers now, used after the shared-memory legs
     SpinorP ftm, ftp;
-    if (!skip_tm) load_spinor_p(ftm, gptr(site_tm + zoff));
-    if (!skip_tp) load_spinor_p(ftp, gptr(site_tp + zoff));
+    if (NT == 1) {
+      if (!skip_tm) load_spinor_p(ftm, gptr(site_tm + zoff));
+      if (!skip_tp) load_spinor_p(ftp, gptr(site_tp + zoff));
+    } else {                                                     // only the leg that leaves the pair of slices is global
+      if (tt == 0) { if (!skip_tm) load_spinor_p(ftm, gptr(site_tm + zoff)); }
+      else if (!skip_tp) load_spinor_p(ftm, gptr(site_tp + zoff));
+    }
     const int pb = (p + a.origin_parity + y + z + (int)t) & 1;
     SpinorP res;
 #pragma unroll
     for (int q = 0; q < 12; q++) res.c[q] = pk(0.f, 0.f);
     mbar_wait(&bars[ub], (uint32_t)(k / 3) & 1);
-    const float4 *Us = Usm + ub * UBUF + sl * FAST_USTRIDE;
+    const float4 *Us = Usm + ub * UBUF + usl * FAST_USTRIDE;
     const float4 *cur = mine + b0 * PLANE;                       // own slot, plane z
     // ---- z- : own slot of plane z-1
     if (!(INTERIOR && ((a.comm_dim_mask >> 2) & 1) && z == 0)) col_leg<DAG, 2, 0>(mine + bm * PLANE, LS, Us, res);
@@ -160,8 +172,16 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col_kernel(const ColArg
     col_leg<DAG, 1, 0>(yl > 0 ? cur - 4 * 6 * LS : gptr(site_ym + zoff), yl > 0 ? LS : W, Us, res);
     col_leg<DAG, 1, 1>(yl < 3 ? cur + 4 * 6 * LS : gptr(site_yp + zoff), yl < 3 ? LS : W, Us, res);
     // ---- t legs from registers
-    if (!skip_tm) col_leg_reg<DAG, 3, 0>(ftm, Us, res);
-    if (!skip_tp) col_leg_reg<DAG, 3, 1>(ftp, Us, res);
+    if (NT == 1) {
+      if (!skip_tm) col_leg_reg<DAG, 3, 0>(ftm, Us, res);
+      if (!skip_tp) col_leg_reg<DAG, 3, 1>(ftp, Us, res);
+    } else if (tt == 0) {                                        // t- global, t+ = the partner slice's slot of plane z
+      if (!skip_tm) col_leg_reg<DAG, 3, 0>(ftm, Us, res);
+      col_leg<DAG, 3, 1>(cur + TSLOT, LS, Us, res);
+    } else {
+      col_leg<DAG, 3, 0>(cur - TSLOT, LS, Us, res);
+      if (!skip_tp) col_leg_reg<DAG, 3, 1>(ftm, Us, res);
+    }
     // ---- z+ : wait for plane z+1 (every thread's copy, issued at the top of this step), read the own slot
     mbar_wait(&bars[3], (uint32_t)k & 1);
     if (!(INTERIOR && ((a.comm_dim_mask >> 2) & 1) && z == a.Lz - 1)) col_leg<DAG, 2, 1>(mine + bp * PLANE, LS, Us, res);

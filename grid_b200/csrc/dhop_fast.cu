@@ -36,6 +36,20 @@ template <int LS> static void launch_col_ls(const ColArgs &a, dim3 grid, int dag
     attr_set = true;
   }
   const int threads = COL_NSITE * LS;
+  if (a.N < 0) {   // marker set by the launcher: two t-slices per CTA
+    ColArgs a2 = a; a2.N = -a.N;
+    if constexpr (LS * COL_NSITE * 2 <= 1024 && col_smem_bytes<LS, 2>() <= 232448) {
+      static bool attr2 = false;
+      const size_t smem2 = col_smem_bytes<LS, 2>();
+      if (!attr2) {
+        GB_CUDA(cudaFuncSetAttribute(dhop_col_kernel<LS, 0, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        GB_CUDA(cudaFuncSetAttribute(dhop_col_kernel<LS, 1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+        attr2 = true;
+      }
+      if (!dag) dhop_col_kernel<LS, 0, 0, 2><<<grid, 2 * threads, smem2, st>>>(a2); else dhop_col_kernel<LS, 1, 0, 2><<<grid, 2 * threads, smem2, st>>>(a2);
+    }
+    return;
+  }
   if (!dag) { if (interior) dhop_col_kernel<LS, 0, 1><<<grid, threads, smem, st>>>(a); else dhop_col_kernel<LS, 0, 0><<<grid, threads, smem, st>>>(a); }
   else { if (interior) dhop_col_kernel<LS, 1, 1><<<grid, threads, smem, st>>>(a); else dhop_col_kernel<LS, 1, 0><<<grid, threads, smem, st>>>(a); }
 }
@@ -65,11 +79,14 @@ static bool dhop_col_launch(gb_fermop *op, const void *const in[2], void *const 
   }
   a.axpy_a = (float)axa; a.axpy_b = (float)axb;
   a.comm_dim_mask = interior ? op->comm_dim_mask : 0;
-  a.Lxh = Lxh; a.Ly = Ly; a.Lz = Lz; a.Lt = Lt; a.N = N;
-  a.dLt = FastDiv(Lt); a.dNxo = FastDiv(Lxh / 4); a.dNyo = FastDiv(Ly / 4);
+  // GB_COL_NT=2: two adjacent t-slices per CTA (only for the single-rank kernel and Ls = 8, 12, 16)
+  static const int env_nt = getenv("GB_COL_NT") ? atoi(getenv("GB_COL_NT")) : 1;
+  const int NT = (env_nt == 2 && !interior && Lt % 2 == 0) ? 2 : 1;
+  a.Lxh = Lxh; a.Ly = Ly; a.Lz = Lz; a.Lt = Lt; a.N = NT == 2 ? -N : N;
+  a.dLt = FastDiv(Lt / NT); a.dNxo = FastDiv(Lxh / 4); a.dNyo = FastDiv(Ly / 4);
   a.first_parity = parity_out_first;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
-  dim3 grid((unsigned)(Lt * (Lxh / 4) * (Ly / 4) * (Lz / N)), nparity);
+  dim3 grid((unsigned)((Lt / NT) * (Lxh / 4) * (Ly / 4) * (Lz / N)), nparity);
   switch (Ls) {
   case 8: launch_col_ls<8>(a, grid, dag, interior, st); break;
   case 12: launch_col_ls<12>(a, grid, dag, interior, st); break;

@@ -75,7 +75,7 @@ static int fermion_create_impl(gb_grid *g, int Ls, int ncomplex, gb_precision pr
   GB_REQUIRE(g && out && Ls >= 1, "bad argument");
   GB_REQUIRE(prec == GB_F32 || prec == GB_F64, "bad precision");
   gb_fermion *f = new gb_fermion();
-  f->grid = g; f->Ls = Ls; f->prec = prec; f->kind = kind; f->cb = GB_EVEN; f->ncomplex = ncomplex;
+  f->ctx = g->ctx; f->grid = g; f->Ls = Ls; f->prec = prec; f->kind = kind; f->cb = GB_EVEN; f->ncomplex = ncomplex;
   f->nsite4 = g->V4cb;
   f->n5cb = g->V4cb * Ls;
   GB_REQUIRE(f->n5cb * 2 < (1ll << 31), "local 5D volume must be < 2^31");
@@ -83,7 +83,20 @@ static int fermion_create_impl(gb_grid *g, int Ls, int ncomplex, gb_precision pr
   f->nparity = kind == GB_HALF ? 1 : 2;
   f->bytes = (size_t)f->nvec() * 16;
   GB_CUDA(cudaSetDevice(g->ctx->device));
-  GB_CUDA(cudaMalloc(&f->data, f->bytes));
+  f->data = nullptr;
+  auto &pool = g->ctx->field_pool;
+  for (size_t i = 0; i < pool.size(); i++)
+    if (pool[i].first == f->bytes) { f->data = pool[i].second; g->ctx->field_pool_bytes -= f->bytes; pool.erase(pool.begin() + i); break; }
+  if (!f->data) {
+    cudaError_t e = cudaMalloc(&f->data, f->bytes);
+    if (e != cudaSuccess && !pool.empty()) {              // out of memory with parked buffers: release them and retry
+      cudaGetLastError();
+      for (auto &b : pool) cudaFree(b.second);
+      pool.clear(); g->ctx->field_pool_bytes = 0;
+      e = cudaMalloc(&f->data, f->bytes);
+    }
+    if (e != cudaSuccess) { delete f; GB_CUDA(e); }
+  }
   GB_CUDA(cudaMemsetAsync(f->data, 0, f->bytes, g->ctx->stream));
   *out = f;
   GB_API_END
@@ -95,7 +108,16 @@ extern "C" int gb_staggered_fermion_create(gb_grid *g, gb_precision prec, gb_gri
   return fermion_create_impl(g, 1, 3, prec, kind, out);
 }
 extern "C" int gb_fermion_destroy(gb_fermion *f) {
-  if (f) { cudaFree(f->data); delete f; }
+  if (!f) return GB_OK;
+  gb_context *ctx = context_alive(f->ctx) ? f->ctx : nullptr;   // a field may be destroyed after its context
+  constexpr size_t POOL_MAX_BYTES = (size_t)48 << 30;     // a quarter of the 180 GB of HBM
+  if (ctx && f->data && ctx->field_pool.size() < 64 && ctx->field_pool_bytes + f->bytes <= POOL_MAX_BYTES) {
+    ctx->field_pool.emplace_back(f->bytes, f->data);
+    ctx->field_pool_bytes += f->bytes;
+  } else {
+    cudaFree(f->data);
+  }
+  delete f;
   return GB_OK;
 }
 extern "C" int gb_fermion_checkerboard(const gb_fermion *f) { return f->cb; }

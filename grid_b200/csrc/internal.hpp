@@ -111,6 +111,11 @@ struct gb_context {
   // host<->device staging (import/export)
   void *staging = nullptr;
   size_t staging_bytes = 0;
+  // recycled field storage (ref: Grid's MemoryManager allocation cache, Grid/allocator/MemoryManagerCache.cc): solver
+  // temporaries of 0.4-1.6 GB are created and destroyed per solve; cudaMalloc / cudaFree of that size costs milliseconds and
+  // synchronises the device, so freed field buffers are parked here (exact-size reuse, stream ordered on `stream`)
+  std::vector<std::pair<size_t, void *>> field_pool;
+  size_t field_pool_bytes = 0;
   // communicator
   int rank = 0, nranks = 1;
   ncclComm *nccl = nullptr;
@@ -124,6 +129,7 @@ struct gb_grid {
 };
 
 struct gb_fermion {
+  gb_context *ctx = nullptr; // owner of the storage (checked against the live-context registry on destroy)
   gb_grid *grid;
   int Ls, prec, kind, cb;
   int64_t nsite4;  // 4D sites per parity block (V4cb)
@@ -150,6 +156,8 @@ struct gb_gauge {
 };
 
 namespace gb {
+// contexts that have been created and not yet destroyed (fields may outlive their context in a host program's teardown)
+bool context_alive(const gb_context *ctx);
 // launch bookkeeping
 inline void count_launch(gb_context *ctx, int n = 1) { ctx->launches += n; }
 void check_launch(gb_context *ctx, const char *what);
