@@ -253,6 +253,22 @@ def main():
     Dw = gb.DomainWallFermion(U, grid, Ls, 0.1, 1.8)
     if args.no_overlap:
         Dw.set_overlap(False)
+    hop_form = "single rank" if world == 1 else ("serial comms" if args.no_overlap else "overlapped, semi-fused")
+    if world > 1 and not args.no_overlap:
+        # self-check of the multi-GPU hop before timing it: the default (semi-fused) form must reproduce the serial-comms form
+        chk_src = gb.LatticeFermion(grid, Ls, gb.F32).random(3)
+        o1, o2 = gb.LatticeFermion(grid, Ls, gb.F32), gb.LatticeFermion(grid, Ls, gb.F32)
+        Dw.Dhop(chk_src, o1, 0)
+        Dw.set_overlap(False); Dw.Dhop(chk_src, o2, 0); Dw.set_overlap(True)
+        ref_n = gb.norm2(o2)
+        gb.axpy(o1, -1.0, o2, o1)
+        rel = (gb.norm2(o1) / ref_n) ** 0.5
+        if not rel < 1e-6:
+            if rank == 0:
+                print(f"bench: semi-fused hop differs from the serial-comms hop (rel {rel:.3e}); timing the interior + exterior form", file=sys.stderr)
+            Dw.set_overlap(2)
+            hop_form = "overlapped, interior + accumulate-exterior (semi-fused self-check failed)"
+        del chk_src, o1, o2
     src = gb.LatticeFermion(grid, Ls, gb.F32).random(2)
     n2 = gb.norm2(src)
     gb.scale(src, 1.0 / np.sqrt(n2), src)     # ref: Benchmark_dwf_fp32.cc:175-176
@@ -362,7 +378,7 @@ def main():
         achieved = bps * sites_local / (ms_step * 1e-3) / 1e9       # per GPU; one dhop_kernel launch per step
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": workload_config(args),
+                "data": "synthetic", "config": dict(workload_config(args), hop_form=hop_form),
                 "per_gpu_gflops": value / world, "vs_published_a100_per_gpu": value / world / PUBLISHED_A100_GFLOPS_PER_GPU,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes) * world, "d2h_bytes_per_step": int(host_out.nbytes) * world,
                         "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},

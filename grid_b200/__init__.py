@@ -376,7 +376,8 @@ class FermionOperator:
         lib().gb_op_set_fast_kernel(self.h, int(on))
 
     def set_overlap(self, on):
-        lib().gb_op_set_overlap(self.h, 1 if on else 0)
+        """True/1: overlapped (semi-fused where it applies); 2: overlapped as interior + accumulate-exterior; False/0: serial"""
+        lib().gb_op_set_overlap(self.h, int(on))
 
 
 def _phases(ph):

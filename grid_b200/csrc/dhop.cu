@@ -547,6 +547,12 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       const int ip = 1 - parity_out_first;
       for (int i = 0; i < 8; i++) if (a.halo[i]) a.halo[i] = (const char *)a.halo[i] - (size_t)ip * op->halo_parity_stride[i & 3] * 16;
     }
+    // semi-fused: after the pack+send kernel ONE hop launch does the local legs and, in its last (surface) CTAs, acquires
+    // the neighbours' flags and adds the halo legs -- no exterior pass, nothing read-modify-written (GB_SEMIFUSED=0 disables)
+    static const bool semifused = !(getenv("GB_SEMIFUSED") && atoi(getenv("GB_SEMIFUSED")) == 0);
+    if (op->overlap_comms && semifused && !op->no_semifused && op->prec == GB_F32 && !op->disable_fast && !(op->comm_dim_mask & 3) &&
+        dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 4, ctx->stream, a.halo, a.flags, epoch))
+      return;
     if (op->overlap_comms) hop_overlapped(ctx->stream, [] {});
     else run(0, ctx->stream);
     return;

@@ -117,6 +117,12 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.axpy_a = (float)axa; a.axpy_b = (float)axb;
   // interior == 3: only the sites whose every leg is local (z, t in [1, L-1) of the decomposed dimensions), all 8 legs;
   //                the surface sites are computed, also with all legs, by the caller's exterior pass -- no read-modify-write
+  // interior == 4: "semi-fused" -- one launch does the local legs AND, in the CTAs that own surface sites (rasterised last),
+  //                acquires the neighbours' epoch flags and adds the off-node legs from the receive buffers; the faces were
+  //                projected and sent by the separate pack_send kernel that precedes it in the stream.  Unlike interior == 2
+  //                (pack CTAs inside the same launch) no CTA ever waits for work of its own launch, so it cannot deadlock.
+  const bool no_pack = interior == 4;
+  if (no_pack) interior = 2;
   const bool inner_box = interior == 3;
   if (inner_box) {
     if (op->comm_dim_mask & 3) return false;               // x / y decomposition: caller uses interior + accumulate passes
@@ -149,7 +155,7 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.npack_items = 0; a.npack_ctas = 0; a.pack_ratio = 4; a.pack_counter = nullptr;
   a.nhop_ctas_per_parity = (a.V4cb + FAST_NSITE - 1) / FAST_NSITE;
   for (int k = 0; k < 8; k++) a.peer_flag[k] = nullptr;
-  if (interior == 2) {
+  if (interior == 2 && !no_pack) {
     // pack items of this hop: for every decomposed dimension, both faces, every input parity
     P2PState &S = op->p2p;
     const size_t eoff = (size_t)(epoch & 1) * S.epoch_stride;

@@ -309,10 +309,19 @@ __global__ void __launch_bounds__(FAST_NSITE *LS, (FAST_NSITE * LS <= 256) ? 3 :
   SpinorP res;
 #pragma unroll
   for (int k = 0; k < 12; k++) res.c[k] = pk(0.f, 0.f);
-#define GB_LEG(I, M, F) if (!INTERIOR || !off[I]) fast_leg<LS, DAG, M, F>(in, nb[I], s, Us, res)
-  GB_LEG(0, 0, 0); GB_LEG(1, 0, 1); GB_LEG(2, 1, 0); GB_LEG(3, 1, 1);
-  GB_LEG(4, 2, 0); GB_LEG(5, 2, 1); GB_LEG(6, 3, 0); GB_LEG(7, 3, 1);
+  // CTAs without surface sites (the great majority) take the unconditional path: with every leg guarded by a per-thread
+  // predicate the compiler cannot batch the loads of a +-mu pair, which costs ~15 % (measured: 1.16 vs 1.0 ms per hop)
+  if (INTERIOR == 2 && !cta_has_off) {
+#define GB_LEG(I, M, F) fast_leg<LS, DAG, M, F>(in, nb[I], s, Us, res)
+    GB_LEG(0, 0, 0); GB_LEG(1, 0, 1); GB_LEG(2, 1, 0); GB_LEG(3, 1, 1);
+    GB_LEG(4, 2, 0); GB_LEG(5, 2, 1); GB_LEG(6, 3, 0); GB_LEG(7, 3, 1);
 #undef GB_LEG
+  } else {
+#define GB_LEG(I, M, F) if (!INTERIOR || !off[I]) fast_leg<LS, DAG, M, F>(in, nb[I], s, Us, res)
+    GB_LEG(0, 0, 0); GB_LEG(1, 0, 1); GB_LEG(2, 1, 0); GB_LEG(3, 1, 1);
+    GB_LEG(4, 2, 0); GB_LEG(5, 2, 1); GB_LEG(6, 3, 0); GB_LEG(7, 3, 1);
+#undef GB_LEG
+  }
   if (INTERIOR == 2) {
     if (cta_has_off) {
       if (threadIdx.x < 8 && ((a.comm_dim_mask >> (threadIdx.x & 3)) & 1)) {

@@ -327,6 +327,7 @@ int gb_op_set_fast_kernel(gb_fermop *op, int enable) {
 }
 int gb_op_set_overlap(gb_fermop *op, int overlap) {
   op->overlap_comms = overlap != 0;
+  op->no_semifused = overlap == 2;
   return GB_OK;
 }
 }

@@ -37,6 +37,7 @@ struct gb_fermop {
   // multi-GPU halos (ref: CartesianStencil u_send_buf/u_recv_buf, Stencil.h:839-848)
   int comm_dim_mask = 0;
   bool overlap_comms = true;
+  bool no_semifused = false;   // overlapped hops: interior + accumulate-exterior passes instead of the semi-fused launch
   bool disable_fast = false;   // force the generic kernel (tests compare the two)
   bool no_col = false;         // fp32: use the micro-block kernel instead of the column-sweep kernel (tests compare them)
   int col_n = 0;               // z-planes per column of the column-sweep kernel (0 = default 16)

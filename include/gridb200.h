@@ -186,7 +186,10 @@ int gb_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out,
 int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_out, gb_precision host_prec, int dag);
 /* tuning knob of the hopping kernel's CTA rasterisation (z/t blocking for L2 reuse); 0 = default */
 int gb_op_set_tiling(gb_fermop *op, int block_y, int block_z, int block_t);
-/* 1 (default): interior kernel overlaps the face exchange (ref: --comms-overlap, WilsonFermion5DImplementation.h:320-384);
+/* 1 (default): the hop overlaps the face exchange (ref: --comms-overlap, WilsonFermion5DImplementation.h:320-384); on z/t
+ *    decomposed fp32 lattices with peer access that is ONE launch after the pack+send kernel: local legs everywhere, and the
+ *    CTAs owning surface sites (rasterised last) acquire the neighbours' flags and add the halo legs ("semi-fused");
+ * 2: overlapped in the reference's form: interior kernel, then an accumulate pass over the surface slabs;
  * 0: exchange then compute (ref: DhopInternalSerialComms, :388-411) */
 int gb_op_set_overlap(gb_fermop *op, int overlap);
 /* fp32 operators: 1 (default) = column-sweep kernel (shared-memory z-column reuse) where it applies, else the micro-block
