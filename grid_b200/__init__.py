@@ -21,7 +21,7 @@ Even, Odd = 0, 1
 FULL, HALF = 0, 1
 DaggerNo, DaggerYes = 0, 1
 (OP_DHOP, OP_DHOP_OE, OP_DHOP_EO, OP_M, OP_MDAG, OP_MEOOE, OP_MEOOE_DAG, OP_MOOEE, OP_MOOEE_DAG, OP_MOOEE_INV,
- OP_MOOEE_INV_DAG, OP_MPC, OP_MPC_DAG, OP_HERMOP, OP_DW, OP_MEOOE5D, OP_MEOOEDAG5D) = range(17)
+ OP_MOOEE_INV_DAG, OP_MPC, OP_MPC_DAG, OP_HERMOP, OP_DW, OP_MEOOE5D, OP_MEOOEDAG5D, OP_DMINUS, OP_DMINUS_DAG) = range(19)
 GB_OK, GB_ERR_INVALID, GB_ERR_CUDA, GB_ERR_NO_DEVICE, GB_ERR_NOT_CONVERGED, GB_ERR_COMM = 0, -1, -2, -3, -4, -5
 UNIQUE_ID_BYTES = 128
 
@@ -54,6 +54,11 @@ SYMBOLS = [
     ("gb_op_dhop_host", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
+    ("gb_op_import_physical_fermion_source", _i, [_vp, _vp, _vp]), ("gb_op_import_unphysical_fermion", _i, [_vp, _vp, _vp]),
+    ("gb_op_export_physical_fermion_solution", _i, [_vp, _vp, _vp]), ("gb_op_export_physical_fermion_source", _i, [_vp, _vp, _vp]),
+    ("gb_schur_redblack_source", _i, [_vp, _vp, _vp, _vp]), ("gb_schur_redblack_solution", _i, [_vp, _vp, _vp, _vp]),
+    ("gb_schur_solve", _i, [_vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
+    ("gb_schur_solve_mixed", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
 ]
 
 _LIB = None
@@ -362,6 +367,14 @@ class FermionOperator:
     def Meooe5D(self, i, o): self._apply(OP_MEOOE5D, i, o)
     def MeooeDag5D(self, i, o): self._apply(OP_MEOOEDAG5D, i, o)
 
+    # physical 4D <-> 5D maps (ref: FermionOperator.h:172-191, CayleyFermion5DImplementation.h:58-153)
+    def Dminus(self, i, o): self._apply(OP_DMINUS, i, o)
+    def DminusDag(self, i, o): self._apply(OP_DMINUS_DAG, i, o)
+    def ImportPhysicalFermionSource(self, input4d, imported5d): _chk(lib().gb_op_import_physical_fermion_source(self.h, input4d.h, imported5d.h))
+    def ImportUnphysicalFermion(self, input4d, imported5d): _chk(lib().gb_op_import_unphysical_fermion(self.h, input4d.h, imported5d.h))
+    def ExportPhysicalFermionSolution(self, solution5d, exported4d): _chk(lib().gb_op_export_physical_fermion_solution(self.h, solution5d.h, exported4d.h))
+    def ExportPhysicalFermionSource(self, source5d, exported4d): _chk(lib().gb_op_export_physical_fermion_source(self.h, source5d.h, exported4d.h))
+
     def Dhop_host(self, host_in, host_out, dag=0):
         """Dhop on host-resident full-lattice arrays [V4*Ls,4,3] (lexicographic); pipelined H2D / hop / D2H on one rank."""
         assert host_in.flags.c_contiguous and host_out.flags.c_contiguous and host_in.dtype == host_out.dtype and host_in.shape == host_out.shape
@@ -525,3 +538,75 @@ class MixedPrecisionConjugateGradient:
         self.TotalInnerIterations, self.TotalOuterIterations, self.TotalFinalStepIterations = it[0], it[1], it[2]
         self.TrueResidual = tr.value
         _chk(rc)
+
+
+class SchurRedBlackDiagMooeeSolve:
+    """ref: Grid/algorithms/iterative/SchurRedBlack.h:96-290,385-430.  SchurSolver = SchurRedBlackDiagMooeeSolve(CG);
+    SchurSolver(Ddwf, src, result) solves M result = src on the full lattice (tests/solver/Test_dwf_cg_schur.cc:46-50).
+    HermitianRBSolver is a ConjugateGradient (fused device path), a MixedPrecisionSchurCG (below) or any callable
+    solver(LinearOperator, src_o, sol_o)."""
+    _Operator = SchurDiagMooeeOperator
+
+    def __init__(self, HermitianRBSolver, initSubGuess=False, solnAsInitGuess=False):
+        self._HermitianRBSolver, self.subGuess, self.useSolnAsInitGuess = HermitianRBSolver, initSubGuess, solnAsInitGuess
+        self.TrueUnprecResidual = None
+
+    def subtractGuess(self, initSubGuess): self.subGuess = initSubGuess
+    def isSubtractGuess(self): return self.subGuess
+
+    def RedBlackSource(self, Matrix, src, src_e, src_o):
+        _chk(lib().gb_schur_redblack_source(Matrix.h, src.h, src_e.h, src_o.h))
+
+    def RedBlackSolution(self, Matrix, sol_o, src_e, sol):
+        _chk(lib().gb_schur_redblack_solution(Matrix.h, sol_o.h, src_e.h, sol.h))
+
+    def RedBlackSolve(self, Matrix, src_o, sol_o):
+        self._HermitianRBSolver(self._Operator(Matrix), src_o, sol_o)
+        assert sol_o.Checkerboard() == Odd
+
+    def __call__(self, Matrix, src, out):
+        S = self._HermitianRBSolver
+        if isinstance(S, ConjugateGradient) and not self.subGuess:   # one call: source, device-resident CG, reconstruction
+            it, rs = C.c_int(), (C.c_double * 2)()
+            rc = lib().gb_schur_solve(Matrix.h, src.h, out.h, S.Tolerance, S.MaxIterations, int(self.useSolnAsInitGuess), C.byref(it), rs)
+            S.IterationsToComplete, S.TrueResidual, self.TrueUnprecResidual = it.value, rs[0], rs[1]
+            if rc == GB_ERR_NOT_CONVERGED:
+                assert not S.ErrorOnNoConverge, "ConjugateGradient did NOT converge"
+                return
+            _chk(rc)
+            return
+        src_e, src_o, sol_o = src.like(kind=HALF), src.like(kind=HALF), src.like(kind=HALF)
+        self.RedBlackSource(Matrix, src, src_e, src_o)
+        if self.useSolnAsInitGuess:
+            pickCheckerboard(Odd, sol_o, out)
+        else:
+            sol_o.zero().set_checkerboard(Odd)       # ZeroGuesser
+        guess_save = None
+        if self.subGuess:
+            guess_save = src.like(kind=HALF)
+            copy(guess_save, sol_o)
+        self.RedBlackSolve(Matrix, src_o, sol_o)
+        if self.subGuess:
+            axpy(sol_o, -1.0, guess_save, sol_o)
+        self.RedBlackSolution(Matrix, sol_o, src_e, out)
+        if not self.subGuess:                       # "true unprec resid", ref: SchurRedBlack.h:277-285
+            resid = src.like()
+            Matrix.M(out, resid)
+            axpy(resid, -1.0, src, resid)
+            self.TrueUnprecResidual = (norm2(resid) / norm2(src)) ** 0.5
+
+
+class SchurRedBlackStaggeredSolve(SchurRedBlackDiagMooeeSolve):
+    """ref: SchurRedBlack.h:294-349 (source carries Mooee = mass instead of MpcDag; the C entry points dispatch on the operator)."""
+    _Operator = SchurStaggeredOperator
+
+
+SchurRedBlackStagSolve = SchurRedBlackStaggeredSolve
+
+
+def schur_solve_mixed(Mat_f, Mat_d, src, out, tol, maxinnerit, maxouterit):
+    """Full-lattice M out = src with MixedPrecisionConjugateGradient as the red-black solver (fp64 outside, fp32 inside).
+    Returns dict(inner, outer, final, true_residual, unprec_residual)."""
+    it, rs = (C.c_int * 3)(), (C.c_double * 2)()
+    _chk(lib().gb_schur_solve_mixed(Mat_f.h, Mat_d.h, src.h, out.h, tol, maxinnerit, maxouterit, it, rs))
+    return dict(inner=it[0], outer=it[1], final=it[2], true_residual=rs[0], unprec_residual=rs[1])

@@ -195,6 +195,16 @@ void op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, i
     check_field(op, in, GB_FULL, "DW"); check_field(op, out, GB_FULL, "DW");
     dhop_full(op, in, out, dag, in, 1.0, 4.0 - op->M5);
     break;
+  case GB_OP_DMINUS: case GB_OP_DMINUS_DAG: { // chi_s = psi_s - cs[s] DW(psi)_s   ref: CayleyFermion5DImplementation.h:132-153
+    check_field(op, in, GB_FULL, "Dminus"); check_field(op, out, GB_FULL, "Dminus");
+    if (op->kind == GB_KIND_WILSON) { scale_field(out, 1.0, in); break; }   // ref: FermionOperator.h:172-173 (chi = psi)
+    gb_fermion *t = op_tmp_full(op, 0);
+    dhop_full(op, in, t, which == GB_OP_DMINUS_DAG, in, 1.0, 4.0 - op->M5);   // t = DW psi
+    std::vector<double> none(op->Ls, 0.0), mcs(op->Ls);
+    for (int s = 0; s < op->Ls; s++) mcs[s] = -op->k.cs[s];
+    m5d_apply(op, t, t, out, none, mcs, none, 0, in, 1.0);                    // out = -cs[s] t + psi
+    break;
+  }
   case GB_OP_M:
     check_field(op, in, GB_FULL, "M"); check_field(op, out, GB_FULL, "M");
     if (op->kind == GB_KIND_WILSON) { dhop_full(op, in, out, 0, in, 1.0, 4.0 + op->mass); break; }

@@ -416,6 +416,10 @@ void stag_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *o
     out->cb = in->cb;
     break;
   }
+  case GB_OP_DMINUS: case GB_OP_DMINUS_DAG:   // ref: FermionOperator.h:172-173 (chi = psi)
+    stag_check(op, in, in->kind, "Dminus"); stag_check(op, out, in->kind, "Dminus");
+    chk(gb_copy(out, in));
+    break;
   default:
     GB_REQUIRE(false, "opcode not defined for staggered operators");
   }

@@ -64,7 +64,9 @@ typedef enum {
   GB_OP_HERMOP = 13,       /* SchurOperatorBase::HermOp = MpcDagMpc  ref: :291-307 */
   GB_OP_DW = 14,           /* WilsonFermion5D::DW = Dhop + (4-M5)    ref: WilsonFermion5DImplementation.h:447-452 */
   GB_OP_MEOOE5D = 15,      /* ref: CayleyFermion5DImplementation.h:165-174 */
-  GB_OP_MEOOEDAG5D = 16    /* ref: :248-271 */
+  GB_OP_MEOOEDAG5D = 16,   /* ref: :248-271 */
+  GB_OP_DMINUS = 17,       /* CayleyFermion5D::Dminus: chi_s = psi_s - cs[s] DW psi_s (identity for 4D operators)  ref: :132-142 */
+  GB_OP_DMINUS_DAG = 18    /* ref: :143-153 */
 } gb_opcode;
 
 /* ---------------------------------------------------------------- context / runtime
@@ -196,6 +198,17 @@ int gb_op_set_overlap(gb_fermop *op, int overlap);
  * FFMA2 + TMA kernel, else the generic kernel; 2 = skip the column-sweep kernel; 0 = always the generic kernel */
 int gb_op_set_fast_kernel(gb_fermop *op, int enable);
 
+/* Physical 4D <-> 5D field maps of the 5D operators.  4D fields are gb_fermion with Ls = 1 on the same grid.
+ * For WilsonFermion / ImprovedStaggeredFermion every map is a copy (ref: FermionOperator.h:172-191).
+ *   ImportPhysicalFermionSource:   5D = Dminus [ P+ in4d at s=0 ; P- in4d at s=Ls-1 ]   ref: CayleyFermion5DImplementation.h:115-130
+ *   ImportUnphysicalFermion:       the same without Dminus                              ref: :100-113
+ *   ExportPhysicalFermionSolution: 4D = P- sol5d[s=0] + P+ sol5d[s=Ls-1]                ref: :58-69
+ *   ExportPhysicalFermionSource:   4D = P+ src5d[s=0] + P- src5d[s=Ls-1]                ref: :88-99 */
+int gb_op_import_physical_fermion_source(gb_fermop *op, const gb_fermion *in4d, gb_fermion *out5d);
+int gb_op_import_unphysical_fermion(gb_fermop *op, const gb_fermion *in4d, gb_fermion *out5d);
+int gb_op_export_physical_fermion_solution(gb_fermop *op, const gb_fermion *sol5d, gb_fermion *out4d);
+int gb_op_export_physical_fermion_source(gb_fermop *op, const gb_fermion *src5d, gb_fermion *out4d);
+
 /* ---------------------------------------------------------------- solvers
  * ConjugateGradient on SchurDiagMooeeOperator(op).HermOp, fused device path.
  * ref: Grid/algorithms/iterative/ConjugateGradient.h:68-257.  sol is the initial guess on entry.
@@ -210,6 +223,23 @@ int gb_cg(gb_context *ctx, gb_hermop_fn hermop, void *user, const gb_fermion *sr
  * iters_out[3] = {TotalInnerIterations, TotalOuterIterations, TotalFinalStepIterations} */
 int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d, gb_fermion *sol_d, double tol, int max_inner,
                       int max_outer, int iters_out[3], double *true_resid_out);
+
+
+/* SchurRedBlackDiagMooeeSolve (Wilson-type operators) / SchurRedBlackStaggeredSolve (staggered): the full-lattice solve
+ * M sol = src through the even-odd Schur decomposition.  ref: Grid/algorithms/iterative/SchurRedBlack.h:238-290,294-349,385-430
+ *   RedBlackSource:   src_e = src|Even ; src_o = MpcDag (src|Odd - Meooe MooeeInv src_e)   (staggered: Mooee in place of MpcDag)
+ *   RedBlackSolution: sol = [ MooeeInv (src_e - Meooe sol_o) | sol_o ]
+ *   gb_schur_solve:   RedBlackSource, ConjugateGradient on the Odd checkerboard (ZeroGuesser, or the Odd part of sol when
+ *                     use_sol_as_guess != 0, ref: :253-257), RedBlackSolution.  resid_out = {CG TrueResidual,
+ *                     |M sol - src| / |src| (the "true unprec resid" the reference logs, ref: :277-285)}
+ *   gb_schur_solve_mixed: the same with MixedPrecisionConjugateGradient as the red-black solver (fp64 fields and op_d outside,
+ *                     fp32 op_f inside); iters_out as gb_mixed_cg_schur */
+int gb_schur_redblack_source(gb_fermop *op, const gb_fermion *src, gb_fermion *src_e, gb_fermion *src_o);
+int gb_schur_redblack_solution(gb_fermop *op, const gb_fermion *sol_o, const gb_fermion *src_e, gb_fermion *sol);
+int gb_schur_solve(gb_fermop *op, const gb_fermion *src, gb_fermion *sol, double tol, int maxit, int use_sol_as_guess, int *iters_out,
+                   double resid_out[2]);
+int gb_schur_solve_mixed(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src, gb_fermion *sol, double tol, int max_inner, int max_outer,
+                         int iters_out[3], double resid_out[2]);
 
 #ifdef __cplusplus
 }

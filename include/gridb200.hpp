@@ -164,6 +164,13 @@ public:
   virtual void DhopOE(const FermionField &in, FermionField &out, int dag) { apply(GB_OP_DHOP_OE, in, out, dag); }
   virtual void DhopEO(const FermionField &in, FermionField &out, int dag) { apply(GB_OP_DHOP_EO, in, out, dag); }
   virtual void ImportGauge(const GaugeField &U) { GB_ASSERT_OK(gb_op_import_gauge(h, U.h)); }
+  // physical 4D <-> 5D maps (ref: FermionOperator.h:172-191 ; CayleyFermion5DImplementation.h:58-153)
+  virtual void Dminus(const FermionField &psi, FermionField &chi) { apply(GB_OP_DMINUS, psi, chi); }
+  virtual void DminusDag(const FermionField &psi, FermionField &chi) { apply(GB_OP_DMINUS_DAG, psi, chi); }
+  virtual void ImportPhysicalFermionSource(const FermionField &input4d, FermionField &imported5d) { GB_ASSERT_OK(gb_op_import_physical_fermion_source(h, input4d.h, imported5d.h)); }
+  virtual void ImportUnphysicalFermion(const FermionField &input4d, FermionField &imported5d) { GB_ASSERT_OK(gb_op_import_unphysical_fermion(h, input4d.h, imported5d.h)); }
+  virtual void ExportPhysicalFermionSolution(const FermionField &solution5d, FermionField &exported4d) { GB_ASSERT_OK(gb_op_export_physical_fermion_solution(h, solution5d.h, exported4d.h)); }
+  virtual void ExportPhysicalFermionSource(const FermionField &solution5d, FermionField &exported4d) { GB_ASSERT_OK(gb_op_export_physical_fermion_source(h, solution5d.h, exported4d.h)); }
   // Dhop on host-resident full-lattice arrays in the reference's unvectorised layout (pipelined H2D / hop / D2H on one rank)
   void DhopHost(const void *host_in, void *host_out, gb_precision host_prec, int dag) { GB_ASSERT_OK(gb_op_dhop_host(h, host_in, host_out, host_prec, dag)); }
 };
@@ -237,15 +244,26 @@ public:
 };
 
 // ---- solvers (ref: Grid/algorithms/iterative/ConjugateGradient.h:42-258, ConjugateGradientMixedPrec.h:34-170)
-template <class Field> class ConjugateGradient {
+// OperatorFunction (ref: Grid/algorithms/LinearOperator.h:590-600): what SchurRedBlack*Solve takes as its red-black solver
+template <class Field> class OperatorFunction {
 public:
+  virtual ~OperatorFunction() {}
+  virtual void operator()(LinearOperatorBase<Field> &Linop, const Field &in, Field &out) = 0;
+  // non-null: SchurRedBlack*Solve may run source preparation, CG and reconstruction as one library call
+  virtual struct FusedCG *Fused() { return nullptr; }
+};
+struct FusedCG { RealD *Tolerance; Integer *MaxIterations; Integer *IterationsToComplete; RealD *TrueResidual; bool *ErrorOnNoConverge; };
+template <class Field> class ConjugateGradient : public OperatorFunction<Field> {
+  FusedCG _fused{&Tolerance, &MaxIterations, &IterationsToComplete, &TrueResidual, &ErrorOnNoConverge};
+public:
+  FusedCG *Fused() override { return &_fused; }
   bool ErrorOnNoConverge;
   RealD Tolerance;
   Integer MaxIterations;
   Integer IterationsToComplete = 0;
   RealD TrueResidual = 0;
   ConjugateGradient(RealD tol, Integer maxit, bool err_on_no_conv = true) : ErrorOnNoConverge(err_on_no_conv), Tolerance(tol), MaxIterations(maxit) {}
-  void operator()(LinearOperatorBase<Field> &Linop, const Field &src, Field &psi) {
+  void operator()(LinearOperatorBase<Field> &Linop, const Field &src, Field &psi) override {
     int rc;
     if (gb_fermop *m = Linop.FusedSchurMatrix()) {
       rc = gb_cg_schur(m, src.h, psi.h, Tolerance, MaxIterations, &IterationsToComplete, &TrueResidual);
@@ -295,5 +313,55 @@ public:
     GB_ASSERT_OK(rc);
   }
 };
+
+
+// ---- SchurRedBlackDiagMooeeSolve / SchurRedBlackStaggeredSolve (ref: Grid/algorithms/iterative/SchurRedBlack.h:96-290,294-349,385-430)
+//   SchurRedBlackDiagMooeeSolve<LatticeFermion> SchurSolver(CG);  SchurSolver(Ddwf, src, result);   solves M result = src
+template <class Field, bool Staggered> class SchurRedBlackSolveT {
+protected:
+  OperatorFunction<Field> &_HermitianRBSolver;
+  bool subGuess, useSolnAsInitGuess;
+public:
+  RealD TrueUnprecResidual = 0;   // the "true unprec resid" the reference logs (ref: :277-285)
+  SchurRedBlackSolveT(OperatorFunction<Field> &HermitianRBSolver, const bool initSubGuess = false, const bool _solnAsInitGuess = false)
+      : _HermitianRBSolver(HermitianRBSolver), subGuess(initSubGuess), useSolnAsInitGuess(_solnAsInitGuess) {}
+  void subtractGuess(const bool initSubGuess) { subGuess = initSubGuess; }
+  bool isSubtractGuess() { return subGuess; }
+  template <class Matrix> void RedBlackSource(Matrix &_Matrix, const Field &src, Field &src_e, Field &src_o) { GB_ASSERT_OK(gb_schur_redblack_source(_Matrix.h, src.h, src_e.h, src_o.h)); }
+  template <class Matrix> void RedBlackSolution(Matrix &_Matrix, const Field &sol_o, const Field &src_e, Field &sol) { GB_ASSERT_OK(gb_schur_redblack_solution(_Matrix.h, sol_o.h, src_e.h, sol.h)); }
+  template <class Matrix> void RedBlackSolve(Matrix &_Matrix, const Field &src_o, Field &sol_o) {
+    if constexpr (Staggered) { SchurStaggeredOperator<Matrix, Field> _HermOpEO(_Matrix); _HermitianRBSolver(_HermOpEO, src_o, sol_o); }
+    else { SchurDiagMooeeOperator<Matrix, Field> _HermOpEO(_Matrix); _HermitianRBSolver(_HermOpEO, src_o, sol_o); }
+    assert(sol_o.Checkerboard() == Odd);
+  }
+  template <class Matrix> void operator()(Matrix &_Matrix, const Field &in, Field &out) {
+    if (FusedCG *f = subGuess ? nullptr : _HermitianRBSolver.Fused()) {
+      double rs[2];
+      int rc = gb_schur_solve(_Matrix.h, in.h, out.h, *f->Tolerance, *f->MaxIterations, useSolnAsInitGuess ? 1 : 0, f->IterationsToComplete, rs);
+      *f->TrueResidual = rs[0]; TrueUnprecResidual = rs[1];
+      if (rc == GB_ERR_NOT_CONVERGED) { if (*f->ErrorOnNoConverge) assert(0 && "ConjugateGradient did NOT converge"); return; }
+      GB_ASSERT_OK(rc);
+      return;
+    }
+    GridBase rb(*in.Grid()); rb.redblack = true;
+    Field src_e(&rb), src_o(&rb), sol_o(&rb), guess_save(&rb);
+    RedBlackSource(_Matrix, in, src_e, src_o);
+    if (useSolnAsInitGuess) pickCheckerboard(Odd, sol_o, out);
+    else { sol_o.Zero(); sol_o.SetCheckerboard(Odd); }                 // ZeroGuesser
+    guess_save = sol_o;
+    RedBlackSolve(_Matrix, src_o, sol_o);
+    if (subGuess) axpy(sol_o, -1.0, guess_save, sol_o);
+    RedBlackSolution(_Matrix, sol_o, src_e, out);
+    if (!subGuess) {
+      Field resid(in.Grid());
+      _Matrix.M(out, resid);
+      axpy(resid, -1.0, in, resid);
+      TrueUnprecResidual = std::sqrt(norm2(resid) / norm2(in));
+    }
+  }
+};
+template <class Field> using SchurRedBlackDiagMooeeSolve = SchurRedBlackSolveT<Field, false>;
+template <class Field> using SchurRedBlackStaggeredSolve = SchurRedBlackSolveT<Field, true>;
+template <class Field> using SchurRedBlackStagSolve = SchurRedBlackSolveT<Field, true>;
 
 } // namespace gridb200

@@ -606,6 +606,79 @@ template <class T> struct FermOp {
   void HermOp(const F *in, F *out, int cb) const { // MpcDagMpc, ref: LinearOperator.h:291-307
     Vec tmp(V5cb()); Mpc(in, tmp.data(), cb); MpcDag(tmp.data(), out, cb);
   }
+  // ---- physical 4D <-> 5D maps.  4D fields have V4 sites, 5D fields V4*Ls (s fastest).
+  // Wilson4D: every map is the identity (ref: FermionOperator.h:172-191).
+  // Dminus: chi_s = psi_s - cs[s] DW(psi)_s ; DminusDag uses DW^dag   ref: CayleyFermion5DImplementation.h:132-153
+  void Dminus(const F *psi, F *chi, int dag) const {
+    if (kind == OpKind::Wilson4D) { std::copy(psi, psi + V5(), chi); return; }
+    Vec tmp(V5()); DW(psi, tmp.data(), dag);
+    const int Ls = k.Ls;
+#pragma omp parallel for
+    for (int64_t i = 0; i < V5(); i++) {
+      const T c = (T)(-k.cs[i % Ls]);
+      for (int a = 0; a < Ns; a++) for (int col = 0; col < Nc; col++) chi[i].v[a][col] = psi[i].v[a][col] + c * tmp[i].v[a][col];
+    }
+  }
+  // imported5d_{s=0} = P+ in4d, imported5d_{s=Ls-1} = P- in4d, zero elsewhere   ref: :100-113
+  void ImportUnphysicalFermion(const F *in4, F *out5) const {
+    if (kind == OpKind::Wilson4D) { std::copy(in4, in4 + V5(), out5); return; }
+    const int Ls = k.Ls;
+    std::memset((void *)out5, 0, sizeof(F) * V5());
+#pragma omp parallel for
+    for (int64_t i4 = 0; i4 < g.V4(); i4++)
+      for (int c = 0; c < Nc; c++) {
+        for (int a = 0; a < 2; a++) out5[i4 * Ls].v[a][c] = in4[i4].v[a][c];           // Ls >= 2 (Cayley operators)
+        for (int a = 2; a < 4; a++) out5[i4 * Ls + Ls - 1].v[a][c] = in4[i4].v[a][c];
+      }
+  }
+  // ref: :115-130  Dminus of the above
+  void ImportPhysicalFermionSource(const F *in4, F *out5) const {
+    if (kind == OpKind::Wilson4D) { std::copy(in4, in4 + V5(), out5); return; }
+    Vec tmp(V5()); ImportUnphysicalFermion(in4, tmp.data()); Dminus(tmp.data(), out5, 0);
+  }
+  // exported4d = P- sol_{s=0} + P+ sol_{s=Ls-1}   ref: :58-69
+  void ExportPhysicalFermionSolution(const F *sol5, F *out4) const {
+    if (kind == OpKind::Wilson4D) { std::copy(sol5, sol5 + V5(), out4); return; }
+    const int Ls = k.Ls;
+#pragma omp parallel for
+    for (int64_t i4 = 0; i4 < g.V4(); i4++)
+      for (int c = 0; c < Nc; c++) {
+        for (int a = 0; a < 2; a++) out4[i4].v[a][c] = sol5[i4 * Ls + Ls - 1].v[a][c];
+        for (int a = 2; a < 4; a++) out4[i4].v[a][c] = sol5[i4 * Ls].v[a][c];
+      }
+  }
+  // exported4d = P+ src_{s=0} + P- src_{s=Ls-1}   ref: :88-99
+  void ExportPhysicalFermionSource(const F *src5, F *out4) const {
+    if (kind == OpKind::Wilson4D) { std::copy(src5, src5 + V5(), out4); return; }
+    const int Ls = k.Ls;
+#pragma omp parallel for
+    for (int64_t i4 = 0; i4 < g.V4(); i4++)
+      for (int c = 0; c < Nc; c++) {
+        for (int a = 0; a < 2; a++) out4[i4].v[a][c] = src5[i4 * Ls].v[a][c];
+        for (int a = 2; a < 4; a++) out4[i4].v[a][c] = src5[i4 * Ls + Ls - 1].v[a][c];
+      }
+  }
+  // ---- SchurRedBlackDiagMooeeSolve pieces   ref: Grid/algorithms/iterative/SchurRedBlack.h:385-430
+  // src_o' = MpcDag (src_o - Meooe MooeeInv src_e)
+  void RedBlackSource(const F *src, F *src_e, F *src_o) const {
+    Geometry g5 = g;
+    Vec tmp(V5cb()), Mtmp(V5cb()), so(V5cb());
+    pickCheckerboard(g5, Even, src_e, src);
+    pickCheckerboard(g5, Odd, so.data(), src);
+    MooeeInv(g.V4cb(), src_e, tmp.data());
+    Meooe(tmp.data(), Mtmp.data(), Even);
+    axpy(V5cb(), tmp.data(), (T)-1, Mtmp.data(), so.data());
+    MpcDag(tmp.data(), src_o, Odd);
+  }
+  // sol_e = MooeeInv (src_e - Meooe sol_o) ; sol = [sol_e, sol_o]
+  void RedBlackSolution(const F *sol_o, const F *src_e, F *sol) const {
+    Vec tmp(V5cb()), sol_e(V5cb());
+    Meooe(sol_o, tmp.data(), Odd);
+    axpy(V5cb(), tmp.data(), (T)-1, tmp.data(), src_e);
+    MooeeInv(g.V4cb(), tmp.data(), sol_e.data());
+    setCheckerboard(g, Even, sol, sol_e.data());
+    setCheckerboard(g, Odd, sol, sol_o);
+  }
 };
 
 // ------------------------------------------------------------------ solvers
@@ -651,6 +724,23 @@ CGResult ConjugateGradient(const FermOp<T> &op, int cb, const Spinor<T> *src, Sp
     }
   }
   res.iterations = k; res.converged = 0;
+  return res;
+}
+
+// SchurRedBlackDiagMooeeSolve<Field>(ConjugateGradient)(op, src, sol) with the ZeroGuesser: red-black source, CG on
+// MpcDagMpc for the odd checkerboard, even-site reconstruction, then the unpreconditioned residual |M sol - src| / |src|
+// the reference prints.   ref: Grid/algorithms/iterative/SchurRedBlack.h:238-290,385-430
+template <class T>
+CGResult SchurRedBlackDiagMooeeSolve(const FermOp<T> &op, const Spinor<T> *src, Spinor<T> *sol, double tol, int maxit, double *unprec_resid) {
+  const int64_t n = op.V5cb(), nf = op.V5();
+  std::vector<Spinor<T>> src_e(n), src_o(n), sol_o(n), resid(nf);
+  op.RedBlackSource(src, src_e.data(), src_o.data());
+  std::memset((void *)sol_o.data(), 0, sizeof(Spinor<T>) * n);
+  CGResult res = ConjugateGradient(op, Odd, src_o.data(), sol_o.data(), tol, maxit);
+  op.RedBlackSolution(sol_o.data(), src_e.data(), sol);
+  op.M(sol, resid.data());
+  axpy(nf, resid.data(), (T)-1, src, resid.data());
+  if (unprec_resid) *unprec_resid = std::sqrt(norm2(nf, resid.data()) / norm2(nf, src));
   return res;
 }
 

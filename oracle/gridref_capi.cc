@@ -20,7 +20,7 @@ namespace {
 enum {
   OP_DHOP = 0, OP_DHOP_OE = 1, OP_DHOP_EO = 2, OP_M = 3, OP_MDAG = 4, OP_MEOOE = 5, OP_MEOOE_DAG = 6, OP_MOOEE = 7,
   OP_MOOEE_DAG = 8, OP_MOOEE_INV = 9, OP_MOOEE_INV_DAG = 10, OP_MPC = 11, OP_MPC_DAG = 12, OP_HERMOP = 13, OP_DW = 14,
-  OP_MEOOE5D = 15, OP_MEOOEDAG5D = 16
+  OP_MEOOE5D = 15, OP_MEOOEDAG5D = 16, OP_DMINUS = 17, OP_DMINUS_DAG = 18
 };
 enum { KIND_WILSON = 0, KIND_CAYLEY = 1, KIND_STAGGERED = 2 };
 
@@ -34,6 +34,11 @@ struct BoxBase {
   virtual void cg(int cb, const void *src, void *sol, double tol, int maxit, int *iters, double *tr) = 0;
   virtual void pick(int cb, void *half, const void *full) = 0;
   virtual void set(int cb, void *full, const void *half) = 0;
+  // physical 4D <-> 5D maps and SchurRedBlack*Solve
+  virtual int physical(int which, const void *in, void *out) { return -1; }
+  virtual void redblack_source(const void *src, void *src_e, void *src_o) = 0;
+  virtual void redblack_solution(const void *sol_o, const void *src_e, void *sol) = 0;
+  virtual void schur_solve(const void *src, void *sol, double tol, int maxit, int *iters, double *resid) = 0;
 };
 
 template <class Field> void import_lex(Field &f, const void *host) {
@@ -48,6 +53,41 @@ template <class Field> void export_lex(const Field &f, void *host) {
   std::vector<sobj> tmp;
   unvectorizeToLexOrdArray(tmp, f);
   std::memcpy(host, (const void *)tmp.data(), tmp.size() * sizeof(sobj));
+}
+
+// the common body of the three SchurRedBlack entry points, for any Solver = SchurRedBlack{DiagMooee,Staggered}Solve<Field>
+template <class Solver, class Matrix, class Field>
+void rb_source(Matrix &M, GridBase *fg, GridBase *rbg, const void *src, void *src_e, void *src_o) {
+  ConjugateGradient<Field> CG(1e-8, 1, false);
+  Solver S(CG);
+  Field f(fg), e(rbg), o(rbg);
+  import_lex(f, src);
+  S.RedBlackSource(M, f, e, o);
+  export_lex(e, src_e); export_lex(o, src_o);
+}
+template <class Solver, class Matrix, class Field>
+void rb_solution(Matrix &M, GridBase *fg, GridBase *rbg, const void *sol_o, const void *src_e, void *sol) {
+  ConjugateGradient<Field> CG(1e-8, 1, false);
+  Solver S(CG);
+  Field f(fg), e(rbg), o(rbg);
+  import_lex(o, sol_o); import_lex(e, src_e);
+  o.Checkerboard() = Odd; e.Checkerboard() = Even;
+  f = Zero();
+  S.RedBlackSolution(M, o, e, f);
+  export_lex(f, sol);
+}
+template <class Solver, class Matrix, class Field>
+void rb_solve(Matrix &M, GridBase *fg, const void *src, void *sol, double tol, int maxit, int *iters, double *resid) {
+  ConjugateGradient<Field> CG(tol, maxit, false);
+  Solver S(CG);
+  Field f(fg), x(fg), r(fg);
+  import_lex(f, src);
+  x = Zero();
+  S(M, f, x);
+  iters[0] = CG.IterationsToComplete; iters[1] = CG.IterationsToComplete < maxit; resid[0] = CG.TrueResidual;
+  M.M(x, r); r = r - f;
+  resid[1] = std::sqrt(norm2(r) / norm2(f));
+  export_lex(x, sol);
 }
 
 // Simd tag -> grids
@@ -116,6 +156,8 @@ template <class Impl, class vComplexT> struct WilsonBox : BoxBase {
     case OP_DW: if (!w5) return -1; w5->DW(x, y, dag); break;
     case OP_MEOOE5D: if (!cay) return -1; cay->Meooe5D(x, y); break;
     case OP_MEOOEDAG5D: if (!cay) return -1; cay->MeooeDag5D(x, y); break;
+    case OP_DMINUS: op->Dminus(x, y); break;
+    case OP_DMINUS_DAG: op->DminusDag(x, y); break;
     default: return -1;
     }
     export_lex(y, out);
@@ -143,6 +185,27 @@ template <class Impl, class vComplexT> struct WilsonBox : BoxBase {
     h.Checkerboard() = cb;
     setCheckerboard(f, h);
     export_lex(f, full);
+  }
+  // which: 0 ImportPhysicalFermionSource, 1 ImportUnphysicalFermion (4D -> 5D), 2 ExportPhysicalFermionSolution,
+  // 3 ExportPhysicalFermionSource (5D -> 4D).  For WilsonFermion both sides are the 4D grid.
+  int physical(int which, const void *in, void *out) override {
+    FermionField f4(G.UGrid), f5(fgrid());
+    if (which < 2) {
+      import_lex(f4, in);
+      if (which == 0) op->ImportPhysicalFermionSource(f4, f5); else op->ImportUnphysicalFermion(f4, f5);
+      export_lex(f5, out);
+    } else {
+      import_lex(f5, in);
+      if (which == 2) op->ExportPhysicalFermionSolution(f5, f4); else op->ExportPhysicalFermionSource(f5, f4);
+      export_lex(f4, out);
+    }
+    return 0;
+  }
+  typedef SchurRedBlackDiagMooeeSolve<FermionField> RBSolver;
+  void redblack_source(const void *src, void *src_e, void *src_o) override { rb_source<RBSolver, OpBase, FermionField>(*op, fgrid(), frbgrid(), src, src_e, src_o); }
+  void redblack_solution(const void *sol_o, const void *src_e, void *sol) override { rb_solution<RBSolver, OpBase, FermionField>(*op, fgrid(), frbgrid(), sol_o, src_e, sol); }
+  void schur_solve(const void *src, void *sol, double tol, int maxit, int *iters, double *resid) override {
+    rb_solve<RBSolver, OpBase, FermionField>(*op, fgrid(), src, sol, tol, maxit, iters, resid);
   }
 };
 
@@ -204,6 +267,13 @@ template <class Impl, class vComplexT> struct StagBox : BoxBase {
     FermionField f(G.UGrid), h(G.UrbGrid);
     import_lex(f, full); import_lex(h, half); h.Checkerboard() = cb; setCheckerboard(f, h); export_lex(f, full);
   }
+  typedef SchurRedBlackStaggeredSolve<FermionField> RBSolver;
+  typedef ImprovedStaggeredFermion<Impl> Op;
+  void redblack_source(const void *src, void *src_e, void *src_o) override { rb_source<RBSolver, Op, FermionField>(*op, G.UGrid, G.UrbGrid, src, src_e, src_o); }
+  void redblack_solution(const void *sol_o, const void *src_e, void *sol) override { rb_solution<RBSolver, Op, FermionField>(*op, G.UGrid, G.UrbGrid, sol_o, src_e, sol); }
+  void schur_solve(const void *src, void *sol, double tol, int maxit, int *iters, double *resid) override {
+    rb_solve<RBSolver, Op, FermionField>(*op, G.UGrid, src, sol, tol, maxit, iters, resid);
+  }
 };
 
 } // namespace
@@ -254,6 +324,16 @@ void gref_pick_checkerboard(void *h, int cb, void *half, const void *full) { ((B
 void gref_set_checkerboard(void *h, int cb, void *full, const void *half) { ((BoxBase *)h)->set(cb, full, half); }
 void gref_cg(void *h, int cb, const void *src, void *sol, double tol, int maxit, int *out_iters, double *out_true_resid) {
   ((BoxBase *)h)->cg(cb, src, sol, tol, maxit, out_iters, out_true_resid);
+}
+
+int gref_physical(void *h, int which, const void *in, void *out) { return ((BoxBase *)h)->physical(which, in, out); }
+void gref_redblack_source(void *h, const void *src, void *src_e, void *src_o) { ((BoxBase *)h)->redblack_source(src, src_e, src_o); }
+void gref_redblack_solution(void *h, const void *sol_o, const void *src_e, void *sol) { ((BoxBase *)h)->redblack_solution(sol_o, src_e, sol); }
+// SchurRedBlackDiagMooeeSolve / SchurRedBlackStaggeredSolve with ConjugateGradient and the ZeroGuesser, as
+// tests/solver/Test_dwf_cg_schur.cc:46-50 and Test_staggered_cg_schur.cc set it up.
+// out_iters: [iterations, converged]; out_resid: [CG TrueResidual, |M sol - src| / |src|]
+void gref_schur_solve(void *h, const void *src, void *sol, double tol, int maxit, int *out_iters, double *out_resid) {
+  ((BoxBase *)h)->schur_solve(src, sol, tol, maxit, out_iters, out_resid);
 }
 
 // MixedPrecisionConjugateGradient exactly as tests/Test_dwf_mixedcg_prec.cc:113-196 sets it up.

@@ -22,7 +22,7 @@ template <> FermOp<double> &get<double>(OpBox *b) { return b->d; }
 enum {
   OP_DHOP = 0, OP_DHOP_OE = 1, OP_DHOP_EO = 2, OP_M = 3, OP_MDAG = 4, OP_MEOOE = 5, OP_MEOOE_DAG = 6, OP_MOOEE = 7,
   OP_MOOEE_DAG = 8, OP_MOOEE_INV = 9, OP_MOOEE_INV_DAG = 10, OP_MPC = 11, OP_MPC_DAG = 12, OP_HERMOP = 13, OP_DW = 14,
-  OP_MEOOE5D = 15, OP_MEOOEDAG5D = 16
+  OP_MEOOE5D = 15, OP_MEOOEDAG5D = 16, OP_DMINUS = 17, OP_DMINUS_DAG = 18
 };
 
 template <class T> int applyT(OpBox *box, int which, const void *vin, void *vout, int dag, int cb_in, int half) {
@@ -48,6 +48,21 @@ template <class T> int applyT(OpBox *box, int which, const void *vin, void *vout
   case OP_DW: op.DW(in, out, dag); break;
   case OP_MEOOE5D: op.Meooe5D(n4, in, out); break;
   case OP_MEOOEDAG5D: op.MeooeDag5D(n4, in, out); break;
+  case OP_DMINUS: op.Dminus(in, out, 0); break;
+  case OP_DMINUS_DAG: op.Dminus(in, out, 1); break;
+  default: return -1;
+  }
+  return 0;
+}
+// Physical 4D <-> 5D maps.  which: 0 ImportPhysicalFermionSource (4D -> 5D), 1 ImportUnphysicalFermion
+// (4D -> 5D), 2 ExportPhysicalFermionSolution (5D -> 4D), 3 ExportPhysicalFermionSource (5D -> 4D)
+template <class T> static int physicalT(FermOp<T> &op, int which, const void *in, void *out) {
+  const Spinor<T> *i = (const Spinor<T> *)in; Spinor<T> *o = (Spinor<T> *)out;
+  switch (which) {
+  case 0: op.ImportPhysicalFermionSource(i, o); break;
+  case 1: op.ImportUnphysicalFermion(i, o); break;
+  case 2: op.ExportPhysicalFermionSolution(i, o); break;
+  case 3: op.ExportPhysicalFermionSource(i, o); break;
   default: return -1;
   }
   return 0;
@@ -128,6 +143,29 @@ void orc_cg(void *h, int cb, const void *src, void *sol, double tol, int maxit, 
                               : ConjugateGradient(box->d, cb, (const Spinor<double> *)src, (Spinor<double> *)sol, tol, maxit);
   out_iters[0] = r.iterations; out_iters[1] = r.converged; *out_true_resid = r.true_residual;
 }
+int orc_physical(void *h, int which, const void *in, void *out) {
+  OpBox *box = (OpBox *)h;
+  return box->prec == 0 ? physicalT(box->f, which, in, out) : physicalT(box->d, which, in, out);
+}
+// SchurRedBlackDiagMooeeSolve pieces: full-lattice src -> (src_e, src_o') ; (sol_o, src_e) -> full-lattice sol
+void orc_redblack_source(void *h, const void *src, void *src_e, void *src_o) {
+  OpBox *box = (OpBox *)h;
+  if (box->prec == 0) box->f.RedBlackSource((const Spinor<float> *)src, (Spinor<float> *)src_e, (Spinor<float> *)src_o);
+  else box->d.RedBlackSource((const Spinor<double> *)src, (Spinor<double> *)src_e, (Spinor<double> *)src_o);
+}
+void orc_redblack_solution(void *h, const void *sol_o, const void *src_e, void *sol) {
+  OpBox *box = (OpBox *)h;
+  if (box->prec == 0) box->f.RedBlackSolution((const Spinor<float> *)sol_o, (const Spinor<float> *)src_e, (Spinor<float> *)sol);
+  else box->d.RedBlackSolution((const Spinor<double> *)sol_o, (const Spinor<double> *)src_e, (Spinor<double> *)sol);
+}
+// the whole solve M sol = src with CG on the odd checkerboard. out_iters: [iterations, converged]; out_resid: [CG true
+// residual, unpreconditioned residual |M sol - src| / |src|]
+void orc_schur_solve(void *h, const void *src, void *sol, double tol, int maxit, int *out_iters, double *out_resid) {
+  OpBox *box = (OpBox *)h;
+  CGResult r = box->prec == 0 ? SchurRedBlackDiagMooeeSolve(box->f, (const Spinor<float> *)src, (Spinor<float> *)sol, tol, maxit, out_resid + 1)
+                              : SchurRedBlackDiagMooeeSolve(box->d, (const Spinor<double> *)src, (Spinor<double> *)sol, tol, maxit, out_resid + 1);
+  out_iters[0] = r.iterations; out_iters[1] = r.converged; out_resid[0] = r.true_residual;
+}
 // out_iters: [inner, outer, final, converged]
 void orc_mixed_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d, double tol, int maxinner, int maxouter,
                   int *out_iters, double *out_true_resid) {
@@ -188,6 +226,22 @@ void orc_stag_cg(void *h, int cb, const void *src, void *sol, double tol, int ma
   CGResult r = b->prec == 0 ? StagConjugateGradient(b->f, cb, (const ColourVector<float> *)src, (ColourVector<float> *)sol, tol, maxit)
                             : StagConjugateGradient(b->d, cb, (const ColourVector<double> *)src, (ColourVector<double> *)sol, tol, maxit);
   out_iters[0] = r.iterations; out_iters[1] = r.converged; *out_true_resid = r.true_residual;
+}
+void orc_stag_redblack_source(void *h, const void *src, void *src_e, void *src_o) {
+  StagBox *b = (StagBox *)h;
+  if (b->prec == 0) StagRedBlackSource(b->f, (const ColourVector<float> *)src, (ColourVector<float> *)src_e, (ColourVector<float> *)src_o);
+  else StagRedBlackSource(b->d, (const ColourVector<double> *)src, (ColourVector<double> *)src_e, (ColourVector<double> *)src_o);
+}
+void orc_stag_redblack_solution(void *h, const void *sol_o, const void *src_e, void *sol) {
+  StagBox *b = (StagBox *)h;
+  if (b->prec == 0) StagRedBlackSolution(b->f, (const ColourVector<float> *)sol_o, (const ColourVector<float> *)src_e, (ColourVector<float> *)sol);
+  else StagRedBlackSolution(b->d, (const ColourVector<double> *)sol_o, (const ColourVector<double> *)src_e, (ColourVector<double> *)sol);
+}
+void orc_stag_schur_solve(void *h, const void *src, void *sol, double tol, int maxit, int *out_iters, double *out_resid) {
+  StagBox *b = (StagBox *)h;
+  CGResult r = b->prec == 0 ? StagSchurSolve(b->f, (const ColourVector<float> *)src, (ColourVector<float> *)sol, tol, maxit, out_resid + 1)
+                            : StagSchurSolve(b->d, (const ColourVector<double> *)src, (ColourVector<double> *)sol, tol, maxit, out_resid + 1);
+  out_iters[0] = r.iterations; out_iters[1] = r.converged; out_resid[0] = r.true_residual;
 }
 void orc_stag_dhop_naive(const int *L, int prec, const void *Uthin, const void *Ufat, double c1, double c2, double u0, const void *in, void *out, int dag) {
   Geometry g; for (int i = 0; i < 4; i++) g.L[i] = L[i]; g.Ls = 1;

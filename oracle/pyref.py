@@ -18,7 +18,9 @@ _PATH = os.path.join(_HERE, "_ref", "libgridref.so")
 _LIB = None
 
 (OP_DHOP, OP_DHOP_OE, OP_DHOP_EO, OP_M, OP_MDAG, OP_MEOOE, OP_MEOOE_DAG, OP_MOOEE, OP_MOOEE_DAG, OP_MOOEE_INV,
- OP_MOOEE_INV_DAG, OP_MPC, OP_MPC_DAG, OP_HERMOP, OP_DW, OP_MEOOE5D, OP_MEOOEDAG5D) = range(17)
+ OP_MOOEE_INV_DAG, OP_MPC, OP_MPC_DAG, OP_HERMOP, OP_DW, OP_MEOOE5D, OP_MEOOEDAG5D, OP_DMINUS, OP_DMINUS_DAG) = range(19)
+# physical 4D <-> 5D maps
+IMPORT_PHYSICAL_SOURCE, IMPORT_UNPHYSICAL, EXPORT_PHYSICAL_SOLUTION, EXPORT_PHYSICAL_SOURCE = range(4)
 KIND_WILSON, KIND_CAYLEY, KIND_STAGGERED = 0, 1, 2
 OPT_GENERIC, OPT_HAND_UNROLL = 0, 1
 
@@ -41,6 +43,11 @@ def lib():
         L.gref_apply.restype = C.c_int
         L.gref_pick_checkerboard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_set_checkerboard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_physical.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_physical.restype = C.c_int
+        L.gref_redblack_source.argtypes = [C.c_void_p] * 4
+        L.gref_redblack_solution.argtypes = [C.c_void_p] * 4
+        L.gref_schur_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -141,6 +148,41 @@ class RefOp:
         tr = np.zeros(1, dtype=np.float64)
         lib().gref_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
         return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
+
+    # ---- physical 4D <-> 5D maps, SchurRedBlackDiagMooeeSolve
+    def physical(self, which, x):
+        """which = IMPORT_PHYSICAL_SOURCE / IMPORT_UNPHYSICAL (x: [V4,4,3] -> [V4*Ls,4,3]) or EXPORT_PHYSICAL_SOLUTION /
+        EXPORT_PHYSICAL_SOURCE ([V4*Ls,4,3] -> [V4,4,3])."""
+        x = np.ascontiguousarray(x, dtype=_cdtype(self.prec))
+        n_out = self.V4 * self.Ls if which < 2 else self.V4
+        assert x.shape[0] == (self.V4 if which < 2 else self.V4 * self.Ls), x.shape
+        out = np.empty((n_out,) + x.shape[1:], dtype=x.dtype)
+        rc = lib().gref_physical(self.h, which, _ptr(x), _ptr(out))
+        assert rc == 0, rc
+        return out
+
+    def redblack_source(self, src):
+        """SchurRedBlack*Solve::RedBlackSource: full-lattice src -> (src_e, src_o')"""
+        src = np.ascontiguousarray(src, dtype=_cdtype(self.prec))
+        e = np.empty((src.shape[0] // 2,) + src.shape[1:], dtype=src.dtype)
+        o = np.empty_like(e)
+        lib().gref_redblack_source(self.h, _ptr(src), _ptr(e), _ptr(o))
+        return e, o
+
+    def redblack_solution(self, sol_o, src_e):
+        sol_o = np.ascontiguousarray(sol_o, dtype=_cdtype(self.prec)); src_e = np.ascontiguousarray(src_e, dtype=_cdtype(self.prec))
+        sol = np.zeros((2 * sol_o.shape[0],) + sol_o.shape[1:], dtype=sol_o.dtype)
+        lib().gref_redblack_solution(self.h, _ptr(sol_o), _ptr(src_e), _ptr(sol))
+        return sol
+
+    def schur_solve(self, src, tol, maxit):
+        """M sol = src on the full lattice through the red-black Schur decomposition + CG (zero guess)."""
+        src = np.ascontiguousarray(src, dtype=_cdtype(self.prec))
+        sol = np.zeros_like(src)
+        it = np.zeros(2, dtype=np.int32)
+        rs = np.zeros(2, dtype=np.float64)
+        lib().gref_schur_solve(self.h, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(rs))
+        return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(rs[0]), unprec_residual=float(rs[1]))
 
 
 def mixed_cg(op_d, op_f, cb, src_d, tol, maxinner, maxouter):

@@ -1,0 +1,58 @@
+#!/usr/bin/env python
+"""Generates tests/golden/next_golden.npz from the COMPILED REFERENCE (oracle/_ref/libgridref.so, see make_golden.py) for the
+SURVEY 8(f) "next" rows.  Inputs (U, src4, src5, src_stag) are those of dirac_golden.npz and are not stored again.
+
+    make -C oracle -f Makefile.ref && python tests/golden/make_golden_next.py
+
+Row f1 (full propagator solve, ref: SchurRedBlack.h:238-290,385-430 ; CayleyFermion5DImplementation.h:58-153):
+  mobius/DMINUS, mobius/DMINUS_DAG                       CayleyFermion5D::Dminus / DminusDag on src5
+  mobius/physical/{0,1}                                  ImportPhysicalFermionSource / ImportUnphysicalFermion of src4
+  mobius/physical/{2,3}                                  ExportPhysicalFermionSolution / ExportPhysicalFermionSource of src5
+  <op>/rb_source/{e,o}, <op>/rb_solution                 SchurRedBlack*Solve::RedBlackSource(src) ; RedBlackSolution(pick(Odd,src), e)
+  <op>/schur_solve/{solution,iterations,true_residual,unprec_residual}   SchurRedBlack*Solve(ConjugateGradient(1e-8))(M, src, sol)
+for op in wilson, dwf, mobius (b=1.5,c=0.5), stag.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import pyref as pr                  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    G = np.load(os.path.join(HERE, "dirac_golden.npz"))
+    DIMS, LS = tuple(int(x) for x in G["dims"]), int(G["Ls"])
+    U, src4, src5, srcs = G["U"], G["src4"], G["src5"], G["src_stag"]
+    out = {}
+    ops = {
+        "wilson": (pr.RefOp(0, DIMS, 1, 0.1, prec=1), src4),
+        "dwf": (pr.RefOp(1, DIMS, LS, 0.1, 1.8, 1.0, 0.0, prec=1), src5),
+        "mobius": (pr.RefOp(1, DIMS, LS, 0.1, 1.8, 1.5, 0.5, prec=1), src5),
+        "stag": (pr.RefOp(2, DIMS, 1, 0.1, 9.0 / 8.0, -1.0 / 24.0, 1.0, prec=1), srcs),
+    }
+    for name, (op, src) in ops.items():
+        op.import_gauge(U)
+        if name == "mobius":
+            out["mobius/DMINUS"], out["mobius/DMINUS_DAG"] = op.apply(pr.OP_DMINUS, src), op.apply(pr.OP_DMINUS_DAG, src)
+            for w in range(4):
+                out[f"mobius/physical/{w}"] = op.physical(w, src4 if w < 2 else src5)
+        if name in ("mobius", "stag"):
+            e, o = op.redblack_source(src)
+            out[f"{name}/rb_source/e"], out[f"{name}/rb_source/o"] = e, o
+            out[f"{name}/rb_solution"] = op.redblack_solution(op.pick_checkerboard(1, src), e)
+        x, info = op.schur_solve(src, 1e-8, 5000)
+        out[f"{name}/schur_solve/solution"] = x
+        for k in ("iterations", "true_residual", "unprec_residual"):
+            out[f"{name}/schur_solve/{k}"] = np.array(info[k])
+    path = os.path.join(HERE, "next_golden.npz")
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB", file=sys.stderr)
+
+
+if __name__ == "__main__":
+    main()
