@@ -11,8 +11,12 @@
 // [block of 32 sites][72 float4 | 144 double2][32 lanes]: every load of a warp is one 512-byte row, each link byte is read
 // exactly once, and the 16 neighbour colour vectors (which fit in L2: 64 MB per parity at 48^4) are gathered with arithmetic
 // addressing -- no stencil table (ref: Grid/stencil/Stencil.h:79-136).
+#include "comm.hpp"
 #include "fermop.hpp"
 #include "kernels_common.cuh"
+#include "stag_halo.cuh"
+#include <cstdlib>
+#include <vector>
 
 namespace gb {
 
@@ -25,31 +29,7 @@ template <> struct CT<double> { using c = double2; using lv = double2; static co
 __device__ __forceinline__ float2 mkc(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ double2 mkc(double a, double b) { return make_double2(a, b); }
 
-struct StagGeom {
-  int L[4], Lxh, origin_parity;
-  int64_t V4cb, hblk;
-  FastDiv dLxh, dLy, dLz;
-};
-static StagGeom stag_geom(const gb_grid *g) {
-  StagGeom G;
-  for (int d = 0; d < 4; d++) G.L[d] = g->ldims[d];
-  G.Lxh = G.L[0] / 2;
-  G.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
-  G.V4cb = g->V4cb; G.hblk = (g->V4cb + W - 1) / W;
-  G.dLxh = FastDiv(G.Lxh); G.dLy = FastDiv(G.L[1]); G.dLz = FastDiv(G.L[2]);
-  return G;
-}
-__device__ __forceinline__ void stag_coor(const StagGeom &G, int p, uint32_t site, int &x, int &y, int &z, int &t) {
-  uint32_t r, xh, yy, zz;
-  G.dLxh.divmod(site, r, xh); G.dLy.divmod(r, r, yy); G.dLz.divmod(r, r, zz);
-  y = yy; z = zz; t = r;
-  x = 2 * xh + ((p + G.origin_parity + y + z + t) & 1);
-}
-__device__ __forceinline__ uint32_t stag_cb(const StagGeom &G, int x, int y, int z, int t) {
-  return (uint32_t)(x >> 1) + (uint32_t)G.Lxh * (y + G.L[1] * (z + G.L[2] * t));
-}
-// complex index of (site, colour) inside one parity block of a ColourVector field
-__device__ __forceinline__ size_t cv_index(uint32_t site, int c) { return ((size_t)(site >> LOGW) * 3 + c) * W + (site & (W - 1)); }
+static StagGeom stag_geom(const gb_grid *g) { return stag_geom_of(g->ldims, g->origin); }   // StagGeom and its index functions: stag_halo.cuh
 
 // =====================================================================================================
 // host <-> device, random, precision change for ColourVector fields
@@ -147,8 +127,8 @@ void stag_precision_change(gb_fermion *out, const gb_fermion *in) {
 // index l*9 + row*3 + col; fp32 packs two complex per float4.
 // =====================================================================================================
 template <class T> struct M3 { T re[9], im[9]; };
-template <class T> __device__ __forceinline__ M3<T> m3_load(const T *U, int64_t lex, int mu) {
-  M3<T> m; const T *p = U + (lex * 4 + mu) * 18;
+template <class T> __device__ __forceinline__ M3<T> m3_load_p(const T *p) {
+  M3<T> m;
 #pragma unroll
   for (int k = 0; k < 9; k++) { m.re[k] = p[2 * k]; m.im[k] = p[2 * k + 1]; }
   return m;
@@ -184,8 +164,10 @@ template <class T> __device__ __forceinline__ void link_store(T *rec_base /* sit
     q[0] = f * m.re[k]; q[1] = f * m.im[k];
   }
 }
+// three-deep faces of U_mu beyond the mu boundaries of a decomposed lattice (layout: stag_halo.cuh); all null on one rank
+template <class T> struct StagGaugeHalo { const T *thin[4][2], *fat[4][2]; int comm_dim_mask; };
 template <class T>
-__global__ void stag_double_store_kernel(T *links, size_t parity_stride /* scalars */, const T *Uthin, const T *Ufat, StagGeom G, int4 go, T f1, T f3) {
+__global__ void stag_double_store_kernel(T *links, size_t parity_stride /* scalars */, const T *Uthin, const T *Ufat, const StagGaugeHalo<T> H, StagGeom G, int4 go, T f1, T f3) {
   const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (e >= G.V4cb * 2 * 4) return;
   const int mu = e & 3;
@@ -194,23 +176,54 @@ __global__ void stag_double_store_kernel(T *links, size_t parity_stride /* scala
   const uint32_t site = (uint32_t)(sp - (int64_t)p * G.V4cb);
   int c[4];
   stag_coor(G, p, site, c[0], c[1], c[2], c[3]);
-  auto lex = [&](int d) { // lexicographic index of x + d*mu (periodic)
-    int q[4] = {c[0], c[1], c[2], c[3]};
-    q[mu] = ((c[mu] + d) % G.L[mu] + G.L[mu]) % G.L[mu];
-    return q[0] + (int64_t)G.L[0] * (q[1] + (int64_t)G.L[1] * (q[2] + (int64_t)G.L[2] * q[3]));
-  };
+  // U_mu(x + d mu): local (periodic wrap in undecomposed dimensions) or from the neighbour's faces
+  auto thin = [&](int d) { int w; const size_t o = stag_link_offset(G.L, H.comm_dim_mask, c, mu, d, &w); return m3_load_p(w < 0 ? Uthin + o : H.thin[mu][w] + o); };
+  auto fat = [&](int d) { int w; const size_t o = stag_link_offset(G.L, H.comm_dim_mask, c, mu, d, &w); return m3_load_p(w < 0 ? Ufat + o : H.fat[mu][w] + o); };
   const int gx = c[0] + go.x, gy = c[1] + go.y, gz = c[2] + go.z;
   const int par = mu == 0 ? 0 : mu == 1 ? gx : mu == 2 ? gx + gy : gx + gy + gz;
   const T eta = (par & 1) ? (T)-1 : (T)1;
   constexpr int VW = sizeof(T) == 4 ? 4 : 2;
   constexpr int LVN = CT<T>::LVN;
   T *rec = links + (size_t)p * parity_stride + ((size_t)(site >> SLOG) * LVN * SW + (site & (SW - 1))) * VW;
-  link_store(rec, mu * 2 + 0, m3_load(Ufat, lex(0), mu), eta * f1);
-  link_store(rec, mu * 2 + 1, m3_adj(m3_load(Ufat, lex(-1), mu)), -eta * f1);
-  const M3<T> fwd = m3_mul(m3_load(Uthin, lex(0), mu), m3_mul(m3_load(Uthin, lex(1), mu), m3_load(Uthin, lex(2), mu)));
-  const M3<T> bwd = m3_adj(m3_mul(m3_load(Uthin, lex(-3), mu), m3_mul(m3_load(Uthin, lex(-2), mu), m3_load(Uthin, lex(-1), mu))));
+  link_store(rec, mu * 2 + 0, fat(0), eta * f1);
+  link_store(rec, mu * 2 + 1, m3_adj(fat(-1)), -eta * f1);
+  const M3<T> fwd = m3_mul(thin(0), m3_mul(thin(1), thin(2)));
+  const M3<T> bwd = m3_adj(m3_mul(thin(-3), m3_mul(thin(-2), thin(-1))));
   link_store(rec, 8 + mu * 2 + 0, fwd, eta * f3);
   link_store(rec, 8 + mu * 2 + 1, bwd, -eta * f3);
+}
+
+// One halo message: my `send` buffer goes to rank `to`, `recv` is filled by rank `from`.  A neighbour that is this rank itself
+// (undecomposed dimension whose halos are forced on, see GB_STAG_SELF_HALO) is a device-to-device copy, like the reference's
+// comms-to-self path (ref: Grid/communicator/Communicator_none.cc SendToRecvFrom, Cshift_common.h local branch).
+struct HaloMsg { const void *send; void *recv; size_t bytes; int to, from; };
+static void stag_sendrecv(gb_context *ctx, const std::vector<HaloMsg> &msgs) {
+  bool remote = false;
+  for (const HaloMsg &m : msgs) {
+    if (m.to == ctx->rank && m.from == ctx->rank) GB_CUDA(cudaMemcpyAsync(m.recv, m.send, m.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    else remote = true;
+  }
+  if (!remote) return;
+  GB_REQUIRE(ctx->nccl != nullptr, "decomposed lattice: call gb_comm_init first");
+  NcclApi &N = nccl();
+  nccl_check(N.GroupStart(), "ncclGroupStart");
+  for (const HaloMsg &m : msgs) if (!(m.to == ctx->rank && m.from == ctx->rank)) {
+    nccl_check(N.Send(m.send, m.bytes, ncclChar, m.to, ctx->nccl, ctx->stream), "ncclSend");
+    nccl_check(N.Recv(m.recv, m.bytes, ncclChar, m.from, ctx->nccl, ctx->stream), "ncclRecv");
+  }
+  nccl_check(N.GroupEnd(), "ncclGroupEnd");
+}
+
+// gather the three slices of U_mu next to a mu boundary (dir 0: x_mu = 0..2, dir 1: x_mu = L-3..L-1) in the halo layout
+template <class T> __global__ void stag_gauge_face_kernel(const T *Ulex, T *face, StagGeom G, int mu, int dir, uint32_t nface) {
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (uint32_t)STAG_DEPTH * nface * 18) return;
+  const uint32_t i = e / 18, k = e - i * 18;
+  const uint32_t d = i / nface, fi = i - d * nface;
+  int x[4];
+  stag_gface_coor(G.L, mu, dir == 0 ? (int)d : G.L[mu] - STAG_DEPTH + (int)d, fi, x);
+  const size_t lex = x[0] + (size_t)G.L[0] * (x[1] + (size_t)G.L[1] * (x[2] + (size_t)G.L[2] * x[3]));
+  face[e] = Ulex[(lex * 4 + mu) * 18 + k];
 }
 
 void stag_import_gauge(gb_fermop *op, const gb_gauge *Uthin, const gb_gauge *Ufat) {
@@ -229,15 +242,53 @@ void stag_import_gauge(gb_fermop *op, const gb_gauge *Uthin, const gb_gauge *Ufa
   }
   StagGeom G = stag_geom(g);
   int4 go = make_int4(g->origin[0], g->origin[1], g->origin[2], g->origin[3]);
+  // decomposed lattice: three slices of U_mu (thin and fat) from both mu neighbours, the reference's Cshift(U, mu, -3..+2)
+  // [which: 0 thin, 1 fat][mu][dir]; dir 0 = my slices 0..2, consumed by the backward neighbour's x + d lookups
+  void *gsend[2][4][2] = {}, *grecv[2][4][2] = {};
+  const size_t esz = op->prec == GB_F32 ? 4 : 8;
+  if (op->comm_dim_mask) {
+    for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+      const uint32_t nface = stag_gface_sites(G.L, mu);
+      const size_t bytes = (size_t)STAG_DEPTH * nface * 18 * esz;
+      const unsigned fb = (unsigned)(((size_t)STAG_DEPTH * nface * 18 + 255) / 256);
+      for (int which = 0; which < 2; which++) for (int dir = 0; dir < 2; dir++) {
+        GB_CUDA(cudaMalloc(&gsend[which][mu][dir], bytes));
+        GB_CUDA(cudaMalloc(&grecv[which][mu][dir], bytes));
+        const void *U = which == 0 ? Uthin->data : Ufat->data;
+        if (op->prec == GB_F32) stag_gauge_face_kernel<float><<<fb, 256, 0, ctx->stream>>>((const float *)U, (float *)gsend[which][mu][dir], G, mu, dir, nface);
+        else stag_gauge_face_kernel<double><<<fb, 256, 0, ctx->stream>>>((const double *)U, (double *)gsend[which][mu][dir], G, mu, dir, nface);
+        count_launch(ctx);
+      }
+    }
+    check_launch(ctx, "stag_gauge_face");
+    std::vector<HaloMsg> msgs;
+    for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+      const size_t bytes = (size_t)STAG_DEPTH * stag_gface_sites(G.L, mu) * 18 * esz;
+      for (int which = 0; which < 2; which++) {
+        // halo dir 0 (x_mu >= L) holds the FORWARD neighbour's first slices: mine travel backward, and vice versa
+        msgs.push_back({gsend[which][mu][0], grecv[which][mu][0], bytes, g->nbr_rank[mu][1], g->nbr_rank[mu][0]});
+        msgs.push_back({gsend[which][mu][1], grecv[which][mu][1], bytes, g->nbr_rank[mu][0], g->nbr_rank[mu][1]});
+      }
+    }
+    stag_sendrecv(ctx, msgs);
+  }
   const int64_t n = g->V4cb * 2 * 4;
   const unsigned blocks = (unsigned)((n + 127) / 128);
   const double f1 = 0.5 * op->stag_c1 / op->stag_u0, f3 = 0.5 * op->stag_c2 / (op->stag_u0 * op->stag_u0 * op->stag_u0);
-  if (op->prec == GB_F32)
-    stag_double_store_kernel<float><<<blocks, 128, 0, ctx->stream>>>((float *)op->stag_links, parity_bytes / 4, (const float *)Uthin->data, (const float *)Ufat->data, G, go, (float)f1, (float)f3);
-  else
-    stag_double_store_kernel<double><<<blocks, 128, 0, ctx->stream>>>((double *)op->stag_links, parity_bytes / 8, (const double *)Uthin->data, (const double *)Ufat->data, G, go, f1, f3);
+  auto run = [&](auto tag) {
+    using T = decltype(tag);
+    StagGaugeHalo<T> H;
+    H.comm_dim_mask = op->comm_dim_mask;
+    for (int mu = 0; mu < 4; mu++) for (int dir = 0; dir < 2; dir++) { H.thin[mu][dir] = (const T *)grecv[0][mu][dir]; H.fat[mu][dir] = (const T *)grecv[1][mu][dir]; }
+    stag_double_store_kernel<T><<<blocks, 128, 0, ctx->stream>>>((T *)op->stag_links, parity_bytes / sizeof(T), (const T *)Uthin->data, (const T *)Ufat->data, H, G, go, (T)f1, (T)f3);
+  };
+  if (op->prec == GB_F32) run(float()); else run(double());
   count_launch(ctx);
   check_launch(ctx, "stag_double_store");
+  if (op->comm_dim_mask) {
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int which = 0; which < 2; which++) for (int mu = 0; mu < 4; mu++) for (int dir = 0; dir < 2; dir++) { cudaFree(gsend[which][mu][dir]); cudaFree(grecv[which][mu][dir]); }
+  }
 }
 
 // =====================================================================================================
@@ -251,6 +302,10 @@ template <class T> struct StagArgs {
   T axb;
   StagGeom G;
   int first_parity;
+  // decomposed lattices: received three-deep halos of the input field, point = mu + 4 * dir (layout: stag_halo.cuh)
+  const typename CT<T>::c *halo[8];
+  size_t halo_parity_stride[4];   // complex numbers between the two input-parity slots of a buffer
+  int comm_dim_mask;
 };
 
 template <class T> struct CV { T re[3], im[3]; };
@@ -288,7 +343,21 @@ __device__ __forceinline__ void pair_load(double (&a)[18], double (&b)[18], cons
   for (int j = 0; j < 9; j++) { const double2 v = __ldcs(rec + (size_t)(q * 18 + 9 + j) * SW); b[2 * j] = v.x; b[2 * j + 1] = v.y; }
 }
 
-template <class T, int DAG, int AX>
+// one thread per halo element: copy the colour vectors of the three boundary slices into the send buffer (no projection to
+// do for staggered fields: the compressor of the reference is the identity here, ref: Grid/stencil/SimpleCompressor.h:22-37)
+template <class T>
+__global__ void stag_pack_kernel(const typename CT<T>::c *__restrict__ in, typename CT<T>::c *__restrict__ buf, StagGeom G, int mu, int dir, int ip, uint32_t nface) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint32_t)STAG_DEPTH * nface) return;
+  const uint32_t d = i / nface, fi = i - d * nface;
+  int x, y, z, t;
+  stag_face_coor(G, mu, stag_send_slice(G, mu, dir, (int)d), fi, ip, x, y, z, t);
+  const uint32_t site = stag_cb(G, x, y, z, t);
+#pragma unroll
+  for (int c = 0; c < 3; c++) buf[cv_index(i, c)] = __ldg(in + cv_index(site, c));
+}
+
+template <class T, int DAG, int AX, int COMM>
 __global__ void __launch_bounds__(128) stag_dhop_kernel(const StagArgs<T> a) {
   const StagGeom &G = a.G;
   const int p = a.first_parity ^ (int)blockIdx.y;
@@ -306,12 +375,21 @@ __global__ void __launch_bounds__(128) stag_dhop_kernel(const StagArgs<T> a) {
     const int mu = q & 3, d = q < 4 ? 1 : 3;
     T uf[18], ub[18];
     pair_load(uf, ub, rec, q);
-    int n[4] = {c[0], c[1], c[2], c[3]};
-    const int L = G.L[mu];
-    n[mu] = c[mu] + d; if (n[mu] >= L) n[mu] -= L;
-    CV<T> xf; cv_load(xf, in, stag_cb(G, n[0], n[1], n[2], n[3]));
-    n[mu] = c[mu] - d; if (n[mu] < 0) n[mu] += L;
-    CV<T> xb; cv_load(xb, in, stag_cb(G, n[0], n[1], n[2], n[3]));
+    CV<T> xf, xb;
+    if (COMM) {   // neighbours beyond a decomposed boundary come from the received halos
+      uint32_t idx;
+      int w = stag_neighbour(G, a.comm_dim_mask, c, mu, d, idx);
+      cv_load(xf, w < 0 ? in : a.halo[mu + 4 * w] + (size_t)(1 - p) * a.halo_parity_stride[mu], idx);
+      w = stag_neighbour(G, a.comm_dim_mask, c, mu, -d, idx);
+      cv_load(xb, w < 0 ? in : a.halo[mu + 4 * w] + (size_t)(1 - p) * a.halo_parity_stride[mu], idx);
+    } else {
+      int n[4] = {c[0], c[1], c[2], c[3]};
+      const int L = G.L[mu];
+      n[mu] = c[mu] + d; if (n[mu] >= L) n[mu] -= L;
+      cv_load(xf, in, stag_cb(G, n[0], n[1], n[2], n[3]));
+      n[mu] = c[mu] - d; if (n[mu] < 0) n[mu] += L;
+      cv_load(xb, in, stag_cb(G, n[0], n[1], n[2], n[3]));
+    }
     mv_add(o, uf, xf);
     mv_add(o, ub, xb);
   }
@@ -322,6 +400,60 @@ __global__ void __launch_bounds__(128) stag_dhop_kernel(const StagArgs<T> a) {
     if (AX) { const auto w = a.ax[p][cv_index(site, k)]; re = fma(a.axb, w.x, re); im = fma(a.axb, w.y, im); }
     out[cv_index(site, k)] = mkc(re, im);
   }
+}
+
+// Halo buffers: per (mu, dir) two input-parity slots of STAG_DEPTH * nface colour vectors (cv_index layout, padded to W).
+static void stag_ensure_halo(gb_fermop *op) {
+  if (op->halo_ready) return;
+  const gb_grid *g = op->grid;
+  StagGeom G = stag_geom(g);
+  const size_t csz = op->prec == GB_F32 ? 8 : 16;
+  for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+    const size_t blocks = ((size_t)STAG_DEPTH * stag_nface(G, mu) + W - 1) / W;
+    op->halo_parity_stride[mu] = blocks * 3 * W;
+    const size_t bytes = 2 * op->halo_parity_stride[mu] * csz;
+    for (int dir = 0; dir < 2; dir++) {
+      GB_CUDA(cudaMalloc(&op->halo_send[mu + 4 * dir], bytes));
+      GB_CUDA(cudaMalloc(&op->halo_recv[mu + 4 * dir], bytes));
+      GB_CUDA(cudaMemsetAsync(op->halo_send[mu + 4 * dir], 0, bytes, op->ctx->stream));
+    }
+  }
+  op->halo_ready = true;
+}
+// pack the three boundary slices of every input parity of this hop and exchange them with the mu neighbours
+// (replaces CartesianStencil::HaloExchange for the 16-point staggered stencil, ref: Grid/stencil/Stencil.h:367-430,
+//  ImprovedStaggeredFermionImplementation.h:337-388 DhopInternalSerialComms)
+template <class T>
+static void stag_exchange(gb_fermop *op, const void *const in[2], int first_parity, int nparity) {
+  gb_context *ctx = op->ctx;
+  const gb_grid *g = op->grid;
+  stag_ensure_halo(op);
+  StagGeom G = stag_geom(g);
+  using C = typename CT<T>::c;
+  // input parities: the opposite of each output parity
+  const int ip0 = 1 - first_parity;
+  for (int k = 0; k < nparity; k++) {
+    const int ip = k == 0 ? ip0 : 1 - ip0;
+    for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+      const uint32_t nface = stag_nface(G, mu);
+      const unsigned blocks = (STAG_DEPTH * nface + 127) / 128;
+      for (int dir = 0; dir < 2; dir++) {
+        C *buf = (C *)op->halo_send[mu + 4 * dir] + (size_t)ip * op->halo_parity_stride[mu];
+        stag_pack_kernel<T><<<blocks, 128, 0, ctx->stream>>>((const C *)in[ip], buf, G, mu, dir, ip, nface);
+        count_launch(ctx);
+      }
+    }
+  }
+  check_launch(ctx, "stag_pack");
+  std::vector<HaloMsg> msgs;
+  for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
+    const size_t stride = op->halo_parity_stride[mu] * sizeof(C);
+    const size_t off = nparity == 2 ? 0 : (size_t)ip0 * stride, bytes = nparity == 2 ? 2 * stride : stride;
+    // halo dir 0 (the receiver's forward legs) is filled from MY first slices: it travels to my backward neighbour
+    msgs.push_back({(const char *)op->halo_send[mu] + off, (char *)op->halo_recv[mu] + off, bytes, g->nbr_rank[mu][1], g->nbr_rank[mu][0]});
+    msgs.push_back({(const char *)op->halo_send[mu + 4] + off, (char *)op->halo_recv[mu + 4] + off, bytes, g->nbr_rank[mu][0], g->nbr_rank[mu][1]});
+  }
+  stag_sendrecv(ctx, msgs);
 }
 
 // in[p]/out[p]: parity blocks.  Output parities first_parity (and the other one when nparity == 2).
@@ -335,9 +467,24 @@ static void stag_launch(gb_fermop *op, const void *const in[2], void *const out[
     a.ax[p] = ax ? (const typename CT<T>::c *)ax[p] : nullptr;
   }
   a.axb = (T)axb; a.G = stag_geom(op->grid); a.first_parity = first_parity;
+  a.comm_dim_mask = op->comm_dim_mask;
+  for (int i = 0; i < 8; i++) a.halo[i] = nullptr;
+  for (int mu = 0; mu < 4; mu++) a.halo_parity_stride[mu] = 0;
+  if (op->comm_dim_mask) {   // serial comms: pack the boundary slices of the input parities, exchange, then hop (ref: DhopInternalSerialComms)
+    stag_exchange<T>(op, in, first_parity, nparity);
+    for (int i = 0; i < 8; i++) a.halo[i] = (const typename CT<T>::c *)op->halo_recv[i];
+    for (int mu = 0; mu < 4; mu++) a.halo_parity_stride[mu] = op->halo_parity_stride[mu];
+  }
   dim3 grid((unsigned)((op->grid->V4cb + 127) / 128), nparity);
-  if (ax) { if (dag) stag_dhop_kernel<T, 1, 1><<<grid, 128, 0, ctx->stream>>>(a); else stag_dhop_kernel<T, 0, 1><<<grid, 128, 0, ctx->stream>>>(a); }
-  else { if (dag) stag_dhop_kernel<T, 1, 0><<<grid, 128, 0, ctx->stream>>>(a); else stag_dhop_kernel<T, 0, 0><<<grid, 128, 0, ctx->stream>>>(a); }
+#define GB_SK(D, A, C) stag_dhop_kernel<T, D, A, C><<<grid, 128, 0, ctx->stream>>>(a)
+  if (op->comm_dim_mask) {
+    if (ax) { if (dag) GB_SK(1, 1, 1); else GB_SK(0, 1, 1); }
+    else { if (dag) GB_SK(1, 0, 1); else GB_SK(0, 0, 1); }
+  } else {
+    if (ax) { if (dag) GB_SK(1, 1, 0); else GB_SK(0, 1, 0); }
+    else { if (dag) GB_SK(1, 0, 0); else GB_SK(0, 0, 0); }
+  }
+#undef GB_SK
   count_launch(ctx);
   check_launch(ctx, "stag_dhop");
 }
@@ -434,9 +581,15 @@ extern "C" {
 int gb_op_create_staggered(gb_grid *g, const gb_gauge *Uthin, const gb_gauge *Ufat, double mass, double c1, double c2, double u0, gb_fermop **out) {
   GB_API_BEGIN
   GB_REQUIRE(g && Uthin && Ufat && out, "null argument");
-  for (int d = 0; d < 4; d++) GB_REQUIRE(g->mpi[d] == 1, "staggered operators are single-rank in this round (three-deep Naik halos not built yet)");
   gb_fermop *op = new gb_fermop();
   op->grid = g; op->ctx = g->ctx; op->kind = GB_KIND_STAGGERED; op->prec = Uthin->prec; op->Ls = 1; op->mass = mass;
+  // three-deep halos in the decomposed dimensions; GB_STAG_SELF_HALO=<bitmask> also routes undecomposed dimensions through
+  // the pack / exchange-with-self / halo-lookup path (what the reference does for every dimension when it is told to treat
+  // local wraps as comms; here it lets one GPU exercise the whole multi-rank code path)
+  const int self_mask = getenv("GB_STAG_SELF_HALO") ? atoi(getenv("GB_STAG_SELF_HALO")) & 15 : 0;
+  bool decomposed = false;
+  for (int d = 0; d < 4; d++) { if (g->mpi[d] > 1) decomposed = true; if (g->mpi[d] > 1 || ((self_mask >> d) & 1)) op->comm_dim_mask |= 1 << d; }
+  if (decomposed && g->ctx->nccl == nullptr) { delete op; GB_REQUIRE(false, "decomposed lattice: call gb_comm_init before creating operators"); }
   op->stag_c1 = c1; op->stag_c2 = c2; op->stag_u0 = u0;
   try { stag_import_gauge(op, Uthin, Ufat); } catch (...) { delete op; throw; }
   *out = op;

@@ -173,7 +173,9 @@ int gb_op_import_gauge(gb_fermop *op, const gb_gauge *Umu);    /* ref: WilsonFer
  * gb_op_apply on it serves Dhop/DhopOE/DhopEO (dag = overall minus sign, ref: StaggeredKernelsImplementation.h:117-119),
  * M/Mdag, Meooe(+Dag), Mooee(+Dag) = mass, MooeeInv(+Dag) = 1/mass, and GB_OP_MPC = GB_OP_MPC_DAG = GB_OP_HERMOP =
  * SchurStaggeredOperator::Mpc = mass^2 - Meooe Meooe (ref: LinearOperator.h:543-584); gb_cg_schur runs CG on that.
- * Single rank this round (the Naik term needs three-deep halos). */
+ * Decomposed lattices: the Naik term reaches three sites, so every split dimension carries three-deep halos of the input
+ * field (packed and exchanged per hop) and of U_mu for the double store (ref: displacements +-1, +-3,
+ * instantiation/ImprovedStaggeredFermionInstantiation.cc:33-34 ; Stencil.h:709 needs local extents > 3). */
 int gb_op_create_staggered(gb_grid *g, const gb_gauge *Uthin, const gb_gauge *Ufat, double mass, double c1, double c2, double u0, gb_fermop **out);
 int gb_op_import_gauge_staggered(gb_fermop *op, const gb_gauge *Uthin, const gb_gauge *Ufat);
 int gb_op_destroy(gb_fermop *op);

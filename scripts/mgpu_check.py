@@ -104,6 +104,54 @@ for mpi, gdims, kinds in CASES:
                 print(f"{'ok  ' if ok else 'FAIL'} mpi {mpi} {kind} Ls{Ls} CG iterations {cg.IterationsToComplete} vs oracle {info['iterations']}, true resid {cg.TrueResidual:.3e} vs {info['true_residual']:.3e}", flush=True)
             if not ok:
                 fails.append("cg")
+# ---- improved staggered on the decomposed lattice (three-deep Naik halos of field and links), SURVEY 8 row a26 / 8e
+for mpi in (MPIS if os.environ.get("MGPU_SKIP_STAG") is None else []):
+    gdims = tuple(max(4 * m, 8) if m > 1 else (6 if d == 1 else 4) for d, m in enumerate(mpi))   # local extents 4 (6 in y when whole)
+    V = int(np.prod(gdims))
+    U = syn.hot_gauge(gdims, seed=5)
+    rng = np.random.default_rng(6)
+    src = rng.random((V, 3)) + 1j * rng.random((V, 3))
+    grid = gb.GridCartesian(ctx, gdims, mpi)
+    orc = po.StagOracleOp(gdims, 0.1, prec=1)
+    orc.import_gauge(U)
+    for prec, tol in ((gb.F32, 1e-6), (gb.F64, 1e-13)):
+        Umu = gb.LatticeGaugeField(grid, prec).import_lex(decomp.scatter(U, gdims, mpi, rank))
+        D = gb.ImprovedStaggeredFermion(Umu, Umu, grid, 0.1)
+        fin = gb.LatticeStaggeredFermion(grid, 1, prec).import_lex(decomp.scatter(src, gdims, mpi, rank).astype(gb._cdtype(prec)))
+        out = gb.LatticeStaggeredFermion(grid, 1, prec)
+
+        def stag_err(got, ref):   # relative to the rms site norm: single sites of a hop can cancel to ~0
+            d = np.linalg.norm(got.astype(np.complex128) - ref, axis=1); nb = np.linalg.norm(ref, axis=1)
+            return float(np.max(d / np.maximum(nb, np.sqrt(np.mean(nb ** 2)))))
+        for dag in (0, 1):
+            D.Dhop(fin, out, dag)
+            check(f"mpi {mpi} staggered prec{prec} Dhop dag{dag}", stag_err(out.export_lex(), decomp.scatter(orc.apply(po.OP_DHOP, src, dag=dag), gdims, mpi, rank)), tol)
+        D.M(fin, out)
+        check(f"mpi {mpi} staggered prec{prec} M", stag_err(out.export_lex(), decomp.scatter(orc.apply(po.OP_M, src), gdims, mpi, rank)), tol)
+        he, ho = gb.LatticeStaggeredFermion(grid, 1, prec, gb.HALF), gb.LatticeStaggeredFermion(grid, 1, prec, gb.HALF)
+        for cb_in, hin, hout, meth in ((gb.Odd, ho, he, D.DhopEO), (gb.Even, he, ho, D.DhopOE)):
+            gb.pickCheckerboard(cb_in, hin, fin)
+            meth(hin, hout, 0)
+            full = gb.LatticeStaggeredFermion(grid, 1, prec).zero()
+            gb.setCheckerboard(full, hout)
+            ref_f = np.zeros_like(src)
+            po.set_checkerboard_sites(gdims, 1 - cb_in, ref_f, orc.apply(po.OP_DHOP_EO if cb_in == gb.Odd else po.OP_DHOP_OE, po.pick_checkerboard_sites(gdims, cb_in, src)))
+            check(f"mpi {mpi} staggered prec{prec} Dhop{'EO' if cb_in == gb.Odd else 'OE'}", stag_err(full.export_lex(), decomp.scatter(ref_f, gdims, mpi, rank)), tol)
+    # CG on SchurStaggeredOperator and the full SchurRedBlackStaggeredSolve vs the oracle on the global lattice (fp64 operator from the loop)
+    x_ref, info = orc.cg(1, po.pick_checkerboard_sites(gdims, 1, src), 1e-8, 5000)
+    so, sol = gb.LatticeStaggeredFermion(grid, 1, gb.F64, gb.HALF), gb.LatticeStaggeredFermion(grid, 1, gb.F64, gb.HALF).zero()
+    gb.pickCheckerboard(gb.Odd, so, fin)
+    cg = gb.ConjugateGradient(1e-8, 5000)
+    cg(gb.SchurStaggeredOperator(D), so, sol)
+    ok = abs(cg.IterationsToComplete - info["iterations"]) <= max(1, 0.02 * info["iterations"])
+    if rank == 0:
+        print(f"{'ok  ' if ok else 'FAIL'} mpi {mpi} staggered CG iterations {cg.IterationsToComplete} vs oracle {info['iterations']}, true resid {cg.TrueResidual:.3e} vs {info['true_residual']:.3e}", flush=True)
+    if not ok:
+        fails.append("stag cg")
+    xs_ref, _ = orc.schur_solve(src, 1e-8, 5000)
+    xs = gb.LatticeStaggeredFermion(grid, 1, gb.F64)
+    gb.SchurRedBlackStaggeredSolve(gb.ConjugateGradient(1e-8, 5000))(D, fin, xs)
+    check(f"mpi {mpi} staggered SchurRedBlackStaggeredSolve", stag_err(xs.export_lex(), decomp.scatter(xs_ref, gdims, mpi, rank)), 1e-6)
 dist.barrier()
 if rank == 0:
     print("MGPU_CHECK " + ("PASS" if not fails else f"FAIL {fails}"), flush=True)
