@@ -54,6 +54,7 @@ SYMBOLS = [
     ("gb_op_dhop_host", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
+    ("gb_cg_multishift_schur", _i, [_vp, _vp, _i, _pd, _pd, _i, _pvp, _pi, _pd]),
     ("gb_op_import_physical_fermion_source", _i, [_vp, _vp, _vp]), ("gb_op_import_unphysical_fermion", _i, [_vp, _vp, _vp]),
     ("gb_op_export_physical_fermion_solution", _i, [_vp, _vp, _vp]), ("gb_op_export_physical_fermion_source", _i, [_vp, _vp, _vp]),
     ("gb_schur_redblack_source", _i, [_vp, _vp, _vp, _vp]), ("gb_schur_redblack_solution", _i, [_vp, _vp, _vp, _vp]),
@@ -610,3 +611,48 @@ def schur_solve_mixed(Mat_f, Mat_d, src, out, tol, maxinnerit, maxouterit):
     it, rs = (C.c_int * 3)(), (C.c_double * 2)()
     _chk(lib().gb_schur_solve_mixed(Mat_f.h, Mat_d.h, src.h, out.h, tol, maxinnerit, maxouterit, it, rs))
     return dict(inner=it[0], outer=it[1], final=it[2], true_residual=rs[0], unprec_residual=rs[1])
+
+
+class MultiShiftFunction:
+    """ref: Grid/algorithms/approx/MultiShiftFunction.h:34-44 -- order, poles, residues, tolerances, norm (no Remez here: the
+    caller supplies the partial-fraction coefficients)."""
+
+    def __init__(self, poles, tolerances, residues=None, norm=0.0):
+        self.poles = [float(x) for x in poles]
+        self.order = len(self.poles)
+        self.tolerances = [float(tolerances)] * self.order if np.isscalar(tolerances) else [float(x) for x in tolerances]
+        self.residues = [1.0] * self.order if residues is None else [float(x) for x in residues]
+        self.norm = float(norm)
+        assert len(self.tolerances) == self.order and len(self.residues) == self.order
+
+    def approx(self, x):
+        return self.norm + sum(r / (x + p) for r, p in zip(self.residues, self.poles))
+
+
+class ConjugateGradientMultiShift:
+    """ref: Grid/algorithms/iterative/ConjugateGradientMultiShift.h:40-343.  MSCG = ConjugateGradientMultiShift(maxit, shifts);
+    MSCG(HermOpEO, src_o, results) fills results[s] = (HermOp + poles[s])^-1 src_o; with a fourth argument psi it also forms
+    psi = norm * src + sum_s residues[s] * results[s] (:69-82)."""
+
+    def __init__(self, maxit, shifts):
+        self.MaxIterations, self.shifts = maxit, shifts
+        self.IterationsToComplete = 0
+        self.IterationsToCompleteShift = [0] * shifts.order
+        self.TrueResidualShift = [0.0] * shifts.order
+
+    def __call__(self, Linop, src, results, psi=None):
+        assert isinstance(Linop, SchurDiagMooeeOperator), "ConjugateGradientMultiShift runs on SchurDiagMooeeOperator / SchurStaggeredOperator"
+        n = self.shifts.order
+        assert len(results) == n
+        poles, tols = (C.c_double * n)(*self.shifts.poles), (C.c_double * n)(*self.shifts.tolerances)
+        handles = (C.c_void_p * n)(*[r.h.value for r in results])
+        it, tr = (C.c_int * (n + 1))(), (C.c_double * n)()
+        rc = lib().gb_cg_multishift_schur(Linop._Mat.h, src.h, n, poles, tols, self.MaxIterations, handles, it, tr)
+        self.IterationsToCompleteShift, self.TrueResidualShift, self.IterationsToComplete = list(it[:n]), list(tr), it[n]
+        if rc != GB_ERR_NOT_CONVERGED:     # the reference only logs "CG multi shift did not converge" (:336-338)
+            _chk(rc)
+        if psi is not None:
+            scale(psi, self.shifts.norm, src)
+            for res, r in zip(self.shifts.residues, results):
+                axpy(psi, res, r, psi)
+        return rc == GB_OK

@@ -6,7 +6,9 @@
 #include "fermop.hpp"
 #include "kernels_common.cuh"
 #include <cmath>
+#include <cstdlib>
 #include <functional>
+#include <vector>
 
 namespace gb {
 
@@ -150,11 +152,175 @@ static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fe
   return out;
 }
 
+// =====================================================================================================
+// ConjugateGradientMultiShift   ref: Grid/algorithms/iterative/ConjugateGradientMultiShift.h:84-343
+// One Krylov space for all shifts: (A + mass[s]) psi[s] = src, zero guess, primary shift = the lightest pole.  The
+// recurrences for z_s, b_s and the stopping rule c z_s^2 < |src|^2 tol_s^2 are the reference's; the per-shift linear algebra
+// is what the reference's own comments ask for (:213-218,:263-274): ONE launch updates every search direction (r is read
+// once for all shifts) and ONE launch updates every solution.  GB_MS_UNFUSED=1 runs the same algorithm through the
+// single-field BLAS entry points instead (tests compare the two bit for bit).
+// =====================================================================================================
+constexpr int MS_MAX = 12;   // fields per launch; more shifts go in chunks
+struct MsEntries { void *y[MS_MAX]; const void *x[MS_MAX]; double a[MS_MAX], b[MS_MAX]; int plain[MS_MAX]; int n; };
+// MODE 0 (search directions, shared r):  y_k = a_k y_k + r            (plain)   |   y_k = b_k r + a_k y_k
+// MODE 1 (solutions):                    y_k = a_k x_k + y_k
+template <class V, class T, int MODE> __global__ void ms_update_kernel(const MsEntries e, const V *__restrict__ r, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    V rv;
+    if (MODE == 0) rv = r[i];
+    for (int k = 0; k < e.n; k++) {
+      V *y = (V *)e.y[k];
+      if (MODE == 0) y[i] = e.plain[k] ? vaxpy((T)e.a[k], y[i], rv) : vaxpby((T)e.b[k], rv, (T)e.a[k], y[i]);
+      else y[i] = vaxpy((T)e.a[k], ((const V *)e.x[k])[i], y[i]);
+    }
+  }
+}
+template <int MODE> static void ms_update(gb_context *ctx, const MsEntries &e, const gb_fermion *r, const gb_fermion *like) {
+  if (e.n == 0) return;
+  const int64_t n = like->nvec();
+  const unsigned blocks = (unsigned)std::min<int64_t>((n + 255) / 256, (int64_t)ctx->sm_count * 16);
+  if (like->prec == GB_F32) ms_update_kernel<float4, float, MODE><<<blocks, 256, 0, ctx->stream>>>(e, r ? (const float4 *)r->data : nullptr, n);
+  else ms_update_kernel<double2, double, MODE><<<blocks, 256, 0, ctx->stream>>>(e, r ? (const double2 *)r->data : nullptr, n);
+  count_launch(ctx);
+  check_launch(ctx, "ms_update");
+}
+
+struct MSOut { std::vector<int> iters; std::vector<double> true_resid; int iters_to_complete = 0; bool converged = false; };
+
+static MSOut multishift_core(gb_context *ctx, const HermOpFn &A, const gb_fermion *src, gb_fermion *const *psi, int nshift, const double *mass,
+                             const double *mresidual, int maxit) {
+  static const bool unfused = getenv("GB_MS_UNFUSED") != nullptr;
+  GB_REQUIRE(nshift >= 1, "ConjugateGradientMultiShift needs at least one shift");
+  for (int s = 0; s < nshift; s++) {
+    GB_REQUIRE(psi[s] != nullptr && psi[s] != src, "null or aliased result field");
+    fermion_check_same(src, psi[s]);
+    GB_REQUIRE(mass[s] >= mass[0], "the first pole must be the lightest (ref: ConjugateGradientMultiShift.h:125-128)");
+  }
+  MSOut R;
+  R.iters.assign(nshift, 0); R.true_resid.assign(nshift, 0.0);
+  std::vector<double> alpha(nshift, 1.0), bs(nshift), rsq(nshift), z0v(nshift, 1.0), z1v(nshift, 1.0);
+  std::vector<int> converged(nshift, 0);
+  std::vector<gb_fermion *> ps(nshift, nullptr);
+  gb_fermion *r = nullptr, *p = nullptr, *tmp = nullptr, *mmp = nullptr;
+  struct Guard {
+    std::vector<gb_fermion *> &v; gb_fermion *&a, *&b, *&c, *&d;
+    ~Guard() { for (auto *f : v) gb_fermion_destroy(f); gb_fermion_destroy(a); gb_fermion_destroy(b); gb_fermion_destroy(c); gb_fermion_destroy(d); }
+  } guard{ps, r, p, tmp, mmp};
+  for (int s = 0; s < nshift; s++) ps[s] = fermion_create_like(src, src->prec);
+  r = fermion_create_like(src, src->prec); p = fermion_create_like(src, src->prec);
+  tmp = fermion_create_like(src, src->prec); mmp = fermion_create_like(src, src->prec);
+  double a, b, c, d, cp, bp, rn, dd[2];
+  chk(gb_norm2(src, &cp));
+  if (cp == 0.0) {   // ref :137-144
+    for (int s = 0; s < nshift; s++) { chk(gb_zero(psi[s])); psi[s]->cb = src->cb; R.iters[s] = 1; }
+    R.converged = true;
+    return R;
+  }
+  for (int s = 0; s < nshift; s++) { rsq[s] = cp * mresidual[s] * mresidual[s]; chk(gb_copy(ps[s], src)); }
+  chk(gb_copy(r, src)); chk(gb_copy(p, src));
+  // z[s][iz] / z[s][1-iz] of the reference are z1v / z0v here ("current" / "previous")
+  A(p, mmp);
+  chk(gb_inner_product(p, mmp, dd)); d = dd[0];
+  chk(gb_axpy(mmp, mass[0], p, mmp));
+  chk(gb_norm2(p, &rn));
+  d += rn * mass[0];
+  b = -cp / d;
+  bs[0] = b;
+  for (int s = 1; s < nshift; s++) { z0v[s] = 1.0; z1v[s] = 1.0 / (1.0 - b * (mass[s] - mass[0])); bs[s] = b * z1v[s]; }
+  chk(gb_axpy_norm(r, b, mmp, r, &c));
+  for (int s = 0; s < nshift; s++) { chk(gb_axpby(psi[s], 0.0, -bs[s] * alpha[s], src, src)); psi[s]->cb = src->cb; }
+  for (int k = 1; k <= maxit; k++) {
+    a = c / cp;
+    // search directions: p = a p + r ; ps[0] = a ps[0] + r ; ps[s] = z_s r + a_s ps[s]
+    if (unfused) {
+      chk(gb_axpy(p, a, p, r));
+      for (int s = 0; s < nshift; s++) if (!converged[s]) {
+        if (s == 0) chk(gb_axpy(ps[s], a, ps[s], r));
+        else chk(gb_axpby(ps[s], z1v[s], a * z1v[s] * bs[s] / (z0v[s] * b), r, ps[s]));
+      }
+    } else {
+      MsEntries e; e.n = 0;
+      auto push = [&](gb_fermion *y, double ca, double cb_, int plain) {
+        e.y[e.n] = y->data; e.x[e.n] = nullptr; e.a[e.n] = ca; e.b[e.n] = cb_; e.plain[e.n] = plain;
+        if (++e.n == MS_MAX) { ms_update<0>(ctx, e, r, src); e.n = 0; }
+      };
+      push(p, a, 1.0, 1);
+      for (int s = 0; s < nshift; s++) if (!converged[s]) {
+        if (s == 0) push(ps[s], a, 1.0, 1);
+        else push(ps[s], a * z1v[s] * bs[s] / (z0v[s] * b), z1v[s], 0);
+      }
+      ms_update<0>(ctx, e, r, src);
+    }
+    cp = c;
+    A(p, mmp);
+    chk(gb_inner_product(p, mmp, dd)); d = dd[0];
+    chk(gb_axpy(mmp, mass[0], p, mmp));
+    chk(gb_norm2(p, &rn));
+    d += rn * mass[0];
+    bp = b;
+    b = -cp / d;
+    chk(gb_axpy_norm(r, b, mmp, r, &c));
+    GB_REQUIRE(!std::isnan(c), "ConjugateGradientMultiShift: residual is NaN");
+    bs[0] = b;
+    for (int s = 1; s < nshift; s++) if (!converged[s]) {   // toggle the recurrence history (ref :246-256)
+      const double z0 = z1v[s], z1 = z0v[s];                // after the toggle: z0 = previous "current", z1 = the one before
+      const double znew = z0 * z1 * bp / (b * a * (z1 - z0) + z1 * bp * (1 - (mass[s] - mass[0]) * b));
+      z0v[s] = z0; z1v[s] = znew;
+      bs[s] = b * znew / z0;
+    }
+    if (unfused) {
+      for (int s = 0; s < nshift; s++) if (!converged[s]) chk(gb_axpy(psi[s], -bs[s] * alpha[s], ps[s], psi[s]));
+    } else {
+      MsEntries e; e.n = 0;
+      for (int s = 0; s < nshift; s++) if (!converged[s]) {
+        e.y[e.n] = psi[s]->data; e.x[e.n] = ps[s]->data; e.a[e.n] = -bs[s] * alpha[s]; e.b[e.n] = 0; e.plain[e.n] = 0;
+        if (++e.n == MS_MAX) { ms_update<1>(ctx, e, nullptr, src); e.n = 0; }
+      }
+      ms_update<1>(ctx, e, nullptr, src);
+    }
+    bool all_converged = true;
+    for (int s = 0; s < nshift; s++) if (!converged[s]) {
+      R.iters[s] = k;
+      const double zc = s == 0 ? 1.0 : z1v[s];
+      if (c * zc * zc < rsq[s]) converged[s] = 1; else all_converged = false;
+    }
+    if (all_converged) {   // check the answers (ref :296-306)
+      double cn;
+      chk(gb_norm2(src, &cn));
+      for (int s = 0; s < nshift; s++) {
+        A(psi[s], mmp);
+        chk(gb_axpy(tmp, mass[s], psi[s], mmp));
+        chk(gb_axpy_norm(r, -alpha[s], src, tmp, &rn));
+        R.true_resid[s] = std::sqrt(rn / cn);
+      }
+      R.iters_to_complete = k; R.converged = true;
+      return R;
+    }
+  }
+  R.iters_to_complete = maxit; R.converged = false;
+  return R;
+}
+
 } // namespace gb
 
 using namespace gb;
 
 extern "C" {
+
+int gb_cg_multishift_schur(gb_fermop *op, const gb_fermion *src, int nshift, const double *poles, const double *tolerances, int maxit,
+                           gb_fermion *const *results, int *iters_out, double *true_resid_out) {
+  GB_API_BEGIN
+  GB_REQUIRE(op && src && poles && tolerances && results, "null argument");
+  GB_REQUIRE(src->kind == GB_HALF, "ConjugateGradientMultiShift on the Schur operator works on red-black fields");
+  MSOut o = multishift_core(op->ctx, [&](const gb_fermion *in, gb_fermion *out) { op_apply(op, GB_OP_HERMOP, in, out, 0); }, src, results, nshift,
+                            poles, tolerances, maxit);
+  for (int s = 0; s < nshift; s++) { if (iters_out) iters_out[s] = o.iters[s]; if (true_resid_out) true_resid_out[s] = o.true_resid[s]; }
+  if (iters_out) iters_out[nshift] = o.iters_to_complete;
+  if (!o.converged) throw Error(GB_ERR_NOT_CONVERGED, "CG multi shift did not converge");
+  GB_API_END
+}
 
 int gb_cg_schur(gb_fermop *op, const gb_fermion *src, gb_fermion *sol, double tol, int maxit, int *iters_out, double *true_resid_out) {
   GB_API_BEGIN

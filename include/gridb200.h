@@ -227,6 +227,16 @@ int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d,
                       int max_outer, int iters_out[3], double *true_resid_out);
 
 
+/* ConjugateGradientMultiShift on SchurDiagMooeeOperator(op).HermOp (staggered: SchurStaggeredOperator), SURVEY 8 row f3:
+ * (HermOp + poles[s]) results[s] = src for s < nshift from one Krylov space; zero guess; poles[0] must be the lightest;
+ * shift s stops when its residual estimate drops below tolerances[s] |src|.
+ * ref: Grid/algorithms/iterative/ConjugateGradientMultiShift.h:84-343 ; shifts = MultiShiftFunction{poles, tolerances},
+ * Grid/algorithms/approx/MultiShiftFunction.h:34-44.  iters_out[nshift + 1] = {IterationsToCompleteShift..., IterationsToComplete},
+ * true_resid_out[nshift] = TrueResidualShift.  Returns GB_ERR_NOT_CONVERGED when MaxIterations is reached (the reference
+ * only logs that case, :336-338; the results hold the iterate reached). */
+int gb_cg_multishift_schur(gb_fermop *op, const gb_fermion *src, int nshift, const double *poles, const double *tolerances, int maxit,
+                           gb_fermion *const *results, int *iters_out, double *true_resid_out);
+
 /* SchurRedBlackDiagMooeeSolve (Wilson-type operators) / SchurRedBlackStaggeredSolve (staggered): the full-lattice solve
  * M sol = src through the even-odd Schur decomposition.  ref: Grid/algorithms/iterative/SchurRedBlack.h:238-290,294-349,385-430
  *   RedBlackSource:   src_e = src|Even ; src_o = MpcDag (src|Odd - Meooe MooeeInv src_e)   (staggered: Mooee in place of MpcDag)

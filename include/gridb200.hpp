@@ -72,7 +72,7 @@ public:
   gb_fermion *h = nullptr;
   GridBase *_grid;
   bool _staggered = false;   // true: one ColourVector per site (LatticeStaggeredFermion), false: SpinColourVector
-  explicit LatticeFermionT(GridBase *g) : _grid(g) { create(); }
+  LatticeFermionT(GridBase *g) : _grid(g) { create(); }   // not explicit: std::vector<Field> v(n, grid) as in the reference's drivers
   LatticeFermionT(const LatticeFermionT &o) : _grid(o._grid), _staggered(o._staggered) { create(); GB_ASSERT_OK(gb_copy(h, o.h)); }
   LatticeFermionT &operator=(const LatticeFermionT &o) { GB_ASSERT_OK(gb_copy(h, o.h)); return *this; }
   ~LatticeFermionT() { gb_fermion_destroy(h); }
@@ -97,7 +97,7 @@ typedef LatticeFermionT<GB_F64> LatticeFermionD;
 // below takes it through its base class
 template <gb_precision Prec> class LatticeStaggeredFermionT : public LatticeFermionT<Prec> {
 public:
-  explicit LatticeStaggeredFermionT(GridBase *g) : LatticeFermionT<Prec>(g, true) {}
+  LatticeStaggeredFermionT(GridBase *g) : LatticeFermionT<Prec>(g, true) {}
 };
 typedef LatticeStaggeredFermionT<GB_F32> LatticeStaggeredFermionF;
 typedef LatticeStaggeredFermionT<GB_F64> LatticeStaggeredFermionD;
@@ -314,6 +314,47 @@ public:
   }
 };
 
+
+// ---- ConjugateGradientMultiShift (ref: Grid/algorithms/approx/MultiShiftFunction.h:34-44 ; iterative/ConjugateGradientMultiShift.h:40-343)
+class MultiShiftFunction {
+public:
+  int order = 0;
+  std::vector<RealD> poles, residues, tolerances;
+  RealD norm = 0, lo = 0, hi = 0;
+  MultiShiftFunction() {}
+  MultiShiftFunction(int n, RealD _lo, RealD _hi) : order(n), poles(n), residues(n), tolerances(n), lo(_lo), hi(_hi) {}
+  RealD approx(RealD x) { RealD a = norm; for (size_t n = 0; n < poles.size(); n++) a += residues[n] / (x + poles[n]); return a; }
+};
+template <class Field> class ConjugateGradientMultiShift {
+public:
+  Integer MaxIterations;
+  Integer IterationsToComplete = 0;
+  std::vector<int> IterationsToCompleteShift;
+  MultiShiftFunction shifts;
+  std::vector<RealD> TrueResidualShift;
+  ConjugateGradientMultiShift(Integer maxit, const MultiShiftFunction &_shifts) : MaxIterations(maxit), shifts(_shifts) {
+    IterationsToCompleteShift.resize(_shifts.order); TrueResidualShift.resize(_shifts.order);
+  }
+  void operator()(LinearOperatorBase<Field> &Linop, const Field &src, std::vector<Field> &psi) {
+    gb_fermop *m = Linop.FusedSchurMatrix();
+    assert(m && "ConjugateGradientMultiShift needs a SchurDiagMooeeOperator / SchurStaggeredOperator");
+    const int n = shifts.order;
+    assert((int)psi.size() == n);
+    std::vector<gb_fermion *> hs(n);
+    for (int i = 0; i < n; i++) hs[i] = psi[i].h;
+    std::vector<int> it(n + 1);
+    int rc = gb_cg_multishift_schur(m, src.h, n, shifts.poles.data(), shifts.tolerances.data(), MaxIterations, hs.data(), it.data(), TrueResidualShift.data());
+    for (int i = 0; i < n; i++) IterationsToCompleteShift[i] = it[i];
+    IterationsToComplete = it[n];
+    if (rc == GB_ERR_NOT_CONVERGED) { std::fprintf(stderr, "CG multi shift did not converge\n"); return; }   // ref :336-338
+    GB_ASSERT_OK(rc);
+  }
+  void operator()(LinearOperatorBase<Field> &Linop, const Field &src, std::vector<Field> &results, Field &psi) {   // ref :69-82
+    (*this)(Linop, src, results);
+    GB_ASSERT_OK(gb_scale(psi.h, shifts.norm, src.h));
+    for (int i = 0; i < shifts.order; i++) axpy(psi, shifts.residues[i], results[i], psi);
+  }
+};
 
 // ---- SchurRedBlackDiagMooeeSolve / SchurRedBlackStaggeredSolve (ref: Grid/algorithms/iterative/SchurRedBlack.h:96-290,294-349,385-430)
 //   SchurRedBlackDiagMooeeSolve<LatticeFermion> SchurSolver(CG);  SchurSolver(Ddwf, src, result);   solves M result = src

@@ -490,6 +490,7 @@ template <class T> struct FermOp {
   CayleyCoeffs k;      // Cayley only
   std::vector<ColourMatrix<T>> Uds; // [V4][8], -1/2 and phases folded in
 
+  T mass_word() const { return (T)mass; }   // the working-precision type, for generic callers
   int64_t V5() const { return g.V4() * g.Ls; }
   int64_t V5cb() const { return g.V4cb() * g.Ls; }
   using F = Spinor<T>;

@@ -39,6 +39,8 @@ struct BoxBase {
   virtual void redblack_source(const void *src, void *src_e, void *src_o) = 0;
   virtual void redblack_solution(const void *sol_o, const void *src_e, void *sol) = 0;
   virtual void schur_solve(const void *src, void *sol, double tol, int maxit, int *iters, double *resid) = 0;
+  // ConjugateGradientMultiShift on the Schur operator of checkerboard cb
+  virtual void multishift(int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results, int *iters, double *tr) = 0;
 };
 
 template <class Field> void import_lex(Field &f, const void *host) {
@@ -88,6 +90,30 @@ void rb_solve(Matrix &M, GridBase *fg, const void *src, void *sol, double tol, i
   M.M(x, r); r = r - f;
   resid[1] = std::sqrt(norm2(r) / norm2(f));
   export_lex(x, sol);
+}
+
+// ConjugateGradientMultiShift<Field>(maxit, MultiShiftFunction{poles, tolerances})(Linop, src, results)
+// iters: [per-shift IterationsToCompleteShift..., IterationsToComplete, converged]
+template <class Field, class Linop>
+void ms_solve(Linop &S, GridBase *rbg, int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results, int *iters, double *tr) {
+  typedef typename Field::vector_object::scalar_object sobj;
+  MultiShiftFunction shifts(nshift, 0.0, 1.0);
+  shifts.order = nshift; shifts.norm = 0.0;
+  for (int s = 0; s < nshift; s++) { shifts.poles[s] = poles[s]; shifts.tolerances[s] = tols[s]; shifts.residues[s] = 1.0; }
+  ConjugateGradientMultiShift<Field> MSCG(maxit, shifts);
+  MSCG.IterationsToComplete = -1;
+  Field s(rbg);
+  import_lex(s, src);
+  s.Checkerboard() = cb;
+  std::vector<Field> res(nshift, rbg);
+  for (auto &f : res) f.Checkerboard() = cb;
+  MSCG(S, s, res);
+  const size_t n = rbg->lSites();
+  for (int i = 0; i < nshift; i++) {
+    export_lex(res[i], (char *)results + (size_t)i * n * sizeof(sobj));
+    iters[i] = MSCG.IterationsToCompleteShift[i]; tr[i] = MSCG.TrueResidualShift[i];
+  }
+  iters[nshift] = MSCG.IterationsToComplete; iters[nshift + 1] = MSCG.IterationsToComplete >= 0;
 }
 
 // Simd tag -> grids
@@ -207,6 +233,10 @@ template <class Impl, class vComplexT> struct WilsonBox : BoxBase {
   void schur_solve(const void *src, void *sol, double tol, int maxit, int *iters, double *resid) override {
     rb_solve<RBSolver, OpBase, FermionField>(*op, fgrid(), src, sol, tol, maxit, iters, resid);
   }
+  void multishift(int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results, int *iters, double *tr) override {
+    SchurDiagMooeeOperator<OpBase, FermionField> S(*op);
+    ms_solve<FermionField>(S, frbgrid(), cb, src, nshift, poles, tols, maxit, results, iters, tr);
+  }
 };
 
 // ---- improved staggered (fat = thin = the imported links, as Benchmark_staggered.cc:92-96 does)
@@ -274,6 +304,10 @@ template <class Impl, class vComplexT> struct StagBox : BoxBase {
   void schur_solve(const void *src, void *sol, double tol, int maxit, int *iters, double *resid) override {
     rb_solve<RBSolver, Op, FermionField>(*op, G.UGrid, src, sol, tol, maxit, iters, resid);
   }
+  void multishift(int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results, int *iters, double *tr) override {
+    SchurStaggeredOperator<Op, FermionField> S(*op);
+    ms_solve<FermionField>(S, G.UrbGrid, cb, src, nshift, poles, tols, maxit, results, iters, tr);
+  }
 };
 
 } // namespace
@@ -334,6 +368,12 @@ void gref_redblack_solution(void *h, const void *sol_o, const void *src_e, void 
 // out_iters: [iterations, converged]; out_resid: [CG TrueResidual, |M sol - src| / |src|]
 void gref_schur_solve(void *h, const void *src, void *sol, double tol, int maxit, int *out_iters, double *out_resid) {
   ((BoxBase *)h)->schur_solve(src, sol, tol, maxit, out_iters, out_resid);
+}
+
+// ConjugateGradientMultiShift as tests/solver/Test_staggered_multishift.cc:98-107 drives it, with explicit poles / tolerances
+void gref_multishift_cg(void *h, int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results,
+                        int *out_iters, double *out_true_resid) {
+  ((BoxBase *)h)->multishift(cb, src, nshift, poles, tols, maxit, results, out_iters, out_true_resid);
 }
 
 // MixedPrecisionConjugateGradient exactly as tests/Test_dwf_mixedcg_prec.cc:113-196 sets it up.

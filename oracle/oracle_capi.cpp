@@ -3,6 +3,8 @@
 // The product library (grid_b200/libgridb200.so) never links or dlopens this file.
 #include "dirac_oracle.hpp"
 #include "stag_oracle.hpp"
+#include "solvers_oracle.hpp"
+#include <array>
 #include <chrono>
 #include <omp.h>
 
@@ -266,6 +268,31 @@ void orc_set_checkerboard_bytes(const int *L, int site_bytes, int cb, void *full
     if (Geometry::parity(x) != cb) continue;
     std::memcpy((char *)full + i4 * site_bytes, (const char *)half + g.cb4(x) * site_bytes, site_bytes);
   }
+}
+// ConjugateGradientMultiShift on the Schur operator of checkerboard cb (Wilson types: MpcDagMpc; staggered: Mpc).
+// results: nshift fields back to back.  out_iters: [nshift per-shift iterations..., IterationsToComplete, converged]
+void orc_multishift_cg(void *h, int staggered, int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit,
+                       void *results, int *out_iters, double *out_true_resid) {
+  std::vector<double> m(poles, poles + nshift), t(tols, tols + nshift);
+  MultiShiftResult R;
+  auto run = [&](auto &op, auto *srcp, auto *resp, int64_t n, auto A) {
+    using F = std::remove_const_t<std::remove_pointer_t<decltype(resp)>>;
+    using T = std::remove_reference_t<decltype(op.mass_word())>;
+    std::vector<F *> psi(nshift);
+    for (int s = 0; s < nshift; s++) psi[s] = resp + (size_t)s * n;
+    R = MultiShiftCG<T, F>(A, n, srcp, psi, m, t, maxit);
+  };
+  if (staggered) {
+    StagBox *b = (StagBox *)h;
+    if (b->prec == 0) run(b->f, (const ColourVector<float> *)src, (ColourVector<float> *)results, b->f.g.V4cb(), [&](const ColourVector<float> *i, ColourVector<float> *o) { b->f.Mpc(i, o, cb); });
+    else run(b->d, (const ColourVector<double> *)src, (ColourVector<double> *)results, b->d.g.V4cb(), [&](const ColourVector<double> *i, ColourVector<double> *o) { b->d.Mpc(i, o, cb); });
+  } else {
+    OpBox *b = (OpBox *)h;
+    if (b->prec == 0) run(b->f, (const Spinor<float> *)src, (Spinor<float> *)results, b->f.V5cb(), [&](const Spinor<float> *i, Spinor<float> *o) { b->f.HermOp(i, o, cb); });
+    else run(b->d, (const Spinor<double> *)src, (Spinor<double> *)results, b->d.V5cb(), [&](const Spinor<double> *i, Spinor<double> *o) { b->d.HermOp(i, o, cb); });
+  }
+  for (int s = 0; s < nshift; s++) { out_iters[s] = R.iterations[s]; out_true_resid[s] = R.true_residual[s]; }
+  out_iters[nshift] = R.iterations_to_complete; out_iters[nshift + 1] = R.converged;
 }
 double orc_stag_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
   auto t0 = std::chrono::steady_clock::now();

@@ -42,6 +42,7 @@ def lib():
         L.orc_pick_checkerboard.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_set_checkerboard.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_inner_product.argtypes = [C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_multishift_cg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_physical.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_physical.restype = C.c_int
         L.orc_redblack_source.argtypes = [C.c_void_p] * 4
@@ -143,6 +144,18 @@ class OracleOp:
         lib().orc_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
         return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
 
+    def multishift_cg(self, cb, src, poles, tols, maxit):
+        """ConjugateGradientMultiShift on the Schur operator of checkerboard cb: (A + poles[s]) x_s = src.
+        Returns ([nshift, nsite, ...] solutions, dict(iterations=[...], true_residual=[...], iterations_to_complete, converged))."""
+        src = np.ascontiguousarray(src, dtype=_cdtype(self.prec))
+        poles = np.ascontiguousarray(poles, dtype=np.float64); tols = np.ascontiguousarray(tols, dtype=np.float64)
+        n = len(poles)
+        res = np.zeros((n,) + src.shape, dtype=src.dtype)
+        it = np.zeros(n + 2, dtype=np.int32)
+        tr = np.zeros(n, dtype=np.float64)
+        lib().orc_multishift_cg(self.h, 0, cb, _ptr(src), n, _ptr(poles), _ptr(tols), maxit, _ptr(res), _ptr(it), _ptr(tr))
+        return res, dict(iterations=[int(x) for x in it[:n]], true_residual=[float(x) for x in tr], iterations_to_complete=int(it[n]), converged=int(it[n + 1]))
+
     # ---- SURVEY 8 row f1: physical 4D <-> 5D maps, SchurRedBlackDiagMooeeSolve
     def physical(self, which, x):
         """which = IMPORT_PHYSICAL_SOURCE / IMPORT_UNPHYSICAL (x: [V4,4,3] -> [V4*Ls,4,3]) or EXPORT_PHYSICAL_SOLUTION /
@@ -222,6 +235,18 @@ class StagOracleOp:
         tr = np.zeros(1, dtype=np.float64)
         lib().orc_stag_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
         return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
+
+    def multishift_cg(self, cb, src, poles, tols, maxit):
+        """ConjugateGradientMultiShift on the Schur operator of checkerboard cb: (A + poles[s]) x_s = src.
+        Returns ([nshift, nsite, ...] solutions, dict(iterations=[...], true_residual=[...], iterations_to_complete, converged))."""
+        src = np.ascontiguousarray(src, dtype=_cdtype(self.prec))
+        poles = np.ascontiguousarray(poles, dtype=np.float64); tols = np.ascontiguousarray(tols, dtype=np.float64)
+        n = len(poles)
+        res = np.zeros((n,) + src.shape, dtype=src.dtype)
+        it = np.zeros(n + 2, dtype=np.int32)
+        tr = np.zeros(n, dtype=np.float64)
+        lib().orc_multishift_cg(self.h, 1, cb, _ptr(src), n, _ptr(poles), _ptr(tols), maxit, _ptr(res), _ptr(it), _ptr(tr))
+        return res, dict(iterations=[int(x) for x in it[:n]], true_residual=[float(x) for x in tr], iterations_to_complete=int(it[n]), converged=int(it[n + 1]))
 
     # ---- SchurRedBlackStaggeredSolve (ref: SchurRedBlack.h:294-349)
     def redblack_source(self, src):

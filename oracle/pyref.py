@@ -43,6 +43,7 @@ def lib():
         L.gref_apply.restype = C.c_int
         L.gref_pick_checkerboard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_set_checkerboard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_multishift_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gref_physical.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_physical.restype = C.c_int
         L.gref_redblack_source.argtypes = [C.c_void_p] * 4
@@ -148,6 +149,18 @@ class RefOp:
         tr = np.zeros(1, dtype=np.float64)
         lib().gref_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
         return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
+
+    def multishift_cg(self, cb, src, poles, tols, maxit):
+        """ConjugateGradientMultiShift on the Schur operator of checkerboard cb: (A + poles[s]) x_s = src.
+        Returns ([nshift, nsite, ...] solutions, dict(iterations=[...], true_residual=[...], iterations_to_complete, converged))."""
+        src = np.ascontiguousarray(src, dtype=_cdtype(self.prec))
+        poles = np.ascontiguousarray(poles, dtype=np.float64); tols = np.ascontiguousarray(tols, dtype=np.float64)
+        n = len(poles)
+        res = np.zeros((n,) + src.shape, dtype=src.dtype)
+        it = np.zeros(n + 2, dtype=np.int32)
+        tr = np.zeros(n, dtype=np.float64)
+        lib().gref_multishift_cg(self.h, cb, _ptr(src), n, _ptr(poles), _ptr(tols), maxit, _ptr(res), _ptr(it), _ptr(tr))
+        return res, dict(iterations=[int(x) for x in it[:n]], true_residual=[float(x) for x in tr], iterations_to_complete=int(it[n]), converged=int(it[n + 1]))
 
     # ---- SURVEY 8 row f1: physical 4D <-> 5D maps, SchurRedBlackDiagMooeeSolve
     def physical(self, which, x):

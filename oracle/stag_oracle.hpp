@@ -54,6 +54,7 @@ template <class T> struct StagOp {
   Geometry g;
   double mass = 0, c1 = 1, c2 = 1, u0 = 1;
   std::vector<ColourMatrix<T>> Uds, UUUds; // [V4][8]
+  T mass_word() const { return (T)mass; }   // the working-precision type, for generic callers
 
   int64_t shifted(const int x[4], int mu, int d) const {
     int y[4] = {x[0], x[1], x[2], x[3]};

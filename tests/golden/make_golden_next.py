@@ -11,6 +11,11 @@ Row f1 (full propagator solve, ref: SchurRedBlack.h:238-290,385-430 ; CayleyFerm
   <op>/rb_source/{e,o}, <op>/rb_solution                 SchurRedBlack*Solve::RedBlackSource(src) ; RedBlackSolution(pick(Odd,src), e)
   <op>/schur_solve/{solution,iterations,true_residual,unprec_residual}   SchurRedBlack*Solve(ConjugateGradient(1e-8))(M, src, sol)
 for op in wilson, dwf, mobius (b=1.5,c=0.5), stag.
+
+Row f3 (ConjugateGradientMultiShift, ref: Grid/algorithms/iterative/ConjugateGradientMultiShift.h:84-343) on the Odd checkerboard of
+the same sources, poles MS_POLES, tolerances MS_TOLS:
+  <op>/multishift/{solutions [nshift, nsite_cb, ...], iterations [nshift], true_residual [nshift], iterations_to_complete}
+for op in mobius, stag.
 """
 import os
 import sys
@@ -22,13 +27,14 @@ sys.path.insert(0, ROOT)
 from oracle import pyref as pr                  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+MS_POLES, MS_TOLS = [0.01, 0.05, 0.3, 1.0], [1e-8, 1e-8, 1e-7, 1e-6]
 
 
 def main():
     G = np.load(os.path.join(HERE, "dirac_golden.npz"))
     DIMS, LS = tuple(int(x) for x in G["dims"]), int(G["Ls"])
     U, src4, src5, srcs = G["U"], G["src4"], G["src5"], G["src_stag"]
-    out = {}
+    out = {"ms_poles": np.array(MS_POLES), "ms_tols": np.array(MS_TOLS)}
     ops = {
         "wilson": (pr.RefOp(0, DIMS, 1, 0.1, prec=1), src4),
         "dwf": (pr.RefOp(1, DIMS, LS, 0.1, 1.8, 1.0, 0.0, prec=1), src5),
@@ -45,6 +51,11 @@ def main():
             e, o = op.redblack_source(src)
             out[f"{name}/rb_source/e"], out[f"{name}/rb_source/o"] = e, o
             out[f"{name}/rb_solution"] = op.redblack_solution(op.pick_checkerboard(1, src), e)
+        if name in ("mobius", "stag"):
+            xs, info = op.multishift_cg(1, op.pick_checkerboard(1, src), MS_POLES, MS_TOLS, 5000)
+            out[f"{name}/multishift/solutions"] = xs
+            for k in ("iterations", "true_residual", "iterations_to_complete"):
+                out[f"{name}/multishift/{k}"] = np.array(info[k])
         x, info = op.schur_solve(src, 1e-8, 5000)
         out[f"{name}/schur_solve/solution"] = x
         for k in ("iterations", "true_residual", "unprec_residual"):
