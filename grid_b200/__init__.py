@@ -54,6 +54,7 @@ SYMBOLS = [
     ("gb_op_dhop_host", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
+    ("gb_op_dhop_dir", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_dhop_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mderiv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_cg_multishift_schur", _i, [_vp, _vp, _i, _pd, _pd, _i, _pvp, _pi, _pd]),
     ("gb_op_import_physical_fermion_source", _i, [_vp, _vp, _vp]), ("gb_op_import_unphysical_fermion", _i, [_vp, _vp, _vp]),
     ("gb_op_export_physical_fermion_solution", _i, [_vp, _vp, _vp]), ("gb_op_export_physical_fermion_source", _i, [_vp, _vp, _vp]),
@@ -375,6 +376,11 @@ class FermionOperator:
     def ImportUnphysicalFermion(self, input4d, imported5d): _chk(lib().gb_op_import_unphysical_fermion(self.h, input4d.h, imported5d.h))
     def ExportPhysicalFermionSolution(self, solution5d, exported4d): _chk(lib().gb_op_export_physical_fermion_solution(self.h, solution5d.h, exported4d.h))
     def ExportPhysicalFermionSource(self, source5d, exported4d): _chk(lib().gb_op_export_physical_fermion_source(self.h, source5d.h, exported4d.h))
+
+    # single hop legs and force terms (ref: FermionOperator.h:79-93; dir = 0..3, disp = +-1; mat = LatticeGaugeField)
+    def DhopDir(self, i, o, dir, disp): _chk(lib().gb_op_dhop_dir(self.h, i.h, o.h, dir, disp))
+    def DhopDeriv(self, mat, U, V, dag): _chk(lib().gb_op_dhop_deriv(self.h, mat.h, U.h, V.h, dag))
+    def MDeriv(self, mat, U, V, dag): _chk(lib().gb_op_mderiv(self.h, mat.h, U.h, V.h, dag))
 
     def Dhop_host(self, host_in, host_out, dag=0):
         """Dhop on host-resident full-lattice arrays [V4*Ls,4,3] (lexicographic); pipelined H2D / hop / D2H on one rank."""

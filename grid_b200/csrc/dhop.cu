@@ -44,6 +44,7 @@ __device__ __forceinline__ void dhop_leg(const DhopArgs &a, const typename Prec<
   // non-dag: forward legs (x+mu) carry (1-gamma), backward legs (1+gamma); dag swaps.
   // ref: WilsonKernelsImplementation.h:127-134 (dag) vs :154-161
   constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
+  if (!((a.leg_mask >> (FWD ? MU : MU + 4)) & 1)) return;   // single-leg applications (DhopDir, force terms)
   const int Lmu = MU == 0 ? a.Lx : MU == 1 ? a.Ly : MU == 2 ? a.Lz : a.Lt;
   int coord;   // local coordinate along MU of the output site
   if (MU == 0) coord = 2 * c.xh + c.pb; else coord = MU == 1 ? c.y : MU == 2 ? c.z : c.t;
@@ -451,6 +452,7 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   a.mode = 0;
   a.box_on = 0;
   a.flags = nullptr; a.epoch = 0;
+  a.leg_mask = op->leg_mask;
 
   auto run = [&](int mode, cudaStream_t st) {
     if (op->prec == GB_F32) launch_dhop_T<float>(op, a, nparity, dag, mode, st);
@@ -632,6 +634,7 @@ void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int 
   for (int i = 0; i < 8; i++) a.halo[i] = nullptr;
   for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = 0;
   a.mode = 0; a.flags = nullptr; a.epoch = 0;
+  a.leg_mask = 0xFF;
   a.box_on = 1;
   a.bo[0] = 0; a.bo[1] = 0; a.bo[2] = 0; a.bo[3] = t0;
   a.be[0] = a.Lxh; a.be[1] = a.Ly; a.be[2] = a.Lz; a.be[3] = nt;

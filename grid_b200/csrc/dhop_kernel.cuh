@@ -40,6 +40,7 @@ struct DhopArgs {
   FastDiv dbe0, dbe1, dbe2;
   int first_parity;    // output parity handled by blockIdx.y == 0
   int origin_parity;
+  int leg_mask;        // bit (FWD ? mu : mu + 4) set: that leg contributes.  0xFF = the hopping term; one bit = DhopDir (generic kernel only)
 };
 
 // ------------------------------------------------------------------ register-resident site objects

@@ -41,6 +41,7 @@ struct gb_fermop {
   bool disable_fast = false;   // force the generic kernel (tests compare the two)
   bool no_col = false;         // fp32: use the micro-block kernel instead of the column-sweep kernel (tests compare them)
   int col_n = 0;               // z-planes per column of the column-sweep kernel (0 = default 16)
+  int leg_mask = 0xFF;         // legs of the hopping term that contribute (0xFF always, except inside op_dhop_leg: DhopDir / force terms)
   // multi-GPU: the single-launch pack+hop+halo kernel is EXPERIMENTAL (opt-in with GB_FUSED=1).  It is parity-green on small
   // lattices but can deadlock at 32^4 per GPU: surface CTAs spinning on the neighbours' flags can fill every resident slot
   // before the last pack CTAs of the same launch are scheduled.  Default = pack+send kernel, interior pass, exterior slabs.
@@ -99,6 +100,8 @@ bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *
 void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st);
 // improved staggered operator entry points (stag.cu)
 void stag_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
+// one leg of the hopping term on full-grid fields: point 0..3 forward mu, 4..7 backward mu (force.cu)
+void op_dhop_leg(gb_fermop *op, const gb_fermion *in, gb_fermion *out, int point, int dag);
 // composite operator pieces used by the solvers
 void op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
 gb_fermion *op_tmp_half(gb_fermop *op, int i);

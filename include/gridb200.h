@@ -211,6 +211,19 @@ int gb_op_import_unphysical_fermion(gb_fermop *op, const gb_fermion *in4d, gb_fe
 int gb_op_export_physical_fermion_solution(gb_fermop *op, const gb_fermion *sol5d, gb_fermion *out4d);
 int gb_op_export_physical_fermion_source(gb_fermop *op, const gb_fermion *src5d, gb_fermion *out4d);
 
+/* Single hop legs and force terms on full-grid fields (Wilson-type operators).
+ *   DhopDir(in, out, dir, disp): the leg of the hopping term that reads x + disp * dir, dir = 0..3 (x,y,z,t), disp = +-1, with the
+ *     hopping term's own -1/2, boundary phases and halo exchange: summed over the eight legs it IS Dhop(in, out, DaggerNo).
+ *     ref: WilsonFermion5DImplementation.h:183-200 (there dir5 = dir + 1), WilsonFermionImplementation.h:344-360
+ *   DhopDeriv(mat, A, B, dag): mat_mu(x) = sum_s trace_spin [ Btilde_mu(x,s) A(x,s)^dagger ], Btilde_mu = forward leg mu of
+ *     Dhop^(dag) applied to B; mat is a LatticeGaugeField [V4][4][3][3] (every entry overwritten).
+ *     ref: WilsonFermion5DImplementation.h:212-275, WilsonImpl.h:173-238 (InsertForce4D/5D)
+ *   MDeriv(mat, U, V, dag): Cayley operators apply Meooe5D to V (dag: to U) first; others = DhopDeriv.
+ *     ref: CayleyFermion5DImplementation.h:347-360 ; driver tests/forces/Test_dwf_force.cc:71-75 */
+int gb_op_dhop_dir(gb_fermop *op, const gb_fermion *in, gb_fermion *out, int dir, int disp);
+int gb_op_dhop_deriv(gb_fermop *op, gb_gauge *mat, const gb_fermion *A, const gb_fermion *B, int dag);
+int gb_op_mderiv(gb_fermop *op, gb_gauge *mat, const gb_fermion *U, const gb_fermion *V, int dag);
+
 /* ---------------------------------------------------------------- solvers
  * ConjugateGradient on SchurDiagMooeeOperator(op).HermOp, fused device path.
  * ref: Grid/algorithms/iterative/ConjugateGradient.h:68-257.  sol is the initial guess on entry.

@@ -171,6 +171,10 @@ public:
   virtual void ImportUnphysicalFermion(const FermionField &input4d, FermionField &imported5d) { GB_ASSERT_OK(gb_op_import_unphysical_fermion(h, input4d.h, imported5d.h)); }
   virtual void ExportPhysicalFermionSolution(const FermionField &solution5d, FermionField &exported4d) { GB_ASSERT_OK(gb_op_export_physical_fermion_solution(h, solution5d.h, exported4d.h)); }
   virtual void ExportPhysicalFermionSource(const FermionField &solution5d, FermionField &exported4d) { GB_ASSERT_OK(gb_op_export_physical_fermion_source(h, solution5d.h, exported4d.h)); }
+  // single hop legs and force terms on full-grid fields (ref: FermionOperator.h:79-93): dir = 0..3, disp = +-1
+  virtual void DhopDir(const FermionField &in, FermionField &out, int dir, int disp) { GB_ASSERT_OK(gb_op_dhop_dir(h, in.h, out.h, dir, disp)); }
+  virtual void DhopDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { GB_ASSERT_OK(gb_op_dhop_deriv(h, mat.h, U.h, V.h, dag)); }
+  virtual void MDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { GB_ASSERT_OK(gb_op_mderiv(h, mat.h, U.h, V.h, dag)); }
   // Dhop on host-resident full-lattice arrays in the reference's unvectorised layout (pipelined H2D / hop / D2H on one rank)
   void DhopHost(const void *host_in, void *host_out, gb_precision host_prec, int dag) { GB_ASSERT_OK(gb_op_dhop_host(h, host_in, host_out, host_prec, dag)); }
 };

@@ -607,6 +607,58 @@ template <class T> struct FermOp {
   void HermOp(const F *in, F *out, int cb) const { // MpcDagMpc, ref: LinearOperator.h:291-307
     Vec tmp(V5cb()); Mpc(in, tmp.data(), cb); MpcDag(tmp.data(), out, cb);
   }
+  // ---- single hop legs and force terms
+  // One leg of the hopping term on the full lattice.  point 0..3 = forward leg mu (reads x+mu, link U_mu(x)), 4..7 = backward
+  // leg mu; projector as in dhopSite (non-dag: forward legs carry (1-gamma), backward (1+gamma); dag swaps).
+  // ref: WilsonKernelsImplementation.h:375-412 (DhopDirKernel), :57-68 (leg)
+  void DhopLeg(const F *in, F *out, int point, int dag) const {
+    const int Ls = g.Ls, mu = point & 3, fwd = point < 4;
+    const int sgn = (fwd ? -1 : +1) * (dag ? -1 : +1);
+#pragma omp parallel for
+    for (int64_t i4 = 0; i4 < g.V4(); i4++) {
+      int x[4]; g.coor4(i4, x);
+      int y[4] = {x[0], x[1], x[2], x[3]};
+      y[mu] = fwd ? (x[mu] + 1) % g.L[mu] : (x[mu] + g.L[mu] - 1) % g.L[mu];
+      const int64_t nb = g.lex4(y);
+      for (int s = 0; s < Ls; s++) {
+        HalfSpinor<T> chi, Uchi;
+        Spinor<T> r; zero(r);
+        spProj(chi, in[nb * Ls + s], mu, sgn);
+        multLink(Uchi, Uds[i4 * 8 + point], chi);
+        accumRecon(r, Uchi, mu, sgn);
+        out[i4 * Ls + s] = r;
+      }
+    }
+  }
+  // DhopDir(in, out, dir, disp = +-1): that leg of the non-dagger hop   ref: WilsonFermion5DImplementation.h:183-200
+  void DhopDir(const F *in, F *out, int dir, int disp) const { DhopLeg(in, out, disp == 1 ? dir : dir + 4, 0); }
+  // DhopDeriv: mat_mu(x) = sum_s trace_spin [ Btilde_mu(x,s) (x) A(x,s)^dagger ], Btilde_mu = forward leg mu of Dhop^(dag) on B
+  // ref: WilsonFermion5DImplementation.h:212-262 (DerivInternal), WilsonImpl.h:193-238 (InsertForce5D),
+  //      Grid/tensors/Tensor_outer.h (outerProduct(l, r) = l conj(r))
+  void DhopDeriv(ColourMatrix<T> *mat /* [V4][4] */, const F *A, const F *B, int dag) const {
+    const int Ls = g.Ls;
+    Vec Btilde(V5());
+    for (int mu = 0; mu < 4; mu++) {
+      DhopLeg(B, Btilde.data(), mu, dag);
+#pragma omp parallel for
+      for (int64_t i4 = 0; i4 < g.V4(); i4++) {
+        ColourMatrix<T> m; std::memset((void *)&m, 0, sizeof(m));
+        for (int s = 0; s < Ls; s++) {
+          const F &b = Btilde[i4 * Ls + s], &a = A[i4 * Ls + s];
+          for (int sp = 0; sp < Ns; sp++) for (int c1 = 0; c1 < Nc; c1++) for (int c2 = 0; c2 < Nc; c2++) m.m[c1][c2] += b.v[sp][c1] * conj(a.v[sp][c2]);
+        }
+        mat[i4 * 4 + mu] = m;
+      }
+    }
+  }
+  // MDeriv(mat, U, V, dag): d/dU of U^dagger M V (dag: U^dagger M^dagger V); the 5D factor is applied to the side it acts on
+  // ref: CayleyFermion5DImplementation.h:347-360 ; WilsonFermion: MDeriv = DhopDeriv (FermionOperator default)
+  void MDeriv(ColourMatrix<T> *mat, const F *U, const F *V, int dag) const {
+    if (kind == OpKind::Wilson4D) { DhopDeriv(mat, U, V, dag); return; }
+    Vec Din(V5());
+    if (!dag) { Meooe5D(g.V4(), V, Din.data()); DhopDeriv(mat, U, Din.data(), dag); }
+    else { Meooe5D(g.V4(), U, Din.data()); DhopDeriv(mat, Din.data(), V, dag); }
+  }
   // ---- physical 4D <-> 5D maps.  4D fields have V4 sites, 5D fields V4*Ls (s fastest).
   // Wilson4D: every map is the identity (ref: FermionOperator.h:172-191).
   // Dminus: chi_s = psi_s - cs[s] DW(psi)_s ; DminusDag uses DW^dag   ref: CayleyFermion5DImplementation.h:132-153

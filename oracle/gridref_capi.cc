@@ -39,6 +39,9 @@ struct BoxBase {
   virtual void redblack_source(const void *src, void *src_e, void *src_o) = 0;
   virtual void redblack_solution(const void *sol_o, const void *src_e, void *sol) = 0;
   virtual void schur_solve(const void *src, void *sol, double tol, int maxit, int *iters, double *resid) = 0;
+  // DhopDir, DhopDeriv (which 0) / MDeriv (which 1) on the full grid; mat = LatticeGaugeField
+  virtual int dhop_dir(const void *in, void *out, int dir, int disp) { return -1; }
+  virtual int deriv(int which, void *mat, const void *U, const void *V, int dag) { return -1; }
   // ConjugateGradientMultiShift on the Schur operator of checkerboard cb
   virtual void multishift(int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results, int *iters, double *tr) = 0;
 };
@@ -227,6 +230,23 @@ template <class Impl, class vComplexT> struct WilsonBox : BoxBase {
     }
     return 0;
   }
+  int dhop_dir(const void *in, void *out, int dir, int disp) override {
+    FermionField x(fgrid()), y(fgrid());
+    import_lex(x, in);
+    // WilsonFermion counts directions 0..3, WilsonFermion5D 1..4 (the fifth dimension is 0): ref WilsonFermion5DImplementation.h:185
+    op->DhopDir(x, y, kind == KIND_WILSON ? dir : dir + 1, disp);
+    export_lex(y, out);
+    return 0;
+  }
+  int deriv(int which, void *mat, const void *U, const void *V, int dag) override {
+    FermionField u(fgrid()), v(fgrid());
+    import_lex(u, U); import_lex(v, V);
+    GaugeField m(G.UGrid);
+    m = Zero();
+    if (which == 0) op->DhopDeriv(m, u, v, dag); else op->MDeriv(m, u, v, dag);
+    export_lex(m, mat);
+    return 0;
+  }
   typedef SchurRedBlackDiagMooeeSolve<FermionField> RBSolver;
   void redblack_source(const void *src, void *src_e, void *src_o) override { rb_source<RBSolver, OpBase, FermionField>(*op, fgrid(), frbgrid(), src, src_e, src_o); }
   void redblack_solution(const void *sol_o, const void *src_e, void *sol) override { rb_solution<RBSolver, OpBase, FermionField>(*op, fgrid(), frbgrid(), sol_o, src_e, sol); }
@@ -370,6 +390,8 @@ void gref_schur_solve(void *h, const void *src, void *sol, double tol, int maxit
   ((BoxBase *)h)->schur_solve(src, sol, tol, maxit, out_iters, out_resid);
 }
 
+int gref_dhop_dir(void *h, const void *in, void *out, int dir, int disp) { return ((BoxBase *)h)->dhop_dir(in, out, dir, disp); }
+int gref_deriv(void *h, int which, void *mat, const void *U, const void *V, int dag) { return ((BoxBase *)h)->deriv(which, mat, U, V, dag); }
 // ConjugateGradientMultiShift as tests/solver/Test_staggered_multishift.cc:98-107 drives it, with explicit poles / tolerances
 void gref_multishift_cg(void *h, int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results,
                         int *out_iters, double *out_true_resid) {

@@ -149,6 +149,19 @@ int orc_physical(void *h, int which, const void *in, void *out) {
   OpBox *box = (OpBox *)h;
   return box->prec == 0 ? physicalT(box->f, which, in, out) : physicalT(box->d, which, in, out);
 }
+// SURVEY 8 row f2.  orc_dhop_dir: FermionOperator::DhopDir(in, out, dir, disp).  orc_deriv: which 0 = DhopDeriv, 1 = MDeriv;
+// mat is a LatticeGaugeField [V4][4][3][3] of the operator's precision.
+void orc_dhop_dir(void *h, const void *in, void *out, int dir, int disp) {
+  OpBox *box = (OpBox *)h;
+  if (box->prec == 0) box->f.DhopDir((const Spinor<float> *)in, (Spinor<float> *)out, dir, disp);
+  else box->d.DhopDir((const Spinor<double> *)in, (Spinor<double> *)out, dir, disp);
+}
+void orc_deriv(void *h, int which, void *mat, const void *U, const void *V, int dag) {
+  OpBox *box = (OpBox *)h;
+  auto run = [&](auto &op, auto *m, auto *u, auto *v) { if (which == 0) op.DhopDeriv(m, u, v, dag); else op.MDeriv(m, u, v, dag); };
+  if (box->prec == 0) run(box->f, (ColourMatrix<float> *)mat, (const Spinor<float> *)U, (const Spinor<float> *)V);
+  else run(box->d, (ColourMatrix<double> *)mat, (const Spinor<double> *)U, (const Spinor<double> *)V);
+}
 // SchurRedBlackDiagMooeeSolve pieces: full-lattice src -> (src_e, src_o') ; (sol_o, src_e) -> full-lattice sol
 void orc_redblack_source(void *h, const void *src, void *src_e, void *src_o) {
   OpBox *box = (OpBox *)h;

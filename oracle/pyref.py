@@ -44,6 +44,8 @@ def lib():
         L.gref_pick_checkerboard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_set_checkerboard.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_multishift_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gref_dhop_dir.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.gref_deriv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gref_physical.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_physical.restype = C.c_int
         L.gref_redblack_source.argtypes = [C.c_void_p] * 4
@@ -149,6 +151,21 @@ class RefOp:
         tr = np.zeros(1, dtype=np.float64)
         lib().gref_cg(self.h, cb, _ptr(src), _ptr(sol), tol, maxit, _ptr(it), _ptr(tr))
         return sol, dict(iterations=int(it[0]), converged=int(it[1]), true_residual=float(tr[0]))
+
+    # ---- single hop legs and force terms (full grid)
+    def dhop_dir(self, x, dir, disp):
+        """FermionOperator::DhopDir(in, out, dir, disp): the leg of the hopping term that reads x + disp * dir (dir = 0..3)."""
+        x = np.ascontiguousarray(x, dtype=_cdtype(self.prec))
+        out = np.empty_like(x)
+        lib().gref_dhop_dir(self.h, _ptr(x), _ptr(out), dir, disp)
+        return out
+
+    def deriv(self, which, U, V, dag=0):
+        """which = 0: DhopDeriv(mat, U, V, dag); 1: MDeriv(mat, U, V, dag).  Returns mat as [V4,4,3,3]."""
+        U = np.ascontiguousarray(U, dtype=_cdtype(self.prec)); V = np.ascontiguousarray(V, dtype=_cdtype(self.prec))
+        mat = np.zeros((self.V4, 4, 3, 3), dtype=U.dtype)
+        lib().gref_deriv(self.h, which, _ptr(mat), _ptr(U), _ptr(V), dag)
+        return mat
 
     def multishift_cg(self, cb, src, poles, tols, maxit):
         """ConjugateGradientMultiShift on the Schur operator of checkerboard cb: (A + poles[s]) x_s = src.

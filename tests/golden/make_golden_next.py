@@ -12,6 +12,10 @@ Row f1 (full propagator solve, ref: SchurRedBlack.h:238-290,385-430 ; CayleyFerm
   <op>/schur_solve/{solution,iterations,true_residual,unprec_residual}   SchurRedBlack*Solve(ConjugateGradient(1e-8))(M, src, sol)
 for op in wilson, dwf, mobius (b=1.5,c=0.5), stag.
 
+Row f2 (single hop legs and force terms, ref: WilsonFermion5DImplementation.h:183-275 ; CayleyFermion5DImplementation.h:347-360), A = src,
+B = the field stored as "src_b" (second random source):
+  mobius/dhop_dir/{dir}_{disp}  for (1,+1), (3,-1);   <op>/deriv/{which}_{dag}  which 0 DhopDeriv, 1 MDeriv, for op in wilson, mobius
+
 Row f3 (ConjugateGradientMultiShift, ref: Grid/algorithms/iterative/ConjugateGradientMultiShift.h:84-343) on the Odd checkerboard of
 the same sources, poles MS_POLES, tolerances MS_TOLS:
   <op>/multishift/{solutions [nshift, nsite_cb, ...], iterations [nshift], true_residual [nshift], iterations_to_complete}
@@ -51,6 +55,15 @@ def main():
             e, o = op.redblack_source(src)
             out[f"{name}/rb_source/e"], out[f"{name}/rb_source/o"] = e, o
             out[f"{name}/rb_solution"] = op.redblack_solution(op.pick_checkerboard(1, src), e)
+        if name in ("wilson", "mobius"):
+            from grid_b200 import synthetic as syn
+            srcb = syn.random_fermion(DIMS, op.Ls, seed=105)
+            out[f"{name}/src_b"] = srcb
+            if name == "mobius":
+                out["mobius/dhop_dir/1_1"], out["mobius/dhop_dir/3_-1"] = op.dhop_dir(src, 1, 1), op.dhop_dir(src, 3, -1)
+            for which in (0, 1):
+                for dag in (0, 1):
+                    out[f"{name}/deriv/{which}_{dag}"] = op.deriv(which, src, srcb, dag)
         if name in ("mobius", "stag"):
             xs, info = op.multishift_cg(1, op.pick_checkerboard(1, src), MS_POLES, MS_TOLS, 5000)
             out[f"{name}/multishift/solutions"] = xs

@@ -1,0 +1,151 @@
+"""SURVEY 8(f) row 2 -- single hop legs and the fermion force terms (full-grid): DhopDir, DhopDeriv, MDeriv
+(ref: WilsonFermion5DImplementation.h:183-275, WilsonImpl.h:173-238, CayleyFermion5DImplementation.h:347-360).
+
+ * CPU: the oracle reproduces the compiled reference's outputs (tests/golden/next_golden.npz; live on a second lattice where
+   oracle/_ref exists), the eight DhopDir legs sum to Dhop, and MDeriv predicts the change of S = |M phi|^2 under a small
+   change of the links -- the reference's own force test (tests/forces/Test_dwf_force.cc:60-141) restated.
+ * GPU: the CUDA path reproduces the fixtures (fp64 <= 2e-13, fp32 <= 4e-6) and the sum-of-legs identity.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from grid_b200 import synthetic as syn
+from oracle import pyoracle as po
+from oracle import pyref as pr
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+UNVERIFIED = pytest.mark.unverified("row f2 was written in round 1 after the GPU budget ran out")
+G = np.load(os.path.join(HERE, "golden", "dirac_golden.npz"))
+N = np.load(os.path.join(HERE, "golden", "next_golden.npz"))
+DIMS, LS = tuple(int(x) for x in G["dims"]), int(G["Ls"])
+OPS = {"wilson": dict(kind=0, Ls=1, b=1.0, c=0.0, src="src4"), "mobius": dict(kind=1, Ls=LS, b=1.5, c=0.5, src="src5")}
+
+
+def rel_err(a, b):
+    return float(np.max(np.abs(a.astype(np.complex128) - b)) / np.max(np.abs(b)))
+
+
+def oracle_op(name, prec=1, U=None, dims=DIMS):
+    cfg = OPS[name]
+    o = po.OracleOp(cfg["kind"], dims, cfg["Ls"], mass=0.1, M5=1.8, b=cfg["b"], c=cfg["c"], prec=prec)
+    o.import_gauge(G["U"] if U is None else U)
+    return o
+
+
+@pytest.mark.parametrize("name", ["wilson", "mobius"])
+def test_oracle_force_terms_match_reference_outputs(name):
+    o = oracle_op(name)
+    A, B = G[OPS[name]["src"]], N[f"{name}/src_b"]
+    for which in (0, 1):
+        for dag in (0, 1):
+            assert rel_err(o.deriv(which, A, B, dag), N[f"{name}/deriv/{which}_{dag}"]) < 1e-13, (which, dag)
+    if name == "mobius":
+        assert rel_err(o.dhop_dir(A, 1, 1), N["mobius/dhop_dir/1_1"]) < 1e-14
+        assert rel_err(o.dhop_dir(A, 3, -1), N["mobius/dhop_dir/3_-1"]) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["wilson", "mobius"])
+def test_oracle_eight_legs_sum_to_dhop(name):
+    o = oracle_op(name)
+    x = G[OPS[name]["src"]]
+    total = sum(o.dhop_dir(x, d, s) for d in range(4) for s in (1, -1))
+    assert rel_err(total, o.apply(po.OP_DHOP, x)) < 1e-14
+    # a leg only reads the neighbour in its own direction: it vanishes when that neighbour slice is zeroed
+    y = x.reshape(DIMS[3], DIMS[2], DIMS[1], DIMS[0], -1).copy()
+    y[:, :, :, 1] = 0                                     # kill x = 1
+    leg = o.dhop_dir(y.reshape(x.shape), 0, 1).reshape(y.shape)
+    assert np.count_nonzero(leg[:, :, :, 0]) == 0          # sites at x = 0 read x + 1 = 1
+
+
+def _ta(M):
+    """Ta: traceless anti-Hermitian part (ref: Grid/tensors/Tensor_Ta.h)"""
+    A = 0.5 * (M - np.conj(np.swapaxes(M, -1, -2)))
+    tr = np.trace(A, axis1=-2, axis2=-1) / 3.0
+    return A - tr[..., None, None] * np.eye(3)
+
+
+@pytest.mark.parametrize("name", ["wilson", "mobius"])
+def test_oracle_mderiv_predicts_the_action_change(name):
+    """tests/forces/Test_dwf_force.cc:60-141: S = |M phi|^2; U' = exp(dt P) U; S' - S == dt sum tr(P 2 Ta(UdSdU)) + O(dt^2)."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(7)
+    U = G["U"]
+    o = oracle_op(name)
+    phi = G[OPS[name]["src"]]
+    Mphi = o.apply(po.OP_M, phi)
+    S = np.vdot(Mphi, Mphi).real
+    UdSdU = o.deriv(1, Mphi, phi, 0) + o.deriv(1, phi, Mphi, 1)
+    P = _ta(rng.normal(size=U.shape) + 1j * rng.normal(size=U.shape))     # momenta: traceless anti-Hermitian
+    dt = 1e-5
+    Up = np.einsum("smij,smjk->smik", np.array([[expm(dt * P[s, m]) for m in range(4)] for s in range(U.shape[0])]), U)
+    o2 = oracle_op(name, U=Up)
+    Mp = o2.apply(po.OP_M, phi)
+    dS = np.vdot(Mp, Mp).real - S
+    pred = dt * np.einsum("smij,smji->", P, 2.0 * _ta(UdSdU)).real
+    assert abs(dS - pred) < 2e-3 * abs(pred), (dS, pred)
+
+
+@pytest.mark.skipif(not pr.available(), reason="oracle/_ref/libgridref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("prec", [1, 0])
+@pytest.mark.parametrize("name", ["wilson", "mobius"])
+def test_oracle_vs_reference_force_terms(name, prec):
+    dims = (4, 6, 8, 4)
+    cfg = OPS[name]
+    U = syn.hot_gauge(dims, seed=21)
+    o = oracle_op(name, prec, U, dims)
+    r = pr.RefOp(cfg["kind"], dims, cfg["Ls"], mass=0.1, M5=1.8, b=cfg["b"], c=cfg["c"], prec=prec); r.import_gauge(U)
+    x = syn.random_fermion(dims, cfg["Ls"], seed=3).astype(po._cdtype(prec)); y = syn.random_fermion(dims, cfg["Ls"], seed=5).astype(po._cdtype(prec))
+    tol = 1e-13 if prec else 1e-6
+    for d in range(4):
+        for s in (1, -1):
+            assert rel_err(o.dhop_dir(x, d, s), r.dhop_dir(x, d, s).astype(np.complex128)) < tol
+    for which in (0, 1):
+        for dag in (0, 1):
+            assert rel_err(o.deriv(which, x, y, dag), r.deriv(which, x, y, dag).astype(np.complex128)) < 4 * tol
+
+
+# ---------------------------------------------------------------------------------------------- GPU
+def _device_op(gb, grid, name, prec):
+    Umu = gb.LatticeGaugeField(grid, prec).import_lex(G["U"])
+    if name == "wilson":
+        return gb.WilsonFermion(Umu, grid, 0.1)
+    return gb.MobiusFermion(Umu, grid, LS, 0.1, 1.8, 1.5, 0.5)
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+@pytest.mark.parametrize("prec_name", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["wilson", "mobius"])
+def test_cuda_dhop_dir_and_force_terms(name, prec_name):
+    import grid_b200 as gb
+    prec = gb.F64 if prec_name == "f64" else gb.F32
+    tol = 2e-13 if prec == gb.F64 else 4e-6
+    dt = gb._cdtype(prec)
+    ctx = gb.Context(0)
+    grid = gb.GridCartesian(ctx, DIMS)
+    D = _device_op(gb, grid, name, prec)
+    Ls = OPS[name]["Ls"]
+    A = gb.LatticeFermion(grid, Ls, prec).import_lex(G[OPS[name]["src"]].astype(dt))
+    B = gb.LatticeFermion(grid, Ls, prec).import_lex(N[f"{name}/src_b"].astype(dt))
+    out, total = gb.LatticeFermion(grid, Ls, prec), gb.LatticeFermion(grid, Ls, prec).zero()
+    o = oracle_op(name)
+    for d in range(4):
+        for s in (1, -1):
+            D.DhopDir(A, out, d, s)
+            assert rel_err(out.export_lex(), o.dhop_dir(G[OPS[name]["src"]], d, s)) < tol, (d, s)
+            gb.axpy(total, 1.0, out, total)
+    D.Dhop(A, out, 0)
+    assert rel_err(total.export_lex(), out.export_lex().astype(np.complex128)) < 4 * tol          # the eight legs sum to Dhop
+    if name == "mobius":
+        D.DhopDir(A, out, 1, 1)
+        assert rel_err(out.export_lex(), N["mobius/dhop_dir/1_1"]) < tol
+    mat = gb.LatticeGaugeField(grid, prec)
+    for which, meth in ((0, D.DhopDeriv), (1, D.MDeriv)):
+        for dag in (0, 1):
+            meth(mat, A, B, dag)
+            assert rel_err(mat.export_lex(dtype=dt), N[f"{name}/deriv/{which}_{dag}"]) < 4 * tol, (which, dag)
+    # the tuned kernels are back in charge afterwards: a plain hop still matches the oracle
+    D.Dhop(A, out, 1)
+    assert rel_err(out.export_lex(), o.apply(po.OP_DHOP, G[OPS[name]["src"]], dag=1)) < tol
