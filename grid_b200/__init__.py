@@ -55,6 +55,7 @@ SYMBOLS = [
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
     ("gb_op_dhop_dir", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_dhop_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mderiv", _i, [_vp, _vp, _vp, _vp, _i]),
+    ("gb_op_meooe_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mpc_deriv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_cg_multishift_schur", _i, [_vp, _vp, _i, _pd, _pd, _i, _pvp, _pi, _pd]),
     ("gb_op_import_physical_fermion_source", _i, [_vp, _vp, _vp]), ("gb_op_import_unphysical_fermion", _i, [_vp, _vp, _vp]),
     ("gb_op_export_physical_fermion_solution", _i, [_vp, _vp, _vp]), ("gb_op_export_physical_fermion_source", _i, [_vp, _vp, _vp]),
@@ -381,6 +382,8 @@ class FermionOperator:
     def DhopDir(self, i, o, dir, disp): _chk(lib().gb_op_dhop_dir(self.h, i.h, o.h, dir, disp))
     def DhopDeriv(self, mat, U, V, dag): _chk(lib().gb_op_dhop_deriv(self.h, mat.h, U.h, V.h, dag))
     def MDeriv(self, mat, U, V, dag): _chk(lib().gb_op_mderiv(self.h, mat.h, U.h, V.h, dag))
+    def MeoDeriv(self, mat, U, V, dag): assert U.Checkerboard() == Even; _chk(lib().gb_op_meooe_deriv(self.h, mat.h, U.h, V.h, dag))
+    def MoeDeriv(self, mat, U, V, dag): assert U.Checkerboard() == Odd; _chk(lib().gb_op_meooe_deriv(self.h, mat.h, U.h, V.h, dag))
 
     def Dhop_host(self, host_in, host_out, dag=0):
         """Dhop on host-resident full-lattice arrays [V4*Ls,4,3] (lexicographic); pipelined H2D / hop / D2H on one rank."""
@@ -473,6 +476,13 @@ class SchurDiagMooeeOperator(LinearOperatorBase):
     def Op(self, i, o): self.Mpc(i, o)
     def AdjOp(self, i, o): self.MpcDag(i, o)
     def HermOp(self, i, o): self.MpcDagMpc(i, o)
+
+
+class SchurDifferentiableOperator(SchurDiagMooeeOperator):
+    """ref: Grid/qcd/action/pseudofermion/EvenOddSchurDifferentiable.h:43-139 -- the Schur operator with its force terms."""
+
+    def MpcDeriv(self, Force, U, V): _chk(lib().gb_op_mpc_deriv(self._Mat.h, Force.h, U.h, V.h, 0))
+    def MpcDagDeriv(self, Force, U, V): _chk(lib().gb_op_mpc_deriv(self._Mat.h, Force.h, U.h, V.h, 1))
 
 
 class SchurStaggeredOperator(SchurDiagMooeeOperator):

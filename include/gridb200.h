@@ -223,6 +223,13 @@ int gb_op_export_physical_fermion_source(gb_fermop *op, const gb_fermion *src5d,
 int gb_op_dhop_dir(gb_fermop *op, const gb_fermion *in, gb_fermion *out, int dir, int disp);
 int gb_op_dhop_deriv(gb_fermop *op, gb_gauge *mat, const gb_fermion *A, const gb_fermion *B, int dag);
 int gb_op_mderiv(gb_fermop *op, gb_gauge *mat, const gb_fermion *U, const gb_fermion *V, int dag);
+/* Even-odd force terms.  MeoDeriv (U Even, V Odd) / MoeDeriv (U Odd, V Even), selected by U's checkerboard: writes the sites of
+ * U's parity of the full-lattice mat and leaves the others alone (the reference assembles ForceE / ForceO with setCheckerboard).
+ *   ref: CayleyFermion5DImplementation.h:361-390, WilsonFermion5DImplementation.h:277-305
+ * SchurDifferentiableOperator::MpcDeriv (dagger = 0) / MpcDagDeriv (1): U, V on the Odd checkerboard, Force on the full grid
+ *   ref: Grid/qcd/action/pseudofermion/EvenOddSchurDifferentiable.h:52-137 (what TwoFlavourEvenOddPseudoFermionAction::deriv calls) */
+int gb_op_meooe_deriv(gb_fermop *op, gb_gauge *mat, const gb_fermion *U, const gb_fermion *V, int dag);
+int gb_op_mpc_deriv(gb_fermop *op, gb_gauge *Force, const gb_fermion *U, const gb_fermion *V, int dagger);
 
 /* ---------------------------------------------------------------- solvers
  * ConjugateGradient on SchurDiagMooeeOperator(op).HermOp, fused device path.

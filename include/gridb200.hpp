@@ -175,6 +175,8 @@ public:
   virtual void DhopDir(const FermionField &in, FermionField &out, int dir, int disp) { GB_ASSERT_OK(gb_op_dhop_dir(h, in.h, out.h, dir, disp)); }
   virtual void DhopDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { GB_ASSERT_OK(gb_op_dhop_deriv(h, mat.h, U.h, V.h, dag)); }
   virtual void MDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { GB_ASSERT_OK(gb_op_mderiv(h, mat.h, U.h, V.h, dag)); }
+  virtual void MeoDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { assert(U.Checkerboard() == Even); GB_ASSERT_OK(gb_op_meooe_deriv(h, mat.h, U.h, V.h, dag)); }
+  virtual void MoeDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { assert(U.Checkerboard() == Odd); GB_ASSERT_OK(gb_op_meooe_deriv(h, mat.h, U.h, V.h, dag)); }
   // Dhop on host-resident full-lattice arrays in the reference's unvectorised layout (pipelined H2D / hop / D2H on one rank)
   void DhopHost(const void *host_in, void *host_out, gb_precision host_prec, int dag) { GB_ASSERT_OK(gb_op_dhop_host(h, host_in, host_out, host_prec, dag)); }
 };
@@ -237,6 +239,14 @@ public:
   void AdjOp(const Field &in, Field &out) override { MpcDag(in, out); }
   void HermOp(const Field &in, Field &out) override { MpcDagMpc(in, out); }
   gb_fermop *FusedSchurMatrix() override { return _Mat.h; }
+};
+
+// SchurDifferentiableOperator (ref: Grid/qcd/action/pseudofermion/EvenOddSchurDifferentiable.h:43-139): Mpc with its force terms
+template <class Matrix, class Field> class SchurDifferentiableOperator : public SchurDiagMooeeOperator<Matrix, Field> {
+public:
+  explicit SchurDifferentiableOperator(Matrix &Mat) : SchurDiagMooeeOperator<Matrix, Field>(Mat) {}
+  template <class GaugeField> void MpcDeriv(GaugeField &Force, const Field &U, const Field &V) { GB_ASSERT_OK(gb_op_mpc_deriv(this->_Mat.h, Force.h, U.h, V.h, 0)); }
+  template <class GaugeField> void MpcDagDeriv(GaugeField &Force, const Field &U, const Field &V) { GB_ASSERT_OK(gb_op_mpc_deriv(this->_Mat.h, Force.h, U.h, V.h, 1)); }
 };
 
 // SchurStaggeredOperator (ref: LinearOperator.h:543-584): Mpc = mass^2 - Meooe Meooe is Hermitian, HermOp = Mpc

@@ -659,6 +659,71 @@ template <class T> struct FermOp {
     if (!dag) { Meooe5D(g.V4(), V, Din.data()); DhopDeriv(mat, U, Din.data(), dag); }
     else { Meooe5D(g.V4(), U, Din.data()); DhopDeriv(mat, Din.data(), V, dag); }
   }
+  // ---- even-odd force terms.  Fields are red-black; mat is the FULL lexicographic gauge field, of which only the sites of
+  // parity ocb (= A's checkerboard) are written, the way SchurDifferentiableOperator assembles ForceE / ForceO.
+  // ref: WilsonFermion5DImplementation.h:277-305 (DhopDerivEO / OE), CayleyFermion5DImplementation.h:361-390 (MoeDeriv / MeoDeriv)
+  void DhopLegCB(const F *in, F *out, int ocb, int point, int dag) const {   // in has parity 1-ocb
+    const int Ls = g.Ls, mu = point & 3, fwd = point < 4;
+    const int sgn = (fwd ? -1 : +1) * (dag ? -1 : +1);
+#pragma omp parallel for
+    for (int64_t ic = 0; ic < g.V4cb(); ic++) {
+      int x[4]; g.cbcoor4(ic, ocb, x);
+      const int64_t i4 = g.lex4(x);
+      int y[4] = {x[0], x[1], x[2], x[3]};
+      y[mu] = fwd ? (x[mu] + 1) % g.L[mu] : (x[mu] + g.L[mu] - 1) % g.L[mu];
+      const int64_t nb = g.cb4(y);
+      for (int s = 0; s < Ls; s++) {
+        HalfSpinor<T> chi, Uchi;
+        Spinor<T> r; zero(r);
+        spProj(chi, in[nb * Ls + s], mu, sgn);
+        multLink(Uchi, Uds[i4 * 8 + point], chi);
+        accumRecon(r, Uchi, mu, sgn);
+        out[ic * Ls + s] = r;
+      }
+    }
+  }
+  // A on parity ocb, B on parity 1-ocb
+  void DhopDerivCB(ColourMatrix<T> *mat, const F *A, const F *B, int dag, int ocb) const {
+    const int Ls = g.Ls;
+    Vec Btilde(V5cb());
+    for (int mu = 0; mu < 4; mu++) {
+      DhopLegCB(B, Btilde.data(), ocb, mu, dag);
+#pragma omp parallel for
+      for (int64_t ic = 0; ic < g.V4cb(); ic++) {
+        int x[4]; g.cbcoor4(ic, ocb, x);
+        ColourMatrix<T> m; std::memset((void *)&m, 0, sizeof(m));
+        for (int s = 0; s < Ls; s++) {
+          const F &b = Btilde[ic * Ls + s], &a = A[ic * Ls + s];
+          for (int sp = 0; sp < Ns; sp++) for (int c1 = 0; c1 < Nc; c1++) for (int c2 = 0; c2 < Nc; c2++) m.m[c1][c2] += b.v[sp][c1] * conj(a.v[sp][c2]);
+        }
+        mat[g.lex4(x) * 4 + mu] = m;
+      }
+    }
+  }
+  // MeoDeriv (ocb = Even: U Even, V Odd) / MoeDeriv (ocb = Odd)
+  void MeooeDeriv(ColourMatrix<T> *mat, const F *U, const F *V, int dag, int ocb) const {
+    if (kind == OpKind::Wilson4D) { DhopDerivCB(mat, U, V, dag, ocb); return; }
+    Vec Din(V5cb());
+    if (!dag) { Meooe5D(g.V4cb(), V, Din.data()); DhopDerivCB(mat, U, Din.data(), dag, ocb); }
+    else { Meooe5D(g.V4cb(), U, Din.data()); DhopDerivCB(mat, Din.data(), V, dag, ocb); }
+  }
+  // SchurDifferentiableOperator::MpcDeriv / MpcDagDeriv: U, V on the Odd checkerboard, Force on the full lattice
+  // ref: Grid/qcd/action/pseudofermion/EvenOddSchurDifferentiable.h:52-137
+  void MpcDeriv(ColourMatrix<T> *Force, const F *U, const F *V, int dagger) const {
+    Vec tmp1(V5cb()), tmp2(V5cb());
+    if (!dagger) {
+      Meooe(V, tmp1.data(), Odd); MooeeInv(g.V4cb(), tmp1.data(), tmp2.data());
+      MeooeDeriv(Force, U, tmp2.data(), 0, Odd);                     // MoeDeriv(ForceO, U, tmp2, DaggerNo)
+      MeooeDag(U, tmp1.data(), Odd); MooeeInvDag(g.V4cb(), tmp1.data(), tmp2.data());
+      MeooeDeriv(Force, tmp2.data(), V, 0, Even);                    // MeoDeriv(ForceE, tmp2, V, DaggerNo)
+    } else {
+      MeooeDag(V, tmp1.data(), Odd); MooeeInvDag(g.V4cb(), tmp1.data(), tmp2.data());
+      MeooeDeriv(Force, U, tmp2.data(), 1, Odd);
+      Meooe(U, tmp1.data(), Odd); MooeeInv(g.V4cb(), tmp1.data(), tmp2.data());
+      MeooeDeriv(Force, tmp2.data(), V, 1, Even);
+    }
+    for (int64_t i = 0; i < g.V4() * 4; i++) for (int a = 0; a < Nc; a++) for (int b = 0; b < Nc; b++) Force[i].m[a][b] = -Force[i].m[a][b];
+  }
   // ---- physical 4D <-> 5D maps.  4D fields have V4 sites, 5D fields V4*Ls (s fastest).
   // Wilson4D: every map is the identity (ref: FermionOperator.h:172-191).
   // Dminus: chi_s = psi_s - cs[s] DW(psi)_s ; DminusDag uses DW^dag   ref: CayleyFermion5DImplementation.h:132-153

@@ -42,6 +42,8 @@ struct BoxBase {
   // DhopDir, DhopDeriv (which 0) / MDeriv (which 1) on the full grid; mat = LatticeGaugeField
   virtual int dhop_dir(const void *in, void *out, int dir, int disp) { return -1; }
   virtual int deriv(int which, void *mat, const void *U, const void *V, int dag) { return -1; }
+  // which 2 = SchurDifferentiableOperator::MpcDeriv, 3 = MpcDagDeriv (U, V on the Odd checkerboard, Force on the full grid)
+  virtual int deriv_eo(int which, void *mat, const void *U, const void *V) { return -1; }
   // ConjugateGradientMultiShift on the Schur operator of checkerboard cb
   virtual void multishift(int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results, int *iters, double *tr) = 0;
 };
@@ -247,6 +249,17 @@ template <class Impl, class vComplexT> struct WilsonBox : BoxBase {
     export_lex(m, mat);
     return 0;
   }
+  int deriv_eo(int which, void *mat, const void *U, const void *V) override {
+    FermionField u(frbgrid()), v(frbgrid());
+    import_lex(u, U); import_lex(v, V);
+    u.Checkerboard() = Odd; v.Checkerboard() = Odd;
+    GaugeField F(G.UGrid);
+    F = Zero();
+    SchurDifferentiableOperator<Impl> S(*op);
+    if (which == 2) S.MpcDeriv(F, u, v); else if (which == 3) S.MpcDagDeriv(F, u, v); else return -1;
+    export_lex(F, mat);
+    return 0;
+  }
   typedef SchurRedBlackDiagMooeeSolve<FermionField> RBSolver;
   void redblack_source(const void *src, void *src_e, void *src_o) override { rb_source<RBSolver, OpBase, FermionField>(*op, fgrid(), frbgrid(), src, src_e, src_o); }
   void redblack_solution(const void *sol_o, const void *src_e, void *sol) override { rb_solution<RBSolver, OpBase, FermionField>(*op, fgrid(), frbgrid(), sol_o, src_e, sol); }
@@ -392,6 +405,7 @@ void gref_schur_solve(void *h, const void *src, void *sol, double tol, int maxit
 
 int gref_dhop_dir(void *h, const void *in, void *out, int dir, int disp) { return ((BoxBase *)h)->dhop_dir(in, out, dir, disp); }
 int gref_deriv(void *h, int which, void *mat, const void *U, const void *V, int dag) { return ((BoxBase *)h)->deriv(which, mat, U, V, dag); }
+int gref_deriv_eo(void *h, int which, void *mat, const void *U, const void *V) { return ((BoxBase *)h)->deriv_eo(which, mat, U, V); }
 // ConjugateGradientMultiShift as tests/solver/Test_staggered_multishift.cc:98-107 drives it, with explicit poles / tolerances
 void gref_multishift_cg(void *h, int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results,
                         int *out_iters, double *out_true_resid) {

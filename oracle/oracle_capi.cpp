@@ -162,6 +162,17 @@ void orc_deriv(void *h, int which, void *mat, const void *U, const void *V, int 
   if (box->prec == 0) run(box->f, (ColourMatrix<float> *)mat, (const Spinor<float> *)U, (const Spinor<float> *)V);
   else run(box->d, (ColourMatrix<double> *)mat, (const Spinor<double> *)U, (const Spinor<double> *)V);
 }
+// which 0 = MeoDeriv (U Even, V Odd), 1 = MoeDeriv (U Odd, V Even): writes the sites of U's parity of the full-lattice mat;
+// which 2 = SchurDifferentiableOperator::MpcDeriv, 3 = MpcDagDeriv (U, V Odd; the whole Force)
+void orc_deriv_eo(void *h, int which, void *mat, const void *U, const void *V, int dag) {
+  OpBox *box = (OpBox *)h;
+  auto run = [&](auto &op, auto *m, auto *u, auto *v) {
+    if (which < 2) op.MeooeDeriv(m, u, v, dag, which == 0 ? Even : Odd);
+    else op.MpcDeriv(m, u, v, which == 3);
+  };
+  if (box->prec == 0) run(box->f, (ColourMatrix<float> *)mat, (const Spinor<float> *)U, (const Spinor<float> *)V);
+  else run(box->d, (ColourMatrix<double> *)mat, (const Spinor<double> *)U, (const Spinor<double> *)V);
+}
 // SchurRedBlackDiagMooeeSolve pieces: full-lattice src -> (src_e, src_o') ; (sol_o, src_e) -> full-lattice sol
 void orc_redblack_source(void *h, const void *src, void *src_e, void *src_o) {
   OpBox *box = (OpBox *)h;

@@ -45,6 +45,7 @@ def lib():
         L.orc_multishift_cg.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_dhop_dir.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_deriv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_deriv_eo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_physical.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_physical.restype = C.c_int
         L.orc_redblack_source.argtypes = [C.c_void_p] * 4
@@ -159,6 +160,14 @@ class OracleOp:
         U = np.ascontiguousarray(U, dtype=_cdtype(self.prec)); V = np.ascontiguousarray(V, dtype=_cdtype(self.prec))
         mat = np.zeros((self.V4, 4, 3, 3), dtype=U.dtype)
         lib().orc_deriv(self.h, which, _ptr(mat), _ptr(U), _ptr(V), dag)
+        return mat
+
+    def deriv_eo(self, which, U, V, dag=0):
+        """which 0 = MeoDeriv (U Even, V Odd), 1 = MoeDeriv (U Odd, V Even): only the sites of U's parity of the returned full-lattice
+        [V4,4,3,3] are written; 2 = SchurDifferentiableOperator::MpcDeriv, 3 = MpcDagDeriv (U, V Odd; the whole force)."""
+        U = np.ascontiguousarray(U, dtype=_cdtype(self.prec)); V = np.ascontiguousarray(V, dtype=_cdtype(self.prec))
+        mat = np.zeros((self.V4, 4, 3, 3), dtype=U.dtype)
+        lib().orc_deriv_eo(self.h, which, _ptr(mat), _ptr(U), _ptr(V), dag)
         return mat
 
     def multishift_cg(self, cb, src, poles, tols, maxit):

@@ -46,6 +46,8 @@ def lib():
         L.gref_multishift_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gref_dhop_dir.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.gref_deriv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.gref_deriv_eo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gref_deriv_eo.restype = C.c_int
         L.gref_physical.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_physical.restype = C.c_int
         L.gref_redblack_source.argtypes = [C.c_void_p] * 4
@@ -165,6 +167,16 @@ class RefOp:
         U = np.ascontiguousarray(U, dtype=_cdtype(self.prec)); V = np.ascontiguousarray(V, dtype=_cdtype(self.prec))
         mat = np.zeros((self.V4, 4, 3, 3), dtype=U.dtype)
         lib().gref_deriv(self.h, which, _ptr(mat), _ptr(U), _ptr(V), dag)
+        return mat
+
+    def deriv_eo(self, which, U, V, dag=0):
+        """which 0 = MeoDeriv (U Even, V Odd), 1 = MoeDeriv (U Odd, V Even): only the sites of U's parity of the returned full-lattice
+        [V4,4,3,3] are written; 2 = SchurDifferentiableOperator::MpcDeriv, 3 = MpcDagDeriv (U, V Odd; the whole force)."""
+        U = np.ascontiguousarray(U, dtype=_cdtype(self.prec)); V = np.ascontiguousarray(V, dtype=_cdtype(self.prec))
+        mat = np.zeros((self.V4, 4, 3, 3), dtype=U.dtype)
+        assert which in (2, 3)
+        rc = lib().gref_deriv_eo(self.h, which, _ptr(mat), _ptr(U), _ptr(V))
+        assert rc == 0, rc
         return mat
 
     def multishift_cg(self, cb, src, poles, tols, maxit):

@@ -15,6 +15,7 @@ for op in wilson, dwf, mobius (b=1.5,c=0.5), stag.
 Row f2 (single hop legs and force terms, ref: WilsonFermion5DImplementation.h:183-275 ; CayleyFermion5DImplementation.h:347-360), A = src,
 B = the field stored as "src_b" (second random source):
   mobius/dhop_dir/{dir}_{disp}  for (1,+1), (3,-1);   <op>/deriv/{which}_{dag}  which 0 DhopDeriv, 1 MDeriv, for op in wilson, mobius
+  <op>/mpc_deriv/{0,1}  SchurDifferentiableOperator::MpcDeriv / MpcDagDeriv(Force, pick(Odd, src), pick(Odd, src_b))
 
 Row f3 (ConjugateGradientMultiShift, ref: Grid/algorithms/iterative/ConjugateGradientMultiShift.h:84-343) on the Odd checkerboard of
 the same sources, poles MS_POLES, tolerances MS_TOLS:
@@ -64,6 +65,8 @@ def main():
             for which in (0, 1):
                 for dag in (0, 1):
                     out[f"{name}/deriv/{which}_{dag}"] = op.deriv(which, src, srcb, dag)
+            uo, vo = op.pick_checkerboard(1, src), op.pick_checkerboard(1, srcb)
+            out[f"{name}/mpc_deriv/0"], out[f"{name}/mpc_deriv/1"] = op.deriv_eo(2, uo, vo), op.deriv_eo(3, uo, vo)
         if name in ("mobius", "stag"):
             xs, info = op.multishift_cg(1, op.pick_checkerboard(1, src), MS_POLES, MS_TOLS, 5000)
             out[f"{name}/multishift/solutions"] = xs

@@ -87,6 +87,36 @@ def test_oracle_mderiv_predicts_the_action_change(name):
     assert abs(dS - pred) < 2e-3 * abs(pred), (dS, pred)
 
 
+@pytest.mark.parametrize("name", ["wilson", "mobius"])
+def test_oracle_even_odd_force_matches_reference_outputs_and_predicts_the_action_change(name):
+    """SchurDifferentiableOperator::MpcDeriv / MpcDagDeriv (ref: EvenOddSchurDifferentiable.h:52-137) against the stored reference
+    outputs, then the even-odd analogue of the force test: S = |Mpc phi_o|^2, dS == dt sum tr(P 2 Ta(MpcDeriv + MpcDagDeriv))."""
+    from scipy.linalg import expm
+    o = oracle_op(name)
+    Ls = OPS[name]["Ls"]
+    uo, vo = po.pick_checkerboard(DIMS, Ls, 1, G[OPS[name]["src"]]), po.pick_checkerboard(DIMS, Ls, 1, N[f"{name}/src_b"])
+    assert rel_err(o.deriv_eo(2, uo, vo), N[f"{name}/mpc_deriv/0"]) < 1e-13
+    assert rel_err(o.deriv_eo(3, uo, vo), N[f"{name}/mpc_deriv/1"]) < 1e-13
+    # MeoDeriv / MoeDeriv only write the sites of U's parity
+    ue = po.pick_checkerboard(DIMS, Ls, 0, G[OPS[name]["src"]])
+    m = o.deriv_eo(0, ue, vo)
+    par = np.indices(DIMS[::-1]).sum(axis=0).reshape(-1) & 1          # lexicographic site parity
+    assert np.count_nonzero(m[par == 1]) == 0 and np.count_nonzero(m[par == 0]) > 0
+    phi = uo
+    Mphi = o.apply(po.OP_MPC, phi, cb_in=1)
+    S = np.vdot(Mphi, Mphi).real
+    UdSdU = o.deriv_eo(2, Mphi, phi) + o.deriv_eo(3, phi, Mphi)
+    rng = np.random.default_rng(8)
+    U = G["U"]
+    P = _ta(rng.normal(size=U.shape) + 1j * rng.normal(size=U.shape))
+    dt = 1e-5
+    Up = np.einsum("smij,smjk->smik", np.array([[expm(dt * P[s, m]) for m in range(4)] for s in range(U.shape[0])]), U)
+    Mp = oracle_op(name, U=Up).apply(po.OP_MPC, phi, cb_in=1)
+    dS = np.vdot(Mp, Mp).real - S
+    pred = dt * np.einsum("smij,smji->", P, 2.0 * _ta(UdSdU)).real
+    assert abs(dS - pred) < 2e-3 * abs(pred), (dS, pred)
+
+
 @pytest.mark.skipif(not pr.available(), reason="oracle/_ref/libgridref.so not built (needs /root/reference)")
 @pytest.mark.parametrize("prec", [1, 0])
 @pytest.mark.parametrize("name", ["wilson", "mobius"])
@@ -104,6 +134,9 @@ def test_oracle_vs_reference_force_terms(name, prec):
     for which in (0, 1):
         for dag in (0, 1):
             assert rel_err(o.deriv(which, x, y, dag), r.deriv(which, x, y, dag).astype(np.complex128)) < 4 * tol
+    xo, yo = po.pick_checkerboard(dims, cfg["Ls"], 1, x), po.pick_checkerboard(dims, cfg["Ls"], 1, y)
+    for which in (2, 3):
+        assert rel_err(o.deriv_eo(which, xo, yo), r.deriv_eo(which, xo, yo).astype(np.complex128)) < 8 * tol
 
 
 # ---------------------------------------------------------------------------------------------- GPU
@@ -149,3 +182,37 @@ def test_cuda_dhop_dir_and_force_terms(name, prec_name):
     # the tuned kernels are back in charge afterwards: a plain hop still matches the oracle
     D.Dhop(A, out, 1)
     assert rel_err(out.export_lex(), o.apply(po.OP_DHOP, G[OPS[name]["src"]], dag=1)) < tol
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+@pytest.mark.parametrize("prec_name", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["wilson", "mobius"])
+def test_cuda_even_odd_force_terms(name, prec_name):
+    import grid_b200 as gb
+    prec = gb.F64 if prec_name == "f64" else gb.F32
+    tol = 4e-13 if prec == gb.F64 else 8e-6
+    dt = gb._cdtype(prec)
+    ctx = gb.Context(0)
+    grid = gb.GridCartesian(ctx, DIMS)
+    D = _device_op(gb, grid, name, prec)
+    Ls = OPS[name]["Ls"]
+    A = gb.LatticeFermion(grid, Ls, prec).import_lex(G[OPS[name]["src"]].astype(dt))
+    B = gb.LatticeFermion(grid, Ls, prec).import_lex(N[f"{name}/src_b"].astype(dt))
+    uo, vo, ue = (gb.LatticeFermion(grid, Ls, prec, gb.HALF) for _ in range(3))
+    gb.pickCheckerboard(gb.Odd, uo, A); gb.pickCheckerboard(gb.Odd, vo, B); gb.pickCheckerboard(gb.Even, ue, A)
+    S = gb.SchurDifferentiableOperator(D)
+    F = gb.LatticeGaugeField(grid, prec)
+    S.MpcDeriv(F, uo, vo)
+    assert rel_err(F.export_lex(dtype=dt), N[f"{name}/mpc_deriv/0"]) < tol
+    S.MpcDagDeriv(F, uo, vo)
+    assert rel_err(F.export_lex(dtype=dt), N[f"{name}/mpc_deriv/1"]) < tol
+    # MeoDeriv against the oracle; it must leave the Odd sites of the force field alone
+    o = oracle_op(name)
+    before = F.export_lex(dtype=dt)
+    D.MeoDeriv(F, ue, vo, 0)
+    got = F.export_lex(dtype=dt)
+    want = o.deriv_eo(0, po.pick_checkerboard(DIMS, Ls, 0, G[OPS[name]["src"]]), po.pick_checkerboard(DIMS, Ls, 1, N[f"{name}/src_b"]))
+    par = np.indices(DIMS[::-1]).sum(axis=0).reshape(-1) & 1
+    assert rel_err(got[par == 0], want[par == 0]) < tol
+    assert np.array_equal(got[par == 1], before[par == 1])
