@@ -51,6 +51,7 @@ SYMBOLS = [
     ("gb_op_create_mobius", _i, [_vp, _vp, _i, _d, _d, _d, _d, _pd, _pvp]), ("gb_op_import_gauge", _i, [_vp, _vp]),
     ("gb_op_create_staggered", _i, [_vp, _vp, _vp, _d, _d, _d, _d, _pvp]), ("gb_op_import_gauge_staggered", _i, [_vp, _vp, _vp]),
     ("gb_op_destroy", _i, [_vp]), ("gb_op_Ls", _i, [_vp]), ("gb_op_apply", _i, [_vp, _i, _vp, _vp, _i]),
+    ("gb_op_halo_exchange", _i, [_vp, _vp, _i, C.POINTER(C.c_int64)]),
     ("gb_op_dhop_host", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
@@ -390,6 +391,12 @@ class FermionOperator:
         assert host_in.flags.c_contiguous and host_out.flags.c_contiguous and host_in.dtype == host_out.dtype and host_in.shape == host_out.shape
         _chk(lib().gb_op_dhop_host(self.h, host_in.ctypes.data_as(C.c_void_p), host_out.ctypes.data_as(C.c_void_p), _prec_of(host_in), dag))
         return host_out
+
+    def halo_exchange(self, i, dag=0):
+        """The face exchange of one full-lattice Dhop without the hop (halo microbenchmark); returns the bytes this rank sent."""
+        b = C.c_int64()
+        _chk(lib().gb_op_halo_exchange(self.h, i.h, dag, C.byref(b)))
+        return b.value
 
     def set_tiling(self, by=0, bz=0, bt=0):
         lib().gb_op_set_tiling(self.h, by, bz, bt)

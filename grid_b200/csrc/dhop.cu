@@ -616,6 +616,43 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   }
 }
 
+// The face exchange of one full-lattice hop on its own (no hopping kernel): project + send every face, then wait until the
+// neighbours' faces have arrived.  This is the library's Benchmark_comms (ref: benchmarks/Benchmark_comms.cc:105-162 times
+// StencilSendToRecvFrom of L^3 Ls half-spinor packets in all split directions concurrently); here the projection is fused
+// into the send, so the timed unit is pack + transfer + arrival.  Returns the bytes this rank sent.
+__global__ void halo_wait_kernel(const unsigned long long *flags, unsigned long long epoch, int comm_dim_mask) {
+  if (threadIdx.x < 8 && ((comm_dim_mask >> (threadIdx.x & 3)) & 1)) {
+    unsigned long long v;
+    do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory"); } while (v < epoch);
+  }
+}
+size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag) {
+  GB_REQUIRE(op && in && op->kind != GB_KIND_STAGGERED, "halo exchange benchmark: Wilson-type operators");
+  GB_REQUIRE(in->grid == op->grid && in->Ls == op->Ls && in->prec == op->prec && in->kind == GB_FULL, "field is not a conformable full-grid field");
+  gb_context *ctx = op->ctx;
+  if (!op->comm_dim_mask) return 0;
+  GB_CUDA(cudaSetDevice(ctx->device));
+  const void *ib[2] = {in->block(0), in->block(1)};
+  size_t bytes = 0;
+  if (p2p_setup(op)) {
+    const unsigned long long epoch = p2p_pack_send(op, ib, 0, 2, dag, ctx->stream);
+    const void *halo[8]; const unsigned long long *flags = nullptr;
+    p2p_fill_halo(op, epoch, halo, &flags);
+    halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(flags, epoch, op->comm_dim_mask);
+    count_launch(ctx);
+    check_launch(ctx, "halo_wait");
+  } else {
+    ensure_halo(op);
+    for (int ip = 0; ip < 2; ip++) {
+      if (op->prec == GB_F32) { if (dag) launch_pack<float, 1>(op, ib[ip], ip, ip, ctx->stream); else launch_pack<float, 0>(op, ib[ip], ip, ip, ctx->stream); }
+      else { if (dag) launch_pack<double, 1>(op, ib[ip], ip, ip, ctx->stream); else launch_pack<double, 0>(op, ib[ip], ip, ip, ctx->stream); }
+    }
+    exchange_halos(op, 2, ctx->stream);
+  }
+  for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) bytes += 2 * 2 * op->halo_parity_stride[mu] * 16;   // two directions, two parities
+  return bytes;
+}
+
 // Hop restricted to the t-slices [t0, t0 + nt) of both output parities, all 8 legs, single rank (periodic wrap inside the
 // local volume).  Used by the host-pipelined Dhop (fields.cu), where slices are computed as their neighbours arrive over PCIe.
 void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st) {

@@ -324,6 +324,12 @@ int gb_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out,
   op_apply(op, which, in, out, dag);
   GB_API_END
 }
+int gb_op_halo_exchange(gb_fermop *op, const gb_fermion *in, int dag, int64_t *bytes_sent) {
+  GB_API_BEGIN
+  const size_t b = halo_exchange_only(op, in, dag ? 1 : 0);
+  if (bytes_sent) *bytes_sent = (int64_t)b;
+  GB_API_END
+}
 int gb_op_set_tiling(gb_fermop *op, int by, int bz, int bt) {
   op->By = by; op->Bz = bz; op->Bt = bt;
   op->col_n = bz;   // column-sweep kernel: z-planes per column

@@ -97,6 +97,7 @@ const void *smat_device(gb_fermop *op, const SMat &m);
 bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha, const gb_fermion *z,
                 gb_fermion *out);
 
+size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag);
 void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st);
 // improved staggered operator entry points (stag.cu)
 void stag_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);

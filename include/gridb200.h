@@ -188,6 +188,11 @@ int gb_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out,
  * Single rank: pipelined over t-slices -- H2D of slice t+1, the hop of slice t and D2H of slice t-1 overlap on three streams,
  * so the call costs one direction of PCIe traffic.  Decomposed lattices: import, hop, export.  Pinned host memory recommended. */
 int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_out, gb_precision host_prec, int dag);
+/* The face exchange of one full-lattice Dhop on its own: project + send every face of both parities, then wait for the
+ * neighbours' faces (no hopping kernel).  The halo microbenchmark of SURVEY 8(d)/(e): time N calls with gb_timer_start/stop and
+ * divide bytes_sent (this rank, all split directions, both senses) by the time.  ref: benchmarks/Benchmark_comms.cc:105-162,
+ * Grid/stencil/Stencil.h:367-430.  bytes_sent = 0 on an undecomposed lattice. */
+int gb_op_halo_exchange(gb_fermop *op, const gb_fermion *in, int dag, int64_t *bytes_sent);
 /* tuning knob of the hopping kernel's CTA rasterisation (z/t blocking for L2 reuse); 0 = default */
 int gb_op_set_tiling(gb_fermop *op, int block_y, int block_z, int block_t);
 /* 1 (default): the hop overlaps the face exchange (ref: --comms-overlap, WilsonFermion5DImplementation.h:320-384); on z/t

@@ -18,5 +18,9 @@ if [ "$ngpu" -ge 2 ]; then
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29544 scripts/stag_bench_mgpu.py 48 100 > $out/stag_bench_n${n}_strong.jsonl 2>$out/stag_bench_n${n}_strong.err
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29545 scripts/stag_bench_mgpu.py 48 100 weak > $out/stag_bench_n${n}_weak.jsonl 2>$out/stag_bench_n${n}_weak.err
   cat $out/stag_bench_n${n}_strong.jsonl $out/stag_bench_n${n}_weak.jsonl
+  # 4. halo microbenchmark: peer-to-peer stores, then the NCCL send/recv path
+  timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29555 scripts/halo_bench.py 32 200 > $out/halo_bench_n${n}.jsonl 2>$out/halo_bench_n${n}.err
+  GB_NO_P2P=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29556 scripts/halo_bench.py 32 200 >> $out/halo_bench_n${n}.jsonl 2>>$out/halo_bench_n${n}.err
+  cat $out/halo_bench_n${n}.jsonl
 fi
 python scripts/stag_bench.py 48 100 > $out/stag_bench_n1.jsonl 2>&1; cat $out/stag_bench_n1.jsonl
