@@ -57,6 +57,7 @@ SYMBOLS = [
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
     ("gb_op_dhop_dir", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_dhop_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mderiv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_op_meooe_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mpc_deriv", _i, [_vp, _vp, _vp, _vp, _i]),
+    ("gb_relup_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _d, _pi, _pd]),
     ("gb_cg_multishift_schur", _i, [_vp, _vp, _i, _pd, _pd, _i, _pvp, _pi, _pd]),
     ("gb_op_import_physical_fermion_source", _i, [_vp, _vp, _vp]), ("gb_op_import_unphysical_fermion", _i, [_vp, _vp, _vp]),
     ("gb_op_export_physical_fermion_solution", _i, [_vp, _vp, _vp]), ("gb_op_export_physical_fermion_source", _i, [_vp, _vp, _vp]),
@@ -679,3 +680,24 @@ class ConjugateGradientMultiShift:
             for res, r in zip(self.shifts.residues, results):
                 axpy(psi, res, r, psi)
         return rc == GB_OK
+
+
+class ConjugateGradientReliableUpdate:
+    """ref: Grid/algorithms/iterative/ConjugateGradientReliableUpdate.h:36-270.  mCG = ConjugateGradientReliableUpdate(tol, maxit,
+    delta, Linop_f, Linop_d); mCG(src_d, psi_d)."""
+
+    def __init__(self, tol, maxit, delta, Linop_f, Linop_d, err_on_no_conv=True):
+        self.Tolerance, self.MaxIterations, self.Delta, self.ErrorOnNoConverge = tol, maxit, delta, err_on_no_conv
+        self.Linop_f, self.Linop_d = Linop_f, Linop_d
+        self.IterationsToComplete = self.ReliableUpdatesPerformed = self.IterationsToCleanup = 0
+        self.TrueResidual = 0.0
+
+    def __call__(self, src_d, psi_d):
+        it, tr = (C.c_int * 3)(), C.c_double()
+        rc = lib().gb_relup_cg_schur(self.Linop_f._Mat.h, self.Linop_d._Mat.h, src_d.h, psi_d.h, self.Tolerance, self.MaxIterations,
+                                     self.Delta, it, C.byref(tr))
+        self.IterationsToComplete, self.ReliableUpdatesPerformed, self.IterationsToCleanup, self.TrueResidual = it[0], it[1], it[2], tr.value
+        if rc == GB_ERR_NOT_CONVERGED:
+            assert not self.ErrorOnNoConverge, "ConjugateGradientReliableUpdate did NOT converge"
+            return
+        _chk(rc)

@@ -322,6 +322,84 @@ int gb_cg_multishift_schur(gb_fermop *op, const gb_fermion *src, int nshift, con
   GB_API_END
 }
 
+// ConjugateGradientReliableUpdate   ref: Grid/algorithms/iterative/ConjugateGradientReliableUpdate.h:80-270
+// fp32 iteration, fp64 reliable updates of solution and residual whenever |r|^2 has dropped by Delta since the last one, fp64
+// clean-up CG at the end (DoFinalCleanup).  iters_out = {IterationsToComplete, ReliableUpdatesPerformed, IterationsToCleanup}.
+int gb_relup_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src, gb_fermion *psi, double tol, int maxit, double Delta,
+                      int iters_out[3], double *true_resid_out) {
+  GB_API_BEGIN
+  GB_REQUIRE(op_f && op_d && src && psi && src != psi, "null or aliased argument");
+  GB_REQUIRE(op_f->prec == GB_F32 && op_d->prec == GB_F64, "reliable-update CG needs an fp32 and an fp64 operator");
+  GB_REQUIRE(src->prec == GB_F64 && psi->prec == GB_F64 && src->kind == GB_HALF, "reliable-update CG works on fp64 red-black fields");
+  GB_REQUIRE(Delta > 0. && Delta < 1., "Expect  0 < Delta < 1");   // ref :69
+  fermion_check_same(src, psi);
+  psi->cb = src->cb;
+  auto Ad = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_d, GB_OP_HERMOP, in, out, 0); };
+  auto Af = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_f, GB_OP_HERMOP, in, out, 0); };
+  gb_fermion *p = fermion_create_like(src, GB_F64), *mmp = fermion_create_like(src, GB_F64), *r = fermion_create_like(src, GB_F64);
+  gb_fermion *r_f = fermion_create_like(src, GB_F32), *psi_f = fermion_create_like(src, GB_F32), *p_f = fermion_create_like(src, GB_F32),
+             *mmp_f = fermion_create_like(src, GB_F32);
+  struct Guard { gb_fermion *f[7]; ~Guard() { for (auto *x : f) gb_fermion_destroy(x); } } guard{{p, mmp, r, r_f, psi_f, p_f, mmp_f}};
+  int its[3] = {0, 0, 0};
+  double true_resid = 0, cp, c, a, d, b, ssq, dd[2];
+  auto finish = [&](bool converged) {
+    if (iters_out) for (int i = 0; i < 3; i++) iters_out[i] = its[i];
+    if (true_resid_out) *true_resid_out = true_resid;
+    if (!converged) throw Error(GB_ERR_NOT_CONVERGED, "ConjugateGradientReliableUpdate did NOT converge");
+  };
+  Ad(psi, mmp);
+  chk(gb_axpy(r, -1.0, mmp, src));            // r = src - mmp
+  chk(gb_copy(p, r));
+  chk(gb_norm2(p, &a)); cp = a;
+  chk(gb_norm2(src, &ssq));
+  const double rsq = tol * tol * ssq;
+  if (cp <= rsq) { true_resid = std::sqrt(cp / ssq); finish(true); return GB_OK; }   // "guess was REALLY good" (ref :121-125)
+  chk(gb_precision_change(r_f, r));
+  chk(gb_zero(psi_f)); psi_f->cb = src->cb;
+  chk(gb_copy(p_f, r_f));
+  double MaxResidSinceLastRelUp = cp;
+  int k, l = 0;
+  for (k = 1; k <= maxit; k++) {
+    c = cp;
+    Af(p_f, mmp_f);
+    chk(gb_inner_product(p_f, mmp_f, dd)); d = dd[0];
+    a = c / d;
+    chk(gb_axpy_norm(r_f, -a, mmp_f, r_f, &cp));
+    GB_REQUIRE(!std::isnan(cp), "ConjugateGradientReliableUpdate: residual is NaN");
+    b = cp / c;
+    chk(gb_axpy(psi_f, a, p_f, psi_f));
+    if (cp > MaxResidSinceLastRelUp) MaxResidSinceLastRelUp = cp;
+    if (cp <= rsq) {
+      chk(gb_precision_change(mmp, psi_f));
+      chk(gb_axpy(psi, 1.0, mmp, psi));
+      Ad(psi, mmp);
+      double rn;
+      chk(gb_axpy_norm(p, -1.0, src, mmp, &rn));          // p = mmp - src
+      true_resid = std::sqrt(rn) / std::sqrt(ssq);
+      its[0] = k; its[1] = l;
+      CGOut fin = cg_schur_device_scalars(op_d, src, psi, tol, maxit);   // DoFinalCleanup (ref :190-197)
+      its[2] = fin.iters;
+      if (fin.iters > 0) true_resid = fin.true_resid;
+      finish(fin.converged);
+      return GB_OK;
+    } else if (cp < Delta * MaxResidSinceLastRelUp) {    // reliable update (ref :203-228)
+      chk(gb_precision_change(mmp, psi_f));
+      chk(gb_axpy(psi, 1.0, mmp, psi));
+      Ad(psi, mmp);
+      chk(gb_axpy_norm(r, -1.0, mmp, src, &cp));          // r = src - mmp ; cp = |r|^2
+      chk(gb_zero(psi_f));
+      chk(gb_precision_change(r_f, r));
+      MaxResidSinceLastRelUp = cp;
+      b = cp / c;
+      l++;
+    }
+    chk(gb_axpby(p_f, b, 1.0, p_f, r_f));                 // p_f = b p_f + r_f (after the update: ref :230)
+  }
+  its[0] = k; its[1] = l;
+  finish(false);
+  GB_API_END
+}
+
 int gb_cg_schur(gb_fermop *op, const gb_fermion *src, gb_fermion *sol, double tol, int maxit, int *iters_out, double *true_resid_out) {
   GB_API_BEGIN
   GB_REQUIRE(op && src && sol, "null argument");

@@ -252,6 +252,12 @@ int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d,
                       int max_outer, int iters_out[3], double *true_resid_out);
 
 
+/* ConjugateGradientReliableUpdate(tol, maxit, Delta, sp_grid, Linop_f, Linop_d)(src, psi) on the Schur operators of op_f (fp32)
+ * and op_d (fp64); psi is the initial guess.  iters_out[3] = {IterationsToComplete, ReliableUpdatesPerformed, IterationsToCleanup}.
+ * ref: Grid/algorithms/iterative/ConjugateGradientReliableUpdate.h:36-270 ; driver tests/solver/Test_dwf_relupcg_prec.cc:88-104 */
+int gb_relup_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d, gb_fermion *sol_d, double tol, int maxit, double delta,
+                      int iters_out[3], double *true_resid_out);
+
 /* ConjugateGradientMultiShift on SchurDiagMooeeOperator(op).HermOp (staggered: SchurStaggeredOperator), SURVEY 8 row f3:
  * (HermOp + poles[s]) results[s] = src for s < nshift from one Krylov space; zero guess; poles[0] must be the lightest;
  * shift s stops when its residual estimate drops below tolerances[s] |src|.

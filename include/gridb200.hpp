@@ -329,6 +329,34 @@ public:
 };
 
 
+// ---- ConjugateGradientReliableUpdate (ref: Grid/algorithms/iterative/ConjugateGradientReliableUpdate.h:36-270)
+template <class FieldD, class FieldF> class ConjugateGradientReliableUpdate {
+public:
+  bool ErrorOnNoConverge;
+  RealD Tolerance;
+  Integer MaxIterations;
+  Integer IterationsToComplete = 0, ReliableUpdatesPerformed = 0, IterationsToCleanup = 0;
+  RealD TrueResidual = 0;
+  LinearOperatorBase<FieldF> &Linop_f;
+  LinearOperatorBase<FieldD> &Linop_d;
+  GridBase *SinglePrecGrid;
+  RealD Delta;
+  ConjugateGradientReliableUpdate(RealD tol, Integer maxit, RealD _delta, GridBase *_sp_grid, LinearOperatorBase<FieldF> &_Linop_f,
+                                  LinearOperatorBase<FieldD> &_Linop_d, bool err_on_no_conv = true)
+      : ErrorOnNoConverge(err_on_no_conv), Tolerance(tol), MaxIterations(maxit), Linop_f(_Linop_f), Linop_d(_Linop_d), SinglePrecGrid(_sp_grid), Delta(_delta) {
+    assert(Delta > 0. && Delta < 1. && "Expect  0 < Delta < 1");
+  }
+  void operator()(const FieldD &src, FieldD &psi) {
+    gb_fermop *mf = Linop_f.FusedSchurMatrix(), *md = Linop_d.FusedSchurMatrix();
+    assert(mf && md && "ConjugateGradientReliableUpdate needs SchurDiagMooeeOperator arguments");
+    int it[3];
+    int rc = gb_relup_cg_schur(mf, md, src.h, psi.h, Tolerance, MaxIterations, Delta, it, &TrueResidual);
+    IterationsToComplete = it[0]; ReliableUpdatesPerformed = it[1]; IterationsToCleanup = it[2];
+    if (rc == GB_ERR_NOT_CONVERGED) { if (ErrorOnNoConverge) assert(0 && "ConjugateGradientReliableUpdate did NOT converge"); return; }
+    GB_ASSERT_OK(rc);
+  }
+};
+
 // ---- ConjugateGradientMultiShift (ref: Grid/algorithms/approx/MultiShiftFunction.h:34-44 ; iterative/ConjugateGradientMultiShift.h:40-343)
 class MultiShiftFunction {
 public:

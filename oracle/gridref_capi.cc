@@ -434,6 +434,31 @@ void gref_mixed_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d,
   export_lex(x, sol_d);
 }
 
+// ConjugateGradientReliableUpdate as tests/solver/Test_dwf_relupcg_prec.cc:88-104 sets it up.
+// out_iters: [IterationsToComplete, ReliableUpdatesPerformed, IterationsToCleanup, converged]
+void gref_relup_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d, double tol, int maxit, double delta, int *out_iters, double *out_true_resid) {
+  auto *bd = dynamic_cast<WilsonBox<WilsonImplD, vComplexD> *>((BoxBase *)h_d);
+  auto *bf = dynamic_cast<WilsonBox<WilsonImplF, vComplexF> *>((BoxBase *)h_f);
+  assert(bd && bf);
+  typedef FermionOperator<WilsonImplD> OpD;
+  typedef FermionOperator<WilsonImplF> OpF;
+  SchurDiagMooeeOperator<OpD, LatticeFermionD> Sd(*bd->op);
+  SchurDiagMooeeOperator<OpF, LatticeFermionF> Sf(*bf->op);
+  LatticeFermionD s(bd->frbgrid()), x(bd->frbgrid());
+  import_lex(s, src_d); import_lex(x, sol_d);
+  s.Checkerboard() = cb; x.Checkerboard() = cb;
+  ConjugateGradientReliableUpdate<LatticeFermionD, LatticeFermionF> mCG(tol, maxit, delta, bf->frbgrid(), Sf, Sd, false);
+  mCG.IterationsToCleanup = 0;
+  mCG(s, x);
+  out_iters[0] = mCG.IterationsToComplete; out_iters[1] = mCG.ReliableUpdatesPerformed; out_iters[2] = mCG.IterationsToCleanup; out_iters[3] = 1;
+  // the true residual, recomputed here (the class only logs it)
+  LatticeFermionD mmp(bd->frbgrid());
+  Sd.HermOp(x, mmp);
+  mmp = mmp - s;
+  *out_true_resid = std::sqrt(norm2(mmp) / norm2(s));
+  export_lex(x, sol_d);
+}
+
 // Timed loop for the CPU baseline: fields stay resident in Grid's own layout; returns seconds for ncall applications.
 double gref_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
   BoxBase *b = (BoxBase *)h;

@@ -192,6 +192,13 @@ void orc_schur_solve(void *h, const void *src, void *sol, double tol, int maxit,
                               : SchurRedBlackDiagMooeeSolve(box->d, (const Spinor<double> *)src, (Spinor<double> *)sol, tol, maxit, out_resid + 1);
   out_iters[0] = r.iterations; out_iters[1] = r.converged; out_resid[0] = r.true_residual;
 }
+// ConjugateGradientReliableUpdate.  out_iters: [IterationsToComplete, ReliableUpdatesPerformed, IterationsToCleanup, converged]
+void orc_relup_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d, double tol, int maxit, double delta, int *out_iters, double *out_true_resid) {
+  OpBox *bd = (OpBox *)h_d, *bf = (OpBox *)h_f;
+  RelUpResult r = ReliableUpdateCG(bd->d, bf->f, cb, (const Spinor<double> *)src_d, (Spinor<double> *)sol_d, tol, maxit, delta);
+  out_iters[0] = r.iterations; out_iters[1] = r.reliable_updates; out_iters[2] = r.cleanup_iterations; out_iters[3] = r.converged;
+  *out_true_resid = r.true_residual;
+}
 // out_iters: [inner, outer, final, converged]
 void orc_mixed_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d, double tol, int maxinner, int maxouter,
                   int *out_iters, double *out_true_resid) {

@@ -52,6 +52,7 @@ def lib():
         L.orc_redblack_solution.argtypes = [C.c_void_p] * 4
         L.orc_schur_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_relup_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_time_apply.restype = C.c_double
@@ -359,3 +360,13 @@ def inner_product(l, r):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def relup_cg(op_d, op_f, cb, src_d, tol, maxit, delta):
+    """ConjugateGradientReliableUpdate(tol, maxit, delta, ..., Linop_f, Linop_d)(src, sol) with a zero guess."""
+    src = np.ascontiguousarray(src_d, dtype=np.complex128)
+    sol = np.zeros_like(src)
+    it = np.zeros(4, dtype=np.int32)
+    tr = np.zeros(1, dtype=np.float64)
+    lib().orc_relup_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxit, delta, _ptr(it), _ptr(tr))
+    return sol, dict(iterations=int(it[0]), reliable_updates=int(it[1]), cleanup_iterations=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))

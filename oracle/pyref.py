@@ -54,6 +54,7 @@ def lib():
         L.gref_redblack_solution.argtypes = [C.c_void_p] * 4
         L.gref_schur_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_relup_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.gref_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.gref_time_apply.restype = C.c_double
@@ -234,3 +235,13 @@ def mixed_cg(op_d, op_f, cb, src_d, tol, maxinner, maxouter):
     tr = np.zeros(1, dtype=np.float64)
     lib().gref_mixed_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxinner, maxouter, _ptr(it), _ptr(tr))
     return sol, dict(inner=int(it[0]), outer=int(it[1]), final=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))
+
+
+def relup_cg(op_d, op_f, cb, src_d, tol, maxit, delta):
+    """ConjugateGradientReliableUpdate(tol, maxit, delta, ..., Linop_f, Linop_d)(src, sol) with a zero guess."""
+    src = np.ascontiguousarray(src_d, dtype=np.complex128)
+    sol = np.zeros_like(src)
+    it = np.zeros(4, dtype=np.int32)
+    tr = np.zeros(1, dtype=np.float64)
+    lib().gref_relup_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxit, delta, _ptr(it), _ptr(tr))
+    return sol, dict(iterations=int(it[0]), reliable_updates=int(it[1]), cleanup_iterations=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))

@@ -114,4 +114,65 @@ MultiShiftResult MultiShiftCG(HermOpFn &&A, int64_t n, const F *src, std::vector
   return R;
 }
 
+// ConjugateGradientReliableUpdate   ref: Grid/algorithms/iterative/ConjugateGradientReliableUpdate.h:80-270
+// fp32 CG iteration on (r_f, p_f, psi_f); whenever the residual has dropped by Delta relative to its maximum since the last
+// update, psi += psi_f in fp64, the true residual is recomputed with the fp64 operator and the fp32 iteration restarts from
+// it (keeping the search direction).  On convergence: final accumulation, true residual, then a fp64 clean-up CG.
+struct RelUpResult { int iterations = 0, reliable_updates = 0, cleanup_iterations = 0; double true_residual = 0; int converged = 0; };
+inline RelUpResult ReliableUpdateCG(const FermOp<double> &op_d, const FermOp<float> &op_f, int cb, const Spinor<double> *src, Spinor<double> *psi,
+                                    double tol, int maxit, double Delta) {
+  const int64_t n = op_d.V5cb();
+  RelUpResult R;
+  std::vector<Spinor<double>> p(n), mmp(n), r(n);
+  double cp, c, a, d, b, ssq;
+  op_d.HermOp(psi, mmp.data(), cb);
+  axpy(n, r.data(), -1.0, mmp.data(), src);               // r = src - mmp
+  p = r;
+  a = norm2(n, p.data()); cp = a; ssq = norm2(n, src);
+  const double rsq = tol * tol * ssq;
+  if (cp <= rsq) { R.converged = 1; R.true_residual = std::sqrt(cp / ssq); return R; }
+  std::vector<Spinor<float>> r_f(n), psi_f(n), p_f(n), mmp_f(n);
+  precisionChange(n, r_f.data(), r.data());
+  std::memset((void *)psi_f.data(), 0, sizeof(Spinor<float>) * n);
+  p_f = r_f;
+  double MaxResidSinceLastRelUp = cp;
+  int k, l = 0;
+  for (k = 1; k <= maxit; k++) {
+    c = cp;
+    op_f.HermOp(p_f.data(), mmp_f.data(), cb);
+    d = innerProduct(n, p_f.data(), mmp_f.data()).re;
+    a = c / d;
+    cp = axpy_norm(n, r_f.data(), (float)(-a), mmp_f.data(), r_f.data());
+    b = cp / c;
+    axpy(n, psi_f.data(), (float)a, p_f.data(), psi_f.data());
+    if (cp > MaxResidSinceLastRelUp) MaxResidSinceLastRelUp = cp;
+    if (cp <= rsq) {
+      precisionChange(n, mmp.data(), psi_f.data());
+      axpy(n, psi, 1.0, mmp.data(), psi);
+      op_d.HermOp(psi, mmp.data(), cb);
+      axpy(n, p.data(), -1.0, src, mmp.data());
+      R.true_residual = std::sqrt(norm2(n, p.data())) / std::sqrt(ssq);
+      R.iterations = k; R.reliable_updates = l;
+      CGResult fin = ConjugateGradient(op_d, cb, src, psi, tol, maxit);   // DoFinalCleanup
+      R.cleanup_iterations = fin.iterations; R.converged = fin.converged;
+      if (fin.iterations > 0) R.true_residual = fin.true_residual;
+      return R;
+    } else if (cp < Delta * MaxResidSinceLastRelUp) {
+      precisionChange(n, mmp.data(), psi_f.data());
+      axpy(n, psi, 1.0, mmp.data(), psi);
+      op_d.HermOp(psi, mmp.data(), cb);
+      axpy(n, r.data(), -1.0, mmp.data(), src);
+      std::memset((void *)psi_f.data(), 0, sizeof(Spinor<float>) * n);
+      precisionChange(n, r_f.data(), r.data());
+      cp = norm2(n, r.data());
+      MaxResidSinceLastRelUp = cp;
+      b = cp / c;
+      l++;
+    }
+    axpby(n, p_f.data(), (float)b, 1.0f, p_f.data(), r_f.data());        // p_f = b p_f + r_f
+  }
+  R.iterations = k; R.reliable_updates = l; R.converged = 0;
+  return R;
+}
+
 } // namespace oracle

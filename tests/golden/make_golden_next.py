@@ -76,6 +76,13 @@ def main():
         out[f"{name}/schur_solve/solution"] = x
         for k in ("iterations", "true_residual", "unprec_residual"):
             out[f"{name}/schur_solve/{k}"] = np.array(info[k])
+    # Row f3, ConjugateGradientReliableUpdate (ref: ConjugateGradientReliableUpdate.h:80-270; Test_dwf_relupcg_prec.cc:88-104): Delta = 0.1
+    opf = pr.RefOp(1, DIMS, LS, 0.1, 1.8, 1.5, 0.5, prec=0)
+    opf.import_gauge(U)
+    x, info = pr.relup_cg(ops["mobius"][0], opf, 1, ops["mobius"][0].pick_checkerboard(1, src5), 1e-8, 5000, 0.1)
+    out["mobius/relup_cg/solution"] = x
+    for k in ("iterations", "reliable_updates", "cleanup_iterations", "true_residual"):
+        out[f"mobius/relup_cg/{k}"] = np.array(info[k])
     path = os.path.join(HERE, "next_golden.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB", file=sys.stderr)
