@@ -100,3 +100,52 @@ def test_face_exchange_pattern_world2_gloo(mpi, gdims):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _naik_worker(rank, world, port, mpi, gdims, q):
+    """Three-deep halos of the improved staggered operator (grid_b200/csrc/stag.cu: stag_exchange): my slices 0..2 fill the
+    BACKWARD neighbour's forward halo (its x_mu = L..L+2), my slices L-3..L-1 the FORWARD neighbour's backward halo
+    (its x_mu = -3..-1).  With the slabs attached, every +-1 and +-3 neighbour of every local site is the global periodic one."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ld, origin, nbr = gb.geometry_query(gdims, mpi, rank)
+        enc = encode(gdims)
+        loc = decomp.scatter(enc, gdims, mpi, rank).reshape(ld[3], ld[2], ld[1], ld[0], 4)
+        ok = True
+        for mu in range(4):
+            ax = 3 - mu
+            if mpi[mu] == 1:      # undecomposed: periodic wrap inside the local volume
+                ext = np.concatenate([np.take(loc, range(ld[mu] - 3, ld[mu]), axis=ax), loc, np.take(loc, range(0, 3), axis=ax)], axis=ax)
+            else:
+                first = np.ascontiguousarray(np.take(loc, range(0, 3), axis=ax))               # halo dir 0 of my backward neighbour
+                last = np.ascontiguousarray(np.take(loc, range(ld[mu] - 3, ld[mu]), axis=ax))   # halo dir 1 of my forward neighbour
+                fwd, bwd = nbr[mu]
+                recv_f, recv_b = torch.empty_like(torch.from_numpy(first)), torch.empty_like(torch.from_numpy(last))
+                ops = [dist.P2POp(dist.isend, torch.from_numpy(first), bwd), dist.P2POp(dist.irecv, recv_f, fwd),
+                       dist.P2POp(dist.isend, torch.from_numpy(last), fwd), dist.P2POp(dist.irecv, recv_b, bwd)]
+                for r in dist.batch_isend_irecv(ops):
+                    r.wait()
+                ext = np.concatenate([recv_b.numpy(), loc, recv_f.numpy()], axis=ax)
+            for disp in (1, -1, 3, -3):
+                got = np.take(ext, range(3 + disp, 3 + disp + ld[mu]), axis=ax)
+                want = loc.copy(); want[..., mu] = (want[..., mu] + disp) % gdims[mu]
+                ok = ok and np.array_equal(got, want)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mpi,gdims", [((1, 1, 1, 2), (4, 4, 4, 8)), ((2, 1, 1, 1), (8, 4, 4, 4)), ((1, 2, 1, 1), (4, 12, 4, 4))])
+def test_naik_three_deep_halo_pattern_world2_gloo(mpi, gdims):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29810 + (hash((mpi, gdims)) % 150)
+    procs = [ctx.Process(target=_naik_worker, args=(r, 2, port, mpi, gdims, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
