@@ -197,10 +197,10 @@ __global__ void stag_double_store_kernel(T *links, size_t parity_stride /* scala
 // (undecomposed dimension whose halos are forced on, see GB_STAG_SELF_HALO) is a device-to-device copy, like the reference's
 // comms-to-self path (ref: Grid/communicator/Communicator_none.cc SendToRecvFrom, Cshift_common.h local branch).
 struct HaloMsg { const void *send; void *recv; size_t bytes; int to, from; };
-static void stag_sendrecv(gb_context *ctx, const std::vector<HaloMsg> &msgs) {
+static void stag_sendrecv(gb_context *ctx, const std::vector<HaloMsg> &msgs, cudaStream_t st) {
   bool remote = false;
   for (const HaloMsg &m : msgs) {
-    if (m.to == ctx->rank && m.from == ctx->rank) GB_CUDA(cudaMemcpyAsync(m.recv, m.send, m.bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (m.to == ctx->rank && m.from == ctx->rank) GB_CUDA(cudaMemcpyAsync(m.recv, m.send, m.bytes, cudaMemcpyDeviceToDevice, st));
     else remote = true;
   }
   if (!remote) return;
@@ -208,8 +208,8 @@ static void stag_sendrecv(gb_context *ctx, const std::vector<HaloMsg> &msgs) {
   NcclApi &N = nccl();
   nccl_check(N.GroupStart(), "ncclGroupStart");
   for (const HaloMsg &m : msgs) if (!(m.to == ctx->rank && m.from == ctx->rank)) {
-    nccl_check(N.Send(m.send, m.bytes, ncclChar, m.to, ctx->nccl, ctx->stream), "ncclSend");
-    nccl_check(N.Recv(m.recv, m.bytes, ncclChar, m.from, ctx->nccl, ctx->stream), "ncclRecv");
+    nccl_check(N.Send(m.send, m.bytes, ncclChar, m.to, ctx->nccl, st), "ncclSend");
+    nccl_check(N.Recv(m.recv, m.bytes, ncclChar, m.from, ctx->nccl, st), "ncclRecv");
   }
   nccl_check(N.GroupEnd(), "ncclGroupEnd");
 }
@@ -270,7 +270,7 @@ void stag_import_gauge(gb_fermop *op, const gb_gauge *Uthin, const gb_gauge *Ufa
         msgs.push_back({gsend[which][mu][1], grecv[which][mu][1], bytes, g->nbr_rank[mu][0], g->nbr_rank[mu][1]});
       }
     }
-    stag_sendrecv(ctx, msgs);
+    stag_sendrecv(ctx, msgs, ctx->stream);
   }
   const int64_t n = g->V4cb * 2 * 4;
   const unsigned blocks = (unsigned)((n + 127) / 128);
@@ -357,6 +357,8 @@ __global__ void stag_pack_kernel(const typename CT<T>::c *__restrict__ in, typen
   for (int c = 0; c < 3; c++) buf[cv_index(i, c)] = __ldg(in + cv_index(site, c));
 }
 
+// COMM 0: one rank, periodic wrap.  COMM 1: every site, halo lookups (serial comms).  COMM 2 / 3: the interior / exterior sites
+// only (overlapped comms: COMM 2 runs while the faces travel and touches no halo, COMM 3 after they have arrived).
 template <class T, int DAG, int AX, int COMM>
 __global__ void __launch_bounds__(128) stag_dhop_kernel(const StagArgs<T> a) {
   const StagGeom &G = a.G;
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(128) stag_dhop_kernel(const StagArgs<T> a) {
   if (site >= G.V4cb) return;
   int c[4];
   stag_coor(G, p, site, c[0], c[1], c[2], c[3]);
+  if (COMM >= 2 && stag_is_exterior(G, a.comm_dim_mask, c) != (COMM == 3)) return;
   const typename CT<T>::c *__restrict__ in = a.in[1 - p];
   const typename CT<T>::lv *__restrict__ rec = a.U[p] + (size_t)(site >> SLOG) * CT<T>::LVN * SW + (site & (SW - 1));
   CV<T> o;
@@ -424,10 +427,9 @@ static void stag_ensure_halo(gb_fermop *op) {
 // (replaces CartesianStencil::HaloExchange for the 16-point staggered stencil, ref: Grid/stencil/Stencil.h:367-430,
 //  ImprovedStaggeredFermionImplementation.h:337-388 DhopInternalSerialComms)
 template <class T>
-static void stag_exchange(gb_fermop *op, const void *const in[2], int first_parity, int nparity) {
+static void stag_pack(gb_fermop *op, const void *const in[2], int first_parity, int nparity) {
   gb_context *ctx = op->ctx;
   const gb_grid *g = op->grid;
-  stag_ensure_halo(op);
   StagGeom G = stag_geom(g);
   using C = typename CT<T>::c;
   // input parities: the opposite of each output parity
@@ -445,6 +447,13 @@ static void stag_exchange(gb_fermop *op, const void *const in[2], int first_pari
     }
   }
   check_launch(ctx, "stag_pack");
+}
+template <class T>
+static void stag_exchange_packed(gb_fermop *op, int first_parity, int nparity, cudaStream_t st) {
+  gb_context *ctx = op->ctx;
+  const gb_grid *g = op->grid;
+  using C = typename CT<T>::c;
+  const int ip0 = 1 - first_parity;
   std::vector<HaloMsg> msgs;
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
     const size_t stride = op->halo_parity_stride[mu] * sizeof(C);
@@ -453,7 +462,7 @@ static void stag_exchange(gb_fermop *op, const void *const in[2], int first_pari
     msgs.push_back({(const char *)op->halo_send[mu] + off, (char *)op->halo_recv[mu] + off, bytes, g->nbr_rank[mu][1], g->nbr_rank[mu][0]});
     msgs.push_back({(const char *)op->halo_send[mu + 4] + off, (char *)op->halo_recv[mu + 4] + off, bytes, g->nbr_rank[mu][0], g->nbr_rank[mu][1]});
   }
-  stag_sendrecv(ctx, msgs);
+  stag_sendrecv(ctx, msgs, st);
 }
 
 // in[p]/out[p]: parity blocks.  Output parities first_parity (and the other one when nparity == 2).
@@ -470,20 +479,35 @@ static void stag_launch(gb_fermop *op, const void *const in[2], void *const out[
   a.comm_dim_mask = op->comm_dim_mask;
   for (int i = 0; i < 8; i++) a.halo[i] = nullptr;
   for (int mu = 0; mu < 4; mu++) a.halo_parity_stride[mu] = 0;
-  if (op->comm_dim_mask) {   // serial comms: pack the boundary slices of the input parities, exchange, then hop (ref: DhopInternalSerialComms)
-    stag_exchange<T>(op, in, first_parity, nparity);
-    for (int i = 0; i < 8; i++) a.halo[i] = (const typename CT<T>::c *)op->halo_recv[i];
-    for (int mu = 0; mu < 4; mu++) a.halo_parity_stride[mu] = op->halo_parity_stride[mu];
-  }
   dim3 grid((unsigned)((op->grid->V4cb + 127) / 128), nparity);
 #define GB_SK(D, A, C) stag_dhop_kernel<T, D, A, C><<<grid, 128, 0, ctx->stream>>>(a)
+#define GB_SKC(C) do { if (ax) { if (dag) GB_SK(1, 1, C); else GB_SK(0, 1, C); } else { if (dag) GB_SK(1, 0, C); else GB_SK(0, 0, C); } } while (0)
   if (op->comm_dim_mask) {
-    if (ax) { if (dag) GB_SK(1, 1, 1); else GB_SK(0, 1, 1); }
-    else { if (dag) GB_SK(1, 0, 1); else GB_SK(0, 0, 1); }
+    stag_ensure_halo(op);
+    for (int i = 0; i < 8; i++) a.halo[i] = (const typename CT<T>::c *)op->halo_recv[i];
+    for (int mu = 0; mu < 4; mu++) a.halo_parity_stride[mu] = op->halo_parity_stride[mu];
+    if (op->overlap_comms) {
+      // pack on the compute stream, exchange on the comm stream while the interior sites are computed, then the exterior
+      // sites (ref: ImprovedStaggeredFermion::DhopInternalOverlappedComms, ImprovedStaggeredFermionImplementation.h:283-335)
+      stag_pack<T>(op, in, first_parity, nparity);
+      GB_CUDA(cudaEventRecord(ctx->ev_comp, ctx->stream));
+      GB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comp, 0));
+      stag_exchange_packed<T>(op, first_parity, nparity, ctx->comm_stream);
+      GB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+      GB_SKC(2);
+      count_launch(ctx);
+      GB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0));
+      GB_SKC(3);
+    } else {   // serial comms (ref: DhopInternalSerialComms, :337-388)
+      stag_pack<T>(op, in, first_parity, nparity);
+      stag_exchange_packed<T>(op, first_parity, nparity, ctx->stream);
+      GB_SKC(1);
+    }
   } else {
     if (ax) { if (dag) GB_SK(1, 1, 0); else GB_SK(0, 1, 0); }
     else { if (dag) GB_SK(1, 0, 0); else GB_SK(0, 0, 0); }
   }
+#undef GB_SKC
 #undef GB_SK
   count_launch(ctx);
   check_launch(ctx, "stag_dhop");

@@ -93,6 +93,16 @@ GB_HD int stag_neighbour(const StagGeom &G, int comm_dim_mask, const int c[4], i
   return -1;
 }
 
+// A site is "exterior" when at least one of its 16 neighbours lives in a halo: within STAG_DEPTH of a decomposed boundary.
+// The overlapped hop computes the other ("interior") sites while the faces travel (ref: the interior / exterior split of
+// ImprovedStaggeredFermion::DhopInternalOverlappedComms, ImprovedStaggeredFermionImplementation.h:283-335).
+GB_HD bool stag_is_exterior(const StagGeom &G, int comm_dim_mask, const int c[4]) {
+  bool ext = false;
+  for (int mu = 0; mu < 4; mu++)
+    if (((comm_dim_mask >> mu) & 1) && (c[mu] < STAG_DEPTH || c[mu] >= G.L[mu] - STAG_DEPTH)) ext = true;
+  return ext;
+}
+
 // ---- gauge halos for the double store.  Links stay lexicographic; only U_mu is needed beyond the mu faces.
 // One buffer per (mu, dir): [depth][lexicographic face, dimension mu removed][18 reals];
 //   dir 0: slices 0..2 of the forward neighbour (x_mu = L + depth), dir 1: slices L-3..L-1 of the backward one (x_mu = depth - 3)

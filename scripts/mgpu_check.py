@@ -123,9 +123,12 @@ for mpi in (MPIS if os.environ.get("MGPU_SKIP_STAG") is None else []):
         def stag_err(got, ref):   # relative to the rms site norm: single sites of a hop can cancel to ~0
             d = np.linalg.norm(got.astype(np.complex128) - ref, axis=1); nb = np.linalg.norm(ref, axis=1)
             return float(np.max(d / np.maximum(nb, np.sqrt(np.mean(nb ** 2)))))
-        for dag in (0, 1):
-            D.Dhop(fin, out, dag)
-            check(f"mpi {mpi} staggered prec{prec} Dhop dag{dag}", stag_err(out.export_lex(), decomp.scatter(orc.apply(po.OP_DHOP, src, dag=dag), gdims, mpi, rank)), tol)
+        for overlap in (True, False):
+            D.set_overlap(overlap)
+            for dag in (0, 1):
+                D.Dhop(fin, out, dag)
+                check(f"mpi {mpi} staggered prec{prec} overlap{int(overlap)} Dhop dag{dag}", stag_err(out.export_lex(), decomp.scatter(orc.apply(po.OP_DHOP, src, dag=dag), gdims, mpi, rank)), tol)
+        D.set_overlap(True)
         D.M(fin, out)
         check(f"mpi {mpi} staggered prec{prec} M", stag_err(out.export_lex(), decomp.scatter(orc.apply(po.OP_M, src), gdims, mpi, rank)), tol)
         he, ho = gb.LatticeStaggeredFermion(grid, 1, prec, gb.HALF), gb.LatticeStaggeredFermion(grid, 1, prec, gb.HALF)

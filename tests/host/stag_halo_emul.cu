@@ -102,6 +102,10 @@ int main(int argc, char **argv) {
     const Rank &k = R[r]; const StagGeom &G = k.G;
     for (int p = 0; p < 2; p++) for (uint32_t s = 0; s < (uint32_t)G.V4cb; s++) {
       int c[4]; stag_coor(G, p, s, c[0], c[1], c[2], c[3]);
+      bool any_halo = false;
+      for (int mu = 0; mu < 4; mu++) for (int di = 0; di < 4; di++) { uint32_t idx; if (stag_neighbour(G, mask, c, mu, disps[di], idx) >= 0) any_halo = true; }
+      checked++;
+      if (any_halo != stag_is_exterior(G, mask, c)) { if (bad++ < 5) std::fprintf(stderr, "exterior flag: rank %d p %d site %u\n", r, p, s); }
       for (int mu = 0; mu < 4; mu++) for (int di = 0; di < 4; di++) {
         uint32_t idx;
         const int where = stag_neighbour(G, mask, c, mu, disps[di], idx);

@@ -52,11 +52,14 @@ def test_self_halo_path_matches_oracle_and_plain_kernel(mask, prec_name):
     Dh, Dp = make_op(gb, grid, U, prec, mask), make_op(gb, grid, U, prec, 0)
     fin = gb.LatticeStaggeredFermion(grid, 1, prec).import_lex(src)
     oh, op_ = gb.LatticeStaggeredFermion(grid, 1, prec), gb.LatticeStaggeredFermion(grid, 1, prec)
-    for dag in (0, 1):
-        Dh.Dhop(fin, oh, dag); Dp.Dhop(fin, op_, dag)
-        got = oh.export_lex()
-        assert stag_err(got, orc.apply(po.OP_DHOP, src.astype(np.complex128), dag=dag)) < tol, (mask, dag)
-        assert np.array_equal(got, op_.export_lex()), (mask, dag)
+    for overlap in (True, False):          # interior || exchange, then exterior  vs  exchange, then one kernel
+        Dh.set_overlap(overlap)
+        for dag in (0, 1):
+            Dh.Dhop(fin, oh, dag); Dp.Dhop(fin, op_, dag)
+            got = oh.export_lex()
+            assert stag_err(got, orc.apply(po.OP_DHOP, src.astype(np.complex128), dag=dag)) < tol, (mask, dag, overlap)
+            assert np.array_equal(got, op_.export_lex()), (mask, dag, overlap)
+    Dh.set_overlap(True)
     Dh.M(fin, oh); Dp.M(fin, op_)
     assert np.array_equal(oh.export_lex(), op_.export_lex())
     assert stag_err(oh.export_lex(), orc.apply(po.OP_M, src.astype(np.complex128))) < tol
