@@ -47,6 +47,8 @@ SYMBOLS = [
     ("gb_inner_product", _i, [_vp, _vp, _pd]),
     ("gb_gauge_create", _i, [_vp, _i, _pvp]), ("gb_gauge_destroy", _i, [_vp]), ("gb_gauge_import", _i, [_vp, _vp, _i]),
     ("gb_gauge_export", _i, [_vp, _vp, _i]), ("gb_gauge_random", _i, [_vp, _u64]), ("gb_gauge_unit", _i, [_vp]),
+    ("gb_nersc_read_host", _i, [C.c_char_p, _vp, _vp]), ("gb_nersc_write_host", _i, [C.c_char_p, _vp, _pi, _i, C.c_char_p, C.c_char_p, _i]),
+    ("gb_gauge_read_nersc", _i, [_vp, C.c_char_p, _vp]), ("gb_gauge_write_nersc", _i, [_vp, C.c_char_p, _i, C.c_char_p, C.c_char_p, _i]),
     ("gb_op_create_wilson", _i, [_vp, _vp, _d, _pd, _pvp]), ("gb_op_create_dwf", _i, [_vp, _vp, _i, _d, _d, _pd, _pvp]),
     ("gb_op_create_mobius", _i, [_vp, _vp, _i, _d, _d, _d, _d, _pd, _pvp]), ("gb_op_import_gauge", _i, [_vp, _vp]),
     ("gb_op_create_staggered", _i, [_vp, _vp, _vp, _d, _d, _d, _d, _pvp]), ("gb_op_import_gauge_staggered", _i, [_vp, _vp, _vp]),
@@ -334,6 +336,48 @@ class LatticeGaugeField:
     def unit(self):
         _chk(lib().gb_gauge_unit(self.h))
         return self
+
+
+class NerscHeader(C.Structure):
+    """gb_nersc_header (include/gridb200.h): FieldMetaData of a NERSC configuration (ref: Grid/parallelIO/MetaData.h:60-97)"""
+    _fields_ = [("dimension", C.c_int * 4), ("link_trace", C.c_double), ("plaquette", C.c_double), ("checksum", C.c_uint32),
+                ("data_type", C.c_char * 64), ("floating_point", C.c_char * 32), ("ensemble_id", C.c_char * 64), ("ensemble_label", C.c_char * 64),
+                ("sequence_number", C.c_int), ("data_start", C.c_int64), ("computed_link_trace", C.c_double), ("computed_plaquette", C.c_double),
+                ("computed_checksum", C.c_uint32)]
+
+
+class NerscIO:
+    """ref: Grid/parallelIO/NerscIO.h:43-290.  readConfiguration / writeConfiguration on device gauge fields; the *_host variants
+    work on a global lexicographic [V,4,3,3] complex128 array and need no GPU."""
+
+    @staticmethod
+    def readHeader(path):
+        h = NerscHeader()
+        _chk(lib().gb_nersc_read_host(str(path).encode(), None, C.byref(h)))
+        return h
+
+    @staticmethod
+    def read_host(path):
+        h = NerscIO.readHeader(path)
+        U = np.empty((int(np.prod(list(h.dimension))), 4, 3, 3), dtype=np.complex128)
+        _chk(lib().gb_nersc_read_host(str(path).encode(), U.ctypes.data_as(C.c_void_p), C.byref(h)))
+        return U, h
+
+    @staticmethod
+    def write_host(path, U, dims, two_row=0, ens_label="DWF", ens_id="UKQCD", sequence_number=1):
+        U = np.ascontiguousarray(U, dtype=np.complex128)
+        assert U.shape == (int(np.prod(dims)), 4, 3, 3)
+        _chk(lib().gb_nersc_write_host(str(path).encode(), U.ctypes.data_as(C.c_void_p), _i4(dims), two_row, ens_label.encode(), ens_id.encode(), sequence_number))
+
+    @staticmethod
+    def readConfiguration(Umu, path):
+        h = NerscHeader()
+        _chk(lib().gb_gauge_read_nersc(Umu.h, str(path).encode(), C.byref(h)))
+        return h
+
+    @staticmethod
+    def writeConfiguration(Umu, path, two_row=0, ens_label="DWF", ens_id="UKQCD", sequence_number=1):
+        _chk(lib().gb_gauge_write_nersc(Umu.h, str(path).encode(), two_row, ens_label.encode(), ens_id.encode(), sequence_number))
 
 
 class FermionOperator:

@@ -157,6 +157,27 @@ int gb_gauge_export(const gb_gauge *u, void *host, gb_precision host_prec);
 int gb_gauge_random(gb_gauge *u, uint64_t seed);
 int gb_gauge_unit(gb_gauge *u);
 
+/* NERSC gauge configurations.  ref: Grid/parallelIO/NerscIO.h:63-290, MetaData.h:143-215.
+ * Reading validates like NerscIO::readConfiguration: checksum (sum of the payload's 32-bit words) exact, plaquette within 1e-5
+ * and link trace within 1e-6 of the header, else GB_ERR_INVALID (the reference exits / asserts); two-row "4D_SU3_GAUGE" links
+ * get their third row reconstructed; IEEE64BIG / IEEE32BIG / IEEE64 / IEEE32 payloads.  Writing is always IEEE64BIG (NerscIO.h:262),
+ * two_row = 1 drops the third row.  The *_host entry points work on a GLOBAL lexicographic [V][4][3][3] complex double array and
+ * need no device; gb_gauge_read_nersc has every rank read and validate the file and import its local block. */
+typedef struct {
+  int dimension[4];
+  double link_trace, plaquette;      /* header values */
+  uint32_t checksum;
+  char data_type[64], floating_point[32], ensemble_id[64], ensemble_label[64];
+  int sequence_number;
+  int64_t data_start;                /* byte offset of the payload */
+  double computed_link_trace, computed_plaquette;   /* recomputed from the payload (0 for a header-only query) */
+  uint32_t computed_checksum;
+} gb_nersc_header;
+int gb_nersc_read_host(const char *path, double *U_out /* NULL: header only */, gb_nersc_header *hdr);
+int gb_nersc_write_host(const char *path, const double *U, const int dims[4], int two_row, const char *ens_label, const char *ens_id, int sequence_number);
+int gb_gauge_read_nersc(gb_gauge *Umu, const char *path, gb_nersc_header *hdr);
+int gb_gauge_write_nersc(const gb_gauge *Umu, const char *path, int two_row, const char *ens_label, const char *ens_id, int sequence_number);
+
 /* ---------------------------------------------------------------- fermion operators
  * ctor analogues: WilsonFermion(Umu,Grid,RBGrid,mass) ref: WilsonFermion.h:139-142
  *                 DomainWallFermion(Umu,FGrid,FrbGrid,UGrid,UrbGrid,mass,M5) ref: DomainWallFermion.h:108-134

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <memory>
+#include <string>
 #include <vector>
 
 namespace gridb200 {
@@ -114,6 +115,19 @@ public:
 };
 typedef LatticeGaugeFieldT<GB_F32> LatticeGaugeFieldF;
 typedef LatticeGaugeFieldT<GB_F64> LatticeGaugeFieldD;
+
+// ---- NerscIO (ref: Grid/parallelIO/NerscIO.h:43-290): checksum / plaquette / link-trace validated reader, IEEE64BIG writer
+typedef gb_nersc_header FieldMetaData;
+class NerscIO {
+public:
+  template <gb_precision P> static void readConfiguration(LatticeGaugeFieldT<P> &Umu, FieldMetaData &header, const std::string &file) {
+    GB_ASSERT_OK(gb_gauge_read_nersc(Umu.h, file.c_str(), &header));
+  }
+  template <gb_precision P> static void writeConfiguration(LatticeGaugeFieldT<P> &Umu, const std::string &file, int two_row = 0, int /*bits32*/ = 0,
+                                                           const std::string &ens_label = "DWF", const std::string &ens_id = "UKQCD", unsigned int sequence_number = 1) {
+    GB_ASSERT_OK(gb_gauge_write_nersc(Umu.h, file.c_str(), two_row, ens_label.c_str(), ens_id.c_str(), (int)sequence_number));
+  }
+};
 
 // ---- RNG facade: synthetic fields are generated on the device, keyed by global site (decomposition independent)
 class GridParallelRNG {

@@ -10,6 +10,7 @@
 // through the same host layouts the C ABI of the product uses (include/gridb200.h), so a test can feed both the
 // same bytes.  Built by oracle/Makefile.ref into oracle/_ref/libgridref.so.
 #include <Grid/Grid.h>
+#include <Grid/parallelIO/NerscIO.h>
 #include <chrono>
 #include <memory>
 
@@ -406,6 +407,24 @@ void gref_schur_solve(void *h, const void *src, void *sol, double tol, int maxit
 int gref_dhop_dir(void *h, const void *in, void *out, int dir, int disp) { return ((BoxBase *)h)->dhop_dir(in, out, dir, disp); }
 int gref_deriv(void *h, int which, void *mat, const void *U, const void *V, int dag) { return ((BoxBase *)h)->deriv(which, mat, U, V, dag); }
 int gref_deriv_eo(void *h, int which, void *mat, const void *U, const void *V) { return ((BoxBase *)h)->deriv_eo(which, mat, U, V); }
+// NerscIO::writeConfiguration / readConfiguration of a LatticeGaugeFieldD given as a lexicographic [V4][4][3][3] complex double array
+// (ref: tests/IO/Test_nersc_io.cc).  gref_nersc_read returns {plaquette, link_trace} of the header after the reference's own QA.
+void gref_nersc_write(const int *L, const void *Umu, const char *path, int two_row) {
+  gref_init(0);
+  Grids<vComplexD> G; G.make(L, 1, false);
+  LatticeGaugeFieldD U(G.UGrid);
+  import_lex(U, Umu);
+  NerscIO::writeConfiguration(U, std::string(path), two_row, 0, std::string("DWF"), std::string("UKQCD"), 7);
+}
+void gref_nersc_read(const int *L, void *Umu_out, const char *path, double *plaq_link) {
+  gref_init(0);
+  Grids<vComplexD> G; G.make(L, 1, false);
+  LatticeGaugeFieldD U(G.UGrid);
+  FieldMetaData header;
+  NerscIO::readConfiguration(U, header, std::string(path));
+  plaq_link[0] = header.plaquette; plaq_link[1] = header.link_trace;
+  export_lex(U, Umu_out);
+}
 // ConjugateGradientMultiShift as tests/solver/Test_staggered_multishift.cc:98-107 drives it, with explicit poles / tolerances
 void gref_multishift_cg(void *h, int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit, void *results,
                         int *out_iters, double *out_true_resid) {

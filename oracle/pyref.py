@@ -48,6 +48,8 @@ def lib():
         L.gref_deriv.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.gref_deriv_eo.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gref_deriv_eo.restype = C.c_int
+        L.gref_nersc_write.argtypes = [C.POINTER(C.c_int), C.c_void_p, C.c_char_p, C.c_int]
+        L.gref_nersc_read.argtypes = [C.POINTER(C.c_int), C.c_void_p, C.c_char_p, C.c_void_p]
         L.gref_physical.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_physical.restype = C.c_int
         L.gref_redblack_source.argtypes = [C.c_void_p] * 4
@@ -245,3 +247,17 @@ def relup_cg(op_d, op_f, cb, src_d, tol, maxit, delta):
     tr = np.zeros(1, dtype=np.float64)
     lib().gref_relup_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxit, delta, _ptr(it), _ptr(tr))
     return sol, dict(iterations=int(it[0]), reliable_updates=int(it[1]), cleanup_iterations=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))
+
+
+def nersc_write(dims, U, path, two_row=0):
+    """NerscIO::writeConfiguration of the reference (IEEE64BIG; two_row drops the third row)."""
+    U = np.ascontiguousarray(U, dtype=np.complex128)
+    lib().gref_nersc_write((C.c_int * 4)(*dims), _ptr(U), str(path).encode(), two_row)
+
+
+def nersc_read(dims, path):
+    """NerscIO::readConfiguration of the reference (with its checksum / plaquette / link-trace QA). Returns (U, plaquette, link_trace)."""
+    U = np.empty((int(np.prod(dims)), 4, 3, 3), dtype=np.complex128)
+    pl = np.zeros(2)
+    lib().gref_nersc_read((C.c_int * 4)(*dims), _ptr(U), str(path).encode(), _ptr(pl))
+    return U, float(pl[0]), float(pl[1])
