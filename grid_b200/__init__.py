@@ -383,6 +383,8 @@ class NerscIO:
 class FermionOperator:
     """Mirror of FermionOperator<Impl> (ref: FermionOperator.h:40-192): same method names, (in, out[, dag])."""
 
+    _cayley = False     # 5D Cayley operators apply Meo5D in front of the directional hops (Mdir, MdirAll)
+
     def __init__(self):
         self.h = C.c_void_p()
         self.grid = None
@@ -426,6 +428,29 @@ class FermionOperator:
 
     # single hop legs and force terms (ref: FermionOperator.h:79-93; dir = 0..3, disp = +-1; mat = LatticeGaugeField)
     def DhopDir(self, i, o, dir, disp): _chk(lib().gb_op_dhop_dir(self.h, i.h, o.h, dir, disp))
+    def DhopDirAll(self, i, outs):
+        """outs[0..3] = forward legs x,y,z,t; outs[4..7] = backward legs (ref: WilsonKernelsImplementation.h:343-372)"""
+        assert len(outs) == 8
+        for p, o in enumerate(outs):
+            self.DhopDir(i, o, p & 3, 1 if p < 4 else -1)
+
+    def Mdir(self, i, o, dir, disp):
+        """ref: CayleyFermion5DImplementation.h:331-337 (Meo5D then DhopDir); WilsonFermionImplementation.h:345-348 (= DhopDir)"""
+        if self._cayley:
+            tmp = i.like()
+            self.Meooe5D(i, tmp)
+            self.DhopDir(tmp, o, dir, disp)
+        else:
+            self.DhopDir(i, o, dir, disp)
+
+    def MdirAll(self, i, outs):
+        if self._cayley:
+            tmp = i.like()
+            self.Meooe5D(i, tmp)
+            self.DhopDirAll(tmp, outs)
+        else:
+            self.DhopDirAll(i, outs)
+
     def DhopDeriv(self, mat, U, V, dag): _chk(lib().gb_op_dhop_deriv(self.h, mat.h, U.h, V.h, dag))
     def MDeriv(self, mat, U, V, dag): _chk(lib().gb_op_mderiv(self.h, mat.h, U.h, V.h, dag))
     def MeoDeriv(self, mat, U, V, dag): assert U.Checkerboard() == Even; _chk(lib().gb_op_meooe_deriv(self.h, mat.h, U.h, V.h, dag))
@@ -473,6 +498,7 @@ class WilsonFermion(FermionOperator):
 
 class DomainWallFermion(FermionOperator):
     """ref: DomainWallFermion.h:108-134 (Shamir: b=1, c=0)"""
+    _cayley = True
 
     def __init__(self, Umu, grid, Ls, mass, M5, boundary_phases=None):
         super().__init__()
@@ -482,6 +508,7 @@ class DomainWallFermion(FermionOperator):
 
 class MobiusFermion(FermionOperator):
     """ref: MobiusFermion.h:45-71"""
+    _cayley = True
 
     def __init__(self, Umu, grid, Ls, mass, M5, b, c, boundary_phases=None):
         super().__init__()

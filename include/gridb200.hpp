@@ -187,6 +187,12 @@ public:
   virtual void ExportPhysicalFermionSource(const FermionField &solution5d, FermionField &exported4d) { GB_ASSERT_OK(gb_op_export_physical_fermion_source(h, solution5d.h, exported4d.h)); }
   // single hop legs and force terms on full-grid fields (ref: FermionOperator.h:79-93): dir = 0..3, disp = +-1
   virtual void DhopDir(const FermionField &in, FermionField &out, int dir, int disp) { GB_ASSERT_OK(gb_op_dhop_dir(h, in.h, out.h, dir, disp)); }
+  virtual void DhopDirAll(const FermionField &in, std::vector<FermionField> &out) {   // out[0..3] forward legs, out[4..7] backward (ref: WilsonKernelsImplementation.h:343-372)
+    assert(out.size() == 8);
+    for (int p = 0; p < 8; p++) DhopDir(in, out[p], p & 3, p < 4 ? 1 : -1);
+  }
+  virtual void Mdir(const FermionField &in, FermionField &out, int dir, int disp) { DhopDir(in, out, dir, disp); }     // ref: WilsonFermionImplementation.h:345-353
+  virtual void MdirAll(const FermionField &in, std::vector<FermionField> &out) { DhopDirAll(in, out); }
   virtual void DhopDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { GB_ASSERT_OK(gb_op_dhop_deriv(h, mat.h, U.h, V.h, dag)); }
   virtual void MDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { GB_ASSERT_OK(gb_op_mderiv(h, mat.h, U.h, V.h, dag)); }
   virtual void MeoDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { assert(U.Checkerboard() == Even); GB_ASSERT_OK(gb_op_meooe_deriv(h, mat.h, U.h, V.h, dag)); }
@@ -200,13 +206,23 @@ public: // ref: WilsonFermion.h:139-142
     GB_ASSERT_OK(gb_op_create_wilson(Fgrid.h, Umu.h, mass, nullptr, &this->h));
   }
 };
-template <gb_precision Prec> class DomainWallFermionT : public FermionOperator<Prec> {
+// CayleyFermion5D pieces shared by DomainWallFermion and MobiusFermion (ref: CayleyFermion5DImplementation.h:165-190,331-344)
+template <gb_precision Prec> class CayleyFermion5DT : public FermionOperator<Prec> {
+public:
+  typedef LatticeFermionT<Prec> FermionField;
+  void Meooe5D(const FermionField &in, FermionField &out) { this->apply(GB_OP_MEOOE5D, in, out); }
+  void Meo5D(const FermionField &in, FermionField &out) { this->apply(GB_OP_MEOOE5D, in, out); }
+  void MeooeDag5D(const FermionField &in, FermionField &out) { this->apply(GB_OP_MEOOEDAG5D, in, out); }
+  void Mdir(const FermionField &psi, FermionField &chi, int dir, int disp) override { FermionField tmp(psi.Grid()); Meo5D(psi, tmp); this->DhopDir(tmp, chi, dir, disp); }
+  void MdirAll(const FermionField &psi, std::vector<FermionField> &out) override { FermionField tmp(psi.Grid()); Meo5D(psi, tmp); this->DhopDirAll(tmp, out); }
+};
+template <gb_precision Prec> class DomainWallFermionT : public CayleyFermion5DT<Prec> {
 public: // ref: DomainWallFermion.h:108-134
   DomainWallFermionT(LatticeGaugeFieldT<Prec> &Umu, GridCartesian &FGrid, GridRedBlackCartesian &, GridCartesian &UGrid, GridRedBlackCartesian &, RealD mass, RealD M5) {
     GB_ASSERT_OK(gb_op_create_dwf(UGrid.h, Umu.h, FGrid.Ls, mass, M5, nullptr, &this->h));
   }
 };
-template <gb_precision Prec> class MobiusFermionT : public FermionOperator<Prec> {
+template <gb_precision Prec> class MobiusFermionT : public CayleyFermion5DT<Prec> {
 public: // ref: MobiusFermion.h:45-71
   MobiusFermionT(LatticeGaugeFieldT<Prec> &Umu, GridCartesian &FGrid, GridRedBlackCartesian &, GridCartesian &UGrid, GridRedBlackCartesian &, RealD mass, RealD M5, RealD b, RealD c) {
     GB_ASSERT_OK(gb_op_create_mobius(UGrid.h, Umu.h, FGrid.Ls, mass, M5, b, c, nullptr, &this->h));

@@ -216,3 +216,24 @@ def test_cuda_even_odd_force_terms(name, prec_name):
     par = np.indices(DIMS[::-1]).sum(axis=0).reshape(-1) & 1
     assert rel_err(got[par == 0], want[par == 0]) < tol
     assert np.array_equal(got[par == 1], before[par == 1])
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cuda_mdir_all():
+    """Mdir / MdirAll (the directional pieces multigrid coarsening reads, ref: CayleyFermion5DImplementation.h:331-344): out[p] is
+    leg p of Dhop applied to Meo5D psi; the eight of them sum to Meooe-style Dhop(Meooe5D psi)."""
+    import grid_b200 as gb
+    ctx = gb.Context(0)
+    grid = gb.GridCartesian(ctx, DIMS)
+    D = _device_op(gb, grid, "mobius", gb.F64)
+    psi = gb.LatticeFermion(grid, LS, gb.F64).import_lex(G["src5"])
+    outs = [gb.LatticeFermion(grid, LS, gb.F64) for _ in range(8)]
+    D.MdirAll(psi, outs)
+    o = oracle_op("mobius")
+    Din = o.apply(po.OP_MEOOE5D, G["src5"])
+    for p, f in enumerate(outs):
+        assert rel_err(f.export_lex(), o.dhop_dir(Din, p & 3, 1 if p < 4 else -1)) < 2e-13, p
+    one = gb.LatticeFermion(grid, LS, gb.F64)
+    D.Mdir(psi, one, 2, -1)
+    assert np.array_equal(one.export_lex(), outs[6].export_lex())
