@@ -1,4 +1,5 @@
 import os
+import subprocess
 import sys
 
 import pytest
@@ -7,19 +8,39 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_CHILD = os.environ.get("GB_UNVERIFIED_CHILD") == "1"
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: long-running CPU test")
     config.addinivalue_line("markers", "unverified(reason): a GPU test of code written after the round's GPU budget was spent -- it "
                             "has never run on a device.  Reported as xfail/xpass (non-strict) so that it can neither hide behind nor "
-                            "break the verified suite; the marker is removed once the test has passed on a B200 (DESIGN.md section 8).")
+                            "break the verified suite, run last, and run in a child process (a crash, a sticky CUDA error or a hang "
+                            "in new code cannot take the session down); the marker is removed once the test has passed on a B200 "
+                            "(DESIGN.md section 8).")
 
 
 def pytest_collection_modifyitems(config, items):
     for item in items:
         m = item.get_closest_marker("unverified")
-        if m is not None:
+        if m is not None and not _CHILD:
             item.add_marker(pytest.mark.xfail(strict=False, reason="never run on a GPU yet: " + (m.args[0] if m.args else "")))
-    # verified tests first, unverified ones last (a sticky CUDA error in new code must not take verified tests down with it)
+    # verified tests first, unverified ones last
     items.sort(key=lambda it: it.get_closest_marker("unverified") is not None)
+
+
+@pytest.hookimpl(tryfirst=True)
+def pytest_pyfunc_call(pyfuncitem):
+    """Unverified tests run in a child pytest process (GB_UNVERIFIED_CHILD=1 there: plain test, real exit code, 15 min limit)."""
+    if _CHILD or pyfuncitem.get_closest_marker("unverified") is None:
+        return None
+    env = dict(os.environ, GB_UNVERIFIED_CHILD="1")
+    try:
+        p = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-p", "no:cacheprovider", pyfuncitem.nodeid], cwd=ROOT, env=env,
+                           capture_output=True, text=True, timeout=900)
+    except subprocess.TimeoutExpired:
+        pytest.fail("unverified test exceeded 900 s in its child process", pytrace=False)
+    if p.returncode != 0:
+        pytest.fail("child pytest exit %d\n%s" % (p.returncode, (p.stdout + p.stderr)[-3000:]), pytrace=False)
+    return True
