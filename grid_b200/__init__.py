@@ -60,6 +60,7 @@ SYMBOLS = [
     ("gb_op_dhop_dir", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_dhop_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mderiv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_op_meooe_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mpc_deriv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_relup_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _d, _pi, _pd]),
+    ("gb_cg_multishift_mixed_schur", _i, [_vp, _vp, _vp, _i, _pd, _pd, _i, _i, _pvp, _pi, _pd]),
     ("gb_cg_multishift_schur", _i, [_vp, _vp, _i, _pd, _pd, _i, _pvp, _pi, _pd]),
     ("gb_op_import_physical_fermion_source", _i, [_vp, _vp, _vp]), ("gb_op_import_unphysical_fermion", _i, [_vp, _vp, _vp]),
     ("gb_op_export_physical_fermion_solution", _i, [_vp, _vp, _vp]), ("gb_op_export_physical_fermion_source", _i, [_vp, _vp, _vp]),
@@ -772,3 +773,27 @@ class ConjugateGradientReliableUpdate:
             assert not self.ErrorOnNoConverge, "ConjugateGradientReliableUpdate did NOT converge"
             return
         _chk(rc)
+
+
+class ConjugateGradientMultiShiftMixedPrec(ConjugateGradientMultiShift):
+    """ref: Grid/algorithms/iterative/ConjugateGradientMultiShiftMixedPrec.h:73-410.  mcg = ConjugateGradientMultiShiftMixedPrec(maxit,
+    shifts, Linop_f, ReliableUpdateFreq); mcg(Linop_d, src_d, results_d[, psi_d])."""
+
+    def __init__(self, maxit, shifts, Linop_f, ReliableUpdateFreq):
+        super().__init__(maxit, shifts)
+        self.Linop_f, self.ReliableUpdateFreq = Linop_f, ReliableUpdateFreq
+
+    def __call__(self, Linop_d, src, results, psi=None):
+        n = self.shifts.order
+        assert len(results) == n
+        poles, tols = (C.c_double * n)(*self.shifts.poles), (C.c_double * n)(*self.shifts.tolerances)
+        handles = (C.c_void_p * n)(*[r.h.value for r in results])
+        it, tr = (C.c_int * (n + 1))(), (C.c_double * n)()
+        _chk(lib().gb_cg_multishift_mixed_schur(self.Linop_f._Mat.h, Linop_d._Mat.h, src.h, n, poles, tols, self.MaxIterations,
+                                                self.ReliableUpdateFreq, handles, it, tr))
+        self.IterationsToCompleteShift, self.TrueResidualShift, self.IterationsToComplete = list(it[:n]), list(tr), it[n]
+        if psi is not None:
+            scale(psi, self.shifts.norm, src)
+            for res, r in zip(self.shifts.residues, results):
+                axpy(psi, res, r, psi)
+        return True

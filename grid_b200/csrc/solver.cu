@@ -94,7 +94,8 @@ void cg_update_dev(gb_context *ctx, gb_fermion *psi, gb_fermion *p, const gb_fer
 //   the consuming kernels, and the next iteration's A p is enqueued before the host looks at cp, so the only host
 //   involvement per iteration is one 8-byte read-back for the stopping test, off the critical path.  If that test says
 //   "converged" the speculative A p has only overwritten the scratch field mmp.
-static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fermion *psi, double tol, int maxit) {
+// shift != 0: CG on HermOp + shift (ShiftedLinop, ref: ConjugateGradientMultiShiftMixedPrec.h:44-70)
+static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fermion *psi, double tol, int maxit, double shift = 0.0) {
   gb_context *ctx = op->ctx;
   fermion_check_same(src, psi);
   gb_grid *g = src->grid;
@@ -102,7 +103,7 @@ static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fe
   auto mk = [&](gb_fermion **f) { *f = fermion_create_like(src, src->prec); };
   mk(&p); mk(&mmp); mk(&r);
   struct Guard { gb_fermion *a, *b, *c; ~Guard() { gb_fermion_destroy(a); gb_fermion_destroy(b); gb_fermion_destroy(c); } } guard{p, mmp, r};
-  auto A = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op, GB_OP_HERMOP, in, out, 0); };
+  auto A = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op, GB_OP_HERMOP, in, out, 0); if (shift != 0.0) chk(gb_axpy(out, shift, in, out)); };
   psi->cb = src->cb;
   CGOut out;
   double ssq, guess, a;
@@ -424,9 +425,22 @@ int gb_cg(gb_context *ctx, gb_hermop_fn hermop, void *user, const gb_fermion *sr
   GB_API_END
 }
 
+struct MixedOut { int inner = 0, outer = 0, fin = 0; double true_resid = 0; bool converged = false; };
+static MixedOut mixed_cg_core(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, int max_inner, int max_outer,
+                              double shift);
 int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, int max_inner,
                       int max_outer, int iters_out[3], double *true_resid_out) {
   GB_API_BEGIN
+  MixedOut o = mixed_cg_core(op_f, op_d, src_d_in, sol_d, tol, max_inner, max_outer, 0.0);
+  if (iters_out) { iters_out[0] = o.inner; iters_out[1] = o.outer; iters_out[2] = o.fin; }
+  if (true_resid_out) *true_resid_out = o.true_resid;
+  if (!o.converged) throw Error(GB_ERR_NOT_CONVERGED, "MixedPrecisionConjugateGradient final solve did NOT converge");
+  GB_API_END
+}
+} // extern "C"
+// MixedPrecisionConjugateGradient on HermOp (+ shift)   ref: ConjugateGradientMixedPrec.h:71-167
+static MixedOut mixed_cg_core(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, int max_inner, int max_outer,
+                              double shift) {
   GB_REQUIRE(op_f && op_d && src_d_in && sol_d, "null argument");
   GB_REQUIRE(op_f->prec == GB_F32 && op_d->prec == GB_F64, "mixed CG needs an fp32 and an fp64 operator");
   GB_REQUIRE(src_d_in->prec == GB_F64 && sol_d->prec == GB_F64, "mixed CG outer fields must be fp64");
@@ -448,8 +462,7 @@ int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_
   const double OuterLoopNormMult = 100.0;
   double inner_tol = tol;
   int total_inner = 0, outer;
-  auto Ad = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_d, GB_OP_HERMOP, in, out, 0); };
-  auto Af = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_f, GB_OP_HERMOP, in, out, 0); };
+  auto Ad = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_d, GB_OP_HERMOP, in, out, 0); if (shift != 0.0) chk(gb_axpy(out, shift, in, out)); };
   chk(gb_copy(src_d, src_d_in));
   for (outer = 0; outer < max_outer; outer++) {
     Ad(sol_d, tmp_d);
@@ -459,15 +472,141 @@ int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_
     while (norm * inner_tol * inner_tol < stop) inner_tol *= 2;
     chk(gb_precision_change(src_f, src_d));
     chk(gb_zero(sol_f));
-    CGOut in = cg_schur_device_scalars(op_f, src_f, sol_f, inner_tol, max_inner); // ErrorOnNoConverge = false
+    CGOut in = cg_schur_device_scalars(op_f, src_f, sol_f, inner_tol, max_inner, shift); // ErrorOnNoConverge = false
     total_inner += in.iters;
     chk(gb_precision_change(tmp_d, sol_f));
     chk(gb_axpy(sol_d, 1.0, tmp_d, sol_d));
   }
-  CGOut fin = cg_schur_device_scalars(op_d, src_d_in, sol_d, tol, max_inner);
-  if (iters_out) { iters_out[0] = total_inner; iters_out[1] = outer; iters_out[2] = fin.iters; }
-  if (true_resid_out) *true_resid_out = fin.true_resid;
-  if (!fin.converged) throw Error(GB_ERR_NOT_CONVERGED, "MixedPrecisionConjugateGradient final solve did NOT converge");
-  GB_API_END
+  CGOut fin = cg_schur_device_scalars(op_d, src_d_in, sol_d, tol, max_inner, shift);
+  MixedOut R;
+  R.inner = total_inner; R.outer = outer; R.fin = fin.iters; R.true_resid = fin.true_resid; R.converged = fin.converged;
+  return R;
 }
+
+// ConjugateGradientMultiShiftMixedPrec   ref: Grid/algorithms/iterative/ConjugateGradientMultiShiftMixedPrec.h:128-410
+// fp64 vectors and recurrences, fp32 operator per iteration, true-residual replacement every relup_freq iterations, clean-up of
+// the shifts that miss their tolerance by MixedPrecisionConjugateGradient on HermOp + pole.  The multi-field updates are the fused
+// kernels of the fp64 multishift solver.
+extern "C" int gb_cg_multishift_mixed_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src, int nshift, const double *mass,
+                                            const double *mresidual, int maxit, int relup_freq, gb_fermion *const *psi, int *iters_out,
+                                            double *true_resid_out) {
+  GB_API_BEGIN
+  GB_REQUIRE(op_f && op_d && src && mass && mresidual && psi, "null argument");
+  GB_REQUIRE(op_f->prec == GB_F32 && op_d->prec == GB_F64 && src->prec == GB_F64 && src->kind == GB_HALF, "needs an fp32 and an fp64 operator and fp64 red-black fields");
+  GB_REQUIRE(nshift >= 1 && relup_freq >= 1, "bad shift count or reliable-update frequency");
+  gb_context *ctx = op_d->ctx;
+  for (int s = 0; s < nshift; s++) {
+    GB_REQUIRE(psi[s] != nullptr && psi[s] != src, "null or aliased result field");
+    fermion_check_same(src, psi[s]);
+    GB_REQUIRE(mass[s] >= mass[0], "the first pole must be the lightest");
+  }
+  auto Ad = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_d, GB_OP_HERMOP, in, out, 0); };
+  auto Af = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_f, GB_OP_HERMOP, in, out, 0); };
+  std::vector<double> alpha(nshift, 1.0), bs(nshift), rsq(nshift), z0v(nshift, 1.0), z1v(nshift, 1.0), tr(nshift, 0.0);
+  std::vector<int> converged(nshift, 0), its(nshift, 0);
+  std::vector<gb_fermion *> tmps;
+  struct Guard { std::vector<gb_fermion *> &v; ~Guard() { for (auto *f : v) gb_fermion_destroy(f); } } guard{tmps};
+  auto mk = [&](int prec) { gb_fermion *f = fermion_create_like(src, prec); tmps.push_back(f); return f; };
+  std::vector<gb_fermion *> ps(nshift);
+  for (int s = 0; s < nshift; s++) ps[s] = mk(GB_F64);
+  gb_fermion *p = mk(GB_F64), *r = mk(GB_F64), *tmp = mk(GB_F64), *mmp = mk(GB_F64), *p_f = mk(GB_F32), *mmp_f = mk(GB_F32);
+  auto report = [&](int k) {
+    for (int s = 0; s < nshift; s++) { if (iters_out) iters_out[s] = its[s]; if (true_resid_out) true_resid_out[s] = tr[s]; }
+    if (iters_out) iters_out[nshift] = k;
+  };
+  double a, b, c, d, cp, bp, rn, dd[2];
+  chk(gb_norm2(src, &cp));
+  if (cp == 0.0) {
+    for (int s = 0; s < nshift; s++) { chk(gb_zero(psi[s])); psi[s]->cb = src->cb; its[s] = 1; }
+    report(0);
+    return GB_OK;
+  }
+  for (int s = 0; s < nshift; s++) { rsq[s] = cp * mresidual[s] * mresidual[s]; chk(gb_copy(ps[s], src)); }
+  chk(gb_copy(p, src)); chk(gb_copy(r, src));
+  Ad(p, mmp);
+  chk(gb_inner_product(p, mmp, dd)); d = dd[0];
+  chk(gb_axpy(mmp, mass[0], p, mmp));
+  chk(gb_norm2(p, &rn));
+  d += rn * mass[0];
+  b = -cp / d;
+  bs[0] = b;
+  for (int s = 1; s < nshift; s++) { z0v[s] = 1.0; z1v[s] = 1.0 / (1.0 - b * (mass[s] - mass[0])); bs[s] = b * z1v[s]; }
+  chk(gb_axpy_norm(r, b, mmp, r, &c));
+  for (int s = 0; s < nshift; s++) { chk(gb_axpby(psi[s], 0.0, -bs[s] * alpha[s], src, src)); psi[s]->cb = src->cb; }
+  for (int k = 1; k <= maxit; k++) {
+    a = c / cp;
+    {
+      MsEntries e; e.n = 0;
+      auto push = [&](gb_fermion *y, double ca, double cb_, int plain) {
+        e.y[e.n] = y->data; e.x[e.n] = nullptr; e.a[e.n] = ca; e.b[e.n] = cb_; e.plain[e.n] = plain;
+        if (++e.n == MS_MAX) { ms_update<0>(ctx, e, r, src); e.n = 0; }
+      };
+      push(p, a, 1.0, 1);
+      for (int s = 0; s < nshift; s++) if (!converged[s]) {
+        if (s == 0) push(ps[s], a, 1.0, 1);
+        else push(ps[s], a * z1v[s] * bs[s] / (z0v[s] * b), z1v[s], 0);
+      }
+      ms_update<0>(ctx, e, r, src);
+    }
+    chk(gb_precision_change(p_f, p));
+    cp = c;
+    Af(p_f, mmp_f);
+    chk(gb_precision_change(mmp, mmp_f));
+    chk(gb_inner_product(p, mmp, dd)); d = dd[0];
+    chk(gb_axpy(mmp, mass[0], p, mmp));
+    chk(gb_norm2(p, &rn));
+    d += rn * mass[0];
+    bp = b;
+    b = -cp / d;
+    bs[0] = b;
+    for (int s = 1; s < nshift; s++) if (!converged[s]) {
+      const double z0 = z1v[s], z1 = z0v[s];
+      const double znew = z0 * z1 * bp / (b * a * (z1 - z0) + z1 * bp * (1 - (mass[s] - mass[0]) * b));
+      z0v[s] = z0; z1v[s] = znew;
+      bs[s] = b * znew / z0;
+    }
+    {
+      MsEntries e; e.n = 0;
+      for (int s = 0; s < nshift; s++) if (!converged[s]) {
+        e.y[e.n] = psi[s]->data; e.x[e.n] = ps[s]->data; e.a[e.n] = -bs[s] * alpha[s]; e.b[e.n] = 0; e.plain[e.n] = 0;
+        if (++e.n == MS_MAX) { ms_update<1>(ctx, e, nullptr, src); e.n = 0; }
+      }
+      ms_update<1>(ctx, e, nullptr, src);
+    }
+    chk(gb_axpy_norm(r, b, mmp, r, &c));
+    GB_REQUIRE(!std::isnan(c), "ConjugateGradientMultiShiftMixedPrec: residual is NaN");
+    if (k % relup_freq == 0) {           // replace r with the true residual of the primary shift (ref :322-336)
+      Ad(psi[0], mmp);
+      chk(gb_axpy(mmp, mass[0], psi[0], mmp));
+      chk(gb_axpy_norm(r, -1.0, mmp, src, &c));
+    }
+    bool all_converged = true;
+    for (int s = 0; s < nshift; s++) if (!converged[s]) {
+      its[s] = k;
+      const double zc = s == 0 ? 1.0 : z1v[s];
+      if (c * zc * zc < rsq[s]) converged[s] = 1; else all_converged = false;
+    }
+    if (all_converged || k == maxit - 1) {
+      double cn;
+      chk(gb_norm2(src, &cn));
+      bool ok = true;
+      for (int s = 0; s < nshift; s++) {
+        Ad(psi[s], mmp);
+        chk(gb_axpy(tmp, mass[s], psi[s], mmp));
+        chk(gb_axpy_norm(r, -alpha[s], src, tmp, &rn));
+        tr[s] = std::sqrt(rn / cn);
+        if (rn >= rsq[s]) {              // clean-up (ref :382-396)
+          MixedOut m = mixed_cg_core(op_f, op_d, src, psi[s], mresidual[s], 20000, 20000, mass[s]);
+          tr[s] = m.true_resid;
+          ok = ok && m.converged;
+        }
+      }
+      report(k);
+      if (!ok) throw Error(GB_ERR_NOT_CONVERGED, "ConjugateGradientMultiShiftMixedPrec: a clean-up solve did NOT converge");
+      return GB_OK;
+    }
+  }
+  report(maxit);
+  throw Error(GB_ERR_NOT_CONVERGED, "ConjugateGradientMultiShiftMixedPrec did NOT converge");   // the reference asserts (:408)
+  GB_API_END
 }

@@ -288,6 +288,14 @@ int gb_relup_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d,
  * only logs that case, :336-338; the results hold the iterate reached). */
 int gb_cg_multishift_schur(gb_fermop *op, const gb_fermion *src, int nshift, const double *poles, const double *tolerances, int maxit,
                            gb_fermion *const *results, int *iters_out, double *true_resid_out);
+/* ConjugateGradientMultiShiftMixedPrec(maxit, shifts, sp_grid, Linop_f, ReliableUpdateFreq)(Linop_d, src, results): the same
+ * recurrences with fp64 vectors and ONE fp32 operator application per iteration; every relup_freq iterations the residual is
+ * replaced by the true fp64 residual of the primary shift; shifts that miss their tolerance are cleaned up with
+ * MixedPrecisionConjugateGradient on HermOp + pole.  ref: Grid/algorithms/iterative/ConjugateGradientMultiShiftMixedPrec.h:36-410 ;
+ * driver tests/solver/Test_dwf_multishift_mixedprec.cc:113-128.  Outputs as gb_cg_multishift_schur. */
+int gb_cg_multishift_mixed_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d, int nshift, const double *poles,
+                                 const double *tolerances, int maxit, int relup_freq, gb_fermion *const *results, int *iters_out,
+                                 double *true_resid_out);
 
 /* SchurRedBlackDiagMooeeSolve (Wilson-type operators) / SchurRedBlackStaggeredSolve (staggered): the full-lattice solve
  * M sol = src through the even-odd Schur decomposition.  ref: Grid/algorithms/iterative/SchurRedBlack.h:238-290,294-349,385-430

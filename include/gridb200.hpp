@@ -428,6 +428,42 @@ public:
   }
 };
 
+// ---- ConjugateGradientMultiShiftMixedPrec (ref: Grid/algorithms/iterative/ConjugateGradientMultiShiftMixedPrec.h:73-410)
+template <class FieldD, class FieldF> class ConjugateGradientMultiShiftMixedPrec {
+public:
+  Integer MaxIterationsMshift;
+  Integer IterationsToComplete = 0;
+  std::vector<int> IterationsToCompleteShift;
+  MultiShiftFunction shifts;
+  std::vector<RealD> TrueResidualShift;
+  int ReliableUpdateFreq;
+  GridBase *SinglePrecGrid;
+  LinearOperatorBase<FieldF> &Linop_f;
+  ConjugateGradientMultiShiftMixedPrec(Integer maxit, const MultiShiftFunction &_shifts, GridBase *_SinglePrecGrid, LinearOperatorBase<FieldF> &_Linop_f,
+                                       int _ReliableUpdateFreq)
+      : MaxIterationsMshift(maxit), shifts(_shifts), ReliableUpdateFreq(_ReliableUpdateFreq), SinglePrecGrid(_SinglePrecGrid), Linop_f(_Linop_f) {
+    IterationsToCompleteShift.resize(_shifts.order); TrueResidualShift.resize(_shifts.order);
+  }
+  void operator()(LinearOperatorBase<FieldD> &Linop_d, const FieldD &src_d, std::vector<FieldD> &psi_d) {
+    gb_fermop *mf = Linop_f.FusedSchurMatrix(), *md = Linop_d.FusedSchurMatrix();
+    assert(mf && md && "ConjugateGradientMultiShiftMixedPrec needs SchurDiagMooeeOperator arguments");
+    const int n = shifts.order;
+    assert((int)psi_d.size() == n);
+    std::vector<gb_fermion *> hs(n);
+    for (int i = 0; i < n; i++) hs[i] = psi_d[i].h;
+    std::vector<int> it(n + 1);
+    GB_ASSERT_OK(gb_cg_multishift_mixed_schur(mf, md, src_d.h, n, shifts.poles.data(), shifts.tolerances.data(), MaxIterationsMshift, ReliableUpdateFreq,
+                                              hs.data(), it.data(), TrueResidualShift.data()));
+    for (int i = 0; i < n; i++) IterationsToCompleteShift[i] = it[i];
+    IterationsToComplete = it[n];
+  }
+  void operator()(LinearOperatorBase<FieldD> &Linop, const FieldD &src, std::vector<FieldD> &results, FieldD &psi) {
+    (*this)(Linop, src, results);
+    GB_ASSERT_OK(gb_scale(psi.h, shifts.norm, src.h));
+    for (int i = 0; i < shifts.order; i++) axpy(psi, shifts.residues[i], results[i], psi);
+  }
+};
+
 // ---- SchurRedBlackDiagMooeeSolve / SchurRedBlackStaggeredSolve (ref: Grid/algorithms/iterative/SchurRedBlack.h:96-290,294-349,385-430)
 //   SchurRedBlackDiagMooeeSolve<LatticeFermion> SchurSolver(CG);  SchurSolver(Ddwf, src, result);   solves M result = src
 template <class Field, bool Staggered> class SchurRedBlackSolveT {

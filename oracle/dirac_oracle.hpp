@@ -804,7 +804,8 @@ struct CGResult { int iterations = 0; double true_residual = 0; int converged = 
 
 // ref: Grid/algorithms/iterative/ConjugateGradient.h:68-257 ; the operator is SchurDiagMooee HermOp on `cb`.
 template <class T>
-CGResult ConjugateGradient(const FermOp<T> &op, int cb, const Spinor<T> *src, Spinor<T> *psi, double tol, int maxit) {
+CGResult ConjugateGradient(const FermOp<T> &op, int cb, const Spinor<T> *src, Spinor<T> *psi, double tol, int maxit, double shift = 0.0) {
+  // shift != 0: the operator is HermOp + shift (ShiftedLinop of ConjugateGradientMultiShiftMixedPrec.h:44-70)
   const int64_t n = op.V5cb();
   std::vector<Spinor<T>> p(n), mmp(n), r(n);
   CGResult res;
@@ -812,6 +813,7 @@ CGResult ConjugateGradient(const FermOp<T> &op, int cb, const Spinor<T> *src, Sp
   if (guess == 0.0) { std::copy(src, src + n, r.begin()); p = r; a = ssq; }
   else {
     op.HermOp(psi, mmp.data(), cb);
+    if (shift != 0.0) axpy(n, mmp.data(), (T)shift, psi, mmp.data());
     axpy(n, r.data(), (T)-1, mmp.data(), src);
     p = r; a = norm2(n, p.data());
   }
@@ -823,6 +825,7 @@ CGResult ConjugateGradient(const FermOp<T> &op, int cb, const Spinor<T> *src, Sp
   for (k = 1; k <= maxit; k++) {
     c = cp;
     op.HermOp(p.data(), mmp.data(), cb);
+    if (shift != 0.0) axpy(n, mmp.data(), (T)shift, p.data(), mmp.data());
     d = innerProduct(n, p.data(), mmp.data()).re;
     a = c / d;
     cp = axpy_norm(n, r.data(), (T)(-a), mmp.data(), r.data());
@@ -835,6 +838,7 @@ CGResult ConjugateGradient(const FermOp<T> &op, int cb, const Spinor<T> *src, Sp
       }
     if (cp <= rsq) {
       op.HermOp(psi, mmp.data(), cb);
+      if (shift != 0.0) axpy(n, mmp.data(), (T)shift, psi, mmp.data());
       axpy(n, p.data(), (T)-1, src, mmp.data()); // p = mmp - src
       res.true_residual = std::sqrt(norm2(n, p.data())) / std::sqrt(ssq);
       res.iterations = k; res.converged = 1;
@@ -872,7 +876,7 @@ template <class TD, class TF> void precisionChange(int64_t n, Spinor<TD> *out, c
 
 // ref: Grid/algorithms/iterative/ConjugateGradientMixedPrec.h:71-167
 inline MixedCGResult MixedPrecisionCG(const FermOp<double> &op_d, const FermOp<float> &op_f, int cb, const Spinor<double> *src_d_in,
-                                      Spinor<double> *sol_d, double tol, int maxinner, int maxouter, double inner_tol0 = -1.0) {
+                                      Spinor<double> *sol_d, double tol, int maxinner, int maxouter, double inner_tol0 = -1.0, double shift = 0.0) {
   const int64_t n = op_d.V5cb();
   MixedCGResult R;
   const double src_norm = norm2(n, src_d_in), stop = src_norm * tol * tol, OuterLoopNormMult = 100.0;
@@ -882,18 +886,19 @@ inline MixedCGResult MixedPrecisionCG(const FermOp<double> &op_d, const FermOp<f
   int outer;
   for (outer = 0; outer < maxouter; outer++) {
     op_d.HermOp(sol_d, tmp_d.data(), cb);
+    if (shift != 0.0) axpy(n, tmp_d.data(), shift, sol_d, tmp_d.data());
     double norm = axpy_norm(n, src_d.data(), -1.0, tmp_d.data(), src_d_in);
     if (norm < OuterLoopNormMult * stop) break;
     while (norm * inner_tol * inner_tol < stop) inner_tol *= 2;
     precisionChange(n, src_f.data(), src_d.data());
     std::memset((void *)sol_f.data(), 0, sizeof(Spinor<float>) * n);
-    CGResult in = ConjugateGradient(op_f, cb, src_f.data(), sol_f.data(), inner_tol, maxinner);
+    CGResult in = ConjugateGradient(op_f, cb, src_f.data(), sol_f.data(), inner_tol, maxinner, shift);
     R.inner_iterations += in.iterations;
     precisionChange(n, tmp_d.data(), sol_f.data());
     axpy(n, sol_d, 1.0, tmp_d.data(), sol_d);
   }
   R.outer_iterations = outer;
-  CGResult fin = ConjugateGradient(op_d, cb, src_d_in, sol_d, tol, maxinner);
+  CGResult fin = ConjugateGradient(op_d, cb, src_d_in, sol_d, tol, maxinner, shift);
   R.final_iterations = fin.iterations; R.true_residual = fin.true_residual; R.converged = fin.converged;
   return R;
 }

@@ -478,6 +478,36 @@ void gref_relup_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d,
   export_lex(x, sol_d);
 }
 
+// ConjugateGradientMultiShiftMixedPrec as tests/solver/Test_dwf_multishift_mixedprec.cc:121-126 drives it, explicit poles / tolerances.
+// out_iters: [per-shift IterationsToCompleteShift..., IterationsToComplete, 0]
+void gref_multishift_mixed_cg(void *h_d, void *h_f, int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit,
+                              int relup_freq, void *results, int *out_iters, double *out_true_resid) {
+  auto *bd = dynamic_cast<WilsonBox<WilsonImplD, vComplexD> *>((BoxBase *)h_d);
+  auto *bf = dynamic_cast<WilsonBox<WilsonImplF, vComplexF> *>((BoxBase *)h_f);
+  assert(bd && bf);
+  typedef FermionOperator<WilsonImplD> OpD;
+  typedef FermionOperator<WilsonImplF> OpF;
+  SchurDiagMooeeOperator<OpD, LatticeFermionD> Sd(*bd->op);
+  SchurDiagMooeeOperator<OpF, LatticeFermionF> Sf(*bf->op);
+  MultiShiftFunction shifts(nshift, 0.0, 1.0);
+  shifts.order = nshift; shifts.norm = 0.0;
+  for (int s = 0; s < nshift; s++) { shifts.poles[s] = poles[s]; shifts.tolerances[s] = tols[s]; shifts.residues[s] = 1.0; }
+  ConjugateGradientMultiShiftMixedPrec<LatticeFermionD, LatticeFermionF> mcg(maxit, shifts, bf->frbgrid(), Sf, relup_freq);
+  LatticeFermionD s(bd->frbgrid());
+  import_lex(s, src);
+  s.Checkerboard() = cb;
+  std::vector<LatticeFermionD> res(nshift, bd->frbgrid());
+  for (auto &f : res) f.Checkerboard() = cb;
+  mcg(Sd, s, res);
+  typedef LatticeFermionD::vector_object::scalar_object sobj;
+  const size_t n = bd->frbgrid()->lSites();
+  for (int i = 0; i < nshift; i++) {
+    export_lex(res[i], (char *)results + (size_t)i * n * sizeof(sobj));
+    out_iters[i] = mcg.IterationsToCompleteShift[i]; out_true_resid[i] = mcg.TrueResidualShift[i];
+  }
+  out_iters[nshift] = mcg.IterationsToComplete; out_iters[nshift + 1] = 0;
+}
+
 // Timed loop for the CPU baseline: fields stay resident in Grid's own layout; returns seconds for ncall applications.
 double gref_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
   BoxBase *b = (BoxBase *)h;

@@ -325,6 +325,18 @@ void orc_multishift_cg(void *h, int staggered, int cb, const void *src, int nshi
   for (int s = 0; s < nshift; s++) { out_iters[s] = R.iterations[s]; out_true_resid[s] = R.true_residual[s]; }
   out_iters[nshift] = R.iterations_to_complete; out_iters[nshift + 1] = R.converged;
 }
+// ConjugateGradientMultiShiftMixedPrec.  out_iters: [per-shift iterations..., IterationsToComplete, number of clean-up solves]
+void orc_multishift_mixed_cg(void *h_d, void *h_f, int cb, const void *src, int nshift, const double *poles, const double *tols, int maxit,
+                             int relup_freq, void *results, int *out_iters, double *out_true_resid) {
+  OpBox *bd = (OpBox *)h_d, *bf = (OpBox *)h_f;
+  const int64_t n = bd->d.V5cb();
+  std::vector<Spinor<double> *> psi(nshift);
+  for (int s = 0; s < nshift; s++) psi[s] = (Spinor<double> *)results + (size_t)s * n;
+  MultiShiftMixedResult R = MultiShiftMixedPrecCG(bd->d, bf->f, cb, (const Spinor<double> *)src, psi, std::vector<double>(poles, poles + nshift),
+                                                  std::vector<double>(tols, tols + nshift), maxit, relup_freq);
+  for (int s = 0; s < nshift; s++) { out_iters[s] = R.iterations[s]; out_true_resid[s] = R.true_residual[s]; }
+  out_iters[nshift] = R.iterations_to_complete; out_iters[nshift + 1] = R.cleanups;
+}
 double orc_stag_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
   auto t0 = std::chrono::steady_clock::now();
   for (int i = 0; i < ncall; i++) orc_stag_apply(h, which, in, out, dag, cb_in, half);

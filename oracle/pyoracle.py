@@ -53,6 +53,7 @@ def lib():
         L.orc_schur_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_relup_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.orc_multishift_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_time_apply.restype = C.c_double
@@ -370,3 +371,15 @@ def relup_cg(op_d, op_f, cb, src_d, tol, maxit, delta):
     tr = np.zeros(1, dtype=np.float64)
     lib().orc_relup_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxit, delta, _ptr(it), _ptr(tr))
     return sol, dict(iterations=int(it[0]), reliable_updates=int(it[1]), cleanup_iterations=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))
+
+
+def multishift_mixed_cg(op_d, op_f, cb, src_d, poles, tols, maxit, relup_freq):
+    """ConjugateGradientMultiShiftMixedPrec(maxit, shifts, ..., Linop_f, relup_freq)(Linop_d, src, results)."""
+    src = np.ascontiguousarray(src_d, dtype=np.complex128)
+    poles = np.ascontiguousarray(poles, dtype=np.float64); tols = np.ascontiguousarray(tols, dtype=np.float64)
+    n = len(poles)
+    res = np.zeros((n,) + src.shape, dtype=src.dtype)
+    it = np.zeros(n + 2, dtype=np.int32)
+    tr = np.zeros(n, dtype=np.float64)
+    lib().orc_multishift_mixed_cg(op_d.h, op_f.h, cb, _ptr(src), n, _ptr(poles), _ptr(tols), maxit, relup_freq, _ptr(res), _ptr(it), _ptr(tr))
+    return res, dict(iterations=[int(x) for x in it[:n]], true_residual=[float(x) for x in tr], iterations_to_complete=int(it[n]), cleanups=int(it[n + 1]))

@@ -57,6 +57,7 @@ def lib():
         L.gref_schur_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_cg.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_relup_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
+        L.gref_multishift_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gref_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.gref_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.gref_time_apply.restype = C.c_double
@@ -261,3 +262,15 @@ def nersc_read(dims, path):
     pl = np.zeros(2)
     lib().gref_nersc_read((C.c_int * 4)(*dims), _ptr(U), str(path).encode(), _ptr(pl))
     return U, float(pl[0]), float(pl[1])
+
+
+def multishift_mixed_cg(op_d, op_f, cb, src_d, poles, tols, maxit, relup_freq):
+    """ConjugateGradientMultiShiftMixedPrec(maxit, shifts, ..., Linop_f, relup_freq)(Linop_d, src, results)."""
+    src = np.ascontiguousarray(src_d, dtype=np.complex128)
+    poles = np.ascontiguousarray(poles, dtype=np.float64); tols = np.ascontiguousarray(tols, dtype=np.float64)
+    n = len(poles)
+    res = np.zeros((n,) + src.shape, dtype=src.dtype)
+    it = np.zeros(n + 2, dtype=np.int32)
+    tr = np.zeros(n, dtype=np.float64)
+    lib().gref_multishift_mixed_cg(op_d.h, op_f.h, cb, _ptr(src), n, _ptr(poles), _ptr(tols), maxit, relup_freq, _ptr(res), _ptr(it), _ptr(tr))
+    return res, dict(iterations=[int(x) for x in it[:n]], true_residual=[float(x) for x in tr], iterations_to_complete=int(it[n]), cleanups=int(it[n + 1]))

@@ -175,4 +175,96 @@ inline RelUpResult ReliableUpdateCG(const FermOp<double> &op_d, const FermOp<flo
   return R;
 }
 
+// ConjugateGradientMultiShiftMixedPrec   ref: Grid/algorithms/iterative/ConjugateGradientMultiShiftMixedPrec.h:128-410
+// The multishift recurrences with fp64 vectors and an fp32 operator application per iteration; every ReliableUpdateFreq
+// iterations the residual is replaced by the true fp64 residual of the primary shift; each shift that misses its tolerance at
+// the end is cleaned up with MixedPrecisionConjugateGradient on HermOp + pole.
+struct MultiShiftMixedResult { std::vector<int> iterations; std::vector<double> true_residual; int iterations_to_complete = 0; int cleanups = 0; };
+inline MultiShiftMixedResult MultiShiftMixedPrecCG(const FermOp<double> &op_d, const FermOp<float> &op_f, int cb, const Spinor<double> *src,
+                                                   std::vector<Spinor<double> *> psi, const std::vector<double> &mass,
+                                                   const std::vector<double> &mresidual, int maxit, int relup_freq) {
+  typedef Spinor<double> FD; typedef Spinor<float> FF;
+  const int64_t n = op_d.V5cb();
+  const int nshift = (int)mass.size();
+  MultiShiftMixedResult R;
+  R.iterations.assign(nshift, 0); R.true_residual.assign(nshift, 0.0);
+  std::vector<double> alpha(nshift, 1.0), bs(nshift), rsq(nshift);
+  std::vector<std::array<double, 2>> z(nshift);
+  std::vector<int> converged(nshift, 0);
+  std::vector<std::vector<FD>> ps(nshift, std::vector<FD>(n));
+  std::vector<FD> p(src, src + n), r(src, src + n), tmp(n), mmp(n);
+  std::vector<FF> p_f(n), mmp_f(n);
+  double a, b, c, d, cp, bp;
+  cp = norm2(n, src);
+  if (cp == 0.0) { for (int s = 0; s < nshift; s++) { std::memset((void *)psi[s], 0, sizeof(FD) * n); R.iterations[s] = 1; } return R; }
+  for (int s = 0; s < nshift; s++) { rsq[s] = cp * mresidual[s] * mresidual[s]; std::copy(src, src + n, ps[s].begin()); }
+  op_d.HermOp(p.data(), mmp.data(), cb);                    // the reference also applies Linop_f here, only to compare (:203-209)
+  d = innerProduct(n, p.data(), mmp.data()).re;
+  axpy(n, mmp.data(), mass[0], p.data(), mmp.data());
+  double rn = norm2(n, p.data());
+  d += rn * mass[0];
+  b = -cp / d;
+  int iz = 0;
+  z[0][1 - iz] = 1.0; z[0][iz] = 1.0; bs[0] = b;
+  for (int s = 1; s < nshift; s++) { z[s][1 - iz] = 1.0; z[s][iz] = 1.0 / (1.0 - b * (mass[s] - mass[0])); bs[s] = b * z[s][iz]; }
+  c = axpy_norm(n, r.data(), b, mmp.data(), r.data());
+  for (int s = 0; s < nshift; s++) axpby(n, psi[s], 0.0, -bs[s] * alpha[s], src, src);
+  for (int k = 1; k <= maxit; k++) {
+    a = c / cp;
+    axpy(n, p.data(), a, p.data(), r.data());
+    for (int s = 0; s < nshift; s++) if (!converged[s]) {
+      if (s == 0) axpy(n, ps[s].data(), a, ps[s].data(), r.data());
+      else { const double as = a * z[s][iz] * bs[s] / (z[s][1 - iz] * b); axpby(n, ps[s].data(), z[s][iz], as, r.data(), ps[s].data()); }
+    }
+    precisionChange(n, p_f.data(), p.data());
+    cp = c;
+    op_f.HermOp(p_f.data(), mmp_f.data(), cb);
+    precisionChange(n, mmp.data(), mmp_f.data());
+    d = innerProduct(n, p.data(), mmp.data()).re;
+    axpy(n, mmp.data(), mass[0], p.data(), mmp.data());
+    rn = norm2(n, p.data());
+    d += rn * mass[0];
+    bp = b;
+    b = -cp / d;
+    bs[0] = b;
+    iz = 1 - iz;
+    for (int s = 1; s < nshift; s++) if (!converged[s]) {
+      const double z0 = z[s][1 - iz], z1 = z[s][iz];
+      z[s][iz] = z0 * z1 * bp / (b * a * (z1 - z0) + z1 * bp * (1 - (mass[s] - mass[0]) * b));
+      bs[s] = b * z[s][iz] / z0;
+    }
+    for (int s = 0; s < nshift; s++) if (!converged[s]) axpy(n, psi[s], -bs[s] * alpha[s], ps[s].data(), psi[s]);
+    c = axpy_norm(n, r.data(), b, mmp.data(), r.data());
+    if (k % relup_freq == 0) {           // replace r with the true residual of the primary shift
+      op_d.HermOp(psi[0], mmp.data(), cb);
+      axpy(n, mmp.data(), mass[0], psi[0], mmp.data());
+      c = axpy_norm(n, r.data(), -1.0, mmp.data(), src);
+    }
+    int all_converged = 1;
+    for (int s = 0; s < nshift; s++) if (!converged[s]) {
+      R.iterations[s] = k;
+      if (c * z[s][iz] * z[s][iz] < rsq[s]) converged[s] = 1; else all_converged = 0;
+    }
+    if (all_converged || k == maxit - 1) {
+      const double cn = norm2(n, src);
+      for (int s = 0; s < nshift; s++) {
+        op_d.HermOp(psi[s], mmp.data(), cb);
+        axpy(n, tmp.data(), mass[s], psi[s], mmp.data());
+        axpy(n, r.data(), -alpha[s], src, tmp.data());
+        rn = norm2(n, r.data());
+        R.true_residual[s] = std::sqrt(rn / cn);
+        if (rn >= rsq[s]) {              // clean up with mixed-precision CG on HermOp + pole (:382-396)
+          MixedCGResult m = MixedPrecisionCG(op_d, op_f, cb, src, psi[s], mresidual[s], 20000, 20000, -1.0, mass[s]);
+          R.true_residual[s] = m.true_residual;
+          R.cleanups++;
+        }
+      }
+      R.iterations_to_complete = k;
+      return R;
+    }
+  }
+  R.iterations_to_complete = maxit;      // the reference asserts here (:408)
+  return R;
+}
+
 } // namespace oracle

@@ -83,6 +83,11 @@ def main():
     out["mobius/relup_cg/solution"] = x
     for k in ("iterations", "reliable_updates", "cleanup_iterations", "true_residual"):
         out[f"mobius/relup_cg/{k}"] = np.array(info[k])
+    # Row f3, ConjugateGradientMultiShiftMixedPrec (ref: ConjugateGradientMultiShiftMixedPrec.h:128-410), reliable update every 20 iterations
+    xs, info = pr.multishift_mixed_cg(ops["mobius"][0], opf, 1, ops["mobius"][0].pick_checkerboard(1, src5), MS_POLES, MS_TOLS, 5000, 20)
+    out["mobius/multishift_mixed/solutions"] = xs
+    for k in ("iterations", "true_residual", "iterations_to_complete"):
+        out[f"mobius/multishift_mixed/{k}"] = np.array(info[k])
     path = os.path.join(HERE, "next_golden.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1e6:.2f} MB", file=sys.stderr)

@@ -92,6 +92,47 @@ def test_oracle_vs_reference_multishift(prec):
         assert site_err(a[s], b[s]) < (1e-7 if prec else 1e-3)
 
 
+def check_mixed_against_fixture(xs, iters, true_resid, to_complete):
+    ref_it = [int(x) for x in N["mobius/multishift_mixed/iterations"]]
+    for s, (a, b) in enumerate(zip(iters, ref_it)):
+        assert abs(a - b) <= max(1, 0.02 * b), (s, iters, ref_it)
+    assert abs(to_complete - int(N["mobius/multishift_mixed/iterations_to_complete"])) <= max(1, 0.02 * ref_it[0])
+    for s in range(len(POLES)):
+        assert true_resid[s] < 1.3 * TOLS[s], (s, true_resid)                 # after the clean-up solves every shift meets its tolerance
+        assert site_err(xs[s], N["mobius/multishift_mixed/solutions"][s]) < 1e-6, s
+
+
+def test_oracle_multishift_mixed_prec_matches_reference_outputs():
+    """ConjugateGradientMultiShiftMixedPrec (ref: ConjugateGradientMultiShiftMixedPrec.h:128-410): fp32 operator, fp64 vectors,
+    true-residual replacement every 20 iterations, mixed-precision clean-up of the shifts that miss their tolerance."""
+    od, src = oracle_case("mobius")
+    of = po.OracleOp(1, DIMS, LS, mass=0.1, M5=1.8, b=1.5, c=0.5, prec=0); of.import_gauge(G["U"])
+    xs, info = po.multishift_mixed_cg(od, of, 1, src, POLES, TOLS, 5000, 20)
+    check_mixed_against_fixture(xs, info["iterations"], info["true_residual"], info["iterations_to_complete"])
+    x64, _ = od.multishift_cg(1, src, POLES, TOLS, 5000)
+    for s in range(len(POLES)):
+        assert site_err(xs[s], x64[s]) < 1e-6                                  # same answers as the all-fp64 multishift
+
+
+@pytest.mark.skipif(not pr.available(), reason="oracle/_ref/libgridref.so not built (needs /root/reference)")
+@pytest.mark.parametrize("freq", [10, 50])
+def test_oracle_vs_reference_multishift_mixed_prec(freq):
+    dims, Ls = (4, 6, 8, 4), 6
+    U = syn.hot_gauge(dims, seed=21)
+    mk = lambda mod, prec: mod(1, dims, Ls, mass=0.1, M5=1.8, b=1.5, c=0.5, prec=prec)
+    od, of, rd, rf = mk(po.OracleOp, 1), mk(po.OracleOp, 0), mk(pr.RefOp, 1), mk(pr.RefOp, 0)
+    for o in (od, of, rd, rf):
+        o.import_gauge(U)
+    src = po.pick_checkerboard(dims, Ls, 1, syn.random_fermion(dims, Ls, seed=3))
+    poles, tols = [0.02, 0.2, 2.0], [1e-9, 1e-9, 1e-8]
+    a, ia = po.multishift_mixed_cg(od, of, 1, src, poles, tols, 3000, freq)
+    b, ib = pr.multishift_mixed_cg(rd, rf, 1, src, poles, tols, 3000, freq)
+    for x, y in zip(ia["iterations"], ib["iterations"]):
+        assert abs(x - y) <= max(1, 0.02 * y), (ia, ib)
+    for s in range(3):
+        assert site_err(a[s], b[s]) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------- GPU
 def _device_case(gb, name, prec):
     ctx = gb.Context(0)
@@ -177,3 +218,15 @@ def test_dwf_multishift_driver():
     p = subprocess.run([exe, "--grid", "8.8.8.8", "--Ls", "8"], capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "PASS" in p.stdout
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cuda_multishift_mixed_prec_matches_reference():
+    import grid_b200 as gb
+    ctx, Dd, lin_d, src, mk = _device_case(gb, "mobius", gb.F64)
+    Df = gb.MobiusFermion(gb.LatticeGaugeField(src.grid, gb.F32).import_lex(G["U"]), src.grid, LS, 0.1, 1.8, 1.5, 0.5)
+    results = [mk() for _ in POLES]
+    mcg = gb.ConjugateGradientMultiShiftMixedPrec(5000, gb.MultiShiftFunction(POLES, TOLS), gb.SchurDiagMooeeOperator(Df), 20)
+    mcg(lin_d, src, results)
+    check_mixed_against_fixture([r.export_lex() for r in results], mcg.IterationsToCompleteShift, mcg.TrueResidualShift, mcg.IterationsToComplete)
