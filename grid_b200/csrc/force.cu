@@ -8,6 +8,7 @@
 // and the -1/2 prefactor are the hopping term's own, so DhopDir summed over the eight legs IS Dhop.
 #include "fermop.hpp"
 #include "kernels_common.cuh"
+#include "next_kernels.cuh"
 
 namespace gb {
 
@@ -48,48 +49,12 @@ void op_dhop_leg_cb(gb_fermop *op, const gb_fermion *in, gb_fermion *out, int po
   out->cb = po;
 }
 
-// mat[lex][mu][c1][c2] = sign * sum_s sum_spin Btilde(x,s)[spin][c1] * conj(A(x,s)[spin][c2])
-// one thread per (parity, cb site, c1*3 + c2) for npar parities starting at p0; fields in the blocked layout (internal.hpp):
-// Bt / A point at the block of parity p0; mat is the full lexicographic gauge field (sites of other parities untouched)
+// one thread per (parity, cb site, c1*3 + c2); the body is insert_force_elem (next_kernels.cuh, shared with the CPU emulation)
 template <class T>
 __global__ void insert_force_kernel(T *__restrict__ mat, const typename Prec<T>::vec *__restrict__ Bt, const typename Prec<T>::vec *__restrict__ A,
                                     int Ls, int Lx, int Ly, int Lz, int origin_parity, uint32_t V4cb, size_t parity_stride /* vecs */, int mu,
                                     int p0, int npar, T sign) {
-  using P = Prec<T>;
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (uint32_t)npar * V4cb * 9) return;
-  const uint32_t k9 = e % 9, sp_ = e / 9;
-  const uint32_t pj = sp_ / V4cb, site = sp_ - pj * V4cb;
-  const uint32_t p = (uint32_t)p0 + pj;
-  const int c1 = k9 / 3, c2 = k9 - 3 * c1;
-  const int Lxh = Lx / 2;
-  uint32_t r = site;
-  const int xh = r % Lxh; r /= Lxh;
-  const int y = r % Ly; r /= Ly;
-  const int z = r % Lz;
-  const int t = r / Lz;
-  const int x = 2 * xh + ((p + origin_parity + y + z + t) & 1);
-  const size_t lex = x + (size_t)Lx * (y + (size_t)Ly * (z + (size_t)Lz * t));
-  const T *bs = (const T *)(Bt + (size_t)pj * parity_stride);
-  const T *as = (const T *)(A + (size_t)pj * parity_stride);
-  constexpr int CPV = sizeof(T) == 4 ? 2 : 1;          // complex numbers per 16-byte vec
-  T re = 0, im = 0;
-  for (int s = 0; s < Ls; s++) {
-    const uint32_t i5 = site * Ls + s;
-    const size_t base = ((size_t)(i5 >> LOGW) * P::NV) << LOGW;   // vec index of element (i5, k = 0) minus the lane
-    const uint32_t lane = i5 & (W - 1);
-#pragma unroll
-    for (int spin = 0; spin < 4; spin++) {
-      const int kb = spin * 3 + c1, ka = spin * 3 + c2;            // complex component index 0..11
-      const size_t ob = ((base + ((size_t)(kb / CPV) << LOGW) + lane) * CPV + (kb % CPV)) * 2;
-      const size_t oa = ((base + ((size_t)(ka / CPV) << LOGW) + lane) * CPV + (ka % CPV)) * 2;
-      const T br = bs[ob], bi = bs[ob + 1], ar = as[oa], ai = as[oa + 1];
-      re += br * ar + bi * ai;     // b * conj(a)
-      im += bi * ar - br * ai;
-    }
-  }
-  T *m = mat + ((lex * 4 + mu) * 9 + k9) * 2;
-  m[0] = sign * re; m[1] = sign * im;
+  insert_force_elem<T>(blockIdx.x * blockDim.x + threadIdx.x, mat, Bt, A, Ls, Lx, Ly, Lz, origin_parity, V4cb, parity_stride, mu, p0, npar, sign);
 }
 
 static void insert_force(gb_fermop *op, gb_gauge *mat, const gb_fermion *Btilde, const gb_fermion *A, int mu, double sign = 1.0) {

@@ -6,31 +6,16 @@
 // halves of a 4D spinor field into / out of the s = 0 and s = Ls-1 walls of a 5D field.
 #include "fermop.hpp"
 #include "kernels_common.cuh"
+#include "next_kernels.cuh"
 #include <cmath>
 
 namespace gb {
 
-// One thread per 16-byte vec of the 4D field (all parity blocks).  Vec k of a spinor holds upper spin components (P+) for
-// k < NV/2 and lower ones (P-) otherwise, so the chiral projectors are a choice of wall per vec, never arithmetic.
-//   DIR 0: f5[s = s_up] <- upper half of f4, f5[s = s_lo] <- lower half   (f5 zeroed beforehand)
-//   DIR 1: f4 upper half <- f5[s = s_up], f4 lower half <- f5[s = s_lo]
+// one thread per 16-byte vec of the 4D field; the body is chiral_wall_elem (next_kernels.cuh, shared with the CPU emulation)
 template <class T, int DIR>
 __global__ void chiral_wall_kernel(typename Prec<T>::vec *f4, typename Prec<T>::vec *f5, int nparity, uint32_t nsite4, uint32_t hblk4,
                                    uint32_t hblk5, int Ls, int s_up, int s_lo) {
-  using P = Prec<T>;
-  const uint32_t per_block = hblk4 * P::NV * W;
-  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= per_block * (uint32_t)nparity) return;
-  const uint32_t p = e / per_block, ep = e - p * per_block;
-  const uint32_t lane = ep & (W - 1);
-  const uint32_t r = ep >> LOGW;
-  const uint32_t blk = r / P::NV, k = r - blk * P::NV;
-  const uint32_t i4 = blk * W + lane;
-  if (i4 >= nsite4) return;
-  const uint32_t i5 = i4 * (uint32_t)Ls + (uint32_t)(k < P::NV / 2 ? s_up : s_lo);
-  const size_t a5 = (size_t)p * hblk5 * P::NV * W + ((((size_t)(i5 >> LOGW)) * P::NV + k) << LOGW) + (i5 & (W - 1));
-  if (DIR == 0) f5[a5] = f4[e];
-  else f4[e] = f5[a5];
+  chiral_wall_elem<T, DIR>(blockIdx.x * blockDim.x + threadIdx.x, f4, f5, nparity, nsite4, hblk4, hblk5, Ls, s_up, s_lo);
 }
 
 static void chk(int rc) { if (rc != GB_OK) throw Error(rc, gb_last_error()); }
