@@ -24,3 +24,9 @@ if [ "$ngpu" -ge 2 ]; then
   cat $out/halo_bench_n${n}.jsonl
 fi
 python scripts/stag_bench.py 48 100 > $out/stag_bench_n1.jsonl 2>&1; cat $out/stag_bench_n1.jsonl
+# 5. BASELINE configs[3] weak-scaling series at ITS local volume (64.64.32.16 x Ls16 per GPU): 1 GPU and N GPUs
+python bench.py --gpus 1 --local 64 64 32 16 --steps 100 --warmup 5 --no-cpu --no-cg --e2e-steps 1 > $out/bench_c4_n1.json 2>$out/bench_c4_n1.err
+if [ "$ngpu" -ge 2 ]; then
+  timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29566 bench.py --gpus $n --local 64 64 32 16 --steps 100 --warmup 5 --no-cpu --no-cg --e2e-steps 1 > $out/bench_c4_n${n}.json 2>$out/bench_c4_n${n}.err
+fi
+grep -o '"ms_per_step": [0-9.]*' $out/bench_c4_n*.json
