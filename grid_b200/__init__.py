@@ -57,6 +57,7 @@ SYMBOLS = [
     ("gb_op_dhop_host", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
+    ("gb_mixed_cg_schur_ex", _i, [_vp, _vp, _vp, _vp, _d, _d, _d, _i, _i, _pi, _pd]),
     ("gb_op_dhop_dir", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_dhop_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mderiv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_op_meooe_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mpc_deriv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_relup_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _d, _pi, _pd]),
@@ -625,13 +626,14 @@ class MixedPrecisionConjugateGradient:
     def __init__(self, tol, maxinnerit, maxouterit, Linop_f, Linop_d):
         self.Tolerance, self.MaxInnerIterations, self.MaxOuterIterations = tol, maxinnerit, maxouterit
         self.Linop_f, self.Linop_d = Linop_f, Linop_d
+        self.InnerTolerance, self.OuterLoopNormMult = tol, 100.0      # public tuning members, ref :41-45,:64-65
         self.TotalInnerIterations = self.TotalOuterIterations = self.TotalFinalStepIterations = 0
         self.TrueResidual = 0.0
 
     def __call__(self, src_d, sol_d):
         it, tr = (C.c_int * 3)(), C.c_double()
-        rc = lib().gb_mixed_cg_schur(self.Linop_f._Mat.h, self.Linop_d._Mat.h, src_d.h, sol_d.h, self.Tolerance,
-                                     self.MaxInnerIterations, self.MaxOuterIterations, it, C.byref(tr))
+        rc = lib().gb_mixed_cg_schur_ex(self.Linop_f._Mat.h, self.Linop_d._Mat.h, src_d.h, sol_d.h, self.Tolerance, self.InnerTolerance,
+                                        self.OuterLoopNormMult, self.MaxInnerIterations, self.MaxOuterIterations, it, C.byref(tr))
         self.TotalInnerIterations, self.TotalOuterIterations, self.TotalFinalStepIterations = it[0], it[1], it[2]
         self.TrueResidual = tr.value
         _chk(rc)

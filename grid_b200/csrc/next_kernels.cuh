@@ -1,6 +1,6 @@
 // next_kernels.cuh -- per-element bodies of the small kernels behind the SURVEY 8(f) rows (schur.cu, force.cu), written as
 // __host__ __device__ functions of the global thread index so that tests/host/next_kernels_emul.cu can run exactly the code
-// the GPU runs, on the CPU, against the oracle (the same idea as stag_halo.cuh).
+// the GPU runs, on the CPU, against independently computed expectations (the same idea as stag_halo.cuh).
 #pragma once
 #include "internal.hpp"
 

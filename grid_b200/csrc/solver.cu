@@ -427,7 +427,7 @@ int gb_cg(gb_context *ctx, gb_hermop_fn hermop, void *user, const gb_fermion *sr
 
 struct MixedOut { int inner = 0, outer = 0, fin = 0; double true_resid = 0; bool converged = false; };
 static MixedOut mixed_cg_core(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, int max_inner, int max_outer,
-                              double shift);
+                              double shift, double inner_tol0 = -1.0, double outer_loop_norm_mult = 100.0);
 int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, int max_inner,
                       int max_outer, int iters_out[3], double *true_resid_out) {
   GB_API_BEGIN
@@ -437,10 +437,21 @@ int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_
   if (!o.converged) throw Error(GB_ERR_NOT_CONVERGED, "MixedPrecisionConjugateGradient final solve did NOT converge");
   GB_API_END
 }
+// the same with the class's public tuning members: InnerTolerance (<= 0: Tolerance) and OuterLoopNormMult   ref: ConjugateGradientMixedPrec.h:41-45
+int gb_mixed_cg_schur_ex(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, double inner_tol,
+                         double outer_loop_norm_mult, int max_inner, int max_outer, int iters_out[3], double *true_resid_out) {
+  GB_API_BEGIN
+  GB_REQUIRE(outer_loop_norm_mult > 0, "OuterLoopNormMult must be positive");
+  MixedOut o = mixed_cg_core(op_f, op_d, src_d_in, sol_d, tol, max_inner, max_outer, 0.0, inner_tol, outer_loop_norm_mult);
+  if (iters_out) { iters_out[0] = o.inner; iters_out[1] = o.outer; iters_out[2] = o.fin; }
+  if (true_resid_out) *true_resid_out = o.true_resid;
+  if (!o.converged) throw Error(GB_ERR_NOT_CONVERGED, "MixedPrecisionConjugateGradient final solve did NOT converge");
+  GB_API_END
+}
 } // extern "C"
 // MixedPrecisionConjugateGradient on HermOp (+ shift)   ref: ConjugateGradientMixedPrec.h:71-167
 static MixedOut mixed_cg_core(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, int max_inner, int max_outer,
-                              double shift) {
+                              double shift, double inner_tol0, double outer_loop_norm_mult) {
   GB_REQUIRE(op_f && op_d && src_d_in && sol_d, "null argument");
   GB_REQUIRE(op_f->prec == GB_F32 && op_d->prec == GB_F64, "mixed CG needs an fp32 and an fp64 operator");
   GB_REQUIRE(src_d_in->prec == GB_F64 && sol_d->prec == GB_F64, "mixed CG outer fields must be fp64");
@@ -459,8 +470,8 @@ static MixedOut mixed_cg_core(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion
   double src_norm;
   chk(gb_norm2(src_d_in, &src_norm));
   const double stop = src_norm * tol * tol;
-  const double OuterLoopNormMult = 100.0;
-  double inner_tol = tol;
+  const double OuterLoopNormMult = outer_loop_norm_mult;     // public member of the reference's class, default 100 (ref :45,:65)
+  double inner_tol = inner_tol0 > 0 ? inner_tol0 : tol;     // InnerTolerance, defaults to Tolerance (ref :41,:64)
   int total_inner = 0, outer;
   auto Ad = [&](const gb_fermion *in, gb_fermion *out) { op_apply(op_d, GB_OP_HERMOP, in, out, 0); if (shift != 0.0) chk(gb_axpy(out, shift, in, out)); };
   chk(gb_copy(src_d, src_d_in));

@@ -271,6 +271,9 @@ int gb_cg(gb_context *ctx, gb_hermop_fn hermop, void *user, const gb_fermion *sr
  * iters_out[3] = {TotalInnerIterations, TotalOuterIterations, TotalFinalStepIterations} */
 int gb_mixed_cg_schur(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d, gb_fermion *sol_d, double tol, int max_inner,
                       int max_outer, int iters_out[3], double *true_resid_out);
+/* the same with the class's public tuning members InnerTolerance (<= 0: = Tolerance) and OuterLoopNormMult (default 100)  ref: :41-45,:64-65 */
+int gb_mixed_cg_schur_ex(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d, gb_fermion *sol_d, double tol, double inner_tol,
+                         double outer_loop_norm_mult, int max_inner, int max_outer, int iters_out[3], double *true_resid_out);
 
 
 /* ConjugateGradientReliableUpdate(tol, maxit, Delta, sp_grid, Linop_f, Linop_d)(src, psi) on the Schur operators of op_f (fp32)

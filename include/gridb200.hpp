@@ -339,7 +339,8 @@ private:
 
 template <class FieldD, class FieldF> class MixedPrecisionConjugateGradient {
 public:
-  RealD Tolerance, InnerTolerance;
+  RealD Tolerance, InnerTolerance;      // InnerTolerance: initial tolerance of the inner CG, defaults to Tolerance (ref :41)
+  RealD OuterLoopNormMult = 100.;       // ref :45
   Integer MaxInnerIterations, MaxOuterIterations;
   GridBase *SinglePrecGrid;
   LinearOperatorBase<FieldF> &Linop_f;
@@ -352,7 +353,7 @@ public:
     gb_fermop *mf = Linop_f.FusedSchurMatrix(), *md = Linop_d.FusedSchurMatrix();
     assert(mf && md && "MixedPrecisionConjugateGradient needs SchurDiagMooeeOperator arguments");
     int it[3];
-    int rc = gb_mixed_cg_schur(mf, md, src.h, sol.h, Tolerance, MaxInnerIterations, MaxOuterIterations, it, &TrueResidual);
+    int rc = gb_mixed_cg_schur_ex(mf, md, src.h, sol.h, Tolerance, InnerTolerance, OuterLoopNormMult, MaxInnerIterations, MaxOuterIterations, it, &TrueResidual);
     TotalInnerIterations = it[0]; TotalOuterIterations = it[1]; TotalFinalStepIterations = it[2];
     GB_ASSERT_OK(rc);
   }
