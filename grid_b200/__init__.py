@@ -545,6 +545,22 @@ class LinearOperatorBase:
         return innerProduct(i, o).real, norm2(o)
 
 
+class MdagMLinearOperator(LinearOperatorBase):
+    """ref: LinearOperator.h:74-105 -- the unpreconditioned normal operator on the full grid: HermOp = Mdag M.  ConjugateGradient
+    drives it through the generic (virtual HermOp) path."""
+
+    def __init__(self, Mat):
+        self._Mat = Mat
+
+    def Op(self, i, o): self._Mat.M(i, o)
+    def AdjOp(self, i, o): self._Mat.Mdag(i, o)
+
+    def HermOp(self, i, o):
+        tmp = i.like()
+        self._Mat.M(i, tmp)
+        self._Mat.Mdag(tmp, o)
+
+
 class SchurDiagMooeeOperator(LinearOperatorBase):
     """ref: LinearOperator.h:325-349.  Mpc = Mooee - Meooe MooeeInv Meooe ; HermOp = MpcDag Mpc."""
 

@@ -258,6 +258,15 @@ public:
   }
   virtual gb_fermop *FusedSchurMatrix() { return nullptr; } // non-null: CG may use the fused device path
 };
+// MdagMLinearOperator (ref: LinearOperator.h:74-105): the unpreconditioned normal operator on the full grid, HermOp = Mdag M
+template <class Matrix, class Field> class MdagMLinearOperator : public LinearOperatorBase<Field> {
+public:
+  Matrix &_Mat;
+  explicit MdagMLinearOperator(Matrix &Mat) : _Mat(Mat) {}
+  void Op(const Field &in, Field &out) override { _Mat.M(in, out); }
+  void AdjOp(const Field &in, Field &out) override { _Mat.Mdag(in, out); }
+  void HermOp(const Field &in, Field &out) override { Field tmp(in.Grid()); _Mat.M(in, tmp); _Mat.Mdag(tmp, out); }
+};
 template <class Matrix, class Field> class SchurDiagMooeeOperator : public LinearOperatorBase<Field> {
 public:
   Matrix &_Mat;

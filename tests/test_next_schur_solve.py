@@ -294,3 +294,23 @@ def test_dwf_cg_schur_driver():
     p = subprocess.run([exe, "--grid", "8.8.8.8", "--Ls", "8"], capture_output=True, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "true unprec resid" in p.stdout and "PASS" in p.stdout
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cuda_unpreconditioned_cg_on_mdagm():
+    """MdagMLinearOperator (ref: LinearOperator.h:74-105) through ConjugateGradient's generic path: Mdag M x = b on the full grid,
+    checked with the oracle's M / Mdag on the host, and against the Schur solve of M y = b (x = M^-1 Mdag^-1 b => M x' = ... )."""
+    import grid_b200 as gb
+    ctx = gb.Context(0)
+    grid = gb.GridCartesian(ctx, DIMS)
+    D = _device_op(gb, grid, "wilson", gb.F64)
+    b = gb.LatticeFermion(grid, 1, gb.F64).import_lex(G["src4"])
+    x = gb.LatticeFermion(grid, 1, gb.F64).zero()
+    CG = gb.ConjugateGradient(1e-9, 5000)
+    CG(gb.MdagMLinearOperator(D), b, x)
+    o, _ = oracle_op("wilson")
+    xs = x.export_lex()
+    r = o.apply(po.OP_MDAG, o.apply(po.OP_M, xs)) - G["src4"]
+    assert np.linalg.norm(r) / np.linalg.norm(G["src4"]) < 1e-8
+    assert CG.IterationsToComplete > 5 and CG.TrueResidual < 1e-8
