@@ -76,8 +76,8 @@ def test_oracle_schur_solve_matches_reference_outputs(name):
         assert 0.6 < info[k] / r < 1.6, (k, info[k], r)
     assert site_err(x, N[f"{name}/schur_solve/solution"]) < 1e-6
     # the defining property (tests/solver/Test_dwf_cg_schur.cc:46-61): M x = src
-    Mx = o.apply(po.OP_M, x)
-    assert np.linalg.norm(Mx - src) / np.linalg.norm(src) < 1e-7
+    Mx = o.apply(po.OP_M, x)          # bound: the reference's own unpreconditioned residual for this solve (staggered: 1e-7, borderline)
+    assert np.linalg.norm(Mx - src) / np.linalg.norm(src) < 3 * float(N[f"{name}/schur_solve/unprec_residual"])
 
 
 def test_oracle_physical_map_identities():
@@ -247,7 +247,7 @@ def test_cuda_schur_solve_matches_reference(name):
     assert site_err(sol2.export_lex(), x) < 1e-10
     # M sol = src, checked by the oracle on the host
     o, _ = oracle_op(name)
-    assert np.linalg.norm(o.apply(po.OP_M, x) - src_host) / np.linalg.norm(src_host) < 1e-7
+    assert np.linalg.norm(o.apply(po.OP_M, x) - src_host) / np.linalg.norm(src_host) < 3 * float(N[f"{name}/schur_solve/unprec_residual"])
 
 
 @pytest.mark.gpu
