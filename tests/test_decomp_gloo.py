@@ -14,6 +14,14 @@ import grid_b200 as gb
 from grid_b200 import decomp
 
 
+def _free_port():
+    """a port nobody listens on right now (the rendezvous of each test gets its own)"""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as so:
+        so.bind(("127.0.0.1", 0))
+        return so.getsockname()[1]
+
+
 def encode(gdims):
     v = int(np.prod(gdims))
     i = np.arange(v)
@@ -92,7 +100,7 @@ def _worker(rank, world, port, mpi, gdims, q):
 def test_face_exchange_pattern_world2_gloo(mpi, gdims):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29600 + (hash((mpi, gdims)) % 200)
+    port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, mpi, gdims, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -141,7 +149,7 @@ def _naik_worker(rank, world, port, mpi, gdims, q):
 def test_naik_three_deep_halo_pattern_world2_gloo(mpi, gdims):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29810 + (hash((mpi, gdims)) % 150)
+    port = _free_port()
     procs = [ctx.Process(target=_naik_worker, args=(r, 2, port, mpi, gdims, q)) for r in range(2)]
     for p in procs:
         p.start()
