@@ -815,3 +815,60 @@ class ConjugateGradientMultiShiftMixedPrec(ConjugateGradientMultiShift):
             for res, r in zip(self.shifts.residues, results):
                 axpy(psi, res, r, psi)
         return True
+
+
+class MixedPrecisionConjugateGradientBatched:
+    """ref: Grid/algorithms/iterative/ConjugateGradientMixedPrecBatched.h:36-213 -- the defect-correction loop of
+    MixedPrecisionConjugateGradient over a batch of right-hand sides with ONE inner tolerance schedule (the largest residual of
+    the batch sets it), then a double-precision patch-up CG per right-hand side.  Composition of the single-field entry points."""
+
+    def __init__(self, tol, maxinnerit, maxouterit, maxpatchit, Linop_f, Linop_d, updateResidual=True):
+        self.Tolerance, self.InnerTolerance = tol, tol
+        self.MaxInnerIterations, self.MaxOuterIterations, self.MaxPatchupIterations = maxinnerit, maxouterit, maxpatchit
+        self.Linop_f, self.Linop_d, self.updateResidual, self.OuterLoopNormMult = Linop_f, Linop_d, updateResidual, 100.0
+        self.TotalOuterIterations, self.TotalInnerIterations, self.TotalFinalStepIterations = 0, [], []
+
+    def __call__(self, srcs_d, sols_d):
+        if not isinstance(srcs_d, (list, tuple)):
+            srcs_d, sols_d = [srcs_d], [sols_d]
+        assert len(srcs_d) == len(sols_d)
+        nb = len(srcs_d)
+        cb = srcs_d[0].Checkerboard()
+        tmp_d = srcs_d[0].like()
+        src_d = [s.like() for s in srcs_d]
+        src_f = [s.like(prec=F32) for s in srcs_d]
+        sol_f = [s.like(prec=F32) for s in srcs_d]
+        stop = [norm2(s) * self.Tolerance ** 2 for s in srcs_d]
+        norm = [0.0] * nb
+        for f in sols_d:
+            f.set_checkerboard(cb)
+        self.TotalInnerIterations, self.TotalFinalStepIterations = [0] * nb, [0] * nb
+        inner_tol = self.InnerTolerance
+        CG_f = ConjugateGradient(inner_tol, self.MaxInnerIterations, err_on_no_conv=False)
+        outer = 0
+        while outer < self.MaxOuterIterations:
+            all_converged = True
+            for i in range(nb):
+                self.Linop_d.HermOp(sols_d[i], tmp_d)
+                norm[i] = axpy_norm(src_d[i], -1.0, tmp_d, srcs_d[i])          # src_d = residual
+                precisionChange(src_f[i], src_d[i])
+                sol_f[i].zero().set_checkerboard(cb)
+                if norm[i] > self.OuterLoopNormMult * stop[i]:
+                    all_converged = False
+            if all_converged:
+                break
+            if self.updateResidual:
+                while max(norm) * inner_tol * inner_tol < max(stop):
+                    inner_tol *= 2
+                CG_f.Tolerance = inner_tol
+            for i in range(nb):
+                CG_f(self.Linop_f, src_f[i], sol_f[i])
+                self.TotalInnerIterations[i] += CG_f.IterationsToComplete
+                precisionChange(tmp_d, sol_f[i])
+                axpy(sols_d[i], 1.0, tmp_d, sols_d[i])
+            outer += 1
+        self.TotalOuterIterations = outer
+        for i in range(nb):
+            CG_d = ConjugateGradient(self.Tolerance, self.MaxPatchupIterations)
+            CG_d(self.Linop_d, srcs_d[i], sols_d[i])
+            self.TotalFinalStepIterations[i] += CG_d.IterationsToComplete

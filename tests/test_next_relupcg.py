@@ -82,3 +82,32 @@ def test_cuda_relup_cg_matches_reference():
     check(dict(iterations=mCG.IterationsToComplete, reliable_updates=mCG.ReliableUpdatesPerformed, cleanup_iterations=mCG.IterationsToCleanup,
                true_residual=mCG.TrueResidual), sol.export_lex())
     assert sol.Checkerboard() == gb.Odd
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cuda_mixed_cg_batched():
+    """MixedPrecisionConjugateGradientBatched (ref: ConjugateGradientMixedPrecBatched.h:36-213): two right-hand sides, one inner
+    tolerance schedule; each solution satisfies HermOp x = b like the single-RHS MixedPrecisionConjugateGradient's."""
+    import grid_b200 as gb
+    ctx = gb.Context(0)
+    grid = gb.GridCartesian(ctx, DIMS)
+    Dd = gb.MobiusFermion(gb.LatticeGaugeField(grid, gb.F64).import_lex(G["U"]), grid, LS, 0.1, 1.8, 1.5, 0.5)
+    Df = gb.MobiusFermion(gb.LatticeGaugeField(grid, gb.F32).import_lex(G["U"]), grid, LS, 0.1, 1.8, 1.5, 0.5)
+    Ld, Lf = gb.SchurDiagMooeeOperator(Dd), gb.SchurDiagMooeeOperator(Df)
+    srcs, sols, singles = [], [], []
+    for seed, host in ((0, G["src5"]), (1, syn.random_fermion(DIMS, LS, seed=77))):
+        full = gb.LatticeFermion(grid, LS, gb.F64).import_lex(host)
+        s = gb.LatticeFermion(grid, LS, gb.F64, gb.HALF)
+        gb.pickCheckerboard(gb.Odd, s, full)
+        srcs.append(s); sols.append(gb.LatticeFermion(grid, LS, gb.F64, gb.HALF).zero()); singles.append(gb.LatticeFermion(grid, LS, gb.F64, gb.HALF).zero())
+    B = gb.MixedPrecisionConjugateGradientBatched(1e-8, 10000, 50, 10000, Lf, Ld)
+    B(srcs, sols)
+    assert B.TotalOuterIterations >= 1 and all(n > 0 for n in B.TotalInnerIterations)
+    for s, x, y in zip(srcs, sols, singles):
+        gb.MixedPrecisionConjugateGradient(1e-8, 10000, 50, Lf, Ld)(s, y)
+        assert site_err(x.export_lex(), y.export_lex()) < 1e-6
+        r = s.like()
+        Ld.HermOp(x, r)
+        gb.axpy(r, -1.0, s, r)
+        assert (gb.norm2(r) / gb.norm2(s)) ** 0.5 < 2e-8
