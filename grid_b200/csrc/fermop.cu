@@ -96,10 +96,6 @@ static void scale_field(gb_fermion *out, double a, const gb_fermion *in) {
   int rc = gb_scale(out, a, in);
   if (rc != GB_OK) throw Error(rc, gb_last_error());
 }
-static void axpy_field(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y) {
-  int rc = gb_axpy(z, a, x, y);
-  if (rc != GB_OK) throw Error(rc, gb_last_error());
-}
 
 static void apply_mooee_like(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, const gb_fermion *w = nullptr, double alpha = 0) {
   // in/out may be half or full fields (Mooee is diagonal in 4D)

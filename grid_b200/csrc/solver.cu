@@ -38,7 +38,6 @@ using HermOpFn = std::function<void(const gb_fermion *, gb_fermion *)>;
 
 static CGOut cg_core(gb_context *ctx, const HermOpFn &A, const gb_fermion *src, gb_fermion *psi, double tol, int maxit) {
   fermion_check_same(src, psi);
-  gb_grid *g = src->grid;
   gb_fermion *p = nullptr, *mmp = nullptr, *r = nullptr;
   auto mk = [&](gb_fermion **f) { *f = fermion_create_like(src, src->prec); };
   mk(&p); mk(&mmp); mk(&r);
@@ -98,7 +97,6 @@ void cg_update_dev(gb_context *ctx, gb_fermion *psi, gb_fermion *p, const gb_fer
 static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fermion *psi, double tol, int maxit, double shift = 0.0) {
   gb_context *ctx = op->ctx;
   fermion_check_same(src, psi);
-  gb_grid *g = src->grid;
   gb_fermion *p = nullptr, *mmp = nullptr, *r = nullptr;
   auto mk = [&](gb_fermion **f) { *f = fermion_create_like(src, src->prec); };
   mk(&p); mk(&mmp); mk(&r);
@@ -455,8 +453,6 @@ static MixedOut mixed_cg_core(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion
   GB_REQUIRE(op_f && op_d && src_d_in && sol_d, "null argument");
   GB_REQUIRE(op_f->prec == GB_F32 && op_d->prec == GB_F64, "mixed CG needs an fp32 and an fp64 operator");
   GB_REQUIRE(src_d_in->prec == GB_F64 && sol_d->prec == GB_F64, "mixed CG outer fields must be fp64");
-  gb_context *ctx = op_d->ctx;
-  gb_grid *g = src_d_in->grid;
   const int cb = src_d_in->cb;
   sol_d->cb = cb;
   gb_fermion *tmp_d = nullptr, *src_d = nullptr, *src_f = nullptr, *sol_f = nullptr;
