@@ -30,3 +30,6 @@ if [ "$ngpu" -ge 2 ]; then
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29566 bench.py --gpus $n --local 64 64 32 16 --steps 100 --warmup 5 --no-cpu --no-cg --e2e-steps 1 > $out/bench_c4_n${n}.json 2>$out/bench_c4_n${n}.err
 fi
 grep -o '"ms_per_step": [0-9.]*' $out/bench_c4_n*.json
+
+# 6. Benchmark_usqcd-shaped table (Wilson / DWF4 / staggered DhopEO fp32 at local L^4, stream triad) next to BASELINE.md's Booster rows
+python scripts/benchmark_usqcd.py > $out/usqcd_n1.jsonl 2>$out/usqcd_n1.err; cat $out/usqcd_n1.jsonl
