@@ -58,3 +58,61 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f"{f} references the oracle"
     assert "oracle" not in open(os.path.join(ROOT, "include", "gridb200.h")).read()
+
+
+def _c_prototypes():
+    """{name: (return type, [parameter types])} parsed from include/gridb200.h"""
+    text = open(os.path.join(ROOT, "include", "gridb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    text = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"([\w\s\*]+?)\b(gb_[a-zA-Z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1).strip(), m.group(2), m.group(3).strip()
+        if name == "gb_hermop_fn" or "typedef" in ret:
+            continue
+        params = [] if args in ("", "void") else [a.strip() for a in re.sub(r"\s+", " ", args).split(",")]
+        protos[name] = (ret, params)
+    return protos
+
+
+def _category(ctype_decl):
+    """coarse ABI class of a C parameter / return declaration"""
+    d = ctype_decl
+    if "gb_hermop_fn" in d:
+        return "fnptr"
+    if "*" in d or "[" in d:
+        return "ptr"
+    if re.search(r"\b(double)\b", d):
+        return "f64"
+    if re.search(r"\b(int64_t|uint64_t|size_t)\b", d):
+        return "i64"
+    return "i32"     # int, enums (gb_precision, gb_gridkind), uint32_t
+
+
+def _py_category(t):
+    import ctypes as C
+    if t is None:
+        return "void"
+    if t in (C.c_double,):
+        return "f64"
+    if t in (C.c_int64, C.c_uint64, C.c_size_t):
+        return "i64"
+    if t in (C.c_int, C.c_uint32):
+        return "i32"
+    if isinstance(t, type) and issubclass(t, C._CFuncPtr):
+        return "fnptr"
+    return "ptr"     # c_void_p, c_char_p, POINTER(...)
+
+
+def test_ctypes_signatures_match_the_header():
+    """Every binding in grid_b200.SYMBOLS has the parameter count and ABI classes (pointer / int / int64 / double / callback) of its
+    prototype in include/gridb200.h -- a wrong argtype here would corrupt a call silently on the GPU box."""
+    protos = _c_prototypes()
+    assert set(protos) == {n for n, _, _ in gb.SYMBOLS}
+    for name, res, args in gb.SYMBOLS:
+        ret, params = protos[name]
+        assert len(params) == len(args), (name, params, args)
+        for p, a in zip(params, args):
+            assert _category(p) == _py_category(a), (name, p, a)
+        want_ret = "ptr" if "*" in ret else _category(ret)
+        assert want_ret == _py_category(res), (name, ret, res)
