@@ -237,3 +237,15 @@ def test_cuda_mdir_all():
     one = gb.LatticeFermion(grid, LS, gb.F64)
     D.Mdir(psi, one, 2, -1)
     assert np.array_equal(one.export_lex(), outs[6].export_lex())
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_dwf_force_driver():
+    """ref: tests/forces/Test_dwf_force.cc -- dS predicted from MDeriv against the measured change of |M phi|^2, through the C++ mirror"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(HERE), "drivers", "Test_dwf_force")
+    assert os.path.exists(exe), f"{exe} missing: run make -C grid_b200"
+    p = subprocess.run([exe, "--grid", "8.8.8.8", "--Ls", "8"], capture_output=True, text=True, timeout=200)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert "predict dS" in p.stdout and "PASS" in p.stdout
