@@ -196,7 +196,10 @@ int gb_op_import_gauge(gb_fermop *op, const gb_gauge *Umu);    /* ref: WilsonFer
  * SchurStaggeredOperator::Mpc = mass^2 - Meooe Meooe (ref: LinearOperator.h:543-584); gb_cg_schur runs CG on that.
  * Decomposed lattices: the Naik term reaches three sites, so every split dimension carries three-deep halos of the input
  * field (packed and exchanged per hop) and of U_mu for the double store (ref: displacements +-1, +-3,
- * instantiation/ImprovedStaggeredFermionInstantiation.cc:33-34 ; Stencil.h:709 needs local extents > 3). */
+ * instantiation/ImprovedStaggeredFermionInstantiation.cc:33-34 ; Stencil.h:709 needs local extents > 3).  gb_op_set_overlap:
+ * 1 (default) interior sites while the faces travel, then the exterior sites; 0 exchange, then one launch.
+ * Environment GB_STAG_SELF_HALO=<bitmask of dimensions>, read at creation: also routes those UNdecomposed dimensions through the
+ * pack / exchange (with the rank itself) / halo-lookup path -- a test knob that lets one GPU exercise the decomposed code. */
 int gb_op_create_staggered(gb_grid *g, const gb_gauge *Uthin, const gb_gauge *Ufat, double mass, double c1, double c2, double u0, gb_fermop **out);
 int gb_op_import_gauge_staggered(gb_fermop *op, const gb_gauge *Uthin, const gb_gauge *Ufat);
 int gb_op_destroy(gb_fermop *op);
