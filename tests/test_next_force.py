@@ -249,3 +249,61 @@ def test_dwf_force_driver():
     p = subprocess.run([exe, "--grid", "8.8.8.8", "--Ls", "8"], capture_output=True, text=True, timeout=200)
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert "predict dS" in p.stdout and "PASS" in p.stdout
+
+
+def _two_flavour_eo_action_and_force(apply_mpc, cg_solve, mpc_deriv, phi_o):
+    """TwoFlavourEvenOddPseudoFermionAction (ref: Grid/qcd/action/pseudofermion/TwoFlavourEvenOdd.h:112-182):
+    S = phi^dag (Mpc^dag Mpc)^-1 phi ;  deriv: X = (Mpc^dag Mpc)^-1 phi, Y = Mpc X, dSdU = MpcDeriv(Y, X) + MpcDagDeriv(X, Y)."""
+    X = cg_solve(phi_o)
+    Y = apply_mpc(X)
+    S = np.vdot(phi_o, X).real
+    return S, mpc_deriv(2, Y, X) + mpc_deriv(3, X, Y)
+
+
+@pytest.mark.parametrize("name", ["wilson", "mobius"])
+def test_oracle_two_flavour_even_odd_pseudofermion_force(name):
+    """The caller SURVEY 8b names (HMC pseudofermion actions): with the reference's conventions dS = -dt sum tr(P 2 Ta(dSdU))."""
+    from scipy.linalg import expm
+    Ls = OPS[name]["Ls"]
+    phi_o = po.pick_checkerboard(DIMS, Ls, 1, G[OPS[name]["src"]])
+
+    def run(U):
+        o = oracle_op(name, U=U)
+        return _two_flavour_eo_action_and_force(lambda x: o.apply(po.OP_MPC, x, cb_in=1), lambda b: o.cg(1, b, 1e-12, 5000)[0], lambda w, a, b: o.deriv_eo(w, a, b), phi_o)
+    U = G["U"]
+    S, dSdU = run(U)
+    rng = np.random.default_rng(9)
+    P = _ta(rng.normal(size=U.shape) + 1j * rng.normal(size=U.shape))
+    dt = 1e-5
+    Up = np.einsum("smij,smjk->smik", np.array([[expm(dt * P[s, m]) for m in range(4)] for s in range(U.shape[0])]), U)
+    Sp, _ = run(Up)
+    pred = -dt * np.einsum("smij,smji->", P, 2.0 * _ta(dSdU)).real
+    assert abs((Sp - S) - pred) < 5e-3 * abs(pred), (Sp - S, pred)
+
+
+@pytest.mark.gpu
+@UNVERIFIED
+def test_cuda_two_flavour_even_odd_pseudofermion_force():
+    """The same action and force through the CUDA path (ConjugateGradient on SchurDifferentiableOperator + MpcDeriv / MpcDagDeriv),
+    against the oracle's force for the same field."""
+    import grid_b200 as gb
+    name = "mobius"
+    ctx = gb.Context(0)
+    grid = gb.GridCartesian(ctx, DIMS)
+    D = _device_op(gb, grid, name, gb.F64)
+    full = gb.LatticeFermion(grid, LS, gb.F64).import_lex(G["src5"])
+    phi, X, Y = (gb.LatticeFermion(grid, LS, gb.F64, gb.HALF) for _ in range(3))
+    gb.pickCheckerboard(gb.Odd, phi, full)
+    Mpc = gb.SchurDifferentiableOperator(D)
+    X.zero()
+    gb.ConjugateGradient(1e-12, 5000)(Mpc, phi, X)          # DerivativeSolver(Mpc, PhiOdd, X)
+    Mpc.Mpc(X, Y)
+    F1, F2 = gb.LatticeGaugeField(grid, gb.F64), gb.LatticeGaugeField(grid, gb.F64)
+    Mpc.MpcDeriv(F1, Y, X)
+    Mpc.MpcDagDeriv(F2, X, Y)
+    got = F1.export_lex() + F2.export_lex()
+    o = oracle_op(name)
+    phi_o = po.pick_checkerboard(DIMS, LS, 1, G["src5"])
+    S, want = _two_flavour_eo_action_and_force(lambda x: o.apply(po.OP_MPC, x, cb_in=1), lambda b: o.cg(1, b, 1e-12, 5000)[0], lambda w, a, b: o.deriv_eo(w, a, b), phi_o)
+    assert rel_err(got, want) < 1e-8
+    assert abs(gb.innerProduct(phi, X).real - S) < 1e-9 * abs(S)
