@@ -214,7 +214,8 @@ class LatticeFermion:
             pass
 
     def like(self, kind=None, prec=None):
-        return type(self)(self.grid, self.Ls, self.prec if prec is None else prec, self.kind if kind is None else kind)
+        cls = getattr(self, "_cls", type(self))     # a borrowed view (generic-CG callback) creates fields of the class it views
+        return cls(self.grid, self.Ls, self.prec if prec is None else prec, self.kind if kind is None else kind)
 
     @property
     def local_sites(self):
@@ -630,6 +631,7 @@ class _Borrowed(LatticeFermion):
 
     def __init__(self, handle, like):
         self.grid, self.Ls, self.prec, self.kind, self.SITE = like.grid, like.Ls, like.prec, like.kind, like.SITE
+        self._cls = getattr(like, "_cls", type(like))
         self.h = C.c_void_p(handle)
 
     def __del__(self):

@@ -156,6 +156,13 @@ void orc_dhop_dir(void *h, const void *in, void *out, int dir, int disp) {
   if (box->prec == 0) box->f.DhopDir((const Spinor<float> *)in, (Spinor<float> *)out, dir, disp);
   else box->d.DhopDir((const Spinor<double> *)in, (Spinor<double> *)out, dir, disp);
 }
+// one leg of the hopping term: point 0..3 forward mu, 4..7 backward; ocb < 0: full grid, else checkerboard hop into parity ocb
+void orc_dhop_leg(void *h, const void *in, void *out, int point, int dag, int ocb) {
+  OpBox *box = (OpBox *)h;
+  auto run = [&](auto &op, auto *i, auto *o) { if (ocb < 0) op.DhopLeg(i, o, point, dag); else op.DhopLegCB(i, o, ocb, point, dag); };
+  if (box->prec == 0) run(box->f, (const Spinor<float> *)in, (Spinor<float> *)out);
+  else run(box->d, (const Spinor<double> *)in, (Spinor<double> *)out);
+}
 void orc_deriv(void *h, int which, void *mat, const void *U, const void *V, int dag) {
   OpBox *box = (OpBox *)h;
   auto run = [&](auto &op, auto *m, auto *u, auto *v) { if (which == 0) op.DhopDeriv(m, u, v, dag); else op.MDeriv(m, u, v, dag); };

@@ -14,6 +14,13 @@ _CHILD_BUDGET_S = 1500          # all unverified tests of a session together; th
 _child_spent = [0.0]
 
 
+if os.environ.get("GB_TEST_MOCK_LIB"):
+    # tests/test_next_on_cpu_mock.py: run the GPU tests of the SURVEY 8(f) rows against the CPU mock of the library (tests/mock/)
+    import grid_b200 as _gb
+    _gb.LIB_PATH = os.environ["GB_TEST_MOCK_LIB"]
+    _gb._LIB = None
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
     config.addinivalue_line("markers", "slow: long-running CPU test")

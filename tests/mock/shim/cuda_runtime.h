@@ -1,0 +1,66 @@
+// cuda_runtime.h -- TEST-ONLY stand-in for the CUDA runtime (tests/mock/README.md).  It lets a HOST compiler build a few of the
+// product's source files (solver.cu, schur.cu, force.cu, nersc.cu) so that their host orchestration and their thread-independent
+// kernels run on the CPU against a mock backend.  Never on an include path of the product build.
+#pragma once
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct double2 { double x, y; };
+struct int4 { int x, y, z, w; };
+struct uint3 { unsigned x, y, z; };
+struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+inline float2 make_float2(float a, float b) { return {a, b}; }
+inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
+inline double2 make_double2(double a, double b) { return {a, b}; }
+inline int4 make_int4(int a, int b, int c, int d) { return {a, b, c, d}; }
+template <class T> inline T __ldg(const T *p) { return *p; }
+template <class T> inline T __ldcs(const T *p) { return *p; }
+inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+typedef void *cudaStream_t;
+typedef void *cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+inline const char *cudaGetErrorString(cudaError_t) { return "mock"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaMalloc(void **p, size_t n) { *p = std::calloc(n ? n : 1, 1); return *p ? cudaSuccess : 2; }
+template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { return cudaMalloc((void **)p, n); }
+inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+
+// sequential "launch": every thread of every block in turn -- valid for kernels whose threads do not communicate
+namespace gb_mock {
+extern thread_local uint3 t_blockIdx, t_threadIdx;
+extern thread_local dim3 t_blockDim, t_gridDim;
+template <class F> inline void launch(dim3 grid, dim3 block, F &&body) {
+  t_gridDim = grid; t_blockDim = block;
+  for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++)
+    for (unsigned tx = 0; tx < block.x; tx++) { t_blockIdx = {bx, by, 0}; t_threadIdx = {tx, 0, 0}; body(); }
+}
+} // namespace gb_mock
+#define blockIdx gb_mock::t_blockIdx
+#define threadIdx gb_mock::t_threadIdx
+#define blockDim gb_mock::t_blockDim
+#define gridDim gb_mock::t_gridDim

@@ -181,7 +181,10 @@ _UNFUSED_SNIPPET = r"""
 import sys, numpy as np
 sys.path.insert(0, {root!r})
 sys.path.insert(0, {tests!r})
+import os
 import grid_b200 as gb
+if os.environ.get("GB_TEST_MOCK_LIB"):      # tests/test_next_on_cpu_mock.py
+    gb.LIB_PATH = os.environ["GB_TEST_MOCK_LIB"]
 import test_next_multishift as t
 ctx, D, lin, src, mk = t._device_case(gb, "mobius", gb.F32)
 results = [mk() for _ in t.POLES]
