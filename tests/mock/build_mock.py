@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Builds the TEST-ONLY CPU mock of libgridb200 (tests/mock/README.md): the product's solver.cu, schur.cu, force.cu and nersc.cu,
-rewritten for a host compiler by transform.py against shim/cuda_runtime.h, linked with mock_backend.cpp and the oracle.
+"""Builds the TEST-ONLY CPU mock of libgridb200 (tests/mock/README.md): the product's fermop.cu, dhop.cu, cayley.cu, stag.cu, solver.cu, schur.cu, force.cu and nersc.cu,
+rewritten for a host compiler by transform.py against shim/, linked with mock_backend.cpp.
 usage: build_mock.py <output directory>  -> <output directory>/libgridb200_mock.so"""
 import os
 import subprocess
@@ -11,15 +11,12 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 from transform import transform  # noqa: E402
 
-PRODUCT_SOURCES = ["solver.cu", "schur.cu", "force.cu", "nersc.cu"]
+PRODUCT_SOURCES = ["fermop.cu", "dhop.cu", "cayley.cu", "stag.cu", "solver.cu", "schur.cu", "force.cu", "nersc.cu"]
 
 
 def build(outdir):
     os.makedirs(outdir, exist_ok=True)
     csrc = os.path.join(ROOT, "grid_b200", "csrc")
-    oracle = os.path.join(ROOT, "oracle")
-    if not os.path.exists(os.path.join(oracle, "liboracle.so")):
-        subprocess.check_call(["make", "-s", "-C", oracle])
     cpps = []
     for f in PRODUCT_SOURCES:
         out = os.path.join(outdir, f.replace(".cu", "_mock.cpp"))
@@ -27,7 +24,7 @@ def build(outdir):
         cpps.append(out)
     lib = os.path.join(outdir, "libgridb200_mock.so")
     cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-I", os.path.join(HERE, "shim"), "-I", csrc, "-o", lib, *cpps,
-           os.path.join(HERE, "mock_backend.cpp"), "-L", oracle, "-loracle", "-Wl,-rpath," + oracle, "-Wl,--no-undefined"]
+           os.path.join(HERE, "mock_backend.cpp"), "-Wl,--no-undefined"]
     subprocess.check_call(cmd)
     return lib
 

@@ -1,10 +1,11 @@
 // mock_backend.cpp -- TEST-ONLY CPU backend behind the C ABI (tests/mock/README.md).
 //
-// Purpose: run the product's HOST ORCHESTRATION of the SURVEY 8(f) rows -- the actual source files grid_b200/csrc/solver.cu,
-// schur.cu, force.cu, nersc.cu, built for the host through tests/mock/shim/cuda_runtime.h and tests/mock/transform.py -- on a
-// machine without a GPU, together with the Python mirror and the GPU tests themselves.  What is mocked is everything those
-// files CALL: field containers and BLAS / reductions (plain host loops over the same blocked layout), and the operator entry
-// points op_apply / dhop_blocks, which are served by the CPU oracle (oracle/liboracle.so, test infrastructure).
+// Purpose: run product source files whose kernels' threads never communicate -- fermop.cu, dhop.cu (generic hopping kernel,
+// double store, leg mask), cayley.cu, stag.cu, solver.cu, schur.cu, force.cu, nersc.cu -- on a machine without a GPU, built for
+// the host through tests/mock/shim/ and tests/mock/transform.py, together with the Python mirror and the GPU tests themselves.
+// What is mocked is the rest: field containers, import / export, BLAS-1 and reductions (plain host loops over the same blocked
+// layout; the real ones use shared memory and warp shuffles), and stubs that switch the tuned kernels off (dhop_fast / dhop_col,
+// smat, peer-to-peer halos, NCCL), so every hop goes through the generic kernel.  No oracle in here: the tests compare with it.
 // Nothing here ships: the product library has no CPU path (tests/test_abi.py::test_no_cpu_fallback_without_a_device).
 #include "fermop.hpp"
 #include <complex>
@@ -18,24 +19,12 @@ thread_local uint3 t_blockIdx, t_threadIdx;
 thread_local dim3 t_blockDim, t_gridDim;
 }
 
-// ---- the oracle's C API (oracle/oracle_capi.cpp)
-extern "C" {
-void *orc_op_create(int kind, const int *L, int Ls, double mass, double M5, double b, double c, int prec);
-void orc_op_destroy(void *h);
-void orc_op_import_gauge(void *h, const void *Umu, const double *phases);
-int orc_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half);
-void orc_dhop_leg(void *h, const void *in, void *out, int point, int dag, int ocb);
-void *orc_stag_create(const int *L, double mass, double c1, double c2, double u0, int prec);
-void orc_stag_destroy(void *h);
-void orc_stag_import_gauge(void *h, const void *Uthin, const void *Ufat);
-int orc_stag_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half);
-}
+#include "comm.hpp"
 
 using namespace gb;
 
 namespace {
 thread_local std::string g_err;
-std::map<const gb_fermop *, void *> g_oracle;     // operator -> oracle handle
 typedef std::complex<double> cd;
 
 template <class T> size_t scalars(const gb_fermion *f) { return (size_t)f->nvec() * (16 / sizeof(T)); }
@@ -73,14 +62,6 @@ template <class T> std::vector<T> to_host(const gb_fermion *f) {
   transfer<T, T>(f, h.data(), false);
   return h;
 }
-// a half field viewed through raw parity-block pointers (dhop_blocks hands those over)
-gb_fermion block_view(const gb_fermop *op, const void *block, int cb) {
-  gb_fermion f;
-  f.grid = op->grid; f.Ls = op->Ls; f.prec = op->prec; f.kind = GB_HALF; f.cb = cb; f.ncomplex = 12;
-  f.nsite4 = op->grid->V4cb; f.n5cb = f.nsite4 * op->Ls; f.hblk = (f.n5cb + W - 1) / W; f.nparity = 1;
-  f.data = const_cast<void *>(block); f.bytes = (size_t)f.nvec() * 16;
-  return f;
-}
 int fail(int code, const std::string &m) { g_err = m; return code; }
 #define MOCK_UNSUPPORTED(name) return fail(GB_ERR_INVALID, std::string(name) + ": not part of the CPU mock backend")
 } // namespace
@@ -106,56 +87,25 @@ gb_fermion *fermion_create_like(const gb_fermion *like, int prec) {
   f->cb = like->cb;
   return f;
 }
-gb_fermion *op_tmp_half(gb_fermop *op, int i) {
-  if (!op->tmp_h[i]) op->tmp_h[i] = create(op->grid, op->Ls, op->kind == GB_KIND_STAGGERED ? 3 : 12, op->prec, GB_HALF);
-  return op->tmp_h[i];
-}
-gb_fermion *op_tmp_full(gb_fermop *op, int i) {
-  if (!op->tmp_f[i]) op->tmp_f[i] = create(op->grid, op->Ls, op->kind == GB_KIND_STAGGERED ? 3 : 12, op->prec, GB_FULL);
-  return op->tmp_f[i];
-}
-// every operator entry point = the oracle on host copies (the mock tests ORCHESTRATION, not these)
-void op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag) {
-  GB_REQUIRE(op && in && out && in != out, "null or aliased argument");
-  GB_REQUIRE(in->grid == op->grid && in->prec == op->prec && in->Ls == op->Ls && out->kind == in->kind && out->prec == in->prec, "field is not conformable with the operator");
-  const bool half = in->kind == GB_HALF;
-  if ((which == GB_OP_DHOP_OE) && in->cb != GB_EVEN) throw Error(GB_ERR_INVALID, "DhopOE needs an Even-checkerboard input");
-  if ((which == GB_OP_DHOP_EO) && in->cb != GB_ODD) throw Error(GB_ERR_INVALID, "DhopEO needs an Odd-checkerboard input");
-  const bool flips = which == GB_OP_DHOP_OE || which == GB_OP_DHOP_EO || which == GB_OP_MEOOE || which == GB_OP_MEOOE_DAG;
-  out->cb = half ? (flips ? 1 - in->cb : in->cb) : in->cb;
-  void *h = g_oracle.at(op);
-  auto run = [&](auto tag) {
-    using T = decltype(tag);
-    std::vector<T> x = to_host<T>(in), y(x.size());
-    int rc;
-    if (op->kind == GB_KIND_STAGGERED) {
-      if (which == GB_OP_DMINUS || which == GB_OP_DMINUS_DAG) { y = x; rc = 0; }
-      else rc = orc_stag_apply(h, which, x.data(), y.data(), dag, in->cb, half);
-    } else rc = orc_apply(h, which, x.data(), y.data(), dag, in->cb, half);
-    GB_REQUIRE(rc == 0, "opcode not served by the oracle");
-    transfer<T, T>(out, y.data(), true);
-  };
-  if (op->prec == GB_F32) run(float()); else run(double());
-}
-// force.cu drives single legs through dhop_blocks with op->leg_mask = 1 << point
-void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag, const void *const ax[2], double, double) {
-  GB_REQUIRE(ax == nullptr, "mock dhop_blocks: no epilogue");
-  int point = -1;
-  for (int p = 0; p < 8; p++) if (op->leg_mask == (1 << p)) point = p;
-  GB_REQUIRE(point >= 0, "mock dhop_blocks serves single legs only");
-  void *h = g_oracle.at(op);
-  auto run = [&](auto tag) {
-    using T = decltype(tag);
-    for (int j = 0; j < nparity; j++) {
-      const int po = parity_out_first ^ j, ip = 1 - po;
-      gb_fermion fi = block_view(op, in[ip], ip), fo = block_view(op, out[po], po);
-      std::vector<T> x = to_host<T>(&fi), y(x.size());
-      orc_dhop_leg(h, x.data(), y.data(), point, dag, po);
-      transfer<T, T>(&fo, y.data(), true);
-    }
-  };
-  if (op->prec == GB_F32) run(float()); else run(double());
-}
+// ---- the tuned paths are switched off: every hop runs the generic kernel, every s-space operator the m5d / mooee_inv kernels
+bool dhop_fast_launch(gb_fermop *, const void *const[2], void *const[2], int, int, int, const void *const[2], double, double, int, cudaStream_t, const void *const[8],
+                      const unsigned long long *, unsigned long long) { return false; }
+bool p2p_setup(gb_fermop *) { return false; }
+void p2p_teardown(gb_fermop *) {}
+unsigned long long p2p_next_epoch(gb_fermop *) { throw Error(GB_ERR_INVALID, "mock: no peer-to-peer halos"); }
+void p2p_send_only(gb_fermop *, unsigned long long, const void *const[2], int, int, int, cudaStream_t) { throw Error(GB_ERR_INVALID, "mock: no peer-to-peer halos"); }
+unsigned long long p2p_pack_send(gb_fermop *, const void *const[2], int, int, int, cudaStream_t) { throw Error(GB_ERR_INVALID, "mock: no peer-to-peer halos"); }
+void p2p_fill_halo(gb_fermop *, unsigned long long, const void *[8], const unsigned long long **) { throw Error(GB_ERR_INVALID, "mock: no peer-to-peer halos"); }
+SMat smat_identity(int) { return SMat(); }
+SMat smat_m5d(int, const std::vector<double> &, const std::vector<double> &, const std::vector<double> &, int) { return SMat(); }
+SMat smat_mooee_inv(const CayleyCoeffs &, int) { return SMat(); }
+SMat smat_mul(const SMat &, const SMat &) { return SMat(); }
+SMat smat_scale(const SMat &, double) { return SMat(); }
+const void *smat_device(gb_fermop *, const SMat &) { return nullptr; }
+bool smat_apply(gb_fermop *, const void *, const gb_fermion *, const void *, const gb_fermion *, double, const gb_fermion *, gb_fermion *) { return false; }
+NcclApi &nccl() { static NcclApi api; return api; }
+void nccl_check(int r, const char *what) { if (r != 0) throw Error(GB_ERR_COMM, what); }
+void global_sum(gb_context *, double *, int) {}
 template <class T> static void inner_T(const gb_fermion *l, const gb_fermion *r, double out[2]) {
   const T *a = (const T *)l->data, *b = (const T *)r->data;
   double re = 0, im = 0;
@@ -316,44 +266,5 @@ int gb_gauge_export(const gb_gauge *u, void *host, gb_precision hp) {
 }
 int gb_gauge_random(gb_gauge *, uint64_t) { MOCK_UNSUPPORTED("gb_gauge_random"); }
 int gb_gauge_unit(gb_gauge *) { MOCK_UNSUPPORTED("gb_gauge_unit"); }
-// operators
-static gb_fermop *make(gb_grid *g, const gb_gauge *U, int kind, int Ls, double mass, double M5, double b, double c, const double *ph) {
-  gb_fermop *op = new gb_fermop();
-  op->grid = g; op->ctx = g->ctx; op->kind = kind; op->prec = U->prec; op->Ls = Ls; op->mass = mass; op->M5 = M5;
-  op->Uds = (void *)1;   // "has a gauge field"
-  void *h = orc_op_create(kind == GB_KIND_WILSON ? 0 : 1, g->ldims, Ls, mass, M5, b, c, U->prec == GB_F32 ? 0 : 1);
-  orc_op_import_gauge(h, U->data, ph);
-  g_oracle[op] = h;
-  return op;
-}
-int gb_op_create_wilson(gb_grid *g, const gb_gauge *U, double mass, const double *ph, gb_fermop **out) { *out = make(g, U, GB_KIND_WILSON, 1, mass, 0, 1, 0, ph); return GB_OK; }
-int gb_op_create_dwf(gb_grid *g, const gb_gauge *U, int Ls, double mass, double M5, const double *ph, gb_fermop **out) { *out = make(g, U, GB_KIND_CAYLEY, Ls, mass, M5, 1, 0, ph); return GB_OK; }
-int gb_op_create_mobius(gb_grid *g, const gb_gauge *U, int Ls, double mass, double M5, double b, double c, const double *ph, gb_fermop **out) { *out = make(g, U, GB_KIND_CAYLEY, Ls, mass, M5, b, c, ph); return GB_OK; }
-int gb_op_import_gauge(gb_fermop *op, const gb_gauge *U) { orc_op_import_gauge(g_oracle.at(op), U->data, nullptr); return GB_OK; }
-int gb_op_create_staggered(gb_grid *g, const gb_gauge *Ut, const gb_gauge *Uf, double mass, double c1, double c2, double u0, gb_fermop **out) {
-  gb_fermop *op = new gb_fermop();
-  op->grid = g; op->ctx = g->ctx; op->kind = GB_KIND_STAGGERED; op->prec = Ut->prec; op->Ls = 1; op->mass = mass;
-  void *h = orc_stag_create(g->ldims, mass, c1, c2, u0, Ut->prec == GB_F32 ? 0 : 1);
-  orc_stag_import_gauge(h, Ut->data, Uf->data);
-  g_oracle[op] = h;
-  *out = op;
-  return GB_OK;
-}
-int gb_op_import_gauge_staggered(gb_fermop *op, const gb_gauge *Ut, const gb_gauge *Uf) { orc_stag_import_gauge(g_oracle.at(op), Ut->data, Uf->data); return GB_OK; }
-int gb_op_destroy(gb_fermop *op) {
-  if (!op) return GB_OK;
-  if (op->kind == GB_KIND_STAGGERED) orc_stag_destroy(g_oracle.at(op)); else orc_op_destroy(g_oracle.at(op));
-  g_oracle.erase(op);
-  for (auto *f : op->tmp_h) gb_fermion_destroy(f);
-  for (auto *f : op->tmp_f) gb_fermion_destroy(f);
-  delete op;
-  return GB_OK;
-}
-int gb_op_Ls(const gb_fermop *op) { return op->Ls; }
-int gb_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag) { GB_API_BEGIN op_apply(op, which, in, out, dag); GB_API_END }
 int gb_op_dhop_host(gb_fermop *, const void *, void *, gb_precision, int) { MOCK_UNSUPPORTED("gb_op_dhop_host"); }
-int gb_op_halo_exchange(gb_fermop *, const gb_fermion *, int, int64_t *) { MOCK_UNSUPPORTED("gb_op_halo_exchange"); }
-int gb_op_set_tiling(gb_fermop *, int, int, int) { return GB_OK; }
-int gb_op_set_overlap(gb_fermop *, int) { return GB_OK; }
-int gb_op_set_fast_kernel(gb_fermop *, int) { return GB_OK; }
 }
