@@ -9,7 +9,10 @@
 // Nothing here ships: the product library has no CPU path (tests/test_abi.py::test_no_cpu_fallback_without_a_device).
 #include "fermop.hpp"
 #include <complex>
+#include <condition_variable>
+#include <deque>
 #include <map>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -44,7 +47,7 @@ template <class T, class H> void transfer(const gb_fermion *f, H *host, bool to_
   const int nc = f->ncomplex, Ls = f->Ls;
   if (to_device) std::fill(raw, raw + scalars<T>(f), (T)0);
   for (int t = 0; t < L[3]; t++) for (int z = 0; z < L[2]; z++) for (int y = 0; y < L[1]; y++) for (int x = 0; x < L[0]; x++) {
-    const int par = (x + y + z + t) & 1;
+    const int par = (x + y + z + t + f->grid->origin[0] + f->grid->origin[1] + f->grid->origin[2] + f->grid->origin[3]) & 1;   // parity of the GLOBAL site
     if (f->kind == GB_HALF && par != f->cb) continue;
     const int64_t site = (x >> 1) + (int64_t)(L[0] / 2) * (y + (int64_t)L[1] * (z + (int64_t)L[2] * t));
     const int64_t i4 = x + (int64_t)L[0] * (y + (int64_t)L[1] * (z + (int64_t)L[2] * t));
@@ -103,16 +106,62 @@ SMat smat_mul(const SMat &, const SMat &) { return SMat(); }
 SMat smat_scale(const SMat &, double) { return SMat(); }
 const void *smat_device(gb_fermop *, const SMat &) { return nullptr; }
 bool smat_apply(gb_fermop *, const void *, const gb_fermion *, const void *, const gb_fermion *, double, const gb_fermion *, gb_fermion *) { return false; }
-NcclApi &nccl() { static NcclApi api; return api; }
+} // namespace gb
+// ---- "ranks" are host threads of one process (each drives its own context); send / recv are copies through mailboxes
+struct ncclComm { int rank, nranks; };
+namespace {
+struct World {
+  std::mutex m;
+  std::condition_variable cv;
+  std::map<std::pair<int, int>, std::deque<std::vector<char>>> box;   // (source, destination) -> messages in order
+  int arrived = 0; long gen = 0;
+  std::vector<double> acc, res;
+} g_world;
+ncclResult_t mock_send(const void *buf, size_t n, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t) {
+  const size_t bytes = n * (t == ncclDouble ? 8 : 1);
+  std::lock_guard<std::mutex> l(g_world.m);
+  g_world.box[{c->rank, peer}].emplace_back((const char *)buf, (const char *)buf + bytes);
+  g_world.cv.notify_all();
+  return 0;
+}
+ncclResult_t mock_recv(void *buf, size_t n, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t) {
+  const size_t bytes = n * (t == ncclDouble ? 8 : 1);
+  std::unique_lock<std::mutex> l(g_world.m);
+  auto &q = g_world.box[{peer, c->rank}];
+  g_world.cv.wait(l, [&] { return !q.empty(); });
+  if (q.front().size() != bytes) return 1;
+  std::memcpy(buf, q.front().data(), bytes);
+  q.pop_front();
+  return 0;
+}
+ncclResult_t mock_group() { return 0; }
+const char *mock_errstr(ncclResult_t) { return "mock nccl error (message size mismatch)"; }
+} // namespace
+namespace gb {
+NcclApi &nccl() {
+  static NcclApi api;
+  if (!api.ok) { api.ok = true; api.Send = mock_send; api.Recv = mock_recv; api.GroupStart = mock_group; api.GroupEnd = mock_group; api.GetErrorString = mock_errstr; }
+  return api;
+}
 void nccl_check(int r, const char *what) { if (r != 0) throw Error(GB_ERR_COMM, what); }
-void global_sum(gb_context *, double *, int) {}
+// sum over the rank threads (all of them call it the same number of times, like an all-reduce)
+void global_sum(gb_context *ctx, double *v, int n) {
+  if (ctx->nranks <= 1) return;
+  std::unique_lock<std::mutex> l(g_world.m);
+  if (g_world.arrived == 0) g_world.acc.assign(n, 0.0);
+  for (int i = 0; i < n; i++) g_world.acc[i] += v[i];
+  const long mygen = g_world.gen;
+  if (++g_world.arrived == ctx->nranks) { g_world.res = g_world.acc; g_world.arrived = 0; g_world.gen++; g_world.cv.notify_all(); }
+  else g_world.cv.wait(l, [&] { return g_world.gen != mygen; });
+  for (int i = 0; i < n; i++) v[i] = g_world.res[i];
+}
 template <class T> static void inner_T(const gb_fermion *l, const gb_fermion *r, double out[2]) {
   const T *a = (const T *)l->data, *b = (const T *)r->data;
   double re = 0, im = 0;
   for (size_t i = 0; i < scalars<T>(l); i += 2) { re += (double)(a[i] * b[i] + a[i + 1] * b[i + 1]); im += (double)(a[i] * b[i + 1] - a[i + 1] * b[i]); }
   out[0] = re; out[1] = im;
 }
-void reduce_inner_dev(gb_context *, const gb_fermion *l, const gb_fermion *r, double *d_out) { if (l->prec == GB_F32) inner_T<float>(l, r, d_out); else inner_T<double>(l, r, d_out); }
+void reduce_inner_dev(gb_context *ctx, const gb_fermion *l, const gb_fermion *r, double *d_out) { if (l->prec == GB_F32) inner_T<float>(l, r, d_out); else inner_T<double>(l, r, d_out); global_sum(ctx, d_out, 2); }
 void axpy_norm_dev(gb_context *, gb_fermion *z, const gb_fermion *x, const gb_fermion *y, const double *d_c, const double *d_d, double *d_out) {
   double n2;
   gb_axpy_norm(z, -(*d_c) / (*d_d), x, y, &n2);
@@ -144,24 +193,41 @@ int gb_timer_start(gb_context *) { return GB_OK; }
 int gb_timer_stop(gb_context *, double *ms) { if (ms) *ms = 0; return GB_OK; }
 int64_t gb_launch_count(gb_context *c) { return c->launches; }
 int gb_flush_l2(gb_context *) { return GB_OK; }
-int gb_comm_unique_id(void *) { MOCK_UNSUPPORTED("gb_comm_unique_id"); }
-int gb_comm_init(gb_context *c, int rank, int nranks, const void *) { if (nranks != 1) MOCK_UNSUPPORTED("gb_comm_init (nranks > 1)"); c->rank = rank; c->nranks = 1; return GB_OK; }
-int gb_comm_rank(gb_context *, int *r, int *n) { if (r) *r = 0; if (n) *n = 1; return GB_OK; }
-int gb_comm_global_sum(gb_context *, double *, int) { return GB_OK; }
-int gb_comm_barrier(gb_context *) { return GB_OK; }
+int gb_comm_unique_id(void *id) { std::memset(id, 0, GB_UNIQUE_ID_BYTES); return GB_OK; }
+int gb_comm_init(gb_context *c, int rank, int nranks, const void *) {
+  c->rank = rank; c->nranks = nranks;
+  if (nranks > 1) c->nccl = new ncclComm{rank, nranks};     // the "communicator" of a rank thread
+  return GB_OK;
+}
+int gb_comm_rank(gb_context *c, int *r, int *n) { if (r) *r = c->rank; if (n) *n = c->nranks; return GB_OK; }
+int gb_comm_global_sum(gb_context *c, double *v, int n) { global_sum(c, v, n); return GB_OK; }
+int gb_comm_barrier(gb_context *c) { double v = 0; global_sum(c, &v, 1); return GB_OK; }
+// rank -> processor coordinate lexicographic with dimension 0 fastest, the library's rule (include/gridb200.h)
+int gb_geometry_query(const int gdims[4], const int mpi[4], int rank, int ldims[4], int origin[4], int nbr[8]) {
+  int pc[4], r = rank;
+  for (int d = 0; d < 4; d++) { if (mpi[d] < 1 || gdims[d] % mpi[d] || (gdims[d] / mpi[d]) % 2) return fail(GB_ERR_INVALID, "bad decomposition"); pc[d] = r % mpi[d]; r /= mpi[d]; }
+  auto rk = [&](const int *p) { return p[0] + mpi[0] * (p[1] + mpi[1] * (p[2] + mpi[2] * p[3])); };
+  for (int d = 0; d < 4; d++) {
+    ldims[d] = gdims[d] / mpi[d]; origin[d] = pc[d] * ldims[d];
+    int q[4] = {pc[0], pc[1], pc[2], pc[3]};
+    q[d] = (pc[d] + 1) % mpi[d]; nbr[2 * d] = rk(q);
+    q[d] = (pc[d] + mpi[d] - 1) % mpi[d]; nbr[2 * d + 1] = rk(q);
+  }
+  return GB_OK;
+}
 int gb_grid_create(gb_context *ctx, const int gdims[4], const int mpi[4], gb_grid **out) {
-  for (int d = 0; d < 4; d++) if (mpi[d] != 1 || gdims[d] % 2) return fail(GB_ERR_INVALID, "mock grid: one rank, even extents");
   gb_grid *g = new gb_grid();
   g->ctx = ctx;
-  for (int d = 0; d < 4; d++) { g->gdims[d] = g->ldims[d] = gdims[d]; g->mpi[d] = 1; g->pcoor[d] = g->origin[d] = 0; g->nbr_rank[d][0] = g->nbr_rank[d][1] = 0; }
-  g->V4 = (int64_t)gdims[0] * gdims[1] * gdims[2] * gdims[3]; g->V4cb = g->V4 / 2;
+  int nbr[8];
+  if (gb_geometry_query(gdims, mpi, ctx->rank, g->ldims, g->origin, nbr) != GB_OK) { delete g; return GB_ERR_INVALID; }
+  for (int d = 0; d < 4; d++) { g->gdims[d] = gdims[d]; g->mpi[d] = mpi[d]; g->pcoor[d] = g->origin[d] / g->ldims[d]; g->nbr_rank[d][0] = nbr[2 * d]; g->nbr_rank[d][1] = nbr[2 * d + 1]; }
+  g->V4 = (int64_t)g->ldims[0] * g->ldims[1] * g->ldims[2] * g->ldims[3]; g->V4cb = g->V4 / 2;
   *out = g;
   return GB_OK;
 }
-int gb_geometry_query(const int *, const int *, int, int *, int *, int *) { MOCK_UNSUPPORTED("gb_geometry_query"); }
 int gb_grid_destroy(gb_grid *g) { delete g; return GB_OK; }
 int gb_grid_local_dims(const gb_grid *g, int l[4]) { for (int d = 0; d < 4; d++) l[d] = g->ldims[d]; return GB_OK; }
-int gb_grid_local_origin(const gb_grid *g, int o[4]) { for (int d = 0; d < 4; d++) o[d] = 0; return GB_OK; }
+int gb_grid_local_origin(const gb_grid *g, int o[4]) { for (int d = 0; d < 4; d++) o[d] = g->origin[d]; return GB_OK; }
 int gb_fermion_create(gb_grid *g, int Ls, gb_precision prec, gb_gridkind kind, gb_fermion **out) { *out = create(g, Ls, 12, prec, kind); return GB_OK; }
 int gb_staggered_fermion_create(gb_grid *g, gb_precision prec, gb_gridkind kind, gb_fermion **out) { *out = create(g, 1, 3, prec, kind); return GB_OK; }
 int gb_fermion_destroy(gb_fermion *f) { if (f) { std::free(f->data); delete f; } return GB_OK; }
@@ -236,10 +302,11 @@ int gb_norm2(const gb_fermion *x, double *out) {
   BY_PREC(x, { const float *p = (const float *)x->data; for (size_t i = 0; i < scalars<float>(x); i++) s += (double)(p[i] * p[i]); },
           { const double *p = (const double *)x->data; for (size_t i = 0; i < scalars<double>(x); i++) s += p[i] * p[i]; });
   *out = s;
+  global_sum(x->grid->ctx, out, 1);
   return GB_OK;
 }
 int gb_axpy_norm(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y, double *n2) { int rc = gb_axpy(z, a, x, y); if (rc != GB_OK) return rc; return gb_norm2(z, n2); }
-int gb_inner_product(const gb_fermion *l, const gb_fermion *r, double out[2]) { if (l->prec == GB_F32) inner_T<float>(l, r, out); else inner_T<double>(l, r, out); return GB_OK; }
+int gb_inner_product(const gb_fermion *l, const gb_fermion *r, double out[2]) { if (l->prec == GB_F32) inner_T<float>(l, r, out); else inner_T<double>(l, r, out); global_sum(l->grid->ctx, out, 2); return GB_OK; }
 // gauge fields: lexicographic host arrays of the field's precision
 int gb_gauge_create(gb_grid *g, gb_precision prec, gb_gauge **out) {
   gb_gauge *u = new gb_gauge();

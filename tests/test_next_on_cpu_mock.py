@@ -11,7 +11,9 @@ the tests compare its results with the oracle, the golden fixtures and the compi
 
  * every `unverified` GPU test of the SURVEY 8(f) rows and of the N-rank staggered path passes on it (41 tests; all but the C++
    drivers, which link the real library);
- * so do the measured suite's golden-vector GPU tests (tests/test_golden.py), which is what says the mock itself can be trusted.
+ * so do the measured suite's golden-vector GPU tests (tests/test_golden.py), which is what says the mock itself can be trusted;
+ * with host threads as ranks and mailboxes as the network, the N-rank checks of scripts/mgpu_check.py pass too: the decomposed
+   Wilson / DWF hops (measured green on 2, 4, 8 B200) and the improved staggered operator with three-deep halos (not yet run on GPUs).
 It cannot see: the tuned fp32 kernels, the dense s-space kernel (so Ls = 8 / 12 / 16 operators), reductions, real streams, NCCL
 and peer-to-peer halos, launch configuration -- the device is still needed for those.  The product has no CPU path: this lives
 under tests/ and is selected only by tests/conftest.py (GB_TEST_MOCK_LIB)."""
@@ -56,6 +58,15 @@ def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(mock_lib):
     """the mock reproduces the reference's outputs through the product's generic path: 4^4 x Ls 4 Wilson / DWF / Moebius / staggered
     operators, CG and mixed CG (the same tests are green on the B200 with the tuned kernels)"""
     assert run_gpu_tests_on_mock(mock_lib, ["tests/test_golden.py"]) >= 10
+
+
+def test_n_rank_parity_on_the_cpu_mock(mock_lib):
+    """tests/mock/mgpu_on_mock.py: ranks are host threads, halo messages go through the mock's mailboxes.  Decomposed Wilson / DWF /
+    Moebius hops (overlapped and serial orchestration, gauge-face exchange, DhopDir legs across the boundary) and the improved
+    staggered operator with three-deep halos on 2 and 4 ranks (1.1.1.2, 2.1.1.1, 1.2.1.1, 1.1.2.2, 1.1.1.4), reductions, CG and the
+    Schur solve against the oracle on the global lattice -- what scripts/mgpu_check.py checks on N GPUs."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "mgpu_on_mock.py"), mock_lib], cwd=ROOT, capture_output=True, text=True, timeout=1500)
+    assert p.returncode == 0 and "MGPU_ON_MOCK PASS" in p.stdout, (p.stdout + p.stderr)[-3000:]
 
 
 def test_the_mock_is_not_reachable_from_the_product():
