@@ -270,7 +270,7 @@ static gb_fermop *make_op(gb_grid *g, const gb_gauge *Umu, int kind, int Ls, dou
     op->sm_B = smat_device(op, smat_mul(A, Mi));
     op->sm_Bdag = smat_device(op, smat_mul(Mid, Ad));
     op->sm_negAdag = smat_device(op, smat_scale(Ad, -1.0));
-    op->use_smat = true;
+    op->use_smat = op->sm_B != nullptr && op->sm_Bdag != nullptr;   // the dense s-space path needs its matrices on the device
   }
   try { op_import_gauge(op, Umu); } catch (...) { delete op; throw; }
   return op;

@@ -157,9 +157,9 @@ void global_sum(gb_context *ctx, double *v, int n) {
 }
 template <class T> static void inner_T(const gb_fermion *l, const gb_fermion *r, double out[2]) {
   const T *a = (const T *)l->data, *b = (const T *)r->data;
-  double re = 0, im = 0;
+  long double re = 0, im = 0;   // site products in working precision, lattice sum in extended precision (the real reductions are trees)
   for (size_t i = 0; i < scalars<T>(l); i += 2) { re += (double)(a[i] * b[i] + a[i + 1] * b[i + 1]); im += (double)(a[i] * b[i + 1] - a[i + 1] * b[i]); }
-  out[0] = re; out[1] = im;
+  out[0] = (double)re; out[1] = (double)im;
 }
 void reduce_inner_dev(gb_context *ctx, const gb_fermion *l, const gb_fermion *r, double *d_out) { if (l->prec == GB_F32) inner_T<float>(l, r, d_out); else inner_T<double>(l, r, d_out); global_sum(ctx, d_out, 2); }
 void axpy_norm_dev(gb_context *, gb_fermion *z, const gb_fermion *x, const gb_fermion *y, const double *d_c, const double *d_d, double *d_out) {
@@ -298,10 +298,10 @@ int gb_axpy(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y) {
   GB_API_END
 }
 int gb_norm2(const gb_fermion *x, double *out) {
-  double s = 0;
+  long double s = 0;
   BY_PREC(x, { const float *p = (const float *)x->data; for (size_t i = 0; i < scalars<float>(x); i++) s += (double)(p[i] * p[i]); },
           { const double *p = (const double *)x->data; for (size_t i = 0; i < scalars<double>(x); i++) s += p[i] * p[i]; });
-  *out = s;
+  *out = (double)s;
   global_sum(x->grid->ctx, out, 1);
   return GB_OK;
 }

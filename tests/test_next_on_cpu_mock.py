@@ -60,6 +60,12 @@ def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(mock_lib):
     assert run_gpu_tests_on_mock(mock_lib, ["tests/test_golden.py"]) >= 10
 
 
+def test_measured_parity_gpu_tests_pass_on_the_cpu_mock(mock_lib):
+    """tests/test_gpu_parity.py (every operator entry, BLAS, reductions, CG on Wilson 8^4, DWF Ls 8, Moebius Ls 12; green on the B200)
+    through the mock's generic path -- all but the host-pipelined Dhop and the device RNG, which the mock does not provide"""
+    assert run_gpu_tests_on_mock(mock_lib, ["tests/test_gpu_parity.py"], ("-k", "not dhop_host and not device_random")) >= 300
+
+
 def test_n_rank_parity_on_the_cpu_mock(mock_lib):
     """tests/mock/mgpu_on_mock.py: ranks are host threads, halo messages go through the mock's mailboxes.  Decomposed Wilson / DWF /
     Moebius hops (overlapped and serial orchestration, gauge-face exchange, DhopDir legs across the boundary) and the improved
