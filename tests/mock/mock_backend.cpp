@@ -331,7 +331,29 @@ int gb_gauge_export(const gb_gauge *u, void *host, gb_precision hp) {
   }
   return GB_OK;
 }
-int gb_gauge_random(gb_gauge *, uint64_t) { MOCK_UNSUPPORTED("gb_gauge_random"); }
-int gb_gauge_unit(gb_gauge *) { MOCK_UNSUPPORTED("gb_gauge_unit"); }
+// some random SU(3) per link (Gram-Schmidt of a Gaussian matrix, determinant rotated to one); not the library's generator
+int gb_gauge_random(gb_gauge *u, uint64_t seed) {
+  std::mt19937_64 gen(seed * 2654435761ull + 17);
+  std::normal_distribution<double> g(0.0, 1.0);
+  std::vector<double> h((size_t)u->grid->V4 * 72);
+  for (size_t l = 0; l < (size_t)u->grid->V4 * 4; l++) {
+    cd m[3][3];
+    for (auto &r : m) for (auto &c : r) c = cd(g(gen), g(gen));
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < i; j++) { cd d = 0; for (int k = 0; k < 3; k++) d += std::conj(m[j][k]) * m[i][k]; for (int k = 0; k < 3; k++) m[i][k] -= d * m[j][k]; }
+      double n = 0; for (int k = 0; k < 3; k++) n += std::norm(m[i][k]);
+      for (int k = 0; k < 3; k++) m[i][k] /= std::sqrt(n);
+    }
+    const cd det = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) + m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+    for (int k = 0; k < 3; k++) m[2][k] /= det;
+    for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) { h[(l * 9 + 3 * i + k) * 2] = m[i][k].real(); h[(l * 9 + 3 * i + k) * 2 + 1] = m[i][k].imag(); }
+  }
+  return gb_gauge_import(u, h.data(), GB_F64);
+}
+int gb_gauge_unit(gb_gauge *u) {
+  std::vector<double> h((size_t)u->grid->V4 * 72, 0.0);
+  for (size_t l = 0; l < (size_t)u->grid->V4 * 4; l++) for (int i = 0; i < 3; i++) h[(l * 9 + 4 * i) * 2] = 1.0;
+  return gb_gauge_import(u, h.data(), GB_F64);
+}
 int gb_op_dhop_host(gb_fermop *, const void *, void *, gb_precision, int) { MOCK_UNSUPPORTED("gb_op_dhop_host"); }
 }

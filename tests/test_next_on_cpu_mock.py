@@ -66,6 +66,22 @@ def test_measured_parity_gpu_tests_pass_on_the_cpu_mock(mock_lib):
     assert run_gpu_tests_on_mock(mock_lib, ["tests/test_gpu_parity.py"], ("-k", "not dhop_host and not device_random")) >= 300
 
 
+DRIVERS = [("Test_dwf_cg_schur", ["--grid", "4.4.4.4", "--Ls", "4"], "PASS"), ("Test_dwf_multishift", ["--grid", "4.4.4.4", "--Ls", "4"], "PASS"),
+           ("Test_dwf_force", ["--grid", "4.4.4.4", "--Ls", "4"], "PASS"), ("Test_dwf_mixedcg_prec", ["--grid", "4.4.4.4", "--Ls", "4"], "done"),
+           ("Benchmark_staggered", ["--grid", "4.4.4.4", "--ncall", "2"], "done"), ("Benchmark_dwf_fp32", ["--grid", "4.4.4.4", "--Ls", "4", "--ncall", "2"], "done")]
+
+
+@pytest.mark.parametrize("name,args,word", DRIVERS)
+def test_cpp_drivers_run_on_the_cpu_mock(mock_lib, name, args, word):
+    """the reference-shaped C++ programs (drivers/*.cc over include/gridb200.hpp), linked against the mock instead of the CUDA library:
+    their asserts are the reference's (residuals, |x_mixed - x_double|, Deo + Doe = D, the force identity)"""
+    d = os.path.dirname(mock_lib)
+    exe = os.path.join(d, name)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "drivers", name + ".cc"), "-L" + d, "-lgridb200_mock", "-Wl,-rpath," + d])
+    p = subprocess.run([exe, *args], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and word in p.stdout, (p.stdout + p.stderr)[-2000:]
+
+
 def test_n_rank_parity_on_the_cpu_mock(mock_lib):
     """tests/mock/mgpu_on_mock.py: ranks are host threads, halo messages go through the mock's mailboxes.  Decomposed Wilson / DWF /
     Moebius hops (overlapped and serial orchestration, gauge-face exchange, DhopDir legs across the boundary) and the improved
