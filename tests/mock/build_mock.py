@@ -14,7 +14,8 @@ from transform import transform  # noqa: E402
 PRODUCT_SOURCES = ["fermop.cu", "dhop.cu", "cayley.cu", "stag.cu", "solver.cu", "schur.cu", "force.cu", "nersc.cu"]
 
 
-def build(outdir):
+def build(outdir, sanitize=False):
+    """sanitize=True: AddressSanitizer + UBSan build (run python with LD_PRELOAD=$(gcc -print-file-name=libasan.so))"""
     os.makedirs(outdir, exist_ok=True)
     csrc = os.path.join(ROOT, "grid_b200", "csrc")
     cpps = []
@@ -23,11 +24,12 @@ def build(outdir):
         open(out, "w").write(f"// generated from grid_b200/csrc/{f} by tests/mock/transform.py\n" + transform(open(os.path.join(csrc, f)).read()))
         cpps.append(out)
     lib = os.path.join(outdir, "libgridb200_mock.so")
-    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-I", os.path.join(HERE, "shim"), "-I", csrc, "-o", lib, *cpps,
+    san = ["-fsanitize=address,undefined", "-fno-omit-frame-pointer", "-g"] if sanitize else []
+    cmd = ["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", *san, "-I", os.path.join(HERE, "shim"), "-I", csrc, "-o", lib, *cpps,
            os.path.join(HERE, "mock_backend.cpp"), "-Wl,--no-undefined"]
     subprocess.check_call(cmd)
     return lib
 
 
 if __name__ == "__main__":
-    print(build(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "_build")))
+    print(build(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "_build"), sanitize="--sanitize" in sys.argv))
