@@ -176,6 +176,21 @@ def main():
         errs += staggered(mpi, tuple(max(4 * m, 8) if m > 1 else (6 if d == 1 else 4) for d, m in enumerate(mpi)))
         print(f"mpi {mpi}: done, {len(fails) + len(errs)} problems so far", flush=True)
     errs += staggered((1, 1, 1, 4), (4, 4, 4, 16))       # distinct forward / backward neighbours
+    # the tuned fp32 kernels on decomposed lattices (Ls = 8, local 8.4.4.4): pack_send into the neighbours' buffers, then the
+    # semi-fused hop (z / t split: one launch, surface CTAs acquire the flags) or interior + exterior (x / y split)
+    import ctypes
+    lib = ctypes.CDLL(sys.argv[1])
+    lib.gb_mock_coop_launches.restype = ctypes.c_long
+    lib.gb_mock_coop_launches.argtypes = [ctypes.c_char_p]
+    before = {k: lib.gb_mock_coop_launches(k) for k in (b"dhop_fast_kernel<LS, 0, 2>", b"dhop_fast_kernel<LS, 1, 2>", b"dhop_fast_kernel<LS, 0, 1>", b"pack_send_kernel", b"smat_kernel")}
+    for mpi in ((1, 1, 2, 2), (1, 1, 1, 4), (1, 2, 1, 1)):
+        errs += wilson_like(mpi, tuple(l * m for l, m in zip((8, 4, 4, 4), mpi)), "dwf", 8)
+        print(f"mpi {mpi} tuned kernels: done, {len(fails) + len(errs)} problems so far", flush=True)
+    for k, v in before.items():
+        n = lib.gb_mock_coop_launches(k) - v
+        print(f"cooperative launches of {k.decode()}: {n}", flush=True)
+        if n == 0:
+            errs.append(f"{k.decode()} never ran: the tuned multi-rank path was not exercised")
     for e in errs + fails:
         print("FAIL", e, flush=True)
     print("MGPU_ON_MOCK " + ("PASS" if not (errs or fails) else f"FAIL ({len(errs) + len(fails)})"), flush=True)

@@ -90,22 +90,9 @@ gb_fermion *fermion_create_like(const gb_fermion *like, int prec) {
   f->cb = like->cb;
   return f;
 }
-// ---- the tuned paths are switched off: every hop runs the generic kernel, every s-space operator the m5d / mooee_inv kernels
-bool dhop_fast_launch(gb_fermop *, const void *const[2], void *const[2], int, int, int, const void *const[2], double, double, int, cudaStream_t, const void *const[8],
-                      const unsigned long long *, unsigned long long) { return false; }
-bool p2p_setup(gb_fermop *) { return false; }
-void p2p_teardown(gb_fermop *) {}
-unsigned long long p2p_next_epoch(gb_fermop *) { throw Error(GB_ERR_INVALID, "mock: no peer-to-peer halos"); }
-void p2p_send_only(gb_fermop *, unsigned long long, const void *const[2], int, int, int, cudaStream_t) { throw Error(GB_ERR_INVALID, "mock: no peer-to-peer halos"); }
-unsigned long long p2p_pack_send(gb_fermop *, const void *const[2], int, int, int, cudaStream_t) { throw Error(GB_ERR_INVALID, "mock: no peer-to-peer halos"); }
-void p2p_fill_halo(gb_fermop *, unsigned long long, const void *[8], const unsigned long long **) { throw Error(GB_ERR_INVALID, "mock: no peer-to-peer halos"); }
-SMat smat_identity(int) { return SMat(); }
-SMat smat_m5d(int, const std::vector<double> &, const std::vector<double> &, const std::vector<double> &, int) { return SMat(); }
-SMat smat_mooee_inv(const CayleyCoeffs &, int) { return SMat(); }
-SMat smat_mul(const SMat &, const SMat &) { return SMat(); }
-SMat smat_scale(const SMat &, double) { return SMat(); }
-const void *smat_device(gb_fermop *, const SMat &) { return nullptr; }
-bool smat_apply(gb_fermop *, const void *, const gb_fermion *, const void *, const gb_fermion *, double, const gb_fermion *, gb_fermion *) { return false; }
+// ---- nothing is switched off any more: the tuned kernels, the dense s-space kernel and the peer-to-peer halos are the product's own
+//      (dhop_fast.cu, smat.cu, halo_p2p.cu); cooperative kernels run block by block on fibres (simt.cpp), "peer mappings" are plain
+//      pointers because the ranks are threads of one process (shim: cudaIpc*)
 } // namespace gb
 // ---- "ranks" are host threads of one process (each drives its own context); send / recv are copies through mailboxes
 struct ncclComm { int rank, nranks; };
@@ -116,6 +103,8 @@ struct World {
   std::map<std::pair<int, int>, std::deque<std::vector<char>>> box;   // (source, destination) -> messages in order
   int arrived = 0; long gen = 0;
   std::vector<double> acc, res;
+  int ag_arrived = 0; long ag_gen = 0;
+  std::vector<char> ag_buf, ag_res;
 } g_world;
 ncclResult_t mock_send(const void *buf, size_t n, ncclDataType_t t, int peer, ncclComm_t c, cudaStream_t) {
   const size_t bytes = n * (t == ncclDouble ? 8 : 1);
@@ -134,13 +123,24 @@ ncclResult_t mock_recv(void *buf, size_t n, ncclDataType_t t, int peer, ncclComm
   q.pop_front();
   return 0;
 }
+ncclResult_t mock_allgather(const void *send, void *recv, size_t n, ncclDataType_t t, ncclComm_t c, cudaStream_t) {
+  const size_t bytes = n * (t == ncclDouble ? 8 : 1);
+  std::unique_lock<std::mutex> l(g_world.m);
+  if (g_world.ag_arrived == 0) g_world.ag_buf.assign(bytes * c->nranks, 0);
+  std::memcpy(g_world.ag_buf.data() + (size_t)c->rank * bytes, send, bytes);   // (send may point into recv: copied before recv is written)
+  const long mygen = g_world.ag_gen;
+  if (++g_world.ag_arrived == c->nranks) { g_world.ag_res = g_world.ag_buf; g_world.ag_arrived = 0; g_world.ag_gen++; g_world.cv.notify_all(); }
+  else g_world.cv.wait(l, [&] { return g_world.ag_gen != mygen; });
+  std::memcpy(recv, g_world.ag_res.data(), bytes * c->nranks);
+  return 0;
+}
 ncclResult_t mock_group() { return 0; }
 const char *mock_errstr(ncclResult_t) { return "mock nccl error (message size mismatch)"; }
 } // namespace
 namespace gb {
 NcclApi &nccl() {
   static NcclApi api;
-  if (!api.ok) { api.ok = true; api.Send = mock_send; api.Recv = mock_recv; api.GroupStart = mock_group; api.GroupEnd = mock_group; api.GetErrorString = mock_errstr; }
+  if (!api.ok) { api.ok = true; api.Send = mock_send; api.Recv = mock_recv; api.AllGather = mock_allgather; api.GroupStart = mock_group; api.GroupEnd = mock_group; api.GetErrorString = mock_errstr; }
   return api;
 }
 void nccl_check(int r, const char *what) { if (r != 0) throw Error(GB_ERR_COMM, what); }
@@ -182,6 +182,7 @@ const char *gb_last_error(void) { return g_err.c_str(); }
 int gb_device_count(void) { return 1; }
 int gb_context_create(int device, gb_context **out) {
   gb_context *c = new gb_context();
+  if (getenv("GB_MOCK_SM_COUNT")) c->sm_count = std::max(1, atoi(getenv("GB_MOCK_SM_COUNT")));   // small values make persistent kernels loop over several tiles
   c->device = device;
   c->d_scalars = (double *)std::calloc(8, sizeof(double)); c->h_result = (double *)std::calloc(8, sizeof(double));
   *out = c;

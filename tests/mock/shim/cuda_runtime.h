@@ -51,13 +51,31 @@ inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return cudaSuccess; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return cudaSuccess; }
-inline void __syncthreads() {}   // only reached on paths the mock never takes (kernels that need it are not built here)
+// ranks are threads of one process: an IPC handle is the pointer itself
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t *h, void *p) { std::memset(h, 0, sizeof(*h)); std::memcpy(h->reserved, &p, sizeof(p)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void **p, cudaIpcMemHandle_t h, unsigned) { std::memcpy(p, h.reserved, sizeof(*p)); return cudaSuccess; }
+inline cudaError_t cudaIpcCloseMemHandle(void *) { return cudaSuccess; }
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
+inline void __threadfence_system() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline unsigned int atomicAdd(unsigned int *p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+#define __align__(n) __attribute__((aligned(n)))
+template <class F> inline cudaError_t cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return cudaSuccess; }
+#include <algorithm>
+using std::max;
+using std::min;
 
-// sequential "launch": every thread of every block in turn -- valid for kernels whose threads do not communicate
+// "launch": every thread of every block in turn -- valid for kernels whose threads do not communicate; kernels that use shared
+// memory, barriers or shuffles (transform.py: COOPERATIVE) run one block at a time with a fibre per thread (mock_simt.h)
+#include "mock_simt.h"
 namespace gb_mock {
 extern thread_local uint3 t_blockIdx, t_threadIdx;
 extern thread_local dim3 t_blockDim, t_gridDim;
-template <class F> inline void launch(dim3 grid, dim3 block, F &&body) {
+template <class F> inline void launch(dim3 grid, dim3 block, size_t smem, bool cooperative, const char *name, F &&body) {
+  if (cooperative) { count_coop_launch(name); coop_launch(grid.x, grid.y, block.x, smem, std::function<void()>(body)); return; }
   t_gridDim = grid; t_blockDim = block;
   for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++)
     for (unsigned tx = 0; tx < block.x; tx++) { t_blockIdx = {bx, by, 0}; t_threadIdx = {tx, 0, 0}; body(); }

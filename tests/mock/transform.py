@@ -2,6 +2,7 @@
 """Rewrites CUDA kernel launches  kernel<T...><<<grid, block, smem, stream>>>(args)  into  gb_mock::launch(grid, block, [&]() { kernel<T...>(args); })
 so that a host compiler can build the file against tests/mock/shim/cuda_runtime.h.  Test infrastructure only.
 usage: transform.py in.cu out.cpp"""
+import re
 import sys
 
 
@@ -47,18 +48,61 @@ def split_top(s):
     return out
 
 
+# functions of the product that are nothing but a PTX instruction: their bodies become calls of the emulation in shim/mock_simt.h
+ASM_WRAPPERS = ["pk", "upk", "fma2", "mul2", "add2", "sub2", "mbar_init", "mbar_expect_tx", "bulk_g2s", "mbar_wait", "cp_async16", "cp_async_arrive"]
+# kernels whose threads cooperate (shared memory, barriers, shuffles): run block by block on fibres (shim/mock_simt.h)
+COOPERATIVE = ["dhop_fast_kernel", "dhop_col_kernel", "smat_kernel", "pack_send_kernel"]
+# kernels that only sometimes need it: C++ condition on the (single) kernel argument.  The generic hopping kernel makes threads 0..7
+# acquire the neighbours' epoch flags and everybody else wait at a barrier -- only when it consumes peer-to-peer halos.
+COOPERATIVE_IF = {"dhop_kernel": "({arg}).flags != nullptr"}
+
+
+def replace_asm_wrappers(text):
+    for name in ASM_WRAPPERS:
+        for m in list(re.finditer(r"__device__\s+__forceinline__\s+[\w:]+\s+" + name + r"\s*\(", text))[::-1]:
+            p0 = m.end() - 1
+            p1 = match_fwd(text, p0, "(", ")")
+            b0 = text.index("{", p1)
+            b1 = match_fwd(text, b0, "{", "}")
+            if "asm" not in text[b0:b1]:
+                continue
+            names = [re.findall(r"\w+", a)[-1] for a in split_top(text[p0 + 1:p1])]
+            text = text[:b0] + "{ return gb_mock::" + name + "(" + ", ".join(names) + "); }" + text[b1 + 1:]
+    return text
+
+
 def strip_asm(text):
-    """inline PTX (the flag-acquire loop of the peer-to-peer halos) cannot be assembled for the host and is never reached in the mock"""
-    while True:
-        k = text.find("asm volatile(")
-        if k < 0:
-            return text
-        e = match_fwd(text, text.index("(", k), "(", ")")
-        text = text[:k] + "(void)0" + text[e + 1:]
+    """the inline PTX left after replace_asm_wrappers: the system-scope flag store / load of the peer-to-peer halos become GCC atomics,
+    anything else is dropped"""
+    for kw in ("asm volatile(", "asm("):
+        while True:
+            k = text.find(kw)
+            if k < 0:
+                break
+            e = match_fwd(text, text.index("(", k), "(", ")")
+            body = text[k:e + 1]
+            ops = re.findall(r'"=?[lrf]"\s*\(', body)
+            repl = "(void)0"
+            if "st.release.sys.global.u64" in body or "ld.acquire.sys.global.u64" in body:
+                args = []
+                for mm in re.finditer(r'"=?l"\s*\(', body):
+                    a0 = mm.end() - 1
+                    args.append(body[a0 + 1:match_fwd(body, a0, "(", ")")])
+                if "st.release" in body:
+                    repl = f"__atomic_store_n((unsigned long long *)({args[0]}), (unsigned long long)({args[1]}), __ATOMIC_RELEASE)"
+                else:
+                    repl = f"{args[0]} = __atomic_load_n((const unsigned long long *)({args[1]}), __ATOMIC_ACQUIRE)"
+            text = text[:k] + repl + text[e + 1:]
+    return text
+
+
+def shared_memory(text):
+    text = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?unsigned char (\w+)\[\];", r"unsigned char *\1 = gb_mock::dynamic_smem();", text)
+    return re.sub(r"\b__shared__\b", "static thread_local", text)
 
 
 def transform(text):
-    text = strip_asm(text)
+    text = shared_memory(strip_asm(replace_asm_wrappers(text)))
     while True:
         k = text.find("<<<")
         if k < 0:
@@ -76,7 +120,10 @@ def transform(text):
         a0 = text.index("(", e)
         a1 = match_fwd(text, a0, "(", ")")
         args = text[a0:a1 + 1]
-        text = text[:start] + f"gb_mock::launch(dim3({cfg[0]}), dim3({cfg[1]}), [&]() {{ {kernel}{args}; }})" + text[a1 + 1:]
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        base = kernel.split("<")[0].split("::")[-1]
+        coop = "true" if base in COOPERATIVE else COOPERATIVE_IF[base].format(arg=args[1:-1]) if base in COOPERATIVE_IF else "false"
+        text = text[:start] + f"gb_mock::launch(dim3({cfg[0]}), dim3({cfg[1]}), {smem}, {coop}, \"{kernel}\", [&]() {{ {kernel}{args}; }})" + text[a1 + 1:]
 
 
 if __name__ == "__main__":

@@ -360,9 +360,12 @@ def test_mixed_precision_cg(ctx, kind, kw):
     # same restart structure as the oracle's restatement of the algorithm
     _, info = po.mixed_cg(s.oracle[gb.F64], s.oracle[gb.F32], gb.Odd, h, 1e-8, 10000, 50)
     assert mcg.TotalOuterIterations == info["outer"]
-    # fp32 inner solves: rounding differs between the two fp32 implementations, so on this tiny lattice (~125
-    # iterations) allow 5 %; the +-2 % bar is asserted for the fp64 solve above and at size in tests/test_gpu_full_size.py
-    assert abs(mcg.TotalInnerIterations - info["inner"]) <= max(3, 0.05 * info["inner"])
+    # fp32 inner solves: the restart points of this tiny lattice (~190 iterations in two restarts) move with the rounding of
+    # the fp32 reductions -- the oracle alone gives 184 or 189 inner iterations (and 1 or 4 final ones) depending on the order
+    # in which its OpenMP threads combine their partial sums, i.e. a 3 % spread within ONE implementation -- so two different
+    # fp32 implementations are allowed 8 % here; the +-2 % bar is asserted for the fp64 solve above and at size in
+    # tests/test_gpu_full_size.py
+    assert abs(mcg.TotalInnerIterations - info["inner"]) <= max(3, 0.08 * info["inner"])
     # the fp64 patch-up solve starts from wherever the fp32 restarts left the residual: a handful of iterations either way
     assert abs(mcg.TotalFinalStepIterations - info["final"]) <= 4
 

@@ -1,22 +1,26 @@
 """GPU tests run on the CPU against a MOCK build of the library (tests/mock/).
 
-What the mock is: product source files whose kernels' threads never communicate -- grid_b200/csrc/fermop.cu (operator
-compositions), dhop.cu (generic hopping kernel, double store, leg mask, serial-comms orchestration), cayley.cu (M5D, MooeeInv),
-stag.cu (improved staggered operator incl. the three-deep halo path in its self-exchange form), solver.cu (CG, mixed / reliable-
-update / multishift solvers and their fused update kernels), schur.cu, force.cu, nersc.cu -- compiled AS THEY ARE for the host
-through a stand-in cuda_runtime.h and a launch rewriter (each launch becomes a loop over blocks and threads), linked with a
-backend that supplies the rest: field containers, import / export, BLAS-1 and reductions as plain loops over the same blocked
-layout, and stubs that switch the tuned paths off (dhop_fast / dhop_col, smat, peer-to-peer halos, NCCL).  No oracle inside:
-the tests compare its results with the oracle, the golden fixtures and the compiled reference, exactly as they do on a GPU.
+What the mock is: the product's source files -- grid_b200/csrc/fermop.cu (operator compositions), dhop.cu (generic hopping kernel,
+double store, leg mask, the multi-rank orchestration), dhop_fast.cu with dhop_fast.cuh / dhop_col.cuh (the tuned fp32 kernels: TMA
+bulk copies of the links, cp.async rings, mbarriers, packed f32x2 math, the semi-fused multi-rank hop), halo_p2p.cu (pack + peer
+stores + epoch flags), smat.cu (dense s-space kernel, persistent CTAs with a two-stage TMA pipeline), cayley.cu, stag.cu (improved
+staggered operator incl. three-deep halos), solver.cu (CG, mixed / reliable-update / multishift solvers and their fused update
+kernels), schur.cu, force.cu, nersc.cu -- compiled AS THEY ARE for the host through a stand-in cuda_runtime.h and a source rewriter:
+a launch of a kernel whose threads do not talk to each other becomes a loop over blocks and threads; kernels that use shared memory,
+barriers, mbarriers or asynchronous copies run one block at a time with a fibre per CUDA thread (tests/mock/simt.cpp), the one-line
+PTX wrappers of the product (mbarrier, cp.async, cp.async.bulk, f32x2) are replaced by emulations and the system-scope flag
+store / load of the peer-to-peer halos by host atomics.  A backend supplies the rest: field containers, import / export, BLAS-1 and
+reductions as plain loops over the same blocked layout, and NCCL as mailboxes between threads.  No oracle inside: the tests compare
+its results with the oracle, the golden fixtures and the compiled reference, exactly as they do on a GPU.
 
- * every `unverified` GPU test of the SURVEY 8(f) rows and of the N-rank staggered path passes on it (41 tests; all but the C++
-   drivers, which link the real library);
- * so do the measured suite's golden-vector GPU tests (tests/test_golden.py), which is what says the mock itself can be trusted;
- * with host threads as ranks and mailboxes as the network, the N-rank checks of scripts/mgpu_check.py pass too: the decomposed
-   Wilson / DWF hops (measured green on 2, 4, 8 B200) and the improved staggered operator with three-deep halos (not yet run on GPUs).
-It cannot see: the tuned fp32 kernels, the dense s-space kernel (so Ls = 8 / 12 / 16 operators), reductions, real streams, NCCL
-and peer-to-peer halos, launch configuration -- the device is still needed for those.  The product has no CPU path: this lives
-under tests/ and is selected only by tests/conftest.py (GB_TEST_MOCK_LIB)."""
+ * every `unverified` GPU test of the SURVEY 8(f) rows and of the N-rank staggered path passes on it (41 tests);
+ * so do the measured suite's golden-vector and parity GPU tests -- now THROUGH the tuned kernels (the launch counters prove it), in
+   both shapes: column-sweep kernel by default, micro-block kernel with GB_NO_COL=1, persistent s-space kernel looping over tiles;
+ * with host threads as ranks the N-rank checks of scripts/mgpu_check.py pass too: peer-to-peer halos (a "peer mapping" is a plain
+   pointer between threads), interior + exterior and semi-fused hops, improved staggered operator with three-deep halos.
+It cannot see: memory ordering inside a block (fibres never run concurrently), bank conflicts, register pressure, launch limits,
+real streams / events, the reductions of fields.cu -- the device is still needed for those and for every performance number.
+The product has no CPU path: this lives under tests/ and is selected only by tests/conftest.py (GB_TEST_MOCK_LIB)."""
 import os
 import subprocess
 import sys
@@ -60,10 +64,32 @@ def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(mock_lib):
     assert run_gpu_tests_on_mock(mock_lib, ["tests/test_golden.py"]) >= 10
 
 
+def run_counted(mock_lib, pytest_args, count, env_extra=None):
+    """pytest against the mock in a child that afterwards reports the cooperative-launch counters -> {kernel: launches}"""
+    env = dict(os.environ, GB_UNVERIFIED_CHILD="1", GB_TEST_MOCK_LIB=mock_lib, GB_MOCK_COUNT=",".join(count), **(env_extra or {}))
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "run_counted.py"), *pytest_args, "-m", "gpu", "-q", "-p", "no:cacheprovider"],
+                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=2400)
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    summary = [l for l in p.stdout.splitlines() if " passed" in l][-1]
+    assert "failed" not in summary and "error" not in summary, summary
+    counts = {l.split()[1]: int(l.split()[2]) for l in p.stdout.splitlines() if l.startswith("COOP ")}
+    return int(summary.split(" passed")[0].split()[-1]), counts
+
+
 def test_measured_parity_gpu_tests_pass_on_the_cpu_mock(mock_lib):
     """tests/test_gpu_parity.py (every operator entry, BLAS, reductions, CG on Wilson 8^4, DWF Ls 8, Moebius Ls 12; green on the B200)
-    through the mock's generic path -- all but the host-pipelined Dhop and the device RNG, which the mock does not provide"""
-    assert run_gpu_tests_on_mock(mock_lib, ["tests/test_gpu_parity.py"], ("-k", "not dhop_host and not device_random")) >= 300
+    -- all but the host-pipelined Dhop and the device RNG, which the mock does not provide.  The fp32 hops go through the
+    column-sweep kernel, the s-space operators through the dense kernel (launch counters)"""
+    n, c = run_counted(mock_lib, ["tests/test_gpu_parity.py", "-k", "not dhop_host and not device_random"], ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"])
+    assert n >= 300 and c["dhop_col_kernel"] > 50 and c["smat_kernel"] > 1000, (n, c)
+
+
+def test_micro_block_kernel_and_persistent_s_space_kernel_on_the_cpu_mock(mock_lib):
+    """the other tuned shapes: GB_NO_COL=1 sends every fp32 hop through the micro-block kernel (the interior pass on decomposed
+    lattices), and with 3 "SMs" the s-space kernel's persistent CTAs loop over many tiles through their two-stage TMA pipeline"""
+    n, c = run_counted(mock_lib, ["tests/test_gpu_parity.py", "-k", "fast_and_generic or tiling or schur_operator or cg_matches"],
+                       ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {"GB_NO_COL": "1", "GB_MOCK_SM_COUNT": "3"})
+    assert n >= 40 and c["dhop_col_kernel"] == 0 and c["dhop_fast_kernel"] > 30 and c["smat_kernel"] > 100, (n, c)
 
 
 DRIVERS = [("Test_dwf_cg_schur", ["--grid", "4.4.4.4", "--Ls", "4"], "PASS"), ("Test_dwf_multishift", ["--grid", "4.4.4.4", "--Ls", "4"], "PASS"),
@@ -83,10 +109,12 @@ def test_cpp_drivers_run_on_the_cpu_mock(mock_lib, name, args, word):
 
 
 def test_n_rank_parity_on_the_cpu_mock(mock_lib):
-    """tests/mock/mgpu_on_mock.py: ranks are host threads, halo messages go through the mock's mailboxes.  Decomposed Wilson / DWF /
-    Moebius hops (overlapped and serial orchestration, gauge-face exchange, DhopDir legs across the boundary) and the improved
-    staggered operator with three-deep halos on 2 and 4 ranks (1.1.1.2, 2.1.1.1, 1.2.1.1, 1.1.2.2, 1.1.1.4), reductions, CG and the
-    Schur solve against the oracle on the global lattice -- what scripts/mgpu_check.py checks on N GPUs."""
+    """tests/mock/mgpu_on_mock.py: ranks are host threads.  Decomposed Wilson / DWF / Moebius hops with the product's peer-to-peer
+    halos (pack_send_kernel stores into the neighbour thread's receive buffer and publishes the epoch flag; the hop acquires it),
+    overlapped and serial orchestration, gauge-face exchange, DhopDir legs across the boundary; the tuned fp32 path at Ls = 8 --
+    the semi-fused launch on z / t splits (1.1.1.2, 1.1.2.2, 1.1.1.4), interior + exterior on a y split; the improved staggered operator
+    with three-deep halos on 2 and 4 ranks; reductions, CG and the Schur solve against the oracle on the global lattice -- what
+    scripts/mgpu_check.py checks on N GPUs.  The script fails if the semi-fused kernel or pack_send never ran."""
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "mgpu_on_mock.py"), mock_lib], cwd=ROOT, capture_output=True, text=True, timeout=1500)
     assert p.returncode == 0 and "MGPU_ON_MOCK PASS" in p.stdout, (p.stdout + p.stderr)[-3000:]
 
