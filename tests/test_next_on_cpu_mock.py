@@ -13,7 +13,8 @@ store / load of the peer-to-peer halos by host atomics.  A backend supplies the 
 reductions as plain loops over the same blocked layout, and NCCL as mailboxes between threads.  No oracle inside: the tests compare
 its results with the oracle, the golden fixtures and the compiled reference, exactly as they do on a GPU.
 
- * every `unverified` GPU test of the SURVEY 8(f) rows and of the N-rank staggered path passes on it (41 tests);
+ * every `unverified` GPU test of the SURVEY 8(f) rows, of the N-rank staggered path and of the tuned kernels' edge shapes passes on
+   it (56 tests);
  * so do the measured suite's golden-vector and parity GPU tests -- now THROUGH the tuned kernels (the launch counters prove it), in
    both shapes: column-sweep kernel by default, micro-block kernel with GB_NO_COL=1, persistent s-space kernel looping over tiles;
  * with host threads as ranks the N-rank checks of scripts/mgpu_check.py pass too: peer-to-peer halos (a "peer mapping" is a plain
@@ -29,7 +30,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NEXT = ["tests/test_next_schur_solve.py", "tests/test_next_force.py", "tests/test_next_multishift.py", "tests/test_next_relupcg.py",
-        "tests/test_next_nersc_io.py", "tests/test_next_stag_halo_gpu.py"]
+        "tests/test_next_nersc_io.py", "tests/test_next_stag_halo_gpu.py", "tests/test_next_tuned_shapes.py"]
 
 
 @pytest.fixture(scope="module")
@@ -55,7 +56,7 @@ def run_gpu_tests_on_mock(mock_lib, files, extra=()):
 
 def test_unverified_gpu_tests_pass_on_the_cpu_mock(mock_lib):
     # the C++ drivers are linked against the real library; everything else of these files runs
-    assert run_gpu_tests_on_mock(mock_lib, NEXT, ("-k", "not driver")) >= 41
+    assert run_gpu_tests_on_mock(mock_lib, NEXT, ("-k", "not driver")) >= 56
 
 
 def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(mock_lib):
@@ -66,13 +67,13 @@ def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(mock_lib):
 
 def run_counted(mock_lib, pytest_args, count, env_extra=None):
     """pytest against the mock in a child that afterwards reports the cooperative-launch counters -> {kernel: launches}"""
-    env = dict(os.environ, GB_UNVERIFIED_CHILD="1", GB_TEST_MOCK_LIB=mock_lib, GB_MOCK_COUNT=",".join(count), **(env_extra or {}))
+    env = dict(os.environ, GB_UNVERIFIED_CHILD="1", GB_TEST_MOCK_LIB=mock_lib, GB_MOCK_COUNT=";".join(count), **(env_extra or {}))
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "run_counted.py"), *pytest_args, "-m", "gpu", "-q", "-p", "no:cacheprovider"],
                        cwd=ROOT, env=env, capture_output=True, text=True, timeout=2400)
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
     summary = [l for l in p.stdout.splitlines() if " passed" in l][-1]
     assert "failed" not in summary and "error" not in summary, summary
-    counts = {l.split()[1]: int(l.split()[2]) for l in p.stdout.splitlines() if l.startswith("COOP ")}
+    counts = {l.split()[1]: int(l.split()[2]) for l in p.stdout.splitlines() if l.startswith("COOP ")}   # (names come back without blanks)
     return int(summary.split(" passed")[0].split()[-1]), counts
 
 
@@ -90,6 +91,13 @@ def test_micro_block_kernel_and_persistent_s_space_kernel_on_the_cpu_mock(mock_l
     n, c = run_counted(mock_lib, ["tests/test_gpu_parity.py", "-k", "fast_and_generic or tiling or schur_operator or cg_matches"],
                        ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {"GB_NO_COL": "1", "GB_MOCK_SM_COUNT": "3"})
     assert n >= 40 and c["dhop_col_kernel"] == 0 and c["dhop_fast_kernel"] > 30 and c["smat_kernel"] > 100, (n, c)
+
+
+def test_two_t_slices_per_cta_column_kernel_on_the_cpu_mock(mock_lib):
+    """GB_COL_NT=2 (opt-in variant, 512 threads: two adjacent t-slices share a CTA and read each other's ring slots for the t legs)"""
+    n, c = run_counted(mock_lib, ["tests/test_gpu_parity.py", "tests/test_next_tuned_shapes.py", "-k", "(fast_and_generic and dwf_col) or (edge_shapes and Ls8_n)"],
+                       ["dhop_col_kernel<LS, 0, 0, 2>", "dhop_col_kernel<LS, 1, 0, 2>"], {"GB_COL_NT": "2"})
+    assert n >= 8 and c["dhop_col_kernel<LS,0,0,2>"] > 5 and c["dhop_col_kernel<LS,1,0,2>"] > 5, (n, c)
 
 
 DRIVERS = [("Test_dwf_cg_schur", ["--grid", "4.4.4.4", "--Ls", "4"], "PASS"), ("Test_dwf_multishift", ["--grid", "4.4.4.4", "--Ls", "4"], "PASS"),
