@@ -13,5 +13,7 @@ lib = ctypes.CDLL(os.environ["GB_TEST_MOCK_LIB"])
 lib.gb_mock_coop_launches.restype = ctypes.c_long
 lib.gb_mock_coop_launches.argtypes = [ctypes.c_char_p]
 for k in os.environ.get("GB_MOCK_COUNT", "dhop_col_kernel;dhop_fast_kernel;smat_kernel").split(";"):
+    if not k:
+        continue
     print("COOP", k.replace(" ", ""), lib.gb_mock_coop_launches(k.encode()), flush=True)
 sys.exit(int(rc))

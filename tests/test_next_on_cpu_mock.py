@@ -43,60 +43,93 @@ def mock_lib(tmp_path_factory):
         sys.path.pop(0)
 
 
-def run_gpu_tests_on_mock(mock_lib, files, extra=()):
-    env = dict(os.environ, GB_UNVERIFIED_CHILD="1", GB_TEST_MOCK_LIB=mock_lib)
-    p = subprocess.run([sys.executable, "-m", "pytest", *files, "-m", "gpu", *extra, "-q", "-p", "no:cacheprovider"], cwd=ROOT, env=env,
-                       capture_output=True, text=True, timeout=2400)
-    tail = (p.stdout + p.stderr)[-3000:]
-    assert p.returncode == 0, tail
-    last = p.stdout.strip().splitlines()[-1]
-    assert " passed" in last and "failed" not in last and "xfailed" not in last and "error" not in last, tail
-    return int(last.split(" passed")[0].split()[-1])
+# every child run of this module, started side by side when the first test asks for one (they are independent processes; run one
+# after the other they take four minutes): name -> (pytest arguments | script, counters to report, extra environment)
+PARITY = ["tests/test_gpu_parity.py", "-k", "not dhop_host and not device_random"]
+JOBS = {
+    "unverified": (NEXT + ["-k", "not driver"], None, {}),
+    "golden": (["tests/test_golden.py"], None, {}),
+    "parity": (PARITY, ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {}),
+    "micro_block": (["tests/test_gpu_parity.py", "-k", "fast_and_generic or tiling or schur_operator or cg_matches"],
+                    ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {"GB_NO_COL": "1", "GB_MOCK_SM_COUNT": "3"}),
+    "two_t_slices": (["tests/test_gpu_parity.py", "tests/test_next_tuned_shapes.py", "-k", "(fast_and_generic and dwf_col) or (edge_shapes and Ls8_n)"],
+                     ["dhop_col_kernel<LS, 0, 0, 2>", "dhop_col_kernel<LS, 1, 0, 2>"], {"GB_COL_NT": "2"}),
+    "n_rank": ("mgpu_on_mock.py", None, {}),
+}
 
 
-def test_unverified_gpu_tests_pass_on_the_cpu_mock(mock_lib):
+class Children:
+    def __init__(self, mock_lib, outdir):
+        self.procs = {}
+        for name, (what, count, extra) in JOBS.items():
+            # the children run side by side: keep the oracle's and numpy's thread pools small or they fight for the cores
+            env = dict(os.environ, GB_UNVERIFIED_CHILD="1", GB_TEST_MOCK_LIB=mock_lib, GB_MOCK_COUNT=";".join(count or []), OMP_NUM_THREADS="2",
+                       OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", **extra)
+            if isinstance(what, str):
+                cmd = [sys.executable, os.path.join(ROOT, "tests", "mock", what), mock_lib]
+            else:
+                cmd = [sys.executable, os.path.join(ROOT, "tests", "mock", "run_counted.py"), *what, "-m", "gpu", "-q", "-p", "no:cacheprovider"]
+            log = open(os.path.join(outdir, name + ".log"), "w")
+            self.procs[name] = (subprocess.Popen(cmd, cwd=ROOT, env=env, stdout=log, stderr=subprocess.STDOUT), log)
+
+    def result(self, name):
+        """-> (exit code, output) of the child, waiting for it if it is still running"""
+        p, log = self.procs[name]
+        try:
+            p.wait(timeout=2400)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            raise
+        log.close()
+        return p.returncode, open(log.name).read()
+
+    def passed_and_counts(self, name):
+        rc, out = self.result(name)
+        assert rc == 0, out[-3000:]
+        summary = [l for l in out.splitlines() if " passed" in l][-1]
+        assert "failed" not in summary and "xfailed" not in summary and "error" not in summary, out[-3000:]
+        counts = {l.split()[1]: int(l.split()[2]) for l in out.splitlines() if l.startswith("COOP ")}   # (names come back without blanks)
+        return int(summary.split(" passed")[0].split()[-1]), counts
+
+
+@pytest.fixture(scope="module")
+def children(mock_lib):
+    c = Children(mock_lib, os.path.dirname(mock_lib))
+    yield c
+    for p, log in c.procs.values():
+        if p.poll() is None:
+            p.kill()
+
+
+def test_unverified_gpu_tests_pass_on_the_cpu_mock(children):
     # the C++ drivers are linked against the real library; everything else of these files runs
-    assert run_gpu_tests_on_mock(mock_lib, NEXT, ("-k", "not driver")) >= 56
+    assert children.passed_and_counts("unverified")[0] >= 56
 
 
-def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(mock_lib):
-    """the mock reproduces the reference's outputs through the product's generic path: 4^4 x Ls 4 Wilson / DWF / Moebius / staggered
-    operators, CG and mixed CG (the same tests are green on the B200 with the tuned kernels)"""
-    assert run_gpu_tests_on_mock(mock_lib, ["tests/test_golden.py"]) >= 10
+def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(children):
+    """the mock reproduces the reference's outputs: 4^4 x Ls 4 Wilson / DWF / Moebius / staggered operators, CG and mixed CG (the same
+    tests are green on the B200)"""
+    assert children.passed_and_counts("golden")[0] >= 10
 
 
-def run_counted(mock_lib, pytest_args, count, env_extra=None):
-    """pytest against the mock in a child that afterwards reports the cooperative-launch counters -> {kernel: launches}"""
-    env = dict(os.environ, GB_UNVERIFIED_CHILD="1", GB_TEST_MOCK_LIB=mock_lib, GB_MOCK_COUNT=";".join(count), **(env_extra or {}))
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "run_counted.py"), *pytest_args, "-m", "gpu", "-q", "-p", "no:cacheprovider"],
-                       cwd=ROOT, env=env, capture_output=True, text=True, timeout=2400)
-    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
-    summary = [l for l in p.stdout.splitlines() if " passed" in l][-1]
-    assert "failed" not in summary and "error" not in summary, summary
-    counts = {l.split()[1]: int(l.split()[2]) for l in p.stdout.splitlines() if l.startswith("COOP ")}   # (names come back without blanks)
-    return int(summary.split(" passed")[0].split()[-1]), counts
-
-
-def test_measured_parity_gpu_tests_pass_on_the_cpu_mock(mock_lib):
+def test_measured_parity_gpu_tests_pass_on_the_cpu_mock(children):
     """tests/test_gpu_parity.py (every operator entry, BLAS, reductions, CG on Wilson 8^4, DWF Ls 8, Moebius Ls 12; green on the B200)
     -- all but the host-pipelined Dhop and the device RNG, which the mock does not provide.  The fp32 hops go through the
     column-sweep kernel, the s-space operators through the dense kernel (launch counters)"""
-    n, c = run_counted(mock_lib, ["tests/test_gpu_parity.py", "-k", "not dhop_host and not device_random"], ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"])
+    n, c = children.passed_and_counts("parity")
     assert n >= 300 and c["dhop_col_kernel"] > 50 and c["smat_kernel"] > 1000, (n, c)
 
 
-def test_micro_block_kernel_and_persistent_s_space_kernel_on_the_cpu_mock(mock_lib):
+def test_micro_block_kernel_and_persistent_s_space_kernel_on_the_cpu_mock(children):
     """the other tuned shapes: GB_NO_COL=1 sends every fp32 hop through the micro-block kernel (the interior pass on decomposed
     lattices), and with 3 "SMs" the s-space kernel's persistent CTAs loop over many tiles through their two-stage TMA pipeline"""
-    n, c = run_counted(mock_lib, ["tests/test_gpu_parity.py", "-k", "fast_and_generic or tiling or schur_operator or cg_matches"],
-                       ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {"GB_NO_COL": "1", "GB_MOCK_SM_COUNT": "3"})
+    n, c = children.passed_and_counts("micro_block")
     assert n >= 40 and c["dhop_col_kernel"] == 0 and c["dhop_fast_kernel"] > 30 and c["smat_kernel"] > 100, (n, c)
 
 
-def test_two_t_slices_per_cta_column_kernel_on_the_cpu_mock(mock_lib):
+def test_two_t_slices_per_cta_column_kernel_on_the_cpu_mock(children):
     """GB_COL_NT=2 (opt-in variant, 512 threads: two adjacent t-slices share a CTA and read each other's ring slots for the t legs)"""
-    n, c = run_counted(mock_lib, ["tests/test_gpu_parity.py", "tests/test_next_tuned_shapes.py", "-k", "(fast_and_generic and dwf_col) or (edge_shapes and Ls8_n)"],
-                       ["dhop_col_kernel<LS, 0, 0, 2>", "dhop_col_kernel<LS, 1, 0, 2>"], {"GB_COL_NT": "2"})
+    n, c = children.passed_and_counts("two_t_slices")
     assert n >= 8 and c["dhop_col_kernel<LS,0,0,2>"] > 5 and c["dhop_col_kernel<LS,1,0,2>"] > 5, (n, c)
 
 
@@ -116,15 +149,15 @@ def test_cpp_drivers_run_on_the_cpu_mock(mock_lib, name, args, word):
     assert p.returncode == 0 and word in p.stdout, (p.stdout + p.stderr)[-2000:]
 
 
-def test_n_rank_parity_on_the_cpu_mock(mock_lib):
+def test_n_rank_parity_on_the_cpu_mock(children):
     """tests/mock/mgpu_on_mock.py: ranks are host threads.  Decomposed Wilson / DWF / Moebius hops with the product's peer-to-peer
     halos (pack_send_kernel stores into the neighbour thread's receive buffer and publishes the epoch flag; the hop acquires it),
     overlapped and serial orchestration, gauge-face exchange, DhopDir legs across the boundary; the tuned fp32 path at Ls = 8 --
     the semi-fused launch on z / t splits (1.1.1.2, 1.1.2.2, 1.1.1.4), interior + exterior on a y split; the improved staggered operator
     with three-deep halos on 2 and 4 ranks; reductions, CG and the Schur solve against the oracle on the global lattice -- what
     scripts/mgpu_check.py checks on N GPUs.  The script fails if the semi-fused kernel or pack_send never ran."""
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mock", "mgpu_on_mock.py"), mock_lib], cwd=ROOT, capture_output=True, text=True, timeout=1500)
-    assert p.returncode == 0 and "MGPU_ON_MOCK PASS" in p.stdout, (p.stdout + p.stderr)[-3000:]
+    rc, out = children.result("n_rank")
+    assert rc == 0 and "MGPU_ON_MOCK PASS" in out, out[-3000:]
 
 
 def test_the_mock_is_not_reachable_from_the_product():
