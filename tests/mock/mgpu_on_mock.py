@@ -101,6 +101,13 @@ def wilson_like(mpi, gdims, kind, Ls):
                     D.DhopDir(fin, out, d, s)
                     gb.axpy(tot, 1.0, out, tot)
             check(rank, f"{tag} prec{prec} sum of DhopDir legs", site_err(tot.export_lex(), decomp.scatter(ref[("dhop", 0)], gdims, mpi, rank, inner=Ls)), 4 * tol)
+            # the face exchange on its own (scripts/halo_bench.py): bytes sent = every split face, both directions, both parities,
+            # half spinors; and the epoch bookkeeping must leave the next hop intact
+            ld = [g // m for g, m in zip(gdims, mpi)]
+            want = sum(4 * (-(-(int(np.prod(ld)) // 2 // ld[mu] * Ls) // 16) * 16) * 6 * (8 if prec == gb.F32 else 16) for mu in range(4) if mpi[mu] > 1)
+            check(rank, f"{tag} prec{prec} halo_exchange bytes {D.halo_exchange(fin)} vs {want}", abs(D.halo_exchange(fin) - want), 0.5)
+            D.Dhop(fin, out, 0)
+            check(rank, f"{tag} prec{prec} Dhop after halo_exchange", site_err(out.export_lex(), decomp.scatter(ref[("dhop", 0)], gdims, mpi, rank, inner=Ls)), tol)
         so, sol = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF), gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()
         gb.pickCheckerboard(gb.Odd, so, fin)
         cg = gb.ConjugateGradient(1e-8, 5000)
