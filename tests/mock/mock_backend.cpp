@@ -1,11 +1,11 @@
 // mock_backend.cpp -- TEST-ONLY CPU backend behind the C ABI (tests/mock/README.md).
 //
-// Purpose: run product source files whose kernels' threads never communicate -- fermop.cu, dhop.cu (generic hopping kernel,
-// double store, leg mask), cayley.cu, stag.cu, solver.cu, schur.cu, force.cu, nersc.cu -- on a machine without a GPU, built for
-// the host through tests/mock/shim/ and tests/mock/transform.py, together with the Python mirror and the GPU tests themselves.
-// What is mocked is the rest: field containers, import / export, BLAS-1 and reductions (plain host loops over the same blocked
-// layout; the real ones use shared memory and warp shuffles), and stubs that switch the tuned kernels off (dhop_fast / dhop_col,
-// smat, peer-to-peer halos, NCCL), so every hop goes through the generic kernel.  No oracle in here: the tests compare with it.
+// Purpose: run the product's source files (tests/mock/build_mock.py lists them: operators, generic and tuned hopping kernels, dense
+// s-space kernel, peer-to-peer halos, staggered operator, solvers, Schur solve, force terms, NERSC I/O) on a machine without a GPU,
+// built for the host through tests/mock/shim/ and tests/mock/transform.py, together with the Python mirror and the GPU tests
+// themselves.  What is mocked HERE is the rest: the context, field containers, import / export, BLAS-1 and reductions (plain host
+// loops over the same blocked layout; the real ones, fields.cu, use shared memory and warp shuffles) and NCCL (mailboxes and
+// barriers between rank threads).  No oracle in here: the tests compare with it.
 // Nothing here ships: the product library has no CPU path (tests/test_abi.py::test_no_cpu_fallback_without_a_device).
 #include "fermop.hpp"
 #include <complex>

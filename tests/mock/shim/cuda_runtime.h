@@ -1,6 +1,6 @@
-// cuda_runtime.h -- TEST-ONLY stand-in for the CUDA runtime (tests/mock/README.md).  It lets a HOST compiler build a few of the
-// product's source files (solver.cu, schur.cu, force.cu, nersc.cu) so that their host orchestration and their thread-independent
-// kernels run on the CPU against a mock backend.  Never on an include path of the product build.
+// cuda_runtime.h -- TEST-ONLY stand-in for the CUDA runtime (tests/mock/README.md).  It lets a HOST compiler build the product's .cu
+// files (rewritten by tests/mock/transform.py) so that their host orchestration and their kernels run on the CPU against a mock
+// backend: thread-independent kernels as loops, cooperative ones on fibres (mock_simt.h).  Never on an include path of the product build.
 #pragma once
 #include <cmath>
 #include <cstddef>
