@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Random shapes / Ls / actions / precisions through the solver rows on the CPU mock (tests/mock/README.md), checked by identities that
 need no oracle: the full propagator solve (SchurRedBlackDiagMooeeSolve) must satisfy |M x - src| / |src| < 20 tol, and every pole of
-ConjugateGradientMultiShift must satisfy |(MpcDagMpc + pole) x - src| / |src| < 20 tol.  Not part of the test suite (open-ended).
-usage: fuzz_solvers.py <libgridb200_mock.so> <seed> <seconds>   (last recorded run: 4 seeds x 240 s = 346 cases, 0 violations)"""
+ConjugateGradientMultiShift must satisfy |(MpcDagMpc + pole) x - src| / |src| < 20 tol; every third case also runs the mixed-precision
+solvers (reliable-update CG, MixedPrecisionConjugateGradient, ConjugateGradientMultiShiftMixedPrec: fp64 vectors, fp32 inner operator)
+against the fp64 operator's residual < 2e-7.  Not part of the test suite (open-ended).
+usage: fuzz_solvers.py <libgridb200_mock.so> <seed> <seconds>   (last recorded runs: 346 cases without and 257 with the mixed-precision solvers, 0 violations)"""
 import os
 import random
 import sys
@@ -57,6 +59,34 @@ while time.time() < t_end:
         r = np.sqrt(gb.norm2(t) / gb.norm2(so))
         if not r < 20 * tol:
             bad.append((tag, f"multishift pole {pole} of {poles}", r))
+    # ---- mixed-precision solvers (fp64 vectors, fp32 inner operator) on the odd checkerboard, every third case
+    if ncase % 3 == 0 and kind != "wilson":
+        U64 = gb.LatticeGaugeField(grid, gb.F64).import_lex(syn.hot_gauge(dims, seed=ncase + 1))
+        U32 = gb.LatticeGaugeField(grid, gb.F32).import_lex(syn.hot_gauge(dims, seed=ncase + 1))
+        mk = (lambda Um: gb.DomainWallFermion(Um, grid, Ls, mass, 1.8)) if kind == "dwf" else (lambda Um: gb.MobiusFermion(Um, grid, Ls, mass, 1.8, 1.5, 0.5))
+        Ld, Lf = gb.SchurDiagMooeeOperator(mk(U64)), gb.SchurDiagMooeeOperator(mk(U32))
+        sd = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF)
+        gb.pickCheckerboard(gb.Odd, sd, gb.LatticeFermion(grid, Ls, gb.F64).import_lex(syn.random_fermion(dims, Ls, seed=300 + ncase)))
+        td = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF)
+
+        def resid(xk, pole=0.0):
+            Ld.HermOp(xk, td)
+            gb.axpy(td, pole, xk, td)
+            gb.axpy(td, -1.0, sd, td)
+            return np.sqrt(gb.norm2(td) / gb.norm2(sd))
+        xs = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()
+        gb.ConjugateGradientReliableUpdate(1e-8, 20000, random.choice([0.1, 0.5]), Lf, Ld, err_on_no_conv=False)(sd, xs)
+        if not resid(xs) < 2e-7:
+            bad.append((tag, "reliable-update CG", resid(xs)))
+        xs = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()
+        gb.MixedPrecisionConjugateGradient(1e-8, 20000, 50, Lf, Ld)(sd, xs)
+        if not resid(xs) < 2e-7:
+            bad.append((tag, "mixed-precision CG", resid(xs)))
+        resm = [gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF) for _ in poles]
+        gb.ConjugateGradientMultiShiftMixedPrec(20000, gb.MultiShiftFunction(poles, 1e-8), Lf, random.choice([10, 50]))(Ld, sd, resm)
+        for pole, xk in zip(poles, resm):
+            if not resid(xk, pole) < 2e-7:
+                bad.append((tag, f"mixed multishift pole {pole} of {poles}", resid(xk, pole)))
     ncase += 1
 print("cases", ncase, "bad", len(bad), bad[:8], flush=True)
 sys.exit(1 if bad else 0)
