@@ -4,7 +4,8 @@ need no oracle: the full propagator solve (SchurRedBlackDiagMooeeSolve) must sat
 ConjugateGradientMultiShift must satisfy |(MpcDagMpc + pole) x - src| / |src| < 20 tol; every third case also runs the mixed-precision
 solvers (reliable-update CG, MixedPrecisionConjugateGradient, ConjugateGradientMultiShiftMixedPrec: fp64 vectors, fp32 inner operator)
 against the fp64 operator's residual < 2e-7.  Not part of the test suite (open-ended).
-usage: fuzz_solvers.py <libgridb200_mock.so> <seed> <seconds>   (last recorded runs: 346 cases without and 257 with the mixed-precision solvers, 0 violations)"""
+usage: fuzz_solvers.py <libgridb200_mock.so> <seed> <seconds>   (last recorded runs: 346 cases without and 257 with the mixed-precision solvers, then 3 seeds x 100 s with the
+improved staggered solve; 0 violations)"""
 import os
 import random
 import sys
@@ -31,6 +32,25 @@ while time.time() < t_end:
     tol = 1e-5 if prec == gb.F32 else 1e-9
     mass = random.choice([0.05, 0.1, 0.3])
     grid = gb.GridCartesian(ctx, dims)
+    if random.random() < 0.2:
+        # improved staggered: SchurRedBlackStaggeredSolve, then |M x - src| / |src|
+        sd_ = tuple(max(d, 4) for d in dims)
+        g = gb.GridCartesian(ctx, sd_)
+        Us = gb.LatticeGaugeField(g, prec).import_lex(syn.hot_gauge(sd_, seed=ncase + 1))
+        Ds = gb.ImprovedStaggeredFermion(Us, Us, g, mass)
+        rng = np.random.default_rng(ncase)
+        V = int(np.prod(sd_))
+        fs = gb.LatticeStaggeredFermion(g, 1, prec).import_lex((rng.random((V, 3)) + 1j * rng.random((V, 3))).astype(gb._cdtype(prec)))
+        xs_, Ms = gb.LatticeStaggeredFermion(g, 1, prec).zero(), gb.LatticeStaggeredFermion(g, 1, prec)
+        gb.SchurRedBlackStaggeredSolve(gb.ConjugateGradient(tol, 20000, err_on_no_conv=False))(Ds, fs, xs_)
+        Ds.M(xs_, Ms)
+        gb.axpy(Ms, -1.0, fs, Ms)
+        r = np.sqrt(gb.norm2(Ms) / gb.norm2(fs))
+        # CG stops on the residual of the preconditioned (m^2 - Deo Doe) system; the unpreconditioned one is larger by ~ 1 / m
+        if not r < 3 * tol / mass:
+            bad.append((f"staggered dims {sd_} prec {prec} mass {mass}", "staggered schur solve", r))
+        ncase += 1
+        continue
     Umu = gb.LatticeGaugeField(grid, prec).import_lex(syn.hot_gauge(dims, seed=ncase + 1))
     D = gb.WilsonFermion(Umu, grid, mass + 0.3) if kind == "wilson" else gb.DomainWallFermion(Umu, grid, Ls, mass, 1.8) if kind == "dwf" else \
         gb.MobiusFermion(Umu, grid, Ls, mass, 1.8, 1.5, 0.5)
