@@ -604,19 +604,26 @@ class ConjugateGradient:
         if isinstance(Linop, SchurDiagMooeeOperator):
             rc = lib().gb_cg_schur(Linop._Mat.h, src.h, psi.h, self.Tolerance, self.MaxIterations, C.byref(it), C.byref(tr))
         else:  # any user-written LinearOperatorBase: CG drives its HermOp through the callback path
-            by_handle = {}
+            raised = []
 
             def cb(_user, hin, hout):
+                # ctypes swallows exceptions raised inside a callback (and returns 0 = GB_OK): stash ANY exception, stop the
+                # solver with an error code, and re-raise once gb_cg has returned
                 try:
                     fin, fout = _Borrowed(hin, src), _Borrowed(hout, src)
                     Linop.HermOp(fin, fout)
                     return GB_OK
                 except GridB200Error as e:
+                    raised.append(e)
                     return e.code
+                except BaseException as e:  # noqa: BLE001
+                    raised.append(e)
+                    return GB_ERR_INVALID
 
             fn = HERMOP_FN(cb)
             rc = lib().gb_cg(src.grid.ctx.h, fn, None, src.h, psi.h, self.Tolerance, self.MaxIterations, C.byref(it), C.byref(tr))
-            del by_handle
+            if raised:
+                raise raised[0]
         self.IterationsToComplete, self.TrueResidual = it.value, tr.value
         if rc == GB_ERR_NOT_CONVERGED:
             assert not self.ErrorOnNoConverge, "ConjugateGradient did NOT converge"  # ref: ConjugateGradient.h:254

@@ -288,6 +288,27 @@ template <class T> __global__ void gauge_face_kernel(const T *Ulex, T *face, int
 // =====================================================================================================
 // host side
 // =====================================================================================================
+// One halo message: my `send` buffer goes to rank `to`, `recv` is filled by rank `from`.  A neighbour that is this rank itself
+// (undecomposed dimension whose halos are forced on, GB_SELF_HALO) is a device-to-device copy, like the reference's
+// comms-to-self path (ref: Grid/communicator/Communicator_none.cc SendToRecvFrom).
+struct HaloMsg { const void *send; void *recv; size_t bytes; int to, from; };
+static void halo_sendrecv(gb_context *ctx, const std::vector<HaloMsg> &msgs, cudaStream_t st) {
+  bool remote = false;
+  for (const HaloMsg &m : msgs) {
+    if (m.to == ctx->rank && m.from == ctx->rank) GB_CUDA(cudaMemcpyAsync(m.recv, m.send, m.bytes, cudaMemcpyDeviceToDevice, st));
+    else remote = true;
+  }
+  if (!remote) return;
+  GB_REQUIRE(ctx->nccl != nullptr, "decomposed lattice: call gb_comm_init first");
+  NcclApi &N = nccl();
+  nccl_check(N.GroupStart(), "ncclGroupStart");
+  for (const HaloMsg &m : msgs) if (!(m.to == ctx->rank && m.from == ctx->rank)) {
+    nccl_check(N.Send(m.send, m.bytes, ncclChar, m.to, ctx->nccl, st), "ncclSend");
+    nccl_check(N.Recv(m.recv, m.bytes, ncclChar, m.from, ctx->nccl, st), "ncclRecv");
+  }
+  nccl_check(N.GroupEnd(), "ncclGroupEnd");
+}
+
 static int pick_block(int L, int want) {
   if (want <= 0 || want >= L) return L;
   int b = want;
@@ -331,14 +352,10 @@ void op_import_gauge(gb_fermop *op, const gb_gauge *Umu) {
       else gauge_face_kernel<double><<<blocks, 256, 0, ctx->stream>>>((const double *)Umu->data, (double *)sendf[mu], L4, mu, nface);
       count_launch(ctx);
     }
-    NcclApi &N = nccl();
-    nccl_check(N.GroupStart(), "ncclGroupStart");
-    for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
-      const size_t bytes = (size_t)(g->V4 / g->ldims[mu]) * 18 * esz;
-      nccl_check(N.Send(sendf[mu], bytes, ncclChar, g->nbr_rank[mu][0], ctx->nccl, ctx->stream), "ncclSend");
-      nccl_check(N.Recv(recvf[mu], bytes, ncclChar, g->nbr_rank[mu][1], ctx->nccl, ctx->stream), "ncclRecv");
-    }
-    nccl_check(N.GroupEnd(), "ncclGroupEnd");
+    std::vector<HaloMsg> msgs;
+    for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1)
+      msgs.push_back({sendf[mu], recvf[mu], (size_t)(g->V4 / g->ldims[mu]) * 18 * esz, g->nbr_rank[mu][0], g->nbr_rank[mu][1]});
+    halo_sendrecv(ctx, msgs, ctx->stream);
     for (int mu = 0; mu < 4; mu++) a.Uhalo[mu] = recvf[mu];
   }
   const uint32_t n = 2u * a.V4cb * 8;
@@ -399,18 +416,15 @@ template <class T, int DAG> static void launch_pack(gb_fermop *op, const void *i
 static void exchange_halos(gb_fermop *op, int nslots, cudaStream_t st) {
   const gb_grid *g = op->grid;
   gb_context *ctx = op->ctx;
-  NcclApi &N = nccl();
-  nccl_check(N.GroupStart(), "ncclGroupStart");
+  std::vector<HaloMsg> msgs;
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
     const size_t bytes = (size_t)nslots * op->halo_parity_stride[mu] * 16;
     // data for the receiver's forward leg (point mu) is my x=0 slice: it travels to my backward neighbour
-    nccl_check(N.Send(op->halo_send[mu], bytes, ncclChar, g->nbr_rank[mu][1], ctx->nccl, st), "ncclSend");
-    nccl_check(N.Recv(op->halo_recv[mu], bytes, ncclChar, g->nbr_rank[mu][0], ctx->nccl, st), "ncclRecv");
+    msgs.push_back({op->halo_send[mu], op->halo_recv[mu], bytes, g->nbr_rank[mu][1], g->nbr_rank[mu][0]});
     // data for the receiver's backward leg (point mu+4) is my x=L-1 slice: it travels forward
-    nccl_check(N.Send(op->halo_send[mu + 4], bytes, ncclChar, g->nbr_rank[mu][0], ctx->nccl, st), "ncclSend");
-    nccl_check(N.Recv(op->halo_recv[mu + 4], bytes, ncclChar, g->nbr_rank[mu][1], ctx->nccl, st), "ncclRecv");
+    msgs.push_back({op->halo_send[mu + 4], op->halo_recv[mu + 4], bytes, g->nbr_rank[mu][0], g->nbr_rank[mu][1]});
   }
-  nccl_check(N.GroupEnd(), "ncclGroupEnd");
+  halo_sendrecv(ctx, msgs, st);
 }
 
 template <class T> static void launch_dhop_T(gb_fermop *op, DhopArgs &a, int nparity, int dag, int mode, cudaStream_t st) {

@@ -25,7 +25,7 @@ template <int LS> static void launch_ls(const FastArgs &a, int nparity, int dag,
 }
 
 // ---- column-sweep kernel (dhop_col.cuh): single-rank hops and the interior pass of z/t-decomposed lattices
-template <int LS> static void launch_col_ls(const ColArgs &a, dim3 grid, int dag, int interior, cudaStream_t st) {
+template <int LS> static bool launch_col_ls(const ColArgs &a, dim3 grid, int dag, int interior, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = col_smem_bytes<LS>();
   if (!attr_set) {
@@ -47,11 +47,13 @@ template <int LS> static void launch_col_ls(const ColArgs &a, dim3 grid, int dag
         attr2 = true;
       }
       if (!dag) dhop_col_kernel<LS, 0, 0, 2><<<grid, 2 * threads, smem2, st>>>(a2); else dhop_col_kernel<LS, 1, 0, 2><<<grid, 2 * threads, smem2, st>>>(a2);
+      return true;
     }
-    return;
+    return false;   // the two-slice variant does not exist for this Ls: nothing was launched, the caller takes another kernel
   }
   if (!dag) { if (interior) dhop_col_kernel<LS, 0, 1><<<grid, threads, smem, st>>>(a); else dhop_col_kernel<LS, 0, 0><<<grid, threads, smem, st>>>(a); }
   else { if (interior) dhop_col_kernel<LS, 1, 1><<<grid, threads, smem, st>>>(a); else dhop_col_kernel<LS, 1, 0><<<grid, threads, smem, st>>>(a); }
+  return true;
 }
 static bool dhop_col_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                             const void *const ax[2], double axa, double axb, int interior, cudaStream_t st) {
@@ -87,11 +89,13 @@ static bool dhop_col_launch(gb_fermop *op, const void *const in[2], void *const 
   a.first_parity = parity_out_first;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
   dim3 grid((unsigned)((Lt / NT) * (Lxh / 4) * (Ly / 4) * (Lz / N)), nparity);
+  bool launched;
   switch (Ls) {
-  case 8: launch_col_ls<8>(a, grid, dag, interior, st); break;
-  case 12: launch_col_ls<12>(a, grid, dag, interior, st); break;
-  default: launch_col_ls<16>(a, grid, dag, interior, st); break;
+  case 8: launched = launch_col_ls<8>(a, grid, dag, interior, st); break;
+  case 12: launched = launch_col_ls<12>(a, grid, dag, interior, st); break;
+  default: launched = launch_col_ls<16>(a, grid, dag, interior, st); break;
   }
+  if (!launched) return false;
   count_launch(op->ctx);
   check_launch(op->ctx, "dhop_col");
   return true;

@@ -70,17 +70,21 @@ __device__ __forceinline__ void store_spinor(const SpinorReg<double> &f, double2
 #pragma unroll
   for (int k = 0; k < 12; k++) p[k << LOGW] = make_double2(f.re[k], f.im[k]);
 }
-__device__ __forceinline__ void load_half(HalfReg<float> &h, const float4 *__restrict__ p) {
+// Halo half-spinors are written by the neighbours' pack kernels WHILE this kernel may already be running (peer-to-peer path:
+// the epoch flag is acquired on the device), and the receive buffers are reused every second epoch -- so they are read with
+// plain coherent loads, never through the non-coherent (ld.global.nc / __ldg) path, which is only legal for data that is
+// read-only for the whole kernel lifetime and is not ordered by the flag acquire.
+__device__ __forceinline__ void load_half(HalfReg<float> &h, const float4 *p) {
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    float4 v = __ldg(p + (k << LOGW));
+    float4 v = p[k << LOGW];
     h.re[2 * k] = v.x; h.im[2 * k] = v.y; h.re[2 * k + 1] = v.z; h.im[2 * k + 1] = v.w;
   }
 }
-__device__ __forceinline__ void load_half(HalfReg<double> &h, const double2 *__restrict__ p) {
+__device__ __forceinline__ void load_half(HalfReg<double> &h, const double2 *p) {
 #pragma unroll
   for (int k = 0; k < 6; k++) {
-    double2 v = __ldg(p + (k << LOGW));
+    double2 v = p[k << LOGW];
     h.re[k] = v.x; h.im[k] = v.y;
   }
 }

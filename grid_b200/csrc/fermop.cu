@@ -256,7 +256,11 @@ static gb_fermop *make_op(gb_grid *g, const gb_gauge *Umu, int kind, int Ls, dou
   op->grid = g; op->ctx = g->ctx; op->kind = kind; op->prec = Umu->prec; op->Ls = Ls; op->mass = mass; op->M5 = M5;
   if (ph) std::memcpy(op->phases, ph, sizeof(double) * 8);
   if (kind == GB_KIND_CAYLEY) { GB_REQUIRE(Ls >= 2, "Cayley operators need Ls >= 2"); op->k = cayley_coeffs(Ls, mass, M5, b, c); }
-  for (int d = 0; d < 4; d++) if (g->mpi[d] > 1) op->comm_dim_mask |= 1 << d;
+  // GB_SELF_HALO=<bitmask of dimensions>, read at creation: also routes those UNdecomposed dimensions through the halo path
+  // (gauge faces, pack -> store into this rank's own receive buffers -> epoch flags -> interior / exterior or semi-fused hop), so
+  // that one GPU exercises the whole multi-rank machinery (tests/test_gpu_self_halo.py)
+  const int self_mask = getenv("GB_SELF_HALO") ? atoi(getenv("GB_SELF_HALO")) & 15 : 0;
+  for (int d = 0; d < 4; d++) if (g->mpi[d] > 1 || ((self_mask >> d) & 1)) op->comm_dim_mask |= 1 << d;
   // default rasterisation: whole y, 8 z-planes at a time, all t ("L2 blocking")
   op->By = 0; op->Bz = 8; op->Bt = 0;
   if (kind == GB_KIND_CAYLEY && (Ls == 8 || Ls == 12 || Ls == 16)) {

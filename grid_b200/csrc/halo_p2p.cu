@@ -94,10 +94,12 @@ bool p2p_setup(gb_fermop *op) {
   P2PState &S = op->p2p;
   if (S.tried) return S.ok;
   S.tried = true;
-  if (getenv("GB_NO_P2P")) return false;
   gb_context *ctx = op->ctx;
   const gb_grid *g = op->grid;
   const int hv = nv_of(op->prec) / 2;
+  // a local failure or an opt-out (GB_NO_P2P) is folded into `ok`: every rank still takes part in the AllGather and the vote
+  // below, so that a rank that cannot map its neighbours makes ALL ranks fall back to NCCL instead of hanging them
+  bool ok = getenv("GB_NO_P2P") == nullptr;
   size_t off = 0;
   for (int p = 0; p < 8; p++) { S.pt_off[p] = 0; S.peer_base[p] = nullptr; }
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
@@ -111,34 +113,42 @@ bool p2p_setup(gb_fermop *op) {
   S.epoch_stride = off;
   S.flags_off = 2 * off;
   S.recv_bytes = 2 * off + 2 * 8 * sizeof(unsigned long long);
-  GB_CUDA(cudaMalloc(&S.recv_base, S.recv_bytes));
-  GB_CUDA(cudaMemset(S.recv_base, 0, S.recv_bytes));
-  GB_CUDA(cudaMalloc(&S.d_counter, sizeof(unsigned int)));
-  GB_CUDA(cudaMemset(S.d_counter, 0, sizeof(unsigned int)));
-  GB_CUDA(cudaDeviceSynchronize());
-  // exchange handles
   cudaIpcMemHandle_t mine;
-  if (cudaIpcGetMemHandle(&mine, S.recv_base) != cudaSuccess) { cudaGetLastError(); return false; }
+  std::memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    GB_CUDA(cudaMalloc(&S.recv_base, S.recv_bytes));
+    GB_CUDA(cudaMemset(S.recv_base, 0, S.recv_bytes));
+    GB_CUDA(cudaMalloc(&S.d_counter, sizeof(unsigned int)));
+    GB_CUDA(cudaMemset(S.d_counter, 0, sizeof(unsigned int)));
+    GB_CUDA(cudaDeviceSynchronize());
+  }
+  // does any halo leave this rank?  (GB_SELF_HALO routes undecomposed dimensions through the same path: the "peer" is this rank)
+  bool any_remote = false;
+  for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1)
+    if (g->nbr_rank[mu][0] != ctx->rank || g->nbr_rank[mu][1] != ctx->rank) any_remote = true;
   const int n = ctx->nranks;
-  char *d_all = nullptr;
-  GB_CUDA(cudaMalloc(&d_all, (size_t)n * sizeof(mine)));
-  GB_CUDA(cudaMemcpy(d_all + (size_t)ctx->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
-  NcclApi &N = nccl();
-  GB_REQUIRE(N.AllGather != nullptr, "ncclAllGather missing");
-  nccl_check(N.AllGather(d_all + (size_t)ctx->rank * sizeof(mine), d_all, sizeof(mine), ncclChar, ctx->nccl, ctx->stream), "ncclAllGather");
   std::vector<cudaIpcMemHandle_t> all(n);
-  GB_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)n * sizeof(mine), cudaMemcpyDeviceToHost, ctx->stream));
-  GB_CUDA(cudaStreamSynchronize(ctx->stream));
-  GB_CUDA(cudaFree(d_all));
+  if (n > 1) {
+    // exchange handles (every rank of the communicator, whether or not its own halos are remote)
+    if (ok && any_remote && cudaIpcGetMemHandle(&mine, S.recv_base) != cudaSuccess) { cudaGetLastError(); ok = false; }
+    char *d_all = nullptr;
+    GB_CUDA(cudaMalloc(&d_all, (size_t)n * sizeof(mine)));
+    GB_CUDA(cudaMemcpy(d_all + (size_t)ctx->rank * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    NcclApi &N = nccl();
+    GB_REQUIRE(N.AllGather != nullptr, "ncclAllGather missing");
+    nccl_check(N.AllGather(d_all + (size_t)ctx->rank * sizeof(mine), d_all, sizeof(mine), ncclChar, ctx->nccl, ctx->stream), "ncclAllGather");
+    GB_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)n * sizeof(mine), cudaMemcpyDeviceToHost, ctx->stream));
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    GB_CUDA(cudaFree(d_all));
+  }
   // map each distinct neighbour once
   std::vector<void *> mapped(n, nullptr);
-  bool ok = true;
   for (int mu = 0; mu < 4 && ok; mu++) if ((op->comm_dim_mask >> mu) & 1) {
     // receiver of my data for ITS point mu (its forward leg) is my backward neighbour; for point mu+4 my forward neighbour
     const int dest[2] = {g->nbr_rank[mu][1], g->nbr_rank[mu][0]};
     for (int k = 0; k < 2; k++) {
       const int r = dest[k];
-      if (r == ctx->rank) { ok = false; break; }
+      if (r == ctx->rank) mapped[r] = S.recv_base;          // halo to self: plain device pointer
       if (!mapped[r]) {
         void *ptr = nullptr;
         if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
@@ -152,6 +162,7 @@ bool p2p_setup(gb_fermop *op) {
   double v = ok ? 0.0 : 1.0;
   global_sum(ctx, &v, 1);
   S.ok = (v == 0.0);
+  if (!S.ok) p2p_teardown(op);
   op->halo_ready = true;
   return S.ok;
 }

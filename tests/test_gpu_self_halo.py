@@ -1,0 +1,158 @@
+"""GPU check of the MULTI-RANK code path of the Wilson / domain-wall hopping term on ONE device.
+
+GB_SELF_HALO=<bitmask of dimensions>, read when an operator is created, makes the library treat the chosen undecomposed
+dimensions as decomposed: the gauge faces of the double store, `pack_send_kernel` (boundary slices projected with the receiving
+leg's projector; ref WilsonCompressor.h:461-511), the stores into the receive buffers (this rank's own: the "peer" of a periodic
+dimension of extent 1 in the processor grid is the rank itself, ref Communicator_none.cc), the epoch flags, and then
+  * the semi-fused launch `dhop_fast_kernel<LS,DAG,2>` (fp32, z / t splits): local legs, flag acquire, halo legs in one kernel,
+  * the interior pass + exterior slabs (`set_overlap(2)`; always for fp64 and x / y splits;
+    ref WilsonKernelsImplementation.h:167-285 DhopSiteInt / DhopSiteExt over the surface list),
+  * the serial-comms form (`set_overlap(0)`: one all-legs kernel reading the halo buffers; ref WilsonFermion5DImplementation.h:386-411).
+The neighbour is this rank, so the result must be the periodic one: every form is compared per site with the fp64 oracle on the
+same lattice (<= 1e-6 fp32, <= 1e-13 fp64) -- NOT with the library's own single-rank kernel.
+GB_NO_P2P=1 additionally routes the same hops through the NCCL-path code (pack_face_kernel + exchange -> device-to-device copies).
+"""
+import os
+
+import numpy as np
+import pytest
+
+import grid_b200 as gb
+from grid_b200 import synthetic as syn
+from oracle import pyoracle as po
+from test_gpu_parity import site_rel_err, TOL_HOP, TOL_COMPOSITE
+
+pytestmark = pytest.mark.gpu
+
+MASKS = {"z": 4, "t": 8, "zt": 12, "x": 1, "y": 2, "xyzt": 15}
+SHAPES = {
+    "dwf16": dict(dims=(8, 8, 8, 8), Ls=16, kind="dwf"),
+    "mobius8": dict(dims=(16, 4, 6, 4), Ls=8, kind="mobius", b=1.5, c=0.5),
+    "wilson": dict(dims=(8, 4, 4, 6), Ls=1, kind="wilson"),
+}
+
+
+def make(ctx, shape, prec, mask, no_p2p=False, phases=None, grid=None):
+    dims, Ls, kind = shape["dims"], shape["Ls"], shape["kind"]
+    grid = grid or gb.GridCartesian(ctx, dims)
+    U = syn.hot_gauge(dims, seed=11)
+    Umu = gb.LatticeGaugeField(grid, prec).import_lex(U)
+    os.environ["GB_SELF_HALO"] = str(mask)
+    if no_p2p:
+        os.environ["GB_NO_P2P"] = "1"
+    try:
+        if kind == "wilson":
+            D = gb.WilsonFermion(Umu, grid, 0.1, phases)
+        elif kind == "dwf":
+            D = gb.DomainWallFermion(Umu, grid, Ls, 0.1, 1.8, phases)
+        else:
+            D = gb.MobiusFermion(Umu, grid, Ls, 0.1, 1.8, shape["b"], shape["c"], phases)
+        # the peer-to-peer state is created by the first hop: run one while the environment still says what to do
+        f = gb.LatticeFermion(grid, Ls, prec).zero()
+        D.Dhop(f, gb.LatticeFermion(grid, Ls, prec), 0)
+    finally:
+        os.environ.pop("GB_SELF_HALO", None)
+        os.environ.pop("GB_NO_P2P", None)
+    orc = po.OracleOp(0 if kind == "wilson" else 1, dims, Ls, mass=0.1, M5=1.8, b=shape.get("b", 1.0), c=shape.get("c", 0.0), prec=prec)
+    orc.import_gauge(U, phases)
+    return grid, D, orc
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = gb.Context(0)
+    yield c
+    c.synchronize()
+
+
+def check_all_entries(grid, D, orc, shape, prec, tag):
+    dims, Ls = shape["dims"], shape["Ls"]
+    src = syn.random_fermion(dims, Ls, seed=12, dtype=gb._cdtype(prec))
+    src64 = src.astype(np.complex128)
+    fin, fout = gb.LatticeFermion(grid, Ls, prec).import_lex(src), gb.LatticeFermion(grid, Ls, prec)
+    he, ho = gb.LatticeFermion(grid, Ls, prec, gb.HALF), gb.LatticeFermion(grid, Ls, prec, gb.HALF)
+    r = gb.LatticeFermion(grid, Ls, prec, gb.HALF)
+    gb.pickCheckerboard(gb.Even, he, fin); gb.pickCheckerboard(gb.Odd, ho, fin)
+    for dag in (0, 1):
+        D.Dhop(fin, fout, dag)
+        assert site_rel_err(fout.export_lex(), orc.apply(po.OP_DHOP, src64, dag=dag)) < TOL_HOP[prec], (tag, "Dhop", dag)
+        D.DhopEO(ho, r, dag)
+        assert r.Checkerboard() == gb.Even
+        assert site_rel_err(r.export_lex(), orc.apply(po.OP_DHOP_EO, po.pick_checkerboard(dims, Ls, 1, src64), dag=dag)) < TOL_HOP[prec], (tag, "DhopEO", dag)
+        D.DhopOE(he, r, dag)
+        assert site_rel_err(r.export_lex(), orc.apply(po.OP_DHOP_OE, po.pick_checkerboard(dims, Ls, 0, src64), dag=dag)) < TOL_HOP[prec], (tag, "DhopOE", dag)
+    D.M(fin, fout)
+    assert site_rel_err(fout.export_lex(), orc.apply(po.OP_M, src64)) < TOL_COMPOSITE[prec], (tag, "M")
+
+
+@pytest.mark.parametrize("prec", [gb.F32, gb.F64], ids=["f32", "f64"])
+@pytest.mark.parametrize("mask", list(MASKS), ids=list(MASKS))
+@pytest.mark.parametrize("shape", list(SHAPES), ids=list(SHAPES))
+def test_self_halo_hops_match_the_oracle(ctx, shape, mask, prec):
+    sh = SHAPES[shape]
+    grid, D, orc = make(ctx, sh, prec, MASKS[mask])
+    # 1 = default overlapped form (semi-fused launch where it exists), 2 = interior + exterior slabs, 0 = serial comms
+    for overlap in (1, 2, 0):
+        D.set_overlap(overlap)
+        check_all_entries(grid, D, orc, sh, prec, (shape, mask, overlap))
+
+
+@pytest.mark.parametrize("prec", [gb.F32, gb.F64], ids=["f32", "f64"])
+def test_self_halo_nccl_path_code(ctx, prec):
+    """GB_NO_P2P: pack_face_kernel + exchange (device-to-device copies for a self neighbour) + interior / exterior or serial."""
+    sh = SHAPES["dwf16"]
+    grid, D, orc = make(ctx, sh, prec, MASKS["zt"], no_p2p=True)
+    for overlap in (1, 0):
+        D.set_overlap(overlap)
+        check_all_entries(grid, D, orc, sh, prec, ("nccl-path", overlap))
+
+
+def test_self_halo_antiperiodic_phases(ctx):
+    """boundary phases sit on the global boundary links, which with a self halo come through the gauge-face exchange"""
+    ph = [1, 1, 1, -1]
+    sh = SHAPES["dwf16"]
+    grid, D, orc = make(ctx, sh, gb.F32, MASKS["zt"], phases=ph)
+    check_all_entries(grid, D, orc, sh, gb.F32, "phases")
+
+
+def test_self_halo_semi_fused_launch_is_taken(ctx):
+    """fp32, t split, Ls 16: the default form is ONE hop launch after the pack kernel (2 launches per Dhop), the interior +
+    exterior form needs more (pack, interior, two slabs per parity pair)."""
+    sh = SHAPES["dwf16"]
+    grid, D, orc = make(ctx, sh, gb.F32, MASKS["t"])
+    fin, fout = gb.LatticeFermion(grid, 16, gb.F32).zero(), gb.LatticeFermion(grid, 16, gb.F32)
+    D.set_overlap(1)
+    n0 = ctx.launch_count(); D.Dhop(fin, fout, 0); n1 = ctx.launch_count()
+    D.set_overlap(2)
+    D.Dhop(fin, fout, 0); n2 = ctx.launch_count()
+    assert n1 - n0 == 2, n1 - n0
+    assert n2 - n1 > 2, n2 - n1
+
+
+def test_self_halo_cg_and_mixed_cg_match_the_oracle(ctx):
+    """Schur CG (fp64: interior + exterior hops) and mixed-precision CG (fp32 semi-fused hops inside) through the halo path:
+    same iteration count as the oracle's solver on the same fields (+-2 %), same true residual."""
+    sh = dict(dims=(4, 4, 8, 8), Ls=8, kind="mobius", b=1.5, c=0.5)
+    grid, Dd, orc_d = make(ctx, sh, gb.F64, MASKS["zt"])
+    _, Df, orc_f = make(ctx, sh, gb.F32, MASKS["zt"], grid=grid)
+    src = syn.random_fermion(sh["dims"], sh["Ls"], seed=21, dtype=np.complex128)
+    h = po.pick_checkerboard(sh["dims"], sh["Ls"], gb.Odd, src)
+    fsrc = gb.LatticeFermion(grid, sh["Ls"], gb.F64, gb.HALF).import_lex(h)
+    fsrc.set_checkerboard(gb.Odd)
+    sol = gb.LatticeFermion(grid, sh["Ls"], gb.F64, gb.HALF).zero()
+    cg = gb.ConjugateGradient(1e-8, 10000)
+    cg(gb.SchurDiagMooeeOperator(Dd), fsrc, sol)
+    x_ref, info = orc_d.cg(gb.Odd, h, 1e-8, 10000)
+    assert abs(cg.IterationsToComplete - info["iterations"]) <= max(1, 0.02 * info["iterations"])
+    assert abs(cg.TrueResidual - info["true_residual"]) < 0.05 * info["true_residual"] + 1e-12
+    x = sol.export_lex()
+    assert np.linalg.norm((x - x_ref).ravel()) / np.linalg.norm(x_ref.ravel()) < 1e-7
+    sol_m = gb.LatticeFermion(grid, sh["Ls"], gb.F64, gb.HALF).zero()
+    mcg = gb.MixedPrecisionConjugateGradient(1e-8, 10000, 50, gb.SchurDiagMooeeOperator(Df), gb.SchurDiagMooeeOperator(Dd))
+    mcg(fsrc, sol_m)
+    assert mcg.TrueResidual < 1e-7
+    xm = sol_m.export_lex()
+    assert np.linalg.norm((xm - x_ref).ravel()) / np.linalg.norm(x_ref.ravel()) < 1e-6
+    _, minfo = po.mixed_cg(orc_d, orc_f, gb.Odd, h, 1e-8, 10000, 50)
+    assert mcg.TotalOuterIterations == minfo["outer"]
+    assert abs(mcg.TotalInnerIterations - minfo["inner"]) <= max(3, 0.08 * minfo["inner"])   # see tests/test_gpu_parity.py on the 8 %

@@ -16,7 +16,6 @@ from oracle import pyoracle as po
 from oracle import pyref as pr
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-UNVERIFIED = pytest.mark.unverified("row f2 was written in round 1 after the GPU budget ran out")
 G = np.load(os.path.join(HERE, "golden", "dirac_golden.npz"))
 N = np.load(os.path.join(HERE, "golden", "next_golden.npz"))
 DIMS, LS = tuple(int(x) for x in G["dims"]), int(G["Ls"])
@@ -148,7 +147,6 @@ def _device_op(gb, grid, name, prec):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 @pytest.mark.parametrize("prec_name", ["f64", "f32"])
 @pytest.mark.parametrize("name", ["wilson", "mobius"])
 def test_cuda_dhop_dir_and_force_terms(name, prec_name):
@@ -185,7 +183,6 @@ def test_cuda_dhop_dir_and_force_terms(name, prec_name):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 @pytest.mark.parametrize("prec_name", ["f64", "f32"])
 @pytest.mark.parametrize("name", ["wilson", "mobius"])
 def test_cuda_even_odd_force_terms(name, prec_name):
@@ -219,7 +216,6 @@ def test_cuda_even_odd_force_terms(name, prec_name):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_cuda_mdir_all():
     """Mdir / MdirAll (the directional pieces multigrid coarsening reads, ref: CayleyFermion5DImplementation.h:331-344): out[p] is
     leg p of Dhop applied to Meo5D psi; the eight of them sum to Meooe-style Dhop(Meooe5D psi)."""
@@ -240,7 +236,6 @@ def test_cuda_mdir_all():
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_dwf_force_driver():
     """ref: tests/forces/Test_dwf_force.cc -- dS predicted from MDeriv against the measured change of |M phi|^2, through the C++ mirror"""
     import subprocess
@@ -282,7 +277,6 @@ def test_oracle_two_flavour_even_odd_pseudofermion_force(name):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_cuda_two_flavour_even_odd_pseudofermion_force():
     """The same action and force through the CUDA path (ConjugateGradient on SchurDifferentiableOperator + MpcDeriv / MpcDagDeriv),
     against the oracle's force for the same field."""

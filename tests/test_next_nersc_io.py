@@ -130,7 +130,6 @@ def test_interoperates_with_the_reference_both_ways(tmp_path, two_row):
 
 
 @pytest.mark.gpu
-@pytest.mark.unverified("row f4's device wrappers were written in round 1 after the GPU budget ran out")
 def test_device_gauge_field_read_write(tmp_path):
     ctx = gb.Context(0)
     grid = gb.GridCartesian(ctx, DIMS)

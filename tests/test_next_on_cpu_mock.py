@@ -13,7 +13,7 @@ store / load of the peer-to-peer halos by host atomics.  A backend supplies the 
 reductions as plain loops over the same blocked layout, and NCCL as mailboxes between threads.  No oracle inside: the tests compare
 its results with the oracle, the golden fixtures and the compiled reference, exactly as they do on a GPU.
 
- * every `unverified` GPU test of the SURVEY 8(f) rows, of the N-rank staggered path and of the tuned kernels' edge shapes passes on
+ * every GPU test of the SURVEY 8(f) rows, of the N-rank staggered path and of the tuned kernels' edge shapes passes on
    it (56 tests);
  * so do the measured suite's golden-vector and parity GPU tests -- now THROUGH the tuned kernels (the launch counters prove it), in
    both shapes: column-sweep kernel by default, micro-block kernel with GB_NO_COL=1, persistent s-space kernel looping over tiles;
@@ -47,7 +47,7 @@ def mock_lib(tmp_path_factory):
 # after the other they take four minutes): name -> (pytest arguments | script, counters to report, extra environment)
 PARITY = ["tests/test_gpu_parity.py", "-k", "not dhop_host and not device_random"]
 JOBS = {
-    "unverified": (NEXT + ["-k", "not driver"], None, {}),
+    "next_rows": (NEXT + ["-k", "not driver"], None, {}),
     "golden": (["tests/test_golden.py"], None, {}),
     "parity": (PARITY, ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {}),
     "micro_block": (["tests/test_gpu_parity.py", "-k", "fast_and_generic or tiling or schur_operator or cg_matches"],
@@ -63,7 +63,7 @@ class Children:
         self.procs = {}
         for name, (what, count, extra) in JOBS.items():
             # the children run side by side: keep the oracle's and numpy's thread pools small or they fight for the cores
-            env = dict(os.environ, GB_UNVERIFIED_CHILD="1", GB_TEST_MOCK_LIB=mock_lib, GB_MOCK_COUNT=";".join(count or []), OMP_NUM_THREADS="2",
+            env = dict(os.environ, GB_TEST_MOCK_LIB=mock_lib, GB_MOCK_COUNT=";".join(count or []), OMP_NUM_THREADS="2",
                        OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", **extra)
             if isinstance(what, str):
                 cmd = [sys.executable, os.path.join(ROOT, "tests", "mock", what), mock_lib]
@@ -101,9 +101,9 @@ def children(mock_lib):
             p.kill()
 
 
-def test_unverified_gpu_tests_pass_on_the_cpu_mock(children):
+def test_next_row_gpu_tests_pass_on_the_cpu_mock(children):
     # the C++ drivers are linked against the real library; everything else of these files runs
-    assert children.passed_and_counts("unverified")[0] >= 56
+    assert children.passed_and_counts("next_rows")[0] >= 56
 
 
 def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(children):

@@ -15,7 +15,6 @@ from oracle import pyoracle as po
 from oracle import pyref as pr
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-UNVERIFIED = pytest.mark.unverified("row f3 was written in round 1 after the GPU budget ran out")
 G = np.load(os.path.join(HERE, "golden", "dirac_golden.npz"))
 N = np.load(os.path.join(HERE, "golden", "next_golden.npz"))
 DIMS, LS = tuple(int(x) for x in G["dims"]), int(G["Ls"])
@@ -67,7 +66,6 @@ def test_oracle_vs_reference_relup_cg(delta):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_cuda_relup_cg_matches_reference():
     import grid_b200 as gb
     ctx = gb.Context(0)
@@ -85,7 +83,6 @@ def test_cuda_relup_cg_matches_reference():
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_cuda_mixed_cg_batched():
     """MixedPrecisionConjugateGradientBatched (ref: ConjugateGradientMixedPrecBatched.h:36-213): two right-hand sides, one inner
     tolerance schedule; each solution satisfies HermOp x = b like the single-RHS MixedPrecisionConjugateGradient's."""

@@ -18,7 +18,6 @@ from oracle import pyoracle as po
 from oracle import pyref as pr
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-UNVERIFIED = pytest.mark.unverified("row f1 was written in round 1 after the GPU budget ran out")
 G = np.load(os.path.join(HERE, "golden", "dirac_golden.npz"))
 N = np.load(os.path.join(HERE, "golden", "next_golden.npz"))
 DIMS, LS = tuple(int(x) for x in G["dims"]), int(G["Ls"])
@@ -164,7 +163,6 @@ def _field(gb, grid, name, prec, kind=None, Ls=None):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 @pytest.mark.parametrize("prec_name", ["f64", "f32"])
 def test_cuda_dminus_and_physical_maps(prec_name):
     import grid_b200 as gb
@@ -198,7 +196,6 @@ def test_cuda_dminus_and_physical_maps(prec_name):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 @pytest.mark.parametrize("name", ["mobius", "stag"])
 def test_cuda_redblack_source_and_solution(name):
     import grid_b200 as gb
@@ -220,7 +217,6 @@ def test_cuda_redblack_source_and_solution(name):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 @pytest.mark.parametrize("name", ["wilson", "dwf", "mobius", "stag"])
 def test_cuda_schur_solve_matches_reference(name):
     import grid_b200 as gb
@@ -251,7 +247,6 @@ def test_cuda_schur_solve_matches_reference(name):
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_cuda_schur_solve_mixed_precision():
     import grid_b200 as gb
     ctx = gb.Context(0)
@@ -265,7 +260,6 @@ def test_cuda_schur_solve_mixed_precision():
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_cuda_propagator_column_4d_to_4d():
     """One column of a propagator the way physics callers drive it: 4D source -> ImportPhysicalFermionSource -> Schur solve ->
     ExportPhysicalFermionSolution, against the oracle doing the same chain."""
@@ -284,7 +278,6 @@ def test_cuda_propagator_column_4d_to_4d():
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_dwf_cg_schur_driver():
     """ref: tests/solver/Test_dwf_cg_schur.cc -- SchurRedBlackDiagMooeeSolve(CG)(Ddwf, src, result), unpreconditioned residual,
     and one 4D -> 5D -> 4D propagator column, through the C++ mirror (include/gridb200.hpp)"""
@@ -297,7 +290,6 @@ def test_dwf_cg_schur_driver():
 
 
 @pytest.mark.gpu
-@UNVERIFIED
 def test_cuda_unpreconditioned_cg_on_mdagm():
     """MdagMLinearOperator (ref: LinearOperator.h:74-105) through ConjugateGradient's generic path: Mdag M x = b on the full grid,
     checked with the oracle's M / Mdag on the host, and against the Schur solve of M y = b (x = M^-1 Mdag^-1 b => M x' = ... )."""

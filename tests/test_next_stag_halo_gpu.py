@@ -16,7 +16,7 @@ import pytest
 from grid_b200 import synthetic as syn
 from oracle import pyoracle as po
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unverified("three-deep staggered halos were written in round 1 after the GPU budget ran out")]
+pytestmark = [pytest.mark.gpu]
 DIMS = (8, 6, 4, 8)
 
 

