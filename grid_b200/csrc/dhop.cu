@@ -531,6 +531,8 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
     // local legs, and surface CTAs acquire the neighbours' flags and add the off-node legs
     const bool try_fused = op->overlap_comms && !op->no_fused && op->prec == GB_F32 && !op->disable_fast;
     unsigned long long epoch = 0;
+    static const bool pack_on_comm_stream = getenv("GB_PACK_STREAM") && atoi(getenv("GB_PACK_STREAM")) != 0;
+    bool pack_pending = false;
     if (try_fused) {
       epoch = p2p_next_epoch(op);
       p2p_fill_halo(op, epoch, a.halo, &a.flags);
@@ -543,9 +545,21 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       }
       if (dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 2, ctx->stream, hb, a.flags, epoch)) return;
       p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, ctx->stream); // configuration not covered: separate pack kernel
+    } else if (pack_on_comm_stream && op->overlap_comms) {
+      // pack + send on the high-priority comm stream: it only reads the hop's input, so the hop need not wait for it; the
+      // compute stream waits for its completion at the END of this call (the input may be overwritten by the next kernel)
+      GB_CUDA(cudaEventRecord(ctx->ev_comp, ctx->stream));
+      GB_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_comp, 0));
+      epoch = p2p_pack_send(op, in, parity_out_first, nparity, dag, ctx->comm_stream);
+      GB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
+      pack_pending = true;
     } else {
       epoch = p2p_pack_send(op, in, parity_out_first, nparity, dag, ctx->stream);
     }
+    struct PackJoin {   // runs on every exit path below
+      gb_context *ctx; bool on;
+      ~PackJoin() { if (on) cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0); }
+    } pack_join{ctx, pack_pending};
     if (prof) GB_CUDA(cudaEventRecord(qe[1], ctx->stream));
     struct ProfEnd {
       gb_context *ctx; bool on; cudaEvent_t *qe; double *qacc; int *qn;
@@ -563,12 +577,24 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       const int ip = 1 - parity_out_first;
       for (int i = 0; i < 8; i++) if (a.halo[i]) a.halo[i] = (const char *)a.halo[i] - (size_t)ip * op->halo_parity_stride[i & 3] * 16;
     }
-    // semi-fused: after the pack+send kernel ONE hop launch does the local legs and, in its last (surface) CTAs, acquires
-    // the neighbours' flags and adds the halo legs -- no exterior pass, nothing read-modify-written (GB_SEMIFUSED=0 disables)
+    // semi-fused: after the pack+send kernel the hop does the local legs and, in its last (surface) CTAs, acquires the
+    // neighbours' flags and adds the halo legs -- no exterior pass, nothing read-modify-written (GB_SEMIFUSED=0 disables).
+    // Default engine: the column-sweep kernel (dhop_col2.cuh) over the planes whose z legs are local, t-surface columns last,
+    // plus the micro-block semi-fused kernel on the two z-surface planes when z is split (GB_COL2_DECOMP=0: micro-block
+    // kernel over the whole volume, the round-1 form).
     static const bool semifused = !(getenv("GB_SEMIFUSED") && atoi(getenv("GB_SEMIFUSED")) == 0);
-    if (op->overlap_comms && semifused && !op->no_semifused && op->prec == GB_F32 && !op->disable_fast && !(op->comm_dim_mask & 3) &&
-        dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 4, ctx->stream, a.halo, a.flags, epoch))
-      return;
+    static const bool col2_decomp = !(getenv("GB_COL2_DECOMP") && atoi(getenv("GB_COL2_DECOMP")) == 0);
+    if (op->overlap_comms && semifused && !op->no_semifused && op->prec == GB_F32 && !op->disable_fast && !(op->comm_dim_mask & 3)) {
+      if (col2_decomp && dhop_col2_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream, a.halo, a.flags, epoch)) {
+        if ((op->comm_dim_mask >> 2) & 1) {
+          const bool z0 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 5, ctx->stream, a.halo, a.flags, epoch);
+          const bool z1 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 6, ctx->stream, a.halo, a.flags, epoch);
+          GB_REQUIRE(z0 && z1, "z-surface planes of the column-sweep hop");
+        }
+        return;
+      }
+      if (dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 4, ctx->stream, a.halo, a.flags, epoch)) return;
+    }
     if (op->overlap_comms) hop_overlapped(ctx->stream, [] {});
     else run(0, ctx->stream);
     return;

@@ -1,0 +1,246 @@
+// dhop_col2.cuh -- column-sweep fp32 hopping kernel, second generation (round 2): the kernel bench.py times.
+//
+// Same sweep as dhop_col.cuh (a CTA owns a 4x4 (x/2, y) micro-block and walks z; the other-parity "central column" lives in
+// a three-plane ring in shared memory and serves 6 of the 8 legs), with what the round-1 ncu capture asked for:
+//   * the ring planes are filled by TMA bulk copies (cp.async.bulk -> UBLKCP), not by 6 per-thread LDGSTS per step: the ring
+//     uses the field's own blocked layout ([block of 16 i5][6 vecs][16 lanes]), in which one x-row of the micro-block (4 sites x
+//     Ls) is ONE contiguous run of 4*Ls*96 bytes in global memory, so a plane is 4 bulk copies issued by 4 threads.  That takes
+//     24-48 of the ~320 L1/LSU wavefronts per warp-step (the pipe that was 67 % busy) and 7 instructions per thread-step away;
+//   * full / free mbarrier pairs instead of "everybody's cp.async arrival": one "plane landed" barrier per ring slot (three
+//     slots, so a waiter can never miss a phase) and one "z- leg done" barrier that tells the issuing threads that the oldest
+//     slot and the oldest link buffer may be overwritten;
+//   * decomposed lattices (z and / or t split over ranks) run THIS kernel too: columns sweep only the planes whose z legs are
+//     local, CTAs on the t surface are rasterised last, acquire the neighbours' epoch flags and take their off-node t leg from
+//     the receive buffer (projected half spinors, written by the neighbour's pack kernel over NVLink) -- a CTA-uniform branch.
+//     The two z-surface planes are left to the micro-block semi-fused kernel (dhop_fast.cuh, box launch).
+// Arithmetic per leg is dhop_fast.cuh's (packed f32x2 projection / SU(3) multiply / reconstruction).
+// ref (what it computes): WilsonKernelsImplementation.h:57-68,112-163 (site), :167-285 (interior / exterior legs).
+#pragma once
+#include "dhop_col.cuh"
+
+namespace gb {
+
+struct Col2Args {
+  const float4 *in[2];
+  float4 *out[2];
+  const float4 *U[2];
+  const float4 *axpy[2];
+  float axpy_a, axpy_b;
+  int Lxh, Ly, Lz, Lt;
+  int z0, N, nzc;               // column c of a (x,y,t) block sweeps planes z0 + c*N ... z0 + c*N + N-1 (mod Lz)
+  // 1-D grid = [interior-t CTAs of parity slot 0][... slot 1][surface-t CTAs slot 0][... slot 1]; inside a segment t runs
+  // fastest (t neighbours side by side in L2), then the x blocks, then the y blocks (raster 1: y blocks before x blocks), then z chunks
+  uint32_t n_int, n_surf;
+  int t_int0, nt_int, nt_surf, raster;
+  FastDiv dnt_int, dnt_surf, dNxo, dNyo;
+  int nparity, first_parity, origin_parity;
+  // off-node t legs (MODE 1): receive buffers of the backward (point 7) and forward (point 3) t leg, epoch flags
+  int t_comm;
+  const float4 *halo_tm, *halo_tp;
+  size_t hstride;               // float4 between the parity-0 and parity-1 faces
+  const unsigned long long *flags;
+  unsigned long long epoch;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// float4 offset, inside one ring plane (or one parity block of a field), of vec 0 of vector site i
+__device__ __forceinline__ int blk_off(int i) { return (((i >> LOGW) * 6) << LOGW) + (i & (W - 1)); }
+
+// one leg whose source spinor is vec k at p[k * 16] (ring plane or global field: same blocked layout)
+template <int DAG, int MU, int FWD>
+__device__ __forceinline__ void col2_leg(const float4 *p, const float4 *Usm, SpinorP &res) {
+  constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
+  SpinorP f; HalfP chi, Uchi; LinkS u;
+#pragma unroll
+  for (int k = 0; k < 6; k++) { const float4 v = p[k << LOGW]; f.c[2 * k] = pk(v.x, v.y); f.c[2 * k + 1] = pk(v.z, v.w); }
+  proj_p<MU, SIGN>(chi, f);
+  lds_link(u, Usm + (FWD ? MU : MU + 4) * 5);
+  mult_p(Uchi, u, chi);
+  recon_p<MU, SIGN>(res, Uchi);
+}
+// t leg from registers: a full spinor (local neighbour), or the already projected half spinor of an off-node neighbour in c[0..5]
+template <int DAG, int MU, int FWD>
+__device__ __forceinline__ void col2_leg_reg(const SpinorP &f, bool is_half, const float4 *Usm, SpinorP &res) {
+  constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
+  HalfP chi, Uchi; LinkS u;
+  if (is_half) {
+#pragma unroll
+    for (int q = 0; q < 6; q++) chi.c[q] = f.c[q];
+  } else proj_p<MU, SIGN>(chi, f);
+  lds_link(u, Usm + (FWD ? MU : MU + 4) * 5);
+  mult_p(Uchi, u, chi);
+  recon_p<MU, SIGN>(res, Uchi);
+}
+
+template <int LS> constexpr size_t col2_smem_bytes() { return (size_t)(3 * COL_NSITE * 6 * LS + 3 * COL_NSITE * FAST_USTRIDE) * 16 + 64; }
+
+// MODE 0: single rank (every leg local, periodic wrap inside the local volume).  MODE 1: decomposed in z and / or t (see above).
+template <int LS, int DAG, int MODE>
+__global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2Args a) {
+  extern __shared__ __align__(128) unsigned char col_smem[];
+  constexpr int PLANE = COL_NSITE * 6 * LS;                  // float4 per ring plane, field layout [block][vec k][lane]
+  constexpr int UBUF = COL_NSITE * FAST_USTRIDE;
+  constexpr int NTHR = COL_NSITE * LS;
+  constexpr uint32_t ROW_BYTES = 4u * LS * 6 * 16;           // one x-row of the micro-block: contiguous in the field
+  float4 *ring = reinterpret_cast<float4 *>(col_smem);
+  float4 *Usm = ring + 3 * PLANE;                            // 3 x [16 sites][41]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(Usm + 3 * UBUF);   // [0..2] links, [3..5] ring slot landed, [6] z- leg done
+  const int sl = threadIdx.x / LS, s = threadIdx.x % LS;
+  const int xl = sl & 3, yl = sl >> 2;
+  // ---- which column
+  uint32_t b = blockIdx.x;
+  int slot = 0;
+  bool surf = false;
+  {
+    const uint32_t tot_int = a.n_int * (uint32_t)a.nparity;
+    if (b >= tot_int) { surf = true; b -= tot_int; if (b >= a.n_surf) { b -= a.n_surf; slot = 1; } }
+    else if (b >= a.n_int) { b -= a.n_int; slot = 1; }
+  }
+  const int p = a.first_parity ^ slot;
+  uint32_t t, xo, yo, zc;
+  if (!surf) { a.dnt_int.divmod(b, b, t); t += a.t_int0; }
+  else { a.dnt_surf.divmod(b, b, t); t = t == 0 ? a.Lt - 1 : 0; }        // surface segment: t = Lt-1, then t = 0
+  if (a.raster == 0) { a.dNxo.divmod(b, b, xo); a.dNyo.divmod(b, zc, yo); }
+  else { a.dNyo.divmod(b, b, yo); a.dNxo.divmod(b, zc, xo); }
+  const int xh = xo * 4 + xl, y = yo * 4 + yl, zfirst = a.z0 + zc * a.N;
+  const float4 *__restrict__ in = a.in[1 - p];
+  const uint32_t zstride = (uint32_t)a.Lxh * a.Ly, tstride = zstride * a.Lz;
+  const uint32_t site_xyt = xh + a.Lxh * y + tstride * t;
+  auto gptr = [&](uint32_t site) { const uint32_t i = site * LS + s; return in + ((size_t)(i >> LOGW) * 6 << LOGW) + (i & (W - 1)); };
+  const int i0 = sl * LS + s;
+  float4 *const mine = ring + blk_off(i0);                     // this thread's element in ring slot 0
+  // in-block neighbours: slot +-1 along x, +-4 along y (float4 offsets from the own element; compile-time constants for Ls = 16,
+  // where a 16-lane block is exactly one 4D site)
+  auto noff = [&](int dslot) { return LS == W ? dslot * 6 * W : blk_off(i0 + dslot * LS) - blk_off(i0); };
+  const int off_x1 = xl < 3 ? noff(1) : 0, off_xm1 = xl > 0 ? noff(-1) : 0;
+  const int off_y1 = yl < 3 ? noff(4) : 0, off_ym1 = yl > 0 ? noff(-4) : 0;
+
+  const bool issuer = s == 0;                                  // 16 threads: each stages the links of its site; 4 of them a ring row
+  const bool row_issuer = issuer && xl == 0;
+  // source / destination of this thread's ring row (row yl of the block)
+  const uint32_t row_site = site_xyt - xl;                      // x-row start (xl == 0 for row issuers)
+  auto row_src = [&](int z) { return in + ((size_t)(((row_site + zstride * (uint32_t)z) * LS) >> LOGW) * 6 << LOGW); };
+  float4 *const row_dst = ring + blk_off(4 * yl * LS);
+  auto wrapz = [&](int z) { return z >= a.Lz ? z - a.Lz : (z < 0 ? z + a.Lz : z); };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init(&bars[3], 1); mbar_init(&bars[4], 1); mbar_init(&bars[5], 1);
+    mbar_init(&bars[6], NTHR);
+  }
+  const bool tm_halo = MODE == 1 && a.t_comm && t == 0, tp_halo = MODE == 1 && a.t_comm && (int)t == a.Lt - 1;
+  if (MODE == 1 && surf) {
+    // acquire the t neighbours' epoch flags (peer-written, system scope) before any thread touches the receive buffers
+    if (threadIdx.x == 3 || threadIdx.x == 7) {
+      unsigned long long v;
+      do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flags + threadIdx.x) : "memory"); } while (v < a.epoch);
+    }
+  }
+  __syncthreads();
+  // ---- prologue: planes zfirst-1 (slot 0) and zfirst (slot 1), links of step 0
+  const int zfirst_w = wrapz(zfirst);
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[3], 4 * ROW_BYTES); mbar_expect_tx(&bars[4], 4 * ROW_BYTES);
+    mbar_expect_tx(&bars[0], COL_NSITE * 640);
+  }
+  if (row_issuer) {
+    bulk_g2s(row_dst, row_src(wrapz(zfirst - 1)), ROW_BYTES, &bars[3]);
+    bulk_g2s(row_dst + PLANE, row_src(zfirst_w), ROW_BYTES, &bars[4]);
+  }
+  if (issuer) bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zfirst_w) * 40, 640, &bars[0]);
+
+  const uint32_t site_tm = site_xyt + (t == 0 ? tstride * (a.Lt - 1) : 0u - tstride);
+  const uint32_t site_tp = site_xyt + ((int)t == a.Lt - 1 ? 0u - tstride * (a.Lt - 1) : tstride);
+  // global fall-backs of the in-plane legs that leave the 4x4 block (periodic wrap inside the local volume)
+  const uint32_t site_xm = site_xyt - xh + (xh == 0 ? a.Lxh - 1 : xh - 1), site_xp = site_xyt - xh + (xh + 1 == a.Lxh ? 0 : xh + 1);
+  const uint32_t site_ym = site_xyt + (y == 0 ? a.Lxh * (a.Ly - 1) : 0u - a.Lxh), site_yp = site_xyt + (y + 1 == a.Ly ? 0u - a.Lxh * (a.Ly - 1) : a.Lxh);
+  // off-node t legs: face index = cb index with t removed; the neighbour stored half spinors in the same 16-lane blocking
+  const int ip = 1 - p;
+  const float4 *hb_tm = nullptr, *hb_tp = nullptr;
+  if (MODE == 1) {
+    if (tm_halo) hb_tm = a.halo_tm + (size_t)ip * a.hstride;
+    if (tp_halo) hb_tp = a.halo_tp + (size_t)ip * a.hstride;
+  }
+  const uint32_t face_xy = xh + a.Lxh * y;
+  auto hptr = [&](const float4 *base, int z) { const uint32_t i = (face_xy + zstride * (uint32_t)z) * LS + s; return base + ((size_t)(i >> LOGW) * 3 << LOGW) + (i & (W - 1)); };
+
+  mbar_wait(&bars[3], 0);
+  mbar_wait(&bars[4], 0);
+  int ub = 0, bm = 0;                                          // link buffer of this step; ring slot of plane z-1
+#pragma unroll 1
+  for (int k = 0; k < a.N; k++) {
+    const int z = wrapz(zfirst + k);
+    const int b0 = bm == 2 ? 0 : bm + 1, bp = b0 == 2 ? 0 : b0 + 1;   // ring slots of planes z, z+1
+    const int un = ub == 2 ? 0 : ub + 1;
+    const uint32_t zoff = zstride * z;
+    const int zp = z + 1 == a.Lz ? 0 : z + 1;
+    // ---- asynchronous: plane z+1 into ring slot bp, the links of the next step.  Slot bp held plane z-2 (read as the z- leg of
+    //      step k-1) and link buffer un the links of step k-2: both free once every thread has arrived on bars[6] in step k-1.
+    if (issuer) {
+      if (k > 0) mbar_wait(&bars[6], (uint32_t)(k - 1) & 1);
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&bars[3 + bp], 4 * ROW_BYTES);
+        if (k + 1 < a.N) mbar_expect_tx(&bars[un], COL_NSITE * 640);
+      }
+      if (row_issuer) bulk_g2s(row_dst + bp * PLANE, row_src(zp), ROW_BYTES, &bars[3 + bp]);
+      if (k + 1 < a.N) bulk_g2s(Usm + un * UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zp) * 40, 640, &bars[un]);
+    }
+    // ---- t neighbours into registers now, used after the shared-memory legs
+    SpinorP ftm, ftp;
+    if (MODE == 1 && tm_halo) {
+      const float4 *h = hptr(hb_tm, z);
+#pragma unroll
+      for (int q = 0; q < 3; q++) { const float4 v = h[q << LOGW]; ftm.c[2 * q] = pk(v.x, v.y); ftm.c[2 * q + 1] = pk(v.z, v.w); }
+    } else load_spinor_p(ftm, gptr(site_tm + zoff));
+    if (MODE == 1 && tp_halo) {
+      const float4 *h = hptr(hb_tp, z);
+#pragma unroll
+      for (int q = 0; q < 3; q++) { const float4 v = h[q << LOGW]; ftp.c[2 * q] = pk(v.x, v.y); ftp.c[2 * q + 1] = pk(v.z, v.w); }
+    } else load_spinor_p(ftp, gptr(site_tp + zoff));
+    const int pb = (p + a.origin_parity + y + z + (int)t) & 1;
+    SpinorP res;
+#pragma unroll
+    for (int q = 0; q < 12; q++) res.c[q] = pk(0.f, 0.f);
+    mbar_wait(&bars[ub], (uint32_t)(k / 3) & 1);
+    const float4 *Us = Usm + ub * UBUF + sl * FAST_USTRIDE;
+    const float4 *cur = mine + b0 * PLANE;                       // own element, plane z
+    // ---- z- : own element of plane z-1; then tell the issuers that this thread is done with that slot
+    col2_leg<DAG, 2, 0>(mine + bm * PLANE, Us, res);
+    mbar_arrive(&bars[6]);
+    // ---- x legs: the neighbour with the same x/2 index is this thread's own ring element; the other one is the adjacent
+    //      slot or, at the block edge, a global load
+    if (pb) {
+      col2_leg<DAG, 0, 0>(cur, Us, res);
+      col2_leg<DAG, 0, 1>(xl < 3 ? cur + off_x1 : gptr(site_xp + zoff), Us, res);
+    } else {
+      col2_leg<DAG, 0, 0>(xl > 0 ? cur + off_xm1 : gptr(site_xm + zoff), Us, res);
+      col2_leg<DAG, 0, 1>(cur, Us, res);
+    }
+    // ---- y legs: slots +-4 inside the block
+    col2_leg<DAG, 1, 0>(yl > 0 ? cur + off_ym1 : gptr(site_ym + zoff), Us, res);
+    col2_leg<DAG, 1, 1>(yl < 3 ? cur + off_y1 : gptr(site_yp + zoff), Us, res);
+    // ---- t legs from registers
+    col2_leg_reg<DAG, 3, 0>(ftm, MODE == 1 && tm_halo, Us, res);
+    col2_leg_reg<DAG, 3, 1>(ftp, MODE == 1 && tp_halo, Us, res);
+    // ---- z+ : wait for plane z+1 (bulk copies issued at the top of this step), read the own element
+    mbar_wait(&bars[3 + bp], (uint32_t)((k + 2) / 3) & 1);
+    col2_leg<DAG, 2, 1>(mine + bp * PLANE, Us, res);
+    // ---- epilogue
+    const uint32_t i = (site_xyt + zoff) * LS + s;
+    const size_t offs = ((size_t)(i >> LOGW) * 6 << LOGW) + (i & (W - 1));
+    if (a.axpy[p] != nullptr) {
+      SpinorP ax;
+      load_spinor_p(ax, a.axpy[p] + offs);
+      const f2 sa = pk(a.axpy_a, a.axpy_a), sb = pk(a.axpy_b, a.axpy_b);
+#pragma unroll
+      for (int q = 0; q < 12; q++) res.c[q] = fma2(sa, res.c[q], mul2(sb, ax.c[q]));
+    }
+    store_spinor_p(res, a.out[p] + offs);
+    bm = b0; ub = un;
+  }
+}
+
+} // namespace gb

@@ -1,6 +1,7 @@
 // dhop_fast.cu -- instantiations + launcher of the tuned fp32 hopping kernel (see dhop_fast.cuh)
 #include "dhop_fast.cuh"
 #include "dhop_col.cuh"
+#include "dhop_col2.cuh"
 #include <cstdlib>
 #include "fermop.hpp"
 #include <algorithm>
@@ -101,13 +102,88 @@ static bool dhop_col_launch(gb_fermop *op, const void *const in[2], void *const 
   return true;
 }
 
+// ---- second-generation column-sweep kernel (dhop_col2.cuh): TMA-filled ring; single rank (mode 0) and z/t-decomposed lattices
+//      (mode 1: local z legs only -> planes [1, Lz-2] when z is split; off-node t legs from the receive buffers in the surface-t
+//      CTAs, which come last in the grid).  The caller computes the z-surface planes with the micro-block kernel (interior 5 / 6).
+template <int LS> static void launch_col2_ls(const Col2Args &a, unsigned nblocks, int dag, int mode, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = col2_smem_bytes<LS>();
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int threads = COL_NSITE * LS;
+  if (!dag) { if (mode) dhop_col2_kernel<LS, 0, 1><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<LS, 0, 0><<<nblocks, threads, smem, st>>>(a); }
+  else { if (mode) dhop_col2_kernel<LS, 1, 1><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<LS, 1, 0><<<nblocks, threads, smem, st>>>(a); }
+}
+bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
+                      const void *const ax[2], double axa, double axb, int mode, cudaStream_t st, const void *const halo[8],
+                      const unsigned long long *flags, unsigned long long epoch) {
+  static const bool disabled = getenv("GB_NO_COL") != nullptr || (getenv("GB_COL2") && atoi(getenv("GB_COL2")) == 0);
+  static const int env_n = getenv("GB_COL_N") ? atoi(getenv("GB_COL_N")) : 0;
+  static const int env_raster = getenv("GB_COL_RASTER") ? atoi(getenv("GB_COL_RASTER")) : 0;
+  const gb_grid *g = op->grid;
+  const int Ls = op->Ls;
+  if (disabled || op->no_col || op->prec != GB_F32 || op->disable_fast || !(Ls == 8 || Ls == 12 || Ls == 16)) return false;
+  const int Lxh = g->ldims[0] / 2, Ly = g->ldims[1], Lz = g->ldims[2], Lt = g->ldims[3];
+  if (Lxh % 4 || Ly % 4) return false;
+  if (mode == 0 && op->comm_dim_mask) return false;
+  if (mode == 1 && ((op->comm_dim_mask & 3) || halo == nullptr || flags == nullptr)) return false;
+  const bool z_comm = mode == 1 && ((op->comm_dim_mask >> 2) & 1), t_comm = mode == 1 && ((op->comm_dim_mask >> 3) & 1);
+  Col2Args a;
+  const size_t per_parity = (size_t)g->V4cb * 8 * 5;
+  for (int p = 0; p < 2; p++) {
+    a.in[p] = (const float4 *)in[p]; a.out[p] = (float4 *)out[p];
+    a.U[p] = (const float4 *)op->Uds + p * per_parity;
+    a.axpy[p] = ax ? (const float4 *)ax[p] : nullptr;
+  }
+  a.axpy_a = (float)axa; a.axpy_b = (float)axb;
+  a.Lxh = Lxh; a.Ly = Ly; a.Lz = Lz; a.Lt = Lt;
+  if (z_comm) {                       // planes 0 and Lz-1 have an off-node z leg: the caller's box launches take them
+    a.z0 = 1; a.N = Lz - 2; a.nzc = 1;
+    if (a.N <= 0) return true;        // nothing but surface planes
+  } else {
+    int N = env_n > 0 ? env_n : (op->col_n > 0 ? op->col_n : Lz);   // default: the whole z extent (no re-read of chunk-edge planes)
+    if (N > Lz) N = Lz;
+    while (Lz % N) N--;
+    a.z0 = 0; a.N = N; a.nzc = Lz / N;
+  }
+  const uint32_t cols_per_t = (uint32_t)(Lxh / 4) * (Ly / 4) * a.nzc;
+  a.t_comm = t_comm ? 1 : 0;
+  a.nt_surf = t_comm ? 2 : 0;
+  a.nt_int = t_comm ? Lt - 2 : Lt; a.t_int0 = t_comm ? 1 : 0;
+  a.n_int = (uint32_t)a.nt_int * cols_per_t; a.n_surf = (uint32_t)a.nt_surf * cols_per_t;
+  a.dnt_int = FastDiv(std::max(1, a.nt_int)); a.dnt_surf = FastDiv(std::max(1, a.nt_surf));
+  a.dNxo = FastDiv(Lxh / 4); a.dNyo = FastDiv(Ly / 4);
+  a.raster = env_raster;
+  a.nparity = nparity; a.first_parity = parity_out_first;
+  a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
+  a.halo_tm = halo ? (const float4 *)halo[7] : nullptr; a.halo_tp = halo ? (const float4 *)halo[3] : nullptr;
+  a.hstride = op->halo_parity_stride[3];
+  a.flags = flags; a.epoch = epoch;
+  const unsigned nblocks = (unsigned)((a.n_int + a.n_surf) * (uint32_t)nparity);
+  if (nblocks == 0) return true;
+  switch (Ls) {
+  case 8: launch_col2_ls<8>(a, nblocks, dag, mode, st); break;
+  case 12: launch_col2_ls<12>(a, nblocks, dag, mode, st); break;
+  default: launch_col2_ls<16>(a, nblocks, dag, mode, st); break;
+  }
+  count_launch(op->ctx);
+  check_launch(op->ctx, "dhop_col2");
+  return true;
+}
+
 // returns false when the configuration is not covered by the fast path (caller falls back to dhop_kernel)
 bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                       const void *const ax[2], double axa, double axb, int interior, cudaStream_t st, const void *const halo[8],
                       const unsigned long long *flags, unsigned long long epoch) {
   const gb_grid *g = op->grid;
   if (op->prec != GB_F32 || op->disable_fast) return false;
-  if (interior != 3 && dhop_col_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, interior, st)) return true;
+  if (interior == 0 && dhop_col2_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 0, st, nullptr, nullptr, 0)) return true;
+  if (interior < 3 && dhop_col_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, interior, st)) return true;
   const int Ls = op->Ls;
   if (!(Ls == 8 || Ls == 12 || Ls == 16 || Ls == 24 || Ls == 32)) return false;
   if (g->V4cb % FAST_NSITE || ((size_t)(g->ldims[0] / 2) * g->ldims[1]) % FAST_NSITE) return false;
@@ -125,7 +201,9 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   //                acquires the neighbours' epoch flags and adds the off-node legs from the receive buffers; the faces were
   //                projected and sent by the separate pack_send kernel that precedes it in the stream.  Unlike interior == 2
   //                (pack CTAs inside the same launch) no CTA ever waits for work of its own launch, so it cannot deadlock.
-  const bool no_pack = interior == 4;
+  // interior == 5 / 6: the semi-fused launch restricted to the plane z = 0 / z = Lz-1 (the z surface of a column-sweep hop)
+  const int zplane = interior == 5 ? 0 : interior == 6 ? g->ldims[2] - 1 : -1;
+  const bool no_pack = interior == 4 || zplane >= 0;
   if (no_pack) interior = 2;
   const bool inner_box = interior == 3;
   if (inner_box) {
@@ -142,6 +220,7 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
     if ((op->comm_dim_mask >> 3) & 1) { a.to = 1; nt = a.Lt - 2; }
     if (nz <= 0 || nt <= 0) return true;                   // no interior sites at all
   }
+  if (zplane >= 0) { a.zo = zplane; nz = 1; }
   int bz = op->Bz <= 0 ? nz : op->Bz;
   if (bz > nz) bz = nz;
   if (nz % bz) { int best = 1; for (int d = 2; d <= 12 && d <= nz; d++) if (nz % d == 0) best = d; bz = best == 1 ? nz : best; }
@@ -154,7 +233,7 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   for (int i = 0; i < 8; i++) a.halo[i] = halo ? (const float4 *)halo[i] : nullptr;
   for (int i = 0; i < 4; i++) a.hstride[i] = op->halo_parity_stride[i];
   a.flags = flags; a.epoch = epoch;
-  a.rot_z = (op->comm_dim_mask >> 2) & 1; a.rot_t = (op->comm_dim_mask >> 3) & 1;
+  a.rot_z = (zplane < 0) && ((op->comm_dim_mask >> 2) & 1); a.rot_t = (op->comm_dim_mask >> 3) & 1;
   if (interior == 2 && (halo == nullptr || flags == nullptr)) return false;
   a.npack_items = 0; a.npack_ctas = 0; a.pack_ratio = 4; a.pack_counter = nullptr;
   a.nhop_ctas_per_parity = (a.V4cb + FAST_NSITE - 1) / FAST_NSITE;

@@ -74,6 +74,10 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
                       const void *const ax[2], double axa, double axb, int interior, cudaStream_t st, const void *const halo[8] = nullptr,
                       const unsigned long long *flags = nullptr, unsigned long long epoch = 0);
 
+bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
+                      const void *const ax[2], double axa, double axb, int mode, cudaStream_t st, const void *const halo[8],
+                      const unsigned long long *flags, unsigned long long epoch);
+
 bool p2p_setup(gb_fermop *op);
 void p2p_teardown(gb_fermop *op);
 unsigned long long p2p_next_epoch(gb_fermop *op);

@@ -58,8 +58,10 @@ __device__ __forceinline__ void pack_body(const PackSendArgs &a, const PackItem 
 
 template <class T, int DAG> __global__ void __launch_bounds__(256) pack_send_kernel(const PackSendArgs a) {
   const PackItem &it = a.item[blockIdx.y];
-  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < it.nface * (uint32_t)a.Ls) {
+  // grid-stride: the launch may cover a face with fewer CTAs than it has 256-thread tiles (persistent form, GB_PACK_CTAS), so
+  // that the pack kernel occupies a few SMs for the duration of the transfer instead of sweeping over all of them
+  const uint32_t nq = it.nface * (uint32_t)a.Ls;
+  for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < nq; q += gridDim.x * blockDim.x) {
     switch (it.mu * 2 + it.fwd) {
     case 0: pack_body<T, DAG, 0, 0>(a, it, q); break;
     case 1: pack_body<T, DAG, 0, 1>(a, it, q); break;
@@ -212,7 +214,11 @@ void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in
       }
     }
   }
-  dim3 grid((maxn + 255) / 256, a.nitems);
+  // GB_PACK_CTAS=<n>: at most n CTAs per face item (grid-stride loop inside), 0 = one CTA per 256 face elements
+  static const unsigned pack_ctas = getenv("GB_PACK_CTAS") ? (unsigned)atoi(getenv("GB_PACK_CTAS")) : 0u;
+  unsigned gx = (maxn + 255) / 256;
+  if (pack_ctas > 0 && gx > pack_ctas) gx = pack_ctas;
+  dim3 grid(gx, a.nitems);
   if (op->prec == GB_F32) { if (dag) pack_send_kernel<float, 1><<<grid, 256, 0, st>>>(a); else pack_send_kernel<float, 0><<<grid, 256, 0, st>>>(a); }
   else { if (dag) pack_send_kernel<double, 1><<<grid, 256, 0, st>>>(a); else pack_send_kernel<double, 0><<<grid, 256, 0, st>>>(a); }
   count_launch(ctx);

@@ -351,10 +351,13 @@ extern "C" {
 // Grid_init with a synthetic command line; threads <= 0 keeps the OpenMP default
 int gref_init(int threads) {
   if (g_inited) return 0;
-  static std::string a0 = "gridref", a1 = "--threads", a2, a3 = "--grid", a4 = "8.8.8.8";
+  // --device-mem: the reference's software cache for lattice fields defaults to 128 MB and asserts on a larger field
+  // (MemoryManagerCache.cc:236); 64 GB lets it hold the 32^4 x 16 and 64.64.32.16 x 16 fields of BASELINE configs[1] and [3]
+  static std::string a0 = "gridref", a1 = "--threads", a2, a3 = "--grid", a4 = "8.8.8.8", a5 = "--device-mem", a6 = "65536";
   a2 = std::to_string(threads > 0 ? threads : omp_get_max_threads());
-  static char *args[] = {(char *)a0.c_str(), (char *)a1.c_str(), (char *)a2.c_str(), (char *)a3.c_str(), (char *)a4.c_str(), nullptr};
-  int argc = 5;
+  static char *args[] = {(char *)a0.c_str(), (char *)a1.c_str(), (char *)a2.c_str(), (char *)a3.c_str(), (char *)a4.c_str(),
+                         (char *)a5.c_str(), (char *)a6.c_str(), nullptr};
+  int argc = 7;
   char **argv = args;
   Grid_init(&argc, &argv);
   g_inited = true;
