@@ -18,6 +18,14 @@ cpu_baseline = the reference's own CPU code (oracle/_ref/libgridref.so: unmodifi
              oracle/Makefile.ref, AVX2 + OpenMP) timed on the host cores on a bounded sample; kind "reference".
              Falls back to the oracle port (kind "port") only where that library was not built.
 --impl reference runs only that CPU leg (rank 0 only) and prints the same JSON line with "impl": "reference".
+Beside the headline the same line carries (each measured in this run, each skippable with --no-...):
+cg         = BASELINE configs[2]: even-odd Schur Moebius mixed-precision CG to 1e-8 at the headline volume, timed AFTER a warm-up
+             solve, with ms per fp32 iteration (from a fixed 50-iteration fp32 CG) and its fraction of the 1872-B/site yardstick.
+e2e_cg     = the call HMC makes: gauge field + source from pinned host memory in, solution back to the host, copies timed.
+config4    = BASELINE configs[3]: Dhop (+ halo-exchange bandwidth + mixed CG) at the local volume 64.64.32.16 x Ls16 per GPU
+             (global 64^4 on 8 GPUs as 1.1.2.4): the weak-scaling series whose 8-vs-1 ratio the north star asks for.
+config5    = BASELINE configs[4]: improved staggered Dhop fp32 at 48^4 (global; split 1.1.2.4 on 8 GPUs).
+At N > 1 the decomposed hop is first compared per site with the CPU oracle on a small global lattice (parity_check).
 """
 import argparse
 import json
@@ -129,22 +137,47 @@ class _StdoutToStderr:
         os.close(self.saved)
 
 
-def cpu_leg(Ls, sample_L=16, target_s=12.0, op="Dhop"):
-    """Times the reference's CPU hopping term (fp32) on the host cores on a bounded sample: same operator and per-site work
-    as the GPU workload, smaller volume.  kind "reference" = the unmodified reference compiled by oracle/Makefile.ref
-    (DomainWallFermionF::Dhop, AVX2 SIMD, OpenMP, comms none; the faster of its generic and hand-unrolled kernels);
-    kind "port" = the oracle restatement, used only where oracle/_ref/libgridref.so is absent."""
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def use_all_host_cores(affinity=None):
+    """torchrun exports OMP_NUM_THREADS=1 to its children and bench.py pins ranks to their GPU's NUMA node: the CPU legs undo
+    both (they run on rank 0 alone while the other ranks wait)."""
+    if affinity:
+        try:
+            os.sched_setaffinity(0, affinity)
+        except Exception:
+            pass
+    n = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ["GRIDREF_THREADS"] = str(n)
+    return n
+
+
+def cpu_leg(Ls, local, target_s=12.0, op="Dhop", fields=None):
+    """Times the reference's CPU hopping term (fp32) on the host cores on a bounded sample of the SAME workload: the local volume
+    of one rank, same operator, `ncall` calls (~target_s seconds).  kind "reference" = the unmodified reference compiled by
+    oracle/Makefile.ref (DomainWallFermionF::Dhop, AVX2 SIMD, OpenMP on all host cores, comms none; the faster of its generic and
+    hand-unrolled kernels); kind "port" = the oracle restatement, used only where oracle/_ref/libgridref.so is absent.
+    fields = (U, x) host arrays exported from the device (same synthetic fields as the GPU run); drawn on the host if None."""
     import numpy as np
     from grid_b200 import synthetic as syn
     from oracle import pyoracle as po
     from oracle import pyref as pr
-    key = (Ls, sample_L, op)
+    dims = tuple(local)
+    key = (Ls, dims, op)
     use_ref = pr.available()
     if key not in _CPU_SETUP:
-        dims = (sample_L,) * 4
-        U = syn.hot_gauge(dims, seed=1, dtype=np.complex64)
-        x = syn.random_fermion(dims, Ls, seed=2, dtype=np.complex64, normalise=True)
-        which, vol = po.OP_DHOP, sample_L ** 4 * Ls
+        if fields is None:
+            U = syn.hot_gauge(dims, seed=1, dtype=np.complex64)
+            x = syn.random_fermion(dims, Ls, seed=2, dtype=np.complex64, normalise=True)
+        else:
+            U, x = fields
+        which, vol = po.OP_DHOP, int(np.prod(dims)) * Ls
         if op == "DhopEO":
             x, which, vol = po.pick_checkerboard(dims, Ls, 1, x), po.OP_DHOP_EO, vol // 2
         if use_ref:
@@ -154,6 +187,7 @@ def cpu_leg(Ls, sample_L=16, target_s=12.0, op="Dhop"):
                 t_opt = {}
                 for opt in (pr.OPT_GENERIC, pr.OPT_HAND_UNROLL):
                     pr.set_kernel_opt(opt)
+                    orc.time_apply(which, x, 1)
                     t_opt[opt] = orc.time_apply(which, x, 2) / 2
                 best = min(t_opt, key=t_opt.get)
                 pr.set_kernel_opt(best)
@@ -164,6 +198,7 @@ def cpu_leg(Ls, sample_L=16, target_s=12.0, op="Dhop"):
             _CPU_SETUP[key] = (orc, x, which, vol, orc.time_apply(which, x, 1), "oracle")
     orc, x, which, vol, t1, variant = _CPU_SETUP[key]
     ncall = max(2, int(target_s / max(t1, 1e-3)))
+    shape = "x".join(map(str, dims))
     if use_ref:
         with _StdoutToStderr():
             t = orc.time_apply(which, x, ncall)
@@ -174,18 +209,19 @@ def cpu_leg(Ls, sample_L=16, target_s=12.0, op="Dhop"):
         cores, kind = po.num_threads(), "port"
         what = f"the oracle {op} fp32 (port of the reference's generic kernel)"
     return {"value": FLOPS_PER_SITE * vol * ncall / t / 1e9, "unit": UNIT, "cores": cores, "kind": kind,
-            "sample": f"{ncall} calls of {what} on a {sample_L}^4 x Ls{Ls} sub-volume (same per-site work as the 32^4 workload), {t:.1f} s",
+            "sample": f"{ncall} calls of {what} on {shape} x Ls{Ls} (the local volume of one GPU of the workload), {t:.1f} s",
             "seconds": t, "calls": ncall, "ms_per_call": 1e3 * t / ncall}
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
+    use_all_host_cores()
     steps = max(1, args.steps)
-    per_step_target = min(20.0, 150.0 / (steps + args.warmup))
+    per_step_target = min(20.0, 120.0 / (steps + args.warmup))
     if os.environ.get("GB_BENCH_REF_SECONDS"):      # tests/test_bench_reference_arm.py shortens the sample; the driver never sets it
         per_step_target = float(os.environ["GB_BENCH_REF_SECONDS"])
-    legs = [cpu_leg(args.Ls, target_s=per_step_target, op=args.op) for _ in range(args.warmup + steps)][args.warmup:]
+    legs = [cpu_leg(args.Ls, args.local, target_s=per_step_target, op=args.op) for _ in range(args.warmup + steps)][args.warmup:]
     value = statistics.mean(l["value"] for l in legs)
     ms = statistics.mean(l["seconds"] for l in legs) * 1e3
     cb = dict(legs[-1]); cb["value"] = value
@@ -193,7 +229,8 @@ def run_reference(args, rank):
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args), "cpu_baseline": cb,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "the reference's own CPU implementation on the host cores (see cpu_baseline.kind / sample); each step is a bounded sample"}
+            "note": "the reference's own CPU implementation on the host cores, one process, all cores (see cpu_baseline.kind / sample); each step is a "
+                    "bounded sample: calls at the per-GPU local volume of the workload (the CPU rate does not depend on the global extent)"}
     print(json.dumps(line), flush=True)
 
 

@@ -34,6 +34,7 @@ struct Col2Args {
   int t_int0, nt_int, nt_surf, raster;
   FastDiv dnt_int, dnt_surf, dNxo, dNyo;
   int nparity, first_parity, origin_parity;
+  int cta_sync;                 // debugging switch (GB_COL2_SYNC=1): a CTA-wide barrier per step instead of the "z- leg done" mbarrier
   // off-node t legs (MODE 1): receive buffers of the backward (point 7) and forward (point 3) t leg, epoch flags
   int t_comm;
   const float4 *halo_tm, *halo_tp;
@@ -179,8 +180,12 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     const int zp = z + 1 == a.Lz ? 0 : z + 1;
     // ---- asynchronous: plane z+1 into ring slot bp, the links of the next step.  Slot bp held plane z-2 (read as the z- leg of
     //      step k-1) and link buffer un the links of step k-2: both free once every thread has arrived on bars[6] in step k-1.
+    // Every thread observes the completion of every phase of bars[6] (an arrive-on of the next phase by a thread that has not
+    // seen the previous one complete is undefined), which also bounds the run-ahead of any warp to one step, as the
+    // everybody-arrives barrier of the round-1 kernel did.
+    if (a.cta_sync) __syncthreads();
+    else if (k > 0) mbar_wait(&bars[6], (uint32_t)(k - 1) & 1);
     if (issuer) {
-      if (k > 0) mbar_wait(&bars[6], (uint32_t)(k - 1) & 1);
       if (threadIdx.x == 0) {
         mbar_expect_tx(&bars[3 + bp], 4 * ROW_BYTES);
         if (k + 1 < a.N) mbar_expect_tx(&bars[un], COL_NSITE * 640);
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     const float4 *cur = mine + b0 * PLANE;                       // own element, plane z
     // ---- z- : own element of plane z-1; then tell the issuers that this thread is done with that slot
     col2_leg<DAG, 2, 0>(mine + bm * PLANE, Us, res);
-    mbar_arrive(&bars[6]);
+    if (!a.cta_sync) mbar_arrive(&bars[6]);
     // ---- x legs: the neighbour with the same x/2 index is this thread's own ring element; the other one is the adjacent
     //      slot or, at the block edge, a global load
     if (pb) {

@@ -159,6 +159,8 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.dnt_int = FastDiv(std::max(1, a.nt_int)); a.dnt_surf = FastDiv(std::max(1, a.nt_surf));
   a.dNxo = FastDiv(Lxh / 4); a.dNyo = FastDiv(Ly / 4);
   a.raster = env_raster;
+  static const int env_sync = getenv("GB_COL2_SYNC") ? atoi(getenv("GB_COL2_SYNC")) : 0;
+  a.cta_sync = env_sync;
   a.nparity = nparity; a.first_parity = parity_out_first;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
   a.halo_tm = halo ? (const float4 *)halo[7] : nullptr; a.halo_tp = halo ? (const float4 *)halo[3] : nullptr;
