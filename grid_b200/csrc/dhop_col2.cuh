@@ -79,7 +79,7 @@ __device__ __forceinline__ void col2_leg_reg(const SpinorP &f, bool is_half, con
 template <int LS> constexpr size_t col2_smem_bytes() { return (size_t)(3 * COL_NSITE * 6 * LS + 3 * COL_NSITE * FAST_USTRIDE) * 16 + 64; }
 
 // MODE 0: single rank (every leg local, periodic wrap inside the local volume).  MODE 1: decomposed in z and / or t (see above).
-template <int LS, int DAG, int MODE>
+template <int LS, int DAG, int MODE, int DEEP = 1>
 __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2Args a) {
   extern __shared__ __align__(128) unsigned char col_smem[];
   constexpr int PLANE = COL_NSITE * 6 * LS;                  // float4 per ring plane, field layout [block][vec k][lane]
@@ -141,17 +141,22 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     }
   }
   __syncthreads();
-  // ---- prologue: planes zfirst-1 (slot 0) and zfirst (slot 1), links of step 0
+  // ---- prologue: planes zfirst-1 (slot 0), zfirst (slot 1) [DEEP: and zfirst+1 (slot 2)], links of step 0 [DEEP: and step 1]
   const int zfirst_w = wrapz(zfirst);
   if (threadIdx.x == 0) {
     mbar_expect_tx(&bars[3], 4 * ROW_BYTES); mbar_expect_tx(&bars[4], 4 * ROW_BYTES);
     mbar_expect_tx(&bars[0], COL_NSITE * 640);
+    if (DEEP) { mbar_expect_tx(&bars[5], 4 * ROW_BYTES); if (a.N > 1) mbar_expect_tx(&bars[1], COL_NSITE * 640); }
   }
   if (row_issuer) {
     bulk_g2s(row_dst, row_src(wrapz(zfirst - 1)), ROW_BYTES, &bars[3]);
     bulk_g2s(row_dst + PLANE, row_src(zfirst_w), ROW_BYTES, &bars[4]);
+    if (DEEP) bulk_g2s(row_dst + 2 * PLANE, row_src(wrapz(zfirst + 1)), ROW_BYTES, &bars[5]);
   }
-  if (issuer) bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zfirst_w) * 40, 640, &bars[0]);
+  if (issuer) {
+    bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zfirst_w) * 40, 640, &bars[0]);
+    if (DEEP && a.N > 1) bulk_g2s(Usm + UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * wrapz(zfirst + 1)) * 40, 640, &bars[1]);
+  }
 
   const uint32_t site_tm = site_xyt + (t == 0 ? tstride * (a.Lt - 1) : 0u - tstride);
   const uint32_t site_tp = site_xyt + ((int)t == a.Lt - 1 ? 0u - tstride * (a.Lt - 1) : tstride);
@@ -170,6 +175,7 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
 
   mbar_wait(&bars[3], 0);
   mbar_wait(&bars[4], 0);
+  if (DEEP) mbar_wait(&bars[5], 0);
   int ub = 0, bm = 0;                                          // link buffer of this step; ring slot of plane z-1
 #pragma unroll 1
   for (int k = 0; k < a.N; k++) {
@@ -178,14 +184,14 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     const int un = ub == 2 ? 0 : ub + 1;
     const uint32_t zoff = zstride * z;
     const int zp = z + 1 == a.Lz ? 0 : z + 1;
-    // ---- asynchronous: plane z+1 into ring slot bp, the links of the next step.  Slot bp held plane z-2 (read as the z- leg of
-    //      step k-1) and link buffer un the links of step k-2: both free once every thread has arrived on bars[6] in step k-1.
     // Every thread observes the completion of every phase of bars[6] (an arrive-on of the next phase by a thread that has not
-    // seen the previous one complete is undefined), which also bounds the run-ahead of any warp to one step, as the
-    // everybody-arrives barrier of the round-1 kernel did.
+    // seen the previous one complete is undefined -- it faulted on the B200), which also bounds the run-ahead of any warp to
+    // one step, as the everybody-arrives barrier of the round-1 kernel did.
     if (a.cta_sync) __syncthreads();
     else if (k > 0) mbar_wait(&bars[6], (uint32_t)(k - 1) & 1);
-    if (issuer) {
+    if (!DEEP && issuer) {
+      // ---- asynchronous (shallow form): plane z+1 into ring slot bp, the links of the next step.  Slot bp held plane z-2 (read
+      //      as the z- leg of step k-1) and link buffer un the links of step k-2: free once everybody arrived in step k-1.
       if (threadIdx.x == 0) {
         mbar_expect_tx(&bars[3 + bp], 4 * ROW_BYTES);
         if (k + 1 < a.N) mbar_expect_tx(&bars[un], COL_NSITE * 640);
@@ -227,10 +233,28 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     // ---- y legs: slots +-4 inside the block
     col2_leg<DAG, 1, 0>(yl > 0 ? cur + off_ym1 : gptr(site_ym + zoff), Us, res);
     col2_leg<DAG, 1, 1>(yl < 3 ? cur + off_y1 : gptr(site_yp + zoff), Us, res);
+    if (DEEP) {
+      // ---- asynchronous (deep form): by now every thread has normally done its z- leg of THIS step (phase k of bars[6]), so ring
+      //      slot bm (plane z-1) and the link buffer of step k-1 are free: fetch plane z+2 and the links of step k+2 into them,
+      //      one and a half steps before they are needed instead of just under one
+      if (issuer) {
+        if (a.cta_sync) asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");
+        else mbar_wait(&bars[6], (uint32_t)k & 1);
+        const int u2 = un == 2 ? 0 : un + 1;                       // link buffer of step k+2 (= the one step k-1 used)
+        if (threadIdx.x == 0) {
+          if (k + 1 < a.N) mbar_expect_tx(&bars[3 + bm], 4 * ROW_BYTES);
+          if (k + 2 < a.N) mbar_expect_tx(&bars[u2], COL_NSITE * 640);
+        }
+        const int zpp = zp + 1 == a.Lz ? 0 : zp + 1;
+        if (row_issuer && k + 1 < a.N) bulk_g2s(row_dst + bm * PLANE, row_src(zpp), ROW_BYTES, &bars[3 + bm]);
+        if (k + 2 < a.N) bulk_g2s(Usm + u2 * UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zpp) * 40, 640, &bars[u2]);
+      } else if (a.cta_sync) asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");
+    }
     // ---- t legs from registers
     col2_leg_reg<DAG, 3, 0>(ftm, MODE == 1 && tm_halo, Us, res);
     col2_leg_reg<DAG, 3, 1>(ftp, MODE == 1 && tp_halo, Us, res);
-    // ---- z+ : wait for plane z+1 (bulk copies issued at the top of this step), read the own element
+    // ---- z+ : wait for plane z+1 (shallow form: issued at the top of this step; deep form: in the middle of step k-1 or by the
+    //      prologue), read the own element
     mbar_wait(&bars[3 + bp], (uint32_t)((k + 2) / 3) & 1);
     col2_leg<DAG, 2, 1>(mine + bp * PLANE, Us, res);
     // ---- epilogue

@@ -105,26 +105,28 @@ static bool dhop_col_launch(gb_fermop *op, const void *const in[2], void *const 
 // ---- second-generation column-sweep kernel (dhop_col2.cuh): TMA-filled ring; single rank (mode 0) and z/t-decomposed lattices
 //      (mode 1: local z legs only -> planes [1, Lz-2] when z is split; off-node t legs from the receive buffers in the surface-t
 //      CTAs, which come last in the grid).  The caller computes the z-surface planes with the micro-block kernel (interior 5 / 6).
-template <int LS> static void launch_col2_ls(const Col2Args &a, unsigned nblocks, int dag, int mode, cudaStream_t st) {
+template <int LS, int DEEP> static void launch_col2_ls(const Col2Args &a, unsigned nblocks, int dag, int mode, cudaStream_t st) {
   static bool attr_set = false;
   const size_t smem = col2_smem_bytes<LS>();
   if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 0, 0, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 1, 0, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 0, 1, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<LS, 1, 1, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   const int threads = COL_NSITE * LS;
-  if (!dag) { if (mode) dhop_col2_kernel<LS, 0, 1><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<LS, 0, 0><<<nblocks, threads, smem, st>>>(a); }
-  else { if (mode) dhop_col2_kernel<LS, 1, 1><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<LS, 1, 0><<<nblocks, threads, smem, st>>>(a); }
+  if (!dag) { if (mode) dhop_col2_kernel<LS, 0, 1, DEEP><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<LS, 0, 0, DEEP><<<nblocks, threads, smem, st>>>(a); }
+  else { if (mode) dhop_col2_kernel<LS, 1, 1, DEEP><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<LS, 1, 0, DEEP><<<nblocks, threads, smem, st>>>(a); }
 }
 bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                       const void *const ax[2], double axa, double axb, int mode, cudaStream_t st, const void *const halo[8],
                       const unsigned long long *flags, unsigned long long epoch) {
   static const bool disabled = getenv("GB_NO_COL") != nullptr || (getenv("GB_COL2") && atoi(getenv("GB_COL2")) == 0);
   static const int env_n = getenv("GB_COL_N") ? atoi(getenv("GB_COL_N")) : 0;
-  static const int env_raster = getenv("GB_COL_RASTER") ? atoi(getenv("GB_COL_RASTER")) : 0;
+  // rasterisation: 1 (default) = t fastest, then the y blocks, then the x blocks: the y-edge rows a column shares with its y
+  // neighbours (half a fetch per site) are then 32 CTAs apart in launch order instead of 128 and are re-hit in L2
+  static const int env_raster = getenv("GB_COL_RASTER") ? atoi(getenv("GB_COL_RASTER")) : 1;
   const gb_grid *g = op->grid;
   const int Ls = op->Ls;
   if (disabled || op->no_col || op->prec != GB_F32 || op->disable_fast || !(Ls == 8 || Ls == 12 || Ls == 16)) return false;
@@ -168,10 +170,15 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.flags = flags; a.epoch = epoch;
   const unsigned nblocks = (unsigned)((a.n_int + a.n_surf) * (uint32_t)nparity);
   if (nblocks == 0) return true;
-  switch (Ls) {
-  case 8: launch_col2_ls<8>(a, nblocks, dag, mode, st); break;
-  case 12: launch_col2_ls<12>(a, nblocks, dag, mode, st); break;
-  default: launch_col2_ls<16>(a, nblocks, dag, mode, st); break;
+  // GB_COL2_DEEP=0: the shallow prefetch form (ring plane and links fetched at the top of the step that needs them at its end)
+  static const bool deep = !(getenv("GB_COL2_DEEP") && atoi(getenv("GB_COL2_DEEP")) == 0);
+  switch (Ls * 2 + (deep ? 1 : 0)) {
+  case 16: launch_col2_ls<8, 0>(a, nblocks, dag, mode, st); break;
+  case 17: launch_col2_ls<8, 1>(a, nblocks, dag, mode, st); break;
+  case 24: launch_col2_ls<12, 0>(a, nblocks, dag, mode, st); break;
+  case 25: launch_col2_ls<12, 1>(a, nblocks, dag, mode, st); break;
+  case 32: launch_col2_ls<16, 0>(a, nblocks, dag, mode, st); break;
+  default: launch_col2_ls<16, 1>(a, nblocks, dag, mode, st); break;
   }
   count_launch(op->ctx);
   check_launch(op->ctx, "dhop_col2");
