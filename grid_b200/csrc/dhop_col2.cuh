@@ -32,7 +32,9 @@ struct Col2Args {
   // fastest (t neighbours side by side in L2), then the x blocks, then the y blocks (raster 1: y blocks before x blocks), then z chunks
   uint32_t n_int, n_surf;
   int t_int0, nt_int, nt_surf, raster;
-  FastDiv dnt_int, dnt_surf, dNxo, dNyo;
+  int tb;                       // t block: inside the interior segment only tb consecutive t run fastest (0 = all of them)
+  int l2pf;                     // issue an L2 prefetch of ring plane z+2 at the top of step z (cp.async.bulk.prefetch.L2)
+  FastDiv dnt_int, dnt_surf, dNxo, dNyo, dtb, dNzc;
   int nparity, first_parity, origin_parity;
   int cta_sync;                 // debugging switch (GB_COL2_SYNC=1): a CTA-wide barrier per step instead of the "z- leg done" mbarrier
   // off-node t legs (MODE 1): receive buffers of the backward (point 7) and forward (point 3) t leg, epoch flags
@@ -79,7 +81,7 @@ __device__ __forceinline__ void col2_leg_reg(const SpinorP &f, bool is_half, con
 template <int LS> constexpr size_t col2_smem_bytes() { return (size_t)(3 * COL_NSITE * 6 * LS + 3 * COL_NSITE * FAST_USTRIDE) * 16 + 64; }
 
 // MODE 0: single rank (every leg local, periodic wrap inside the local volume).  MODE 1: decomposed in z and / or t (see above).
-template <int LS, int DAG, int MODE, int DEEP = 1>
+template <int LS, int DAG, int MODE>
 __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2Args a) {
   extern __shared__ __align__(128) unsigned char col_smem[];
   constexpr int PLANE = COL_NSITE * 6 * LS;                  // float4 per ring plane, field layout [block][vec k][lane]
@@ -102,10 +104,16 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
   }
   const int p = a.first_parity ^ slot;
   uint32_t t, xo, yo, zc;
-  if (!surf) { a.dnt_int.divmod(b, b, t); t += a.t_int0; }
+  uint32_t tg = 0;
+  if (!surf) { if (a.tb) a.dtb.divmod(b, b, t); else a.dnt_int.divmod(b, b, t); }
   else { a.dnt_surf.divmod(b, b, t); t = t == 0 ? a.Lt - 1 : 0; }        // surface segment: t = Lt-1, then t = 0
   if (a.raster == 0) { a.dNxo.divmod(b, b, xo); a.dNyo.divmod(b, zc, yo); }
-  else { a.dNyo.divmod(b, b, yo); a.dNxo.divmod(b, zc, xo); }
+  else if (a.raster == 1) { a.dNyo.divmod(b, b, yo); a.dNxo.divmod(b, zc, xo); }
+  else { a.dNzc.divmod(b, b, zc); a.dNyo.divmod(b, b, yo); a.dNxo.divmod(b, tg, xo); }   // z chunks of a column side by side
+  if (!surf) {
+    if (a.tb && a.raster != 2) { const uint32_t ntg = (uint32_t)(a.nt_int / a.tb); tg = zc % ntg; zc /= ntg; }   // t groups outside x / y, inside z chunks
+    t += (a.tb ? tg * a.tb : 0) + a.t_int0;
+  }
   const int xh = xo * 4 + xl, y = yo * 4 + yl, zfirst = a.z0 + zc * a.N;
   const float4 *__restrict__ in = a.in[1 - p];
   const uint32_t zstride = (uint32_t)a.Lxh * a.Ly, tstride = zstride * a.Lz;
@@ -141,22 +149,17 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     }
   }
   __syncthreads();
-  // ---- prologue: planes zfirst-1 (slot 0), zfirst (slot 1) [DEEP: and zfirst+1 (slot 2)], links of step 0 [DEEP: and step 1]
+  // ---- prologue: planes zfirst-1 (slot 0) and zfirst (slot 1), links of step 0
   const int zfirst_w = wrapz(zfirst);
   if (threadIdx.x == 0) {
     mbar_expect_tx(&bars[3], 4 * ROW_BYTES); mbar_expect_tx(&bars[4], 4 * ROW_BYTES);
     mbar_expect_tx(&bars[0], COL_NSITE * 640);
-    if (DEEP) { mbar_expect_tx(&bars[5], 4 * ROW_BYTES); if (a.N > 1) mbar_expect_tx(&bars[1], COL_NSITE * 640); }
   }
   if (row_issuer) {
     bulk_g2s(row_dst, row_src(wrapz(zfirst - 1)), ROW_BYTES, &bars[3]);
     bulk_g2s(row_dst + PLANE, row_src(zfirst_w), ROW_BYTES, &bars[4]);
-    if (DEEP) bulk_g2s(row_dst + 2 * PLANE, row_src(wrapz(zfirst + 1)), ROW_BYTES, &bars[5]);
   }
-  if (issuer) {
-    bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zfirst_w) * 40, 640, &bars[0]);
-    if (DEEP && a.N > 1) bulk_g2s(Usm + UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * wrapz(zfirst + 1)) * 40, 640, &bars[1]);
-  }
+  if (issuer) bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zfirst_w) * 40, 640, &bars[0]);
 
   const uint32_t site_tm = site_xyt + (t == 0 ? tstride * (a.Lt - 1) : 0u - tstride);
   const uint32_t site_tp = site_xyt + ((int)t == a.Lt - 1 ? 0u - tstride * (a.Lt - 1) : tstride);
@@ -175,7 +178,6 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
 
   mbar_wait(&bars[3], 0);
   mbar_wait(&bars[4], 0);
-  if (DEEP) mbar_wait(&bars[5], 0);
   int ub = 0, bm = 0;                                          // link buffer of this step; ring slot of plane z-1
 #pragma unroll 1
   for (int k = 0; k < a.N; k++) {
@@ -189,14 +191,20 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     // one step, as the everybody-arrives barrier of the round-1 kernel did.
     if (a.cta_sync) __syncthreads();
     else if (k > 0) mbar_wait(&bars[6], (uint32_t)(k - 1) & 1);
-    if (!DEEP && issuer) {
-      // ---- asynchronous (shallow form): plane z+1 into ring slot bp, the links of the next step.  Slot bp held plane z-2 (read
-      //      as the z- leg of step k-1) and link buffer un the links of step k-2: free once everybody arrived in step k-1.
+    if (issuer) {
+      // ---- asynchronous: plane z+1 into ring slot bp, the links of the next step.  Slot bp held plane z-2 (read as the z- leg
+      //      of step k-1) and link buffer un the links of step k-2: free once everybody arrived in step k-1.
       if (threadIdx.x == 0) {
         mbar_expect_tx(&bars[3 + bp], 4 * ROW_BYTES);
         if (k + 1 < a.N) mbar_expect_tx(&bars[un], COL_NSITE * 640);
       }
-      if (row_issuer) bulk_g2s(row_dst + bp * PLANE, row_src(zp), ROW_BYTES, &bars[3 + bp]);
+      if (row_issuer) {
+        bulk_g2s(row_dst + bp * PLANE, row_src(zp), ROW_BYTES, &bars[3 + bp]);
+        if (a.l2pf && k + 1 < a.N) {
+          const int zpp = zp + 1 == a.Lz ? 0 : zp + 1;
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row_src(zpp)), "r"(ROW_BYTES) : "memory");
+        }
+      }
       if (k + 1 < a.N) bulk_g2s(Usm + un * UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zp) * 40, 640, &bars[un]);
     }
     // ---- t neighbours into registers now, used after the shared-memory legs
@@ -233,28 +241,10 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     // ---- y legs: slots +-4 inside the block
     col2_leg<DAG, 1, 0>(yl > 0 ? cur + off_ym1 : gptr(site_ym + zoff), Us, res);
     col2_leg<DAG, 1, 1>(yl < 3 ? cur + off_y1 : gptr(site_yp + zoff), Us, res);
-    if (DEEP) {
-      // ---- asynchronous (deep form): by now every thread has normally done its z- leg of THIS step (phase k of bars[6]), so ring
-      //      slot bm (plane z-1) and the link buffer of step k-1 are free: fetch plane z+2 and the links of step k+2 into them,
-      //      one and a half steps before they are needed instead of just under one
-      if (issuer) {
-        if (a.cta_sync) asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");
-        else mbar_wait(&bars[6], (uint32_t)k & 1);
-        const int u2 = un == 2 ? 0 : un + 1;                       // link buffer of step k+2 (= the one step k-1 used)
-        if (threadIdx.x == 0) {
-          if (k + 1 < a.N) mbar_expect_tx(&bars[3 + bm], 4 * ROW_BYTES);
-          if (k + 2 < a.N) mbar_expect_tx(&bars[u2], COL_NSITE * 640);
-        }
-        const int zpp = zp + 1 == a.Lz ? 0 : zp + 1;
-        if (row_issuer && k + 1 < a.N) bulk_g2s(row_dst + bm * PLANE, row_src(zpp), ROW_BYTES, &bars[3 + bm]);
-        if (k + 2 < a.N) bulk_g2s(Usm + u2 * UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zpp) * 40, 640, &bars[u2]);
-      } else if (a.cta_sync) asm volatile("bar.sync 1, %0;" ::"r"(NTHR) : "memory");
-    }
     // ---- t legs from registers
     col2_leg_reg<DAG, 3, 0>(ftm, MODE == 1 && tm_halo, Us, res);
     col2_leg_reg<DAG, 3, 1>(ftp, MODE == 1 && tp_halo, Us, res);
-    // ---- z+ : wait for plane z+1 (shallow form: issued at the top of this step; deep form: in the middle of step k-1 or by the
-    //      prologue), read the own element
+    // ---- z+ : wait for plane z+1 (bulk copies issued at the top of this step), read the own element
     mbar_wait(&bars[3 + bp], (uint32_t)((k + 2) / 3) & 1);
     col2_leg<DAG, 2, 1>(mine + bp * PLANE, Us, res);
     // ---- epilogue
