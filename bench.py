@@ -243,6 +243,35 @@ def workload_config(args):
             "mass": 0.1, "M5": 1.8, "l2": "inputs (1.6 GB/field) larger than the 126 MB L2; no flush needed"}
 
 
+def pin_to_gpu_numa(local_rank):
+    """Pins this rank to the cores of its GPU's NUMA node (pinned staging buffers are then first-touched next to the GPU's PCIe
+    root).  Returns (the affinity before pinning, a note)."""
+    before = None
+    try:
+        before = os.sched_getaffinity(0)
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local_rank)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:       # nvml prints an 8-digit domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return before, "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return before, f"numa node {node}, {len(cpus)} cores"
+        return before, f"numa node {node} has no allowed cores"
+    except Exception as e:                     # no nvml / no sysfs: run unpinned
+        return before, f"unpinned ({type(e).__name__})"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -255,7 +284,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
-    ap.add_argument("--no-cg", action="store_true", help="skip the (untimed-region) mixed-precision CG time-to-solution report")
+    ap.add_argument("--no-cg", action="store_true", help="skip the mixed-precision CG blocks (cg, e2e_cg)")
+    ap.add_argument("--no-config4", action="store_true", help="skip the 64.64.32.16 x Ls16 per-GPU block (BASELINE configs[3])")
+    ap.add_argument("--no-config5", action="store_true", help="skip the improved staggered 48^4 block (BASELINE configs[4])")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -270,7 +301,9 @@ def main():
     import numpy as np
     import torch
     import grid_b200 as gb
+    from grid_b200 import decomp
 
+    affinity0, numa_note = pin_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -283,44 +316,9 @@ def main():
         ctx.comm_init(rank, world, uid[0])
     else:
         ctx.comm_init(0, 1, None)
-
     mpi = MPI_FOR_N[args.gpus]
-    gdims = [l * m for l, m in zip(args.local, mpi)]
-    grid = gb.GridCartesian(ctx, gdims, mpi)
-    Ls = args.Ls
-    U = gb.LatticeGaugeField(grid, gb.F32).random(1)
-    Dw = gb.DomainWallFermion(U, grid, Ls, 0.1, 1.8)
-    if args.no_overlap:
-        Dw.set_overlap(False)
-    hop_form = "single rank" if world == 1 else ("serial comms" if args.no_overlap else "overlapped, semi-fused")
-    if world > 1 and not args.no_overlap:
-        # self-check of the multi-GPU hop before timing it: the default (semi-fused) form must reproduce the serial-comms form
-        chk_src = gb.LatticeFermion(grid, Ls, gb.F32).random(3)
-        o1, o2 = gb.LatticeFermion(grid, Ls, gb.F32), gb.LatticeFermion(grid, Ls, gb.F32)
-        Dw.Dhop(chk_src, o1, 0)
-        Dw.set_overlap(False); Dw.Dhop(chk_src, o2, 0); Dw.set_overlap(True)
-        ref_n = gb.norm2(o2)
-        gb.axpy(o1, -1.0, o2, o1)
-        rel = (gb.norm2(o1) / ref_n) ** 0.5
-        if not rel < 1e-6:
-            if rank == 0:
-                print(f"bench: semi-fused hop differs from the serial-comms hop (rel {rel:.3e}); timing the interior + exterior form", file=sys.stderr)
-            Dw.set_overlap(2)
-            hop_form = "overlapped, interior + accumulate-exterior (semi-fused self-check failed)"
-        del chk_src, o1, o2
-    src = gb.LatticeFermion(grid, Ls, gb.F32).random(2)
-    n2 = gb.norm2(src)
-    gb.scale(src, 1.0 / np.sqrt(n2), src)     # ref: Benchmark_dwf_fp32.cc:175-176
-    if args.op == "Dhop":
-        fin, fout = src, gb.LatticeFermion(grid, Ls, gb.F32)
-        step = lambda: Dw.Dhop(fin, fout, 0)
-        sites_local = grid.lsites * Ls
-    else:
-        fin, fout = gb.LatticeFermion(grid, Ls, gb.F32, gb.HALF), gb.LatticeFermion(grid, Ls, gb.F32, gb.HALF)
-        gb.pickCheckerboard(gb.Odd, fin, src)
-        step = lambda: Dw.DhopEO(fin, fout, 0)
-        sites_local = grid.lsites * Ls // 2
-    sites_total = sites_local * world
+    nsplit = sum(1 for m in mpi if m > 1)
+    peak, peak_src = measured_peak()
 
     def barrier():
         ctx.synchronize()
@@ -335,41 +333,99 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def timed(step, steps, warmup):
+        """W untimed calls, then exactly `steps` calls between barriers; CUDA events on the library's stream, max over ranks.
+        Returns (ms per step, launches in the timed region on this rank)."""
+        for _ in range(warmup):
+            step()
+        barrier()
+        l0 = ctx.launch_count()
+        ctx.timer_start()
+        for _ in range(steps):
+            step()
+        ms = ctx.timer_stop()
+        launches = ctx.launch_count() - l0
+        barrier()
+        return max_over_ranks(ms) / steps, launches
+
+    def pinned(shape, dtype):
+        return torch.empty(shape, dtype=dtype).pin_memory().numpy()
+
+    # ---- N > 1: per-site parity of the decomposed hop (the form that is timed below) against the CPU oracle on a small GLOBAL
+    #      lattice, before anything is timed
+    parity_check = None
+    if world > 1:
+        from grid_b200 import synthetic as syn
+        from oracle import pyoracle as po
+        pl = [8, 8, 8, 8]
+        pg = tuple(l * m for l, m in zip(pl, mpi))
+        pLs = 16
+        Ug = syn.hot_gauge(pg, seed=11)
+        xg = syn.random_fermion(pg, pLs, seed=12)
+        orc = po.OracleOp(1, pg, pLs, mass=0.1, M5=1.8, prec=1)
+        orc.import_gauge(Ug)
+        pgrid = gb.GridCartesian(ctx, pg, mpi)
+        pD = gb.DomainWallFermion(gb.LatticeGaugeField(pgrid, gb.F32).import_lex(decomp.scatter(Ug, pg, mpi, rank)), pgrid, pLs, 0.1, 1.8)
+        pin = gb.LatticeFermion(pgrid, pLs, gb.F32).import_lex(decomp.scatter(xg, pg, mpi, rank, inner=pLs).astype(np.complex64))
+        pout = gb.LatticeFermion(pgrid, pLs, gb.F32)
+        errs = {}
+        for dag in (0, 1):
+            pD.Dhop(pin, pout, dag)
+            ref = decomp.scatter(orc.apply(po.OP_DHOP, xg, dag=dag), pg, mpi, rank, inner=pLs)
+            a = pout.export_lex().reshape(ref.shape[0], -1).astype(np.complex128); r = ref.reshape(ref.shape[0], -1)
+            errs[f"Dhop dag{dag}"] = max_over_ranks(float(np.max(np.linalg.norm(a - r, axis=1) / np.linalg.norm(r, axis=1))))
+        parity_check = {"against": "CPU oracle (fp64) on the global lattice", "global_lattice": list(pg), "Ls": pLs, "mpi": list(mpi),
+                        "max_site_rel_err": errs, "tolerance": 1e-6, "ok": all(e < 1e-6 for e in errs.values())}
+        del pD, pin, pout, pgrid, orc, Ug, xg
+        if not parity_check["ok"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "error": "decomposed hop differs from the oracle", "parity_check": parity_check}), flush=True)
+            sys.exit(1)
+
+    # =========================================================== headline: BASELINE configs[1] per GPU
+    gdims = [l * m for l, m in zip(args.local, mpi)]
+    grid = gb.GridCartesian(ctx, gdims, mpi)
+    Ls = args.Ls
+    U = gb.LatticeGaugeField(grid, gb.F32).random(1)
+    Dw = gb.DomainWallFermion(U, grid, Ls, 0.1, 1.8)
+    if args.no_overlap:
+        Dw.set_overlap(False)
+    hop_form = "single rank" if world == 1 else ("serial comms" if args.no_overlap else "overlapped: pack+send, one hop launch that acquires the halos in its surface CTAs")
+    src = gb.LatticeFermion(grid, Ls, gb.F32).random(2)
+    n2 = gb.norm2(src)
+    gb.scale(src, 1.0 / np.sqrt(n2), src)     # ref: Benchmark_dwf_fp32.cc:175-176
+    if args.op == "Dhop":
+        fin, fout = src, gb.LatticeFermion(grid, Ls, gb.F32)
+        step = lambda: Dw.Dhop(fin, fout, 0)
+        sites_local = grid.lsites * Ls
+    else:
+        fin, fout = gb.LatticeFermion(grid, Ls, gb.F32, gb.HALF), gb.LatticeFermion(grid, Ls, gb.F32, gb.HALF)
+        gb.pickCheckerboard(gb.Odd, fin, src)
+        step = lambda: Dw.DhopEO(fin, fout, 0)
+        sites_local = grid.lsites * Ls // 2
+    sites_total = sites_local * world
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for _ in range(args.warmup):
-        step()
-    barrier()
-    l0 = ctx.launch_count()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        step()
-    ms_total = ctx.timer_stop()
-    launches = ctx.launch_count() - l0
-    barrier()
-    ms_total = max_over_ranks(ms_total)
-    ms_step = ms_total / args.steps
+    ms_step, launches = timed(step, args.steps, args.warmup)
     value = FLOPS_PER_SITE * sites_total / (ms_step * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers (pinned), copies inside the timed region
-    host_in = torch.empty((fin.local_sites, 4, 3), dtype=torch.complex64).pin_memory().numpy()
-    host_out = torch.empty((fin.local_sites, 4, 3), dtype=torch.complex64).pin_memory().numpy()
+    host_in = pinned((fin.local_sites, 4, 3), torch.complex64)
+    host_out = pinned((fin.local_sites, 4, 3), torch.complex64)
     host_in[...] = fin.export_lex()
     e2e_in = fin.like()
+
     def e2e_step():
         if args.op == "Dhop":
-            # the host-buffer entry point of the C ABI: single rank = H2D / hop / D2H pipelined over t-slices
+            # the host-buffer entry point of the C ABI: H2D / hop / D2H pipelined over t-slices
             Dw.Dhop_host(host_in, host_out, 0)
             return
         e2e_in.import_lex(host_in)
-        if args.op == "DhopEO":
-            e2e_in.set_checkerboard(gb.Odd)
-            Dw.DhopEO(e2e_in, fout, 0)
-        else:
-            Dw.Dhop(e2e_in, fout, 0)
-        lib = gb.lib()
-        gb._chk(lib.gb_fermion_export(fout.h, host_out.ctypes.data, gb.F32))
+        e2e_in.set_checkerboard(gb.Odd)
+        Dw.DhopEO(e2e_in, fout, 0)
+        gb._chk(gb.lib().gb_fermion_export(fout.h, host_out.ctypes.data, gb.F32))
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -386,48 +442,184 @@ def main():
             step()
         ctx.synchronize()
     clocks = sampler.stop() if rank == 0 else None
+    barrier()
+    # the same synthetic fields for the CPU leg (exported before they are released)
+    cpu_fields = None
+    if rank == 0 and not args.no_cpu and args.op == "Dhop":
+        try:
+            cpu_fields = (U.export_lex(np.complex64), host_in.copy())
+        except Exception:
+            cpu_fields = None
+    del e2e_in, host_out
 
-    # ---- CG time-to-solution (BASELINE configs[2]): even-odd Schur Moebius mixed-precision CG to 1e-8, outside the timed region
-    cg = None
-    if not args.no_cg:
-        del e2e_in, fout
-        Ud = gb.LatticeGaugeField(grid, gb.F64).random(1)
-        Dd = gb.MobiusFermion(Ud, grid, Ls, 0.1, 1.8, 1.5, 0.5)
-        Df = gb.MobiusFermion(U, grid, Ls, 0.1, 1.8, 1.5, 0.5)
-        srcd = gb.LatticeFermion(grid, Ls, gb.F64).random(2)
-        so = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF)
+    # =========================================================== cg: BASELINE configs[2] at the headline volume
+    def mixed_cg_block(grid_, U32, tag):
+        """Even-odd Schur Moebius mixed-precision CG to 1e-8 (Test_dwf_mixedcg_prec shape): warm-up solve, timed solve, and a fixed
+        50-iteration fp32 CG for the steady-state cost of one inner iteration."""
+        vol_cb = grid_.lsites * Ls // 2
+        Ud = gb.LatticeGaugeField(grid_, gb.F64).random(1)
+        Dd = gb.MobiusFermion(Ud, grid_, Ls, 0.1, 1.8, 1.5, 0.5)
+        Df = gb.MobiusFermion(U32, grid_, Ls, 0.1, 1.8, 1.5, 0.5)
+        del Ud
+        srcd = gb.LatticeFermion(grid_, Ls, gb.F64).random(2)
+        so = gb.LatticeFermion(grid_, Ls, gb.F64, gb.HALF)
         gb.pickCheckerboard(gb.Odd, so, srcd)
         del srcd
-        sol = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()
-        mcg = gb.MixedPrecisionConjugateGradient(1e-8, 10000, 50, gb.SchurDiagMooeeOperator(Df), gb.SchurDiagMooeeOperator(Dd))
+        sol = gb.LatticeFermion(grid_, Ls, gb.F64, gb.HALF).zero()
+        Lf, Ld = gb.SchurDiagMooeeOperator(Df), gb.SchurDiagMooeeOperator(Dd)
+        warm = gb.MixedPrecisionConjugateGradient(1e-3, 10000, 50, Lf, Ld)
+        warm(so, sol)                                                     # pools, s-space matrices, first-touch: not timed
+        sol.zero()
+        mcg = gb.MixedPrecisionConjugateGradient(1e-8, 10000, 50, Lf, Ld)
         barrier()
         t0 = time.perf_counter()
         mcg(so, sol)
         ctx.synchronize()
         cg_s = max_over_ranks(time.perf_counter() - t0)
         its = mcg.TotalInnerIterations + mcg.TotalFinalStepIterations
-        cg = {"solver": "MixedPrecisionConjugateGradient on SchurDiagMooeeOperator(MobiusFermion b=1.5 c=0.5, m=0.1, M5=1.8), tol 1e-8",
-              "time_to_solution_s": cg_s, "inner_iterations": mcg.TotalInnerIterations, "outer_iterations": mcg.TotalOuterIterations,
-              "final_iterations": mcg.TotalFinalStepIterations, "true_residual": mcg.TrueResidual,
-              "gflops": (1452.0 * 4 + 336.0) * (sites_total if args.op == "DhopEO" else sites_total / 2) * its / cg_s / 1e9}
+        # steady-state fp32 iteration: a ConjugateGradient on the fp32 operator stopped after 50 iterations
+        sf, xf = gb.LatticeFermion(grid_, Ls, gb.F32, gb.HALF), gb.LatticeFermion(grid_, Ls, gb.F32, gb.HALF).zero()
+        gb.precisionChange(sf, so)
+        cg50 = gb.ConjugateGradient(1e-30, 50, err_on_no_conv=False)
+        cg50(Lf, sf, xf)
+        xf.zero()
+        barrier()
+        l0 = ctx.launch_count()
+        ctx.timer_start()
+        cg50(Lf, sf, xf)
+        ms_it = max_over_ranks(ctx.timer_stop()) / max(cg50.IterationsToComplete, 1)
+        l_it = (ctx.launch_count() - l0) / max(cg50.IterationsToComplete, 1)
+        yard = 1872.0 * vol_cb                                            # SURVEY 8d: ideal-fused bytes per Schur CG iteration and cb site
+        out = {"solver": "MixedPrecisionConjugateGradient on SchurDiagMooeeOperator(MobiusFermion b=1.5 c=0.5, m=0.1, M5=1.8), tol 1e-8",
+               "lattice": tag, "time_to_solution_s": cg_s, "timed_after_warmup_solve": True,
+               "inner_iterations": mcg.TotalInnerIterations, "outer_iterations": mcg.TotalOuterIterations,
+               "final_iterations": mcg.TotalFinalStepIterations, "true_residual": mcg.TrueResidual,
+               "gflops": (1452.0 * 4 + 336.0) * vol_cb * world * its / cg_s / 1e9,
+               "ms_per_iteration": ms_it, "launches_per_iteration": l_it,
+               "roofline_frac": yard / (ms_it * 1e-3) / 1e9 / peak, "yardstick_bytes_per_cb_site": 1872.0}
+        return out, (Dd, Df, so, sol)
 
+    cg = e2e_cg = None
+    if not args.no_cg:
+        del fout
+        cg, (Dd, Df, so, sol) = mixed_cg_block(grid, U, "headline volume")
+        # ---- e2e_cg: what HMC calls -- gauge field and source arrive in host memory, the solution goes back to it
+        try:
+            hU = pinned((grid.lsites, 4, 3, 3), torch.complex128)
+            hs = pinned((so.local_sites, 4, 3), torch.complex128)
+            hx = pinned((so.local_sites, 4, 3), torch.complex128)
+            Ud2 = gb.LatticeGaugeField(grid, gb.F64).random(1)
+            hU[...] = Ud2.export_lex()
+            hs[...] = so.export_lex()
+            Uf2 = gb.LatticeGaugeField(grid, gb.F32)
+            hU32 = pinned((grid.lsites, 4, 3, 3), torch.complex64)
+            barrier()
+            t0 = time.perf_counter()
+            Ud2.import_lex(hU)
+            hU32[...] = hU                                               # the fp32 copy of the links HMC's inner solver uses
+            Uf2.import_lex(hU32)
+            Dd.ImportGauge(Ud2); Df.ImportGauge(Uf2)
+            so.import_lex(hs); so.set_checkerboard(gb.Odd)
+            sol.zero()
+            m2 = gb.MixedPrecisionConjugateGradient(1e-8, 10000, 50, gb.SchurDiagMooeeOperator(Df), gb.SchurDiagMooeeOperator(Dd))
+            m2(so, sol)
+            gb._chk(gb.lib().gb_fermion_export(sol.h, hx.ctypes.data, gb.F64))
+            ctx.synchronize()
+            e2e_cg_s = max_over_ranks(time.perf_counter() - t0)
+            e2e_cg = {"time_to_solution_s": e2e_cg_s, "h2d_bytes": int(hU.nbytes + hU32.nbytes + hs.nbytes) * world, "d2h_bytes": int(hx.nbytes) * world,
+                      "true_residual": m2.TrueResidual, "iterations": m2.TotalInnerIterations + m2.TotalFinalStepIterations,
+                      "what": "LatticeGaugeField (fp64 + fp32) and odd-checkerboard source from pinned host memory, ImportGauge on both operators, "
+                              "mixed CG to 1e-8, solution exported to host memory; wall clock, max over ranks"}
+            del hU, hs, hx, hU32, Ud2, Uf2
+        except Exception as e:                                          # never lose the headline line to a secondary block
+            e2e_cg = {"error": f"{type(e).__name__}: {e}"}
+        del Dd, Df, so, sol
+    del Dw, src, fin, U, grid
+
+    # =========================================================== config4: BASELINE configs[3], 64.64.32.16 x Ls16 per GPU
+    config4 = None
+    if not args.no_config4:
+        try:
+            l4 = [64, 64, 32, 16]
+            g4 = [l * m for l, m in zip(l4, mpi)]
+            grid4 = gb.GridCartesian(ctx, g4, mpi)
+            U4 = gb.LatticeGaugeField(grid4, gb.F32).random(1)
+            D4 = gb.DomainWallFermion(U4, grid4, 16, 0.1, 1.8)
+            s4 = gb.LatticeFermion(grid4, 16, gb.F32).random(2)
+            gb.scale(s4, 1.0 / np.sqrt(gb.norm2(s4)), s4)
+            o4 = gb.LatticeFermion(grid4, 16, gb.F32)
+            ms4, l4n = timed(lambda: D4.Dhop(s4, o4, 0), 100, 5)
+            sites4 = grid4.lsites * 16
+            config4 = {"workload": f"DomainWallFermionF::Dhop fp32, local 64x64x32x16 x Ls16 per GPU, global {'x'.join(map(str, g4))}, mpi {'.'.join(map(str, mpi))} "
+                                   "(BASELINE configs[3]: global 64^4 x Ls16 at 8 GPUs; weak-scaling series, efficiency = per-GPU GFlop/s at N over N=1)",
+                       "ms_per_step": ms4, "per_gpu_gflops": FLOPS_PER_SITE * sites4 / (ms4 * 1e-3) / 1e9, "gflops": FLOPS_PER_SITE * sites4 * world / (ms4 * 1e-3) / 1e9,
+                       "roofline_frac": alg_bytes_per_site(16) * sites4 / (ms4 * 1e-3) / 1e9 / peak, "gpu_launches_per_step": l4n / 100}
+            if world > 1:
+                nbytes = 0
+                for _ in range(5):
+                    nbytes = D4.halo_exchange(s4)
+                barrier()
+                ctx.timer_start()
+                for _ in range(50):
+                    D4.halo_exchange(s4)
+                msh = max_over_ranks(ctx.timer_stop()) / 50
+                config4["halo"] = {"bytes_sent_per_gpu_per_hop": int(nbytes), "ms_exchange_alone": msh, "nvlink_GBs_out_per_gpu": nbytes / msh / 1e6,
+                                   "nvlink_GBs_per_direction": nbytes / msh / 1e6 / (2 * nsplit),
+                                   "what": "pack (project) + peer stores of every face of one Dhop + arrival, nothing else running; "
+                                           "bytes / time, so this is a latency-inclusive lower bound of the link rate"}
+            del D4, s4, o4
+            if not args.no_cg:
+                c4, keep = mixed_cg_block(grid4, U4, "local 64x64x32x16 x Ls16 per GPU")
+                del keep
+                config4["cg"] = c4
+            del U4, grid4
+        except Exception as e:
+            config4 = {"error": f"{type(e).__name__}: {e}"}
+
+    # =========================================================== config5: BASELINE configs[4], improved staggered 48^4 (global)
+    config5 = None
+    if not args.no_config5:
+        try:
+            g5 = [48, 48, 48, 48]
+            grid5 = gb.GridCartesian(ctx, g5, mpi)
+            U5 = gb.LatticeGaugeField(grid5, gb.F32).random(1)
+            D5 = gb.ImprovedStaggeredFermion(U5, U5, grid5, 0.1)
+            del U5
+            s5, o5 = gb.LatticeStaggeredFermion(grid5, 1, gb.F32).random(2), gb.LatticeStaggeredFermion(grid5, 1, gb.F32)
+            ms5, l5n = timed(lambda: D5.Dhop(s5, o5, 0), 100, 5)
+            sites5 = 48 ** 4
+            config5 = {"workload": f"ImprovedStaggeredFermionF::Dhop fp32 (Naik 3-hop), global 48^4, mpi {'.'.join(map(str, mpi))} (BASELINE configs[4]; strong scaling)",
+                       "ms_per_step": ms5, "gflops": 1146.0 * sites5 / (ms5 * 1e-3) / 1e9,      # ref: benchmarks/Benchmark_staggered.cc:105
+                       "roofline_frac": 1200.0 * sites5 / world / (ms5 * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_site": 1200.0, "gpu_launches_per_step": l5n / 100}
+            del D5, s5, o5, grid5
+        except Exception as e:
+            config5 = {"error": f"{type(e).__name__}: {e}"}
+
+    # =========================================================== the reference's CPU code beside it (rank 0, every N)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        use_all_host_cores(affinity0)
+        try:
+            cpu = cpu_leg(Ls, args.local, op=args.op, fields=cpu_fields)
+        except Exception as e:
+            cpu = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        peak, peak_src = measured_peak()
         bps = alg_bytes_per_site(Ls)
-        achieved = bps * sites_local / (ms_step * 1e-3) / 1e9       # per GPU; one dhop_kernel launch per step
+        achieved = bps * sites_local / (ms_step * 1e-3) / 1e9       # per GPU
+        kernel = "gb::dhop_col3_kernel<16,0,0,1>" if world == 1 else "gb::dhop_col3_kernel<16,0,1,1> (+ pack_send_kernel, z-surface planes by dhop_fast_kernel<16,0,2>)"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                "data": "synthetic", "config": dict(workload_config(args), hop_form=hop_form),
+                "data": "synthetic", "config": workload_config(args), "hop_form": hop_form,
                 "per_gpu_gflops": value / world, "vs_published_a100_per_gpu": value / world / PUBLISHED_A100_GFLOPS_PER_GPU,
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes) * world, "d2h_bytes_per_step": int(host_out.nbytes) * world,
-                        "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_in.nbytes) * world, "d2h_bytes_per_step": int(host_in.nbytes) * world,
+                        "ms_per_step": e2e_s * 1e3, "steps": args.e2e_steps, "GBs_per_direction_per_gpu": host_in.nbytes / e2e_s / 1e9, "host_pinning": numa_note},
                 "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "gb::dhop_col_kernel<16,0,0> (N=1) | gb::dhop_fast_kernel<16,0,1> + pack_send + exterior dhop_kernel (N>1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                             "frac": achieved / peak, "traffic": ncu_traffic(args.op), "peak_source": peak_src,
+                "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                             "frac": achieved / peak, "traffic": ncu_traffic(args.op) if world == 1 else None, "peak_source": peak_src,
                              "algorithmic_bytes_per_site": bps, "sites_per_launch": sites_local},
-                "clocks": clocks, "cg": cg}
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_leg(Ls, op=args.op)
+                "clocks": clocks, "cg": cg, "e2e_cg": e2e_cg, "config4": config4, "config5": config5, "parity_check": parity_check}
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()

@@ -21,7 +21,8 @@ void sync_block();
 int sync_block_or(int pred);
 void sync_warp();
 void yield();
-uint64_t shfl_raw(uint64_t v, int src_lane_delta);   // value held by lane + delta of the caller's warp (own value if out of range)
+uint64_t shfl_raw(uint64_t v, int src_lane_delta);
+uint64_t shfl_idx(uint64_t v, int src_lane);          // value held by lane src_lane of the caller's warp   // value held by lane + delta of the caller's warp (own value if out of range)
 
 // ---- mbarrier (transaction barrier in shared memory; state kept in the 8 bytes the kernel declares)
 void mbar_init(uint64_t *bar, int count);
@@ -53,3 +54,10 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, int delta) {
   raw = gb_mock::shfl_raw(raw, delta);
   T r; std::memcpy(&r, &raw, sizeof(T)); return r;
 }
+template <class T> inline T __shfl_sync(unsigned, T v, int src_lane) {
+  static_assert(sizeof(T) <= 8, "shuffle of at most 8 bytes");
+  uint64_t raw = 0; std::memcpy(&raw, &v, sizeof(T));
+  raw = gb_mock::shfl_idx(raw, src_lane);
+  T r; std::memcpy(&r, &raw, sizeof(T)); return r;
+}
+inline void __threadfence_block() {}

@@ -99,6 +99,11 @@ uint64_t shfl_raw(uint64_t v, int delta) {
   return r;
 }
 
+uint64_t shfl_idx(uint64_t v, int src_lane) {
+  if (!E.active) return v;
+  return shfl_raw(v, src_lane - (int)(E.current % 32));
+}
+
 void mbar_init(uint64_t *bar, int count) { MBar *b = (MBar *)bar; b->count = (uint16_t)count; b->pending = (uint16_t)count; b->tx = 0; b->phase = 0; }
 void mbar_expect_tx(uint64_t *bar, uint32_t bytes) { MBar *b = (MBar *)bar; b->tx += (int32_t)bytes; b->pending--; mbar_check(b); }
 void mbar_complete_tx(uint64_t *bar, uint32_t bytes) { MBar *b = (MBar *)bar; b->tx -= (int32_t)bytes; mbar_check(b); }

@@ -49,11 +49,11 @@ PARITY = ["tests/test_gpu_parity.py", "-k", "not dhop_host and not device_random
 JOBS = {
     "next_rows": (NEXT + ["-k", "not driver"], None, {}),
     "golden": (["tests/test_golden.py"], None, {}),
-    "parity": (PARITY, ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {}),
+    "parity": (PARITY, ["dhop_col2_kernel", "dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {}),
     "micro_block": (["tests/test_gpu_parity.py", "-k", "fast_and_generic or tiling or schur_operator or cg_matches"],
-                    ["dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {"GB_NO_COL": "1", "GB_MOCK_SM_COUNT": "3"}),
+                    ["dhop_col2_kernel", "dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {"GB_NO_COL": "1", "GB_MOCK_SM_COUNT": "3"}),
     "two_t_slices": (["tests/test_gpu_parity.py", "tests/test_next_tuned_shapes.py", "-k", "(fast_and_generic and dwf_col) or (edge_shapes and Ls8_n)"],
-                     ["dhop_col_kernel<LS, 0, 0, 2>", "dhop_col_kernel<LS, 1, 0, 2>"], {"GB_COL_NT": "2"}),
+                     ["dhop_col_kernel<LS, 0, 0, 2>", "dhop_col_kernel<LS, 1, 0, 2>"], {"GB_COL_NT": "2", "GB_COL2": "0"}),
     "n_rank": ("mgpu_on_mock.py", None, {}),
 }
 
@@ -117,14 +117,14 @@ def test_measured_parity_gpu_tests_pass_on_the_cpu_mock(children):
     -- all but the host-pipelined Dhop and the device RNG, which the mock does not provide.  The fp32 hops go through the
     column-sweep kernel, the s-space operators through the dense kernel (launch counters)"""
     n, c = children.passed_and_counts("parity")
-    assert n >= 300 and c["dhop_col_kernel"] > 50 and c["smat_kernel"] > 1000, (n, c)
+    assert n >= 300 and c["dhop_col2_kernel"] > 50 and c["smat_kernel"] > 1000, (n, c)
 
 
 def test_micro_block_kernel_and_persistent_s_space_kernel_on_the_cpu_mock(children):
     """the other tuned shapes: GB_NO_COL=1 sends every fp32 hop through the micro-block kernel (the interior pass on decomposed
     lattices), and with 3 "SMs" the s-space kernel's persistent CTAs loop over many tiles through their two-stage TMA pipeline"""
     n, c = children.passed_and_counts("micro_block")
-    assert n >= 40 and c["dhop_col_kernel"] == 0 and c["dhop_fast_kernel"] > 30 and c["smat_kernel"] > 100, (n, c)
+    assert n >= 40 and c["dhop_col_kernel"] == 0 and c["dhop_col2_kernel"] == 0 and c["dhop_fast_kernel"] > 30 and c["smat_kernel"] > 100, (n, c)
 
 
 def test_two_t_slices_per_cta_column_kernel_on_the_cpu_mock(children):
