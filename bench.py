@@ -606,7 +606,7 @@ def main():
     if rank == 0:
         bps = alg_bytes_per_site(Ls)
         achieved = bps * sites_local / (ms_step * 1e-3) / 1e9       # per GPU
-        kernel = "gb::dhop_col3_kernel<16,0,0,1>" if world == 1 else "gb::dhop_col3_kernel<16,0,1,1> (+ pack_send_kernel, z-surface planes by dhop_fast_kernel<16,0,2>)"
+        kernel = "gb::dhop_col2_kernel<16,0,0>" if world == 1 else "gb::dhop_col2_kernel<16,0,1> (+ pack_send_kernel; z-surface planes by dhop_fast_kernel<16,0,2> where z is split)"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(args), "hop_form": hop_form,

@@ -56,6 +56,8 @@ struct gb_fermop {
   const void *sm_meooe5d = nullptr, *sm_meooedag5d = nullptr, *sm_mooee = nullptr, *sm_mooeedag = nullptr, *sm_mooeeinv = nullptr,
              *sm_mooeeinvdag = nullptr, *sm_m5unit = nullptr, *sm_m5unitdag = nullptr, *sm_B = nullptr, *sm_Bdag = nullptr, *sm_negAdag = nullptr;
   std::vector<void *> smat_allocs;
+  double *smat_partials = nullptr;   // per-CTA partial sums of the s-space passes that carry a reduction (smat.cu)
+  size_t smat_partials_n = 0;
   // improved staggered (stag.cu): 16 scaled + phased links per site, per output parity, streamed layout
   void *stag_links = nullptr;
   size_t stag_parity_bytes = 0;
@@ -100,6 +102,18 @@ SMat smat_scale(const SMat &A, double f);
 const void *smat_device(gb_fermop *op, const SMat &m);
 bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha, const gb_fermion *z,
                 gb_fermion *out);
+// the same pass with the conjugate-gradient linear algebra folded in (device-resident scalars; see smat.cu)
+struct SMatCG { const double *d_c = nullptr, *d_d = nullptr, *d_cp = nullptr; double *d_out = nullptr; gb_fermion *psi = nullptr, *p = nullptr; };
+bool smat_apply_norm(gb_fermop *op, const void *dM, const gb_fermion *x, double alpha, const gb_fermion *z, gb_fermion *out, double *d_out);
+bool smat_apply_rupd(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, gb_fermion *r, const double *d_c,
+                     const double *d_d, double *d_out);
+bool smat_apply_cgupd(gb_fermop *op, const void *dM, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, gb_fermion *out, const double *d_c,
+                      const double *d_d, const double *d_cp);
+void device_global_sum(gb_context *ctx, double *d_vals, int n); // context.cu: in-stream all-reduce of device scalars
+// Schur CG with the linear algebra folded into the s-space passes (fermop.cu): available for Cayley operators on the dense s-space path
+bool cg_fused_available(const gb_fermop *op);
+void cg_fused_first(gb_fermop *op, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, const double *d_c, const double *d_d, const double *d_cp);
+void cg_fused_rest(gb_fermop *op, const gb_fermion *p, gb_fermion *r, const double *d_c, double *d_d, double *d_cp);
 
 size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag);
 void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st);

@@ -14,6 +14,7 @@
 // the matrices in registers and accumulates with packed f32x2 FMAs, reading x[site][k][s'] as a broadcast LDS.128.
 #include "fermop.hpp"
 #include "dhop_fast.cuh"
+#include "kernels_common.cuh"
 #include <algorithm>
 
 namespace gb {
@@ -22,6 +23,12 @@ constexpr int SM_NSITE = 16;
 
 template <class T, int LS> struct SMatRows { T mp[LS], mm[LS]; };
 
+// Epilogues that fold the conjugate-gradient linear algebra of the Schur solve into the s-space passes (solver.cu):
+//   EPI_NORM  : out = M x [+ N y] [+ alpha z], and |out|^2 is reduced into *d_out (this is d = |Mpc p|^2 = <p, MpcDag Mpc p>)
+//   EPI_RUPD  : q = M x [+ N y] is NOT stored: out = z - (c/d) q (the residual update r -= a A p), |out|^2 reduced into *d_out
+//   EPI_CGUPD : x = r, y = p, N = M: b = cp/c, a = c/d; out = M (r + b p) (the first s-space pass of the next A p), and on the way
+//               psi += a p, p = r + b p (ref: ConjugateGradient.h:176-183) for the thread's own element
+enum { EPI_NONE = 0, EPI_NORM = 1, EPI_RUPD = 2, EPI_CGUPD = 3 };
 template <class T> struct SMatArgs {
   const typename Prec<T>::vec *x, *y, *z;
   typename Prec<T>::vec *out;
@@ -29,6 +36,10 @@ template <class T> struct SMatArgs {
   T alpha;
   uint32_t nsite;        // 4D sites in this parity block
   size_t block_stride;   // vecs between parity blocks
+  // epilogues
+  const double *d_c = nullptr, *d_d = nullptr, *d_cp = nullptr;   // device-resident CG scalars
+  double *partials = nullptr;                                    // one slot per CTA
+  typename Prec<T>::vec *psi = nullptr, *p = nullptr;            // EPI_CGUPD
 };
 
 template <class V> __device__ __forceinline__ V v_fma(float a, V x, V acc);
@@ -39,7 +50,7 @@ template <> __device__ __forceinline__ float4 v_fma<float4>(float a, float4 x, f
 }
 __device__ __forceinline__ double2 v_fmad(double a, double2 x, double2 acc) { return make_double2(fma(a, x.x, acc.x), fma(a, x.y, acc.y)); }
 
-template <class T, int LS, int NIN>
+template <class T, int LS, int NIN, int EPI>
 __global__ void __launch_bounds__(SM_NSITE *LS) smat_kernel(const SMatArgs<T> a) {
   using P = Prec<T>;
   using V = typename P::vec;
@@ -61,6 +72,17 @@ __global__ void __launch_bounds__(SM_NSITE *LS) smat_kernel(const SMatArgs<T> a)
   for (int j = 0; j < LS; j++) {
     mp[j] = a.M[s * LS + j]; mm[j] = a.M[LS * LS + s * LS + j];
     if (NIN == 2) { np_[j] = a.N[s * LS + j]; nm_[j] = a.N[LS * LS + s * LS + j]; }
+  }
+  T cg_a = 0, cg_b = 0;
+  T alpha = a.alpha;
+  double nrm = 0;
+  if (EPI == EPI_RUPD) alpha = (T)(-(*a.d_c) / (*a.d_d));
+  if (EPI == EPI_CGUPD) {
+    cg_a = (T)((*a.d_c) / (*a.d_d)); cg_b = (T)((*a.d_cp) / (*a.d_c));
+    if (NIN == 2) {
+#pragma unroll
+      for (int j = 0; j < LS; j++) { np_[j] *= cg_b; nm_[j] *= cg_b; }
+    }
   }
   auto issue = [&](uint32_t tile, int st) { // called by all threads; thread 0 arms the barrier, lane s==0 of each site copies
     uint32_t site = tile * SM_NSITE + sl;
@@ -139,13 +161,54 @@ __global__ void __launch_bounds__(SM_NSITE *LS) smat_kernel(const SMatArgs<T> a)
           if constexpr (sizeof(T) == 4) acc = v_fma<float4>(upper ? np_[j] : nm_[j], yv, acc); else acc = v_fmad(upper ? np_[j] : nm_[j], yv, acc);
         }
       }
-      if (a.z != nullptr) {
+      if (EPI == EPI_RUPD) {
         const V zv = a.z[g + ((size_t)k << LOGW)];
-        if constexpr (sizeof(T) == 4) acc = v_fma<float4>(a.alpha, zv, acc); else acc = v_fmad(a.alpha, zv, acc);
+        if constexpr (sizeof(T) == 4) acc = v_fma<float4>(alpha, acc, zv); else acc = v_fmad(alpha, acc, zv);
+      } else if (a.z != nullptr) {
+        const V zv = a.z[g + ((size_t)k << LOGW)];
+        if constexpr (sizeof(T) == 4) acc = v_fma<float4>(alpha, zv, acc); else acc = v_fmad(alpha, zv, acc);
       }
-      if (active) a.out[g + ((size_t)k << LOGW)] = acc;
+      if (active) {
+        a.out[g + ((size_t)k << LOGW)] = acc;
+        if (EPI == EPI_NORM || EPI == EPI_RUPD) nrm += vnorm2(acc);
+        if (EPI == EPI_CGUPD && NIN == 2) {
+          const V rv = sx[sidx(k, s)], pv = sy[sidx(k, s)];
+          a.psi[g + ((size_t)k << LOGW)] = vaxpy(cg_a, pv, a.psi[g + ((size_t)k << LOGW)]);
+          a.p[g + ((size_t)k << LOGW)] = vaxpy(cg_b, pv, rv);
+        }
+      }
     }
     __syncthreads(); // every thread is done with this stage before it is refilled
+  }
+  if (EPI == EPI_NORM || EPI == EPI_RUPD) {
+    // fixed-shape block tree, one partial per CTA; the second stage (smat_reduce_kernel) adds them in a fixed order
+    __shared__ double red[SM_NSITE * LS / 32 + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v = nrm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0;
+      for (int w = 0; w < (SM_NSITE * LS + 31) / 32; w++) t += red[w];
+      a.partials[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = t;
+    }
+  }
+}
+__global__ void smat_reduce_kernel(const double *partials, int n, double *result) {
+  double acc = 0;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partials[i];
+  __shared__ double sm[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if (lane == 0) sm[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; w++) t += sm[w];
+    *result = t;
   }
 }
 
@@ -225,60 +288,106 @@ const void *smat_device(gb_fermop *op, const SMat &m) {
   return d;
 }
 
-template <class T, int LS> static void smat_launch_ls(gb_context *ctx, const SMatArgs<T> &a, int nin, int nparity) {
+template <class T, int LS, int NIN, int EPI> static void smat_launch_k(gb_fermop *op, SMatArgs<T> &a, int nparity, double *d_out) {
   using P = Prec<T>;
+  gb_context *ctx = op->ctx;
   constexpr bool CONTIG = (LS % W) == 0;
-  const size_t stage = (size_t)nin * SM_NSITE * (P::NV * LS + 1) * 16;
+  const size_t stage = (size_t)NIN * SM_NSITE * (P::NV * LS + 1) * 16;
   const size_t smem = stage * (CONTIG ? 2 : 1);
   const uint32_t ntiles = (a.nsite + SM_NSITE - 1) / SM_NSITE;
-  int per_sm = 1;
-  if (nin == 2) {
-    GB_CUDA(cudaFuncSetAttribute(smat_kernel<T, LS, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smat_kernel<T, LS, 2>, SM_NSITE * LS, smem));
-  } else {
-    GB_CUDA(cudaFuncSetAttribute(smat_kernel<T, LS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smat_kernel<T, LS, 1>, SM_NSITE * LS, smem));
+  static int per_sm = 0;                    // per instantiation: attribute set and occupancy asked once
+  if (per_sm == 0) {
+    GB_CUDA(cudaFuncSetAttribute(smat_kernel<T, LS, NIN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, smat_kernel<T, LS, NIN, EPI>, SM_NSITE * LS, smem));
+    if (per_sm < 1) per_sm = 1;
   }
-  if (per_sm < 1) per_sm = 1;
   uint32_t gx = CONTIG ? std::min<uint32_t>(ntiles, (uint32_t)(ctx->sm_count * per_sm + nparity - 1) / nparity) : ntiles;
   if (gx < 1) gx = 1;
+  const size_t nctas = (size_t)gx * nparity;
+  if (EPI == EPI_NORM || EPI == EPI_RUPD) {
+    if (op->smat_partials_n < nctas) {
+      if (op->smat_partials) cudaFree(op->smat_partials);
+      op->smat_partials = nullptr; op->smat_partials_n = 0;
+      GB_CUDA(cudaMalloc(&op->smat_partials, nctas * sizeof(double)));
+      op->smat_partials_n = nctas;
+    }
+    a.partials = op->smat_partials;
+  }
   dim3 grid(gx, nparity);
-  if (nin == 2) smat_kernel<T, LS, 2><<<grid, SM_NSITE * LS, smem, ctx->stream>>>(a);
-  else smat_kernel<T, LS, 1><<<grid, SM_NSITE * LS, smem, ctx->stream>>>(a);
+  smat_kernel<T, LS, NIN, EPI><<<grid, SM_NSITE * LS, smem, ctx->stream>>>(a);
+  count_launch(ctx);
+  if (EPI == EPI_NORM || EPI == EPI_RUPD) {
+    smat_reduce_kernel<<<1, 256, 0, ctx->stream>>>(op->smat_partials, (int)nctas, d_out);
+    count_launch(ctx);
+  }
 }
-template <class T> static bool smat_launch_T(gb_context *ctx, int Ls, const SMatArgs<T> &a, int nin, int nparity) {
+template <class T, int LS> static void smat_launch_ls(gb_fermop *op, SMatArgs<T> &a, int nin, int epi, int nparity, double *d_out) {
+  if (epi == EPI_NONE) { if (nin == 2) smat_launch_k<T, LS, 2, EPI_NONE>(op, a, nparity, d_out); else smat_launch_k<T, LS, 1, EPI_NONE>(op, a, nparity, d_out); }
+  else if (epi == EPI_NORM) { GB_REQUIRE(nin == 1, "smat: EPI_NORM takes one input"); smat_launch_k<T, LS, 1, EPI_NORM>(op, a, nparity, d_out); }
+  else if (epi == EPI_RUPD) { GB_REQUIRE(nin == 2, "smat: EPI_RUPD takes two inputs"); smat_launch_k<T, LS, 2, EPI_RUPD>(op, a, nparity, d_out); }
+  else { GB_REQUIRE(nin == 2, "smat: EPI_CGUPD takes two inputs"); smat_launch_k<T, LS, 2, EPI_CGUPD>(op, a, nparity, d_out); }
+}
+template <class T> static bool smat_launch_T(gb_fermop *op, int Ls, SMatArgs<T> &a, int nin, int epi, int nparity, double *d_out) {
   switch (Ls) {
-  case 8: smat_launch_ls<T, 8>(ctx, a, nin, nparity); return true;
-  case 12: smat_launch_ls<T, 12>(ctx, a, nin, nparity); return true;
-  case 16: smat_launch_ls<T, 16>(ctx, a, nin, nparity); return true;
+  case 8: smat_launch_ls<T, 8>(op, a, nin, epi, nparity, d_out); return true;
+  case 12: smat_launch_ls<T, 12>(op, a, nin, epi, nparity, d_out); return true;
+  case 16: smat_launch_ls<T, 16>(op, a, nin, epi, nparity, d_out); return true;
   default: return false;
   }
 }
 
 // out = M x [+ N y] [+ alpha z]; returns false when Ls is outside the instantiated set (caller falls back)
-bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha, const gb_fermion *z,
-                gb_fermion *out) {
+static bool smat_apply_epi(gb_fermop *op, int epi, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha,
+                           const gb_fermion *z, gb_fermion *out, const SMatCG *cg) {
   gb_context *ctx = op->ctx;
   const int Ls = op->Ls;
   if (!(Ls == 8 || Ls == 12 || Ls == 16)) return false;
   fermion_check_same(x, out);
   if (y) fermion_check_same(x, y);
   if (z) fermion_check_same(x, z);
+  if (cg && cg->psi) { fermion_check_same(x, cg->psi); fermion_check_same(x, cg->p); }
   // aliasing x/y/z with out is safe: a CTA stages its whole tile in shared memory before it writes, tiles are disjoint
   const int nin = y ? 2 : 1;
   const size_t bstride = (size_t)x->hblk * nv_of(op->prec) * W;
+  double *d_out = cg ? cg->d_out : nullptr;
   bool ok;
   if (op->prec == GB_F32) {
     SMatArgs<float> a{(const float4 *)x->data, y ? (const float4 *)y->data : nullptr, z ? (const float4 *)z->data : nullptr, (float4 *)out->data,
                       (const float *)dM, (const float *)dN, (float)alpha, (uint32_t)x->nsite4, bstride};
-    ok = smat_launch_T<float>(ctx, Ls, a, nin, x->nparity);
+    if (cg) { a.d_c = cg->d_c; a.d_d = cg->d_d; a.d_cp = cg->d_cp; a.psi = cg->psi ? (float4 *)cg->psi->data : nullptr; a.p = cg->p ? (float4 *)cg->p->data : nullptr; }
+    ok = smat_launch_T<float>(op, Ls, a, nin, epi, x->nparity, d_out);
   } else {
     SMatArgs<double> a{(const double2 *)x->data, y ? (const double2 *)y->data : nullptr, z ? (const double2 *)z->data : nullptr, (double2 *)out->data,
                        (const double *)dM, (const double *)dN, alpha, (uint32_t)x->nsite4, bstride};
-    ok = smat_launch_T<double>(ctx, Ls, a, nin, x->nparity);
+    if (cg) { a.d_c = cg->d_c; a.d_d = cg->d_d; a.d_cp = cg->d_cp; a.psi = cg->psi ? (double2 *)cg->psi->data : nullptr; a.p = cg->p ? (double2 *)cg->p->data : nullptr; }
+    ok = smat_launch_T<double>(op, Ls, a, nin, epi, x->nparity, d_out);
   }
-  if (ok) { count_launch(ctx); check_launch(ctx, "smat"); out->cb = x->cb; }
+  if (ok) { check_launch(ctx, "smat"); out->cb = x->cb; }
   return ok;
+}
+bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha, const gb_fermion *z,
+                gb_fermion *out) {
+  return smat_apply_epi(op, EPI_NONE, dM, x, dN, y, alpha, z, out, nullptr);
+}
+// out = M x + alpha z ; *d_out = |out|^2 on this rank (device)
+bool smat_apply_norm(gb_fermop *op, const void *dM, const gb_fermion *x, double alpha, const gb_fermion *z, gb_fermion *out, double *d_out) {
+  SMatCG cg; cg.d_out = d_out;
+  return smat_apply_epi(op, EPI_NORM, dM, x, nullptr, nullptr, alpha, z, out, &cg);
+}
+// r = r - (c/d) (M x + N y) ; *d_out = |r|^2 on this rank (device)
+bool smat_apply_rupd(gb_fermop *op, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, gb_fermion *r, const double *d_c,
+                     const double *d_d, double *d_out) {
+  SMatCG cg; cg.d_c = d_c; cg.d_d = d_d; cg.d_out = d_out;
+  const int cb = r->cb;
+  const bool ok = smat_apply_epi(op, EPI_RUPD, dM, x, dN, y, 0.0, r, r, &cg);
+  r->cb = cb;
+  return ok;
+}
+// psi += (c/d) p ; p = r + (cp/c) p ; out = M p(new)
+bool smat_apply_cgupd(gb_fermop *op, const void *dM, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, gb_fermion *out, const double *d_c,
+                      const double *d_d, const double *d_cp) {
+  SMatCG cg; cg.d_c = d_c; cg.d_d = d_d; cg.d_cp = d_cp; cg.psi = psi; cg.p = p;
+  return smat_apply_epi(op, EPI_CGUPD, dM, r, dM, p, 0.0, nullptr, out, &cg);
 }
 
 } // namespace gb

@@ -123,8 +123,37 @@ static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fe
   double *cv = ctx->d_scalars, *dd = ctx->d_scalars + 2;
   GB_CUDA(cudaMemcpyAsync(cv, &cp, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
-  A(p, mmp);
   int k;
+  const bool unfused = getenv("GB_CG_UNFUSED") != nullptr;   // read per solve: tests compare the two forms in one process
+  if (shift == 0.0 && !unfused && cg_fused_available(op)) {
+    // the linear algebra rides on the s-space passes of A p (fermop.cu: cg_fused_first / cg_fused_rest); same scalars, same
+    // update order, same stopping test; mmp (= A p) is never materialised
+    cg_fused_first(op, nullptr, p, nullptr, nullptr, nullptr, nullptr);
+    for (k = 1; k <= maxit; k++) {
+      double *d_c = cv + ((k - 1) & 1), *d_cp = cv + (k & 1);
+      cg_fused_rest(op, p, r, d_c, dd, d_cp);            // d = <p, A p> ; r -= (c/d) A p ; cp = |r|^2
+      GB_CUDA(cudaMemcpyAsync(ctx->h_result, d_cp, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      GB_CUDA(cudaEventRecord(ctx->ev_scalar, ctx->stream));
+      if (k < maxit) cg_fused_first(op, psi, p, r, d_c, dd, d_cp);   // psi += a p ; p = b p + r ; and the first pass of the next A p
+      else cg_update_dev(ctx, psi, p, r, d_c, dd, d_cp);
+      GB_CUDA(cudaEventSynchronize(ctx->ev_scalar));
+      cp = ctx->h_result[0];
+      GB_REQUIRE(!std::isnan(cp), "ConjugateGradient: residual is NaN");
+      if (cp <= rsq) {
+        A(psi, mmp);
+        chk(gb_axpy(p, -1.0, src, mmp)); // p = mmp - src
+        double rn;
+        chk(gb_norm2(p, &rn));
+        out.true_resid = std::sqrt(rn) / std::sqrt(ssq);
+        out.iters = k; out.converged = true;
+        return out;
+      }
+    }
+    GB_CUDA(cudaStreamSynchronize(ctx->stream));
+    out.iters = k; out.converged = false;
+    return out;
+  }
+  A(p, mmp);
   for (k = 1; k <= maxit; k++) {
     double *d_c = cv + ((k - 1) & 1), *d_cp = cv + (k & 1);
     reduce_inner_dev(ctx, p, mmp, dd);                 // d = <p, A p>

@@ -353,6 +353,8 @@ int gref_init(int threads) {
   if (g_inited) return 0;
   // --device-mem: the reference's software cache for lattice fields defaults to 128 MB and asserts on a larger field
   // (MemoryManagerCache.cc:236); 64 GB lets it hold the 32^4 x 16 and 64.64.32.16 x 16 fields of BASELINE configs[1] and [3]
+  // GridThread::SetThreads caps --threads at omp_get_max_threads(), which torchrun's OMP_NUM_THREADS=1 pins to one: raise it first
+  if (threads > 0) omp_set_num_threads(threads);
   static std::string a0 = "gridref", a1 = "--threads", a2, a3 = "--grid", a4 = "8.8.8.8", a5 = "--device-mem", a6 = "65536";
   a2 = std::to_string(threads > 0 ? threads : omp_get_max_threads());
   static char *args[] = {(char *)a0.c_str(), (char *)a1.c_str(), (char *)a2.c_str(), (char *)a3.c_str(), (char *)a4.c_str(),

@@ -155,6 +155,7 @@ void global_sum(gb_context *ctx, double *v, int n) {
   else g_world.cv.wait(l, [&] { return g_world.gen != mygen; });
   for (int i = 0; i < n; i++) v[i] = g_world.res[i];
 }
+void device_global_sum(gb_context *ctx, double *d_vals, int n) { global_sum(ctx, d_vals, n); }   // "device" scalars are host memory here
 template <class T> static void inner_T(const gb_fermion *l, const gb_fermion *r, double out[2]) {
   const T *a = (const T *)l->data, *b = (const T *)r->data;
   long double re = 0, im = 0;   // site products in working precision, lattice sum in extended precision (the real reductions are trees)
