@@ -317,6 +317,7 @@ static int pick_block(int L, int want) {
 }
 
 void op_import_gauge(gb_fermop *op, const gb_gauge *Umu) {
+  GB_TRACE("ImportGauge");
   gb_context *ctx = op->ctx;
   const gb_grid *g = op->grid;
   GB_REQUIRE(Umu->grid == g, "gauge field lives on a different grid");
@@ -443,6 +444,7 @@ template <class T> static void launch_dhop_T(gb_fermop *op, DhopArgs &a, int npa
 void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                  const void *const ax[2], double axa, double axb) {
   gb_context *ctx = op->ctx;
+  GB_TRACE(dag ? "DhopDag" : "Dhop");
   const gb_grid *g = op->grid;
   GB_CUDA(cudaSetDevice(ctx->device));
   DhopArgs a;
@@ -667,6 +669,7 @@ __global__ void halo_wait_kernel(const unsigned long long *flags, unsigned long 
   }
 }
 size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag) {
+  GB_TRACE("HaloExchange");
   GB_REQUIRE(op && in && op->kind != GB_KIND_STAGGERED, "halo exchange benchmark: Wilson-type operators");
   GB_REQUIRE(in->grid == op->grid && in->Ls == op->Ls && in->prec == op->prec && in->kind == GB_FULL, "field is not a conformable full-grid field");
   gb_context *ctx = op->ctx;

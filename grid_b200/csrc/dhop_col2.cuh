@@ -37,6 +37,7 @@ struct Col2Args {
   FastDiv dnt_int, dnt_surf, dNxo, dNyo, dtb, dNzc;
   int nparity, first_parity, origin_parity;
   int cta_sync;                 // debugging switch (GB_COL2_SYNC=1): a CTA-wide barrier per step instead of the "z- leg done" mbarrier
+  uint32_t zero;                // always 0, but only the host knows: lets the kernel build register dependencies ptxas cannot fold
   // off-node t legs (MODE 1): receive buffers of the backward (point 7) and forward (point 3) t leg, epoch flags
   int t_comm;
   const float4 *halo_tm, *halo_tp;
@@ -63,6 +64,25 @@ __device__ __forceinline__ void col2_leg(const float4 *p, const float4 *Usm, Spi
   lds_link(u, Usm + (FWD ? MU : MU + 4) * 5);
   mult_p(Uchi, u, chi);
   recon_p<MU, SIGN>(res, Uchi);
+}
+// The z- leg, which reads ring slot bm for the last time: its six shared-memory loads must have RETURNED before this thread
+// tells the issuers that the slot may be refilled.  mbarrier.arrive orders the loads' issue, not their completion (the SASS had
+// the arrive ahead of the FFMA2 that first consumes the last two loads), and a bulk copy into the slot can overtake a load that
+// still waits in the shared-memory pipe: measured on the B200 as one stale spinor in ~2 of 1000 launches at 32^4 x 16
+// (scripts/hop_stress.py; zero with a CTA-wide barrier instead).  So the arrive's ADDRESS is made to depend on one register of
+// each load (an LDS.128 delivers its four registers together): (bits & a.zero) is 0, which the compiler cannot know.
+template <int DAG>
+__device__ __forceinline__ void col2_leg_zm_arrive(const float4 *p, const float4 *Usm, SpinorP &res, uint64_t *bar, uint32_t zero, bool arrive) {
+  constexpr int SIGN = DAG ? -1 : +1;
+  SpinorP f; HalfP chi, Uchi; LinkS u;
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) { const float4 v = p[k << LOGW]; f.c[2 * k] = pk(v.x, v.y); f.c[2 * k + 1] = pk(v.z, v.w); bits |= __float_as_uint(v.x); }
+  if (arrive) mbar_arrive(reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(bar) + (bits & zero)));
+  proj_p<2, SIGN>(chi, f);
+  lds_link(u, Usm + 6 * 5);
+  mult_p(Uchi, u, chi);
+  recon_p<2, SIGN>(res, Uchi);
 }
 // t leg from registers: a full spinor (local neighbour), or the already projected half spinor of an off-node neighbour in c[0..5]
 template <int DAG, int MU, int FWD>
@@ -227,8 +247,7 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     const float4 *Us = Usm + ub * UBUF + sl * FAST_USTRIDE;
     const float4 *cur = mine + b0 * PLANE;                       // own element, plane z
     // ---- z- : own element of plane z-1; then tell the issuers that this thread is done with that slot
-    col2_leg<DAG, 2, 0>(mine + bm * PLANE, Us, res);
-    if (!a.cta_sync) mbar_arrive(&bars[6]);
+    col2_leg_zm_arrive<DAG>(mine + bm * PLANE, Us, res, &bars[6], a.zero, !a.cta_sync);
     // ---- x legs: the neighbour with the same x/2 index is this thread's own ring element; the other one is the adjacent
     //      slot or, at the block edge, a global load
     if (pb) {

@@ -2,7 +2,6 @@
 #include "dhop_fast.cuh"
 #include "dhop_col.cuh"
 #include "dhop_col2.cuh"
-#include "dhop_col3.cuh"
 #include <cstdlib>
 #include "fermop.hpp"
 #include <algorithm>
@@ -137,21 +136,6 @@ template <int LS> static void launch_col2_ls(const Col2Args &a, unsigned nblocks
   if (!dag) { if (mode) launch_col2_k(dhop_col2_kernel<LS, 0, 1>, a, nblocks, threads, smem, cluster, st); else launch_col2_k(dhop_col2_kernel<LS, 0, 0>, a, nblocks, threads, smem, cluster, st); }
   else { if (mode) launch_col2_k(dhop_col2_kernel<LS, 1, 1>, a, nblocks, threads, smem, cluster, st); else launch_col2_k(dhop_col2_kernel<LS, 1, 0>, a, nblocks, threads, smem, cluster, st); }
 }
-// third generation (dhop_col3.cuh): same arguments and grid; CARRY = 1 keeps the z- projection in registers
-template <int LS, int CARRY> static void launch_col3_ls(const Col2Args &a, unsigned nblocks, int dag, int mode, cudaStream_t st) {
-  static bool attr_set = false;
-  const size_t smem = col3_smem_bytes<LS>();
-  if (!attr_set) {
-    GB_CUDA(cudaFuncSetAttribute(dhop_col3_kernel<LS, 0, 0, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaFuncSetAttribute(dhop_col3_kernel<LS, 1, 0, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaFuncSetAttribute(dhop_col3_kernel<LS, 0, 1, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    GB_CUDA(cudaFuncSetAttribute(dhop_col3_kernel<LS, 1, 1, CARRY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
-  const int threads = COL_NSITE * LS;
-  if (!dag) { if (mode) dhop_col3_kernel<LS, 0, 1, CARRY><<<nblocks, threads, smem, st>>>(a); else dhop_col3_kernel<LS, 0, 0, CARRY><<<nblocks, threads, smem, st>>>(a); }
-  else { if (mode) dhop_col3_kernel<LS, 1, 1, CARRY><<<nblocks, threads, smem, st>>>(a); else dhop_col3_kernel<LS, 1, 0, CARRY><<<nblocks, threads, smem, st>>>(a); }
-}
 bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                       const void *const ax[2], double axa, double axb, int mode, cudaStream_t st, const void *const halo[8],
                       const unsigned long long *flags, unsigned long long epoch) {
@@ -204,6 +188,7 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   if (a.raster == 2 && t_comm) a.raster = 1;
   static const int env_sync = getenv("GB_COL2_SYNC") ? atoi(getenv("GB_COL2_SYNC")) : 0;
   a.cta_sync = env_sync;
+  a.zero = 0;
   a.nparity = nparity; a.first_parity = parity_out_first;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
   a.halo_tm = halo ? (const float4 *)halo[7] : nullptr; a.halo_tp = halo ? (const float4 *)halo[3] : nullptr;
@@ -212,22 +197,6 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   const unsigned nblocks = (unsigned)((a.n_int + a.n_surf) * (uint32_t)nparity);
   if (nblocks == 0) return true;
   static const int env_cluster = getenv("GB_COL_CLUSTER") ? atoi(getenv("GB_COL_CLUSTER")) : 0;
-  // GB_COL3=1/2: the third-generation kernel without / with the carried z- projection
-  static const int env_col3 = getenv("GB_COL3") ? atoi(getenv("GB_COL3")) : 0;
-  if (env_col3) {
-    if (a.raster > 1) a.raster = 1;
-    switch (Ls * 2 + (env_col3 == 2 ? 1 : 0)) {
-    case 16: launch_col3_ls<8, 0>(a, nblocks, dag, mode, st); break;
-    case 17: launch_col3_ls<8, 1>(a, nblocks, dag, mode, st); break;
-    case 24: launch_col3_ls<12, 0>(a, nblocks, dag, mode, st); break;
-    case 25: launch_col3_ls<12, 1>(a, nblocks, dag, mode, st); break;
-    case 32: launch_col3_ls<16, 0>(a, nblocks, dag, mode, st); break;
-    default: launch_col3_ls<16, 1>(a, nblocks, dag, mode, st); break;
-    }
-    count_launch(op->ctx);
-    check_launch(op->ctx, "dhop_col3");
-    return true;
-  }
   switch (Ls) {
   case 8: launch_col2_ls<8>(a, nblocks, dag, mode, env_cluster, st); break;
   case 12: launch_col2_ls<12>(a, nblocks, dag, mode, env_cluster, st); break;

@@ -2,6 +2,7 @@
 #pragma once
 #include "internal.hpp"
 #include <cstdlib>
+#include <map>
 
 enum gb_opkind { GB_KIND_WILSON = 0, GB_KIND_CAYLEY = 1, GB_KIND_STAGGERED = 2 };
 
@@ -56,6 +57,7 @@ struct gb_fermop {
   const void *sm_meooe5d = nullptr, *sm_meooedag5d = nullptr, *sm_mooee = nullptr, *sm_mooeedag = nullptr, *sm_mooeeinv = nullptr,
              *sm_mooeeinvdag = nullptr, *sm_m5unit = nullptr, *sm_m5unitdag = nullptr, *sm_B = nullptr, *sm_Bdag = nullptr, *sm_negAdag = nullptr;
   std::vector<void *> smat_allocs;
+  std::map<const void *, gb::SMat> smat_host;   // host copies by device pointer (the streaming kernel of smat.cu takes its coefficients from them)
   double *smat_partials = nullptr;   // per-CTA partial sums of the s-space passes that carry a reduction (smat.cu)
   size_t smat_partials_n = 0;
   // improved staggered (stag.cu): 16 scaled + phased links per site, per output parity, streamed layout

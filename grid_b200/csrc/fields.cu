@@ -881,6 +881,7 @@ template <int DIR> void slab_transfer(gb_context *ctx, const gb_fermion *f, void
 extern "C" int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_out, gb_precision host_prec, int dag) {
   GB_API_BEGIN
   GB_REQUIRE(op && host_in && host_out, "null argument");
+  GB_TRACE("DhopHost");
   GB_REQUIRE(op->kind != GB_KIND_STAGGERED, "gb_op_dhop_host serves the Wilson-type operators");
   gb_context *ctx = op->ctx;
   gb_grid *g = op->grid;

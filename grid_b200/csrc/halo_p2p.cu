@@ -182,6 +182,7 @@ unsigned long long p2p_next_epoch(gb_fermop *op) { return ++op->p2p.epoch; }
 
 // pack + send every face of this hop in one launch; returns the epoch the consumer must wait for
 unsigned long long p2p_pack_send(gb_fermop *op, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st) {
+  GB_TRACE("Gather");   // pack (project) + peer stores: the reference's Gather + CommunicateBegin
   const unsigned long long epoch = p2p_next_epoch(op);
   p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, st);
   return epoch;

@@ -1,6 +1,7 @@
 // internal.hpp -- private structures of libgridb200 (not part of the C ABI).
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdint>
 #include <cstdio>
 #include <stdexcept>
@@ -33,6 +34,17 @@ void set_last_error(const std::string &m);
   }                                                                                                          \
   catch (const gb::Error &e) { gb::set_last_error(e.what()); return e.code; }                               \
   catch (const std::exception &e) { gb::set_last_error(e.what()); return GB_ERR_INVALID; }
+
+// ------------------------------------------------------------------ NVTX ranges (ref: Grid/perfmon/Tracing.h:5-70 GRID_TRACE; names follow
+// the reference's: Dhop, DhopDag, HaloExchange, Gather, ConjugateGradient, ...).  Header-only NVTX v3: free unless a tool is attached.
+struct TraceRange {
+  explicit TraceRange(const char *name) { nvtxRangePushA(name); }
+  ~TraceRange() { nvtxRangePop(); }
+  TraceRange(const TraceRange &) = delete;
+};
+#define GB_TRACE_CAT2(a, b) a##b
+#define GB_TRACE_CAT(a, b) GB_TRACE_CAT2(a, b)
+#define GB_TRACE(name) gb::TraceRange GB_TRACE_CAT(gb_trace_, __LINE__)(name)
 
 // ------------------------------------------------------------------ device layout constants
 // A fermion field is an array of "vector sites" i5 = site4*Ls + s.  Storage is blocked:

@@ -285,6 +285,7 @@ const void *smat_device(gb_fermop *op, const SMat &m) {
     GB_CUDA(cudaMemcpy(d, m.a.data(), bytes, cudaMemcpyHostToDevice));
   }
   op->smat_allocs.push_back(d);
+  op->smat_host[d] = m;
   return d;
 }
 
@@ -336,9 +337,160 @@ template <class T> static bool smat_launch_T(gb_fermop *op, int Ls, SMatArgs<T> 
   }
 }
 
+
+// ------------------------------------------------------------------ tridiagonal (cyclic) s-space operators with the CG epilogues
+// Mooee, MooeeDag, Meooe5D and MeooeDag5D couple s only to s-1 and s+1 (cyclically: the corner carries the mass term), per chirality
+// (ref: CayleyFermion5Dcache.h:43-114 M5D / M5Ddag).  For Ls = 16 one 16-lane block of the field layout is one 4D site, so the
+// neighbours in s are two warp shuffles away and the fused CG passes become pure streaming kernels (no shared-memory staging, no
+// broadcast LDS: the dense form spends 2 x 16 LDS.128 per output vec on matrices that have three non-zero entries per row).
+constexpr int STRI_THREADS = 192;      // a multiple of 16 lanes x NV vecs (96 fp32, 192 fp64): (k, s) is fixed per thread
+template <class T> struct STriArgs {
+  using V = typename Prec<T>::vec;
+  const V *x, *y, *z;
+  V *out, *psi, *p;
+  T dM[2][16], lM[2][16], uM[2][16], dN[2][16], lN[2][16], uN[2][16];   // [chirality][s]: out_s = d x_s + l x_{s-1} + u x_{s+1}
+  T alpha;
+  int64_t n;                           // vecs in the field (all parity blocks)
+  const double *d_c, *d_d, *d_cp;
+  double *partials;
+};
+__device__ __forceinline__ float4 shfl_vec(float4 v, int src) {
+  return make_float4(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src), __shfl_sync(0xffffffffu, v.z, src), __shfl_sync(0xffffffffu, v.w, src));
+}
+__device__ __forceinline__ double2 shfl_vec(double2 v, int src) { return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src)); }
+__device__ __forceinline__ float4 tri3(float d, float4 x, float l, float4 xm, float u, float4 xp) {
+  return make_float4(fmaf(u, xp.x, fmaf(l, xm.x, d * x.x)), fmaf(u, xp.y, fmaf(l, xm.y, d * x.y)), fmaf(u, xp.z, fmaf(l, xm.z, d * x.z)), fmaf(u, xp.w, fmaf(l, xm.w, d * x.w)));
+}
+__device__ __forceinline__ double2 tri3(double d, double2 x, double l, double2 xm, double u, double2 xp) {
+  return make_double2(fma(u, xp.x, fma(l, xm.x, d * x.x)), fma(u, xp.y, fma(l, xm.y, d * x.y)));
+}
+
+template <class T, int EPI>
+__global__ void __launch_bounds__(STRI_THREADS) stri_kernel(const STriArgs<T> a) {
+  using V = typename Prec<T>::vec;
+  constexpr int NV = Prec<T>::NV;
+  const int t = threadIdx.x, s = t & 15, k = (t >> 4) % NV, c = k >= NV / 2 ? 1 : 0;
+  const int lane = t & 31, src_m = (lane & 16) | ((s + 15) & 15), src_p = (lane & 16) | ((s + 1) & 15);
+  const T dM = a.dM[c][s], lM = a.lM[c][s], uM = a.uM[c][s];
+  T dN = 0, lN = 0, uN = 0;
+  if (EPI == EPI_RUPD) { dN = a.dN[c][s]; lN = a.lN[c][s]; uN = a.uN[c][s]; }
+  T alpha = a.alpha, cg_a = 0, cg_b = 0;
+  if (EPI == EPI_RUPD) alpha = (T)(-(*a.d_c) / (*a.d_d));
+  if (EPI == EPI_CGUPD) { cg_a = (T)((*a.d_c) / (*a.d_d)); cg_b = (T)((*a.d_cp) / (*a.d_c)); }
+  double nrm = 0;
+  const int64_t stride = (int64_t)gridDim.x * STRI_THREADS;
+  for (int64_t i = (int64_t)blockIdx.x * STRI_THREADS + t; i < a.n; i += stride) {   // whole warps drop out together (n is a multiple of 32)
+    V r;
+    if (EPI == EPI_CGUPD) {
+      const V rv = a.x[i], pv = a.y[i];
+      const V pn = vaxpy(cg_b, pv, rv);                         // p = r + b p
+      a.psi[i] = vaxpy(cg_a, pv, a.psi[i]);                     // psi += a p
+      a.p[i] = pn;
+      r = tri3(dM, pn, lM, shfl_vec(pn, src_m), uM, shfl_vec(pn, src_p));
+    } else {
+      const V xv = a.x[i];
+      r = tri3(dM, xv, lM, shfl_vec(xv, src_m), uM, shfl_vec(xv, src_p));
+      if (EPI == EPI_RUPD) {
+        const V yv = a.y[i];
+        r = vadd(r, tri3(dN, yv, lN, shfl_vec(yv, src_m), uN, shfl_vec(yv, src_p)));
+        r = vaxpy(alpha, r, a.z[i]);                            // r_new = r_old - (c/d) q
+      } else if (a.z != nullptr) r = vaxpy(alpha, a.z[i], r);
+    }
+    a.out[i] = r;
+    if (EPI == EPI_NORM || EPI == EPI_RUPD) nrm += vnorm2(r);
+  }
+  if (EPI == EPI_NORM || EPI == EPI_RUPD) {
+    __shared__ double red[STRI_THREADS / 32];
+    double v = nrm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) red[t >> 5] = v;
+    __syncthreads();
+    if (t == 0) {
+      double tot = 0;
+      for (int w = 0; w < STRI_THREADS / 32; w++) tot += red[w];
+      a.partials[blockIdx.x] = tot;
+    }
+  }
+}
+
+// d / l / u of a cyclic-tridiagonal [2][Ls][Ls] matrix; false if it has any other non-zero entry
+static bool tri_extract(const SMat &m, double d[2][16], double l[2][16], double u[2][16]) {
+  const int Ls = m.Ls;
+  if (Ls != 16) return false;
+  for (int c = 0; c < 2; c++)
+    for (int i = 0; i < Ls; i++) {
+      const int im = (i + Ls - 1) % Ls, ip = (i + 1) % Ls;
+      for (int j = 0; j < Ls; j++) {
+        const double v = m.a[(c * Ls + i) * Ls + j];
+        if (j == i) d[c][i] = v; else if (j == im) l[c][i] = v; else if (j == ip) u[c][i] = v; else if (v != 0.0) return false;
+      }
+    }
+  return true;
+}
+template <class T, int EPI> static void stri_launch(gb_fermop *op, STriArgs<T> &a, double *d_out) {
+  gb_context *ctx = op->ctx;
+  const unsigned blocks = (unsigned)std::min<int64_t>((a.n + STRI_THREADS - 1) / STRI_THREADS, (int64_t)ctx->sm_count * 10);
+  if (EPI == EPI_NORM || EPI == EPI_RUPD) {
+    if (op->smat_partials_n < blocks) {
+      if (op->smat_partials) cudaFree(op->smat_partials);
+      op->smat_partials = nullptr; op->smat_partials_n = 0;
+      GB_CUDA(cudaMalloc(&op->smat_partials, blocks * sizeof(double)));
+      op->smat_partials_n = blocks;
+    }
+    a.partials = op->smat_partials;
+  }
+  stri_kernel<T, EPI><<<blocks, STRI_THREADS, 0, ctx->stream>>>(a);
+  count_launch(ctx);
+  if (EPI == EPI_NORM || EPI == EPI_RUPD) {
+    smat_reduce_kernel<<<1, 256, 0, ctx->stream>>>(op->smat_partials, (int)blocks, d_out);
+    count_launch(ctx);
+  }
+  check_launch(ctx, "stri");
+}
+// the fused CG passes through the streaming kernel; false = not applicable (Ls != 16, a dense matrix, or switched off): use the dense form
+template <class T> static bool stri_apply_T(gb_fermop *op, int epi, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y,
+                                            double alpha, const gb_fermion *z, gb_fermion *out, const SMatCG *cg) {
+  using V = typename Prec<T>::vec;
+  auto hm = op->smat_host.find(dM);
+  if (hm == op->smat_host.end()) return false;
+  double d[2][16] = {}, l[2][16] = {}, u[2][16] = {}, dn[2][16] = {}, ln[2][16] = {}, un[2][16] = {};
+  if (!tri_extract(hm->second, d, l, u)) return false;
+  if (epi == EPI_RUPD) {
+    auto hn = op->smat_host.find(dN);
+    if (hn == op->smat_host.end() || !tri_extract(hn->second, dn, ln, un)) return false;
+  }
+  STriArgs<T> a;
+  a.x = (const V *)x->data; a.y = y ? (const V *)y->data : nullptr; a.z = z ? (const V *)z->data : nullptr; a.out = (V *)out->data;
+  a.psi = cg && cg->psi ? (V *)cg->psi->data : nullptr; a.p = cg && cg->p ? (V *)cg->p->data : nullptr;
+  for (int c = 0; c < 2; c++) for (int i = 0; i < 16; i++) {
+    a.dM[c][i] = (T)d[c][i]; a.lM[c][i] = (T)l[c][i]; a.uM[c][i] = (T)u[c][i];
+    a.dN[c][i] = (T)dn[c][i]; a.lN[c][i] = (T)ln[c][i]; a.uN[c][i] = (T)un[c][i];
+  }
+  a.alpha = (T)alpha; a.n = x->nvec();
+  a.d_c = cg ? cg->d_c : nullptr; a.d_d = cg ? cg->d_d : nullptr; a.d_cp = cg ? cg->d_cp : nullptr; a.partials = nullptr;
+  double *d_out = cg ? cg->d_out : nullptr;
+  if (epi == EPI_NORM) stri_launch<T, EPI_NORM>(op, a, d_out);
+  else if (epi == EPI_RUPD) stri_launch<T, EPI_RUPD>(op, a, d_out);
+  else if (epi == EPI_CGUPD) stri_launch<T, EPI_CGUPD>(op, a, d_out);
+  else return false;
+  out->cb = x->cb;
+  return true;
+}
+static bool stri_apply(gb_fermop *op, int epi, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha,
+                       const gb_fermion *z, gb_fermion *out, const SMatCG *cg) {
+  if (op->Ls != 16 || getenv("GB_NO_STRI") != nullptr) return false;
+  fermion_check_same(x, out);
+  if (y) fermion_check_same(x, y);
+  if (z) fermion_check_same(x, z);
+  if (cg && cg->psi) { fermion_check_same(x, cg->psi); fermion_check_same(x, cg->p); }
+  return op->prec == GB_F32 ? stri_apply_T<float>(op, epi, dM, x, dN, y, alpha, z, out, cg) : stri_apply_T<double>(op, epi, dM, x, dN, y, alpha, z, out, cg);
+}
+
 // out = M x [+ N y] [+ alpha z]; returns false when Ls is outside the instantiated set (caller falls back)
 static bool smat_apply_epi(gb_fermop *op, int epi, const void *dM, const gb_fermion *x, const void *dN, const gb_fermion *y, double alpha,
                            const gb_fermion *z, gb_fermion *out, const SMatCG *cg) {
+  GB_TRACE("SSpaceDense");
   gb_context *ctx = op->ctx;
   const int Ls = op->Ls;
   if (!(Ls == 8 || Ls == 12 || Ls == 16)) return false;
@@ -372,6 +524,7 @@ bool smat_apply(gb_fermop *op, const void *dM, const gb_fermion *x, const void *
 // out = M x + alpha z ; *d_out = |out|^2 on this rank (device)
 bool smat_apply_norm(gb_fermop *op, const void *dM, const gb_fermion *x, double alpha, const gb_fermion *z, gb_fermion *out, double *d_out) {
   SMatCG cg; cg.d_out = d_out;
+  if (stri_apply(op, EPI_NORM, dM, x, nullptr, nullptr, alpha, z, out, &cg)) return true;
   return smat_apply_epi(op, EPI_NORM, dM, x, nullptr, nullptr, alpha, z, out, &cg);
 }
 // r = r - (c/d) (M x + N y) ; *d_out = |r|^2 on this rank (device)
@@ -379,7 +532,7 @@ bool smat_apply_rupd(gb_fermop *op, const void *dM, const gb_fermion *x, const v
                      const double *d_d, double *d_out) {
   SMatCG cg; cg.d_c = d_c; cg.d_d = d_d; cg.d_out = d_out;
   const int cb = r->cb;
-  const bool ok = smat_apply_epi(op, EPI_RUPD, dM, x, dN, y, 0.0, r, r, &cg);
+  const bool ok = stri_apply(op, EPI_RUPD, dM, x, dN, y, 0.0, r, r, &cg) || smat_apply_epi(op, EPI_RUPD, dM, x, dN, y, 0.0, r, r, &cg);
   r->cb = cb;
   return ok;
 }
@@ -387,6 +540,7 @@ bool smat_apply_rupd(gb_fermop *op, const void *dM, const gb_fermion *x, const v
 bool smat_apply_cgupd(gb_fermop *op, const void *dM, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, gb_fermion *out, const double *d_c,
                       const double *d_d, const double *d_cp) {
   SMatCG cg; cg.d_c = d_c; cg.d_d = d_d; cg.d_cp = d_cp; cg.psi = psi; cg.p = p;
+  if (stri_apply(op, EPI_CGUPD, dM, r, dM, p, 0.0, nullptr, out, &cg)) return true;
   return smat_apply_epi(op, EPI_CGUPD, dM, r, dM, p, 0.0, nullptr, out, &cg);
 }
 

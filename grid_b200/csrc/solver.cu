@@ -37,6 +37,7 @@ struct CGOut { int iters = 0; double true_resid = 0; bool converged = false; };
 using HermOpFn = std::function<void(const gb_fermion *, gb_fermion *)>;
 
 static CGOut cg_core(gb_context *ctx, const HermOpFn &A, const gb_fermion *src, gb_fermion *psi, double tol, int maxit) {
+  GB_TRACE("ConjugateGradient");
   fermion_check_same(src, psi);
   gb_fermion *p = nullptr, *mmp = nullptr, *r = nullptr;
   auto mk = [&](gb_fermion **f) { *f = fermion_create_like(src, src->prec); };
@@ -95,6 +96,7 @@ void cg_update_dev(gb_context *ctx, gb_fermion *psi, gb_fermion *p, const gb_fer
 //   "converged" the speculative A p has only overwritten the scratch field mmp.
 // shift != 0: CG on HermOp + shift (ShiftedLinop, ref: ConjugateGradientMultiShiftMixedPrec.h:44-70)
 static CGOut cg_schur_device_scalars(gb_fermop *op, const gb_fermion *src, gb_fermion *psi, double tol, int maxit, double shift = 0.0) {
+  GB_TRACE("ConjugateGradient");
   gb_context *ctx = op->ctx;
   fermion_check_same(src, psi);
   gb_fermion *p = nullptr, *mmp = nullptr, *r = nullptr;
@@ -480,6 +482,7 @@ int gb_mixed_cg_schur_ex(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src
 static MixedOut mixed_cg_core(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src_d_in, gb_fermion *sol_d, double tol, int max_inner, int max_outer,
                               double shift, double inner_tol0, double outer_loop_norm_mult) {
   GB_REQUIRE(op_f && op_d && src_d_in && sol_d, "null argument");
+  GB_TRACE("MixedPrecisionConjugateGradient");
   GB_REQUIRE(op_f->prec == GB_F32 && op_d->prec == GB_F64, "mixed CG needs an fp32 and an fp64 operator");
   GB_REQUIRE(src_d_in->prec == GB_F64 && sol_d->prec == GB_F64, "mixed CG outer fields must be fp64");
   const int cb = src_d_in->cb;

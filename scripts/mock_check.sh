@@ -9,7 +9,7 @@ set -e
 cd "$(dirname "$0")/.."
 OUT=${GB_MOCK_DIR:-/tmp/gridb200_mock_check}
 LIB=$(python tests/mock/build_mock.py "$OUT")
-export GB_TEST_MOCK_LIB="$LIB" GB_MOCK_COUNT="dhop_col3_kernel;dhop_col2_kernel;dhop_col_kernel;dhop_fast_kernel;smat_kernel;pack_send_kernel"
+export GB_TEST_MOCK_LIB="$LIB" GB_MOCK_COUNT="dhop_col2_kernel;dhop_col_kernel;dhop_fast_kernel;smat_kernel;pack_send_kernel"
 python tests/mock/run_counted.py tests/test_next_tuned_shapes.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x \
   -k "edge_shapes or fast_and_generic or tiling or schur_operator or dhop_full or dhop_oe_eo"
 if [ "$1" = "all" ]; then

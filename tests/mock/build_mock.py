@@ -13,7 +13,7 @@ from transform import transform  # noqa: E402
 
 PRODUCT_SOURCES = ["fermop.cu", "dhop.cu", "dhop_fast.cu", "halo_p2p.cu", "smat.cu", "cayley.cu", "stag.cu", "solver.cu", "schur.cu", "force.cu", "nersc.cu"]
 # headers that hold kernels with inline PTX or shared memory: rewritten too, and found first on the include path
-PRODUCT_HEADERS = ["dhop_fast.cuh", "dhop_col.cuh", "dhop_col2.cuh", "dhop_col3.cuh"]
+PRODUCT_HEADERS = ["dhop_fast.cuh", "dhop_col.cuh", "dhop_col2.cuh"]
 
 
 def build(outdir, sanitize=False):

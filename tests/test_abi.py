@@ -116,3 +116,11 @@ def test_ctypes_signatures_match_the_header():
             assert _category(p) == _py_category(a), (name, p, a)
         want_ret = "ptr" if "*" in ret else _category(ret)
         assert want_ret == _py_category(res), (name, ret, res)
+
+
+def test_library_carries_the_nvtx_trace_ranges():
+    """NVTX ranges named like the reference's GRID_TRACE regions (ref: Grid/perfmon/Tracing.h:5-70; WilsonFermion5DImplementation.h:324-408,
+    ConjugateGradient.h:72) are compiled into the product library"""
+    blob = open(os.path.join(ROOT, "grid_b200", "libgridb200.so"), "rb").read()
+    for name in (b"Dhop", b"DhopDag", b"HaloExchange", b"Gather", b"ConjugateGradient", b"MixedPrecisionConjugateGradient", b"ImportGauge", b"DhopHost"):
+        assert name + b"\x00" in blob, name

@@ -167,3 +167,21 @@ def test_the_mock_is_not_reachable_from_the_product():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "GB_TEST_MOCK_LIB" not in src and "gb_mock" not in src, f
+
+
+@pytest.mark.parametrize("exe,args", [("Benchmark_dwf_fp32", ["--grid", "4.4.4.4", "-Ls", "8"]), ("Test_dwf_mixedcg_prec", ["--grid", "4.4.4.4", "--seconds", "1"])])
+def test_unmodified_reference_programs_through_the_bridge_on_the_cpu_mock(mock_lib, exe, args):
+    """bridge/_build/* are the reference's own Benchmark_dwf_fp32.cc / Test_dwf_mixedcg_prec.cc compiled unmodified against the C ABI
+    (bridge/GridB200Bridge.h); preloading the mock library in front of libgridb200.so runs them here.  Their own asserts decide
+    (Dhop against the Cshift implementation, Deo + Doe = D, |x_mixed - x_double| < 1e-4); tests/test_gpu_bridge.py is the GPU run."""
+    path = os.path.join(ROOT, "bridge", "_build", exe)
+    if not os.path.exists(path):
+        pytest.skip("bridge/_build is made by __graft_entry__.build() where /root/reference is present")
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import test_gpu_bridge as tb
+    finally:
+        sys.path.pop(0)
+    p = subprocess.run([path, *args], capture_output=True, text=True, timeout=1200, env=dict(os.environ, LD_PRELOAD=mock_lib, OMP_NUM_THREADS="4"))
+    assert p.returncode == 0, (p.stdout[-3000:], p.stderr[-2000:])
+    (tb._check_benchmark if exe.startswith("Benchmark") else tb._check_mixedcg)(p.stdout)
