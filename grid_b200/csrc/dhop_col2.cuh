@@ -44,7 +44,21 @@ struct Col2Args {
   size_t hstride;               // float4 between the parity-0 and parity-1 faces
   const unsigned long long *flags;
   unsigned long long epoch;
+  // ---- optional epilogue (template parameter EPI != 0, Ls = 16, one parity): the s-space pass of the Schur CG that follows this
+  //      hop is applied to the result while it is still in registers (fermop.cu: cg_fused_rest).  The operators are the cyclic
+  //      bidiagonal-per-chirality ones (Mooee, MooeeDag, MeooeDag5D; ref: CayleyFermion5Dcache.h:43-114): y_s = d_s x_s + o_s x_{s+dir},
+  //      dir = -1 or +1 per chirality, the 16 s of a site being the 16 lanes of a half warp.
+  //      EPI 1:  w = T_aux(aux) - hop            -> out ; |w|^2 -> partials[cta]      (w = Mpc p, d = |w|^2)
+  //      EPI 2:  r += -(c/d) (T_aux(aux) + T_hop(hop))  -> e_r (out is not written) ; |r|^2 -> partials[cta]
+  const float4 *e_aux;
+  float4 *e_r;
+  float e_ad[2][16], e_ao[2][16], e_hd[2][16], e_ho[2][16];
+  int e_adir[2], e_hdir[2];
+  const double *e_c, *e_d;
+  double *e_partials;
 };
+__device__ __forceinline__ f2 shfl_f2(f2 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+__device__ __forceinline__ float norm2_f2(f2 v) { float x, y; upk(v, x, y); return x * x + y * y; }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
@@ -101,8 +115,9 @@ __device__ __forceinline__ void col2_leg_reg(const SpinorP &f, bool is_half, con
 template <int LS> constexpr size_t col2_smem_bytes() { return (size_t)(3 * COL_NSITE * 6 * LS + 3 * COL_NSITE * FAST_USTRIDE) * 16 + 64; }
 
 // MODE 0: single rank (every leg local, periodic wrap inside the local volume).  MODE 1: decomposed in z and / or t (see above).
-template <int LS, int DAG, int MODE>
+template <int LS, int DAG, int MODE, int EPI = 0>
 __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2Args a) {
+  static_assert(EPI == 0 || LS == W, "the s-space epilogues need one 4D site per 16-lane block");
   extern __shared__ __align__(128) unsigned char col_smem[];
   constexpr int PLANE = COL_NSITE * 6 * LS;                  // float4 per ring plane, field layout [block][vec k][lane]
   constexpr int UBUF = COL_NSITE * FAST_USTRIDE;
@@ -196,6 +211,23 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
   const uint32_t face_xy = xh + a.Lxh * y;
   auto hptr = [&](const float4 *base, int z) { const uint32_t i = (face_xy + zstride * (uint32_t)z) * LS + s; return base + ((size_t)(i >> LOGW) * 3 << LOGW) + (i & (W - 1)); };
 
+  // epilogue constants of this thread's s (both chiralities), the lanes of its s neighbours, the CG scalar, the norm accumulator
+  f2 e_ad[2], e_ao[2], e_hd[2], e_ho[2], e_alpha = pk(0.f, 0.f);
+  int e_anb[2] = {0, 0}, e_hnb[2] = {0, 0};
+  double e_nrm = 0;
+  if (EPI != 0) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+      e_ad[c] = pk(a.e_ad[c][s], a.e_ad[c][s]); e_ao[c] = pk(a.e_ao[c][s], a.e_ao[c][s]);
+      e_anb[c] = (lane & 16) | ((s + a.e_adir[c]) & 15);
+      if (EPI == 2) {
+        e_hd[c] = pk(a.e_hd[c][s], a.e_hd[c][s]); e_ho[c] = pk(a.e_ho[c][s], a.e_ho[c][s]);
+        e_hnb[c] = (lane & 16) | ((s + a.e_hdir[c]) & 15);
+      }
+    }
+    if (EPI == 2) { const float al = (float)(-(*a.e_c) / (*a.e_d)); e_alpha = pk(al, al); }
+  }
   mbar_wait(&bars[3], 0);
   mbar_wait(&bars[4], 0);
   int ub = 0, bm = 0;                                          // link buffer of this step; ring slot of plane z-1
@@ -269,15 +301,59 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     // ---- epilogue
     const uint32_t i = (site_xyt + zoff) * LS + s;
     const size_t offs = ((size_t)(i >> LOGW) * 6 << LOGW) + (i & (W - 1));
-    if (a.axpy[p] != nullptr) {
-      SpinorP ax;
-      load_spinor_p(ax, a.axpy[p] + offs);
-      const f2 sa = pk(a.axpy_a, a.axpy_a), sb = pk(a.axpy_b, a.axpy_b);
+    if (EPI != 0) {
+      SpinorP aux;
+      load_spinor_p(aux, a.e_aux + offs);
+      float n2 = 0.f;
+      if (EPI == 1) {
 #pragma unroll
-      for (int q = 0; q < 12; q++) res.c[q] = fma2(sa, res.c[q], mul2(sb, ax.c[q]));
+        for (int q = 0; q < 12; q++) {
+          const int c = q >= 6 ? 1 : 0;
+          const f2 y = fma2(e_ao[c], shfl_f2(aux.c[q], e_anb[c]), mul2(e_ad[c], aux.c[q]));
+          res.c[q] = fma2(pk(-1.f, -1.f), res.c[q], y);                   // w = T(aux) - hop
+          n2 += norm2_f2(res.c[q]);
+        }
+        store_spinor_p(res, a.out[p] + offs);
+      } else {
+        SpinorP r;
+        load_spinor_rw(r, a.e_r + offs);
+#pragma unroll
+        for (int q = 0; q < 12; q++) {
+          const int c = q >= 6 ? 1 : 0;
+          f2 y = fma2(e_ao[c], shfl_f2(aux.c[q], e_anb[c]), mul2(e_ad[c], aux.c[q]));
+          y = fma2(e_hd[c], res.c[q], y);
+          y = fma2(e_ho[c], shfl_f2(res.c[q], e_hnb[c]), y);               // q = T_aux(aux) + T_hop(hop)
+          r.c[q] = fma2(e_alpha, y, r.c[q]);                               // r -= (c/d) q
+          n2 += norm2_f2(r.c[q]);
+        }
+        store_spinor_p(r, a.e_r + offs);
+      }
+      e_nrm += (double)n2;
+    } else {
+      if (a.axpy[p] != nullptr) {
+        SpinorP ax;
+        load_spinor_p(ax, a.axpy[p] + offs);
+        const f2 sa = pk(a.axpy_a, a.axpy_a), sb = pk(a.axpy_b, a.axpy_b);
+#pragma unroll
+        for (int q = 0; q < 12; q++) res.c[q] = fma2(sa, res.c[q], mul2(sb, ax.c[q]));
+      }
+      store_spinor_p(res, a.out[p] + offs);
     }
-    store_spinor_p(res, a.out[p] + offs);
     bm = b0; ub = un;
+  }
+  if (EPI != 0) {
+    // one partial per CTA (fixed-shape tree); the caller's second stage adds the partials in a fixed order
+    __shared__ double e_red[NTHR / 32];
+    double v = e_nrm;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) e_red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t2 = 0;
+      for (int w = 0; w < NTHR / 32; w++) t2 += e_red[w];
+      a.e_partials[blockIdx.x] = t2;
+    }
   }
 }
 

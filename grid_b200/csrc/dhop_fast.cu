@@ -136,6 +136,21 @@ template <int LS> static void launch_col2_ls(const Col2Args &a, unsigned nblocks
   if (!dag) { if (mode) launch_col2_k(dhop_col2_kernel<LS, 0, 1>, a, nblocks, threads, smem, cluster, st); else launch_col2_k(dhop_col2_kernel<LS, 0, 0>, a, nblocks, threads, smem, cluster, st); }
   else { if (mode) launch_col2_k(dhop_col2_kernel<LS, 1, 1>, a, nblocks, threads, smem, cluster, st); else launch_col2_k(dhop_col2_kernel<LS, 1, 0>, a, nblocks, threads, smem, cluster, st); }
 }
+// the two epilogue instantiations (Ls = 16, one for each direction of the Schur operator)
+static void launch_col2_epi(const Col2Args &a, unsigned nblocks, int dag, int mode, int epi, cudaStream_t st) {
+  static bool attr_set = false;
+  const size_t smem = col2_smem_bytes<16>();
+  if (!attr_set) {
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<16, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<16, 0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<16, 1, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    GB_CUDA(cudaFuncSetAttribute(dhop_col2_kernel<16, 1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int threads = COL_NSITE * 16;
+  if (epi == 1) { if (mode) dhop_col2_kernel<16, 0, 1, 1><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<16, 0, 0, 1><<<nblocks, threads, smem, st>>>(a); }
+  else { if (mode) dhop_col2_kernel<16, 1, 1, 2><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<16, 1, 0, 2><<<nblocks, threads, smem, st>>>(a); }
+}
 bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                       const void *const ax[2], double axa, double axb, int mode, cudaStream_t st, const void *const halo[8],
                       const unsigned long long *flags, unsigned long long epoch) {
@@ -196,6 +211,24 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.flags = flags; a.epoch = epoch;
   const unsigned nblocks = (unsigned)((a.n_int + a.n_surf) * (uint32_t)nparity);
   if (nblocks == 0) return true;
+  // an s-space pass of the Schur CG parked on the operator for this hop (fermop.cu): EPI 1 rides on the plain hop, EPI 2 on the daggered one
+  a.e_aux = nullptr; a.e_r = nullptr; a.e_c = a.e_d = nullptr; a.e_partials = nullptr;
+  if (HopEpilogue *E = op->hop_epi) {
+    const bool want = E->kind != 0 && !E->applied && getenv("GB_NO_HOP_EPI") == nullptr;
+    if (want && Ls == 16 && nparity == 1 && !z_comm && ax == nullptr && dag == (E->kind == 2 ? 1 : 0) &&
+        smat_tri_onesided(op, E->Maux, a.e_ad, a.e_ao, a.e_adir) && (E->kind == 1 || smat_tri_onesided(op, E->Mhop, a.e_hd, a.e_ho, a.e_hdir))) {
+      a.e_aux = (const float4 *)E->aux->data;
+      a.e_r = E->r ? (float4 *)E->r->data : nullptr;
+      a.e_c = E->d_c; a.e_d = E->d_d;
+      a.e_partials = smat_partials_ensure(op, nblocks);
+      launch_col2_epi(a, nblocks, dag, mode, E->kind, st);
+      count_launch(op->ctx);
+      check_launch(op->ctx, "dhop_col2 + s-space epilogue");
+      smat_reduce_partials(op, nblocks, E->d_out);
+      E->applied = true;
+      return true;
+    }
+  }
   static const int env_cluster = getenv("GB_COL_CLUSTER") ? atoi(getenv("GB_COL_CLUSTER")) : 0;
   switch (Ls) {
   case 8: launch_col2_ls<8>(a, nblocks, dag, mode, env_cluster, st); break;

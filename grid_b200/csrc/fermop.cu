@@ -187,15 +187,25 @@ void cg_fused_rest(gb_fermop *op, const gb_fermion *p, gb_fermion *r, const doub
   dhop_cb(op, t1, t2, 0);
   GB_REQUIRE(smat_apply(op, op->sm_B, t2, nullptr, nullptr, 0, nullptr, t1), "smat");
   t1->cb = t2->cb;
-  dhop_cb(op, t1, t2, 0);
-  GB_REQUIRE(smat_apply_norm(op, op->sm_mooee, p, -1.0, t2, w, d_d), "smat");                 // w = Mooee p - t2 ; d = |w|^2
+  {   // w = Mooee p - Dhop t1 ; d = |w|^2 : as the hop's epilogue where the column kernel can, else hop + streaming pass
+    HopEpilogue e; e.kind = 1; e.aux = p; e.Maux = op->sm_mooee; e.d_out = d_d;
+    op->hop_epi = &e;
+    try { dhop_cb(op, t1, w, 0); } catch (...) { op->hop_epi = nullptr; throw; }
+    op->hop_epi = nullptr;
+    if (!e.applied) GB_REQUIRE(smat_apply_norm(op, op->sm_mooee, p, -1.0, w, w, d_d), "smat");
+  }
   device_global_sum(op->ctx, d_d, 1);
   w->cb = p->cb;
   dhop_cb(op, w, t2, 1);
   GB_REQUIRE(smat_apply(op, op->sm_Bdag, t2, nullptr, nullptr, 0, nullptr, t1), "smat");
   t1->cb = t2->cb;
-  dhop_cb(op, t1, t2, 1);
-  GB_REQUIRE(smat_apply_rupd(op, op->sm_mooeedag, w, op->sm_negAdag, t2, r, d_c, d_d, d_cp), "smat");   // r -= (c/d)(MooeeDag w - MeooeDag5D t2)
+  {   // r -= (c/d)(MooeeDag w - MeooeDag5D Dhop^dag t1) ; cp = |r|^2 : likewise
+    HopEpilogue e; e.kind = 2; e.aux = w; e.r = r; e.Maux = op->sm_mooeedag; e.Mhop = op->sm_negAdag; e.d_c = d_c; e.d_d = d_d; e.d_out = d_cp;
+    op->hop_epi = &e;
+    try { dhop_cb(op, t1, t2, 1); } catch (...) { op->hop_epi = nullptr; throw; }
+    op->hop_epi = nullptr;
+    if (!e.applied) GB_REQUIRE(smat_apply_rupd(op, op->sm_mooeedag, w, op->sm_negAdag, t2, r, d_c, d_d, d_cp), "smat");
+  }
   device_global_sum(op->ctx, d_cp, 1);
 }
 

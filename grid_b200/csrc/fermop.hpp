@@ -24,6 +24,21 @@ struct P2PState {
 };
 }
 
+namespace gb {
+// An s-space pass of the Schur CG folded into the hop that precedes it (dhop_col2.cuh, EPI 1 / 2).  The caller parks a request in
+// gb_fermop::hop_epi around ONE checkerboard hop; the column-sweep launch honours it where it can (fp32, Ls = 16, no x / y / z
+// decomposition, cyclic-bidiagonal operators) and sets `applied`, otherwise the hop runs plain and the caller does the pass itself.
+struct HopEpilogue {
+  int kind = 0;                                  // 1: out = T_aux(aux) - hop, |out|^2 -> d_out ; 2: r -= (c/d)(T_aux(aux) + T_hop(hop)), |r|^2 -> d_out
+  const gb_fermion *aux = nullptr;
+  gb_fermion *r = nullptr;
+  const void *Maux = nullptr, *Mhop = nullptr;   // device handles of the operators (their host copies: gb_fermop::smat_host)
+  const double *d_c = nullptr, *d_d = nullptr;
+  double *d_out = nullptr;
+  bool applied = false;
+};
+}
+
 struct gb_fermop {
   gb_grid *grid = nullptr;
   gb_context *ctx = nullptr;
@@ -58,6 +73,7 @@ struct gb_fermop {
              *sm_mooeeinvdag = nullptr, *sm_m5unit = nullptr, *sm_m5unitdag = nullptr, *sm_B = nullptr, *sm_Bdag = nullptr, *sm_negAdag = nullptr;
   std::vector<void *> smat_allocs;
   std::map<const void *, gb::SMat> smat_host;   // host copies by device pointer (the streaming kernel of smat.cu takes its coefficients from them)
+  gb::HopEpilogue *hop_epi = nullptr;   // request parked around one hop (see HopEpilogue)
   double *smat_partials = nullptr;   // per-CTA partial sums of the s-space passes that carry a reduction (smat.cu)
   size_t smat_partials_n = 0;
   // improved staggered (stag.cu): 16 scaled + phased links per site, per output parity, streamed layout
@@ -112,6 +128,10 @@ bool smat_apply_rupd(gb_fermop *op, const void *dM, const gb_fermion *x, const v
 bool smat_apply_cgupd(gb_fermop *op, const void *dM, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, gb_fermion *out, const double *d_c,
                       const double *d_d, const double *d_cp);
 void device_global_sum(gb_context *ctx, double *d_vals, int n); // context.cu: in-stream all-reduce of device scalars
+// d / o / dir of a cyclic operator that couples s only to s + dir[c] per chirality c (false if M is anything else); partial-sum buffer
+bool smat_tri_onesided(const gb_fermop *op, const void *dM, float d[2][16], float o[2][16], int dir[2]);
+double *smat_partials_ensure(gb_fermop *op, size_t n);
+void smat_reduce_partials(gb_fermop *op, size_t n, double *d_out);
 // Schur CG with the linear algebra folded into the s-space passes (fermop.cu): available for Cayley operators on the dense s-space path
 bool cg_fused_available(const gb_fermop *op);
 void cg_fused_first(gb_fermop *op, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, const double *d_c, const double *d_d, const double *d_cp);

@@ -428,6 +428,33 @@ static bool tri_extract(const SMat &m, double d[2][16], double l[2][16], double 
     }
   return true;
 }
+bool smat_tri_onesided(const gb_fermop *op, const void *dM, float d[2][16], float o[2][16], int dir[2]) {
+  auto h = op->smat_host.find(dM);
+  if (h == op->smat_host.end()) return false;
+  double dd[2][16] = {}, l[2][16] = {}, u[2][16] = {};
+  if (!tri_extract(h->second, dd, l, u)) return false;
+  for (int c = 0; c < 2; c++) {
+    bool has_l = false, has_u = false;
+    for (int i = 0; i < 16; i++) { has_l |= l[c][i] != 0.0; has_u |= u[c][i] != 0.0; }
+    if (has_l && has_u) return false;
+    dir[c] = has_u ? +1 : -1;
+    for (int i = 0; i < 16; i++) { d[c][i] = (float)dd[c][i]; o[c][i] = (float)(has_u ? u[c][i] : l[c][i]); }
+  }
+  return true;
+}
+double *smat_partials_ensure(gb_fermop *op, size_t n) {
+  if (op->smat_partials_n < n) {
+    if (op->smat_partials) cudaFree(op->smat_partials);
+    op->smat_partials = nullptr; op->smat_partials_n = 0;
+    GB_CUDA(cudaMalloc(&op->smat_partials, n * sizeof(double)));
+    op->smat_partials_n = n;
+  }
+  return op->smat_partials;
+}
+void smat_reduce_partials(gb_fermop *op, size_t n, double *d_out) {
+  smat_reduce_kernel<<<1, 256, 0, op->ctx->stream>>>(op->smat_partials, (int)n, d_out);
+  count_launch(op->ctx);
+}
 template <class T, int EPI> static void stri_launch(gb_fermop *op, STriArgs<T> &a, double *d_out) {
   gb_context *ctx = op->ctx;
   const unsigned blocks = (unsigned)std::min<int64_t>((a.n + STRI_THREADS - 1) / STRI_THREADS, (int64_t)ctx->sm_count * 10);

@@ -36,9 +36,13 @@ def test_fused_cg_matches_unfused_and_oracle(ctx, dims, Ls, kind, b, c, prec, to
     src = gb.LatticeFermion(grid, Ls, prec, gb.HALF).import_lex(h)
     src.set_checkerboard(gb.Odd)
     res = {}
-    for form in ("fused", "unfused"):
+    for form in ("fused", "unfused", "fused_no_hop_epilogue"):
+        # fused = the default: at fp32 / Ls 16 the w = Mooee p - Dhop(..) and the residual-update passes ride on the hops as epilogues of
+        # the column kernel (dhop_col2.cuh EPI 1 / 2); GB_NO_HOP_EPI=1 keeps them as separate streaming passes
         if form == "unfused":
             os.environ["GB_CG_UNFUSED"] = "1"
+        if form == "fused_no_hop_epilogue":
+            os.environ["GB_NO_HOP_EPI"] = "1"
         try:
             sol = gb.LatticeFermion(grid, Ls, prec, gb.HALF).zero()
             cg = gb.ConjugateGradient(tol, 10000)
@@ -47,7 +51,13 @@ def test_fused_cg_matches_unfused_and_oracle(ctx, dims, Ls, kind, b, c, prec, to
             res[form] = (cg.IterationsToComplete, cg.TrueResidual, sol.export_lex(), (ctx.launch_count() - l0) / cg.IterationsToComplete)
         finally:
             os.environ.pop("GB_CG_UNFUSED", None)
+            os.environ.pop("GB_NO_HOP_EPI", None)
     (it_f, tr_f, x_f, lf), (it_u, tr_u, x_u, lu) = res["fused"], res["unfused"]
+    it_s, tr_s, x_s, ls_ = res["fused_no_hop_epilogue"]
+    assert abs(it_s - it_u) <= max(1, 0.02 * it_u) and tr_s < 1.5 * tol
+    assert np.linalg.norm((x_s - x_u).ravel()) / np.linalg.norm(x_u.ravel()) < (1e-4 if prec == gb.F32 else 1e-9)
+    if prec == gb.F32 and Ls == 16 and dims[0] % 8 == 0 and not os.environ.get("GB_TEST_MOCK_LIB"):
+        assert lf < ls_, (lf, ls_)                     # the hop epilogues were taken: two launches fewer per iteration
     assert abs(it_f - it_u) <= max(1, 0.02 * it_u), (it_f, it_u)
     assert tr_f < 1.5 * tol and tr_u < 1.5 * tol
     rel = np.linalg.norm((x_f - x_u).ravel()) / np.linalg.norm(x_u.ravel())
