@@ -533,6 +533,14 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
     // local legs, and surface CTAs acquire the neighbours' flags and add the off-node legs
     const bool try_fused = op->overlap_comms && !op->no_fused && op->prec == GB_F32 && !op->disable_fast;
     unsigned long long epoch = 0;
+    bool hop_sends_t = false;
+    // semi-fused: after the pack+send kernel the hop does the local legs and, in its last (surface) CTAs, acquires the
+    // neighbours' flags and adds the halo legs -- no exterior pass, nothing read-modify-written (GB_SEMIFUSED=0 disables).
+    // Default engine: the column-sweep kernel (dhop_col2.cuh) over the planes whose z legs are local, t-surface columns last,
+    // plus the micro-block semi-fused kernel on the two z-surface planes when z is split (GB_COL2_DECOMP=0: micro-block
+    // kernel over the whole volume, the round-1 form).
+    static const bool semifused = !(getenv("GB_SEMIFUSED") && atoi(getenv("GB_SEMIFUSED")) == 0);
+    static const bool col2_decomp = !(getenv("GB_COL2_DECOMP") && atoi(getenv("GB_COL2_DECOMP")) == 0);
     static const bool pack_on_comm_stream = getenv("GB_PACK_STREAM") && atoi(getenv("GB_PACK_STREAM")) != 0;
     bool pack_pending = false;
     if (try_fused) {
@@ -556,7 +564,14 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       GB_CUDA(cudaEventRecord(ctx->ev_comm, ctx->comm_stream));
       pack_pending = true;
     } else {
-      epoch = p2p_pack_send(op, in, parity_out_first, nparity, dag, ctx->stream);
+      // default: the column-sweep hop sends its own t faces (no re-read of them by the pack kernel), the pack kernel the rest
+      hop_sends_t = op->overlap_comms && semifused && col2_decomp && !op->no_semifused && ((op->comm_dim_mask >> 3) & 1) && g->ldims[3] >= 4 &&
+                    dhop_col2_applicable(op, 1) && !(getenv("GB_HOP_SENDS_T") && atoi(getenv("GB_HOP_SENDS_T")) == 0);
+      epoch = p2p_next_epoch(op);
+      {
+        GB_TRACE("Gather");
+        p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, ctx->stream, hop_sends_t);
+      }
     }
     struct PackJoin {   // runs on every exit path below
       gb_context *ctx; bool on;
@@ -579,13 +594,18 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       const int ip = 1 - parity_out_first;
       for (int i = 0; i < 8; i++) if (a.halo[i]) a.halo[i] = (const char *)a.halo[i] - (size_t)ip * op->halo_parity_stride[i & 3] * 16;
     }
-    // semi-fused: after the pack+send kernel the hop does the local legs and, in its last (surface) CTAs, acquires the
-    // neighbours' flags and adds the halo legs -- no exterior pass, nothing read-modify-written (GB_SEMIFUSED=0 disables).
-    // Default engine: the column-sweep kernel (dhop_col2.cuh) over the planes whose z legs are local, t-surface columns last,
-    // plus the micro-block semi-fused kernel on the two z-surface planes when z is split (GB_COL2_DECOMP=0: micro-block
-    // kernel over the whole volume, the round-1 form).
-    static const bool semifused = !(getenv("GB_SEMIFUSED") && atoi(getenv("GB_SEMIFUSED")) == 0);
-    static const bool col2_decomp = !(getenv("GB_COL2_DECOMP") && atoi(getenv("GB_COL2_DECOMP")) == 0);
+    if (hop_sends_t) {
+      Col2Send snd;
+      p2p_fill_send_t(op, epoch, snd.dst, snd.flag, &snd.counter);
+      GB_REQUIRE(dhop_col2_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream, a.halo, a.flags, epoch, &snd),
+                 "column-sweep hop with hop-sent t faces");
+      if ((op->comm_dim_mask >> 2) & 1) {
+        const bool z0 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 5, ctx->stream, a.halo, a.flags, epoch);
+        const bool z1 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 6, ctx->stream, a.halo, a.flags, epoch);
+        GB_REQUIRE(z0 && z1, "z-surface planes of the column-sweep hop");
+      }
+      return;
+    }
     if (op->overlap_comms && semifused && !op->no_semifused && op->prec == GB_F32 && !op->disable_fast && !(op->comm_dim_mask & 3)) {
       if (col2_decomp && dhop_col2_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream, a.halo, a.flags, epoch)) {
         if ((op->comm_dim_mask >> 2) & 1) {

@@ -44,6 +44,17 @@ struct Col2Args {
   size_t hstride;               // float4 between the parity-0 and parity-1 faces
   const unsigned long long *flags;
   unsigned long long epoch;
+  // ---- t faces sent by the hop itself (MODE 1, t decomposed, Lt >= 4): the CTAs of slice t = 1 hold every input spinor of plane 0 in
+  //      registers (their backward t neighbour), those of slice Lt-2 every spinor of plane Lt-1: they project them with the RECEIVER's
+  //      projector and store the half spinors into the neighbour rank's receive buffer, so the pack kernel never re-reads the t faces.
+  //      The last of these sender CTAs publishes the two t epoch flags.  Sender CTAs are interior CTAs (they wait for nobody) and
+  //      precede the surface CTAs in the grid, so a surface CTA spinning on a flag never keeps a sender from being scheduled.
+  int send_on;
+  float4 *send_dst[2];          // [0]: plane 0 -> the backward neighbour's point-3 buffer ; [1]: plane Lt-1 -> the forward neighbour's point-7 buffer
+  size_t send_pstride;          // float4 between the parity slots of a face buffer (full-lattice hops)
+  unsigned long long *send_flag[2];
+  unsigned int *send_counter;
+  uint32_t n_senders;
   // ---- optional epilogue (template parameter EPI != 0, Ls = 16, one parity): the s-space pass of the Schur CG that follows this
   //      hop is applied to the result while it is still in registers (fermop.cu: cg_fused_rest).  The operators are the cyclic
   //      bidiagonal-per-chirality ones (Mooee, MooeeDag, MeooeDag5D; ref: CayleyFermion5Dcache.h:43-114): y_s = d_s x_s + o_s x_{s+dir},
@@ -208,6 +219,7 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     if (tm_halo) hb_tm = a.halo_tm + (size_t)ip * a.hstride;
     if (tp_halo) hb_tp = a.halo_tp + (size_t)ip * a.hstride;
   }
+  const bool snd_m = MODE == 1 && a.send_on && t == 1, snd_p = MODE == 1 && a.send_on && (int)t == a.Lt - 2;
   const uint32_t face_xy = xh + a.Lxh * y;
   auto hptr = [&](const float4 *base, int z) { const uint32_t i = (face_xy + zstride * (uint32_t)z) * LS + s; return base + ((size_t)(i >> LOGW) * 3 << LOGW) + (i & (W - 1)); };
 
@@ -271,6 +283,23 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
 #pragma unroll
       for (int q = 0; q < 3; q++) { const float4 v = h[q << LOGW]; ftp.c[2 * q] = pk(v.x, v.y); ftp.c[2 * q + 1] = pk(v.z, v.w); }
     } else load_spinor_p(ftp, gptr(site_tp + zoff));
+    if (MODE == 1 && (snd_m || snd_p)) {
+      // the neighbour rank's t leg of this face site: forward leg (projector sign of FWD = 1) for plane 0, backward leg for plane Lt-1
+      const uint32_t i = (face_xy + zstride * (uint32_t)z) * LS + s;
+      const size_t ho = ((size_t)(i >> LOGW) * 3 << LOGW) + (i & (W - 1)) + (a.nparity == 1 ? 0 : (size_t)ip * a.send_pstride);
+      if (snd_m) {
+        HalfP h; proj_p<3, (DAG ? +1 : -1)>(h, ftm);
+        float4 *d = a.send_dst[0] + ho;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { float4 v; upk(h.c[2 * q], v.x, v.y); upk(h.c[2 * q + 1], v.z, v.w); d[q << LOGW] = v; }
+      }
+      if (snd_p) {
+        HalfP h; proj_p<3, (DAG ? -1 : +1)>(h, ftp);
+        float4 *d = a.send_dst[1] + ho;
+#pragma unroll
+        for (int q = 0; q < 3; q++) { float4 v; upk(h.c[2 * q], v.x, v.y); upk(h.c[2 * q + 1], v.z, v.w); d[q << LOGW] = v; }
+      }
+    }
     const int pb = (p + a.origin_parity + y + z + (int)t) & 1;
     SpinorP res;
 #pragma unroll
@@ -340,6 +369,20 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
       store_spinor_p(res, a.out[p] + offs);
     }
     bm = b0; ub = un;
+  }
+  if (MODE == 1 && (snd_m || snd_p)) {
+    // publish: fence this CTA's peer stores; the last sender CTA of the launch writes the t epoch flags into the neighbours' memory
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int prev = atomicAdd(a.send_counter, 1u);
+      if (prev == a.n_senders - 1) {
+        *a.send_counter = 0;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.send_flag[0]), "l"(a.epoch) : "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.send_flag[1]), "l"(a.epoch) : "memory");
+      }
+    }
   }
   if (EPI != 0) {
     // one partial per CTA (fixed-shape tree); the caller's second stage adds the partials in a fixed order

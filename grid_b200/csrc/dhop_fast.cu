@@ -151,21 +151,28 @@ static void launch_col2_epi(const Col2Args &a, unsigned nblocks, int dag, int mo
   if (epi == 1) { if (mode) dhop_col2_kernel<16, 0, 1, 1><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<16, 0, 0, 1><<<nblocks, threads, smem, st>>>(a); }
   else { if (mode) dhop_col2_kernel<16, 1, 1, 2><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<16, 1, 0, 2><<<nblocks, threads, smem, st>>>(a); }
 }
+bool dhop_col2_applicable(const gb_fermop *op, int mode) {
+  static const bool disabled = getenv("GB_NO_COL") != nullptr || (getenv("GB_COL2") && atoi(getenv("GB_COL2")) == 0);
+  const gb_grid *g = op->grid;
+  const int Ls = op->Ls;
+  if (disabled || op->no_col || op->prec != GB_F32 || op->disable_fast || !(Ls == 8 || Ls == 12 || Ls == 16)) return false;
+  if ((g->ldims[0] / 2) % 4 || g->ldims[1] % 4) return false;
+  if (mode == 0 && op->comm_dim_mask) return false;
+  if (mode == 1 && (op->comm_dim_mask & 3)) return false;
+  return true;
+}
 bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                       const void *const ax[2], double axa, double axb, int mode, cudaStream_t st, const void *const halo[8],
-                      const unsigned long long *flags, unsigned long long epoch) {
-  static const bool disabled = getenv("GB_NO_COL") != nullptr || (getenv("GB_COL2") && atoi(getenv("GB_COL2")) == 0);
+                      const unsigned long long *flags, unsigned long long epoch, const Col2Send *snd) {
   static const int env_n = getenv("GB_COL_N") ? atoi(getenv("GB_COL_N")) : 0;
   // rasterisation: 1 (default) = t fastest, then the y blocks, then the x blocks: the y-edge rows a column shares with its y
   // neighbours (half a fetch per site) are then 32 CTAs apart in launch order instead of 128 and are re-hit in L2
   static const int env_raster = getenv("GB_COL_RASTER") ? atoi(getenv("GB_COL_RASTER")) : 1;
   const gb_grid *g = op->grid;
   const int Ls = op->Ls;
-  if (disabled || op->no_col || op->prec != GB_F32 || op->disable_fast || !(Ls == 8 || Ls == 12 || Ls == 16)) return false;
+  if (!dhop_col2_applicable(op, mode)) return false;
   const int Lxh = g->ldims[0] / 2, Ly = g->ldims[1], Lz = g->ldims[2], Lt = g->ldims[3];
-  if (Lxh % 4 || Ly % 4) return false;
-  if (mode == 0 && op->comm_dim_mask) return false;
-  if (mode == 1 && ((op->comm_dim_mask & 3) || halo == nullptr || flags == nullptr)) return false;
+  if (mode == 1 && (halo == nullptr || flags == nullptr)) return false;
   const bool z_comm = mode == 1 && ((op->comm_dim_mask >> 2) & 1), t_comm = mode == 1 && ((op->comm_dim_mask >> 3) & 1);
   Col2Args a;
   const size_t per_parity = (size_t)g->V4cb * 8 * 5;
@@ -209,6 +216,16 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.halo_tm = halo ? (const float4 *)halo[7] : nullptr; a.halo_tp = halo ? (const float4 *)halo[3] : nullptr;
   a.hstride = op->halo_parity_stride[3];
   a.flags = flags; a.epoch = epoch;
+  a.send_on = 0; a.send_dst[0] = a.send_dst[1] = nullptr; a.send_flag[0] = a.send_flag[1] = nullptr; a.send_counter = nullptr; a.n_senders = 0;
+  a.send_pstride = op->halo_parity_stride[3];
+  if (snd != nullptr) {
+    GB_REQUIRE(t_comm && Lt >= 4, "hop-sent t faces need a t-decomposed lattice with Lt >= 4");
+    a.send_on = 1;
+    a.send_dst[0] = (float4 *)snd->dst[0]; a.send_dst[1] = (float4 *)snd->dst[1];
+    a.send_flag[0] = snd->flag[0]; a.send_flag[1] = snd->flag[1];
+    a.send_counter = snd->counter;
+    a.n_senders = 2u * cols_per_t * (uint32_t)nparity;      // the columns of slices t = 1 and t = Lt-2
+  }
   const unsigned nblocks = (unsigned)((a.n_int + a.n_surf) * (uint32_t)nparity);
   if (nblocks == 0) return true;
   // an s-space pass of the Schur CG parked on the operator for this hop (fermop.cu): EPI 1 rides on the plain hop, EPI 2 on the daggered one

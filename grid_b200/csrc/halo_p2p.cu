@@ -21,6 +21,7 @@ struct PackItem {
   void *dst;         // peer-mapped destination (this epoch, this point, this parity slot)
   uint32_t nface;    // face sites (cb)
   int mu, fwd, ip;
+  int zedge;         // t faces only: pack just the planes z = 0 and z = Lz-1 (the rest of the face is sent by the hop kernel itself)
 };
 struct PackSendArgs {
   PackItem item[16];
@@ -45,9 +46,10 @@ __device__ __forceinline__ void pack_body(const PackSendArgs &a, const PackItem 
     y = 2 * yhalf + ypar; xh = slice >> 1;
   } else if (MU == 1) { xh = r % a.Lxh; r /= a.Lxh; z = r % a.Lz; t = r / a.Lz; y = slice; }
   else if (MU == 2) { xh = r % a.Lxh; r /= a.Lxh; y = r % a.Ly; t = r / a.Ly; z = slice; }
-  else { xh = r % a.Lxh; r /= a.Lxh; y = r % a.Ly; z = r / a.Ly; t = slice; }
+  else { xh = r % a.Lxh; r /= a.Lxh; y = r % a.Ly; z = r / a.Ly; t = slice; if (it.zedge) z = z ? a.Lz - 1 : 0; }
   const uint32_t site = xh + a.Lxh * (y + a.Ly * (z + a.Lz * t));
   const uint32_t i = site * a.Ls + s;
+  if (MU == 3 && it.zedge) q = (xh + a.Lxh * (y + a.Ly * z)) * a.Ls + s;    // position inside the whole face
   SpinorReg<T> f;
   load_spinor(f, (const V *)it.src + ((size_t)(i >> LOGW) * P::NV << LOGW) + (i & (W - 1)));
   constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
@@ -120,8 +122,8 @@ bool p2p_setup(gb_fermop *op) {
   if (ok) {
     GB_CUDA(cudaMalloc(&S.recv_base, S.recv_bytes));
     GB_CUDA(cudaMemset(S.recv_base, 0, S.recv_bytes));
-    GB_CUDA(cudaMalloc(&S.d_counter, sizeof(unsigned int)));
-    GB_CUDA(cudaMemset(S.d_counter, 0, sizeof(unsigned int)));
+    GB_CUDA(cudaMalloc(&S.d_counter, 2 * sizeof(unsigned int)));     // [0] pack kernel, [1] sender CTAs of the hop kernel
+    GB_CUDA(cudaMemset(S.d_counter, 0, 2 * sizeof(unsigned int)));
     GB_CUDA(cudaDeviceSynchronize());
   }
   // does any halo leave this rank?  (GB_SELF_HALO routes undecomposed dimensions through the same path: the "peer" is this rank)
@@ -184,10 +186,13 @@ unsigned long long p2p_next_epoch(gb_fermop *op) { return ++op->p2p.epoch; }
 unsigned long long p2p_pack_send(gb_fermop *op, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st) {
   GB_TRACE("Gather");   // pack (project) + peer stores: the reference's Gather + CommunicateBegin
   const unsigned long long epoch = p2p_next_epoch(op);
-  p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, st);
+  p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, st, false);
   return epoch;
 }
-void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st) {
+// hop_sends_t: the column-sweep hop that follows sends the t faces itself (dhop_col2.cuh, send_on) -- all of them when z is not
+// decomposed, all but the planes z = 0 and z = Lz-1 (which its columns do not visit) when it is; the t flags are then the hop's to set
+void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st,
+                   bool hop_sends_t) {
   P2PState &S = op->p2p;
   gb_context *ctx = op->ctx;
   const gb_grid *g = op->grid;
@@ -199,24 +204,28 @@ void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in
   a.counter = S.d_counter;
   a.epoch = epoch;
   uint32_t maxn = 0;
+  const bool z_comm = (op->comm_dim_mask >> 2) & 1;
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
-    const uint32_t nface = (uint32_t)(g->V4cb / g->ldims[mu]);
+    const bool hop_face = hop_sends_t && mu == 3;
+    if (hop_face && !z_comm) continue;
+    const uint32_t nface = hop_face ? (uint32_t)(2 * (g->ldims[0] / 2) * g->ldims[1]) : (uint32_t)(g->V4cb / g->ldims[mu]);
     maxn = std::max(maxn, nface * (uint32_t)op->Ls);
     for (int fwd = 0; fwd < 2; fwd++) {
       const int point = fwd ? mu : mu + 4;
-      a.flag[point] = (unsigned long long *)((char *)S.peer_base[point] + S.flags_off) + (epoch & 1) * 8 + point;
+      if (!hop_face) a.flag[point] = (unsigned long long *)((char *)S.peer_base[point] + S.flags_off) + (epoch & 1) * 8 + point;
       for (int j = 0; j < nparity; j++) {
         const int po = parity_out_first ^ j, ip = 1 - po;
         const int slot = nparity == 1 ? 0 : ip;
         PackItem &it = a.item[a.nitems++];
         it.src = in[ip];
         it.dst = (char *)S.peer_base[point] + eoff + S.pt_off[point] + (size_t)slot * op->halo_parity_stride[mu] * 16;
-        it.nface = nface; it.mu = mu; it.fwd = fwd; it.ip = ip;
+        it.nface = nface; it.mu = mu; it.fwd = fwd; it.ip = ip; it.zedge = hop_face ? 1 : 0;
       }
     }
   }
   // GB_PACK_CTAS=<n>: at most n CTAs per face item (grid-stride loop inside), 0 = one CTA per 256 face elements
   static const unsigned pack_ctas = getenv("GB_PACK_CTAS") ? (unsigned)atoi(getenv("GB_PACK_CTAS")) : 0u;
+  if (a.nitems == 0) return;                     // every face of this hop is sent by the hop kernel
   unsigned gx = (maxn + 255) / 256;
   if (pack_ctas > 0 && gx > pack_ctas) gx = pack_ctas;
   dim3 grid(gx, a.nitems);
@@ -226,6 +235,17 @@ void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in
   check_launch(ctx, "pack_send");
 }
 
+// sender-side pointers of this epoch for a hop that sends its own t faces: destination buffers and flags in the neighbours' memory
+void p2p_fill_send_t(gb_fermop *op, unsigned long long epoch, void *dst[2], unsigned long long *flag[2], unsigned int **counter) {
+  P2PState &S = op->p2p;
+  const size_t eoff = (size_t)(epoch & 1) * S.epoch_stride;
+  const int points[2] = {3, 7};   // plane 0 feeds the backward neighbour's forward t leg (point 3), plane Lt-1 the forward neighbour's point 7
+  for (int k = 0; k < 2; k++) {
+    dst[k] = (char *)S.peer_base[points[k]] + eoff + S.pt_off[points[k]];
+    flag[k] = (unsigned long long *)((char *)S.peer_base[points[k]] + S.flags_off) + (epoch & 1) * 8 + points[k];
+  }
+  *counter = S.d_counter + 1;
+}
 // receive-side pointers of this epoch for the hop kernels
 void p2p_fill_halo(gb_fermop *op, unsigned long long epoch, const void *halo[8], const unsigned long long **flags) {
   P2PState &S = op->p2p;
