@@ -91,10 +91,16 @@ def check_all_entries(grid, D, orc, shape, prec, tag):
 def test_self_halo_hops_match_the_oracle(ctx, shape, mask, prec):
     sh = SHAPES[shape]
     grid, D, orc = make(ctx, sh, prec, MASKS[mask])
-    # 1 = default overlapped form (semi-fused launch where it exists), 2 = interior + exterior slabs, 0 = serial comms
-    for overlap in (1, 2, 0):
+    # 1 = default overlapped form (semi-fused launch where it exists; on t splits the column kernel projects and sends the t faces
+    # itself, GB_HOP_SENDS_T=0 leaves them to the pack kernel), 2 = interior + exterior slabs, 0 = serial comms
+    for overlap, env in ((1, {}), (1, {"GB_HOP_SENDS_T": "0"}), (2, {}), (0, {})):
         D.set_overlap(overlap)
-        check_all_entries(grid, D, orc, sh, prec, (shape, mask, overlap))
+        os.environ.update(env)
+        try:
+            check_all_entries(grid, D, orc, sh, prec, (shape, mask, overlap, env))
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
 
 
 @pytest.mark.parametrize("prec", [gb.F32, gb.F64], ids=["f32", "f64"])
@@ -116,17 +122,24 @@ def test_self_halo_antiperiodic_phases(ctx):
 
 
 def test_self_halo_semi_fused_launch_is_taken(ctx):
-    """fp32, t split, Ls 16: the default form is ONE hop launch after the pack kernel (2 launches per Dhop), the interior +
-    exterior form needs more (pack, interior, two slabs per parity pair)."""
+    """fp32, t split, Ls 16: the default form is ONE launch per Dhop (the column kernel sends its own t faces: no pack kernel), two
+    with the t faces left to the pack kernel (GB_HOP_SENDS_T=0); the interior + exterior form needs more (pack, interior, two slabs
+    per parity pair)."""
     sh = SHAPES["dwf16"]
     grid, D, orc = make(ctx, sh, gb.F32, MASKS["t"])
     fin, fout = gb.LatticeFermion(grid, 16, gb.F32).zero(), gb.LatticeFermion(grid, 16, gb.F32)
     D.set_overlap(1)
     n0 = ctx.launch_count(); D.Dhop(fin, fout, 0); n1 = ctx.launch_count()
+    os.environ["GB_HOP_SENDS_T"] = "0"
+    try:
+        D.Dhop(fin, fout, 0); n1b = ctx.launch_count()
+    finally:
+        os.environ.pop("GB_HOP_SENDS_T", None)
     D.set_overlap(2)
     D.Dhop(fin, fout, 0); n2 = ctx.launch_count()
-    assert n1 - n0 == 2, n1 - n0
-    assert n2 - n1 > 2, n2 - n1
+    assert n1 - n0 == 1, n1 - n0
+    assert n1b - n1 == 2, n1b - n1
+    assert n2 - n1b > 2, n2 - n1b
 
 
 def test_self_halo_cg_and_mixed_cg_match_the_oracle(ctx):
