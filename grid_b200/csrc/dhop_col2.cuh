@@ -54,9 +54,7 @@ struct Col2Args {
   size_t send_pstride;          // float4 between the parity slots of a face buffer (full-lattice hops)
   unsigned long long *send_flag[2];
   unsigned int *send_counter;
-  uint32_t n_senders, n_send_seg;   // sender CTAs of the launch ; of one parity segment (they come first in it)
-  int send_log2r;                   // every 2^send_log2r-th CTA at the head of the segment is a sender
-  FastDiv dnt_rest;                 // the other interior slices t = 2 ... Lt-3
+  uint32_t n_senders;               // sender CTAs of the launch
   // ---- optional epilogue (template parameter EPI != 0, Ls = 16, one parity): the s-space pass of the Schur CG that follows this
   //      hop is applied to the result while it is still in registers (fermop.cu: cg_fused_rest).  The operators are the cyclic
   //      bidiagonal-per-chirality ones (Mooee, MooeeDag, MeooeDag5D; ref: CayleyFermion5Dcache.h:43-114): y_s = d_s x_s + o_s x_{s+dir},
@@ -156,16 +154,11 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
   bool sender_seg = false;
   if (!surf) {
     if (MODE == 1 && a.send_on) {
-      // hop-sent t faces: the columns of the two sender slices (t = 1, Lt-2) come first inside the interior segment, so that the
-      // neighbours' flags are published long before their surface CTAs (the last of the grid) ask for them
-      // ... and interleaved 1 : 2^send_log2r - 1 with other interior CTAs, so that the NVLink stores of the faces are spread over a
-      // longer stretch of the launch instead of saturating the link while every SM runs a sender
-      const uint32_t q = b >> a.send_log2r;
-      if ((b & ((1u << a.send_log2r) - 1u)) == 0 && q < a.n_send_seg) { sender_seg = true; t = q & 1u; b = q >> 1; }
-      else {
-        const uint32_t before = min((b + (1u << a.send_log2r) - 1u) >> a.send_log2r, a.n_send_seg);   // sender positions below b
-        b -= before; a.dnt_rest.divmod(b, b, t);
-      }
+      // hop-sent t faces: t still runs fastest (the t neighbours of a column block stay side by side in the schedule, which is what
+      // lets their re-reads hit L2 -- putting the sender slices in a segment of their own cost 0.8 GB of extra DRAM reads per hop at
+      // 64.64.32.16 x 16), but inside each column block the two sender slices t = 1 and t = Lt-2 come first
+      a.dnt_int.divmod(b, b, t);
+      sender_seg = t < 2;
     } else if (a.tb) a.dtb.divmod(b, b, t);
     else a.dnt_int.divmod(b, b, t);
   } else { a.dnt_surf.divmod(b, b, t); t = t == 0 ? a.Lt - 1 : 0; }        // surface segment: t = Lt-1, then t = 0
@@ -174,7 +167,7 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
   else { a.dNzc.divmod(b, b, zc); a.dNyo.divmod(b, b, yo); a.dNxo.divmod(b, tg, xo); }   // z chunks of a column side by side
   if (!surf) {
     if (a.tb && a.raster != 2) { const uint32_t ntg = (uint32_t)(a.nt_int / a.tb); tg = zc % ntg; zc /= ntg; }   // t groups outside x / y, inside z chunks
-    if (MODE == 1 && a.send_on) t = sender_seg ? (t ? (uint32_t)a.Lt - 2 : 1u) : t + 2;
+    if (MODE == 1 && a.send_on) t = sender_seg ? (t ? (uint32_t)a.Lt - 2 : 1u) : t;      // slices 1, Lt-2, 2, 3, ..., Lt-3
     else t += (a.tb ? tg * a.tb : 0) + a.t_int0;
   }
   const int xh = xo * 4 + xl, y = yo * 4 + yl, zfirst = a.z0 + zc * a.N;

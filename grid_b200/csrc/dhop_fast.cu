@@ -216,7 +216,6 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.halo_tm = halo ? (const float4 *)halo[7] : nullptr; a.halo_tp = halo ? (const float4 *)halo[3] : nullptr;
   a.hstride = op->halo_parity_stride[3];
   a.flags = flags; a.epoch = epoch;
-  a.n_send_seg = 0; a.dnt_rest = FastDiv(1); a.send_log2r = 0;
   a.send_on = 0; a.send_dst[0] = a.send_dst[1] = nullptr; a.send_flag[0] = a.send_flag[1] = nullptr; a.send_counter = nullptr; a.n_senders = 0;
   a.send_pstride = op->halo_parity_stride[3];
   if (snd != nullptr) {
@@ -226,11 +225,6 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
     a.send_flag[0] = snd->flag[0]; a.send_flag[1] = snd->flag[1];
     a.send_counter = snd->counter;
     a.n_senders = 2u * cols_per_t * (uint32_t)nparity;      // the columns of slices t = 1 and t = Lt-2
-    a.n_send_seg = 2u * cols_per_t;
-    static const int env_il = getenv("GB_SEND_INTERLEAVE") ? atoi(getenv("GB_SEND_INTERLEAVE")) : 2;   // log2 of the interleave ratio
-    a.send_log2r = 0;
-    while (a.send_log2r < env_il && ((uint64_t)a.n_send_seg << (a.send_log2r + 1)) <= (uint64_t)a.n_int) a.send_log2r++;
-    a.dnt_rest = FastDiv((uint32_t)std::max(1, a.nt_int - 2));
     a.tb = 0;
   }
   const unsigned nblocks = (unsigned)((a.n_int + a.n_surf) * (uint32_t)nparity);
