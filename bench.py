@@ -390,7 +390,7 @@ def main():
     Dw = gb.DomainWallFermion(U, grid, Ls, 0.1, 1.8)
     if args.no_overlap:
         Dw.set_overlap(False)
-    hop_form = "single rank" if world == 1 else ("serial comms" if args.no_overlap else "overlapped: pack+send, one hop launch that acquires the halos in its surface CTAs")
+    hop_form = "single rank" if world == 1 else ("serial comms" if args.no_overlap else "overlapped: one hop launch that sends its own t faces and acquires the halos in its surface CTAs (z faces by a pack kernel in front of it)")
     src = gb.LatticeFermion(grid, Ls, gb.F32).random(2)
     n2 = gb.norm2(src)
     gb.scale(src, 1.0 / np.sqrt(n2), src)     # ref: Benchmark_dwf_fp32.cc:175-176
@@ -606,7 +606,7 @@ def main():
     if rank == 0:
         bps = alg_bytes_per_site(Ls)
         achieved = bps * sites_local / (ms_step * 1e-3) / 1e9       # per GPU
-        kernel = "gb::dhop_col2_kernel<16,0,0>" if world == 1 else "gb::dhop_col2_kernel<16,0,1> (+ pack_send_kernel; z-surface planes by dhop_fast_kernel<16,0,2> where z is split)"
+        kernel = "gb::dhop_col2_kernel<16,0,0>" if world == 1 else "gb::dhop_col2_kernel<16,0,1> (projects and sends its own t faces; + pack_send_kernel for the z faces where z is split)"
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": workload_config(args), "hop_form": hop_form,

@@ -570,7 +570,8 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       epoch = p2p_next_epoch(op);
       {
         GB_TRACE("Gather");
-        p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, ctx->stream, hop_sends_t);
+        const bool z_in = ((op->comm_dim_mask >> 2) & 1) && dhop_col2_zplanes_inkernel();
+        p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, ctx->stream, hop_sends_t ? (z_in ? 2 : 1) : 0);
       }
     }
     struct PackJoin {   // runs on every exit path below
@@ -599,7 +600,7 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       p2p_fill_send_t(op, epoch, snd.dst, snd.flag, &snd.counter);
       GB_REQUIRE(dhop_col2_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream, a.halo, a.flags, epoch, &snd),
                  "column-sweep hop with hop-sent t faces");
-      if ((op->comm_dim_mask >> 2) & 1) {
+      if (((op->comm_dim_mask >> 2) & 1) && !dhop_col2_zplanes_inkernel()) {
         const bool z0 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 5, ctx->stream, a.halo, a.flags, epoch);
         const bool z1 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 6, ctx->stream, a.halo, a.flags, epoch);
         GB_REQUIRE(z0 && z1, "z-surface planes of the column-sweep hop");
@@ -608,7 +609,7 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
     }
     if (op->overlap_comms && semifused && !op->no_semifused && op->prec == GB_F32 && !op->disable_fast && !(op->comm_dim_mask & 3)) {
       if (col2_decomp && dhop_col2_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream, a.halo, a.flags, epoch)) {
-        if ((op->comm_dim_mask >> 2) & 1) {
+        if (((op->comm_dim_mask >> 2) & 1) && !dhop_col2_zplanes_inkernel()) {
           const bool z0 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 5, ctx->stream, a.halo, a.flags, epoch);
           const bool z1 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 6, ctx->stream, a.halo, a.flags, epoch);
           GB_REQUIRE(z0 && z1, "z-surface planes of the column-sweep hop");

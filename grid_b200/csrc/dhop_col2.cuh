@@ -42,6 +42,11 @@ struct Col2Args {
   int t_comm;
   const float4 *halo_tm, *halo_tp;
   size_t hstride;               // float4 between the parity-0 and parity-1 faces
+  // off-node z legs (MODE 1, z_inkernel): the columns sweep ALL planes; the z- leg of plane 0 and the z+ leg of plane Lz-1 come from
+  // the receive buffers of points 6 / 2 (written by the neighbours' pack kernels, which precede their hop launches)
+  int z_inkernel;
+  const float4 *halo_zm, *halo_zp;
+  size_t hstride_z;
   const unsigned long long *flags;
   unsigned long long epoch;
   // ---- t faces sent by the hop itself (MODE 1, t decomposed, Lt >= 4): the CTAs of slice t = 1 hold every input spinor of plane 0 in
@@ -96,6 +101,17 @@ __device__ __forceinline__ void col2_leg(const float4 *p, const float4 *Usm, Spi
 // still waits in the shared-memory pipe: measured on the B200 as one stale spinor in ~2 of 1000 launches at 32^4 x 16
 // (scripts/hop_stress.py; zero with a CTA-wide barrier instead).  So the arrive's ADDRESS is made to depend on one register of
 // each load (an LDS.128 delivers its four registers together): (bits & a.zero) is 0, which the compiler cannot know.
+// a z leg whose source is the already projected half spinor of an off-node neighbour (3 vecs in the halo blocking)
+template <int DAG, int FWD>
+__device__ __forceinline__ void col2_leg_zhalo(const float4 *h, const float4 *Usm, SpinorP &res) {
+  constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
+  HalfP chi, Uchi; LinkS u;
+#pragma unroll
+  for (int q = 0; q < 3; q++) { const float4 v = h[q << LOGW]; chi.c[2 * q] = pk(v.x, v.y); chi.c[2 * q + 1] = pk(v.z, v.w); }
+  lds_link(u, Usm + (FWD ? 2 : 6) * 5);
+  mult_p(Uchi, u, chi);
+  recon_p<2, SIGN>(res, Uchi);
+}
 template <int DAG>
 __device__ __forceinline__ void col2_leg_zm_arrive(const float4 *p, const float4 *Usm, SpinorP &res, uint64_t *bar, uint32_t zero, bool arrive) {
   constexpr int SIGN = DAG ? -1 : +1;
@@ -197,11 +213,16 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     mbar_init(&bars[6], NTHR);
   }
   const bool tm_halo = MODE == 1 && a.t_comm && t == 0, tp_halo = MODE == 1 && a.t_comm && (int)t == a.Lt - 1;
-  if (MODE == 1 && surf) {
-    // acquire the t neighbours' epoch flags (peer-written, system scope) before any thread touches the receive buffers
-    if (threadIdx.x == 3 || threadIdx.x == 7) {
+  // columns that start at plane 0 / end at plane Lz-1 of a z-decomposed lattice take that plane's outward z leg from the receive buffer
+  const bool zm_halo = MODE == 1 && a.z_inkernel && zfirst == 0, zp_halo = MODE == 1 && a.z_inkernel && zfirst + a.N == a.Lz;
+  if (MODE == 1 && (surf || zm_halo || zp_halo)) {
+    // acquire the neighbours' epoch flags (peer-written, system scope) before any thread touches the receive buffers: points 3 / 7
+    // (t; set by the neighbours' sender CTAs or pack kernels) in the t-surface CTAs, points 2 / 6 (z; pack kernels) where a z halo is read
+    const int pt = threadIdx.x;
+    const bool mine_to_wait = (surf && (pt == 3 || pt == 7)) || (zp_halo && pt == 2) || (zm_halo && pt == 6);
+    if (mine_to_wait) {
       unsigned long long v;
-      do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flags + threadIdx.x) : "memory"); } while (v < a.epoch);
+      do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.flags + pt) : "memory"); } while (v < a.epoch);
     }
   }
   __syncthreads();
@@ -233,6 +254,14 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
   const uint32_t face_xy = xh + a.Lxh * y;
   auto hptr = [&](const float4 *base, int z) { const uint32_t i = (face_xy + zstride * (uint32_t)z) * LS + s; return base + ((size_t)(i >> LOGW) * 3 << LOGW) + (i & (W - 1)); };
 
+  // off-node z legs: face index = cb index with z removed; this thread's half spinor in the point-6 / point-2 receive buffer
+  const float4 *hz_m = nullptr, *hz_p = nullptr;
+  if (MODE == 1 && (zm_halo || zp_halo)) {
+    const uint32_t i = (face_xy + zstride * t) * LS + s;                 // (xh + Lxh (y + Ly t)) Ls + s
+    const size_t ho = ((size_t)(i >> LOGW) * 3 << LOGW) + (i & (W - 1)) + (size_t)ip * a.hstride_z;
+    if (zm_halo) hz_m = a.halo_zm + ho;
+    if (zp_halo) hz_p = a.halo_zp + ho;
+  }
   // epilogue constants of this thread's s (both chiralities), the lanes of its s neighbours, the CG scalar, the norm accumulator
   f2 e_ad[2], e_ao[2], e_hd[2], e_ho[2], e_alpha = pk(0.f, 0.f);
   int e_anb[2] = {0, 0}, e_hnb[2] = {0, 0};
@@ -318,7 +347,10 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     const float4 *Us = Usm + ub * UBUF + sl * FAST_USTRIDE;
     const float4 *cur = mine + b0 * PLANE;                       // own element, plane z
     // ---- z- : own element of plane z-1; then tell the issuers that this thread is done with that slot
-    col2_leg_zm_arrive<DAG>(mine + bm * PLANE, Us, res, &bars[6], a.zero, !a.cta_sync);
+    if (MODE == 1 && zm_halo && k == 0) {                          // (CTA-uniform) plane 0 of a z-decomposed lattice: the halo leg; nothing
+      col2_leg_zhalo<DAG, 0>(hz_m, Us, res);                       // of ring slot bm is read, so the arrive needs no dependency
+      if (!a.cta_sync) mbar_arrive(&bars[6]);
+    } else col2_leg_zm_arrive<DAG>(mine + bm * PLANE, Us, res, &bars[6], a.zero, !a.cta_sync);
     // ---- x legs: the neighbour with the same x/2 index is this thread's own ring element; the other one is the adjacent
     //      slot or, at the block edge, a global load
     if (pb) {
@@ -335,8 +367,9 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     col2_leg_reg<DAG, 3, 0>(ftm, MODE == 1 && tm_halo, Us, res);
     col2_leg_reg<DAG, 3, 1>(ftp, MODE == 1 && tp_halo, Us, res);
     // ---- z+ : wait for plane z+1 (bulk copies issued at the top of this step), read the own element
-    mbar_wait(&bars[3 + bp], (uint32_t)((k + 2) / 3) & 1);
-    col2_leg<DAG, 2, 1>(mine + bp * PLANE, Us, res);
+    mbar_wait(&bars[3 + bp], (uint32_t)((k + 2) / 3) & 1);        // (observed in every step, also when the plane is not used)
+    if (MODE == 1 && zp_halo && k == a.N - 1) col2_leg_zhalo<DAG, 1>(hz_p, Us, res);
+    else col2_leg<DAG, 2, 1>(mine + bp * PLANE, Us, res);
     // ---- epilogue
     const uint32_t i = (site_xyt + zoff) * LS + s;
     const size_t offs = ((size_t)(i >> LOGW) * 6 << LOGW) + (i & (W - 1));

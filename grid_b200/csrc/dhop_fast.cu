@@ -151,6 +151,7 @@ static void launch_col2_epi(const Col2Args &a, unsigned nblocks, int dag, int mo
   if (epi == 1) { if (mode) dhop_col2_kernel<16, 0, 1, 1><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<16, 0, 0, 1><<<nblocks, threads, smem, st>>>(a); }
   else { if (mode) dhop_col2_kernel<16, 1, 1, 2><<<nblocks, threads, smem, st>>>(a); else dhop_col2_kernel<16, 1, 0, 2><<<nblocks, threads, smem, st>>>(a); }
 }
+bool dhop_col2_zplanes_inkernel() { return !(getenv("GB_COL2_ZPLANES") && atoi(getenv("GB_COL2_ZPLANES")) == 0); }
 bool dhop_col2_applicable(const gb_fermop *op, int mode) {
   static const bool disabled = getenv("GB_NO_COL") != nullptr || (getenv("GB_COL2") && atoi(getenv("GB_COL2")) == 0);
   const gb_grid *g = op->grid;
@@ -183,7 +184,14 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   }
   a.axpy_a = (float)axa; a.axpy_b = (float)axb;
   a.Lxh = Lxh; a.Ly = Ly; a.Lz = Lz; a.Lt = Lt;
-  if (z_comm) {                       // planes 0 and Lz-1 have an off-node z leg: the caller's box launches take them
+  // z-decomposed lattices: by default the columns sweep all planes and take the outward z legs of planes 0 and Lz-1 from the receive
+  // buffers themselves (z_inkernel); GB_COL2_ZPLANES=0 restores the round-2a form (columns over planes 1 ... Lz-2, the two surface planes
+  // by box launches of the micro-block kernel)
+  const bool z_inkernel = z_comm && dhop_col2_zplanes_inkernel() && Lz >= 2;
+  a.z_inkernel = z_inkernel ? 1 : 0;
+  a.halo_zm = halo ? (const float4 *)halo[6] : nullptr; a.halo_zp = halo ? (const float4 *)halo[2] : nullptr;
+  a.hstride_z = op->halo_parity_stride[2];
+  if (z_comm && !z_inkernel) {        // planes 0 and Lz-1 have an off-node z leg: the caller's box launches take them
     a.z0 = 1; a.N = Lz - 2; a.nzc = 1;
     if (a.N <= 0) return true;        // nothing but surface planes
   } else {
@@ -233,7 +241,7 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   a.e_aux = nullptr; a.e_r = nullptr; a.e_c = a.e_d = nullptr; a.e_partials = nullptr;
   if (HopEpilogue *E = op->hop_epi) {
     const bool want = E->kind != 0 && !E->applied && getenv("GB_NO_HOP_EPI") == nullptr;
-    if (want && Ls == 16 && nparity == 1 && !z_comm && ax == nullptr && dag == (E->kind == 2 ? 1 : 0) &&
+    if (want && Ls == 16 && nparity == 1 && !(z_comm && !z_inkernel) && ax == nullptr && dag == (E->kind == 2 ? 1 : 0) &&
         smat_tri_onesided(op, E->Maux, a.e_ad, a.e_ao, a.e_adir) && (E->kind == 1 || smat_tri_onesided(op, E->Mhop, a.e_hd, a.e_ho, a.e_hdir))) {
       a.e_aux = (const float4 *)E->aux->data;
       a.e_r = E->r ? (float4 *)E->r->data : nullptr;

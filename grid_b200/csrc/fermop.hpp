@@ -97,6 +97,7 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
 // t faces sent by the hop itself (dhop_col2.cuh send_on): destinations and flags in the neighbours' memory, last-sender counter
 struct Col2Send { void *dst[2] = {nullptr, nullptr}; unsigned long long *flag[2] = {nullptr, nullptr}; unsigned int *counter = nullptr; };
 bool dhop_col2_applicable(const gb_fermop *op, int mode);   // would dhop_col2_launch take this operator in this mode?
+bool dhop_col2_zplanes_inkernel();                          // z-decomposed lattices: the columns take the z-surface planes themselves
 bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,
                       const void *const ax[2], double axa, double axb, int mode, cudaStream_t st, const void *const halo[8],
                       const unsigned long long *flags, unsigned long long epoch, const Col2Send *snd = nullptr);
@@ -105,7 +106,7 @@ bool p2p_setup(gb_fermop *op);
 void p2p_teardown(gb_fermop *op);
 unsigned long long p2p_next_epoch(gb_fermop *op);
 void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st,
-                   bool hop_sends_t = false);
+                   int hop_sends_t = 0);
 void p2p_fill_send_t(gb_fermop *op, unsigned long long epoch, void *dst[2], unsigned long long *flag[2], unsigned int **counter);
 unsigned long long p2p_pack_send(gb_fermop *op, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st);
 void p2p_fill_halo(gb_fermop *op, unsigned long long epoch, const void *halo[8], const unsigned long long **flags);

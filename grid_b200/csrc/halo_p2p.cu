@@ -186,13 +186,14 @@ unsigned long long p2p_next_epoch(gb_fermop *op) { return ++op->p2p.epoch; }
 unsigned long long p2p_pack_send(gb_fermop *op, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st) {
   GB_TRACE("Gather");   // pack (project) + peer stores: the reference's Gather + CommunicateBegin
   const unsigned long long epoch = p2p_next_epoch(op);
-  p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, st, false);
+  p2p_send_only(op, epoch, in, parity_out_first, nparity, dag, st, 0);
   return epoch;
 }
-// hop_sends_t: the column-sweep hop that follows sends the t faces itself (dhop_col2.cuh, send_on) -- all of them when z is not
-// decomposed, all but the planes z = 0 and z = Lz-1 (which its columns do not visit) when it is; the t flags are then the hop's to set
+// hop_sends_t: the column-sweep hop that follows sends the t faces itself (dhop_col2.cuh, send_on) -- 2: all of them (its columns
+// visit every plane), 1: all but the planes z = 0 and z = Lz-1 of a z-decomposed lattice (columns over planes 1 ... Lz-2), which this
+// kernel then packs; the t flags are the hop's to set in both cases
 void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in[2], int parity_out_first, int nparity, int dag, cudaStream_t st,
-                   bool hop_sends_t) {
+                   int hop_sends_t) {
   P2PState &S = op->p2p;
   gb_context *ctx = op->ctx;
   const gb_grid *g = op->grid;
@@ -206,8 +207,8 @@ void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in
   uint32_t maxn = 0;
   const bool z_comm = (op->comm_dim_mask >> 2) & 1;
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
-    const bool hop_face = hop_sends_t && mu == 3;
-    if (hop_face && !z_comm) continue;
+    const bool hop_face = hop_sends_t != 0 && mu == 3;
+    if (hop_face && (!z_comm || hop_sends_t == 2)) continue;
     const uint32_t nface = hop_face ? (uint32_t)(2 * (g->ldims[0] / 2) * g->ldims[1]) : (uint32_t)(g->V4cb / g->ldims[mu]);
     maxn = std::max(maxn, nface * (uint32_t)op->Ls);
     for (int fwd = 0; fwd < 2; fwd++) {

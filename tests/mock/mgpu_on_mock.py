@@ -189,7 +189,7 @@ def main():
     lib = ctypes.CDLL(sys.argv[1])
     lib.gb_mock_coop_launches.restype = ctypes.c_long
     lib.gb_mock_coop_launches.argtypes = [ctypes.c_char_p]
-    before = {k: lib.gb_mock_coop_launches(k) for k in (b"dhop_fast_kernel<LS, 0, 2>", b"dhop_fast_kernel<LS, 1, 2>", b"dhop_fast_kernel<LS, 0, 1>", b"pack_send_kernel", b"smat_kernel")}
+    before = {k: lib.gb_mock_coop_launches(k) for k in (b"dhop_col2_kernel_fn", b"dhop_fast_kernel<LS, 0, 1>", b"pack_send_kernel", b"smat_kernel")}
     for mpi in ((1, 1, 2, 2), (1, 1, 1, 4), (1, 2, 1, 1), (2, 1, 1, 1)):
         errs += wilson_like(mpi, tuple(l * m for l, m in zip((8, 4, 4, 4), mpi)), "dwf", 8)
         print(f"mpi {mpi} tuned kernels: done, {len(fails) + len(errs)} problems so far", flush=True)
