@@ -25,7 +25,9 @@ e2e_cg     = the call HMC makes: gauge field + source from pinned host memory in
 config4    = BASELINE configs[3]: Dhop (+ halo-exchange bandwidth + mixed CG) at the local volume 64.64.32.16 x Ls16 per GPU
              (global 64^4 on 8 GPUs as 1.1.2.4): the weak-scaling series whose 8-vs-1 ratio the north star asks for.
 config5    = BASELINE configs[4]: improved staggered Dhop fp32 at 48^4 (global; split 1.1.2.4 on 8 GPUs).
-At N > 1 the decomposed hop is first compared per site with the CPU oracle on a small global lattice (parity_check).
+At N > 1 the decomposed path is first compared with the CPU oracle on a small global lattice (parity_check): the hop per site (fp32, +-dag,
+tolerance 1e-6) and a Schur conjugate-gradient solve (fp64: iteration count, true residual, solution) -- the driver-side parity of the
+halo exchange and of the reductions summed over ranks.
 """
 import argparse
 import json
@@ -374,8 +376,48 @@ def main():
             ref = decomp.scatter(orc.apply(po.OP_DHOP, xg, dag=dag), pg, mpi, rank, inner=pLs)
             a = pout.export_lex().reshape(ref.shape[0], -1).astype(np.complex128); r = ref.reshape(ref.shape[0], -1)
             errs[f"Dhop dag{dag}"] = max_over_ranks(float(np.max(np.linalg.norm(a - r, axis=1) / np.linalg.norm(r, axis=1))))
+        # ... and of the decomposed Schur CG (hops with halos, s-space passes, reductions summed over ranks by ncclAllReduce in-stream):
+        # iteration count, true residual and the solution itself against the oracle's ConjugateGradient on the global lattice
+        cg_par, cg_ok = {}, True
+        try:
+            cLs = 8
+            Mf = gb.MobiusFermion(gb.LatticeGaugeField(pgrid, gb.F64).import_lex(decomp.scatter(Ug, pg, mpi, rank)), pgrid, cLs, 0.1, 1.8, 1.5, 0.5)
+            sg = syn.random_fermion(pg, cLs, seed=13)
+            sfull = gb.LatticeFermion(pgrid, cLs, gb.F64).import_lex(decomp.scatter(sg, pg, mpi, rank, inner=cLs))
+            so_ = gb.LatticeFermion(pgrid, cLs, gb.F64, gb.HALF)
+            gb.pickCheckerboard(gb.Odd, so_, sfull)
+            xo_ = gb.LatticeFermion(pgrid, cLs, gb.F64, gb.HALF).zero()
+            pcg = gb.ConjugateGradient(1e-8, 10000)
+            pcg(gb.SchurDiagMooeeOperator(Mf), so_, xo_)
+            xfull = gb.LatticeFermion(pgrid, cLs, gb.F64).zero()
+            gb.setCheckerboard(xfull, xo_)
+            cg_par = {"iterations": pcg.IterationsToComplete, "true_residual": pcg.TrueResidual}
+            ref_info = [None]
+            if rank == 0:
+                try:                                                        # whatever happens here, the broadcast below is reached
+                    orc2 = po.OracleOp(1, pg, cLs, mass=0.1, M5=1.8, b=1.5, c=0.5, prec=1)
+                    orc2.import_gauge(Ug)
+                    x_ref, info = orc2.cg(1, po.pick_checkerboard(pg, cLs, 1, sg), 1e-8, 10000)
+                    xr = np.zeros_like(sg)
+                    po.set_checkerboard(pg, cLs, 1, xr, x_ref)
+                    ref_info = [(info, xr)]
+                    del orc2
+                except Exception as e:
+                    ref_info = [(f"{type(e).__name__}: {e}", None)]
+            dist.broadcast_object_list(ref_info, src=0)
+            info, xref_full = ref_info[0]
+            if xref_full is None:
+                raise RuntimeError(f"oracle side of the check failed on rank 0: {info}")
+            mine = xfull.export_lex().reshape(-1); want = decomp.scatter(xref_full, pg, mpi, rank, inner=cLs).reshape(-1)
+            num = max_over_ranks(float(np.linalg.norm(mine - want))); den = float(np.linalg.norm(xref_full.ravel()))
+            cg_par.update(oracle_iterations=info["iterations"], oracle_true_residual=info["true_residual"], solution_rel_err=num / den * np.sqrt(world))
+            cg_ok = abs(cg_par["iterations"] - info["iterations"]) <= max(1, 0.02 * info["iterations"]) and cg_par["solution_rel_err"] < 1e-6 and cg_par["true_residual"] < 1.5e-8
+        except Exception as e:                                          # a fault of the check itself must not cost the bench line
+            cg_par = {"error": f"{type(e).__name__}: {e}"}
         parity_check = {"against": "CPU oracle (fp64) on the global lattice", "global_lattice": list(pg), "Ls": pLs, "mpi": list(mpi),
-                        "max_site_rel_err": errs, "tolerance": 1e-6, "ok": all(e < 1e-6 for e in errs.values())}
+                        "max_site_rel_err": errs, "tolerance": 1e-6,
+                        "schur_cg": dict(cg_par, what="ConjugateGradient on SchurDiagMooeeOperator(MobiusFermion fp64, Ls 8) to 1e-8, decomposed over the ranks"),
+                        "ok": all(e < 1e-6 for e in errs.values()) and cg_ok}
         del pD, pin, pout, pgrid, orc, Ug, xg
         if not parity_check["ok"]:
             if rank == 0:

@@ -1,0 +1,11 @@
+#!/bin/bash
+# GPU call (2 GPUs): the bench line with the decomposed-CG parity check in front.
+set -u
+out=gpurun_out/r3a; mkdir -p $out
+( time timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus 2 --steps 20 --warmup 5 ) > $out/bench_n2.json 2> $out/bench_n2.err
+echo "bench n2 rc $?"; python - <<PY
+import json
+l=json.loads([x for x in open("$out/bench_n2.json").read().splitlines() if x.startswith("{")][-1])
+print(json.dumps(l["parity_check"])[:1500]); print(l["ms_per_step"], l["config4"]["ms_per_step"], l["cg"]["ms_per_iteration"], l["config4"]["cg"]["ms_per_iteration"])
+PY
+tail -3 $out/bench_n2.err
