@@ -829,23 +829,28 @@ __global__ void fermion_slab_transfer_kernel(typename Prec<TD>::vec *dev, TH *sl
 
 namespace {
 struct HostPipe {          // per-context scratch of the pipelined path (grow-only)
-  cudaStream_t h2d = nullptr, d2h = nullptr;
-  void *stage_in[2] = {nullptr, nullptr}, *stage_out[2] = {nullptr, nullptr};
+  // four streams: the two copy engines never wait for a layout kernel (those run on xin / xout between them and the compute stream)
+  cudaStream_t h2d = nullptr, d2h = nullptr, xin = nullptr, xout = nullptr;
+  static constexpr int NB = 3;                               // staging buffers per direction
+  void *stage_in[NB] = {nullptr, nullptr, nullptr}, *stage_out[NB] = {nullptr, nullptr, nullptr};
   size_t stage_bytes = 0;
-  std::vector<cudaEvent_t> ev_in, ev_hop, ev_out_free[2];
-  cudaEvent_t ev_in_free[2] = {nullptr, nullptr}, ev_packed[2] = {nullptr, nullptr}, ev_done = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_hop;
+  cudaEvent_t ev_copied[NB] = {}, ev_xin_done[NB] = {}, ev_packed[NB] = {}, ev_out_copied[NB] = {}, ev_done = nullptr;
 };
 HostPipe &host_pipe(gb_context *ctx, size_t slab_bytes, int nslab) {
   static HostPipe P;       // one context per process in this library's usage (one process per GPU)
   if (!P.h2d) {
     GB_CUDA(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking));
     GB_CUDA(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) { GB_CUDA(cudaEventCreateWithFlags(&P.ev_in_free[i], cudaEventDisableTiming)); GB_CUDA(cudaEventCreateWithFlags(&P.ev_packed[i], cudaEventDisableTiming)); }
+    GB_CUDA(cudaStreamCreateWithFlags(&P.xin, cudaStreamNonBlocking));
+    GB_CUDA(cudaStreamCreateWithFlags(&P.xout, cudaStreamNonBlocking));
+    for (int i = 0; i < HostPipe::NB; i++)
+      for (cudaEvent_t *e : {&P.ev_copied[i], &P.ev_xin_done[i], &P.ev_packed[i], &P.ev_out_copied[i]}) GB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     GB_CUDA(cudaEventCreateWithFlags(&P.ev_done, cudaEventDisableTiming));
   }
   if (P.stage_bytes < slab_bytes) {
     GB_CUDA(cudaDeviceSynchronize());
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < HostPipe::NB; i++) {
       if (P.stage_in[i]) cudaFree(P.stage_in[i]);
       if (P.stage_out[i]) cudaFree(P.stage_out[i]);
       GB_CUDA(cudaMalloc(&P.stage_in[i], slab_bytes));
@@ -904,13 +909,19 @@ extern "C" int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_ou
   GB_CUDA(cudaEventRecord(P.ev_done, ctx->stream));
   GB_CUDA(cudaStreamWaitEvent(P.h2d, P.ev_done, 0));
   GB_CUDA(cudaStreamWaitEvent(P.d2h, P.ev_done, 0));
+  GB_CUDA(cudaStreamWaitEvent(P.xin, P.ev_done, 0));
+  GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_done, 0));
+  int nin = 0, nout = 0;
   auto import_slice = [&](int t) {
-    const int b = t & 1;
+    const int b = nin++ % HostPipe::NB;
+    GB_CUDA(cudaStreamWaitEvent(P.h2d, P.ev_xin_done[b], 0));          // the layout kernel that last read this staging buffer
     GB_CUDA(cudaMemcpyAsync(P.stage_in[b], (const char *)host_in + (size_t)t * slab_bytes, slab_bytes, cudaMemcpyHostToDevice, P.h2d));
-    slab_transfer<0>(ctx, fin, P.stage_in[b], host_prec, t, P.h2d);   // same stream: the next copy into this buffer is ordered after it
-    GB_CUDA(cudaEventRecord(P.ev_in[t], P.h2d));
+    GB_CUDA(cudaEventRecord(P.ev_copied[b], P.h2d));
+    GB_CUDA(cudaStreamWaitEvent(P.xin, P.ev_copied[b], 0));
+    slab_transfer<0>(ctx, fin, P.stage_in[b], host_prec, t, P.xin);
+    GB_CUDA(cudaEventRecord(P.ev_in[t], P.xin));
+    GB_CUDA(cudaEventRecord(P.ev_xin_done[b], P.xin));
   };
-  int nout = 0;
   auto hop_and_export = [&](int t) {
     // slice t needs input slices t-1, t, t+1 (periodic)
     const int tm = t == 0 ? Lt - 1 : t - 1, tp = t == Lt - 1 ? 0 : t + 1;
@@ -919,14 +930,21 @@ extern "C" int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_ou
     GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_in[tp], 0));
     dhop_tslab(op, ib, ob, dag, t, 1, ctx->stream);
     GB_CUDA(cudaEventRecord(P.ev_hop[t], ctx->stream));
-    const int b = nout++ & 1;
-    GB_CUDA(cudaStreamWaitEvent(P.d2h, P.ev_hop[t], 0));
-    slab_transfer<1>(ctx, fout, P.stage_out[b], host_prec, t, P.d2h);
+    const int b = nout++ % HostPipe::NB;
+    GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_hop[t], 0));
+    GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_out_copied[b], 0));       // the D2H copy that last read this staging buffer
+    slab_transfer<1>(ctx, fout, P.stage_out[b], host_prec, t, P.xout);
+    GB_CUDA(cudaEventRecord(P.ev_packed[b], P.xout));
+    GB_CUDA(cudaStreamWaitEvent(P.d2h, P.ev_packed[b], 0));
     GB_CUDA(cudaMemcpyAsync((char *)host_out + (size_t)t * slab_bytes, P.stage_out[b], slab_bytes, cudaMemcpyDeviceToHost, P.d2h));
+    GB_CUDA(cudaEventRecord(P.ev_out_copied[b], P.d2h));
   };
-  import_slice(0); import_slice(1);
-  for (int t = 1; t < Lt - 1; t++) { import_slice(t + 1); hop_and_export(t); }
-  hop_and_export(0); hop_and_export(Lt - 1);
+  // slice Lt-1 goes in first (slice 0 needs it across the periodic boundary), so that every slice but the last can be finished as
+  // soon as its forward neighbour has arrived and only ONE hop + D2H is left when the H2D stream runs dry
+  import_slice(Lt - 1); import_slice(0); import_slice(1);
+  hop_and_export(0);
+  for (int t = 1; t < Lt - 2; t++) { import_slice(t + 1); hop_and_export(t); }
+  hop_and_export(Lt - 2); hop_and_export(Lt - 1);
   GB_CUDA(cudaEventRecord(P.ev_done, P.d2h));
   GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_done, 0));
   GB_CUDA(cudaStreamSynchronize(P.d2h));

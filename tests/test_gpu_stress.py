@@ -77,3 +77,26 @@ def test_conjugate_gradient_walks_the_same_path_every_time(setup):
         runs.append((cg.IterationsToComplete, cg.TrueResidual, hashlib.sha1(x.export_lex().tobytes()).hexdigest()))
     assert len(set(runs)) == 1, runs
     assert runs[0][1] < 1.1e-5, runs[0]
+
+
+def test_decomposed_hop_forms_are_bit_reproducible(setup):
+    """the multi-rank launch forms on one GPU (GB_SELF_HALO: faces exchanged with this rank itself): t split (the column kernel sends
+    its own t faces, surface CTAs acquire the flags) and z+t split (plus the pack kernel for the z faces and the in-kernel z-surface
+    planes) -- 1500 launches each, every result compared with the first"""
+    import os
+    ctx, grid, D, src, so, U = setup
+    for mask in (8, 12):
+        os.environ["GB_SELF_HALO"] = str(mask)
+        try:
+            Dh = gb.MobiusFermion(U, grid, LS, 0.1, 1.8, 1.5, 0.5)
+            a, b = gb.LatticeFermion(grid, LS, gb.F32, gb.HALF), gb.LatticeFermion(grid, LS, gb.F32, gb.HALF)
+            Dh.DhopEO(so, a, 0)                          # (the peer-to-peer state is created by the first hop, while the switch is set)
+        finally:
+            os.environ.pop("GB_SELF_HALO", None)
+        bad = _repeat(lambda o: Dh.DhopEO(so, o, 0), a, b, 1500)
+        assert not bad, (mask, len(bad), bad[:5])
+        # and it is the periodic hop: same result as the single-rank kernel up to rounding of the summation order
+        D.DhopEO(so, b, 0)
+        gb.axpy(b, -1.0, a, b)
+        assert gb.norm2(b) < 1e-10 * gb.norm2(a), mask
+        del Dh, a, b
