@@ -37,6 +37,8 @@ struct Col2Args {
   FastDiv dnt_int, dnt_surf, dNxo, dNyo, dtb, dNzc;
   int nparity, first_parity, origin_parity;
   int cta_sync;                 // debugging switch (GB_COL2_SYNC=1): a CTA-wide barrier per step instead of the "z- leg done" mbarrier
+  int hints;                    // cache hints (GB_COL_HINTS bit mask): 1 = streaming (evict-first) stores of the result, 2 = evict-first
+                                // L2 policy on the link copies (each link is read once per hop), 4 = evict-last on the ring-plane copies
   uint32_t zero;                // always 0, but only the host knows: lets the kernel build register dependencies ptxas cannot fold
   // off-node t legs (MODE 1): receive buffers of the backward (point 7) and forward (point 3) t leg, epoch flags
   int t_comm;
@@ -76,6 +78,18 @@ struct Col2Args {
 __device__ __forceinline__ f2 shfl_f2(f2 v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ float norm2_f2(f2 v) { float x, y; upk(v, x, y); return x * x + y * y; }
 
+__device__ __forceinline__ void bulk_g2s_hint(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   (uint32_t)__cvta_generic_to_shared(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"((uint32_t)__cvta_generic_to_shared(bar)), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ uint64_t l2_policy_evict_last() { uint64_t p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p; }
+__device__ __forceinline__ void store_spinor_stream(const SpinorP &f, float4 *p) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) { float4 v; upk(f.c[2 * k], v.x, v.y); upk(f.c[2 * k + 1], v.z, v.w); __stcs(p + (k << LOGW), v); }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
 }
@@ -236,7 +250,10 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
     bulk_g2s(row_dst, row_src(wrapz(zfirst - 1)), ROW_BYTES, &bars[3]);
     bulk_g2s(row_dst + PLANE, row_src(zfirst_w), ROW_BYTES, &bars[4]);
   }
-  if (issuer) bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zfirst_w) * 40, 640, &bars[0]);
+  if (issuer) {
+    if (a.hints & 2) bulk_g2s_hint(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zfirst_w) * 40, 640, &bars[0], l2_policy_evict_first());
+    else bulk_g2s(Usm + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zfirst_w) * 40, 640, &bars[0]);
+  }
 
   const uint32_t site_tm = site_xyt + (t == 0 ? tstride * (a.Lt - 1) : 0u - tstride);
   const uint32_t site_tp = site_xyt + ((int)t == a.Lt - 1 ? 0u - tstride * (a.Lt - 1) : tstride);
@@ -302,13 +319,17 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
         if (k + 1 < a.N) mbar_expect_tx(&bars[un], COL_NSITE * 640);
       }
       if (row_issuer) {
-        bulk_g2s(row_dst + bp * PLANE, row_src(zp), ROW_BYTES, &bars[3 + bp]);
+        if (a.hints & 4) bulk_g2s_hint(row_dst + bp * PLANE, row_src(zp), ROW_BYTES, &bars[3 + bp], l2_policy_evict_last());
+        else bulk_g2s(row_dst + bp * PLANE, row_src(zp), ROW_BYTES, &bars[3 + bp]);
         if (a.l2pf && k + 1 < a.N) {
           const int zpp = zp + 1 == a.Lz ? 0 : zp + 1;
           asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row_src(zpp)), "r"(ROW_BYTES) : "memory");
         }
       }
-      if (k + 1 < a.N) bulk_g2s(Usm + un * UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zp) * 40, 640, &bars[un]);
+      if (k + 1 < a.N) {
+        if (a.hints & 2) bulk_g2s_hint(Usm + un * UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zp) * 40, 640, &bars[un], l2_policy_evict_first());
+        else bulk_g2s(Usm + un * UBUF + sl * FAST_USTRIDE, a.U[p] + (size_t)(site_xyt + zstride * zp) * 40, 640, &bars[un]);
+      }
     }
     // ---- t neighbours into registers now, used after the shared-memory legs
     SpinorP ftm, ftp;
@@ -409,7 +430,8 @@ __global__ void __launch_bounds__(COL_NSITE *LS, 2) dhop_col2_kernel(const Col2A
 #pragma unroll
         for (int q = 0; q < 12; q++) res.c[q] = fma2(sa, res.c[q], mul2(sb, ax.c[q]));
       }
-      store_spinor_p(res, a.out[p] + offs);
+      if (a.hints & 1) store_spinor_stream(res, a.out[p] + offs);
+      else store_spinor_p(res, a.out[p] + offs);
     }
     bm = b0; ub = un;
   }

@@ -219,6 +219,8 @@ bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2]
   static const int env_sync = getenv("GB_COL2_SYNC") ? atoi(getenv("GB_COL2_SYNC")) : 0;
   a.cta_sync = env_sync;
   a.zero = 0;
+  static const int env_hints = getenv("GB_COL_HINTS") ? atoi(getenv("GB_COL_HINTS")) : 0;
+  a.hints = env_hints;
   a.nparity = nparity; a.first_parity = parity_out_first;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
   a.halo_tm = halo ? (const float4 *)halo[7] : nullptr; a.halo_tp = halo ? (const float4 *)halo[3] : nullptr;

@@ -27,6 +27,7 @@ inline double2 make_double2(double a, double b) { return {a, b}; }
 inline int4 make_int4(int a, int b, int c, int d) { return {a, b, c, d}; }
 template <class T> inline T __ldg(const T *p) { return *p; }
 template <class T> inline T __ldcs(const T *p) { return *p; }
+template <class T> inline void __stcs(T *p, T v) { *p = v; }
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 

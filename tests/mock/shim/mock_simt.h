@@ -31,6 +31,7 @@ void mbar_complete_tx(uint64_t *bar, uint32_t bytes);
 void mbar_arrive(uint64_t *bar);
 void mbar_wait(uint64_t *bar, uint32_t parity);
 inline void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) { std::memcpy(smem_dst, gsrc, bytes); mbar_complete_tx(bar, bytes); }
+inline void bulk_g2s_hint(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar, uint64_t) { bulk_g2s(smem_dst, gsrc, bytes, bar); }
 inline void cp_async16(void *smem_dst, const void *gsrc) { std::memcpy(smem_dst, gsrc, 16); }
 inline void cp_async_arrive(uint64_t *bar) { mbar_arrive(bar); }   // the copies of this thread have already landed
 

@@ -49,7 +49,7 @@ def split_top(s):
 
 
 # functions of the product that are nothing but a PTX instruction: their bodies become calls of the emulation in shim/mock_simt.h
-ASM_WRAPPERS = ["pk", "upk", "fma2", "mul2", "add2", "sub2", "mbar_init", "mbar_expect_tx", "bulk_g2s", "mbar_wait", "cp_async16", "cp_async_arrive", "mbar_arrive"]
+ASM_WRAPPERS = ["pk", "upk", "fma2", "mul2", "add2", "sub2", "mbar_init", "mbar_expect_tx", "bulk_g2s", "bulk_g2s_hint", "mbar_wait", "cp_async16", "cp_async_arrive", "mbar_arrive"]
 # kernels whose threads cooperate (shared memory, barriers, shuffles): run block by block on fibres (shim/mock_simt.h)
 COOPERATIVE = ["dhop_fast_kernel", "dhop_col_kernel", "dhop_col2_kernel", "dhop_col2_kernel_fn", "smat_kernel", "smat_reduce_kernel", "stri_kernel", "pack_send_kernel"]
 # kernels that only sometimes need it: C++ condition on the (single) kernel argument.  The generic hopping kernel makes threads 0..7
