@@ -129,6 +129,12 @@ void fermion_check_same(const gb_fermion *a, const gb_fermion *b) {
   GB_REQUIRE(a && b, "null field");
   GB_REQUIRE(a->grid == b->grid && a->Ls == b->Ls && a->kind == b->kind && a->prec == b->prec && a->ncomplex == b->ncomplex, "fields are not conformable");
 }
+// two INPUT fields of a binary operation on the red-black grid must live on the same checkerboard
+// (ref: conformable(), Grid/lattice/Lattice_conformable.h: assert(lhs.Checkerboard() == rhs.Checkerboard()))
+void fermion_check_same_cb(const gb_fermion *a, const gb_fermion *b) {
+  if (a->kind == GB_HALF && a->cb != b->cb)
+    throw Error(GB_ERR_INVALID, "fields live on different checkerboards (Even vs Odd): not conformable");
+}
 gb_fermion *fermion_create_like(const gb_fermion *like, int prec) {
   gb_fermion *f = nullptr;
   int rc = fermion_create_impl(like->grid, like->Ls, like->ncomplex, (gb_precision)prec, (gb_gridkind)like->kind, &f);
@@ -403,14 +409,14 @@ extern "C" int gb_scale(gb_fermion *z, double a, const gb_fermion *x) {
 }
 extern "C" int gb_axpy(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y) {
   GB_API_BEGIN
-  fermion_check_same(z, x); fermion_check_same(z, y);
+  fermion_check_same(z, x); fermion_check_same(z, y); fermion_check_same_cb(x, y);
   blas_launch<BL_AXPY>(z, a, 0, x, y);
   z->cb = x->cb;
   GB_API_END
 }
 extern "C" int gb_axpby(gb_fermion *z, double a, double b, const gb_fermion *x, const gb_fermion *y) {
   GB_API_BEGIN
-  fermion_check_same(z, x); fermion_check_same(z, y);
+  fermion_check_same(z, x); fermion_check_same(z, y); fermion_check_same_cb(x, y);
   blas_launch<BL_AXPBY>(z, a, b, x, y);
   z->cb = x->cb;
   GB_API_END
@@ -618,13 +624,13 @@ extern "C" int gb_norm2(const gb_fermion *x, double *out) {
 }
 extern "C" int gb_inner_product(const gb_fermion *l, const gb_fermion *r, double out[2]) {
   GB_API_BEGIN
-  fermion_check_same(l, r);
+  fermion_check_same(l, r); fermion_check_same_cb(l, r);
   reduce_inner(l->grid->ctx, l, r, out);
   GB_API_END
 }
 extern "C" int gb_axpy_norm(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y, double *norm2_z) {
   GB_API_BEGIN
-  fermion_check_same(z, x); fermion_check_same(z, y);
+  fermion_check_same(z, x); fermion_check_same(z, y); fermion_check_same_cb(x, y);
   gb_context *ctx = z->grid->ctx;
   const int64_t n = z->nvec();
   const unsigned blocks = red_blocks(ctx, n);

@@ -408,3 +408,17 @@ def test_dhop_host_pipelined_matches_device_path(setup, prec, dag):
     if prec == gb.F32:
         got64 = setup.dev[prec].Dhop_host(h.astype(np.complex128), np.empty(h.shape, np.complex128), dag)
         assert site_rel_err(got64, ref) < TOL_HOP[prec]
+
+
+def test_blas_rejects_fields_on_different_checkerboards(ctx):
+    """ref: conformable() asserts lhs.Checkerboard() == rhs.Checkerboard() (Grid/lattice/Lattice_conformable.h) for every binary
+    lattice operation; here axpy / axpby / axpy_norm / innerProduct of an Even with an Odd field return GB_ERR_INVALID"""
+    grid = gb.GridCartesian(ctx, (4, 4, 4, 4))
+    full = gb.LatticeFermion(grid, 4, gb.F64).random(3)
+    e, o, z = (gb.LatticeFermion(grid, 4, gb.F64, gb.HALF) for _ in range(3))
+    gb.pickCheckerboard(gb.Even, e, full); gb.pickCheckerboard(gb.Odd, o, full)
+    for f in (lambda: gb.axpy(z, 1.0, e, o), lambda: gb.innerProduct(e, o), lambda: gb.axpy_norm(z, 1.0, e, o)):
+        with pytest.raises(gb.GridB200Error):
+            f()
+    gb.axpy(z, 1.0, e, e)                       # same checkerboard: fine, and the result carries it
+    assert z.Checkerboard() == gb.Even
