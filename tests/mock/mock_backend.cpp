@@ -283,9 +283,12 @@ int gb_scale(gb_fermion *z, double a, const gb_fermion *x) {
   z->cb = x->cb;
   GB_API_END
 }
+static void check_same_cb(const gb_fermion *a, const gb_fermion *b) {   // as fields.cu: the reference's conformable()
+  if (a->kind == GB_HALF && a->cb != b->cb) throw Error(GB_ERR_INVALID, "fields live on different checkerboards (Even vs Odd): not conformable");
+}
 int gb_axpby(gb_fermion *z, double a, double b, const gb_fermion *x, const gb_fermion *y) {
   GB_API_BEGIN
-  fermion_check_same(z, x); fermion_check_same(z, y);
+  fermion_check_same(z, x); fermion_check_same(z, y); check_same_cb(x, y);
   BY_PREC(z, (each<float>(z, [&](size_t i) { return std::fmaf((float)a, ((const float *)x->data)[i], (float)b * ((const float *)y->data)[i]); })),
           (each<double>(z, [&](size_t i) { return std::fma(a, ((const double *)x->data)[i], b * ((const double *)y->data)[i]); })));
   z->cb = x->cb;
@@ -293,7 +296,7 @@ int gb_axpby(gb_fermion *z, double a, double b, const gb_fermion *x, const gb_fe
 }
 int gb_axpy(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y) {
   GB_API_BEGIN
-  fermion_check_same(z, x); fermion_check_same(z, y);
+  fermion_check_same(z, x); fermion_check_same(z, y); check_same_cb(x, y);
   BY_PREC(z, (each<float>(z, [&](size_t i) { return std::fmaf((float)a, ((const float *)x->data)[i], ((const float *)y->data)[i]); })),
           (each<double>(z, [&](size_t i) { return std::fma(a, ((const double *)x->data)[i], ((const double *)y->data)[i]); })));
   z->cb = x->cb;
@@ -308,7 +311,13 @@ int gb_norm2(const gb_fermion *x, double *out) {
   return GB_OK;
 }
 int gb_axpy_norm(gb_fermion *z, double a, const gb_fermion *x, const gb_fermion *y, double *n2) { int rc = gb_axpy(z, a, x, y); if (rc != GB_OK) return rc; return gb_norm2(z, n2); }
-int gb_inner_product(const gb_fermion *l, const gb_fermion *r, double out[2]) { if (l->prec == GB_F32) inner_T<float>(l, r, out); else inner_T<double>(l, r, out); global_sum(l->grid->ctx, out, 2); return GB_OK; }
+int gb_inner_product(const gb_fermion *l, const gb_fermion *r, double out[2]) {
+  GB_API_BEGIN
+  check_same_cb(l, r);
+  if (l->prec == GB_F32) inner_T<float>(l, r, out); else inner_T<double>(l, r, out);
+  global_sum(l->grid->ctx, out, 2);
+  GB_API_END
+}
 // gauge fields: lexicographic host arrays of the field's precision
 int gb_gauge_create(gb_grid *g, gb_precision prec, gb_gauge **out) {
   gb_gauge *u = new gb_gauge();
