@@ -58,6 +58,7 @@ SYMBOLS = [
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
     ("gb_mixed_cg_schur_ex", _i, [_vp, _vp, _vp, _vp, _d, _d, _d, _i, _i, _pi, _pd]),
+    ("gb_mixed_cg_batched_schur", _i, [_vp, _vp, _i, _vp, _vp, _d, _i, _i, _i, _i, _pi, _pd]),
     ("gb_op_dhop_dir", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_dhop_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mderiv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_op_meooe_deriv", _i, [_vp, _vp, _vp, _vp, _i]), ("gb_op_mpc_deriv", _i, [_vp, _vp, _vp, _vp, _i]),
     ("gb_relup_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _d, _pi, _pd]),
@@ -829,7 +830,8 @@ class ConjugateGradientMultiShiftMixedPrec(ConjugateGradientMultiShift):
 class MixedPrecisionConjugateGradientBatched:
     """ref: Grid/algorithms/iterative/ConjugateGradientMixedPrecBatched.h:36-213 -- the defect-correction loop of
     MixedPrecisionConjugateGradient over a batch of right-hand sides with ONE inner tolerance schedule (the largest residual of
-    the batch sets it), then a double-precision patch-up CG per right-hand side.  Composition of the single-field entry points."""
+    the batch sets it), then a double-precision patch-up CG per right-hand side: gb_mixed_cg_batched_schur.  The reference keeps its
+    counts in locals and only logs them; here they are members."""
 
     def __init__(self, tol, maxinnerit, maxouterit, maxpatchit, Linop_f, Linop_d, updateResidual=True):
         self.Tolerance, self.InnerTolerance = tol, tol
@@ -842,42 +844,12 @@ class MixedPrecisionConjugateGradientBatched:
             srcs_d, sols_d = [srcs_d], [sols_d]
         assert len(srcs_d) == len(sols_d)
         nb = len(srcs_d)
-        cb = srcs_d[0].Checkerboard()
-        tmp_d = srcs_d[0].like()
-        src_d = [s.like() for s in srcs_d]
-        src_f = [s.like(prec=F32) for s in srcs_d]
-        sol_f = [s.like(prec=F32) for s in srcs_d]
-        stop = [norm2(s) * self.Tolerance ** 2 for s in srcs_d]
-        norm = [0.0] * nb
-        for f in sols_d:
-            f.set_checkerboard(cb)
-        self.TotalInnerIterations, self.TotalFinalStepIterations = [0] * nb, [0] * nb
-        inner_tol = self.InnerTolerance
-        CG_f = ConjugateGradient(inner_tol, self.MaxInnerIterations, err_on_no_conv=False)
-        outer = 0
-        while outer < self.MaxOuterIterations:
-            all_converged = True
-            for i in range(nb):
-                self.Linop_d.HermOp(sols_d[i], tmp_d)
-                norm[i] = axpy_norm(src_d[i], -1.0, tmp_d, srcs_d[i])          # src_d = residual
-                precisionChange(src_f[i], src_d[i])
-                sol_f[i].zero().set_checkerboard(cb)
-                if norm[i] > self.OuterLoopNormMult * stop[i]:
-                    all_converged = False
-            if all_converged:
-                break
-            if self.updateResidual:
-                while max(norm) * inner_tol * inner_tol < max(stop):
-                    inner_tol *= 2
-                CG_f.Tolerance = inner_tol
-            for i in range(nb):
-                CG_f(self.Linop_f, src_f[i], sol_f[i])
-                self.TotalInnerIterations[i] += CG_f.IterationsToComplete
-                precisionChange(tmp_d, sol_f[i])
-                axpy(sols_d[i], 1.0, tmp_d, sols_d[i])
-            outer += 1
-        self.TotalOuterIterations = outer
-        for i in range(nb):
-            CG_d = ConjugateGradient(self.Tolerance, self.MaxPatchupIterations)
-            CG_d(self.Linop_d, srcs_d[i], sols_d[i])
-            self.TotalFinalStepIterations[i] += CG_d.IterationsToComplete
+        S = (C.c_void_p * nb)(*[f.h for f in srcs_d])
+        X = (C.c_void_p * nb)(*[f.h for f in sols_d])
+        it, tr = (C.c_int * (1 + 2 * nb))(), (C.c_double * nb)()
+        rc = lib().gb_mixed_cg_batched_schur(self.Linop_f._Mat.h, self.Linop_d._Mat.h, nb, S, X, self.Tolerance, self.MaxInnerIterations,
+                                             self.MaxOuterIterations, self.MaxPatchupIterations, 1 if self.updateResidual else 0, it, tr)
+        self.TotalOuterIterations = it[0]
+        self.TotalInnerIterations, self.TotalFinalStepIterations = list(it[1:1 + nb]), list(it[1 + nb:])
+        self.TrueResidual = list(tr)
+        _chk(rc)

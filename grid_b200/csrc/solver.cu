@@ -4,6 +4,7 @@
 // The iteration is   d = <p, A p> ; a = c/d ; r -= a Ap ; cp = |r|^2 ; b = cp/c ; psi += a p ; p = b p + r
 // with the norm fused into the r-update (axpy_norm) and the two axpys fused into one pass (ConjugateGradient.h:176-183).
 #include "fermop.hpp"
+#include <algorithm>
 #include "kernels_common.cuh"
 #include <cmath>
 #include <cstdlib>
@@ -475,6 +476,72 @@ int gb_mixed_cg_schur_ex(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src
   if (iters_out) { iters_out[0] = o.inner; iters_out[1] = o.outer; iters_out[2] = o.fin; }
   if (true_resid_out) *true_resid_out = o.true_resid;
   if (!o.converged) throw Error(GB_ERR_NOT_CONVERGED, "MixedPrecisionConjugateGradient final solve did NOT converge");
+  GB_API_END
+}
+// MixedPrecisionConjugateGradientBatched   ref: ConjugateGradientMixedPrecBatched.h:79-207 (same order of operations)
+int gb_mixed_cg_batched_schur(gb_fermop *op_f, gb_fermop *op_d, int nbatch, const gb_fermion *const *srcs_d, gb_fermion *const *sols_d,
+                              double tol, int max_inner, int max_outer, int max_patchup, int update_residual, int *iters_out,
+                              double *true_resid_out) {
+  GB_API_BEGIN
+  GB_REQUIRE(op_f && op_d && srcs_d && sols_d && nbatch >= 1, "null argument");
+  GB_TRACE("MixedPrecisionConjugateGradientBatched");
+  GB_REQUIRE(op_f->prec == GB_F32 && op_d->prec == GB_F64, "mixed CG needs an fp32 and an fp64 operator");
+  const int cb = srcs_d[0]->cb;
+  std::vector<gb_fermion *> src_d(nbatch, nullptr), src_f(nbatch, nullptr), sol_f(nbatch, nullptr);
+  gb_fermion *tmp_d = nullptr;
+  struct Guard {
+    std::vector<gb_fermion *> &a, &b, &c; gb_fermion *&t;
+    ~Guard() { for (auto *f : a) gb_fermion_destroy(f); for (auto *f : b) gb_fermion_destroy(f); for (auto *f : c) gb_fermion_destroy(f); gb_fermion_destroy(t); }
+  } guard{src_d, src_f, sol_f, tmp_d};
+  std::vector<double> stop(nbatch), norm(nbatch, 0.0);
+  for (int i = 0; i < nbatch; i++) {
+    GB_REQUIRE(srcs_d[i] && sols_d[i] && srcs_d[i]->prec == GB_F64 && sols_d[i]->prec == GB_F64 && srcs_d[i]->kind == GB_HALF, "batched mixed CG works on fp64 red-black fields");
+    GB_REQUIRE(srcs_d[i]->cb == cb, "the right-hand sides of a batch live on one checkerboard");
+    fermion_check_same(srcs_d[0], srcs_d[i]); fermion_check_same(srcs_d[i], sols_d[i]);
+    sols_d[i]->cb = cb;
+    double n2;
+    chk(gb_norm2(srcs_d[i], &n2));
+    stop[i] = n2 * tol * tol;
+    src_d[i] = fermion_create_like(srcs_d[i], GB_F64); src_f[i] = fermion_create_like(srcs_d[i], GB_F32); sol_f[i] = fermion_create_like(srcs_d[i], GB_F32);
+    src_d[i]->cb = src_f[i]->cb = sol_f[i]->cb = cb;
+    chk(gb_copy(src_d[i], srcs_d[i]));
+  }
+  tmp_d = fermion_create_like(srcs_d[0], GB_F64);
+  tmp_d->cb = cb;
+  const double OuterLoopNormMult = 100.0;
+  double inner_tol = tol;
+  std::vector<int> inner(nbatch, 0), fin(nbatch, 0);
+  int outer;
+  for (outer = 0; outer < max_outer; outer++) {
+    bool all_converged = true;
+    for (int i = 0; i < nbatch; i++) {
+      op_apply(op_d, GB_OP_HERMOP, sols_d[i], tmp_d, 0);
+      chk(gb_axpy_norm(src_d[i], -1.0, tmp_d, srcs_d[i], &norm[i]));       // src_d = residual
+      chk(gb_precision_change(src_f[i], src_d[i]));
+      chk(gb_zero(sol_f[i]));
+      if (norm[i] > OuterLoopNormMult * stop[i]) all_converged = false;
+    }
+    if (all_converged) break;
+    if (update_residual) {
+      const double norm_max = *std::max_element(norm.begin(), norm.end()), stop_max = *std::max_element(stop.begin(), stop.end());
+      while (norm_max * inner_tol * inner_tol < stop_max) inner_tol *= 2;
+    }
+    for (int i = 0; i < nbatch; i++) {
+      CGOut in = cg_schur_device_scalars(op_f, src_f[i], sol_f[i], inner_tol, max_inner);   // ErrorOnNoConverge = false
+      inner[i] += in.iters;
+      chk(gb_precision_change(tmp_d, sol_f[i]));
+      chk(gb_axpy(sols_d[i], 1.0, tmp_d, sols_d[i]));
+    }
+  }
+  bool all_ok = true;
+  for (int i = 0; i < nbatch; i++) {
+    CGOut f = cg_schur_device_scalars(op_d, srcs_d[i], sols_d[i], tol, max_patchup);
+    fin[i] = f.iters;
+    if (true_resid_out) true_resid_out[i] = f.true_resid;
+    all_ok = all_ok && f.converged;
+  }
+  if (iters_out) { iters_out[0] = outer; for (int i = 0; i < nbatch; i++) { iters_out[1 + i] = inner[i]; iters_out[1 + nbatch + i] = fin[i]; } }
+  if (!all_ok) throw Error(GB_ERR_NOT_CONVERGED, "MixedPrecisionConjugateGradientBatched: a patch-up solve did NOT converge");
   GB_API_END
 }
 } // extern "C"

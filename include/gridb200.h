@@ -279,6 +279,16 @@ int gb_mixed_cg_schur_ex(gb_fermop *op_f, gb_fermop *op_d, const gb_fermion *src
                          double outer_loop_norm_mult, int max_inner, int max_outer, int iters_out[3], double *true_resid_out);
 
 
+/* MixedPrecisionConjugateGradientBatched(tol, maxinnerit, maxouterit, maxpatchit, sp_grid, Linop_f, Linop_d)(srcs, sols) on the Schur
+ * operators of op_f (fp32) and op_d (fp64): the defect-correction loop over a batch of right-hand sides with ONE restart schedule -- all
+ * residuals recomputed in double precision each outer iteration, the common inner tolerance loosened by the largest residual / target of
+ * the batch, one fp32 CG per right-hand side, then a double-precision patch-up CG per right-hand side.  sols are the initial guesses.
+ * iters_out[1 + 2 nbatch] = {restarts, inner iterations per right-hand side..., patch-up iterations per right-hand side...};
+ * true_resid_out[nbatch].   ref: Grid/algorithms/iterative/ConjugateGradientMixedPrecBatched.h:36-213 */
+int gb_mixed_cg_batched_schur(gb_fermop *op_f, gb_fermop *op_d, int nbatch, const gb_fermion *const *srcs_d, gb_fermion *const *sols_d,
+                              double tol, int max_inner, int max_outer, int max_patchup, int update_residual, int *iters_out,
+                              double *true_resid_out);
+
 /* ConjugateGradientReliableUpdate(tol, maxit, Delta, sp_grid, Linop_f, Linop_d)(src, psi) on the Schur operators of op_f (fp32)
  * and op_d (fp64); psi is the initial guess.  iters_out[3] = {IterationsToComplete, ReliableUpdatesPerformed, IterationsToCleanup}.
  * ref: Grid/algorithms/iterative/ConjugateGradientReliableUpdate.h:36-270 ; driver tests/solver/Test_dwf_relupcg_prec.cc:88-104 */

@@ -371,7 +371,7 @@ public:
 
 
 // ---- MixedPrecisionConjugateGradientBatched (ref: Grid/algorithms/iterative/ConjugateGradientMixedPrecBatched.h:36-213)
-// the defect-correction loop over a batch of right-hand sides with one inner-tolerance schedule, then a patch-up CG each
+// the defect-correction loop over a batch of right-hand sides with one inner-tolerance schedule, then a patch-up CG each: gb_mixed_cg_batched_schur
 template <class FieldD, class FieldF> class MixedPrecisionConjugateGradientBatched {
 public:
   RealD Tolerance, InnerTolerance;
@@ -385,41 +385,38 @@ public:
                                          LinearOperatorBase<FieldF> &_Linop_f, LinearOperatorBase<FieldD> &_Linop_d, bool _updateResidual = true)
       : Tolerance(tol), InnerTolerance(tol), MaxInnerIterations(maxinnerit), MaxOuterIterations(maxouterit), MaxPatchupIterations(maxpatchit),
         SinglePrecGrid(_sp_grid), Linop_f(_Linop_f), Linop_d(_Linop_d), updateResidual(_updateResidual) {}
+  // counts the reference only logs (:201), kept here as members
+  Integer TotalOuterIterations = 0;
+  std::vector<Integer> TotalInnerIterations, TotalFinalStepIterations;
+  std::vector<RealD> TrueResidual;
   void operator()(const std::vector<FieldD> &src_d_in, std::vector<FieldD> &sol_d) {
     assert(src_d_in.size() == sol_d.size());
     const int NBatch = (int)src_d_in.size();
-    const int cb = src_d_in[0].Checkerboard();
-    GridBase *DoublePrecGrid = src_d_in[0].Grid();
-    FieldD tmp_d(DoublePrecGrid);
-    std::vector<RealD> norm(NBatch, 0.), stop(NBatch);
-    std::vector<FieldD> src_d(src_d_in);
-    std::vector<FieldF> src_f(NBatch, SinglePrecGrid), sol_f(NBatch, SinglePrecGrid);
-    for (int i = 0; i < NBatch; i++) { sol_d[i].SetCheckerboard(cb); stop[i] = norm2(src_d_in[i]) * Tolerance * Tolerance; }
-    RealD inner_tol = InnerTolerance;
-    ConjugateGradient<FieldF> CG_f(inner_tol, MaxInnerIterations, false);
-    for (Integer outer_iter = 0; outer_iter < MaxOuterIterations; outer_iter++) {
-      bool allConverged = true;
-      for (int i = 0; i < NBatch; i++) {
-        Linop_d.HermOp(sol_d[i], tmp_d);
-        norm[i] = axpy_norm(src_d[i], -1., tmp_d, src_d_in[i]);
-        precisionChange(src_f[i], src_d[i]);
-        sol_f[i].Zero(); sol_f[i].SetCheckerboard(cb);
-        if (norm[i] > OuterLoopNormMult * stop[i]) allConverged = false;
-      }
-      if (allConverged) break;
-      if (updateResidual) {
-        RealD normMax = 0, stopMax = 0;
-        for (int i = 0; i < NBatch; i++) { normMax = std::max(normMax, norm[i]); stopMax = std::max(stopMax, stop[i]); }
-        while (normMax * inner_tol * inner_tol < stopMax) inner_tol *= 2;
-        CG_f.Tolerance = inner_tol;
-      }
-      for (int i = 0; i < NBatch; i++) {
-        CG_f(Linop_f, src_f[i], sol_f[i]);
-        precisionChange(tmp_d, sol_f[i]);
-        axpy(sol_d[i], 1.0, tmp_d, sol_d[i]);
-      }
-    }
-    for (int i = 0; i < NBatch; i++) { ConjugateGradient<FieldD> CG_d(Tolerance, MaxPatchupIterations); CG_d(Linop_d, src_d_in[i], sol_d[i]); }
+    gb_fermop *mf = Linop_f.FusedSchurMatrix(), *md = Linop_d.FusedSchurMatrix();
+    assert(mf && md && "MixedPrecisionConjugateGradientBatched needs SchurDiagMooeeOperator arguments");
+    std::vector<const gb_fermion *> s(NBatch);
+    std::vector<gb_fermion *> x(NBatch);
+    for (int i = 0; i < NBatch; i++) { s[i] = src_d_in[i].h; x[i] = sol_d[i].h; }
+    std::vector<int> it(1 + 2 * NBatch, 0);
+    TrueResidual.assign(NBatch, 0.);
+    int rc = gb_mixed_cg_batched_schur(mf, md, NBatch, s.data(), x.data(), Tolerance, MaxInnerIterations, MaxOuterIterations, MaxPatchupIterations,
+                                       updateResidual ? 1 : 0, it.data(), TrueResidual.data());
+    TotalOuterIterations = it[0];
+    TotalInnerIterations.assign(it.begin() + 1, it.begin() + 1 + NBatch);
+    TotalFinalStepIterations.assign(it.begin() + 1 + NBatch, it.end());
+    GB_ASSERT_OK(rc);
+  }
+  void operator()(const FieldD &src_d_in, FieldD &sol_d) {        // ref :70-77
+    std::vector<const gb_fermion *> s{src_d_in.h};
+    std::vector<gb_fermion *> x{sol_d.h};
+    int it[3] = {0, 0, 0};
+    TrueResidual.assign(1, 0.);
+    gb_fermop *mf = Linop_f.FusedSchurMatrix(), *md = Linop_d.FusedSchurMatrix();
+    assert(mf && md && "MixedPrecisionConjugateGradientBatched needs SchurDiagMooeeOperator arguments");
+    int rc = gb_mixed_cg_batched_schur(mf, md, 1, s.data(), x.data(), Tolerance, MaxInnerIterations, MaxOuterIterations, MaxPatchupIterations,
+                                       updateResidual ? 1 : 0, it, TrueResidual.data());
+    TotalOuterIterations = it[0]; TotalInnerIterations.assign(1, it[1]); TotalFinalStepIterations.assign(1, it[2]);
+    GB_ASSERT_OK(rc);
   }
 };
 

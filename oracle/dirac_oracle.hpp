@@ -903,4 +903,52 @@ inline MixedCGResult MixedPrecisionCG(const FermOp<double> &op_d, const FermOp<f
   return R;
 }
 
+// ref: Grid/algorithms/iterative/ConjugateGradientMixedPrecBatched.h:79-207 -- the defect-correction loop over a BATCH of right-hand
+// sides with one restart schedule: every outer iteration recomputes all residuals in double precision, stops when ALL are below
+// OuterLoopNormMult * stop, loosens the common inner tolerance by the LARGEST residual / stop of the batch (:158-163), runs one
+// single-precision CG per right-hand side, and finishes with a double-precision patch-up CG per right-hand side (:190-195).
+struct BatchedCGResult { int outer_iterations = 0; std::vector<int> inner_iterations, final_iterations; std::vector<double> true_residual; };
+inline BatchedCGResult MixedPrecisionCGBatched(const FermOp<double> &op_d, const FermOp<float> &op_f, int cb, int nbatch, const Spinor<double> *const *src_d_in,
+                                               Spinor<double> *const *sol_d, double tol, int maxinner, int maxouter, int maxpatch) {
+  const int64_t n = op_d.V5cb();
+  BatchedCGResult R;
+  R.inner_iterations.assign(nbatch, 0); R.final_iterations.assign(nbatch, 0); R.true_residual.assign(nbatch, 0.0);
+  const double OuterLoopNormMult = 100.0;
+  std::vector<double> stop(nbatch), norm(nbatch, 0.0);
+  std::vector<std::vector<Spinor<double>>> src_d(nbatch);
+  std::vector<std::vector<Spinor<float>>> src_f(nbatch), sol_f(nbatch);
+  std::vector<Spinor<double>> tmp_d(n);
+  for (int i = 0; i < nbatch; i++) {
+    stop[i] = norm2(n, src_d_in[i]) * tol * tol;
+    src_d[i].assign(src_d_in[i], src_d_in[i] + n); src_f[i].resize(n); sol_f[i].resize(n);
+  }
+  double inner_tol = tol;
+  int outer;
+  for (outer = 0; outer < maxouter; outer++) {
+    bool all_converged = true;
+    for (int i = 0; i < nbatch; i++) {
+      op_d.HermOp(sol_d[i], tmp_d.data(), cb);
+      norm[i] = axpy_norm(n, src_d[i].data(), -1.0, tmp_d.data(), src_d_in[i]);
+      precisionChange(n, src_f[i].data(), src_d[i].data());
+      std::memset((void *)sol_f[i].data(), 0, sizeof(Spinor<float>) * n);
+      if (norm[i] > OuterLoopNormMult * stop[i]) all_converged = false;
+    }
+    if (all_converged) break;
+    const double norm_max = *std::max_element(norm.begin(), norm.end()), stop_max = *std::max_element(stop.begin(), stop.end());
+    while (norm_max * inner_tol * inner_tol < stop_max) inner_tol *= 2;
+    for (int i = 0; i < nbatch; i++) {
+      CGResult in = ConjugateGradient(op_f, cb, src_f[i].data(), sol_f[i].data(), inner_tol, maxinner, 0.0);
+      R.inner_iterations[i] += in.iterations;
+      precisionChange(n, tmp_d.data(), sol_f[i].data());
+      axpy(n, sol_d[i], 1.0, tmp_d.data(), sol_d[i]);
+    }
+  }
+  R.outer_iterations = outer;
+  for (int i = 0; i < nbatch; i++) {
+    CGResult fin = ConjugateGradient(op_d, cb, src_d_in[i], sol_d[i], tol, maxpatch, 0.0);
+    R.final_iterations[i] = fin.iterations; R.true_residual[i] = fin.true_residual;
+  }
+  return R;
+}
+
 } // namespace oracle

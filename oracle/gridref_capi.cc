@@ -13,6 +13,8 @@
 #include <Grid/parallelIO/NerscIO.h>
 #include <chrono>
 #include <memory>
+#include <sstream>
+#include <cstdio>
 
 using namespace Grid;
 
@@ -456,6 +458,44 @@ void gref_mixed_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d,
   out_iters[3] = 1;
   *out_true_resid = mCG.TrueResidual;
   export_lex(x, sol_d);
+}
+
+// MixedPrecisionConjugateGradientBatched (Grid/algorithms/iterative/ConjugateGradientMixedPrecBatched.h).  The class keeps its iteration
+// counts in locals and only logs them, so they are read back from its own GridLogMessage lines
+//   "MixedPrecisionConjugateGradientBatched: solve i Inner CG iterations N Restarts R Final CG iterations F"   (:201)
+// srcs / sols: nbatch fields back to back; out_iters: [restarts, inner_0.., final_0..]
+void gref_mixed_cg_batched(void *h_d, void *h_f, int cb, int nbatch, const void *srcs_d, void *sols_d, double tol, int maxinner, int maxouter,
+                           int maxpatch, int *out_iters) {
+  auto *bd = dynamic_cast<WilsonBox<WilsonImplD, vComplexD> *>((BoxBase *)h_d);
+  auto *bf = dynamic_cast<WilsonBox<WilsonImplF, vComplexF> *>((BoxBase *)h_f);
+  assert(bd && bf);
+  typedef FermionOperator<WilsonImplD> OpD;
+  typedef FermionOperator<WilsonImplF> OpF;
+  SchurDiagMooeeOperator<OpD, LatticeFermionD> Sd(*bd->op);
+  SchurDiagMooeeOperator<OpF, LatticeFermionF> Sf(*bf->op);
+  typedef LatticeFermionD::vector_object::scalar_object sobj;
+  const size_t n = bd->frbgrid()->lSites();
+  std::vector<LatticeFermionD> s(nbatch, bd->frbgrid()), x(nbatch, bd->frbgrid());
+  for (int i = 0; i < nbatch; i++) {
+    import_lex(s[i], (const char *)srcs_d + (size_t)i * n * sizeof(sobj)); import_lex(x[i], (const char *)sols_d + (size_t)i * n * sizeof(sobj));
+    s[i].Checkerboard() = cb; x[i].Checkerboard() = cb;
+  }
+  MixedPrecisionConjugateGradientBatched<LatticeFermionD, LatticeFermionF> mCG(tol, maxinner, maxouter, maxpatch, bf->frbgrid(), Sf, Sd);
+  std::stringstream log;
+  std::streambuf *saved = std::cout.rdbuf(log.rdbuf());
+  mCG(s, x);
+  std::cout.rdbuf(saved);
+  for (int i = 0; i < 1 + 2 * nbatch; i++) out_iters[i] = -1;
+  std::string line;
+  while (std::getline(log, line)) {
+    const size_t k = line.find("MixedPrecisionConjugateGradientBatched: solve ");
+    int i, inner, restarts, fin;
+    if (k != std::string::npos && std::sscanf(line.c_str() + k, "MixedPrecisionConjugateGradientBatched: solve %d Inner CG iterations %d Restarts %d Final CG iterations %d",
+                                               &i, &inner, &restarts, &fin) == 4 && i >= 0 && i < nbatch) {
+      out_iters[0] = restarts; out_iters[1 + i] = inner; out_iters[1 + nbatch + i] = fin;
+    }
+  }
+  for (int i = 0; i < nbatch; i++) export_lex(x[i], (char *)sols_d + (size_t)i * n * sizeof(sobj));
 }
 
 // ConjugateGradientReliableUpdate as tests/solver/Test_dwf_relupcg_prec.cc:88-104 sets it up.

@@ -214,6 +214,18 @@ void orc_mixed_cg(void *h_d, void *h_f, int cb, const void *src_d, void *sol_d, 
   out_iters[0] = r.inner_iterations; out_iters[1] = r.outer_iterations; out_iters[2] = r.final_iterations; out_iters[3] = r.converged;
   *out_true_resid = r.true_residual;
 }
+// srcs / sols: nbatch fields back to back; out_iters: [outer, inner_0..inner_{n-1}, final_0..final_{n-1}]; out_tr: [n]
+void orc_mixed_cg_batched(void *h_d, void *h_f, int cb, int nbatch, const void *srcs_d, void *sols_d, double tol, int maxinner, int maxouter,
+                          int maxpatch, int *out_iters, double *out_tr) {
+  OpBox *bd = (OpBox *)h_d, *bf = (OpBox *)h_f;
+  const int64_t n = bd->d.V5cb();
+  std::vector<const Spinor<double> *> s(nbatch);
+  std::vector<Spinor<double> *> x(nbatch);
+  for (int i = 0; i < nbatch; i++) { s[i] = (const Spinor<double> *)srcs_d + (size_t)i * n; x[i] = (Spinor<double> *)sols_d + (size_t)i * n; }
+  BatchedCGResult r = MixedPrecisionCGBatched(bd->d, bf->f, cb, nbatch, s.data(), x.data(), tol, maxinner, maxouter, maxpatch);
+  out_iters[0] = r.outer_iterations;
+  for (int i = 0; i < nbatch; i++) { out_iters[1 + i] = r.inner_iterations[i]; out_iters[1 + nbatch + i] = r.final_iterations[i]; out_tr[i] = r.true_residual[i]; }
+}
 // Timed loop for the CPU baseline: applies `which` ncall times, returns seconds.
 double orc_time_apply(void *h, int which, const void *in, void *out, int dag, int cb_in, int half, int ncall) {
   auto t0 = std::chrono::steady_clock::now();

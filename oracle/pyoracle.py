@@ -55,6 +55,7 @@ def lib():
         L.orc_relup_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.orc_multishift_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_mixed_cg_batched.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.orc_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.orc_time_apply.restype = C.c_double
         L.orc_num_threads.restype = C.c_int
@@ -327,6 +328,18 @@ def mixed_cg(op_d, op_f, cb, src_d, tol, maxinner, maxouter):
     tr = np.zeros(1, dtype=np.float64)
     lib().orc_mixed_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxinner, maxouter, _ptr(it), _ptr(tr))
     return sol, dict(inner=int(it[0]), outer=int(it[1]), final=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))
+
+
+def mixed_cg_batched(op_d, op_f, cb, srcs_d, tol, maxinner, maxouter, maxpatch):
+    """MixedPrecisionConjugateGradientBatched (ref: ConjugateGradientMixedPrecBatched.h:79-207) from zero guesses.
+    srcs_d: [nbatch, nsite, ...] complex128.  Returns (solutions, dict(outer, inner=[...], final=[...], true_residual=[...]))."""
+    srcs = np.ascontiguousarray(srcs_d, dtype=np.complex128)
+    nb = srcs.shape[0]
+    sols = np.zeros_like(srcs)
+    it = np.zeros(1 + 2 * nb, dtype=np.int32)
+    tr = np.zeros(nb, dtype=np.float64)
+    lib().orc_mixed_cg_batched(op_d.h, op_f.h, cb, nb, _ptr(srcs), _ptr(sols), tol, maxinner, maxouter, maxpatch, _ptr(it), _ptr(tr))
+    return sols, dict(outer=int(it[0]), inner=[int(v) for v in it[1:1 + nb]], final=[int(v) for v in it[1 + nb:]], true_residual=[float(v) for v in tr])
 
 
 def dhop_naive(dims, Ls, Umu, x, dag=0, prec=1):

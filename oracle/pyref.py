@@ -59,6 +59,7 @@ def lib():
         L.gref_relup_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_void_p, C.c_void_p]
         L.gref_multishift_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gref_mixed_cg.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.gref_mixed_cg_batched.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.gref_time_apply.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
         L.gref_time_apply.restype = C.c_double
         L.gref_init.argtypes = [C.c_int]
@@ -238,6 +239,17 @@ def mixed_cg(op_d, op_f, cb, src_d, tol, maxinner, maxouter):
     tr = np.zeros(1, dtype=np.float64)
     lib().gref_mixed_cg(op_d.h, op_f.h, cb, _ptr(src), _ptr(sol), tol, maxinner, maxouter, _ptr(it), _ptr(tr))
     return sol, dict(inner=int(it[0]), outer=int(it[1]), final=int(it[2]), converged=int(it[3]), true_residual=float(tr[0]))
+
+
+def mixed_cg_batched(op_d, op_f, cb, srcs_d, tol, maxinner, maxouter, maxpatch):
+    """MixedPrecisionConjugateGradientBatched(tol, maxinner, maxouter, maxpatch, ..., Linop_f, Linop_d)(srcs, sols) from zero guesses;
+    the iteration counts are the ones the class logs (it keeps no members for them)."""
+    srcs = np.ascontiguousarray(srcs_d, dtype=np.complex128)
+    nb = srcs.shape[0]
+    sols = np.zeros_like(srcs)
+    it = np.zeros(1 + 2 * nb, dtype=np.int32)
+    lib().gref_mixed_cg_batched(op_d.h, op_f.h, cb, nb, _ptr(srcs), _ptr(sols), tol, maxinner, maxouter, maxpatch, _ptr(it))
+    return sols, dict(outer=int(it[0]), inner=[int(v) for v in it[1:1 + nb]], final=[int(v) for v in it[1 + nb:]])
 
 
 def relup_cg(op_d, op_f, cb, src_d, tol, maxit, delta):

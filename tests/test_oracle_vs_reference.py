@@ -120,6 +120,25 @@ def test_mixed_precision_cg(gauge):
     assert site_err(xo, xr) < 1e-6
 
 
+def test_mixed_precision_cg_batched(gauge):
+    """ref: Grid/algorithms/iterative/ConjugateGradientMixedPrecBatched.h:79-207 -- three right-hand sides of different norms (the common
+    inner tolerance follows the largest residual / target of the batch): same number of restarts, inner and patch-up iterations per
+    right-hand side as the reference logs, same solutions."""
+    od, rd = pair(1, gauge, LS, 1)
+    of, rf = pair(1, gauge, LS, 0)
+    srcs = np.stack([f * po.pick_checkerboard(DIMS, LS, 1, syn.random_fermion(DIMS, LS, seed=sd)) for sd, f in ((21, 1.0), (22, 3.0), (23, 0.2))])
+    xo, io = po.mixed_cg_batched(od, of, 1, srcs, 1e-8, 10000, 50, 10000)
+    xr, ir = pr.mixed_cg_batched(rd, rf, 1, srcs, 1e-8, 10000, 50, 10000)
+    assert io["outer"] == ir["outer"] and min(ir["inner"]) > 0, (io, ir)
+    for a, b in zip(io["inner"], ir["inner"]):
+        assert abs(a - b) <= max(3, 0.05 * b), (io, ir)          # fp32 inner solves: see test_mixed_precision_cg
+    for a, b in zip(io["final"], ir["final"]):
+        assert abs(a - b) <= 2, (io, ir)                          # 1-3 clean-up iterations: where the fp32 solves' rounding left the residual
+    assert max(io["true_residual"]) < 1e-8
+    for i in range(3):
+        assert site_err(xo[i], xr[i]) < 1e-6
+
+
 # ---------------------------------------------------------------------------------------------- improved staggered
 @pytest.mark.parametrize("prec", [1, 0])
 def test_improved_staggered_all_entries(gauge, prec):
