@@ -23,7 +23,8 @@ cg         = BASELINE configs[2]: even-odd Schur Moebius mixed-precision CG to 1
              solve, with ms per fp32 iteration (from a fixed 50-iteration fp32 CG) and its fraction of the 1872-B/site yardstick.
 e2e_cg     = the call HMC makes: gauge field + source from pinned host memory in, solution back to the host, copies timed.
 config4    = BASELINE configs[3]: Dhop (+ halo-exchange bandwidth + mixed CG) at the local volume 64.64.32.16 x Ls16 per GPU
-             (global 64^4 on 8 GPUs as 1.1.2.4): the weak-scaling series whose 8-vs-1 ratio the north star asks for.
+             (global 64^4 on 8 GPUs as 1.1.2.4): the weak-scaling series whose 8-vs-1 ratio the north star asks for; its "strong" entry is
+             the Dhop at FIXED global 64^4 x Ls16 on the N GPUs of the run (the strong-scaling series of the same config).
 config5    = BASELINE configs[4]: improved staggered Dhop fp32 at 48^4 (global; split 1.1.2.4 on 8 GPUs).
 At N > 1 the decomposed path is first compared with the CPU oracle on a small global lattice (parity_check): the hop per site (fp32, +-dag,
 tolerance 1e-6) and a Schur conjugate-gradient solve (fp64: iteration count, true residual, solution) -- the driver-side parity of the
@@ -615,6 +616,27 @@ def main():
                 del keep
                 config4["cg"] = c4
             del U4, grid4
+            # ---- the strong-scaling series of the same config: global 64^4 x Ls16 on N GPUs (N = 8 is the line above)
+            try:
+                if world == 8:
+                    config4["strong"] = {"global_lattice": [64, 64, 64, 64], "ms_per_step": config4["ms_per_step"], "gflops": config4["gflops"],
+                                         "note": "identical to the weak-scaling line at 8 GPUs"}
+                else:
+                    gS = [64, 64, 64, 64]
+                    gridS = gb.GridCartesian(ctx, gS, mpi)
+                    US = gb.LatticeGaugeField(gridS, gb.F32).random(1)
+                    DS = gb.DomainWallFermion(US, gridS, 16, 0.1, 1.8)
+                    del US
+                    sS = gb.LatticeFermion(gridS, 16, gb.F32).random(2)
+                    oS = gb.LatticeFermion(gridS, 16, gb.F32)
+                    msS, _ = timed(lambda: DS.Dhop(sS, oS, 0), 10, 3)
+                    config4["strong"] = {"global_lattice": gS, "local_lattice": [g // m for g, m in zip(gS, mpi)], "ms_per_step": msS,
+                                         "gflops": FLOPS_PER_SITE * 64 ** 4 * 16 / (msS * 1e-3) / 1e9,
+                                         "roofline_frac": alg_bytes_per_site(16) * 64 ** 4 * 16 / world / (msS * 1e-3) / 1e9 / peak,
+                                         "what": "DomainWallFermionF::Dhop fp32 at FIXED global 64^4 x Ls16 (strong scaling: ms at N over ms at 1)"}
+                    del DS, sS, oS, gridS
+            except Exception as e:
+                config4["strong"] = {"error": f"{type(e).__name__}: {e}"}
         except Exception as e:
             config4 = {"error": f"{type(e).__name__}: {e}"}
 
