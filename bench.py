@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--op", default="Dhop", choices=["Dhop", "DhopEO"])
     ap.add_argument("--local", type=int, nargs=4, default=[32, 32, 32, 32])
     ap.add_argument("--Ls", type=int, default=16)
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=8)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-cg", action="store_true", help="skip the mixed-precision CG blocks (cg, e2e_cg)")
@@ -469,7 +469,7 @@ def main():
         e2e_in.set_checkerboard(gb.Odd)
         Dw.DhopEO(e2e_in, fout, 0)
         gb._chk(gb.lib().gb_fermion_export(fout.h, host_out.ctypes.data, gb.F32))
-    e2e_step()
+    e2e_step(); e2e_step()                      # untimed: staging buffers, first touch of the pinned host pages
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
