@@ -377,6 +377,19 @@ def main():
             ref = decomp.scatter(orc.apply(po.OP_DHOP, xg, dag=dag), pg, mpi, rank, inner=pLs)
             a = pout.export_lex().reshape(ref.shape[0], -1).astype(np.complex128); r = ref.reshape(ref.shape[0], -1)
             errs[f"Dhop dag{dag}"] = max_over_ranks(float(np.max(np.linalg.norm(a - r, axis=1) / np.linalg.norm(r, axis=1))))
+        # the host-buffer entry point that the e2e figure times (faces first, one exchange, slices streamed: dhop_host.cu); should it
+        # ever disagree, the e2e leg falls back to import + hop + export (GB_HOST_PIPE_DECOMP=0) and says so
+        host_form = "pipelined"
+        hx = decomp.scatter(xg, pg, mpi, rank, inner=pLs).astype(np.complex64)
+        refh = decomp.scatter(orc.apply(po.OP_DHOP, xg, dag=0), pg, mpi, rank, inner=pLs)
+        for attempt in (0, 1):
+            a = pD.Dhop_host(hx, np.empty_like(hx), 0).reshape(refh.shape[0], -1).astype(np.complex128); r = refh.reshape(refh.shape[0], -1)
+            eh = max_over_ranks(float(np.max(np.linalg.norm(a - r, axis=1) / np.linalg.norm(r, axis=1))))
+            if eh < 1e-6 or attempt == 1:
+                break
+            os.environ["GB_HOST_PIPE_DECOMP"] = "0"
+            host_form = f"import + hop + export (the pipelined form differed from the oracle: {eh:.3e})"
+        errs["Dhop_host dag0"] = eh
         # ... and of the decomposed Schur CG (hops with halos, s-space passes, reductions summed over ranks by ncclAllReduce in-stream):
         # iteration count, true residual and the solution itself against the oracle's ConjugateGradient on the global lattice
         cg_par, cg_ok = {}, True
@@ -416,7 +429,7 @@ def main():
         except Exception as e:                                          # a fault of the check itself must not cost the bench line
             cg_par = {"error": f"{type(e).__name__}: {e}"}
         parity_check = {"against": "CPU oracle (fp64) on the global lattice", "global_lattice": list(pg), "Ls": pLs, "mpi": list(mpi),
-                        "max_site_rel_err": errs, "tolerance": 1e-6,
+                        "max_site_rel_err": errs, "tolerance": 1e-6, "host_entry_form": host_form,
                         "schur_cg": dict(cg_par, what="ConjugateGradient on SchurDiagMooeeOperator(MobiusFermion fp64, Ls 8) to 1e-8, decomposed over the ranks"),
                         "ok": all(e < 1e-6 for e in errs.values()) and cg_ok}
         del pD, pin, pout, pgrid, orc, Ug, xg

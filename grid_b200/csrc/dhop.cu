@@ -689,7 +689,7 @@ __global__ void halo_wait_kernel(const unsigned long long *flags, unsigned long 
     do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory"); } while (v < epoch);
   }
 }
-size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag) {
+size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag, const void **halo_out) {
   GB_TRACE("HaloExchange");
   GB_REQUIRE(op && in && op->kind != GB_KIND_STAGGERED, "halo exchange benchmark: Wilson-type operators");
   GB_REQUIRE(in->grid == op->grid && in->Ls == op->Ls && in->prec == op->prec && in->kind == GB_FULL, "field is not a conformable full-grid field");
@@ -705,6 +705,7 @@ size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag) {
     halo_wait_kernel<<<1, 32, 0, ctx->stream>>>(flags, epoch, op->comm_dim_mask);
     count_launch(ctx);
     check_launch(ctx, "halo_wait");
+    if (halo_out) for (int i = 0; i < 8; i++) halo_out[i] = halo[i];
   } else {
     ensure_halo(op);
     for (int ip = 0; ip < 2; ip++) {
@@ -712,30 +713,33 @@ size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag) {
       else { if (dag) launch_pack<double, 1>(op, ib[ip], ip, ip, ctx->stream); else launch_pack<double, 0>(op, ib[ip], ip, ip, ctx->stream); }
     }
     exchange_halos(op, 2, ctx->stream);
+    if (halo_out) for (int i = 0; i < 8; i++) halo_out[i] = op->halo_recv[i];
   }
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) bytes += 2 * 2 * op->halo_parity_stride[mu] * 16;   // two directions, two parities
   return bytes;
 }
 
-// Hop restricted to the t-slices [t0, t0 + nt) of both output parities, all 8 legs, single rank (periodic wrap inside the
-// local volume).  Used by the host-pipelined Dhop (fields.cu), where slices are computed as their neighbours arrive over PCIe.
-void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st) {
+// Hop restricted to the t-slices [t0, t0 + nt) of both output parities, all 8 legs.  halo == nullptr: single rank (periodic wrap
+// inside the local volume).  halo != nullptr (decomposed lattice): the legs that leave the rank read the receive buffers of a halo
+// exchange that has COMPLETED in front of this launch on `st` (halo_exchange_only: both input parities, slot = parity).
+// Used by the host-pipelined Dhop (dhop_host.cu), where slices are computed as their neighbours arrive over PCIe.
+void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo) {
   const gb_grid *g = op->grid;
   DhopArgs a;
   const size_t per_parity = (size_t)g->V4cb * 8 * lv_of(op->prec) * 16;
   for (int p = 0; p < 2; p++) { a.in[p] = in[p]; a.out[p] = out[p]; a.U[p] = (char *)op->Uds + p * per_parity; a.axpy[p] = nullptr; }
   a.axpy_a = 1; a.axpy_b = 0;
-  a.comm_dim_mask = 0;
+  a.comm_dim_mask = halo ? op->comm_dim_mask : 0;
   a.Ls = op->Ls; a.Lx = g->ldims[0]; a.Lxh = a.Lx / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
   a.By = a.Ly; a.Bz = a.Lz; a.Bt = a.Lt;
   a.dLs = FastDiv(a.Ls); a.dLxh = FastDiv(a.Lxh); a.dBy = FastDiv(a.By); a.dBz = FastDiv(a.Bz); a.dBt = FastDiv(a.Bt);
   a.dNy = FastDiv(1); a.dNz = FastDiv(1);
   a.first_parity = 0;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
-  for (int i = 0; i < 8; i++) a.halo[i] = nullptr;
-  for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = 0;
+  for (int i = 0; i < 8; i++) a.halo[i] = halo ? halo[i] : nullptr;
+  for (int i = 0; i < 4; i++) a.halo_parity_stride[i] = halo ? op->halo_parity_stride[i] : 0;
   a.mode = 0; a.flags = nullptr; a.epoch = 0;
-  a.leg_mask = 0xFF;
+  a.leg_mask = halo ? op->leg_mask : 0xFF;
   a.box_on = 1;
   a.bo[0] = 0; a.bo[1] = 0; a.bo[2] = 0; a.bo[3] = t0;
   a.be[0] = a.Lxh; a.be[1] = a.Ly; a.be[2] = a.Lz; a.be[3] = nt;

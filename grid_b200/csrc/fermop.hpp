@@ -143,8 +143,8 @@ bool cg_fused_available(const gb_fermop *op);
 void cg_fused_first(gb_fermop *op, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, const double *d_c, const double *d_d, const double *d_cp);
 void cg_fused_rest(gb_fermop *op, const gb_fermion *p, gb_fermion *r, const double *d_c, double *d_d, double *d_cp);
 
-size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag);
-void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st);
+size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag, const void **halo_out = nullptr);   // halo_out[8]: the receive buffers, complete in stream order
+void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo = nullptr);
 // improved staggered operator entry points (stag.cu)
 void stag_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
 // one leg of the hopping term on full-grid fields: point 0..3 forward mu, 4..7 backward mu (force.cu)

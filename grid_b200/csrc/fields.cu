@@ -797,163 +797,3 @@ extern "C" int gb_gauge_unit(gb_gauge *u) {
   gauge_fill(u, 0, 1);
   GB_API_END
 }
-
-
-// =====================================================================================================
-// Dhop on HOST-resident fields, pipelined over t-slices: H2D of slice t+1, the hop of slice t and D2H of slice t-1 run
-// concurrently on three streams (PCIe is full duplex), so a host-to-host Dhop costs one direction of PCIe traffic instead
-// of import + hop + export back to back.  This is the call a reference-side binding whose Lattice objects live in host
-// memory makes (ref: FermionOperator::Dhop(in,out,dag) with in/out unvectorised by unvectorizeToLexOrdArray).
-// =====================================================================================================
-template <class TD, class TH, int DIR>
-__global__ void fermion_slab_transfer_kernel(typename Prec<TD>::vec *dev, TH *slab /* host order, starts at t-slice t0 */, LatGeom G,
-                                             int64_t blk0 /* first block of the slab inside a parity block */, int64_t nblk, int64_t host_site0) {
-  using P = Prec<TD>;
-  const int64_t nelem = 2 * nblk * P::NV * W;
-  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (e >= nelem) return;
-  const int lane = e & (W - 1);
-  int64_t r = e >> LOGW;
-  const int k = r % P::NV;
-  int64_t lb = r / P::NV;
-  const int p = lb / nblk;
-  lb -= (int64_t)p * nblk;
-  const int64_t i5cb = (blk0 + lb) * W + lane;
-  const int64_t site = i5cb / G.Ls;
-  const int s = i5cb - site * G.Ls;
-  const int64_t hidx = s + (int64_t)G.Ls * cb_to_lex(G, p, site) - host_site0;
-  TH *h = slab + hidx * 24;
-  const int64_t de = (((int64_t)p * G.hblk + blk0 + lb) * P::NV + k) * W + lane;
-  if constexpr (sizeof(TD) == 4) {
-    if (DIR == 0) dev[de] = make_float4((float)h[4 * k], (float)h[4 * k + 1], (float)h[4 * k + 2], (float)h[4 * k + 3]);
-    else { float4 v = dev[de]; h[4 * k] = (TH)v.x; h[4 * k + 1] = (TH)v.y; h[4 * k + 2] = (TH)v.z; h[4 * k + 3] = (TH)v.w; }
-  } else {
-    if (DIR == 0) dev[de] = make_double2((double)h[2 * k], (double)h[2 * k + 1]);
-    else { double2 v = dev[de]; h[2 * k] = (TH)v.x; h[2 * k + 1] = (TH)v.y; }
-  }
-}
-
-namespace {
-struct HostPipe {          // per-context scratch of the pipelined path (grow-only)
-  // four streams: the two copy engines never wait for a layout kernel (those run on xin / xout between them and the compute stream)
-  cudaStream_t h2d = nullptr, d2h = nullptr, xin = nullptr, xout = nullptr;
-  static constexpr int NB = 3;                               // staging buffers per direction
-  void *stage_in[NB] = {nullptr, nullptr, nullptr}, *stage_out[NB] = {nullptr, nullptr, nullptr};
-  size_t stage_bytes = 0;
-  std::vector<cudaEvent_t> ev_in, ev_hop;
-  cudaEvent_t ev_copied[NB] = {}, ev_xin_done[NB] = {}, ev_packed[NB] = {}, ev_out_copied[NB] = {}, ev_done = nullptr;
-};
-HostPipe &host_pipe(gb_context *ctx, size_t slab_bytes, int nslab) {
-  static HostPipe P;       // one context per process in this library's usage (one process per GPU)
-  if (!P.h2d) {
-    GB_CUDA(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking));
-    GB_CUDA(cudaStreamCreateWithFlags(&P.d2h, cudaStreamNonBlocking));
-    GB_CUDA(cudaStreamCreateWithFlags(&P.xin, cudaStreamNonBlocking));
-    GB_CUDA(cudaStreamCreateWithFlags(&P.xout, cudaStreamNonBlocking));
-    for (int i = 0; i < HostPipe::NB; i++)
-      for (cudaEvent_t *e : {&P.ev_copied[i], &P.ev_xin_done[i], &P.ev_packed[i], &P.ev_out_copied[i]}) GB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-    GB_CUDA(cudaEventCreateWithFlags(&P.ev_done, cudaEventDisableTiming));
-  }
-  if (P.stage_bytes < slab_bytes) {
-    GB_CUDA(cudaDeviceSynchronize());
-    for (int i = 0; i < HostPipe::NB; i++) {
-      if (P.stage_in[i]) cudaFree(P.stage_in[i]);
-      if (P.stage_out[i]) cudaFree(P.stage_out[i]);
-      GB_CUDA(cudaMalloc(&P.stage_in[i], slab_bytes));
-      GB_CUDA(cudaMalloc(&P.stage_out[i], slab_bytes));
-    }
-    P.stage_bytes = slab_bytes;
-  }
-  while ((int)P.ev_in.size() < nslab) {
-    cudaEvent_t a, b;
-    GB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); GB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
-    P.ev_in.push_back(a); P.ev_hop.push_back(b);
-  }
-  return P;
-}
-template <int DIR> void slab_transfer(gb_context *ctx, const gb_fermion *f, void *stage, int host_prec, int t, cudaStream_t st) {
-  LatGeom G = geom_of(f);
-  const gb_grid *g = f->grid;
-  const int64_t v3cb = g->V4cb / g->ldims[3];
-  const int64_t nblk = v3cb * f->Ls / W, blk0 = (int64_t)t * nblk;
-  const int64_t host_site0 = (int64_t)t * 2 * v3cb * f->Ls;
-  const int64_t nelem = 2 * nblk * nv_of(f->prec) * W;
-  const unsigned blocks = (unsigned)((nelem + 255) / 256);
-#define GB_L(TD, TH) fermion_slab_transfer_kernel<TD, TH, DIR><<<blocks, 256, 0, st>>>((typename Prec<TD>::vec *)f->data, (TH *)stage, G, blk0, nblk, host_site0)
-  if (f->prec == GB_F32 && host_prec == GB_F32) GB_L(float, float);
-  else if (f->prec == GB_F32) GB_L(float, double);
-  else if (host_prec == GB_F32) GB_L(double, float);
-  else GB_L(double, double);
-#undef GB_L
-  count_launch(ctx);
-}
-} // namespace
-
-extern "C" int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_out, gb_precision host_prec, int dag) {
-  GB_API_BEGIN
-  GB_REQUIRE(op && host_in && host_out, "null argument");
-  GB_TRACE("DhopHost");
-  GB_REQUIRE(op->kind != GB_KIND_STAGGERED, "gb_op_dhop_host serves the Wilson-type operators");
-  gb_context *ctx = op->ctx;
-  gb_grid *g = op->grid;
-  GB_CUDA(cudaSetDevice(ctx->device));
-  gb_fermion *fin = op_tmp_full(op, 0), *fout = op_tmp_full(op, 1);
-  const int Lt = g->ldims[3];
-  const int64_t v3cb = g->V4cb / Lt;
-  const bool pipelined = op->comm_dim_mask == 0 && Lt >= 4 && (v3cb * op->Ls) % W == 0;
-  if (!pipelined) {   // decomposed lattices need whole faces before any slice can be finished: import, hop, export
-    int rc = gb_fermion_import(fin, host_in, host_prec); if (rc != GB_OK) return rc;
-    op_apply(op, GB_OP_DHOP, fin, fout, dag);
-    return gb_fermion_export(fout, host_out, host_prec);
-  }
-  const size_t hsz = host_prec == GB_F32 ? 4 : 8;
-  const size_t slab_bytes = (size_t)2 * v3cb * op->Ls * 24 * hsz;
-  HostPipe &P = host_pipe(ctx, slab_bytes, Lt);
-  const void *ib[2] = {fin->block(0), fin->block(1)};
-  void *ob[2] = {fout->block(0), fout->block(1)};
-  // everything previously queued on the compute stream must be done before the copy streams touch the temporaries
-  GB_CUDA(cudaEventRecord(P.ev_done, ctx->stream));
-  GB_CUDA(cudaStreamWaitEvent(P.h2d, P.ev_done, 0));
-  GB_CUDA(cudaStreamWaitEvent(P.d2h, P.ev_done, 0));
-  GB_CUDA(cudaStreamWaitEvent(P.xin, P.ev_done, 0));
-  GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_done, 0));
-  int nin = 0, nout = 0;
-  auto import_slice = [&](int t) {
-    const int b = nin++ % HostPipe::NB;
-    GB_CUDA(cudaStreamWaitEvent(P.h2d, P.ev_xin_done[b], 0));          // the layout kernel that last read this staging buffer
-    GB_CUDA(cudaMemcpyAsync(P.stage_in[b], (const char *)host_in + (size_t)t * slab_bytes, slab_bytes, cudaMemcpyHostToDevice, P.h2d));
-    GB_CUDA(cudaEventRecord(P.ev_copied[b], P.h2d));
-    GB_CUDA(cudaStreamWaitEvent(P.xin, P.ev_copied[b], 0));
-    slab_transfer<0>(ctx, fin, P.stage_in[b], host_prec, t, P.xin);
-    GB_CUDA(cudaEventRecord(P.ev_in[t], P.xin));
-    GB_CUDA(cudaEventRecord(P.ev_xin_done[b], P.xin));
-  };
-  auto hop_and_export = [&](int t) {
-    // slice t needs input slices t-1, t, t+1 (periodic)
-    const int tm = t == 0 ? Lt - 1 : t - 1, tp = t == Lt - 1 ? 0 : t + 1;
-    GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_in[tm], 0));
-    GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_in[t], 0));
-    GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_in[tp], 0));
-    dhop_tslab(op, ib, ob, dag, t, 1, ctx->stream);
-    GB_CUDA(cudaEventRecord(P.ev_hop[t], ctx->stream));
-    const int b = nout++ % HostPipe::NB;
-    GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_hop[t], 0));
-    GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_out_copied[b], 0));       // the D2H copy that last read this staging buffer
-    slab_transfer<1>(ctx, fout, P.stage_out[b], host_prec, t, P.xout);
-    GB_CUDA(cudaEventRecord(P.ev_packed[b], P.xout));
-    GB_CUDA(cudaStreamWaitEvent(P.d2h, P.ev_packed[b], 0));
-    GB_CUDA(cudaMemcpyAsync((char *)host_out + (size_t)t * slab_bytes, P.stage_out[b], slab_bytes, cudaMemcpyDeviceToHost, P.d2h));
-    GB_CUDA(cudaEventRecord(P.ev_out_copied[b], P.d2h));
-  };
-  // slice Lt-1 goes in first (slice 0 needs it across the periodic boundary), so that every slice but the last can be finished as
-  // soon as its forward neighbour has arrived and only ONE hop + D2H is left when the H2D stream runs dry
-  import_slice(Lt - 1); import_slice(0); import_slice(1);
-  hop_and_export(0);
-  for (int t = 1; t < Lt - 2; t++) { import_slice(t + 1); hop_and_export(t); }
-  hop_and_export(Lt - 2); hop_and_export(Lt - 1);
-  GB_CUDA(cudaEventRecord(P.ev_done, P.d2h));
-  GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_done, 0));
-  GB_CUDA(cudaStreamSynchronize(P.d2h));
-  check_launch(ctx, "dhop_host");
-  GB_API_END
-}

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, HERE)
 from transform import transform  # noqa: E402
 
-PRODUCT_SOURCES = ["fermop.cu", "dhop.cu", "dhop_fast.cu", "halo_p2p.cu", "smat.cu", "cayley.cu", "stag.cu", "solver.cu", "schur.cu", "force.cu", "nersc.cu"]
+PRODUCT_SOURCES = ["fermop.cu", "dhop.cu", "dhop_host.cu", "dhop_fast.cu", "halo_p2p.cu", "smat.cu", "cayley.cu", "stag.cu", "solver.cu", "schur.cu", "force.cu", "nersc.cu"]
 # headers that hold kernels with inline PTX or shared memory: rewritten too, and found first on the include path
 PRODUCT_HEADERS = ["dhop_fast.cuh", "dhop_col.cuh", "dhop_col2.cuh"]
 

@@ -106,6 +106,11 @@ def wilson_like(mpi, gdims, kind, Ls):
             ld = [g // m for g, m in zip(gdims, mpi)]
             want = sum(4 * (-(-(int(np.prod(ld)) // 2 // ld[mu] * Ls) // 16) * 16) * 6 * (8 if prec == gb.F32 else 16) for mu in range(4) if mpi[mu] > 1)
             check(rank, f"{tag} prec{prec} halo_exchange bytes {D.halo_exchange(fin)} vs {want}", abs(D.halo_exchange(fin) - want), 0.5)
+            # host-resident fields through gb_op_dhop_host: on z / t splits the faces go in first, one exchange, then the slices stream
+            hloc = decomp.scatter(src, gdims, mpi, rank, inner=Ls).astype(gb._cdtype(prec))
+            for dag in (0, 1):
+                got = D.Dhop_host(hloc, np.empty_like(hloc), dag)
+                check(rank, f"{tag} prec{prec} Dhop_host dag{dag}", site_err(got, decomp.scatter(ref[("dhop", dag)], gdims, mpi, rank, inner=Ls)), tol)
             D.Dhop(fin, out, 0)
             check(rank, f"{tag} prec{prec} Dhop after halo_exchange", site_err(out.export_lex(), decomp.scatter(ref[("dhop", 0)], gdims, mpi, rank, inner=Ls)), tol)
         so, sol = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF), gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()

@@ -366,5 +366,4 @@ int gb_gauge_unit(gb_gauge *u) {
   for (size_t l = 0; l < (size_t)u->grid->V4 * 4; l++) for (int i = 0; i < 3; i++) h[(l * 9 + 4 * i) * 2] = 1.0;
   return gb_gauge_import(u, h.data(), GB_F64);
 }
-int gb_op_dhop_host(gb_fermop *, const void *, void *, gb_precision, int) { MOCK_UNSUPPORTED("gb_op_dhop_host"); }
 }

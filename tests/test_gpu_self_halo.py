@@ -169,3 +169,37 @@ def test_self_halo_cg_and_mixed_cg_match_the_oracle(ctx):
     _, minfo = po.mixed_cg(orc_d, orc_f, gb.Odd, h, 1e-8, 10000, 50)
     assert mcg.TotalOuterIterations == minfo["outer"]
     assert abs(mcg.TotalInnerIterations - minfo["inner"]) <= max(3, 0.08 * minfo["inner"])   # see tests/test_gpu_parity.py on the 8 %
+
+
+@pytest.mark.parametrize("no_p2p", [False, True], ids=["p2p", "nccl-path"])
+@pytest.mark.parametrize("prec", [gb.F32, gb.F64], ids=["f32", "f64"])
+@pytest.mark.parametrize("mask", ["z", "t", "zt", "x"])
+@pytest.mark.parametrize("shape", ["dwf16", "mobius8"])
+def test_self_halo_host_dhop_pipelined_on_decomposed_lattices(ctx, shape, mask, prec, no_p2p):
+    """gb_op_dhop_host on a z / t / z+t decomposed lattice: the faces the neighbours need (t-slices 0 and Lt-1, z planes 0 and Lz-1
+    of every slice, one strided H2D copy per face) go in first, ONE halo exchange, then the slices stream through H2D / hop / D2H
+    with every slab hop reading the receive buffers -- against the fp64 oracle per site, both daggers, host precision equal to and
+    different from the operator's.  An x split keeps the import + hop + export form (and the same result).
+    ref: FermionOperator::Dhop (FermionOperator.h:75-77) on a decomposed Grid; WilsonFermion5DImplementation.h:386-411"""
+    sh = SHAPES[shape]
+    dims, Ls = sh["dims"], sh["Ls"]
+    grid, D, orc = make(ctx, sh, prec, MASKS[mask], no_p2p=no_p2p)
+    h = syn.random_fermion(dims, Ls, seed=31, dtype=gb._cdtype(prec))
+    for dag in (0, 1):
+        ref = orc.apply(po.OP_DHOP, h.astype(np.complex128), dag=dag)
+        n0 = ctx.launch_count()
+        got = D.Dhop_host(h, np.empty_like(h), dag)
+        n1 = ctx.launch_count()
+        assert site_rel_err(got, ref) < TOL_HOP[prec], (shape, mask, prec, dag)
+        if mask != "x":   # pipelined: one hop launch per t-slice (plus layout kernels and the exchange), not one for the lattice
+            assert n1 - n0 >= 3 * dims[3], (n1 - n0, dims)
+        # a second call reuses receive buffers of the other epoch parity, a third the first again
+        got = D.Dhop_host(h, np.empty_like(h), dag)
+        assert site_rel_err(got, ref) < TOL_HOP[prec], (shape, mask, prec, dag, "second call")
+    other = np.complex128 if prec == gb.F32 else np.complex64
+    got = D.Dhop_host(h.astype(other), np.empty(h.shape, other), 0)
+    assert site_rel_err(got, orc.apply(po.OP_DHOP, h.astype(np.complex128), dag=0)) < TOL_HOP[gb.F32], (shape, mask, "host precision differs")
+    # the device-resident decomposed hop still agrees after the host calls moved the epochs on
+    fin, fout = gb.LatticeFermion(grid, Ls, prec).import_lex(h), gb.LatticeFermion(grid, Ls, prec)
+    D.Dhop(fin, fout, 0)
+    assert site_rel_err(fout.export_lex(), orc.apply(po.OP_DHOP, h.astype(np.complex128), dag=0)) < TOL_HOP[prec]
