@@ -11,8 +11,8 @@ global lattice over z,t like the reference's --mpi 1.1.2.4: N=2 -> 1.1.1.2, N=4 
 value      = whole-job GFlop/s (1320 flop per 5D site, ref Benchmark_dwf_fp32.cc:124), fields resident in HBM,
              CUDA events on the library's compute stream, max over ranks.
 e2e        = same metric through the C ABI with HOST buffers (gb_op_dhop_host): every step moves the source from pinned
-             host memory to the device, runs Dhop and moves the result back; on one rank the three are pipelined over
-             t-slices so H2D and D2H overlap (PCIe full duplex).
+             host memory to the device, runs Dhop and moves the result back; the three are pipelined over t-slices so
+             H2D and D2H overlap (PCIe full duplex) -- at N > 1 too (faces first, one halo exchange, slices streamed).
 roofline   = algorithmic bytes (228 B per 5D site fp32) / measured kernel time vs MEASURED_PEAKS.json.
 cpu_baseline = the reference's own CPU code (oracle/_ref/libgridref.so: unmodified paboyle/Grid compiled by
              oracle/Makefile.ref, AVX2 + OpenMP) timed on the host cores on a bounded sample; kind "reference".

@@ -461,7 +461,7 @@ class FermionOperator:
     def MoeDeriv(self, mat, U, V, dag): assert U.Checkerboard() == Odd; _chk(lib().gb_op_meooe_deriv(self.h, mat.h, U.h, V.h, dag))
 
     def Dhop_host(self, host_in, host_out, dag=0):
-        """Dhop on host-resident full-lattice arrays [V4*Ls,4,3] (lexicographic); pipelined H2D / hop / D2H on one rank."""
+        """Dhop on host-resident full-lattice arrays [V4*Ls,4,3] (lexicographic); pipelined H2D / hop / D2H (on z / t decomposed lattices: faces first, one halo exchange, then the slices stream)."""
         assert host_in.flags.c_contiguous and host_out.flags.c_contiguous and host_in.dtype == host_out.dtype and host_in.shape == host_out.shape
         _chk(lib().gb_op_dhop_host(self.h, host_in.ctypes.data_as(C.c_void_p), host_out.ctypes.data_as(C.c_void_p), _prec_of(host_in), dag))
         return host_out

@@ -209,8 +209,11 @@ int gb_op_Ls(const gb_fermop *op);
 int gb_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
 /* Dhop(in,out,dag) on HOST-resident full-lattice fields (layout at top of file), for callers whose Lattice objects live in
  * host memory (the reference's CPU build; ref: FermionOperator.h:72 Dhop + Lattice_transfer.h:1123,1218 for the layout).
- * Single rank: pipelined over t-slices -- H2D of slice t+1, the hop of slice t and D2H of slice t-1 overlap on three streams,
- * so the call costs one direction of PCIe traffic.  Decomposed lattices: import, hop, export.  Pinned host memory recommended. */
+ * Pipelined over t-slices -- H2D of slice t+1, the hop of slice t and D2H of slice t-1 overlap on separate streams, so the call
+ * costs one direction of PCIe traffic.  On z / t decomposed lattices (each rank passes its LOCAL volume; collective over the
+ * ranks like Dhop itself) the sites the neighbours need go in first (t-slices 0 and Lt-1, z planes 0 and Lz-1 of every slice by
+ * one strided copy per face), the halo exchange runs once, and the slices stream through with every slab hop reading the receive
+ * buffers (GB_HOST_PIPE_DECOMP=0: import, hop, export; also the form of x / y splits).  Pinned host memory recommended. */
 int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_out, gb_precision host_prec, int dag);
 /* The face exchange of one full-lattice Dhop on its own: project + send every face of both parities, then wait for the
  * neighbours' faces (no hopping kernel).  The halo microbenchmark of SURVEY 8(d)/(e): time N calls with gb_timer_start/stop and

@@ -198,7 +198,7 @@ public:
   virtual void MDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { GB_ASSERT_OK(gb_op_mderiv(h, mat.h, U.h, V.h, dag)); }
   virtual void MeoDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { assert(U.Checkerboard() == Even); GB_ASSERT_OK(gb_op_meooe_deriv(h, mat.h, U.h, V.h, dag)); }
   virtual void MoeDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { assert(U.Checkerboard() == Odd); GB_ASSERT_OK(gb_op_meooe_deriv(h, mat.h, U.h, V.h, dag)); }
-  // Dhop on host-resident full-lattice arrays in the reference's unvectorised layout (pipelined H2D / hop / D2H on one rank)
+  // Dhop on host-resident full-lattice arrays in the reference's unvectorised layout (pipelined H2D / hop / D2H, also on z / t decomposed lattices)
   void DhopHost(const void *host_in, void *host_out, gb_precision host_prec, int dag) { GB_ASSERT_OK(gb_op_dhop_host(h, host_in, host_out, host_prec, dag)); }
 };
 template <gb_precision Prec> class WilsonFermionT : public FermionOperator<Prec> {

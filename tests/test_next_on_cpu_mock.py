@@ -45,7 +45,7 @@ def mock_lib(tmp_path_factory):
 
 # every child run of this module, started side by side when the first test asks for one (they are independent processes; run one
 # after the other they take four minutes): name -> (pytest arguments | script, counters to report, extra environment)
-PARITY = ["tests/test_gpu_parity.py", "-k", "not dhop_host and not device_random"]
+PARITY = ["tests/test_gpu_parity.py", "-k", "not device_random"]
 JOBS = {
     "next_rows": (NEXT + ["-k", "not driver"], None, {}),
     "golden": (["tests/test_golden.py"], None, {}),
@@ -54,6 +54,7 @@ JOBS = {
                     ["dhop_col2_kernel", "dhop_col_kernel", "dhop_fast_kernel", "smat_kernel"], {"GB_NO_COL": "1", "GB_MOCK_SM_COUNT": "3"}),
     "two_t_slices": (["tests/test_gpu_parity.py", "tests/test_next_tuned_shapes.py", "-k", "(fast_and_generic and dwf_col) or (edge_shapes and Ls8_n)"],
                      ["dhop_col_kernel<LS, 0, 0, 2>", "dhop_col_kernel<LS, 1, 0, 2>"], {"GB_COL_NT": "2", "GB_COL2": "0"}),
+    "host_dhop": (["tests/test_gpu_self_halo.py", "-k", "host_dhop"], None, {}),
     "n_rank": ("mgpu_on_mock.py", None, {}),
 }
 
@@ -114,7 +115,8 @@ def test_measured_golden_vector_gpu_tests_pass_on_the_cpu_mock(children):
 
 def test_measured_parity_gpu_tests_pass_on_the_cpu_mock(children):
     """tests/test_gpu_parity.py (every operator entry, BLAS, reductions, CG on Wilson 8^4, DWF Ls 8, Moebius Ls 12; green on the B200)
-    -- all but the host-pipelined Dhop and the device RNG, which the mock does not provide.  The fp32 hops go through the
+    -- all but the device RNG, which the mock does not provide; the host-pipelined Dhop runs with copies as memmove and no stream
+    concurrency.  The fp32 hops go through the
     column-sweep kernel, the s-space operators through the dense kernel (launch counters)"""
     n, c = children.passed_and_counts("parity")
     assert n >= 300 and c["dhop_col2_kernel"] > 50 and c["smat_kernel"] > 1000, (n, c)
@@ -125,6 +127,13 @@ def test_micro_block_kernel_and_persistent_s_space_kernel_on_the_cpu_mock(childr
     lattices), and with 3 "SMs" the s-space kernel's persistent CTAs loop over many tiles through their two-stage TMA pipeline"""
     n, c = children.passed_and_counts("micro_block")
     assert n >= 40 and c["dhop_col_kernel"] == 0 and c["dhop_col2_kernel"] == 0 and c["dhop_fast_kernel"] > 30 and c["smat_kernel"] > 100, (n, c)
+
+
+def test_host_pipelined_dhop_on_decomposed_lattices_on_the_cpu_mock(children):
+    """gb_op_dhop_host (dhop_host.cu) with a self halo in z, t, z+t (faces first, one exchange, slab hops reading the receive buffers)
+    and x (import + hop + export), peer-to-peer and NCCL-path code, both precisions: the index arithmetic of the strided z-face import
+    and of the slab hop's halo legs.  Stream / event ordering is the device's to prove (the same tests are green on the B200)."""
+    assert children.passed_and_counts("host_dhop")[0] >= 32
 
 
 def test_two_t_slices_per_cta_column_kernel_on_the_cpu_mock(children):
