@@ -56,9 +56,10 @@ __device__ __forceinline__ void dhop_leg(const DhopArgs &a, const typename Prec<
   if (MODE != 1 && offnode) {
     const uint32_t fi = face_index<MU>(a, c.xh, c.y, c.z, c.t);
     const uint32_t i = fi * a.Ls + c.s;
-    const typename P::vec *hp = (const typename P::vec *)a.halo[FWD ? MU : MU + 4] + (size_t)ip * a.halo_parity_stride[MU] +
-                                ((size_t)(i >> LOGW) * (P::NV / 2) << LOGW) + (i & (W - 1));
-    load_half(chi, hp);
+    const typename P::vec *slot = (const typename P::vec *)a.halo[FWD ? MU : MU + 4] + (size_t)ip * a.halo_parity_stride[MU];
+    const size_t vi = ((size_t)(i >> LOGW) * (P::NV / 2) << LOGW) + (i & (W - 1));
+    if (a.halo_lowp) load_half_lowp(chi, (const typename LowpVec<T>::type *)slot + vi);
+    else load_half(chi, slot + vi);
   } else {
     uint32_t nsite;
     if (MU == 0) {
@@ -169,6 +170,7 @@ struct PackArgs {
   int Ls, Lx, Lxh, Ly, Lz, Lt;
   int ip;              // parity of the packed field
   int origin_parity;
+  int lowp;            // compressed halos (store_half_lowp)
   uint32_t nface;      // face sites (cb) = V4cb / L_mu
 };
 template <class T, int DAG, int MU, int FWD>
@@ -196,7 +198,9 @@ __global__ void pack_face_kernel(const PackArgs a) {
   constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
   HalfReg<T> h;
   sp_proj<MU, SIGN>(h, f);
-  store_half(h, (V *)a.buf + ((size_t)(q >> LOGW) * (P::NV / 2) << LOGW) + (q & (W - 1)));
+  const size_t vi = ((size_t)(q >> LOGW) * (P::NV / 2) << LOGW) + (q & (W - 1));
+  if (a.lowp) store_half_lowp(h, (typename LowpVec<T>::type *)a.buf + vi);
+  else store_half(h, (V *)a.buf + vi);
 }
 
 // =====================================================================================================
@@ -394,6 +398,7 @@ template <class T, int DAG> static void launch_pack(gb_fermop *op, const void *i
   a.in = in_block; a.Ls = op->Ls;
   a.Lx = g->ldims[0]; a.Lxh = a.Lx / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
   a.ip = ip;
+  a.lowp = op->halo_lowp;
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
     a.nface = (uint32_t)(g->V4cb / g->ldims[mu]);
@@ -419,7 +424,8 @@ static void exchange_halos(gb_fermop *op, int nslots, cudaStream_t st) {
   gb_context *ctx = op->ctx;
   std::vector<HaloMsg> msgs;
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {
-    const size_t bytes = (size_t)nslots * op->halo_parity_stride[mu] * 16;
+    // compressed halos fill the first half of each parity slot: the message ends with the last slot's data
+    const size_t bytes = ((size_t)nslots * 16 - (op->halo_lowp ? 8 : 0)) * op->halo_parity_stride[mu];
     // data for the receiver's forward leg (point mu) is my x=0 slice: it travels to my backward neighbour
     msgs.push_back({op->halo_send[mu], op->halo_recv[mu], bytes, g->nbr_rank[mu][1], g->nbr_rank[mu][0]});
     // data for the receiver's backward leg (point mu+4) is my x=L-1 slice: it travels forward
@@ -456,6 +462,7 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   }
   a.axpy_a = axa; a.axpy_b = axb;
   a.comm_dim_mask = op->comm_dim_mask;
+  a.halo_lowp = op->halo_lowp;
   a.Ls = op->Ls; a.Lx = g->ldims[0]; a.Lxh = a.Lx / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
   a.By = pick_block(a.Ly, op->By); a.Bz = pick_block(a.Lz, op->Bz); a.Bt = pick_block(a.Lt, op->Bt);
   a.dLs = FastDiv(a.Ls); a.dLxh = FastDiv(a.Lxh); a.dBy = FastDiv(a.By); a.dBz = FastDiv(a.Bz); a.dBt = FastDiv(a.Bt);
@@ -531,7 +538,10 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
     if (prof) GB_CUDA(cudaEventRecord(qe[0], ctx->stream));
     // fully fused path: ONE launch projects + sends the faces (pack CTAs interleaved at the head of the grid), does the
     // local legs, and surface CTAs acquire the neighbours' flags and add the off-node legs
-    const bool try_fused = op->overlap_comms && !op->no_fused && op->prec == GB_F32 && !op->disable_fast;
+    // (the tuned multi-rank launches read and send uncompressed halos: an operator with compressed halos takes the pack kernel and the
+    //  reference's interior + exterior form -- tuned kernel on the local legs, generic kernel on the surface slabs -- or the serial form)
+    const bool lowp = op->halo_lowp != 0;
+    const bool try_fused = op->overlap_comms && !op->no_fused && op->prec == GB_F32 && !op->disable_fast && !lowp;
     unsigned long long epoch = 0;
     bool hop_sends_t = false;
     // semi-fused: after the pack+send kernel the hop does the local legs and, in its last (surface) CTAs, acquires the
@@ -565,7 +575,7 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       pack_pending = true;
     } else {
       // default: the column-sweep hop sends its own t faces (no re-read of them by the pack kernel), the pack kernel the rest
-      hop_sends_t = op->overlap_comms && semifused && col2_decomp && !op->no_semifused && ((op->comm_dim_mask >> 3) & 1) && g->ldims[3] >= 4 &&
+      hop_sends_t = !lowp && op->overlap_comms && semifused && col2_decomp && !op->no_semifused && ((op->comm_dim_mask >> 3) & 1) && g->ldims[3] >= 4 &&
                     dhop_col2_applicable(op, 1) && !(getenv("GB_HOP_SENDS_T") && atoi(getenv("GB_HOP_SENDS_T")) == 0);
       epoch = p2p_next_epoch(op);
       {
@@ -607,7 +617,7 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
       }
       return;
     }
-    if (op->overlap_comms && semifused && !op->no_semifused && op->prec == GB_F32 && !op->disable_fast && !(op->comm_dim_mask & 3)) {
+    if (!lowp && op->overlap_comms && semifused && !op->no_semifused && op->prec == GB_F32 && !op->disable_fast && !(op->comm_dim_mask & 3)) {
       if (col2_decomp && dhop_col2_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 1, ctx->stream, a.halo, a.flags, epoch)) {
         if (((op->comm_dim_mask >> 2) & 1) && !dhop_col2_zplanes_inkernel()) {
           const bool z0 = dhop_fast_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 5, ctx->stream, a.halo, a.flags, epoch);
@@ -730,6 +740,7 @@ void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int 
   for (int p = 0; p < 2; p++) { a.in[p] = in[p]; a.out[p] = out[p]; a.U[p] = (char *)op->Uds + p * per_parity; a.axpy[p] = nullptr; }
   a.axpy_a = 1; a.axpy_b = 0;
   a.comm_dim_mask = halo ? op->comm_dim_mask : 0;
+  a.halo_lowp = op->halo_lowp;
   a.Ls = op->Ls; a.Lx = g->ldims[0]; a.Lxh = a.Lx / 2; a.Ly = g->ldims[1]; a.Lz = g->ldims[2]; a.Lt = g->ldims[3];
   a.By = a.Ly; a.Bz = a.Lz; a.Bt = a.Lt;
   a.dLs = FastDiv(a.Ls); a.dLxh = FastDiv(a.Lxh); a.dBy = FastDiv(a.By); a.dBz = FastDiv(a.Bz); a.dBt = FastDiv(a.Bt);

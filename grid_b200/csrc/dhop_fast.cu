@@ -160,6 +160,7 @@ bool dhop_col2_applicable(const gb_fermop *op, int mode) {
   if ((g->ldims[0] / 2) % 4 || g->ldims[1] % 4) return false;
   if (mode == 0 && op->comm_dim_mask) return false;
   if (mode == 1 && (op->comm_dim_mask & 3)) return false;
+  if (mode == 1 && op->halo_lowp) return false;   // compressed halos: generic surface kernel (dhop.cu)
   return true;
 }
 bool dhop_col2_launch(gb_fermop *op, const void *const in[2], void *const out[2], int parity_out_first, int nparity, int dag,

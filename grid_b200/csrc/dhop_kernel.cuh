@@ -29,6 +29,7 @@ struct DhopArgs {
   const unsigned long long *flags;
   unsigned long long epoch;
   int comm_dim_mask;   // bit mu set: dimension mu is decomposed over ranks
+  int halo_lowp;       // halos travel one precision down (load_half_lowp): fp32 operators bf16, fp64 operators fp32
   int mode;            // 0 = all legs (single rank or serial comms), 1 = interior legs only, 2 = exterior legs only (accumulate)
   int Ls, Lx, Lxh, Ly, Lz, Lt;
   int By, Bz, Bt;      // rasterisation block extents (divide Ly, Lz, Lt)
@@ -95,6 +96,41 @@ __device__ __forceinline__ void store_half(const HalfReg<float> &h, float4 *__re
 __device__ __forceinline__ void store_half(const HalfReg<double> &h, double2 *__restrict__ p) {
 #pragma unroll
   for (int k = 0; k < 6; k++) p[k << LOGW] = make_double2(h.re[k], h.im[k]);
+}
+// Compressed halos ("half-precision comms"; ref: FermionOperatorImpl.h:96-137 LowerPrecisionMapper / CoeffRealHalfComms,
+// WilsonImpl.h:59-65 SiteHalfCommSpinor, WilsonCompressor.h:244-306, tests/Test_dwf_mixedcg_prec_halfcomms.cc:71 DomainWallFermionFH): the projected half spinor travels one precision down and is widened
+// again by the consumer; arithmetic stays in the operator's precision.  Every 16-byte vec of the uncompressed layout becomes an 8-byte
+// vec at the SAME vec index, so face indexing is unchanged and the bytes on the link halve.  fp64 operators send fp32; fp32 operators
+// send bf16 rather than the reference's fp16: same 16 bits, but fp32's exponent range, so the ever smaller residual vectors of a
+// restarted solve keep their relative precision instead of sinking into fp16's subnormals (the reference leaves its fp16 form disabled).
+template <class T> struct LowpVec;
+template <> struct LowpVec<float> { using type = uint2; };     // 4 x bf16
+template <> struct LowpVec<double> { using type = float2; };   // one complex fp32
+__device__ __forceinline__ uint32_t f32_to_bf16(float x) {     // round to nearest even; NaN stays NaN
+  uint32_t u = __float_as_uint(x);
+  if ((u & 0x7FFFFFFFu) > 0x7F800000u) return (u >> 16) | 0x40u;
+  return (u + 0x7FFFu + ((u >> 16) & 1u)) >> 16;
+}
+__device__ __forceinline__ uint32_t bf16x2(float lo, float hi) { return f32_to_bf16(lo) | (f32_to_bf16(hi) << 16); }
+__device__ __forceinline__ void load_half_lowp(HalfReg<float> &h, const uint2 *p) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const uint2 v = p[k << LOGW];
+    h.re[2 * k] = __uint_as_float(v.x << 16); h.im[2 * k] = __uint_as_float(v.x & 0xFFFF0000u);
+    h.re[2 * k + 1] = __uint_as_float(v.y << 16); h.im[2 * k + 1] = __uint_as_float(v.y & 0xFFFF0000u);
+  }
+}
+__device__ __forceinline__ void load_half_lowp(HalfReg<double> &h, const float2 *p) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) { const float2 v = p[k << LOGW]; h.re[k] = v.x; h.im[k] = v.y; }
+}
+__device__ __forceinline__ void store_half_lowp(const HalfReg<float> &h, uint2 *p) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) p[k << LOGW] = make_uint2(bf16x2(h.re[2 * k], h.im[2 * k]), bf16x2(h.re[2 * k + 1], h.im[2 * k + 1]));
+}
+__device__ __forceinline__ void store_half_lowp(const HalfReg<double> &h, float2 *p) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) p[k << LOGW] = make_float2((float)h.re[k], (float)h.im[k]);
 }
 // stored link: fp32 5 x float4 (18 reals + 2 pad), fp64 9 x double2
 __device__ __forceinline__ void load_link(LinkReg<float> &u, const float4 *__restrict__ p) {

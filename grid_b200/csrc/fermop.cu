@@ -385,6 +385,13 @@ int gb_op_set_fast_kernel(gb_fermop *op, int enable) {
   op->use_smat = enable != 0 && op->sm_B != nullptr;
   return GB_OK;
 }
+int gb_op_set_halo_compression(gb_fermop *op, int on) {
+  GB_API_BEGIN
+  GB_REQUIRE(op != nullptr, "null operator");
+  GB_REQUIRE(op->kind != GB_KIND_STAGGERED, "compressed halos serve the Wilson-type operators (the reference's ...ImplFH / ...ImplDF: fp32 compute with half comms, fp64 compute with fp32 comms)");
+  op->halo_lowp = on != 0;
+  GB_API_END
+}
 int gb_op_set_overlap(gb_fermop *op, int overlap) {
   op->overlap_comms = overlap != 0;
   op->no_semifused = overlap == 2;

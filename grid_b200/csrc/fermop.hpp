@@ -57,6 +57,7 @@ struct gb_fermop {
   bool disable_fast = false;   // force the generic kernel (tests compare the two)
   bool no_col = false;         // fp32: use the micro-block kernel instead of the column-sweep kernel (tests compare them)
   int col_n = 0;               // z-planes per column of the column-sweep kernel (0 = default 16)
+  int halo_lowp = 0;           // gb_op_set_halo_compression: halos one precision down (fp32 -> bf16, fp64 -> fp32); generic multi-rank forms only
   int leg_mask = 0xFF;         // legs of the hopping term that contribute (0xFF always, except inside op_dhop_leg: DhopDir / force terms)
   // multi-GPU: the single-launch pack+hop+halo kernel is EXPERIMENTAL (opt-in with GB_FUSED=1).  It is parity-green on small
   // lattices but can deadlock at 32^4 per GPU: surface CTAs spinning on the neighbours' flags can fill every resident slot

@@ -27,6 +27,7 @@ struct PackSendArgs {
   PackItem item[16];
   int nitems;
   int Ls, Lx, Lxh, Ly, Lz, Lt, origin_parity;
+  int lowp;                       // compressed halos (dhop_kernel.cuh store_half_lowp): half the bytes over the link
   unsigned int *counter;          // last-CTA detection
   unsigned long long *flag[8];    // peer-mapped flag slot per point (nullptr if unused)
   unsigned long long epoch;
@@ -55,7 +56,9 @@ __device__ __forceinline__ void pack_body(const PackSendArgs &a, const PackItem 
   constexpr int SIGN = (FWD ? -1 : +1) * (DAG ? -1 : +1);
   HalfReg<T> h;
   sp_proj<MU, SIGN>(h, f);
-  store_half(h, (V *)it.dst + ((size_t)(q >> LOGW) * (P::NV / 2) << LOGW) + (q & (W - 1)));
+  const size_t vi = ((size_t)(q >> LOGW) * (P::NV / 2) << LOGW) + (q & (W - 1));
+  if (a.lowp) store_half_lowp(h, (typename LowpVec<T>::type *)it.dst + vi);
+  else store_half(h, (V *)it.dst + vi);
 }
 
 template <class T, int DAG> __global__ void __launch_bounds__(256) pack_send_kernel(const PackSendArgs a) {
@@ -204,6 +207,7 @@ void p2p_send_only(gb_fermop *op, unsigned long long epoch, const void *const in
   a.origin_parity = (g->origin[0] + g->origin[1] + g->origin[2] + g->origin[3]) & 1;
   a.counter = S.d_counter;
   a.epoch = epoch;
+  a.lowp = op->halo_lowp;
   uint32_t maxn = 0;
   const bool z_comm = (op->comm_dim_mask >> 2) & 1;
   for (int mu = 0; mu < 4; mu++) if ((op->comm_dim_mask >> mu) & 1) {

@@ -228,6 +228,17 @@ int gb_op_set_tiling(gb_fermop *op, int block_y, int block_z, int block_t);
  * 2: overlapped in the reference's form: interior kernel, then an accumulate pass over the surface slabs;
  * 0: exchange then compute (ref: DhopInternalSerialComms, :388-411) */
 int gb_op_set_overlap(gb_fermop *op, int overlap);
+/* Compressed halos ("half-precision comms"): 1 = the projected half spinors of every face travel one precision below the
+ * operator's -- an fp32 operator sends bf16, an fp64 operator sends fp32 -- and are widened by the consuming leg; the arithmetic stays
+ * in the operator's precision and sites without an off-rank leg are bit-identical.  0 (default) = uncompressed.
+ * ref: FermionOperatorImpl.h:96-137 (LowerPrecisionMapper: vComplexF -> vComplexH, vComplexD -> vComplexF; CoeffRealHalfComms),
+ * WilsonImpl.h:59-65 (SiteHalfCommSpinor), WilsonCompressor.h:244-306 (compressor on _HCspinor; Decompress is "out = in" today),
+ * tests/Test_dwf_mixedcg_prec_halfcomms.cc:71-96 (DomainWallFermionFH as the inner operator of the mixed / reliable-update CG; the
+ * program is compiled out at :33-34).
+ * bf16 instead of the reference's fp16: the same 16 bits with fp32's exponent range, so the shrinking residual vectors of a restarted
+ * solve keep their relative precision (2^-9 per component) instead of underflowing.  A compressed-halo operator takes the pack kernel
+ * plus the interior + exterior (or serial) hop; the fused multi-rank launches stay with uncompressed halos.  Wilson-type operators. */
+int gb_op_set_halo_compression(gb_fermop *op, int on);
 /* fp32 operators: 1 (default) = column-sweep kernel (shared-memory z-column reuse) where it applies, else the micro-block
  * FFMA2 + TMA kernel, else the generic kernel; 2 = skip the column-sweep kernel; 0 = always the generic kernel */
 int gb_op_set_fast_kernel(gb_fermop *op, int enable);

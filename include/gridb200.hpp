@@ -200,6 +200,8 @@ public:
   virtual void MoeDeriv(GaugeField &mat, const FermionField &U, const FermionField &V, int dag) { assert(U.Checkerboard() == Odd); GB_ASSERT_OK(gb_op_meooe_deriv(h, mat.h, U.h, V.h, dag)); }
   // Dhop on host-resident full-lattice arrays in the reference's unvectorised layout (pipelined H2D / hop / D2H, also on z / t decomposed lattices)
   void DhopHost(const void *host_in, void *host_out, gb_precision host_prec, int dag) { GB_ASSERT_OK(gb_op_dhop_host(h, host_in, host_out, host_prec, dag)); }
+  // halos one precision below the operator's (ref: CoeffRealHalfComms, FermionOperatorImpl.h:96-137); see the typedefs ...FH / ...DF below
+  void SetHaloCompression(bool on) { GB_ASSERT_OK(gb_op_set_halo_compression(h, on ? 1 : 0)); }
 };
 template <gb_precision Prec> class WilsonFermionT : public FermionOperator<Prec> {
 public: // ref: WilsonFermion.h:139-142
@@ -244,6 +246,15 @@ typedef ImprovedStaggeredFermionT<GB_F32> ImprovedStaggeredFermionF; typedef Imp
 typedef WilsonFermionT<GB_F32> WilsonFermionF; typedef WilsonFermionT<GB_F64> WilsonFermionD;
 typedef DomainWallFermionT<GB_F32> DomainWallFermionF; typedef DomainWallFermionT<GB_F64> DomainWallFermionD;
 typedef MobiusFermionT<GB_F32> MobiusFermionF; typedef MobiusFermionT<GB_F64> MobiusFermionD;
+// compressed-comms operators (ref: DomainWallFermionFH in tests/Test_dwf_mixedcg_prec_halfcomms.cc:71; impl typedefs ...ImplFH / ...ImplDF, DomainWallVec5dImpl.h:204-206):
+// the same operator with SetHaloCompression(true) from construction
+template <class Base> class CompressedComms : public Base {
+public:
+  template <class... A> CompressedComms(A &&...a) : Base(std::forward<A>(a)...) { this->SetHaloCompression(true); }
+};
+typedef CompressedComms<WilsonFermionF> WilsonFermionFH; typedef CompressedComms<WilsonFermionD> WilsonFermionDF;
+typedef CompressedComms<DomainWallFermionF> DomainWallFermionFH; typedef CompressedComms<DomainWallFermionD> DomainWallFermionDF;
+typedef CompressedComms<MobiusFermionF> MobiusFermionFH; typedef CompressedComms<MobiusFermionD> MobiusFermionDF;
 
 // ---- linear operators (ref: Grid/algorithms/LinearOperator.h:44-56,286-349)
 template <class Field> class LinearOperatorBase {

@@ -47,6 +47,25 @@ for local, Ls, kind in (((8, 8, 8, 8), 16, "dwf"), ((16, 4, 6, 4), 8, "mobius"))
                 ok = e < tol; fails += not ok
                 if rank == 0:
                     print(f"{'ok  ' if ok else 'FAIL'} mpi {mpi} {kind} Ls{Ls} prec{prec} Dhop_host dag{dag} call{call}: {e:.3e}", flush=True)
+        # compressed halos (fp32 operator: bf16 on the wire, fp64 operator: fp32) on real peers: within the comms precision, every form
+        fin = gb.LatticeFermion(grid, Ls, prec).import_lex(h); out = gb.LatticeFermion(grid, Ls, prec)
+        D.set_halo_compression(True)
+        ref = decomp.scatter(orc.apply(po.OP_DHOP, src, dag=0), gd, mpi, rank, inner=Ls)
+        for overlap in (1, 2, 0):
+            D.set_overlap(overlap)
+            D.Dhop(fin, out, 0)
+            e = mx(site_err(out.export_lex(), ref)); lo, hi = (20 * tol, 8e-3 if prec == gb.F32 else 2e-6)
+            ok = lo < e < hi; fails += not ok
+            if rank == 0:
+                print(f"{'ok  ' if ok else 'FAIL'} mpi {mpi} {kind} Ls{Ls} prec{prec} overlap{overlap} Dhop compressed halos: {e:.3e} (expected in ({lo:.0e}, {hi:.0e}))", flush=True)
+        e = mx(site_err(D.Dhop_host(h, np.empty_like(h), 0), ref)); ok = e < hi; fails += not ok
+        if rank == 0:
+            print(f"{'ok  ' if ok else 'FAIL'} mpi {mpi} {kind} Ls{Ls} prec{prec} Dhop_host compressed halos: {e:.3e}", flush=True)
+        D.set_halo_compression(False); D.set_overlap(1)
+        D.Dhop(fin, out, 0)
+        e = mx(site_err(out.export_lex(), ref)); ok = e < tol; fails += not ok
+        if rank == 0:
+            print(f"{'ok  ' if ok else 'FAIL'} mpi {mpi} {kind} Ls{Ls} prec{prec} Dhop after compression switched off: {e:.3e}", flush=True)
 local, Ls = (32, 32, 32, 32), 16
 gd = [l * m for l, m in zip(local, mpi)]
 grid = gb.GridCartesian(ctx, gd, mpi)

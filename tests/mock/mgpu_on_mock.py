@@ -111,6 +111,15 @@ def wilson_like(mpi, gdims, kind, Ls):
             for dag in (0, 1):
                 got = D.Dhop_host(hloc, np.empty_like(hloc), dag)
                 check(rank, f"{tag} prec{prec} Dhop_host dag{dag}", site_err(got, decomp.scatter(ref[("dhop", dag)], gdims, mpi, rank, inner=Ls)), tol)
+            # compressed halos (fp32 operator: bf16 on the wire, fp64 operator: fp32): within the comms precision of the oracle, and back
+            D.set_halo_compression(True)
+            for overlap in (True, False):
+                D.set_overlap(overlap)
+                D.Dhop(fin, out, 1)
+                check(rank, f"{tag} prec{prec} overlap{int(overlap)} Dhop dag1 compressed halos", site_err(out.export_lex(), decomp.scatter(ref[("dhop", 1)], gdims, mpi, rank, inner=Ls)), 8e-3 if prec == gb.F32 else 2e-6)
+            got = D.Dhop_host(hloc, np.empty_like(hloc), 0)
+            check(rank, f"{tag} prec{prec} Dhop_host compressed halos", site_err(got, decomp.scatter(ref[("dhop", 0)], gdims, mpi, rank, inner=Ls)), 8e-3 if prec == gb.F32 else 2e-6)
+            D.set_halo_compression(False); D.set_overlap(True)
             D.Dhop(fin, out, 0)
             check(rank, f"{tag} prec{prec} Dhop after halo_exchange", site_err(out.export_lex(), decomp.scatter(ref[("dhop", 0)], gdims, mpi, rank, inner=Ls)), tol)
         so, sol = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF), gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()

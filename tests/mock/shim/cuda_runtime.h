@@ -16,12 +16,14 @@
 #define __launch_bounds__(...)
 
 struct float2 { float x, y; };
+struct uint2 { uint32_t x, y; };
 struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 struct int4 { int x, y, z, w; };
 struct uint3 { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 inline float2 make_float2(float a, float b) { return {a, b}; }
+inline uint2 make_uint2(uint32_t a, uint32_t b) { return {a, b}; }
 inline float4 make_float4(float a, float b, float c, float d) { return {a, b, c, d}; }
 inline double2 make_double2(double a, double b) { return {a, b}; }
 inline int4 make_int4(int a, int b, int c, int d) { return {a, b, c, d}; }
@@ -30,6 +32,7 @@ template <class T> inline T __ldcs(const T *p) { return *p; }
 template <class T> inline void __stcs(T *p, T v) { *p = v; }
 inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };

@@ -203,3 +203,85 @@ def test_self_halo_host_dhop_pipelined_on_decomposed_lattices(ctx, shape, mask, 
     fin, fout = gb.LatticeFermion(grid, Ls, prec).import_lex(h), gb.LatticeFermion(grid, Ls, prec)
     D.Dhop(fin, fout, 0)
     assert site_rel_err(fout.export_lex(), orc.apply(po.OP_DHOP, h.astype(np.complex128), dag=0)) < TOL_HOP[prec]
+
+
+def _surface_mask(dims, Ls, mask):
+    """sites (x fastest, s innermost of the exported [V4*Ls] order) with at least one leg that leaves the rank in a masked dimension"""
+    idx = np.arange(int(np.prod(dims)))
+    surf = np.zeros(idx.shape, bool)
+    for d in range(4):
+        c = idx % dims[d]; idx = idx // dims[d]
+        if (mask >> d) & 1:
+            surf |= (c == 0) | (c == dims[d] - 1)
+    return np.repeat(surf, Ls)
+
+
+def _site_errs(got, ref):
+    a = got.reshape(got.shape[0], -1).astype(np.complex128); b = ref.reshape(ref.shape[0], -1).astype(np.complex128)
+    return np.linalg.norm(a - b, axis=1) / np.linalg.norm(b, axis=1)
+
+
+@pytest.mark.parametrize("no_p2p", [False, True], ids=["p2p", "nccl-path"])
+@pytest.mark.parametrize("prec", [gb.F32, gb.F64], ids=["f32-bf16", "f64-f32"])
+@pytest.mark.parametrize("mask", ["t", "zt", "xyzt"])
+def test_self_halo_compressed_halos(ctx, mask, prec, no_p2p):
+    """gb_op_set_halo_compression: the projected half spinors of every face travel one precision down (fp32 operator: bf16, fp64
+    operator: fp32) and are widened by the consuming leg.  Sites without an off-rank leg stay within the operator's own tolerance of
+    the fp64 oracle; surface sites within the comms precision (and measurably off the uncompressed result: the compression is on);
+    every multi-rank form (overlapped, interior + exterior, serial), the checkerboard hops and the host-pipelined entry point.
+    ref: FermionOperatorImpl.h:96-137 (CoeffRealHalfComms), WilsonCompressor.h:244-306, DomainWallVec5dImpl.h:204-206 (...ImplFH / DF)"""
+    sh = SHAPES["dwf16"]
+    dims, Ls = sh["dims"], sh["Ls"]
+    grid, D, orc = make(ctx, sh, prec, MASKS[mask], no_p2p=no_p2p)
+    surf = _surface_mask(dims, Ls, MASKS[mask])
+    tol_comm = 8e-3 if prec == gb.F32 else 2e-6          # bf16: 2^-9 per component; fp32: 6e-8 per component
+    src = syn.random_fermion(dims, Ls, seed=41, dtype=gb._cdtype(prec))
+    src64 = src.astype(np.complex128)
+    fin, fout = gb.LatticeFermion(grid, Ls, prec).import_lex(src), gb.LatticeFermion(grid, Ls, prec)
+    ho, r = gb.LatticeFermion(grid, Ls, prec, gb.HALF), gb.LatticeFermion(grid, Ls, prec, gb.HALF)
+    gb.pickCheckerboard(gb.Odd, ho, fin)
+    D.set_halo_compression(True)
+    for overlap in (1, 2, 0):
+        D.set_overlap(overlap)
+        for dag in (0, 1):
+            D.Dhop(fin, fout, dag)
+            e = _site_errs(fout.export_lex(), orc.apply(po.OP_DHOP, src64, dag=dag))
+            assert e[~surf].max() < TOL_HOP[prec], (mask, prec, overlap, dag, "interior sites must not see the compression")
+            assert 20 * TOL_HOP[prec] < e[surf].max() < tol_comm, (mask, prec, overlap, dag, e[surf].max())
+        D.DhopEO(ho, r, 0)
+        full = gb.LatticeFermion(grid, Ls, prec).zero(); gb.setCheckerboard(full, r)
+        eo = orc.apply(po.OP_DHOP_EO, po.pick_checkerboard(dims, Ls, 1, src64))
+        ref = np.zeros(src64.shape, eo.dtype); po.set_checkerboard(dims, Ls, 0, ref, eo)
+        even = np.linalg.norm(ref.reshape(ref.shape[0], -1), axis=1) > 0
+        e = _site_errs(full.export_lex()[even], ref[even])
+        assert e[~surf[even]].max() < TOL_HOP[prec] and e[surf[even]].max() < tol_comm, (mask, prec, overlap, "DhopEO")
+    D.set_overlap(1)
+    e = _site_errs(D.Dhop_host(src, np.empty_like(src), 0), orc.apply(po.OP_DHOP, src64, dag=0))
+    assert e[~surf].max() < TOL_HOP[prec] and 20 * TOL_HOP[prec] < e[surf].max() < tol_comm, (mask, prec, "Dhop_host")
+    D.set_halo_compression(False)
+    D.Dhop(fin, fout, 0)
+    assert _site_errs(fout.export_lex(), orc.apply(po.OP_DHOP, src64, dag=0)).max() < TOL_HOP[prec], "compression off again"
+
+
+def test_self_halo_mixed_cg_with_compressed_halo_inner_operator(ctx):
+    """the reference's Test_dwf_mixedcg_prec_halfcomms.cc:71-96 (compiled out there at :33-34): MixedPrecisionConjugateGradient whose
+    inner fp32 operator exchanges half-precision halos still reaches the fp64 tolerance, because the outer defect correction is done
+    with the uncompressed fp64 operator; the solution agrees with the plain fp64 CG"""
+    sh = SHAPES["mobius8"]
+    dims, Ls = sh["dims"], sh["Ls"]
+    grid, Dd, orc = make(ctx, sh, gb.F64, MASKS["zt"])
+    _, Df, _ = make(ctx, sh, gb.F32, MASKS["zt"], grid=grid)
+    Df.set_halo_compression(True)
+    src = syn.random_fermion(dims, Ls, seed=43)
+    so = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF)
+    gb.pickCheckerboard(gb.Odd, so, gb.LatticeFermion(grid, Ls, gb.F64).import_lex(src))
+    lin_d, lin_f = gb.SchurDiagMooeeOperator(Dd), gb.SchurDiagMooeeOperator(Df)
+    sol_m, sol_d = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero(), gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()
+    mcg = gb.MixedPrecisionConjugateGradient(1e-8, 10000, 50, lin_f, lin_d)
+    mcg.InnerTolerance = 3.0e-5                                     # as the reference's program sets it (:88)
+    mcg(so, sol_m)
+    cg = gb.ConjugateGradient(1e-8, 10000)
+    cg(lin_d, so, sol_d)
+    xm, xd = sol_m.export_lex(), sol_d.export_lex()
+    assert mcg.TrueResidual < 1e-7
+    assert np.linalg.norm((xm - xd).ravel()) / np.linalg.norm(xd.ravel()) < 1e-6
