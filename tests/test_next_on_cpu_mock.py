@@ -158,6 +158,16 @@ def test_cpp_drivers_run_on_the_cpu_mock(mock_lib, name, args, word):
     assert p.returncode == 0 and word in p.stdout, (p.stdout + p.stderr)[-2000:]
 
 
+def test_halfcomms_driver_runs_on_the_cpu_mock(mock_lib):
+    """drivers/Test_dwf_mixedcg_prec_halfcomms.cc (the reference's compiled-out program of that name, enabled): DomainWallFermionFH as the
+    inner operator of the mixed and the reliable-update CG, z / t halos through the halo path (GB_SELF_HALO=12) so that they are compressed"""
+    d = os.path.dirname(mock_lib)
+    exe = os.path.join(d, "Test_dwf_mixedcg_prec_halfcomms")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "drivers", "Test_dwf_mixedcg_prec_halfcomms.cc"), "-L" + d, "-lgridb200_mock", "-Wl,-rpath," + d])
+    p = subprocess.run([exe, "--grid", "4.4.4.4", "--Ls", "4"], capture_output=True, text=True, timeout=900, env=dict(os.environ, GB_SELF_HALO="12"))
+    assert p.returncode == 0 and "done" in p.stdout, (p.stdout + p.stderr)[-2000:]
+
+
 def test_n_rank_parity_on_the_cpu_mock(children):
     """tests/mock/mgpu_on_mock.py: ranks are host threads.  Decomposed Wilson / DWF / Moebius hops with the product's peer-to-peer
     halos (pack_send_kernel stores into the neighbour thread's receive buffer and publishes the epoch flag; the hop acquires it),
