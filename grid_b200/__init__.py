@@ -54,7 +54,7 @@ SYMBOLS = [
     ("gb_op_create_staggered", _i, [_vp, _vp, _vp, _d, _d, _d, _d, _pvp]), ("gb_op_import_gauge_staggered", _i, [_vp, _vp, _vp]),
     ("gb_op_destroy", _i, [_vp]), ("gb_op_Ls", _i, [_vp]), ("gb_op_apply", _i, [_vp, _i, _vp, _vp, _i]),
     ("gb_op_halo_exchange", _i, [_vp, _vp, _i, C.POINTER(C.c_int64)]),
-    ("gb_op_dhop_host", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_halo_compression", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
+    ("gb_op_dhop_host", _i, [_vp, _vp, _vp, _i, _i]), ("gb_op_set_tiling", _i, [_vp, _i, _i, _i]), ("gb_op_set_overlap", _i, [_vp, _i]), ("gb_op_set_halo_compression", _i, [_vp, _i]), ("gb_op_set_link_reconstruct", _i, [_vp, _i]), ("gb_op_set_fast_kernel", _i, [_vp, _i]),
     ("gb_cg_schur", _i, [_vp, _vp, _vp, _d, _i, _pi, _pd]), ("gb_cg", _i, [_vp, HERMOP_FN, _vp, _vp, _vp, _d, _i, _pi, _pd]),
     ("gb_mixed_cg_schur", _i, [_vp, _vp, _vp, _vp, _d, _i, _i, _pi, _pd]),
     ("gb_mixed_cg_schur_ex", _i, [_vp, _vp, _vp, _vp, _d, _d, _d, _i, _i, _pi, _pd]),
@@ -478,6 +478,11 @@ class FermionOperator:
     def set_fast_kernel(self, on):
         """True/1: default kernel selection; 2: micro-block kernel instead of the column-sweep kernel; False/0: generic kernel"""
         lib().gb_op_set_fast_kernel(self.h, int(on))
+
+    def set_link_reconstruct(self, nreal):
+        """12: two rows per link, third row rebuilt in registers (needs special unitary links); 18: full store (default)"""
+        _chk(lib().gb_op_set_link_reconstruct(self.h, int(nreal)))
+        return self
 
     def set_halo_compression(self, on):
         """halos one precision down (fp32 operator: bf16, fp64 operator: fp32), the reference's ...FH / ...DF comms

@@ -78,8 +78,17 @@ __device__ __forceinline__ void dhop_leg(const DhopArgs &a, const typename Prec<
     sp_proj<MU, SIGN>(chi, f);
   }
   LinkReg<T> u;
-  load_link(u, Usite + (FWD ? MU : MU + 4) * P::LV);
-  mult_link(Uchi, u, chi);
+  if (a.recon12) {
+    load_link12(u, Usite + (FWD ? MU : MU + 4) * Recon12<T>::LV);
+    mult_link(Uchi, u, chi);
+    // the factor the full store folds into the link: -1/2, times the boundary phase (its conjugate on the backward link) on the global boundary
+    const int gc = coord + a.origin[MU];
+    const bool bnd = FWD ? (gc == a.gL[MU] - 1) : (gc == 0);
+    scale_half(Uchi, bnd ? (T)a.bnd_re[FWD ? MU : MU + 4] : (T)-0.5, bnd ? (T)a.bnd_im[FWD ? MU : MU + 4] : (T)0);
+  } else {
+    load_link(u, Usite + (FWD ? MU : MU + 4) * P::LV);
+    mult_link(Uchi, u, chi);
+  }
   accum_recon<MU, SIGN>(result, Uchi);
   nleg++;
 }
@@ -121,7 +130,7 @@ __global__ void __launch_bounds__(256) dhop_kernel(const DhopArgs a) {
   c.pb = (p + a.origin_parity + c.y + c.z + c.t) & 1;
 
   const V *__restrict__ in = (const V *)a.in[1 - p];
-  const V *__restrict__ Usite = (const V *)a.U[p] + (size_t)c.site * 8 * P::LV;
+  const V *__restrict__ Usite = (const V *)a.U[p] + (size_t)c.site * 8 * (a.recon12 ? Recon12<T>::LV : P::LV);
   const int ip = 1 - p;
 
   SpinorReg<T> result;
@@ -370,6 +379,7 @@ void op_import_gauge(gb_fermop *op, const gb_gauge *Umu) {
   check_launch(ctx, "double_store");
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int mu = 0; mu < 4; mu++) { if (sendf[mu]) cudaFree(sendf[mu]); if (recvf[mu]) cudaFree(recvf[mu]); }
+  if (op->recon12) op_build_recon12(op);   // a new gauge field: the two-row store follows (and is checked again)
 }
 
 // allocate halo send/recv buffers (both parities) on first use
@@ -444,6 +454,106 @@ template <class T> static void launch_dhop_T(gb_fermop *op, DhopArgs &a, int npa
   check_launch(op->ctx, "dhop");
 }
 
+// link pointers of the generic kernel: the full doubled store, or (gb_op_set_link_reconstruct 12) the two-row store plus what the
+// kernel needs to put the folded-in factors back
+static void fill_link_args(const gb_fermop *op, DhopArgs &a) {
+  const gb_grid *g = op->grid;
+  a.recon12 = op->recon12 && op->Uds12 != nullptr;
+  const size_t per_parity = (size_t)g->V4cb * 8 * (a.recon12 ? (op->prec == GB_F32 ? 3 : 6) : lv_of(op->prec)) * 16;
+  for (int p = 0; p < 2; p++) a.U[p] = (const char *)(a.recon12 ? op->Uds12 : op->Uds) + p * per_parity;
+  for (int d = 0; d < 4; d++) {
+    a.gL[d] = g->gdims[d]; a.origin[d] = g->origin[d];
+    a.bnd_re[d] = -0.5 * op->phases[2 * d]; a.bnd_im[d] = -0.5 * op->phases[2 * d + 1];            // forward link on the global boundary
+    a.bnd_re[d + 4] = -0.5 * op->phases[2 * d]; a.bnd_im[d + 4] = 0.5 * op->phases[2 * d + 1];    // backward link: conjugate phase
+  }
+}
+
+// Two-row link store built from the full doubled store (so the neighbours' backward links are already in place): rows 0 and 1 of
+// every link divided by its folded-in factor.  dev[] receives, per link, how far the third row rebuilt from the two stored ones is
+// from the stored third row -- the links must be special unitary for the reconstruction to be legitimate.
+struct Recon12Args {
+  const void *Uds; void *Uds12; float *dev;
+  int L[4], gL[4], origin[4];
+  double bnd_re[8], bnd_im[8];
+  uint32_t V4cb;
+};
+template <class T> __global__ void recon12_store_kernel(const Recon12Args a) {
+  using P = Prec<T>;
+  using V = typename P::vec;
+  const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; // (parity, site, point)
+  if (e >= 2u * a.V4cb * 8) return;
+  const int pt = e & 7, mu = pt & 3;
+  uint32_t r = e >> 3;
+  const int p = r / a.V4cb;
+  const uint32_t site = r - p * a.V4cb;
+  const int Lxh = a.L[0] / 2;
+  int x[4];
+  uint32_t q = site;
+  const int xh = q % Lxh; q /= Lxh; x[1] = q % a.L[1]; q /= a.L[1]; x[2] = q % a.L[2]; x[3] = q / a.L[2];
+  const int opar = (a.origin[0] + a.origin[1] + a.origin[2] + a.origin[3]) & 1;
+  x[0] = 2 * xh + ((p + opar + x[1] + x[2] + x[3]) & 1);
+  const int gx = x[mu] + a.origin[mu];
+  const bool bnd = pt < 4 ? (gx == a.gL[mu] - 1) : (gx == 0);
+  const double cr = bnd ? a.bnd_re[pt] : -0.5, ci = bnd ? a.bnd_im[pt] : 0.0;
+  const double n = 1.0 / (cr * cr + ci * ci);
+  const T ir = (T)(cr * n), ii = (T)(-ci * n);          // 1 / c
+  LinkReg<T> u;
+  load_link(u, (const V *)a.Uds + (size_t)p * a.V4cb * 8 * P::LV + ((size_t)site * 8 + pt) * P::LV);
+#pragma unroll
+  for (int k = 0; k < 9; k++) { const T re = u.re[k], im = u.im[k]; u.re[k] = ir * re - ii * im; u.im[k] = ir * im + ii * re; }
+  LinkReg<T> w = u;
+  recon_row2(w);
+  T d = 0;
+#pragma unroll
+  for (int k = 6; k < 9; k++) d = fmax(d, fmax(fabs(w.re[k] - u.re[k]), fabs(w.im[k] - u.im[k])));
+  a.dev[e] = (float)d;
+  constexpr int LV12 = Recon12<T>::LV;
+  V *o = (V *)a.Uds12 + (size_t)p * a.V4cb * 8 * LV12 + ((size_t)site * 8 + pt) * LV12;
+  if constexpr (sizeof(T) == 4) {
+    o[0] = make_float4(u.re[0], u.im[0], u.re[1], u.im[1]);
+    o[1] = make_float4(u.re[2], u.im[2], u.re[3], u.im[3]);
+    o[2] = make_float4(u.re[4], u.im[4], u.re[5], u.im[5]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 6; k++) o[k] = make_double2(u.re[k], u.im[k]);
+  }
+}
+// (re)build the two-row store of an operator that asked for it; throws GB_ERR_INVALID (and leaves the full store in use) when the
+// links are not special unitary to working precision
+void op_build_recon12(gb_fermop *op) {
+  gb_context *ctx = op->ctx;
+  const gb_grid *g = op->grid;
+  GB_REQUIRE(op->Uds != nullptr, "operator has no gauge field: call ImportGauge first");
+  GB_CUDA(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)2 * g->V4cb * 8 * (op->prec == GB_F32 ? 3 : 6) * 16;
+  if (!op->Uds12) GB_CUDA(cudaMalloc(&op->Uds12, bytes));
+  const uint32_t n = 2u * (uint32_t)g->V4cb * 8;
+  float *dev = nullptr;
+  GB_CUDA(cudaMalloc(&dev, (size_t)n * sizeof(float)));
+  Recon12Args a;
+  a.Uds = op->Uds; a.Uds12 = op->Uds12; a.dev = dev; a.V4cb = (uint32_t)g->V4cb;
+  DhopArgs la;
+  fill_link_args(op, la);
+  for (int d = 0; d < 4; d++) { a.L[d] = g->ldims[d]; a.gL[d] = la.gL[d]; a.origin[d] = la.origin[d]; }
+  for (int k = 0; k < 8; k++) { a.bnd_re[k] = la.bnd_re[k]; a.bnd_im[k] = la.bnd_im[k]; }
+  if (op->prec == GB_F32) recon12_store_kernel<float><<<(n + 127) / 128, 128, 0, ctx->stream>>>(a);
+  else recon12_store_kernel<double><<<(n + 127) / 128, 128, 0, ctx->stream>>>(a);
+  count_launch(ctx);
+  check_launch(ctx, "recon12_store");
+  std::vector<float> h(n);
+  GB_CUDA(cudaMemcpyAsync(h.data(), dev, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  GB_CUDA(cudaStreamSynchronize(ctx->stream));
+  cudaFree(dev);
+  float worst = 0;
+  for (float v : h) worst = v > worst || v != v ? v : worst;
+  const float tol = op->prec == GB_F32 ? 2e-5f : 1e-12f;
+  if (!(worst <= tol)) {
+    cudaFree(op->Uds12); op->Uds12 = nullptr;
+    throw Error(GB_ERR_INVALID, "12-real link reconstruction needs special unitary links: the third row rebuilt from the first two differs from the stored one by " +
+                                    std::to_string(worst));
+  }
+}
+
 // The one entry used by every operator: hop from the parity blocks in[] to out[].
 //   parity_out_first: output parity of the first (or only) parity; nparity 1 (DhopEO/OE) or 2 (full Dhop)
 //   axpy: optional out = a*hop + b*ax (ax blocks indexed by output parity)
@@ -454,10 +564,9 @@ void dhop_blocks(gb_fermop *op, const void *const in[2], void *const out[2], int
   const gb_grid *g = op->grid;
   GB_CUDA(cudaSetDevice(ctx->device));
   DhopArgs a;
-  const size_t per_parity = (size_t)g->V4cb * 8 * lv_of(op->prec) * 16;
+  fill_link_args(op, a);
   for (int p = 0; p < 2; p++) {
     a.in[p] = in[p]; a.out[p] = out[p];
-    a.U[p] = (char *)op->Uds + p * per_parity;
     a.axpy[p] = ax ? ax[p] : nullptr;
   }
   a.axpy_a = axa; a.axpy_b = axb;
@@ -736,8 +845,8 @@ size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag, const vo
 void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo) {
   const gb_grid *g = op->grid;
   DhopArgs a;
-  const size_t per_parity = (size_t)g->V4cb * 8 * lv_of(op->prec) * 16;
-  for (int p = 0; p < 2; p++) { a.in[p] = in[p]; a.out[p] = out[p]; a.U[p] = (char *)op->Uds + p * per_parity; a.axpy[p] = nullptr; }
+  fill_link_args(op, a);
+  for (int p = 0; p < 2; p++) { a.in[p] = in[p]; a.out[p] = out[p]; a.axpy[p] = nullptr; }
   a.axpy_a = 1; a.axpy_b = 0;
   a.comm_dim_mask = halo ? op->comm_dim_mask : 0;
   a.halo_lowp = op->halo_lowp;

@@ -156,7 +156,7 @@ bool dhop_col2_applicable(const gb_fermop *op, int mode) {
   static const bool disabled = getenv("GB_NO_COL") != nullptr || (getenv("GB_COL2") && atoi(getenv("GB_COL2")) == 0);
   const gb_grid *g = op->grid;
   const int Ls = op->Ls;
-  if (disabled || op->no_col || op->prec != GB_F32 || op->disable_fast || !(Ls == 8 || Ls == 12 || Ls == 16)) return false;
+  if (disabled || op->no_col || op->prec != GB_F32 || op->disable_fast || op->recon12 || !(Ls == 8 || Ls == 12 || Ls == 16)) return false;
   if ((g->ldims[0] / 2) % 4 || g->ldims[1] % 4) return false;
   if (mode == 0 && op->comm_dim_mask) return false;
   if (mode == 1 && (op->comm_dim_mask & 3)) return false;
@@ -274,7 +274,7 @@ bool dhop_fast_launch(gb_fermop *op, const void *const in[2], void *const out[2]
                       const void *const ax[2], double axa, double axb, int interior, cudaStream_t st, const void *const halo[8],
                       const unsigned long long *flags, unsigned long long epoch) {
   const gb_grid *g = op->grid;
-  if (op->prec != GB_F32 || op->disable_fast) return false;
+  if (op->prec != GB_F32 || op->disable_fast || op->recon12) return false;   // (two-row links: generic kernel)
   if (interior == 0 && dhop_col2_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, 0, st, nullptr, nullptr, 0)) return true;
   if (interior < 3 && dhop_col_launch(op, in, out, parity_out_first, nparity, dag, ax, axa, axb, interior, st)) return true;
   const int Ls = op->Ls;

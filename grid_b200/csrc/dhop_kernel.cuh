@@ -29,6 +29,12 @@ struct DhopArgs {
   const unsigned long long *flags;
   unsigned long long epoch;
   int comm_dim_mask;   // bit mu set: dimension mu is decomposed over ranks
+  // 12-real link storage (gb_op_set_link_reconstruct): U[] then holds two rows of the bare SU(3) matrices (Recon12<T>::LV vecs per link),
+  // the third row is rebuilt in registers and the folded-in factor (-1/2, times the boundary phase on the global boundary) is applied
+  // to the product: link_c = {re, im} per stencil point on the boundary, (-1/2, 0) elsewhere
+  int recon12;
+  int gL[4], origin[4];
+  double bnd_re[8], bnd_im[8];
   int halo_lowp;       // halos travel one precision down (load_half_lowp): fp32 operators bf16, fp64 operators fp32
   int mode;            // 0 = all legs (single rank or serial comms), 1 = interior legs only, 2 = exterior legs only (accumulate)
   int Ls, Lx, Lxh, Ly, Lz, Lt;
@@ -144,6 +150,35 @@ __device__ __forceinline__ void load_link(LinkReg<float> &u, const float4 *__res
 __device__ __forceinline__ void load_link(LinkReg<double> &u, const double2 *__restrict__ p) {
 #pragma unroll
   for (int k = 0; k < 9; k++) { double2 v = __ldg(p + k); u.re[k] = v.x; u.im[k] = v.y; }
+}
+
+// 12-real links: rows 0 and 1 stored (fp32 3 x float4, fp64 6 x double2), row 2 = conj(row0 x row1) for a special unitary matrix
+template <class T> struct Recon12 { static constexpr int LV = sizeof(T) == 4 ? 3 : 6; };
+template <class T> __device__ __forceinline__ void recon_row2(LinkReg<T> &u) {
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    const int c1 = (c + 1) % 3, c2 = (c + 2) % 3;
+    // (row0 x row1)_c = u0[c1] u1[c2] - u0[c2] u1[c1], conjugated
+    const T re = (u.re[c1] * u.re[3 + c2] - u.im[c1] * u.im[3 + c2]) - (u.re[c2] * u.re[3 + c1] - u.im[c2] * u.im[3 + c1]);
+    const T im = (u.re[c1] * u.im[3 + c2] + u.im[c1] * u.re[3 + c2]) - (u.re[c2] * u.im[3 + c1] + u.im[c2] * u.re[3 + c1]);
+    u.re[6 + c] = re; u.im[6 + c] = -im;
+  }
+}
+__device__ __forceinline__ void load_link12(LinkReg<float> &u, const float4 *__restrict__ p) {
+  const float4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+  u.re[0] = v0.x; u.im[0] = v0.y; u.re[1] = v0.z; u.im[1] = v0.w;
+  u.re[2] = v1.x; u.im[2] = v1.y; u.re[3] = v1.z; u.im[3] = v1.w;
+  u.re[4] = v2.x; u.im[4] = v2.y; u.re[5] = v2.z; u.im[5] = v2.w;
+  recon_row2(u);
+}
+__device__ __forceinline__ void load_link12(LinkReg<double> &u, const double2 *__restrict__ p) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) { const double2 v = __ldg(p + k); u.re[k] = v.x; u.im[k] = v.y; }
+  recon_row2(u);
+}
+template <class T> __device__ __forceinline__ void scale_half(HalfReg<T> &h, T cr, T ci) {
+#pragma unroll
+  for (int k = 0; k < 6; k++) { const T re = h.re[k], im = h.im[k]; h.re[k] = cr * re - ci * im; h.im[k] = cr * im + ci * re; }
 }
 
 // ------------------------------------------------------------------ spin projection: h = (1 + SIGN*gamma_MU) f, upper two components

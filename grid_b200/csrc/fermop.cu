@@ -352,6 +352,7 @@ int gb_op_import_gauge(gb_fermop *op, const gb_gauge *Umu) {
 int gb_op_destroy(gb_fermop *op) {
   if (!op) return GB_OK;
   cudaFree(op->Uds);
+  cudaFree(op->Uds12);
   cudaFree(op->stag_links);
   for (int i = 0; i < 8; i++) { if (op->halo_send[i]) cudaFree(op->halo_send[i]); if (op->halo_recv[i]) cudaFree(op->halo_recv[i]); }
   p2p_teardown(op);
@@ -384,6 +385,16 @@ int gb_op_set_fast_kernel(gb_fermop *op, int enable) {
   op->no_col = enable == 2;
   op->use_smat = enable != 0 && op->sm_B != nullptr;
   return GB_OK;
+}
+int gb_op_set_link_reconstruct(gb_fermop *op, int nreal) {
+  GB_API_BEGIN
+  GB_REQUIRE(op != nullptr, "null operator");
+  GB_REQUIRE(nreal == 18 || nreal == 12, "links are stored with 18 reals (full) or 12 (two rows, third row rebuilt)");
+  GB_REQUIRE(op->kind != GB_KIND_STAGGERED, "link reconstruction serves the Wilson-type operators (fat staggered links are not unitary)");
+  if (nreal == 18) { op->recon12 = 0; return GB_OK; }
+  op->recon12 = 1;
+  try { op_build_recon12(op); } catch (...) { op->recon12 = 0; throw; }
+  GB_API_END
 }
 int gb_op_set_halo_compression(gb_fermop *op, int on) {
   GB_API_BEGIN

@@ -46,6 +46,8 @@ struct gb_fermop {
   double mass = 0, M5 = 0;
   double phases[8] = {1, 0, 1, 0, 1, 0, 1, 0};
   gb::CayleyCoeffs k;
+  void *Uds12 = nullptr;       // gb_op_set_link_reconstruct(12): two rows of the bare SU(3) links, [2][V4cb][8][3 float4 | 6 double2] (generic kernel)
+  int recon12 = 0;
   void *Uds = nullptr; // doubled links [2 parities][V4cb][8][LV] vecs, -1/2 and phases folded in
   size_t uds_bytes = 0;
   // rasterisation blocking of the hopping kernel (0 = whole extent)
@@ -144,6 +146,7 @@ bool cg_fused_available(const gb_fermop *op);
 void cg_fused_first(gb_fermop *op, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, const double *d_c, const double *d_d, const double *d_cp);
 void cg_fused_rest(gb_fermop *op, const gb_fermion *p, gb_fermion *r, const double *d_c, double *d_d, double *d_cp);
 
+void op_build_recon12(gb_fermop *op);   // dhop.cu: (re)build and check the two-row link store
 size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag, const void **halo_out = nullptr);   // halo_out[8]: the receive buffers, complete in stream order
 void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo = nullptr);
 // improved staggered operator entry points (stag.cu)

@@ -228,6 +228,14 @@ int gb_op_set_tiling(gb_fermop *op, int block_y, int block_z, int block_t);
  * 2: overlapped in the reference's form: interior kernel, then an accumulate pass over the surface slabs;
  * 0: exchange then compute (ref: DhopInternalSerialComms, :388-411) */
 int gb_op_set_overlap(gb_fermop *op, int overlap);
+/* Link storage of the hopping term: 18 (default) = the full doubled 3x3 store with -1/2 and the boundary phases folded in;
+ * 12 = two rows of the bare SU(3) matrix per link, the third row rebuilt in registers as conj(row0 x row1) and the folded-in factor
+ * applied to the product (the north star's "optional 12-real SU(3) link reconstruction"; the reference always stores 18 reals,
+ * WilsonImpl.h:127-171 DoubleStore).  Trades a third of the link bytes for ~60 flops per link; it takes the generic kernel (any Ls,
+ * both precisions, every multi-rank form), so it pays where links dominate the traffic -- 4D Wilson, small Ls -- not at Ls = 16 where the
+ * tuned kernels already reuse each link across the fifth dimension.  Needs a gauge field (call after creation / ImportGauge; a later
+ * ImportGauge rebuilds it) whose links are special unitary to working precision: otherwise GB_ERR_INVALID and the full store stays. */
+int gb_op_set_link_reconstruct(gb_fermop *op, int nreal);
 /* Compressed halos ("half-precision comms"): 1 = the projected half spinors of every face travel one precision below the
  * operator's -- an fp32 operator sends bf16, an fp64 operator sends fp32 -- and are widened by the consuming leg; the arithmetic stays
  * in the operator's precision and sites without an off-rank leg are bit-identical.  0 (default) = uncompressed.

@@ -201,6 +201,8 @@ public:
   // Dhop on host-resident full-lattice arrays in the reference's unvectorised layout (pipelined H2D / hop / D2H, also on z / t decomposed lattices)
   void DhopHost(const void *host_in, void *host_out, gb_precision host_prec, int dag) { GB_ASSERT_OK(gb_op_dhop_host(h, host_in, host_out, host_prec, dag)); }
   // halos one precision below the operator's (ref: CoeffRealHalfComms, FermionOperatorImpl.h:96-137); see the typedefs ...FH / ...DF below
+  // 12: two-row link storage with the third row rebuilt in registers (special unitary links only); 18: the full store
+  void SetLinkReconstruct(int nreal) { GB_ASSERT_OK(gb_op_set_link_reconstruct(h, nreal)); }
   void SetHaloCompression(bool on) { GB_ASSERT_OK(gb_op_set_halo_compression(h, on ? 1 : 0)); }
 };
 template <gb_precision Prec> class WilsonFermionT : public FermionOperator<Prec> {

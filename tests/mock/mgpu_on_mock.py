@@ -52,12 +52,12 @@ def run_ranks(world, body):
     return errs
 
 
-def wilson_like(mpi, gdims, kind, Ls):
+def wilson_like(mpi, gdims, kind, Ls, phases=None):
     world = int(np.prod(mpi))
     U = syn.hot_gauge(gdims, seed=3)
     src = syn.random_fermion(gdims, Ls, seed=4)
     orc = po.OracleOp(0 if kind == "wilson" else 1, gdims, Ls, mass=0.1, M5=1.8, b=1.5 if kind == "mobius" else 1.0, c=0.5 if kind == "mobius" else 0.0, prec=1)
-    orc.import_gauge(U)
+    orc.import_gauge(U, phases)
     ref = {("dhop", d): orc.apply(po.OP_DHOP, src, dag=d) for d in (0, 1)}
     ref["M"] = orc.apply(po.OP_M, src)
     src_o = po.pick_checkerboard(gdims, Ls, 1, src)
@@ -73,8 +73,8 @@ def wilson_like(mpi, gdims, kind, Ls):
         tag = f"mpi {mpi} {kind} Ls{Ls}"
         for prec, tol in ((gb.F32, 1e-6), (gb.F64, 1e-13)):
             Umu = gb.LatticeGaugeField(grid, prec).import_lex(decomp.scatter(U, gdims, mpi, rank))
-            D = gb.WilsonFermion(Umu, grid, 0.1) if kind == "wilson" else gb.DomainWallFermion(Umu, grid, Ls, 0.1, 1.8) if kind == "dwf" else \
-                gb.MobiusFermion(Umu, grid, Ls, 0.1, 1.8, 1.5, 0.5)
+            D = gb.WilsonFermion(Umu, grid, 0.1, phases) if kind == "wilson" else gb.DomainWallFermion(Umu, grid, Ls, 0.1, 1.8, phases) if kind == "dwf" else \
+                gb.MobiusFermion(Umu, grid, Ls, 0.1, 1.8, 1.5, 0.5, phases)
             fin = gb.LatticeFermion(grid, Ls, prec).import_lex(decomp.scatter(src, gdims, mpi, rank, inner=Ls).astype(gb._cdtype(prec)))
             out = gb.LatticeFermion(grid, Ls, prec)
             for overlap in (True, False):
@@ -120,6 +120,13 @@ def wilson_like(mpi, gdims, kind, Ls):
             got = D.Dhop_host(hloc, np.empty_like(hloc), 0)
             check(rank, f"{tag} prec{prec} Dhop_host compressed halos", site_err(got, decomp.scatter(ref[("dhop", 0)], gdims, mpi, rank, inner=Ls)), 8e-3 if prec == gb.F32 else 2e-6)
             D.set_halo_compression(False); D.set_overlap(True)
+            # two-row links (third row rebuilt in registers; the folded-in factor and boundary phase go on by GLOBAL coordinate)
+            D.set_link_reconstruct(12)
+            for overlap in (True, False):
+                D.set_overlap(overlap)
+                D.Dhop(fin, out, 1)
+                check(rank, f"{tag} prec{prec} overlap{int(overlap)} Dhop dag1 two-row links", site_err(out.export_lex(), decomp.scatter(ref[("dhop", 1)], gdims, mpi, rank, inner=Ls)), tol)
+            D.set_link_reconstruct(18); D.set_overlap(True)
             D.Dhop(fin, out, 0)
             check(rank, f"{tag} prec{prec} Dhop after halo_exchange", site_err(out.export_lex(), decomp.scatter(ref[("dhop", 0)], gdims, mpi, rank, inner=Ls)), tol)
         so, sol = gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF), gb.LatticeFermion(grid, Ls, gb.F64, gb.HALF).zero()
@@ -197,6 +204,9 @@ def main():
         errs += staggered(mpi, tuple(max(4 * m, 8) if m > 1 else (6 if d == 1 else 4) for d, m in enumerate(mpi)))
         print(f"mpi {mpi}: done, {len(fails) + len(errs)} problems so far", flush=True)
     errs += staggered((1, 1, 1, 4), (4, 4, 4, 16))       # distinct forward / backward neighbours
+    # boundary phases on a decomposed lattice: they sit on the GLOBAL boundary links (full store: gauge-face exchange; two-row store: by coordinate)
+    errs += wilson_like((1, 1, 2, 2), (4, 4, 8, 8), "dwf", 4, phases=[1, np.exp(0.4j), -1, np.exp(-0.9j)])
+    errs += wilson_like((2, 1, 1, 1), (8, 4, 4, 4), "wilson", 1, phases=[-1, 1, 1, 1])
     # the tuned fp32 kernels on decomposed lattices (Ls = 8, local 8.4.4.4): pack_send into the neighbours' buffers, then the
     # semi-fused hop (z / t split: one launch, surface CTAs acquire the flags) or interior + exterior (x / y split)
     import ctypes
