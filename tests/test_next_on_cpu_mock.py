@@ -55,6 +55,7 @@ JOBS = {
     "two_t_slices": (["tests/test_gpu_parity.py", "tests/test_next_tuned_shapes.py", "-k", "(fast_and_generic and dwf_col) or (edge_shapes and Ls8_n)"],
                      ["dhop_col_kernel<LS, 0, 0, 2>", "dhop_col_kernel<LS, 1, 0, 2>"], {"GB_COL_NT": "2", "GB_COL2": "0"}),
     "host_dhop": (["tests/test_gpu_self_halo.py", "-k", "host_dhop"], None, {}),
+    "optional_forms": (["tests/test_gpu_recon12.py", "tests/test_gpu_self_halo.py", "-k", "recon12 or (compressed_halos and zt and nccl)"], None, {}),
     "n_rank": ("mgpu_on_mock.py", None, {}),
 }
 
@@ -134,6 +135,12 @@ def test_host_pipelined_dhop_on_decomposed_lattices_on_the_cpu_mock(children):
     and x (import + hop + export), peer-to-peer and NCCL-path code, both precisions: the index arithmetic of the strided z-face import
     and of the slab hop's halo legs.  Stream / event ordering is the device's to prove (the same tests are green on the B200)."""
     assert children.passed_and_counts("host_dhop")[0] >= 32
+
+
+def test_optional_forms_on_the_cpu_mock(children):
+    """two-row (12-real) link storage (tests/test_gpu_recon12.py: every operator entry, boundary phases, decomposed lattice, the refusal of
+    links that are not special unitary) and compressed halos (bf16 / fp32 on the wire; the mixed CG with the compressed inner operator runs here as the halfcomms driver)"""
+    assert children.passed_and_counts("optional_forms")[0] >= 25
 
 
 def test_two_t_slices_per_cta_column_kernel_on_the_cpu_mock(children):
