@@ -530,6 +530,7 @@ void op_build_recon12(gb_fermop *op) {
   const uint32_t n = 2u * (uint32_t)g->V4cb * 8;
   float *dev = nullptr;
   GB_CUDA(cudaMalloc(&dev, (size_t)n * sizeof(float)));
+  struct Free { float *p; ~Free() { cudaFree(p); } } free_dev{dev};   // also on the error paths below
   Recon12Args a;
   a.Uds = op->Uds; a.Uds12 = op->Uds12; a.dev = dev; a.V4cb = (uint32_t)g->V4cb;
   DhopArgs la;
@@ -543,7 +544,6 @@ void op_build_recon12(gb_fermop *op) {
   std::vector<float> h(n);
   GB_CUDA(cudaMemcpyAsync(h.data(), dev, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   GB_CUDA(cudaStreamSynchronize(ctx->stream));
-  cudaFree(dev);
   float worst = 0;
   for (float v : h) worst = v > worst || v != v ? v : worst;
   const float tol = op->prec == GB_F32 ? 2e-5f : 1e-12f;
