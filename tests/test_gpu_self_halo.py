@@ -174,7 +174,7 @@ def test_self_halo_cg_and_mixed_cg_match_the_oracle(ctx):
 @pytest.mark.parametrize("no_p2p", [False, True], ids=["p2p", "nccl-path"])
 @pytest.mark.parametrize("prec", [gb.F32, gb.F64], ids=["f32", "f64"])
 @pytest.mark.parametrize("mask", ["z", "t", "zt", "x"])
-@pytest.mark.parametrize("shape", ["dwf16", "mobius8"])
+@pytest.mark.parametrize("shape", ["dwf16", "mobius8", "wilson"])
 def test_self_halo_host_dhop_pipelined_on_decomposed_lattices(ctx, shape, mask, prec, no_p2p):
     """gb_op_dhop_host on a z / t / z+t decomposed lattice: the faces the neighbours need (t-slices 0 and Lt-1, z planes 0 and Lz-1
     of every slice, one strided H2D copy per face) go in first, ONE halo exchange, then the slices stream through H2D / hop / D2H
