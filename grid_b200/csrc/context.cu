@@ -70,6 +70,7 @@ void device_global_sum(gb_context *ctx, double *d_vals, int n) {
 }
 } // namespace gb
 
+namespace gb { void host_pipe_release(gb_context *ctx); }   // dhop_host.cu
 using namespace gb;
 
 __global__ void gb_l2_flush_kernel(float4 *p, size_t n) {
@@ -128,6 +129,7 @@ int gb_context_destroy(gb_context *c) {
   gb::live_contexts().erase(c);
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
+  gb::host_pipe_release(c);
   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
   cudaFree(c->d_partials); cudaFree(c->d_result); cudaFreeHost(c->h_result); cudaFree(c->d_scalars); cudaEventDestroy(c->ev_scalar);
   if (c->l2_scratch) cudaFree(c->l2_scratch);

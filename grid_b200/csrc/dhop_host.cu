@@ -90,11 +90,11 @@ struct HostPipe {          // per-context scratch of the pipelined path (grow-on
   cudaEvent_t ev_copied[NB] = {}, ev_xin_done[NB] = {}, ev_packed[NB] = {}, ev_out_copied[NB] = {}, ev_done = nullptr, ev_face_copied = nullptr,
               ev_faces = nullptr;
 };
+std::mutex pipes_mu;     // one pipe per context (one context per process in this library's usage: one process per GPU)
+std::map<gb_context *, HostPipe> &pipes() { static std::map<gb_context *, HostPipe> m; return m; }
 HostPipe &host_pipe(gb_context *ctx, size_t slab_bytes, size_t face_bytes, int nslab) {
-  static std::mutex mu;     // one pipe per context (one context per process in this library's usage: one process per GPU)
-  static std::map<gb_context *, HostPipe> pipes;
-  std::unique_lock<std::mutex> lk(mu);
-  HostPipe &P = pipes[ctx];
+  std::unique_lock<std::mutex> lk(pipes_mu);
+  HostPipe &P = pipes()[ctx];
   lk.unlock();
   if (!P.h2d) {
     GB_CUDA(cudaStreamCreateWithFlags(&P.h2d, cudaStreamNonBlocking));
@@ -150,6 +150,27 @@ template <int DIR> void slab_transfer(gb_context *ctx, const gb_fermion *f, void
   launch_transfer<DIR>(ctx, f, stage, host_prec, (int64_t)t * nblk, nblk, (int64_t)t * 2 * v3cb * f->Ls, 1, 0, 0, st);
 }
 } // namespace
+
+// called by gb_context_destroy (context.cu) with the device idle: streams, events and staging buffers of that context's pipe
+namespace gb {
+void host_pipe_release(gb_context *ctx) {
+  std::unique_lock<std::mutex> lk(pipes_mu);
+  auto it = pipes().find(ctx);
+  if (it == pipes().end()) return;
+  HostPipe &P = it->second;
+  for (int i = 0; i < HostPipe::NB; i++) {
+    if (P.stage_in[i]) cudaFree(P.stage_in[i]);
+    if (P.stage_out[i]) cudaFree(P.stage_out[i]);
+    for (cudaEvent_t e : {P.ev_copied[i], P.ev_xin_done[i], P.ev_packed[i], P.ev_out_copied[i]}) if (e) cudaEventDestroy(e);
+  }
+  if (P.stage_face) cudaFree(P.stage_face);
+  for (cudaEvent_t e : {P.ev_done, P.ev_face_copied, P.ev_faces}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : P.ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : P.ev_hop) cudaEventDestroy(e);
+  for (cudaStream_t s : {P.h2d, P.d2h, P.xin, P.xout}) if (s) cudaStreamDestroy(s);
+  pipes().erase(it);
+}
+} // namespace gb
 
 extern "C" int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_out, gb_precision host_prec, int dag) {
   GB_API_BEGIN

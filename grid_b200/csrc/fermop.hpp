@@ -146,6 +146,7 @@ bool cg_fused_available(const gb_fermop *op);
 void cg_fused_first(gb_fermop *op, gb_fermion *psi, gb_fermion *p, const gb_fermion *r, const double *d_c, const double *d_d, const double *d_cp);
 void cg_fused_rest(gb_fermop *op, const gb_fermion *p, gb_fermion *r, const double *d_c, double *d_d, double *d_cp);
 
+void host_pipe_release(gb_context *ctx);   // dhop_host.cu: scratch of the host-pipelined Dhop of a context that is being destroyed
 void op_build_recon12(gb_fermop *op);   // dhop.cu: (re)build and check the two-row link store
 size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag, const void **halo_out = nullptr);   // halo_out[8]: the receive buffers, complete in stream order
 void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo = nullptr);

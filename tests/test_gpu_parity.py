@@ -422,3 +422,21 @@ def test_blas_rejects_fields_on_different_checkerboards(ctx):
             f()
     gb.axpy(z, 1.0, e, e)                       # same checkerboard: fine, and the result carries it
     assert z.Checkerboard() == gb.Even
+
+
+def test_dhop_host_scratch_follows_the_context_lifetime():
+    """streams, events and staging buffers of the host-pipelined Dhop belong to a context: destroying it releases them, and a new
+    context (which may get the same address) starts from a fresh pipe"""
+    dims, Ls = (8, 8, 8, 8), 8
+    U = syn.hot_gauge(dims, seed=91)
+    h = syn.random_fermion(dims, Ls, seed=92, dtype=np.complex64)
+    orc = po.OracleOp(1, dims, Ls, mass=0.1, M5=1.8, prec=1)
+    orc.import_gauge(U)
+    ref = orc.apply(po.OP_DHOP, h.astype(np.complex128), dag=0)
+    for _ in range(3):
+        c = gb.Context(0)
+        grid = gb.GridCartesian(c, dims)
+        D = gb.DomainWallFermion(gb.LatticeGaugeField(grid, gb.F32).import_lex(U), grid, Ls, 0.1, 1.8)
+        assert site_rel_err(D.Dhop_host(h, np.empty_like(h), 0), ref) < TOL_HOP[gb.F32]
+        del D, grid
+        c.close()
