@@ -3,7 +3,8 @@
 tests/mock/README.md).  The N-rank result (overlapped = semi-fused where it applies, overlapped as interior + exterior, serial) of
 Dhop +-dag and DhopEO must agree per site with the SAME library run on one rank over the global lattice.  fp32, Ls 8 / 12 / 16 (tuned
 kernels) and Ls 4 (generic kernel).  Not part of the test suite (open-ended); run by hand when the halo code or a tuned kernel changes.
-usage: fuzz_ranks.py <libgridb200_mock.so> <seed> <seconds>   (last recorded run: 3 seeds x 150 s = 905 cases, 0 disagreements)"""
+The optional forms ride along: gb_op_dhop_host (pipelined on z / t splits), two-row links, compressed halos.
+usage: fuzz_ranks.py <libgridb200_mock.so> <seed> <seconds>   (recorded runs: 3 seeds x 150 s = 905 cases, 0 disagreements; with the optional forms: see tests/mock/README.md)"""
 import os
 import random
 import sys
@@ -81,6 +82,25 @@ while time.time() < t_end:
                 if not e < 4e-6:
                     with lock:
                         bad.append((tag, rank, f"overlap {overlap} DhopEO", e))
+            # the optional forms on the same decomposition: host-buffer entry point (pipelined on z / t splits), two-row links
+            # (same bar as the full store), compressed halos (bf16 on the wire: within 8e-3, and not better than fp32 roundoff
+            # would be only if no leg left the rank)
+            D.set_overlap(1)
+            hloc = decomp.scatter(src, gdims, mpi, rank, inner=Ls)
+            want = decomp.scatter(ref[0], gdims, mpi, rank, inner=Ls)
+            for form, setup, tol in (("Dhop_host", lambda: None, 4e-6), ("two-row links", lambda: D.set_link_reconstruct(12), 4e-6),
+                                     ("two-row links Dhop_host", lambda: None, 4e-6), ("compressed halos", lambda: (D.set_link_reconstruct(18), D.set_halo_compression(True)), 8e-3),
+                                     ("compressed halos Dhop_host", lambda: None, 8e-3)):
+                setup()
+                if "Dhop_host" in form:
+                    got = D.Dhop_host(hloc, np.empty_like(hloc), 0)
+                else:
+                    D.Dhop(fin, out, 0); got = out.export_lex()
+                e = err(got, want)
+                if not e < tol:
+                    with lock:
+                        bad.append((tag, rank, form, e))
+            D.set_halo_compression(False)
         except Exception as ex:     # noqa: BLE001
             with lock:
                 bad.append((tag, rank, f"{type(ex).__name__}: {ex}", 0.0))
