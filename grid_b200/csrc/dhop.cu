@@ -842,7 +842,8 @@ size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag, const vo
 // inside the local volume).  halo != nullptr (decomposed lattice): the legs that leave the rank read the receive buffers of a halo
 // exchange that has COMPLETED in front of this launch on `st` (halo_exchange_only: both input parities, slot = parity).
 // Used by the host-pipelined Dhop (dhop_host.cu), where slices are computed as their neighbours arrive over PCIe.
-void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo) {
+void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo,
+                int z0, int nz) {
   const gb_grid *g = op->grid;
   DhopArgs a;
   fill_link_args(op, a);
@@ -861,10 +862,11 @@ void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int 
   a.mode = 0; a.flags = nullptr; a.epoch = 0;
   a.leg_mask = halo ? op->leg_mask : 0xFF;
   a.box_on = 1;
-  a.bo[0] = 0; a.bo[1] = 0; a.bo[2] = 0; a.bo[3] = t0;
-  a.be[0] = a.Lxh; a.be[1] = a.Ly; a.be[2] = a.Lz; a.be[3] = nt;
+  if (nz < 0) { z0 = 0; nz = a.Lz; }                       // the planes [z0, z0 + nz) of those slices (default: all)
+  a.bo[0] = 0; a.bo[1] = 0; a.bo[2] = z0; a.bo[3] = t0;
+  a.be[0] = a.Lxh; a.be[1] = a.Ly; a.be[2] = nz; a.be[3] = nt;
   a.dbe0 = FastDiv(a.be[0]); a.dbe1 = FastDiv(a.be[1]); a.dbe2 = FastDiv(a.be[2]);
-  a.n5cb = (uint32_t)((size_t)a.Lxh * a.Ly * a.Lz * nt * op->Ls);
+  a.n5cb = (uint32_t)((size_t)a.Lxh * a.Ly * nz * nt * op->Ls);
   if (op->prec == GB_F32) launch_dhop_T<float>(op, a, 2, dag, 0, st);
   else launch_dhop_T<double>(op, a, 2, dag, 0, st);
 }

@@ -142,13 +142,6 @@ void launch_transfer(gb_context *ctx, const gb_fermion *f, void *stage, int host
 #undef GB_L
   count_launch(ctx);
 }
-// whole t-slice t <-> a staging buffer holding that slice in host order
-template <int DIR> void slab_transfer(gb_context *ctx, const gb_fermion *f, void *stage, int host_prec, int t, cudaStream_t st) {
-  const gb_grid *g = f->grid;
-  const int64_t v3cb = g->V4cb / g->ldims[3];
-  const int64_t nblk = v3cb * f->Ls / W;
-  launch_transfer<DIR>(ctx, f, stage, host_prec, (int64_t)t * nblk, nblk, (int64_t)t * 2 * v3cb * f->Ls, 1, 0, 0, st);
-}
 } // namespace
 
 // called by gb_context_destroy (context.cu) with the device idle: streams, events and staging buffers of that context's pipe
@@ -193,10 +186,23 @@ extern "C" int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_ou
     op_apply(op, GB_OP_DHOP, fin, fout, dag);
     return gb_fermion_export(fout, host_out, host_prec);
   }
+  // The unit of the pipeline is a z-chunk of a t-slice: (t, c) = planes [c zc, (c+1) zc) of slice t, contiguous in host memory and a
+  // run of whole blocks on the device.  Its hop needs the chunks (t, c-1), (t, c), (t, c+1) (z legs, periodic) and (t-1, c), (t+1, c)
+  // (t legs), so the first result leaves after 1 + 2/k slices have arrived instead of 3, and 2 + 1/k slices are left to export when
+  // the H2D stream runs dry instead of 3.  k = GB_HOST_PIPE_ZCHUNKS, reduced until the chunks are whole blocks.  Default 1 (whole
+  // slices): measured on the B200 at 32^4 x 16, k = 1 / 4 / 8 -> 37.5 / 42.3 / 47.7 ms per call -- with 4 or 8 times as many copies, layout
+  // kernels and stream hand-overs (20 driver calls per unit) the host cannot enqueue the units as fast as PCIe moves them, which costs
+  // more than the shorter ramps save (profiles/r2_host_dhop_zchunks.jsonl).
+  int k = getenv("GB_HOST_PIPE_ZCHUNKS") ? atoi(getenv("GB_HOST_PIPE_ZCHUNKS")) : 1;
+  if (k < 1) k = 1;
+  while (k > 1 && (Lz % k != 0 || (plane_cb * op->Ls * (Lz / k)) % W != 0)) k--;
+  const int zc = Lz / k;
   const size_t hsz = host_prec == GB_F32 ? 4 : 8;
   const size_t slab_bytes = (size_t)2 * v3cb * op->Ls * 24 * hsz;
-  const size_t plane_bytes = slab_bytes / Lz;
-  HostPipe &P = host_pipe(ctx, slab_bytes, z_split ? 2 * (size_t)(Lt - 2) * plane_bytes : 0, Lt);
+  const size_t plane_bytes = slab_bytes / Lz, chunk_bytes = plane_bytes * zc;
+  const int64_t chunk_blocks = plane_cb * op->Ls * zc / W;          // device blocks of a chunk per parity
+  const int64_t chunk_elems = 2 * plane_cb * op->Ls * zc;           // host-order spinors of a chunk
+  HostPipe &P = host_pipe(ctx, chunk_bytes, z_split ? 2 * (size_t)(Lt - 2) * plane_bytes : 0, Lt * k);
   const void *ib[2] = {fin->block(0), fin->block(1)};
   void *ob[2] = {fout->block(0), fout->block(1)};
   // everything previously queued on the compute stream must be done before the copy streams touch the temporaries
@@ -206,41 +212,45 @@ extern "C" int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_ou
   GB_CUDA(cudaStreamWaitEvent(P.xin, P.ev_done, 0));
   GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_done, 0));
   int nin = 0, nout = 0;
-  auto import_slice = [&](int t) {
+  std::vector<char> imported((size_t)Lt * k, 0);   // host-side record: a hop may only wait for events that were recorded in THIS call
+  auto import_unit = [&](int t, int c) {
+    const int u = t * k + c;
     const int b = nin++ % HostPipe::NB;
     GB_CUDA(cudaStreamWaitEvent(P.h2d, P.ev_xin_done[b], 0));          // the layout kernel that last read this staging buffer
-    GB_CUDA(cudaMemcpyAsync(P.stage_in[b], (const char *)host_in + (size_t)t * slab_bytes, slab_bytes, cudaMemcpyHostToDevice, P.h2d));
+    GB_CUDA(cudaMemcpyAsync(P.stage_in[b], (const char *)host_in + (size_t)u * chunk_bytes, chunk_bytes, cudaMemcpyHostToDevice, P.h2d));
     GB_CUDA(cudaEventRecord(P.ev_copied[b], P.h2d));
     GB_CUDA(cudaStreamWaitEvent(P.xin, P.ev_copied[b], 0));
-    slab_transfer<0>(ctx, fin, P.stage_in[b], host_prec, t, P.xin);
-    GB_CUDA(cudaEventRecord(P.ev_in[t], P.xin));
+    launch_transfer<0>(ctx, fin, P.stage_in[b], host_prec, (int64_t)u * chunk_blocks, chunk_blocks, (int64_t)u * chunk_elems, 1, 0, 0, P.xin);
+    GB_CUDA(cudaEventRecord(P.ev_in[u], P.xin));
     GB_CUDA(cudaEventRecord(P.ev_xin_done[b], P.xin));
+    imported[u] = 1;
   };
+  auto import_slice = [&](int t) { for (int c = 0; c < k; c++) import_unit(t, c); };
   const void *halo[8];
   const void *const *halo_arg = nullptr;
-  auto hop_and_export = [&](int t) {
-    // slice t needs input slices t-1, t, t+1 (periodic; on a t-decomposed lattice the legs that leave the rank read the halo instead)
-    const int tm = t == 0 ? Lt - 1 : t - 1, tp = t == Lt - 1 ? 0 : t + 1;
-    GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_in[tm], 0));
-    GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_in[t], 0));
-    GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_in[tp], 0));
-    dhop_tslab(op, ib, ob, dag, t, 1, ctx->stream, halo_arg);
-    GB_CUDA(cudaEventRecord(P.ev_hop[t], ctx->stream));
+  auto hop_and_export = [&](int t, int c) {
+    const int u = t * k + c;
+    const int tm = t == 0 ? Lt - 1 : t - 1, tp = t == Lt - 1 ? 0 : t + 1, cm = c == 0 ? k - 1 : c - 1, cp = c == k - 1 ? 0 : c + 1;
+    // (on a decomposed lattice the legs that leave the rank read the halo instead: the periodic neighbour is a harmless extra wait)
+    for (int need : {tm * k + c, tp * k + c, t * k + cm, u, t * k + cp}) {
+      GB_REQUIRE(imported[need], "host pipeline: a unit is scheduled before its inputs");
+      GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_in[need], 0));
+    }
+    dhop_tslab(op, ib, ob, dag, t, 1, ctx->stream, halo_arg, c * zc, zc);
+    GB_CUDA(cudaEventRecord(P.ev_hop[u], ctx->stream));
     const int b = nout++ % HostPipe::NB;
-    GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_hop[t], 0));
+    GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_hop[u], 0));
     GB_CUDA(cudaStreamWaitEvent(P.xout, P.ev_out_copied[b], 0));       // the D2H copy that last read this staging buffer
-    slab_transfer<1>(ctx, fout, P.stage_out[b], host_prec, t, P.xout);
+    launch_transfer<1>(ctx, fout, P.stage_out[b], host_prec, (int64_t)u * chunk_blocks, chunk_blocks, (int64_t)u * chunk_elems, 1, 0, 0, P.xout);
     GB_CUDA(cudaEventRecord(P.ev_packed[b], P.xout));
     GB_CUDA(cudaStreamWaitEvent(P.d2h, P.ev_packed[b], 0));
-    GB_CUDA(cudaMemcpyAsync((char *)host_out + (size_t)t * slab_bytes, P.stage_out[b], slab_bytes, cudaMemcpyDeviceToHost, P.d2h));
+    GB_CUDA(cudaMemcpyAsync((char *)host_out + (size_t)u * chunk_bytes, P.stage_out[b], chunk_bytes, cudaMemcpyDeviceToHost, P.d2h));
     GB_CUDA(cudaEventRecord(P.ev_out_copied[b], P.d2h));
   };
-  // slice Lt-1 goes in first (slice 0 needs it across the periodic boundary), so that every slice but the last can be finished as
-  // soon as its forward neighbour has arrived and only ONE hop + D2H is left when the H2D stream runs dry
-  import_slice(Lt - 1); import_slice(0);
   if (decomposed) {
-    // the faces the neighbours need are now on their way in (t faces = the two slices above); z faces: planes z = 0 and z = Lz-1 of
-    // the slices 1 ... Lt-2, one strided copy per face (rows = planes, pitch = a slice), then one layout launch per face
+    // the sites the neighbours need go in first: the t faces are the slices 0 and Lt-1; z faces: planes z = 0 and z = Lz-1 of the
+    // slices 1 ... Lt-2, one strided copy per face (rows = planes, pitch = a slice), then one layout launch per face
+    import_slice(Lt - 1); import_slice(0);
     if (z_split) {
       const int np = Lt - 2;
       const int64_t nblk_plane = plane_cb * op->Ls / W;
@@ -266,11 +276,16 @@ extern "C" int gb_op_dhop_host(gb_fermop *op, const void *host_in, void *host_ou
     GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_faces, 0));
     halo_exchange_only(op, fin, dag, halo);                            // project + send the faces, wait for the neighbours' (compute stream)
     halo_arg = halo;
+    for (int c = 0; c < k; c++) { import_unit(1, c); hop_and_export(0, c); }
+  } else {
+    // slice 0 whole (its chunks are each other's z neighbours), then chunk by chunk its two t neighbours
+    import_slice(0);
+    for (int c = 0; c < k; c++) { import_unit(Lt - 1, c); import_unit(1, c); hop_and_export(0, c); }
   }
-  import_slice(1);
-  hop_and_export(0);
-  for (int t = 1; t < Lt - 2; t++) { import_slice(t + 1); hop_and_export(t); }
-  hop_and_export(Lt - 2); hop_and_export(Lt - 1);
+  for (int t = 1; t < Lt - 2; t++)
+    for (int c = 0; c < k; c++) { import_unit(t + 1, c); hop_and_export(t, c); }
+  for (int c = 0; c < k; c++) hop_and_export(Lt - 2, c);
+  for (int c = 0; c < k; c++) hop_and_export(Lt - 1, c);
   GB_CUDA(cudaEventRecord(P.ev_done, P.d2h));
   GB_CUDA(cudaStreamWaitEvent(ctx->stream, P.ev_done, 0));
   GB_CUDA(cudaStreamSynchronize(P.d2h));

@@ -149,7 +149,8 @@ void cg_fused_rest(gb_fermop *op, const gb_fermion *p, gb_fermion *r, const doub
 void host_pipe_release(gb_context *ctx);   // dhop_host.cu: scratch of the host-pipelined Dhop of a context that is being destroyed
 void op_build_recon12(gb_fermop *op);   // dhop.cu: (re)build and check the two-row link store
 size_t halo_exchange_only(gb_fermop *op, const gb_fermion *in, int dag, const void **halo_out = nullptr);   // halo_out[8]: the receive buffers, complete in stream order
-void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo = nullptr);
+void dhop_tslab(gb_fermop *op, const void *const in[2], void *const out[2], int dag, int t0, int nt, cudaStream_t st, const void *const *halo = nullptr,
+                int z0 = 0, int nz = -1);
 // improved staggered operator entry points (stag.cu)
 void stag_op_apply(gb_fermop *op, int which, const gb_fermion *in, gb_fermion *out, int dag);
 // one leg of the hopping term on full-grid fields: point 0..3 forward mu, 4..7 backward mu (force.cu)

@@ -3,6 +3,7 @@
 Tolerances are the north star's: per-site relative error <= 1e-6 (fp32) / <= 1e-13 (fp64) for the hopping term;
 composite fp32 operators (several hops + 5D solves chained) are allowed 4e-6; CG iteration count within +-2 %.
 """
+import os
 import numpy as np
 import pytest
 
@@ -440,3 +441,17 @@ def test_dhop_host_scratch_follows_the_context_lifetime():
         assert site_rel_err(D.Dhop_host(h, np.empty_like(h), 0), ref) < TOL_HOP[gb.F32]
         del D, grid
         c.close()
+
+
+@pytest.mark.parametrize("k", [2, 4])
+def test_dhop_host_z_chunked_units(setup, k):
+    """GB_HOST_PIPE_ZCHUNKS=k: the pipeline's unit is a z-chunk of a t-slice (its hop waits for the chunks (t, c +- 1) and (t +- 1, c));
+    measured slower than whole slices on the B200 (the host cannot enqueue the smaller units fast enough), kept as a switch: same result"""
+    h = setup.host(63, gb.F32)
+    ref = setup.oracle[gb.F64].apply(po.OP_DHOP, h.astype(np.complex128), dag=0)
+    os.environ["GB_HOST_PIPE_ZCHUNKS"] = str(k)
+    try:
+        got = setup.dev[gb.F32].Dhop_host(h, np.empty_like(h), 0)
+    finally:
+        os.environ.pop("GB_HOST_PIPE_ZCHUNKS", None)
+    assert site_rel_err(got, ref) < TOL_HOP[gb.F32]
