@@ -13,6 +13,7 @@ export GB_TEST_MOCK_LIB="$LIB" GB_MOCK_COUNT="dhop_col2_kernel;dhop_col_kernel;d
 python tests/mock/run_counted.py tests/test_next_tuned_shapes.py tests/test_gpu_parity.py -m gpu -q -p no:cacheprovider -x \
   -k "edge_shapes or fast_and_generic or tiling or schur_operator or dhop_full or dhop_oe_eo"
 if [ "$1" = "all" ]; then
-  python tests/mock/run_counted.py tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -p no:cacheprovider -x -k "not dhop_host and not device_random"
+  python tests/mock/run_counted.py tests/test_gpu_parity.py tests/test_golden.py -m gpu -q -p no:cacheprovider -x -k "not device_random"
+  python tests/mock/run_counted.py tests/test_gpu_recon12.py tests/test_gpu_self_halo.py -m gpu -q -p no:cacheprovider -x -k "recon12 or host_dhop or (compressed_halos and zt)"
   python tests/mock/mgpu_on_mock.py "$LIB"
 fi
