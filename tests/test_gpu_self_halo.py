@@ -285,3 +285,61 @@ def test_self_halo_mixed_cg_with_compressed_halo_inner_operator(ctx):
     xm, xd = sol_m.export_lex(), sol_d.export_lex()
     assert mcg.TrueResidual < 1e-7
     assert np.linalg.norm((xm - xd).ravel()) / np.linalg.norm(xd.ravel()) < 1e-6
+
+
+def _proj_upper(psi, mu, sign):
+    """upper two spin components of (1 + sign gamma_mu) psi in the reference's chiral basis (ref: Grid/qcd/spin/TwoSpinor.h:75-133), computed
+    in psi's own precision exactly as the pack kernel does (one add per component)"""
+    f0, f1, f2, f3 = (psi[:, k, :] for k in range(4))
+    i = psi.dtype.type(1j)
+    if mu == 0:
+        return (f0 + i * f3, f1 + i * f2) if sign > 0 else (f0 - i * f3, f1 - i * f2)
+    if mu == 1:
+        return (f0 - f3, f1 + f2) if sign > 0 else (f0 + f3, f1 - f2)
+    if mu == 2:
+        return (f0 + i * f2, f1 - i * f3) if sign > 0 else (f0 - i * f2, f1 + i * f3)
+    return (f0 + f2, f1 + f3) if sign > 0 else (f0 - f2, f1 - f3)
+
+
+def _round_bf16(c64):
+    """round-to-nearest-even of both parts of complex64 values to bf16 (kept in complex64)"""
+    u = np.ascontiguousarray(c64).view(np.uint32)
+    r = ((u + np.uint32(0x7FFF) + ((u >> np.uint32(16)) & np.uint32(1))) >> np.uint32(16)) << np.uint32(16)
+    return r.view(np.complex64).reshape(c64.shape)
+
+
+@pytest.mark.parametrize("mask", ["t", "zt", "xyzt"])
+def test_self_halo_compressed_halos_match_a_model_of_the_compressor(ctx, mask):
+    """Exact statement of what bf16 halos do: a leg that leaves the rank sees the neighbour's PROJECTED half spinor rounded to bf16 (ref:
+    WilsonCompressorTemplate::Compress, WilsonCompressor.h:271-277 -- project, then store in the comms precision), nothing else changes.
+    Model built from the oracle's single legs (DhopDir): since the projection only reads the rounded upper components when the lower ones
+    are zero, the compressed leg equals the oracle's leg applied to psi' = (round(h0), round(h1), 0, 0).  The library must agree with
+    Dhop(psi) + sum over off-rank legs [leg(psi') - leg(psi)] per site to the fp32 tolerance -- surface sites included."""
+    sh = SHAPES["dwf16"]
+    dims, Ls = sh["dims"], sh["Ls"]
+    grid, D, orc = make(ctx, sh, gb.F32, MASKS[mask])
+    src = syn.random_fermion(dims, Ls, seed=47, dtype=np.complex64)
+    src64 = src.astype(np.complex128)
+    model = orc.apply(po.OP_DHOP, src64, dag=0).astype(np.complex128)
+    idx = np.arange(int(np.prod(dims)))
+    coord = []
+    for d in range(4):
+        coord.append(np.repeat(idx % dims[d], Ls)); idx = idx // dims[d]
+    for mu in range(4):
+        if not (MASKS[mask] >> mu) & 1:
+            continue
+        for disp in (+1, -1):
+            sign = -1 if disp > 0 else +1                       # non-dag: forward legs carry (1 - gamma), backward legs (1 + gamma)
+            h0, h1 = _proj_upper(src, mu, sign)
+            psi_c = np.zeros_like(src)
+            psi_c[:, 0, :] = _round_bf16(h0); psi_c[:, 1, :] = _round_bf16(h1)
+            off_rank = coord[mu] == (dims[mu] - 1 if disp > 0 else 0)     # output sites whose (mu, disp) leg leaves the rank
+            delta = orc.dhop_dir(psi_c.astype(np.complex128), mu, disp) - orc.dhop_dir(src64, mu, disp)
+            model[off_rank] += delta[off_rank]
+    fin, fout = gb.LatticeFermion(grid, Ls, gb.F32).import_lex(src), gb.LatticeFermion(grid, Ls, gb.F32)
+    D.set_halo_compression(True)
+    for overlap in (1, 0):
+        D.set_overlap(overlap)
+        D.Dhop(fin, fout, 0)
+        assert site_rel_err(fout.export_lex(), model) < TOL_HOP[gb.F32], (mask, overlap)
+    D.set_halo_compression(False)
