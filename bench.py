@@ -28,7 +28,9 @@ config4    = BASELINE configs[3]: Dhop (+ halo-exchange bandwidth + mixed CG) at
 config5    = BASELINE configs[4]: improved staggered Dhop fp32 at 48^4 (global; split 1.1.2.4 on 8 GPUs).
 At N > 1 the decomposed path is first compared with the CPU oracle on a small global lattice (parity_check): the hop per site (fp32, +-dag,
 tolerance 1e-6) and a Schur conjugate-gradient solve (fp64: iteration count, true residual, solution) -- the driver-side parity of the
-halo exchange and of the reductions summed over ranks.
+halo exchange and of the reductions summed over ranks -- and the host-buffer entry point that `e2e` times (pipelined on z / t splits: faces
+first, one exchange, slices streamed); should that one disagree, `e2e` falls back to import + hop + export (parity_check.host_entry_form)
+and e2e.parity_ok says whether the timed form matched.
 """
 import argparse
 import json
